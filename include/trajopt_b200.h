@@ -1,0 +1,188 @@
+/* trajopt_b200.h -- C ABI of the B200-native batched problem-evaluation hot path of TrajectoryOptimization.jl.
+ *
+ * The reference (/root/reference, v0.7.1) is pure Julia and has no FFI: its "operator API" is the set of
+ * Julia functions a solver (Altro.jl) calls on a `Problem`.  Each entry point below replaces one of those
+ * calls for a BATCH of B independent problem instances that share model / objective / constraints and
+ * differ in x0, X, U, multipliers.  Every function cites the reference interface it stands in for.  The
+ * Julia-side binding (ccall) that a maintainer adds is shown in INTEGRATION.md.
+ *
+ * Conventions
+ *   - all functions return 0 on success or a negative TO_E* code; to_last_error() gives the message
+ *     (the analogue of the reference's DimensionMismatch / ArgumentError exceptions, src/problem.jl:64-68,87-91).
+ *     Nothing throws across the ABI.
+ *   - host arrays are caller-owned, instance-major, Julia column-major within an instance:
+ *       X[B][N][n]  == Julia Array{Float64,3}(n, N, B)        U[B][N-1][m] == Array(m, N-1, B)
+ *       matrices are column-major (Julia), knot ranges and indices are 1-based like the reference.
+ *   - device memory is owned by the library behind the opaque handle; one handle <-> one GPU <-> one stream;
+ *     a handle is not thread-safe.  Multi-GPU = one process/handle per device, batch sharded (no data-path
+ *     collective; the global merit all-reduce runs on to_merit_device_ptr()).
+ *   - there is NO CPU fallback: every compute entry point launches sm_100a kernels or fails.
+ */
+#ifndef TRAJOPT_B200_H
+#define TRAJOPT_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TO_OK 0
+#define TO_EINVAL (-1)   /* invalid argument (ArgumentError) */
+#define TO_EDIM (-2)     /* dimension mismatch (DimensionMismatch, src/problem.jl:64-68, src/constraint_list.jl:108-110) */
+#define TO_ECUDA (-3)    /* CUDA runtime failure */
+#define TO_ENOMEM (-4)
+#define TO_ESTATE (-5)   /* call order violated (e.g. backward pass before expansion) */
+#define TO_ECONE (-6)    /* "Invalid second-order cone projection" (src/cones.jl:91,124) */
+
+/* RobotZoo / example models on the path */
+enum to_model_id {
+    TO_MODEL_DOUBLE_INTEGRATOR = 0, /* examples/quickstart.jl:11-23 ; n = 2*dim, m = dim, params[0] = mass */
+    TO_MODEL_CARTPOLE = 1,          /* docs/src/model.md:14-51 ; params = mc, mp, l, g */
+    TO_MODEL_QUADROTOR = 2,         /* examples/Quadrotor.ipynb cells 4,8 ; params = mass, J1..3, g1..3, motor_dist, kf, km */
+    TO_MODEL_ACROBOT = 3            /* RobotZoo.Acrobot ; params = l1,l2,m1,m2,J1,J2,friction,g */
+};
+
+/* QuadraticCostFunction (src/cost_functions.jl:326-347 DiagonalCost, :417-454 QuadraticCost) */
+enum to_cost_kind { TO_COST_DIAGONAL = 0, TO_COST_QUADRATIC = 1 };
+typedef struct {
+    int32_t kind;     /* to_cost_kind */
+    int32_t terminal; /* `terminal` flag of the cost (LQRObjective sets it on the last cost, src/objective.jl:154,180) */
+    const double* Q;  /* DIAGONAL: n diagonal entries ; QUADRATIC: n*n column-major */
+    const double* R;  /* DIAGONAL: m ; QUADRATIC: m*m column-major */
+    const double* H;  /* QUADRATIC: m*n column-major cross term u'Hx, or NULL (zero) */
+    const double* q;  /* n */
+    const double* r;  /* m */
+    double c;
+} to_cost_spec;
+
+/* ConstraintSense (src/cones.jl:17-61) */
+enum to_cone { TO_CONE_ZERO = 0 /* Equality */, TO_CONE_NEGATIVE_ORTHANT = 1 /* Inequality */, TO_CONE_SECOND_ORDER = 2,
+               TO_CONE_IDENTITY = 3, TO_CONE_POSITIVE_ORTHANT = 4 };
+
+/* AbstractConstraint subtypes (src/constraints.jl) */
+enum to_con_kind {
+    TO_CON_GOAL = 0,   /* GoalConstraint :22-87      a = xf[ninds], inds = 1-based state indices             */
+    TO_CON_BOUND = 1,  /* BoundConstraint :644-783   a = z_max[n+m], b = z_min[n+m] (+-Inf = unbounded)        */
+    TO_CON_LINEAR = 2, /* LinearConstraint :103-150  a = A[p x w] col-major, b = b[p], flag = 0 state | 1 control, sense */
+    TO_CON_CIRCLE = 3, /* CircleConstraint :168-233  a = xc[p], b = yc[p], rad = r[p], inds = {xi, yi} (1-based) */
+    TO_CON_SPHERE = 4, /* SphereConstraint :249-326  a,b,c = centers, rad, inds = {xi, yi, zi}                 */
+    TO_CON_NORM = 5    /* NormConstraint :438-521    val, inds = 1-based indices into z, sense (orthant | SOC)   */
+};
+typedef struct {
+    int32_t kind;        /* to_con_kind */
+    int32_t first, last; /* knot range first:last, 1-based inclusive (add_constraint!, src/constraint_list.jl:103-134) */
+    int32_t sense;       /* to_cone; ignored for GOAL (Equality) and BOUND/CIRCLE/SPHERE (Inequality) */
+    int32_t p;           /* rows for LINEAR / number of obstacles for CIRCLE, SPHERE; ignored otherwise */
+    int32_t flag;
+    int32_t ninds;
+    const int32_t* inds;
+    const double* a;
+    const double* b;
+    const double* c;
+    const double* rad;
+    double val;
+} to_constraint_spec;
+
+/* Problem(model, obj, x0, tf; constraints, ...)  src/problem.jl:79-123 */
+typedef struct {
+    int32_t model;           /* to_model_id */
+    int32_t n, m;            /* state / control dimension (checked against the model, src/problem.jl:64-68) */
+    int32_t N;               /* knot points == length(obj) (src/problem.jl:95) */
+    int32_t B;               /* batch: independent problem instances on this device */
+    int32_t device;          /* CUDA device ordinal */
+    int32_t nparams;
+    const double* params;    /* model parameters, NULL = the model's defaults */
+    const double* dt;        /* N-1 time steps (vector dt allowed, test/problems_tests.jl:79-82) */
+    double t0;
+    int32_t ncost;           /* distinct cost functions */
+    const to_cost_spec* costs;
+    const int32_t* cost_index; /* N entries, 0-based index into costs (Objective.cost, src/objective.jl:27-45) */
+    int32_t ncon;
+    const to_constraint_spec* cons; /* ConstraintList, in add_constraint! order */
+} to_spec;
+
+/* Solver options on the path (Altro.jl SolverOptions, restated in oracle/oracle.hpp `Options`) */
+typedef struct {
+    double bp_reg_increase_factor, bp_reg_max, bp_reg_min, bp_reg_initial, bp_reg_fp;
+    double line_search_lower_bound, line_search_upper_bound;
+    int32_t iterations_linesearch;
+    int32_t reserved;
+    double max_state_value, max_control_value;
+    double penalty_initial, penalty_scaling, penalty_max, dual_max;
+} to_options;
+
+typedef struct to_handle to_handle;
+
+/* ---- lifecycle -------------------------------------------------------------------------------------- */
+int to_create(const to_spec* spec, to_handle** out);                 /* Problem(...)           src/problem.jl:79-111 */
+int to_destroy(to_handle* h);
+const char* to_last_error(const to_handle* h);                       /* h may be NULL: error of the last failed to_create */
+int to_default_options(to_options* o);
+int to_set_options(to_handle* h, const to_options* o);
+int to_set_stream(to_handle* h, void* cuda_stream);                  /* run on the caller's stream (e.g. torch's current stream) */
+int to_synchronize(to_handle* h);
+int to_dims(const to_handle* h, int32_t* n, int32_t* m, int32_t* N, int32_t* B); /* RD.dims(prob)  src/problem.jl:139-147 */
+int to_num_constraints(const to_handle* h, int32_t* p_per_knot /*[N]*/);         /* num_constraints(prob) src/problem.jl:206 */
+int to_constraint_info(const to_handle* h, int32_t con, int32_t* p, int32_t* sense, int32_t* first, int32_t* last);
+int to_bounds(const to_handle* h, int32_t con, double* lower /*[p]*/, double* upper /*[p]*/); /* lower_bound/upper_bound src/abstract_constraint.jl:97-123 */
+
+/* ---- setters / getters (host arrays, instance-major) ------------------------------------------------ */
+int to_set_initial_state(to_handle* h, const double* x0 /*[B][n]*/);          /* set_initial_state! src/problem.jl:270 */
+int to_set_controls(to_handle* h, const double* U /*[B][N-1][m]*/);           /* initial_controls!  src/problem.jl:261 */
+int to_set_states(to_handle* h, const double* X /*[B][N][n]*/);               /* initial_states!    src/problem.jl:253 */
+int to_set_goal_state(to_handle* h, const double* xf /*[n]*/, int objective, int constraint); /* set_goal_state! src/problem.jl:294-310 */
+int to_set_initial_time(to_handle* h, double t0, double* tf_out);             /* setinitialtime!    src/problem.jl:280 */
+int to_get_states(to_handle* h, double* X /*[B][N][n]*/);                     /* states(prob)       src/problem.jl:175 */
+int to_get_controls(to_handle* h, double* U /*[B][N-1][m]*/);                 /* controls(prob)     src/problem.jl:168 */
+int to_get_times(to_handle* h, double* t /*[N]*/);                            /* gettimes(prob)     src/problem.jl:182 */
+
+/* ---- kernel 1: batched RK4 rollout (+ dual-number Jacobians) ---------------------------------------- */
+int to_rollout(to_handle* h);                                                 /* rollout!           src/problem.jl:330-340 */
+int to_expand(to_handle* h);                                                  /* RD.jacobian!(ForwardAD) on the discretized dynamics at every knot */
+int to_get_dynamics_jacobians(to_handle* h, double* AB /*[B][N-1][n+m][n]: n x (n+m) col-major*/);
+
+/* ---- kernel 2: cost + constraint + AL sweep --------------------------------------------------------- */
+int to_cost(to_handle* h, double* J /*[B]*/);                                 /* cost(prob)         src/problem.jl:321, src/objective.jl:89-93 */
+int to_cost_knots(to_handle* h, double* Jk /*[B][N]*/);                       /* cost! / get_J      src/objective.jl:104-110 */
+int to_cost_gradient(to_handle* h, double* grad /*[B][N][n+m]*/);             /* RD.gradient!       src/cost_functions.jl:137-172 */
+int to_cost_hessian(to_handle* h, double* hess /*[B][N][n+m][n+m]*/);         /* RD.hessian!        src/cost_functions.jl:212-233 (written symmetric) */
+int to_eval_constraints(to_handle* h, int32_t con, double* vals /*[B][last-first+1][p]*/);      /* evaluate_constraints! src/abstract_constraint.jl:200-225 */
+int to_constraint_jacobians(to_handle* h, int32_t con, double* jac /*[B][last-first+1][n+m][p]*/); /* constraint_jacobians! src/abstract_constraint.jl:236-248 */
+int to_max_violation(to_handle* h, double* v /*[B]*/);
+int to_merit(to_handle* h, double* J /*[B]*/);                                /* cost + AL penalty of the current trajectory */
+int to_al_expansion(to_handle* h, double* grad /*[B][N][n+m]*/, double* hess /*[B][N][n+m][n+m]*/); /* cost expansion incl. AL terms */
+
+/* cones (stand-alone, batched over `count` vectors of length p)  src/cones.jl */
+int to_projection(to_handle* h, int32_t cone, int32_t p, int32_t count, const double* x, double* px);      /* projection!  :96-127 */
+int to_grad_projection(to_handle* h, int32_t cone, int32_t p, int32_t count, const double* x, double* J);  /* grad-projection! :129-188, p x p col-major each */
+int to_hess_projection(to_handle* h, int32_t cone, int32_t p, int32_t count, const double* x, const double* b, double* H); /* :201-276 */
+
+/* ---- kernel 3 + forward pass (what Altro.jl's iLQR does with the API above) --------------------------- */
+int to_backward(to_handle* h, int32_t* status /*[B] or NULL*/);               /* Riccati backward pass (needs to_expand) */
+int to_forward(to_handle* h, double* J /*[B] or NULL*/, double* alpha /*[B] or NULL*/); /* closed-loop rollout + line search */
+int to_ilqr_step(to_handle* h, int32_t iters);                                /* iters x (expand, backward, forward), no host sync */
+int to_al_update(to_handle* h);                                               /* dual + penalty update */
+int to_get_gains(to_handle* h, double* K /*[B][N-1][n][m]: m x n col-major*/, double* d /*[B][N-1][m]*/);
+int to_get_multipliers(to_handle* h, int32_t con, double* lambda /*[B][last-first+1][p]*/);
+int to_set_multipliers(to_handle* h, int32_t con, const double* lambda);
+int to_get_penalty(to_handle* h, int32_t con, double* mu);
+int to_set_penalty(to_handle* h, int32_t con, double mu);
+int to_get_solver_state(to_handle* h, double* rho /*[B]*/, double* dV /*[B][2]*/, double* alpha /*[B]*/, int32_t* ls_iters /*[B]*/, int32_t* bp_status /*[B]*/);
+
+/* ---- multi-GPU / measurement plumbing --------------------------------------------------------------- */
+/* device pointer to {sum_b J_b, max_b violation_b} (2 doubles) refreshed by to_reduce_merit(); the host
+ * framework all-reduces it (NCCL: sum on [0], max on [1]).  SURVEY 8(e). */
+int to_reduce_merit(to_handle* h);
+int to_merit_device_ptr(to_handle* h, void** ptr);
+/* per-phase device timing (CUDA events on the handle's stream) for the roofline report */
+enum to_phase { TO_PHASE_EXPAND = 0, TO_PHASE_BACKWARD = 1, TO_PHASE_FORWARD = 2, TO_PHASE_LADDER = 3, TO_PHASE_ACCEPT = 4, TO_PHASE_COUNT = 8 };
+int to_set_phase_timing(to_handle* h, int enable);
+int to_get_phase_times(to_handle* h, double* ms /*[TO_PHASE_COUNT] accumulated*/, int64_t* launches /*[TO_PHASE_COUNT]*/, int reset);
+int64_t to_launch_count(const to_handle* h);                                  /* kernels launched by this handle so far */
+int to_algorithmic_bytes(const to_handle* h, int64_t* E, int64_t* R, int64_t* F); /* per instance per iteration, SURVEY 8(d) */
+
+#ifdef __cplusplus
+}
+#endif
+#endif

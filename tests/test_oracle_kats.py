@@ -1,0 +1,404 @@
+"""CPU tests (no GPU): pin the oracle against every closed form / literal KAT the reference's own tests hold
+for the hot path, plus independent checks for the parts whose arithmetic lives in un-vendored
+Julia packages (RK4, dynamics Jacobians, Riccati, line search).  Each test cites the reference test it
+re-expresses.  Tolerance: the reference's `≈` (rtol sqrt(eps) ~ 1.5e-8) unless stated.
+"""
+import numpy as np
+import pytest
+
+import trajopt_b200 as TO
+from oracle_binding import (OracleProblem, oracle_discrete_dynamics, oracle_discrete_jacobian, oracle_dynamics,
+                            oracle_grad_projection, oracle_hess_projection, oracle_projection)
+
+RTOL = 1.5e-8
+
+
+def rng():
+    return np.random.default_rng(1)   # Random.seed!(1), test/runtests.jl:13
+
+
+def psd(r, k):
+    A = r.standard_normal((k, k))
+    return A @ A.T + k * np.eye(k)
+
+
+# ------------------------------------------------------------------------------------------------------------
+# costs: test/cost_tests.jl:229-279
+@pytest.mark.parametrize("kind", ["quadratic", "diagonal"])
+def test_cost_value_gradient_hessian_closed_forms(kind):
+    r = rng()
+    model = TO.Cartpole()
+    n, m = 4, 1
+    if kind == "quadratic":
+        Q, R, H = psd(r, n), psd(r, m), r.standard_normal((m, n))
+        cost = TO.QuadraticCost(Q, R, H=H, q=r.standard_normal(n), r=r.standard_normal(m), c=r.standard_normal())
+    else:
+        Q, R, H = np.diag(r.random(n) + 0.1), np.diag(r.random(m) + 0.1), np.zeros((m, n))
+        cost = TO.DiagonalCost(Q, R, q=r.standard_normal(n), r=r.standard_normal(m), c=r.standard_normal())
+    q, rr, c = cost.q, cost.r, cost.c
+    # knot 1 = stage knot z, knot 2 = terminal knot zterm (dt = 0 => is_terminal, test/cost_tests.jl:235-236)
+    prob = OracleProblem(model, TO.Objective(cost, 2), np.zeros(n), 0.1)
+    x, u = r.random(n), r.random(m)
+    TO.initial_states(prob, np.stack([x, x]))
+    TO.initial_controls(prob, u)
+    Jk = TO.cost_knots(prob)[0]
+    assert np.isclose(Jk[0], 0.5 * (x @ Q @ x + u @ R @ u) + q @ x + rr @ u + c + u @ H @ x, rtol=RTOL)   # :238-241
+    grad = TO.cost_gradient(prob)[0]
+    assert np.allclose(grad[0, :n], Q @ x + q + H.T @ u, rtol=RTOL)        # :249-251
+    assert np.allclose(grad[0, n:], R @ u + rr + H @ x, rtol=RTOL)
+    assert np.allclose(grad[1, :n], Q @ x + q, rtol=RTOL)                  # terminal :245-247
+    assert np.allclose(grad[1, n:], 0.0)
+    hess = TO.cost_hessian(prob)[0]
+    assert np.allclose(hess[1, :n, :n], Q) and np.allclose(hess[1, n:, n:], 0.0)    # :253-256
+    assert np.allclose(hess[0, n:, n:], R) and np.allclose(hess[0, n:, :n], H)      # :257-258
+    assert np.allclose(hess[0, :n, n:], H.T)   # this build writes the symmetric counterpart too
+
+
+# test/objective_tests.jl:86-96: LQRObjective parameters (host logic)
+def test_lqr_objective_parameters():
+    r = rng()
+    n, m, N = 4, 1, 11
+    Q, R, Qf = np.diag(r.random(n)), np.diag(r.random(m)), np.diag(r.random(n))
+    xf = r.random(n)
+    obj = TO.LQRObjective(Q, R, Qf, xf, N)
+    assert len(obj) == N and isinstance(obj[0], TO.DiagonalCost)
+    assert np.allclose(obj[0].Q, Q) and np.allclose(obj[0].q, -Q @ xf)
+    assert np.allclose(obj[1].r, 0.0)
+    assert np.isclose(obj[1].c, 0.5 * xf @ Q @ xf)
+    assert np.isclose(obj[-1].c, 0.5 * xf @ Qf @ xf)
+    assert np.allclose(obj[-1].q, -Qf @ xf) and np.allclose(obj[-1].Q, Qf) and np.allclose(obj[-1].R, R)
+    obj2 = TO.LQRObjective(Q + 0.01 * np.ones((n, n)), R, Qf, xf, N)     # dense Q -> QuadraticCost (:98-99)
+    assert isinstance(obj2[0], TO.QuadraticCost)
+
+
+# test/objective_tests.jl:124-140: trajectory cost, N = 101, explicit (u - uref) LQR sum
+def test_trajectory_cost_closed_form():
+    r = rng()
+    n, m, N = 4, 1, 101
+    Q, R, Qf = np.diag(r.random(n)), np.diag(r.random(m)), np.diag(r.random(n))
+    xf, uref = r.random(n), r.random(m)
+    obj = TO.LQRObjective(Q, R, Qf, xf, N, uf=uref)
+    prob = OracleProblem(TO.Cartpole(), obj, np.zeros(n), 1.0)
+    X, U = r.random((N, n)), r.random((N - 1, m))
+    TO.initial_states(prob, X)
+    TO.initial_controls(prob, U)
+    J = sum(0.5 * (X[k] - xf) @ Q @ (X[k] - xf) + 0.5 * (U[k] - uref) @ R @ (U[k] - uref) for k in range(N - 1))
+    J += 0.5 * (X[-1] - xf) @ Qf @ (X[-1] - xf) + 0.5 * uref @ R @ uref   # terminal control = 0 keeps R, r (src/objective.jl:154,180)
+    # the reference's terminal cost omits the constant 1/2 uf'R uf (cf = 1/2 xf'Qf xf) and evaluates u_N = 0:
+    J -= 0.5 * uref @ R @ uref
+    assert np.isclose(TO.cost(prob)[0], J, rtol=RTOL)
+    assert np.isclose(TO.cost_knots(prob)[0].sum(), J, rtol=RTOL)
+
+
+# ------------------------------------------------------------------------------------------------------------
+# constraints: test/constraint_tests.jl
+def _cartpole_problem(cons_builder, N=5):
+    n, m = 4, 1
+    obj = TO.LQRObjective(np.eye(n), np.eye(m), np.eye(n), np.zeros(n), N)
+    cons = TO.ConstraintList(n, m, N)
+    cons_builder(cons, n, m, N)
+    return OracleProblem(TO.Cartpole(), obj, np.zeros(n), 1.0, constraints=cons)
+
+
+def test_goal_constraint():   # :17-39
+    r = rng()
+    xf = r.random(4)
+    goal = TO.GoalConstraint(xf)
+    prob = _cartpole_problem(lambda c, n, m, N: TO.add_constraint(c, goal, N))
+    X = r.random((5, 4))
+    TO.initial_states(prob, X)
+    assert np.allclose(TO.evaluate_constraints(prob, goal)[0, 0], X[-1] - xf)
+    assert np.allclose(TO.constraint_jacobians(prob, goal)[0, 0], np.hstack([np.eye(4), np.zeros((4, 1))]))
+    assert TO.output_dim(goal) == 4 and TO.is_bound(goal)
+    assert np.allclose(TO.upper_bound(goal), 0) and np.allclose(TO.lower_bound(goal), 0)
+    assert TO.sense(goal) == TO.Equality()
+    part = TO.GoalConstraint(xf, inds=[1, 3])   # src/constraints.jl:27-29
+    prob2 = _cartpole_problem(lambda c, n, m, N: TO.add_constraint(c, part, N))
+    TO.initial_states(prob2, X)
+    assert np.allclose(TO.evaluate_constraints(prob2, part)[0, 0], X[-1, [0, 2]] - xf[[0, 2]])
+
+
+def test_bound_constraint():   # :209-266
+    r = rng()
+    n, m = 4, 1
+    xmin, xmax, umin, umax = -r.random(n), r.random(n), -r.random(m), r.random(m)
+    bnd = TO.BoundConstraint(n, m, x_min=xmin, x_max=xmax, u_min=umin, u_max=umax)
+    prob = _cartpole_problem(lambda c, n_, m_, N: TO.add_constraint(c, bnd, (1, N - 1)))
+    X, U = r.random((5, n)), r.random((4, m))
+    TO.initial_states(prob, X); TO.initial_controls(prob, U)
+    x, u = X[0], U[0]
+    assert np.allclose(TO.evaluate_constraints(prob, bnd)[0, 0], np.concatenate([x - xmax, u - umax, xmin - x, umin - u]))   # :217
+    assert np.allclose(TO.constraint_jacobians(prob, bnd)[0, 0], np.vstack([np.eye(n + m), -np.eye(n + m)]))                # :221
+    assert TO.output_dim(bnd) == 2 * (n + m)
+    assert np.array_equal(TO.upper_bound(bnd), np.concatenate([xmax, umax])) and np.array_equal(TO.lower_bound(bnd), np.concatenate([xmin, umin]))
+    # +-Inf pruning :228-245
+    xmin2 = xmin.copy(); xmin2[0] = -np.inf
+    umax2 = np.array([np.inf])
+    bnd2 = TO.BoundConstraint(n, m, x_min=xmin2, x_max=xmax, u_min=umin, u_max=umax2)
+    prob2 = _cartpole_problem(lambda c, n_, m_, N: TO.add_constraint(c, bnd2, (1, N - 1)))
+    TO.initial_states(prob2, X); TO.initial_controls(prob2, U)
+    assert TO.output_dim(bnd2) == 2 * (n + m) - 2
+    assert np.allclose(TO.evaluate_constraints(prob2, bnd2)[0, 0], np.concatenate([x - xmax, xmin[1:] - x[1:], umin - u]))
+    iz = np.ones(2 * (n + m), dtype=bool); iz[n] = False; iz[n + m] = False
+    assert np.allclose(TO.constraint_jacobians(prob2, bnd2)[0, 0], np.vstack([np.eye(n + m), -np.eye(n + m)])[iz])
+    with pytest.raises(TO.ArgumentError):   # :265
+        TO.BoundConstraint(n, m, x_min=10, x_max=-10, u_min=umin, u_max=umax)
+
+
+def test_state_and_control_bound_integer_kats():
+    """StateBound / ControlBound literal KATs (test/constraint_tests.jl:280,292,302,319,331,341), expressed through
+    BoundConstraint on the quadrotor dims with every other entry unbounded."""
+    n, m, N = 13, 4, 3
+    obj = TO.LQRObjective(np.eye(n), np.eye(m), np.eye(n), np.zeros(n), N)
+
+    def run(bnd, x3=None, u3=None):
+        cons = TO.ConstraintList(n, m, N)
+        TO.add_constraint(cons, bnd, (1, N - 1))
+        prob = OracleProblem(TO.Quadrotor(), obj, np.zeros(n), 1.0, constraints=cons)
+        X, U = np.zeros((N, n)), np.zeros((N - 1, m))
+        if x3 is not None: X[:, :3] = x3
+        if u3 is not None: U[:, :3] = u3
+        TO.initial_states(prob, X); TO.initial_controls(prob, U)
+        return TO.evaluate_constraints(prob, bnd)[0, 0], TO.constraint_jacobians(prob, bnd)[0, 0]
+
+    inf = np.inf
+    xm = lambda a: np.concatenate([a, np.full(10, inf)])
+    xn = lambda a: np.concatenate([a, np.full(10, -inf)])
+    c, J = run(TO.BoundConstraint(n, m, x_max=xm([10, 2, 5.]), x_min=xn([0, -3, -4.])), x3=[0, 1, 2.])
+    assert np.array_equal(c, [-10, -1, -3, 0, -4, -6])                                          # :280
+    assert np.array_equal(J[:, :3], np.vstack([np.eye(3), -np.eye(3)])) and not J[:, 3:].any()   # :282-285
+    c, _ = run(TO.BoundConstraint(n, m, x_max=xm([10, 2, 5.]), x_min=xn([-inf, -3, -4.])), x3=[0, 1, 2.])
+    assert np.array_equal(c, [-10, -1, -3, -4, -6])                                             # :292
+    c, _ = run(TO.BoundConstraint(n, m, x_max=xm([10, 10, 10.])), x3=[0, 1, 2.])
+    assert np.array_equal(c, [-10, -9, -8])                                                     # :302
+    um = lambda a: np.concatenate([a, [inf]])
+    un = lambda a: np.concatenate([a, [-inf]])
+    c, _ = run(TO.BoundConstraint(n, m, u_max=um([10, 2, 5.]), u_min=un([0, -3, -4.])), u3=[0, 1, 2.])
+    assert np.array_equal(c, [-10, -1, -3, 0, -4, -6])                                          # :319
+    c, _ = run(TO.BoundConstraint(n, m, u_max=um([10, 2, 5.]), u_min=un([-inf, -3, -4.])), u3=[0, 1, 2.])
+    assert np.array_equal(c, [-10, -1, -3, -4, -6])                                             # :331
+    c, _ = run(TO.BoundConstraint(n, m, u_max=um([10, 10, 10.])), u3=[0, 1, 2.])
+    assert np.array_equal(c, [-10, -9, -8])                                                     # :341
+
+
+def test_circle_sphere_norm_linear_closed_forms():   # :43-205
+    r = rng()
+    n, m, N = 13, 4, 3
+    obj = TO.LQRObjective(np.eye(n), np.eye(m), np.eye(n), np.zeros(n), N)
+    xc, yc, zc, rad = r.random(3), r.random(3), r.random(3), r.random(3)
+    circ = TO.CircleConstraint(n, xc, yc, rad)
+    sph = TO.SphereConstraint(n, xc, yc, zc, rad)
+    A, b = r.standard_normal((5, m)), r.standard_normal(5)
+    lin = TO.LinearConstraint(n, m, A, b, TO.Inequality(), "control")
+    nrm = TO.NormConstraint(n, m, 2.0, TO.SecondOrderCone(), "control")
+    nrm2 = TO.NormConstraint(n, m, 3.0, TO.Inequality(), [1, 2, 3])
+    cons = TO.ConstraintList(n, m, N)
+    for c in (circ, sph, lin, nrm, nrm2):
+        TO.add_constraint(cons, c, (1, N - 1))
+    prob = OracleProblem(TO.Quadrotor(), obj, np.zeros(n), 1.0, constraints=cons)
+    X, U = r.random((N, n)), r.random((N - 1, m))
+    TO.initial_states(prob, X); TO.initial_controls(prob, U)
+    x, u = X[0], U[0]
+    assert np.allclose(TO.evaluate_constraints(prob, circ)[0, 0], -(x[0] - xc) ** 2 - (x[1] - yc) ** 2 + rad ** 2)      # :107-109
+    Jc = TO.constraint_jacobians(prob, circ)[0, 0]
+    assert np.allclose(Jc[:, 0], -2 * (x[0] - xc)) and np.allclose(Jc[:, 1], -2 * (x[1] - yc)) and not Jc[:, 2:].any()
+    assert np.allclose(TO.evaluate_constraints(prob, sph)[0, 0], -(x[0] - xc) ** 2 - (x[1] - yc) ** 2 - (x[2] - zc) ** 2 + rad ** 2)
+    assert np.allclose(TO.evaluate_constraints(prob, lin)[0, 0], A @ u - b)                                                   # :60-66
+    assert np.allclose(TO.constraint_jacobians(prob, lin)[0, 0], np.hstack([np.zeros((5, n)), A]))
+    assert np.allclose(TO.evaluate_constraints(prob, nrm)[0, 0], np.concatenate([u, [2.0]]))                                  # :187-188
+    assert np.allclose(TO.evaluate_constraints(prob, nrm2)[0, 0], [x[:3] @ x[:3] - 9.0])                                     # :180
+    Jn = TO.constraint_jacobians(prob, nrm2)[0, 0]
+    assert np.allclose(Jn[0, :3], 2 * x[:3]) and not Jn[0, 3:].any()
+    assert np.array_equal(TO.num_constraints(prob), [3 + 3 + 5 + 5 + 1] * 2 + [0])
+
+
+# ------------------------------------------------------------------------------------------------------------
+# cones: test/cone_tests.jl:8-75, reference closed forms test/socp.jl:6-50
+def Pi_soc(x):
+    v, s = x[:-1], x[-1]
+    a = np.linalg.norm(v)
+    if a <= -s: return np.zeros_like(x)
+    if a <= s: return x.copy()
+    return 0.5 * (1 + s / a) * np.concatenate([v, [a]])
+
+
+def numjac(f, x, h=1e-6):
+    J = np.zeros((f(x).size, x.size))
+    for i in range(x.size):
+        e = np.zeros_like(x); e[i] = h
+        J[:, i] = (f(x + e) - f(x - e)) / (2 * h)
+    return J
+
+
+@pytest.mark.parametrize("x", [[2, 3, 1, 1.0], [2, 3, 1, -10.0], [2, 3, 1, 10.0]])   # :51,58,64 (outside / below / in)
+def test_soc_projection_and_derivatives(x):
+    x = np.array(x)
+    b = rng().standard_normal(4)
+    cone = TO.SecondOrderCone()
+    px, rc = oracle_projection(cone, x)
+    assert rc == 0 and np.allclose(px[0], Pi_soc(x), rtol=RTOL)
+    J, _ = oracle_grad_projection(cone, x)
+    assert np.allclose(J[0], numjac(Pi_soc, x), atol=1e-6)                             # J ~ ForwardDiff.jacobian(Pi, x) :39
+    H, _ = oracle_hess_projection(cone, x, b)
+    assert np.allclose(H[0], numjac(lambda y: numjac(Pi_soc, y, 1e-5).T @ b, x, 1e-4), atol=1e-4)   # :40
+
+
+def test_orthant_projection_and_derivatives():   # :70-75
+    x = np.array([1, 2, -3.0])
+    cone = TO.Inequality()
+    px, _ = oracle_projection(cone, x)
+    assert np.array_equal(px[0], np.minimum(0, x))
+    J, _ = oracle_grad_projection(cone, x)
+    assert np.array_equal(J[0], np.diag([0, 0, 1.0]))
+    H, _ = oracle_hess_projection(cone, x, np.ones(3))
+    assert not H.any()
+    pz, _ = oracle_projection(TO.ZeroCone(), x)
+    assert not pz.any()
+    assert TO.dualcone(TO.ZeroCone()) == TO.IdentityCone() and TO.dualcone(TO.Inequality()) == TO.Inequality()   # src/cones.jl:65-69
+
+
+# ------------------------------------------------------------------------------------------------------------
+# examples/quickstart.jl (the reference's end-to-end API tour with @tests)
+def test_quickstart():
+    r = rng()
+    model = TO.DoubleIntegrator(2)
+    n, m = model.dims()
+    tf, N = 3.0, 21
+    dt = tf / (N - 1)
+    assert (n, m) == (4, 2)                                                                   # :32
+    x0, xf = np.zeros(4), np.array([0, 2.0, 0, 0])
+    Q, R = np.eye(n), np.eye(m)
+    Qf = Q * (N - 1)
+    obj = TO.LQRObjective(Q, R, Qf, xf, N)
+    cons = TO.ConstraintList(n, m, N)
+    TO.add_constraint(cons, TO.GoalConstraint(xf), N)                                          # :53-56
+    TO.add_constraint(cons, TO.CircleConstraint(n, [0.0], [1.0], [0.5]), (2, N - 1))
+    TO.add_constraint(cons, TO.NormConstraint(n, m, 5.0, TO.SecondOrderCone(), "control"), (1, N - 1))
+    TO.add_constraint(cons, TO.BoundConstraint(n, m, u_min=-10, u_max=10), (1, N - 1))
+    prob = OracleProblem(model, obj, x0, tf, xf=xf, constraints=cons)
+    U0 = r.standard_normal((N - 1, m))
+    TO.initial_controls(prob, U0)
+    X0 = np.zeros((N, n))
+    TO.initial_states(prob, X0)
+    J = sum(0.5 * (X0[k] - xf) @ Q @ (X0[k] - xf) + 0.5 * U0[k] @ R @ U0[k] for k in range(N - 1)) + 0.5 * (X0[-1] - xf) @ Qf @ (X0[-1] - xf)
+    assert np.isclose(TO.cost(prob)[0], J, rtol=RTOL)                                          # :71-80
+    TO.rollout(prob)
+    # hand-rolled RK4 of the (linear) double integrator: x+ = x + dt*[v; u] + dt^2/2*[u; 0]
+    Xr = np.zeros((N, n))
+    for k in range(N - 1):
+        x, u = Xr[k], U0[k]
+        Xr[k + 1] = np.concatenate([x[:2] + dt * x[2:] + 0.5 * dt * dt * u, x[2:] + dt * u])
+    assert np.allclose(TO.states(prob)[0], Xr, rtol=RTOL, atol=1e-12)                          # :83-96
+    assert np.allclose(TO.gettimes(prob), np.arange(N) * dt)
+    assert [TO.sense(c) for c in cons] == [TO.ZeroCone(), TO.NegativeOrthant(), TO.SecondOrderCone(), TO.NegativeOrthant()]   # :121-122
+    assert [TO.is_bound(c) for c in cons] == [True, False, False, True]                        # :128-129
+    lower = np.concatenate([TO.lower_bound(c) for c in cons])
+    upper = np.concatenate([TO.upper_bound(c) for c in cons])
+    assert np.allclose(lower, np.concatenate([np.zeros(n), [-np.inf], np.full(m + 1, -np.inf), np.full(n, -np.inf), np.full(m, -10)]))   # :134
+    assert np.allclose(upper, np.concatenate([np.zeros(n), [0.0], np.full(m + 1, np.inf), np.full(n, np.inf), np.full(m, 10)]))          # :135
+    # trajectory-level sweeps :169-197
+    vals = TO.evaluate_constraints(prob, 0)
+    assert vals.shape == (1, 1, n) and np.allclose(vals[0, 0], Xr[-1] - xf)
+    nv = TO.evaluate_constraints(prob, 2)
+    assert nv.shape == (1, N - 1, m + 1) and np.allclose(nv[0, :, :m], U0) and np.allclose(nv[0, :, m], 5.0)
+    jac = TO.constraint_jacobians(prob, 2)
+    assert np.allclose(jac[0, 3], np.vstack([np.hstack([np.zeros((m, n)), np.eye(m)]), np.zeros((1, n + m))]))
+    assert np.array_equal(TO.num_constraints(prob), [m + 1 + 2 * m] + [1 + m + 1 + 2 * m] * (N - 2) + [n])
+
+
+# ------------------------------------------------------------------------------------------------------------
+# dynamics / RK4 / Jacobians (parity unpinned in the reference -> independent checks)
+def cartpole_numpy(x, u, mc=1.0, mp=0.2, l=0.5, g=9.81):   # docs/src/model.md:32-51 with numpy linear algebra
+    q, qd = x[:2], x[2:]
+    s, c = np.sin(q[1]), np.cos(q[1])
+    H = np.array([[mc + mp, mp * l * c], [mp * l * c, mp * l ** 2]])
+    Cm = np.array([[0, -mp * qd[1] * l * s], [0, 0]])
+    G = np.array([0, mp * g * l * s])
+    Bv = np.array([1.0, 0])
+    qdd = -np.linalg.solve(H, Cm @ qd + G - Bv * u[0])
+    return np.concatenate([qd, qdd])
+
+
+def rk4_numpy(f, x, u, h):
+    k1 = f(x, u) * h; k2 = f(x + k1 / 2, u) * h; k3 = f(x + k2 / 2, u) * h; k4 = f(x + k3, u) * h
+    return x + (k1 + 2 * k2 + 2 * k3 + k4) / 6
+
+
+def test_cartpole_dynamics_and_rk4_vs_numpy():
+    r = rng()
+    for _ in range(5):
+        x, u = r.standard_normal(4), r.standard_normal(1)
+        assert np.allclose(oracle_dynamics(TO.Cartpole(), x, u), cartpole_numpy(x, u), rtol=1e-12)
+        assert np.allclose(oracle_discrete_dynamics(TO.Cartpole(), x, u, 0.05), rk4_numpy(cartpole_numpy, x, u, 0.05), rtol=1e-12)
+
+
+def test_rk4_order_against_scipy():
+    from scipy.integrate import solve_ivp
+    x, u = np.array([0.1, 0.5, -0.2, 0.3]), np.array([0.7])
+    ref = solve_ivp(lambda t, y: cartpole_numpy(y, u), (0, 0.02), x, rtol=1e-13, atol=1e-15, method="DOP853").y[:, -1]
+    e1 = np.abs(oracle_discrete_dynamics(TO.Cartpole(), x, u, 0.02) - ref).max()
+    half = oracle_discrete_dynamics(TO.Cartpole(), oracle_discrete_dynamics(TO.Cartpole(), x, u, 0.01), u, 0.01)
+    e2 = np.abs(half - ref).max()
+    assert e1 < 1e-6 and 8 < e1 / e2 < 40   # 4th-order: halving h cuts the error ~16x
+
+
+def quadrotor_numpy(x, u, mass=0.5, J=np.diag([0.0023, 0.0023, 0.004]), g=np.array([0, 0, -9.81]), L=0.175, kf=1.0, km=0.0245):
+    """examples/Quadrotor.ipynb cells 4,8 + rigid-body equations, written with rotation matrices (independent of
+    the oracle's quaternion-product form)."""
+    q, v, w = x[3:7], x[7:10], x[10:13]
+    qw, qv = q[0], q[1:]
+    F = np.maximum(0, kf * u)
+    Fb = np.array([0, 0, F.sum()])
+    skew = lambda a: np.array([[0, -a[2], a[1]], [a[2], 0, -a[0]], [-a[1], a[0], 0]])
+    Rm = (qw * qw - qv @ qv) * np.eye(3) + 2 * np.outer(qv, qv) + 2 * qw * skew(qv)   # rotation (scaled if |q| != 1)
+    Fw = mass * g + Rm @ Fb
+    M = km * u
+    tau = np.array([L * (F[1] - F[3]), L * (F[2] - F[0]), M[0] - M[1] + M[2] - M[3]])
+    qdot = 0.5 * np.concatenate([[-qv @ w], qw * w + np.cross(qv, w)])
+    return np.concatenate([v, qdot, Fw / mass, np.linalg.solve(J, tau - np.cross(w, J @ w))])
+
+
+def test_quadrotor_dynamics_vs_numpy_and_hover():
+    r = rng()
+    model = TO.Quadrotor()
+    for _ in range(5):
+        x, u = r.standard_normal(13), r.random(4) * 3
+        assert np.allclose(oracle_dynamics(model, x, u), quadrotor_numpy(x, u), rtol=1e-11, atol=1e-12)
+    x0 = np.array([1, 2, 1, 1, 0, 0, 0, 0, 0, 0, 0, 0, 0.0])
+    assert np.allclose(oracle_dynamics(model, x0, model.hover_control()), 0.0, atol=1e-14)
+
+
+def test_hover_rollout_stays_at_x0():   # test/internal_api.jl:50-56 (N = 51, tf = 5)
+    model = TO.Quadrotor()
+    n, m, N = 13, 4, 51
+    x0 = np.array([1, 2, 1, 1, 0, 0, 0, 0, 0, 0, 0, 0, 0.0])
+    xf = np.array([0, 0, 2, 1, 0, 0, 0, 0, 0, 0, 0, 0, 0.0])
+    obj = TO.LQRObjective(np.full(n, 0.1), np.full(m, 0.01), np.full(n, 100.0), xf, N)
+    prob = OracleProblem(model, obj, x0, 5.0, xf=xf)
+    assert np.isnan(TO.states(prob)).all()                                   # X0 = NaN before rollout (test/problems_tests.jl:209)
+    TO.initial_controls(prob, model.hover_control())
+    TO.rollout(prob)
+    X = TO.states(prob)[0]
+    assert np.array_equal(X[0], x0) and np.allclose(X[-1], x0, rtol=RTOL)    # :51-52
+
+
+@pytest.mark.parametrize("model", [TO.Cartpole(), TO.Quadrotor(), TO.Acrobot(), TO.DoubleIntegrator(2), TO.DoubleIntegrator(1)])
+def test_discrete_jacobian_vs_central_differences(model):   # stale test/dynamics_constraints.jl:57-71 (AD vs FD at 1e-6)
+    r = rng()
+    n, m = model.dims()
+    x, u = r.standard_normal(n) * 0.5, r.random(m) + 0.5
+    AB = oracle_discrete_jacobian(model, x, u, 0.05)
+    f = lambda z: oracle_discrete_dynamics(model, z[:n], z[n:], 0.05)
+    assert AB.shape == (n, n + m)
+    assert np.allclose(AB, numjac(f, np.concatenate([x, u]), 1e-6), atol=1e-6)
+
+
+def test_relu_tie_convention():
+    """max(0, kf*w) at w == 0: derivative 0 (the constant wins the tie), SURVEY.md section 7."""
+    model = TO.Quadrotor()
+    x = np.array([0, 0, 0, 1, 0, 0, 0, 0, 0, 0, 0, 0, 0.0])
+    AB = oracle_discrete_jacobian(model, x, np.zeros(4), 0.05)
+    # thrust derivative vanishes at w = 0, the motor-torque (km*w) derivative of the yaw rate does not
+    assert np.allclose(AB[7:10, 13:], 0.0) and np.allclose(AB[10:12, 13:], 0.0) and np.all(np.abs(AB[12, 13:]) > 0)
+    ABp = oracle_discrete_jacobian(model, x, np.full(4, 1e-9), 0.05)
+    assert np.all(ABp[9, 13:] > 0)

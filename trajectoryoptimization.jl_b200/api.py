@@ -1,0 +1,805 @@
+"""Host-side mirror of the TrajectoryOptimization.jl problem-definition API for the batched B200 hot path.
+
+Same names, argument meaning and error behaviour as the reference's Julia functions (minus the ``!``), so a
+user -- or a parity test -- reads like the reference's own code (examples/quickstart.jl).  A ``Problem`` here
+is a BATCH of ``B`` independent instances that share model / objective / constraints and differ in ``x0``,
+states, controls and multipliers; every numerical call goes through the C ABI (``_capi``) to the sm_100a
+kernels.  Nothing in this file computes on the host.
+
+Array conventions: numpy row-major with the batch first -- ``X[B, N, n]``, ``U[B, N-1, m]`` -- which is the
+same memory as Julia's ``Array{Float64,3}(n, N, B)``.  Knot indices given to ``add_constraint`` are 1-based
+inclusive ranges exactly like the reference (``add_constraint!(cons, con, 1:N-1)`` -> ``(1, N-1)``).
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _capi as K
+from ._capi import ArgumentError, DimensionMismatch, TrajOptError  # noqa: F401  (re-exported)
+
+# ------------------------------------------------------------------------------------------------------------
+# Cones / constraint senses (reference src/cones.jl:17-69)
+
+
+class ConstraintSense:
+    code = None
+
+    def __eq__(self, other):
+        return type(self) is type(other)
+
+    def __hash__(self):
+        return hash(type(self).__name__)
+
+    def __repr__(self):
+        return type(self).__name__ + "()"
+
+
+class ZeroCone(ConstraintSense):
+    code = K.CONE_ZERO
+
+
+class NegativeOrthant(ConstraintSense):
+    code = K.CONE_NEGATIVE_ORTHANT
+
+
+class SecondOrderCone(ConstraintSense):
+    code = K.CONE_SECOND_ORDER
+
+
+class IdentityCone(ConstraintSense):
+    code = K.CONE_IDENTITY
+
+
+class PositiveOrthant(ConstraintSense):
+    code = K.CONE_POSITIVE_ORTHANT
+
+
+Equality = ZeroCone
+Inequality = NegativeOrthant
+_CONES = {c.code: c for c in (ZeroCone, NegativeOrthant, SecondOrderCone, IdentityCone, PositiveOrthant)}
+
+
+def dualcone(cone):   # src/cones.jl:65-69
+    return {IdentityCone: ZeroCone, ZeroCone: IdentityCone}.get(type(cone), type(cone))()
+
+
+_util = None
+
+
+def _util_handle():
+    """A tiny resident problem whose handle serves the stand-alone cone operators."""
+    global _util
+    if _util is None:
+        obj = LQRObjective(np.eye(2), np.eye(1), np.eye(2), np.zeros(2), 2)
+        _util = Problem(DoubleIntegrator(1), obj, np.zeros(2), 1.0)
+    return _util
+
+
+def _cone_op(which, cone, x, b=None):
+    x = np.ascontiguousarray(np.asarray(x, dtype=np.float64))
+    single = x.ndim == 1
+    xs = x.reshape(1, -1) if single else x
+    count, p = xs.shape
+    prob = _util_handle()
+    lib = prob._lib
+    if which == 0:
+        out = np.empty((count, p))
+        rc = lib.to_projection(prob._h, cone.code, p, count, K._dp(xs), K._dp(out))
+    elif which == 1:
+        out = np.empty((count, p, p))
+        rc = lib.to_grad_projection(prob._h, cone.code, p, count, K._dp(xs), K._dp(out))
+    else:
+        bb = np.ascontiguousarray(np.asarray(b, dtype=np.float64)).reshape(count, p)
+        out = np.empty((count, p, p))
+        rc = lib.to_hess_projection(prob._h, cone.code, p, count, K._dp(xs), K._dp(bb), K._dp(out))
+    K.check(lib, prob._h, rc)
+    if which > 0:
+        out = np.swapaxes(out, -1, -2)   # column-major p x p -> numpy
+    return out[0] if single else out
+
+
+def projection(cone, x):
+    """``projection!(cone, px, x)`` (src/cones.jl:96-127) for one vector or a batch ``[count, p]``."""
+    return _cone_op(0, cone, x)
+
+
+def grad_projection(cone, x):
+    """``∇projection!(cone, J, x)`` (src/cones.jl:129-188)."""
+    return _cone_op(1, cone, x)
+
+
+def hess_projection(cone, x, b):
+    """``∇²projection!(cone, hess, x, b)`` (src/cones.jl:201-276): Hessian of ``x -> Π(x)'b``."""
+    return _cone_op(2, cone, x, b)
+
+
+# ------------------------------------------------------------------------------------------------------------
+# Models (RobotZoo / example models; reference docs/src/model.md, examples/Quadrotor.ipynb, examples/quickstart.jl)
+
+
+class _Model:
+    model_id = None
+    n = m = None
+    params = None
+
+    def dims(self):
+        return self.n, self.m
+
+
+class DoubleIntegrator(_Model):
+    model_id = K.MODEL_DOUBLE_INTEGRATOR
+
+    def __init__(self, dim=1, mass=1.0):
+        self.n, self.m, self.params = 2 * dim, dim, [float(mass)]
+
+
+class Cartpole(_Model):
+    model_id = K.MODEL_CARTPOLE
+    n, m = 4, 1
+
+    def __init__(self, mc=1.0, mp=0.2, l=0.5, g=9.81):
+        self.params = [mc, mp, l, g]
+
+
+class Quadrotor(_Model):
+    model_id = K.MODEL_QUADROTOR
+    n, m = 13, 4
+
+    def __init__(self, mass=0.5, J=(0.0023, 0.0023, 0.004), gravity=(0.0, 0.0, -9.81), motor_dist=0.1750, kf=1.0, km=0.0245):
+        self.params = [mass, *J, *gravity, motor_dist, kf, km]
+        self.mass, self.gravity = mass, gravity
+
+    def hover_control(self):
+        """zeros(model)[2] of RobotZoo.Quadrotor: thrust that cancels gravity (test/internal_api.jl:37)."""
+        return np.full(4, -self.gravity[2] * self.mass / 4.0)
+
+
+class Acrobot(_Model):
+    model_id = K.MODEL_ACROBOT
+    n, m = 4, 1
+
+    def __init__(self, l=(1.0, 1.0), m=(1.0, 1.0), J=None, friction=1.0, g=9.81):
+        J = J or (m[0] * l[0] ** 2 / 12.0, m[1] * l[1] ** 2 / 12.0)
+        self.params = [l[0], l[1], m[0], m[1], J[0], J[1], friction, g]
+
+
+# ------------------------------------------------------------------------------------------------------------
+# Cost functions (reference src/cost_functions.jl)
+
+
+def _isdiag(A):
+    A = np.asarray(A, dtype=float)
+    return A.ndim == 1 or np.count_nonzero(A - np.diag(np.diagonal(A))) == 0
+
+
+class QuadraticCostFunction:
+    """``1/2 x'Qx + 1/2 u'Ru + u'Hx + q'x + r'u + c`` (src/cost_functions.jl:30-58)."""
+    is_diag = False
+
+    def __init__(self, Q, R, H=None, q=None, r=None, c=0.0, terminal=False):
+        Q, R = np.asarray(Q, dtype=float), np.asarray(R, dtype=float)
+        self.Q = np.diag(Q) if Q.ndim == 1 else Q.copy()
+        self.R = np.diag(R) if R.ndim == 1 else R.copy()
+        n, m = self.Q.shape[0], self.R.shape[0]
+        self.H = np.zeros((m, n)) if H is None else np.asarray(H, dtype=float).copy()
+        self.q = np.zeros(n) if q is None else np.asarray(q, dtype=float).copy()
+        self.r = np.zeros(m) if r is None else np.asarray(r, dtype=float).copy()
+        self.c, self.terminal = float(c), bool(terminal)
+        if self.q.shape != (n,) or self.r.shape != (m,) or self.H.shape != (m, n):   # asserts at src/cost_functions.jl:434-436
+            raise DimensionMismatch("cost function blocks have inconsistent sizes")
+
+    state_dim = property(lambda s: s.Q.shape[0])
+    control_dim = property(lambda s: s.R.shape[0])
+
+    def is_blockdiag(self):
+        return self.is_diag or np.max(np.abs(self.H), initial=0.0) == 0.0
+
+    def copy(self):
+        return type(self)(self.Q, self.R, H=self.H, q=self.q, r=self.r, c=self.c, terminal=self.terminal)
+
+    def __add__(self, other):   # +(c1, c2)  src/cost_functions.jl:259-270
+        cls = DiagonalCost if (self.is_diag and other.is_diag) else QuadraticCost
+        return cls(self.Q + other.Q, self.R + other.R, H=self.H + other.H, q=self.q + other.q, r=self.r + other.r,
+                   c=self.c + other.c, terminal=self.terminal and other.terminal)
+
+    def _spec(self):
+        if self.is_diag:
+            return dict(kind=K.COST_DIAGONAL, terminal=self.terminal, Q=np.diag(self.Q).copy(), R=np.diag(self.R).copy(),
+                        q=self.q, r=self.r, c=self.c)
+        return dict(kind=K.COST_QUADRATIC, terminal=self.terminal, Q=self.Q, R=self.R, H=self.H, q=self.q, r=self.r, c=self.c)
+
+
+class DiagonalCost(QuadraticCostFunction):   # src/cost_functions.jl:326-347
+    is_diag = True
+
+    def __init__(self, Q, R, H=None, q=None, r=None, c=0.0, terminal=False):
+        super().__init__(Q, R, None, q, r, c, terminal)
+        self.Q = np.diag(np.diagonal(self.Q))
+        self.R = np.diag(np.diagonal(self.R))
+
+
+class QuadraticCost(QuadraticCostFunction):   # src/cost_functions.jl:417-454
+    pass
+
+
+def make_quadratic_cost(Q, R, H=None, q=None, r=None, c=0.0, **kw):
+    """``QuadraticCostFunction(Q,R,H,q,r,c)`` (src/cost_functions.jl:60-68): Diagonal when it can be."""
+    Hn = 0.0 if H is None else float(np.max(np.abs(H), initial=0.0))
+    cls = DiagonalCost if (_isdiag(Q) and _isdiag(R) and Hn == 0.0) else QuadraticCost
+    return cls(Q, R, H=H, q=q, r=r, c=c, **kw)
+
+
+def set_LQR_goal(cost, xf, uf=None):   # set_LQR_goal!  src/cost_functions.jl:245-254 (c is left as is)
+    cost.q = -cost.Q @ np.asarray(xf, dtype=float)
+    if uf is not None:
+        cost.r = -cost.R @ np.asarray(uf, dtype=float)
+
+
+def LQRCost(Q, R, xf, uf=None, **kw):   # src/cost_functions.jl:532-547
+    Q, R = np.asarray(Q, dtype=float), np.asarray(R, dtype=float)
+    Qm = np.diag(Q) if Q.ndim == 1 else Q
+    Rm = np.diag(R) if R.ndim == 1 else R
+    xf = np.asarray(xf, dtype=float)
+    uf = np.zeros(Rm.shape[0]) if uf is None else np.asarray(uf, dtype=float)
+    return make_quadratic_cost(Qm, Rm, None, -Qm @ xf, -Rm @ uf, 0.5 * xf @ Qm @ xf + 0.5 * uf @ Rm @ uf, **kw)
+
+
+class Objective:
+    """``Objective`` (src/objective.jl:27-45): one cost function per knot point."""
+
+    def __init__(self, cost, *args):
+        if isinstance(cost, QuadraticCostFunction) and len(args) == 1:          # Objective(cost, N)       :69-71
+            self.cost = [cost for _ in range(int(args[0]))]
+        elif isinstance(cost, QuadraticCostFunction) and len(args) == 2:        # Objective(cost, term, N) :73-76
+            N = int(args[1])
+            self.cost = [cost if k < N - 1 else args[0] for k in range(N)]
+        elif len(args) == 1:                                                     # Objective(costs, term)   :78-81
+            self.cost = list(cost) + [args[0]]
+        else:
+            self.cost = list(cost)
+        n, m = self.cost[0].state_dim, self.cost[0].control_dim
+        for c in self.cost:
+            if (c.state_dim, c.control_dim) != (n, m):
+                raise DimensionMismatch("all cost functions of an Objective must have the same dimensions")
+        self.J = np.zeros(len(self.cost))
+
+    def __len__(self):
+        return len(self.cost)
+
+    def __getitem__(self, k):
+        return self.cost[k]
+
+    def __iter__(self):
+        return iter(self.cost)
+
+    def dims(self):
+        return self.cost[0].state_dim, self.cost[0].control_dim
+
+    def _tables(self):
+        """distinct cost objects + per-knot index (what the device cost table holds)."""
+        uniq, index, seen = [], [], {}
+        for c in self.cost:
+            if id(c) not in seen:
+                seen[id(c)] = len(uniq)
+                uniq.append(c)
+            index.append(seen[id(c)])
+        return uniq, index
+
+
+def LQRObjective(Q, R, Qf, xf, N, uf=None):
+    """``LQRObjective(Q, R, Qf, xf, N; uf)`` (src/objective.jl:137-183): the terminal cost keeps R and r."""
+    Q, R, Qf = (np.asarray(a, dtype=float) for a in (Q, R, Qf))
+    Qm, Rm, Qfm = (np.diag(a) if a.ndim == 1 else a for a in (Q, R, Qf))
+    xf = np.asarray(xf, dtype=float)
+    if Qm.shape[0] != xf.size or Qfm.shape[0] != xf.size:
+        raise DimensionMismatch("Q / Qf size does not match xf")   # @assert src/objective.jl:141-143
+    uf = np.zeros(Rm.shape[0]) if uf is None else np.asarray(uf, dtype=float)
+    if Rm.shape[0] != uf.size:
+        raise DimensionMismatch("R size does not match uf")
+    q, r = -Qm @ xf, -Rm @ uf
+    c = 0.5 * xf @ Qm @ xf + 0.5 * uf @ Rm @ uf
+    qf, cf = -Qfm @ xf, 0.5 * xf @ Qfm @ xf
+    diag = _isdiag(Qm) and _isdiag(Rm) and _isdiag(Qfm)
+    cls = DiagonalCost if diag else QuadraticCost
+    stage = cls(Qm, Rm, q=q, r=r, c=c)
+    term = cls(Qfm, Rm, q=qf, r=r, c=cf, terminal=True)
+    return Objective(stage, term, N)
+
+
+def TrackingObjective(Q, R, X, U, Qf=None):
+    """``TrackingObjective(Q, R, Z; Qf)`` (src/objective.jl:190-196); ``X[N,n]``, ``U[N-1,m]`` reference trajectory."""
+    X, U = np.asarray(X, dtype=float), np.asarray(U, dtype=float)
+    N = X.shape[0]
+    costs = [LQRCost(Q, R, X[k], U[k]) for k in range(N - 1)]
+    costs.append(LQRCost(Q if Qf is None else Qf, R, X[N - 1], terminal=True))
+    return Objective(costs)
+
+
+# ------------------------------------------------------------------------------------------------------------
+# Constraints (reference src/constraints.jl, src/abstract_constraint.jl, src/constraint_list.jl)
+
+
+class AbstractConstraint:
+    sense_ = Inequality()
+
+    def _spec(self, first, last):
+        raise NotImplementedError
+
+
+def sense(con):   # src/abstract_constraint.jl:97
+    return con.sense_
+
+
+def output_dim(con):
+    return con.p
+
+
+def is_bound(con):   # src/abstract_constraint.jl:139
+    return isinstance(con, (GoalConstraint, BoundConstraint))
+
+
+def upper_bound(con):   # src/abstract_constraint.jl:104-109
+    if isinstance(con, BoundConstraint):
+        return con.z_max.copy()      # src/constraints.jl:733
+    return np.full(con.p, {ZeroCone: 0.0, NegativeOrthant: 0.0}.get(type(con.sense_), np.inf))
+
+
+def lower_bound(con):   # src/abstract_constraint.jl:116-121
+    if isinstance(con, BoundConstraint):
+        return con.z_min.copy()      # src/constraints.jl:732
+    return np.full(con.p, {ZeroCone: 0.0}.get(type(con.sense_), -np.inf))
+
+
+class GoalConstraint(AbstractConstraint):   # src/constraints.jl:22-87
+    sense_ = Equality()
+
+    def __init__(self, xf, inds=None):
+        xf = np.asarray(xf, dtype=float)
+        self.n = xf.size
+        self.inds = np.arange(1, self.n + 1) if inds is None else np.asarray(inds, dtype=int)
+        self.xf = xf[self.inds - 1].copy()
+        self.p = self.inds.size
+
+    def _spec(self, first, last):
+        return dict(kind=K.CON_GOAL, first=first, last=last, sense=K.CONE_ZERO, inds=self.inds, a=self.xf)
+
+
+def _check_bounds(k, hi, lo):   # checkBounds  src/constraints.jl:708-719
+    hi = np.full(k, float(hi)) if np.ndim(hi) == 0 else np.asarray(hi, dtype=float)
+    lo = np.full(k, float(lo)) if np.ndim(lo) == 0 else np.asarray(lo, dtype=float)
+    if not np.all(hi >= lo):
+        raise ArgumentError("Upper bounds must be greater than or equal to lower bounds")
+    return hi, lo
+
+
+class BoundConstraint(AbstractConstraint):   # src/constraints.jl:644-783
+    sense_ = Inequality()
+
+    def __init__(self, n, m, x_min=-np.inf, x_max=np.inf, u_min=-np.inf, u_max=np.inf):
+        self.n, self.m = n, m
+        x_max, x_min = _check_bounds(n, x_max, x_min)
+        u_max, u_min = _check_bounds(m, u_max, u_min)
+        self.z_max, self.z_min = np.concatenate([x_max, u_max]), np.concatenate([x_min, u_min])
+        self.p = int(np.isfinite(self.z_max).sum() + np.isfinite(self.z_min).sum())
+
+    def _spec(self, first, last):
+        return dict(kind=K.CON_BOUND, first=first, last=last, sense=K.CONE_NEGATIVE_ORTHANT, a=self.z_max, b=self.z_min)
+
+
+class LinearConstraint(AbstractConstraint):   # src/constraints.jl:103-150
+    def __init__(self, n, m, A, b, sense, inds="state"):
+        self.n, self.m = n, m
+        self.A, self.b = np.atleast_2d(np.asarray(A, dtype=float)), np.asarray(b, dtype=float)
+        self.on_control = inds in ("control", 1)
+        self.p, self.sense_ = self.A.shape[0], sense
+        if self.A.shape[1] != (m if self.on_control else n) or self.b.size != self.p:
+            raise DimensionMismatch("LinearConstraint: A / b size mismatch")   # @assert src/constraints.jl:113-116
+
+    def _spec(self, first, last):
+        return dict(kind=K.CON_LINEAR, first=first, last=last, sense=self.sense_.code, p=self.p, flag=int(self.on_control), a=self.A, b=self.b)
+
+
+class CircleConstraint(AbstractConstraint):   # src/constraints.jl:168-233
+    def __init__(self, n, xc, yc, radius, xi=1, yi=2):
+        self.n = n
+        self.x, self.y, self.radius = (np.atleast_1d(np.asarray(a, dtype=float)) for a in (xc, yc, radius))
+        self.xi, self.yi, self.p = xi, yi, self.x.size
+
+    def _spec(self, first, last):
+        return dict(kind=K.CON_CIRCLE, first=first, last=last, sense=K.CONE_NEGATIVE_ORTHANT, p=self.p, a=self.x, b=self.y,
+                    rad=self.radius, inds=[self.xi, self.yi])
+
+
+class SphereConstraint(AbstractConstraint):   # src/constraints.jl:249-326
+    def __init__(self, n, xc, yc, zc, radius, xi=1, yi=2, zi=3):
+        self.n = n
+        self.x, self.y, self.z, self.radius = (np.atleast_1d(np.asarray(a, dtype=float)) for a in (xc, yc, zc, radius))
+        self.xi, self.yi, self.zi, self.p = xi, yi, zi, self.x.size
+
+    def _spec(self, first, last):
+        return dict(kind=K.CON_SPHERE, first=first, last=last, sense=K.CONE_NEGATIVE_ORTHANT, p=self.p, a=self.x, b=self.y, c=self.z,
+                    rad=self.radius, inds=[self.xi, self.yi, self.zi])
+
+
+class NormConstraint(AbstractConstraint):   # src/constraints.jl:438-521
+    def __init__(self, n, m, val, sense, inds="all"):
+        self.n, self.m, self.val, self.sense_ = n, m, float(val), sense
+        if isinstance(inds, str):   # src/constraints.jl:446-454
+            inds = {"state": range(1, n + 1), "control": range(n + 1, n + m + 1), "all": range(1, n + m + 1)}[inds]
+        self.inds = np.asarray(list(inds), dtype=int)
+        if self.val < 0:
+            raise ArgumentError("NormConstraint value must be non-negative")   # @assert val >= 0 src/constraints.jl:443
+        self.p = self.inds.size + 1 if isinstance(sense, SecondOrderCone) else 1
+
+    def _spec(self, first, last):
+        return dict(kind=K.CON_NORM, first=first, last=last, sense=self.sense_.code, val=self.val, inds=self.inds)
+
+
+class ConstraintList:
+    """``ConstraintList(n, m, N)`` (src/constraint_list.jl:35-52)."""
+
+    def __init__(self, n, m, N):
+        self.n, self.m, self.N = n, m, N
+        self.constraints, self.inds = [], []
+        self.p = np.zeros(N, dtype=int)
+
+    def __len__(self):
+        return len(self.constraints)
+
+    def __getitem__(self, i):
+        return self.constraints[i]
+
+    def __iter__(self):
+        return iter(self.constraints)
+
+    def zip(self):   # Base.zip(cons)  src/constraint_list.jl:147
+        return zip(self.inds, self.constraints)
+
+
+def add_constraint(cons, con, inds, idx=-1):
+    """``add_constraint!(cons, con, inds)`` (src/constraint_list.jl:103-134); ``inds`` = knot ``k`` or ``(first, last)``."""
+    first, last = (inds, inds) if np.ndim(inds) == 0 else (inds[0], inds[-1])
+    n_ok = getattr(con, "n", cons.n) == cons.n
+    m_ok = getattr(con, "m", cons.m) == cons.m
+    if not (n_ok and m_ok):
+        raise DimensionMismatch("New constraint not consistent with n and m")   # src/constraint_list.jl:108-110
+    if not (1 <= first <= last <= cons.N):
+        raise ArgumentError("Invalid inds, inds[end] must be less than number of knotpoints")   # @assert :107
+    pos = len(cons.constraints) if idx == -1 else idx
+    cons.constraints.insert(pos, con)
+    cons.inds.insert(pos, (int(first), int(last)))
+    cons.p[first - 1:last] += con.p   # num_constraints!  src/constraint_list.jl:198-206
+
+
+def num_constraints(cons_or_prob):
+    cons = cons_or_prob.constraints if isinstance(cons_or_prob, Problem) else cons_or_prob
+    return cons.p.copy()
+
+
+# ------------------------------------------------------------------------------------------------------------
+# Problem (reference src/problem.jl)
+
+
+class Problem:
+    """``Problem(model, obj, x0, tf; xf, constraints, t0, X0, U0, dt)`` (src/problem.jl:79-123) for a batch.
+
+    ``x0`` is ``[n]`` (shared) or ``[B, n]``; ``batch`` gives ``B`` when ``x0`` is shared.  The integrator is RK4
+    (the reference's default, src/problem.jl:119-123).  States start as NaN and controls as zeros like the
+    reference (src/problem.jl:83-84).
+    """
+
+    def __init__(self, model, obj, x0, tf, xf=None, constraints=None, t0=0.0, X0=None, U0=None, dt=None, batch=None, device=0, **kwargs):
+        if "x0" in kwargs:   # src/problem.jl:87-91
+            raise ArgumentError("Cannot pass x0 as a keyword argument. It is now a positional argument, and xf is a keyword argument.")
+        n, m = model.dims()
+        N = len(obj)
+        x0 = np.asarray(x0, dtype=float)
+        B = int(batch) if batch is not None else (x0.shape[0] if x0.ndim == 2 else 1)
+        if x0.shape[-1] != n:
+            raise DimensionMismatch("x0 does not match the model's state dimension")   # @assert src/problem.jl:48
+        cons = constraints if constraints is not None else ConstraintList(n, m, N)
+        if (cons.n, cons.m) != (n, m):
+            raise DimensionMismatch("Constraint state dimensions don't match model")   # src/problem.jl:64-65
+        if cons.N != N:
+            raise DimensionMismatch("ConstraintList horizon does not match the objective")
+        if dt is None:
+            dtv = np.full(N - 1, float(tf - t0) / (N - 1))
+        else:
+            dtv = np.full(N - 1, float(dt)) if np.ndim(dt) == 0 else np.asarray(dt, dtype=float)
+        if not tf > t0:
+            raise ArgumentError("tf must be greater than t0")   # @assert tf > t0 src/problem.jl:52
+        self.model, self.obj, self.constraints = model, obj, cons
+        self.N, self.n, self.m, self.B = N, n, m, B
+        self.x0 = np.broadcast_to(x0, (B, n)).copy()
+        self.xf = np.full(n, np.nan) if xf is None else np.asarray(xf, dtype=float).copy()
+        uniq, index = obj._tables()
+        self._cost_objs = uniq
+        con_specs = [c._spec(f, l) for (f, l), c in zip(cons.inds, cons.constraints)]
+        self.spec = K.Spec(model.model_id, n, m, N, B, dtv, [c._spec() for c in uniq], index, con_specs,
+                           params=model.params, t0=t0, device=device)
+        self._open()
+        self._call("to_set_initial_state", K._dp(self.x0))
+        if U0 is not None:
+            initial_controls(self, U0)
+        if X0 is not None:
+            initial_states(self, X0)
+
+    def _open(self):
+        """create the device-side problem (to_create); fails loudly without the CUDA library / a GPU."""
+        self._lib = K.load_library()
+        self._h = C.c_void_p()
+        rc = self._lib.to_create(C.byref(self.spec.c), C.byref(self._h))
+        K.check(self._lib, None, rc)
+
+    def _call(self, name, *args):
+        rc = getattr(self._lib, name)(self._h, *args)
+        K.check(self._lib, self._h, rc)
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            self._lib.to_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def dims(prob):   # RD.dims(prob, k)  src/problem.jl:147
+    return prob.n, prob.m, prob.N
+
+
+def horizonlength(prob):
+    return prob.N
+
+
+def get_model(prob):
+    return prob.model
+
+
+def get_objective(prob):
+    return prob.obj
+
+
+def get_constraints(prob):
+    return prob.constraints
+
+
+def get_initial_state(prob):
+    return prob.x0
+
+
+def get_final_state(prob):
+    return prob.xf
+
+
+def is_constrained(prob):
+    """True when the problem has constraints.  (The reference returns ``isempty(constraints)``, an inverted
+    test enshrined in test/problems_tests.jl:208 -- SURVEY.md 2.4; this mirror returns the intended value.)"""
+    return len(prob.constraints) > 0
+
+
+def _bcast(a, shape, what):
+    a = np.asarray(a, dtype=np.float64)
+    try:
+        return np.ascontiguousarray(np.broadcast_to(a, shape))
+    except ValueError:
+        raise DimensionMismatch(f"{what} has shape {a.shape}, expected broadcastable to {shape}")
+
+
+def initial_controls(prob, U0):   # initial_controls!  src/problem.jl:261
+    U = _bcast(U0, (prob.B, prob.N - 1, prob.m), "U0")
+    prob._call("to_set_controls", K._dp(U))
+
+
+def initial_states(prob, X0):   # initial_states!  src/problem.jl:253
+    X = _bcast(X0, (prob.B, prob.N, prob.n), "X0")
+    prob._call("to_set_states", K._dp(X))
+
+
+def set_initial_state(prob, x0):   # set_initial_state!  src/problem.jl:270
+    prob.x0 = _bcast(x0, (prob.B, prob.n), "x0").copy()
+    prob._call("to_set_initial_state", K._dp(prob.x0))
+
+
+def setinitialtime(prob, t0):   # RD.setinitialtime!  src/problem.jl:280
+    tf = C.c_double()
+    prob._call("to_set_initial_time", float(t0), C.byref(tf))
+    return tf.value
+
+
+def set_goal_state(prob, xf, objective=True, constraint=True):   # set_goal_state!  src/problem.jl:294-310
+    xf = np.ascontiguousarray(np.asarray(xf, dtype=np.float64))
+    if objective:
+        for c in prob._cost_objs:
+            set_LQR_goal(c, xf)
+    if constraint:
+        for con in prob.constraints:
+            if isinstance(con, GoalConstraint):
+                con.xf = xf[con.inds - 1].copy() if xf.size != con.xf.size else xf.copy()
+    prob.xf = xf.copy()
+    prob._call("to_set_goal_state", K._dp(xf), int(objective), int(constraint))
+
+
+def states(prob, k=None):   # states(prob)  src/problem.jl:175
+    X = np.empty((prob.B, prob.N, prob.n))
+    prob._call("to_get_states", K._dp(X))
+    return X if k is None else X[:, k - 1]
+
+
+def controls(prob, k=None):   # controls(prob)  src/problem.jl:168
+    U = np.empty((prob.B, prob.N - 1, prob.m))
+    prob._call("to_get_controls", K._dp(U))
+    return U if k is None else U[:, k - 1]
+
+
+def gettimes(prob):   # gettimes(prob)  src/problem.jl:182
+    t = np.empty(prob.N)
+    prob._call("to_get_times", K._dp(t))
+    return t
+
+
+def rollout(prob):   # rollout!(prob)  src/problem.jl:330-340
+    prob._call("to_rollout")
+
+
+def cost(prob):   # cost(prob)  src/problem.jl:321 -> [B]
+    J = np.empty(prob.B)
+    prob._call("to_cost", K._dp(J))
+    return J
+
+
+def cost_knots(prob):   # cost!(obj, Z); get_J(obj)  src/objective.jl:104-110 -> [B, N]
+    Jk = np.empty((prob.B, prob.N))
+    prob._call("to_cost_knots", K._dp(Jk))
+    return Jk
+
+
+def cost_gradient(prob):   # RD.gradient!(cost_k, grad, z_k) for all knots  src/cost_functions.jl:137-172 -> [B, N, n+m]
+    g = np.empty((prob.B, prob.N, prob.n + prob.m))
+    prob._call("to_cost_gradient", K._dp(g))
+    return g
+
+
+def cost_hessian(prob):   # RD.hessian!  src/cost_functions.jl:212-233 -> [B, N, n+m, n+m]
+    nm = prob.n + prob.m
+    H = np.empty((prob.B, prob.N, nm, nm))
+    prob._call("to_cost_hessian", K._dp(H))
+    return np.swapaxes(H, -1, -2)
+
+
+def _con_index(prob, con):
+    if isinstance(con, (int, np.integer)):
+        return int(con)
+    for i, c in enumerate(prob.constraints):
+        if c is con:
+            return i
+    raise ArgumentError("constraint is not part of the problem's ConstraintList")
+
+
+def evaluate_constraints(prob, con):
+    """``evaluate_constraints!(sig, con, vals, Z, inds)`` (src/abstract_constraint.jl:200-225) -> ``[B, len(inds), p]``."""
+    i = _con_index(prob, con)
+    first, last = prob.constraints.inds[i]
+    vals = np.empty((prob.B, last - first + 1, prob.constraints[i].p))
+    prob._call("to_eval_constraints", i, K._dp(vals))
+    return vals
+
+
+def constraint_jacobians(prob, con):
+    """``constraint_jacobians!`` (src/abstract_constraint.jl:236-248) -> ``[B, len(inds), p, n+m]``."""
+    i = _con_index(prob, con)
+    first, last = prob.constraints.inds[i]
+    p = prob.constraints[i].p
+    jac = np.empty((prob.B, last - first + 1, prob.n + prob.m, p))
+    prob._call("to_constraint_jacobians", i, K._dp(jac))
+    return np.swapaxes(jac, -1, -2)
+
+
+def max_violation(prob):
+    v = np.empty(prob.B)
+    prob._call("to_max_violation", K._dp(v))
+    return v
+
+
+def merit(prob):
+    """cost + augmented-Lagrangian penalty of the current trajectory -> [B]."""
+    J = np.empty(prob.B)
+    prob._call("to_merit", K._dp(J))
+    return J
+
+
+def al_expansion(prob):
+    nm = prob.n + prob.m
+    g = np.empty((prob.B, prob.N, nm))
+    H = np.empty((prob.B, prob.N, nm, nm))
+    prob._call("to_al_expansion", K._dp(g), K._dp(H))
+    return g, np.swapaxes(H, -1, -2)
+
+
+# ---- what Altro.jl does with the API above ---------------------------------------------------------------------
+
+
+def expand(prob):
+    """dynamics expansion (RD.jacobian!(ForwardAD) at every knot)."""
+    prob._call("to_expand")
+
+
+def dynamics_jacobians(prob):
+    """-> ``[B, N-1, n, n+m]`` = [A B] per knot."""
+    AB = np.empty((prob.B, prob.N - 1, prob.n + prob.m, prob.n))
+    prob._call("to_get_dynamics_jacobians", K._dp(AB))
+    return np.swapaxes(AB, -1, -2)
+
+
+def backward(prob):
+    status = np.empty(prob.B, dtype=np.int32)
+    prob._call("to_backward", K._ip(status))
+    return status
+
+
+def forward(prob):
+    J, alpha = np.empty(prob.B), np.empty(prob.B)
+    prob._call("to_forward", K._dp(J), K._dp(alpha))
+    return J, alpha
+
+
+def ilqr_step(prob, iters=1):
+    prob._call("to_ilqr_step", int(iters))
+
+
+def al_update(prob):
+    prob._call("to_al_update")
+
+
+def gains(prob):
+    """-> ``K[B, N-1, m, n]``, ``d[B, N-1, m]``."""
+    Kk = np.empty((prob.B, prob.N - 1, prob.n, prob.m))
+    d = np.empty((prob.B, prob.N - 1, prob.m))
+    prob._call("to_get_gains", K._dp(Kk), K._dp(d))
+    return np.swapaxes(Kk, -1, -2), d
+
+
+def multipliers(prob, con):
+    i = _con_index(prob, con)
+    first, last = prob.constraints.inds[i]
+    lam = np.empty((prob.B, last - first + 1, prob.constraints[i].p))
+    prob._call("to_get_multipliers", i, K._dp(lam))
+    return lam
+
+
+def set_multipliers(prob, con, lam):
+    i = _con_index(prob, con)
+    first, last = prob.constraints.inds[i]
+    lam = _bcast(lam, (prob.B, last - first + 1, prob.constraints[i].p), "lambda")
+    prob._call("to_set_multipliers", i, K._dp(lam))
+
+
+def penalty(prob, con):
+    mu = C.c_double()
+    prob._call("to_get_penalty", _con_index(prob, con), C.byref(mu))
+    return mu.value
+
+
+def set_penalty(prob, con, mu):
+    prob._call("to_set_penalty", _con_index(prob, con), float(mu))
+
+
+def solver_state(prob):
+    B = prob.B
+    rho, dV, alpha = np.empty(B), np.empty((B, 2)), np.empty(B)
+    ls, bp = np.empty(B, dtype=np.int32), np.empty(B, dtype=np.int32)
+    prob._call("to_get_solver_state", K._dp(rho), K._dp(dV), K._dp(alpha), K._ip(ls), K._ip(bp))
+    return dict(rho=rho, dV=dV, alpha=alpha, ls_iters=ls, bp_status=bp)
+
+
+def set_options(prob, **kw):
+    o = K.to_options()
+    prob._lib.to_default_options(C.byref(o))
+    for k, v in kw.items():
+        if not hasattr(o, k):
+            raise ArgumentError(f"unknown solver option {k}")
+        setattr(o, k, v)
+    prob._call("to_set_options", C.byref(o))

@@ -1,0 +1,773 @@
+// capi.cu -- the C ABI (include/trajopt_b200.h): opaque handle, device memory, descriptor tables, and the
+// sequencing of the hot-path kernels.  No compute happens on the host: every compute entry point launches the
+// sm_100a kernels of rollout.cu / sweep.cu / riccati.cu / forward.cu on the handle's stream.
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/trajopt_b200.h"
+#include "kernels.h"
+
+namespace {
+
+std::string g_create_error;
+
+struct Scratch {
+    void* ptr = nullptr;
+    size_t bytes = 0;
+};
+
+}  // namespace
+
+struct to_handle {
+    DevProblem P{};
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    std::string err;
+    std::vector<void*> allocs;
+    std::vector<DevCost> h_costs;
+    std::vector<DevCon> h_cons;
+    std::vector<double> h_mu, h_dt;
+    std::vector<int> h_cost_index;
+    DevCost* d_costs = nullptr;
+    DevCon* d_cons = nullptr;
+    double* d_mu = nullptr;
+    double* d_stageX = nullptr;   // dense [B][N][n] staging for get/set
+    double* d_stageU = nullptr;
+    double* d_viol = nullptr;     // [B]
+    double* d_merit2 = nullptr;   // {sum J, max viol}
+    int* d_work = nullptr;
+    int* d_err = nullptr;
+    Scratch scratch;
+    double t0 = 0;
+    bool J_valid = false, expanded = false, backward_done = false;
+    int64_t launches = 0;
+    // phase timing
+    bool timing = false;
+    struct Ev { cudaEvent_t a, b; int phase; };
+    std::vector<Ev> pending;
+    std::vector<cudaEvent_t> pool;
+    double phase_ms[TO_PHASE_COUNT] = {0};
+    int64_t phase_launches[TO_PHASE_COUNT] = {0};
+};
+
+namespace {
+
+int fail(to_handle* h, int code, const std::string& msg) {
+    if (h) h->err = msg; else g_create_error = msg;
+    return code;
+}
+int cuda_fail(to_handle* h, cudaError_t e, const char* what) {
+    return fail(h, e == cudaErrorMemoryAllocation ? TO_ENOMEM : TO_ECUDA, std::string(what) + ": " + cudaGetErrorString(e));
+}
+#define CU(h, expr)                                                   \
+    do {                                                              \
+        cudaError_t e__ = (expr);                                     \
+        if (e__ != cudaSuccess) return cuda_fail(h, e__, #expr);      \
+    } while (0)
+
+template <class T>
+int dalloc(to_handle* h, T** p, size_t count) {
+    void* q = nullptr;
+    cudaError_t e = cudaMalloc(&q, std::max<size_t>(count, 1) * sizeof(T));
+    if (e != cudaSuccess) return cuda_fail(h, e, "cudaMalloc");
+    h->allocs.push_back(q);
+    *p = static_cast<T*>(q);
+    return TO_OK;
+}
+
+int ensure_scratch(to_handle* h, size_t bytes) {
+    if (h->scratch.bytes >= bytes) return TO_OK;
+    if (h->scratch.ptr) { cudaStreamSynchronize(h->stream); cudaFree(h->scratch.ptr); h->scratch.ptr = nullptr; h->scratch.bytes = 0; }
+    cudaError_t e = cudaMalloc(&h->scratch.ptr, bytes);
+    if (e != cudaSuccess) return cuda_fail(h, e, "cudaMalloc(scratch)");
+    h->scratch.bytes = bytes;
+    return TO_OK;
+}
+
+int upload_tables(to_handle* h) {
+    CU(h, cudaMemcpyAsync(h->d_costs, h->h_costs.data(), sizeof(DevCost) * h->h_costs.size(), cudaMemcpyHostToDevice, h->stream));
+    if (!h->h_cons.empty()) {
+        CU(h, cudaMemcpyAsync(h->d_cons, h->h_cons.data(), sizeof(DevCon) * h->h_cons.size(), cudaMemcpyHostToDevice, h->stream));
+        CU(h, cudaMemcpyAsync(h->d_mu, h->h_mu.data(), sizeof(double) * h->h_mu.size(), cudaMemcpyHostToDevice, h->stream));
+    }
+    CU(h, cudaStreamSynchronize(h->stream));   // the host vectors may change right after
+    return TO_OK;
+}
+
+// phase timing helpers
+struct PhaseScope {
+    to_handle* h; int phase; cudaEvent_t a = nullptr, b = nullptr;
+    PhaseScope(to_handle* h_, int phase_) : h(h_), phase(phase_) {
+        if (!h->timing) return;
+        auto get = [&]() { cudaEvent_t e; if (!h->pool.empty()) { e = h->pool.back(); h->pool.pop_back(); } else cudaEventCreate(&e); return e; };
+        a = get(); b = get();
+        cudaEventRecord(a, h->stream);
+    }
+    ~PhaseScope() {
+        if (!h->timing) return;
+        cudaEventRecord(b, h->stream);
+        h->pending.push_back({a, b, phase});
+    }
+};
+
+void set_default_options(DevOptions& o) {
+    o.bp_reg_increase_factor = 1.6; o.bp_reg_max = 1e8; o.bp_reg_min = 1e-8; o.bp_reg_initial = 0.0; o.bp_reg_fp = 10.0;
+    o.ls_lower = 1e-8; o.ls_upper = 10.0; o.ls_iters = 10; o.pad = 0;
+    o.max_state_value = 1e8; o.max_control_value = 1e8;
+    o.penalty_initial = 1.0; o.penalty_scaling = 10.0; o.penalty_max = 1e8; o.dual_max = 1e8;
+}
+
+void model_defaults(int model, int m, int& n_out, int& m_out, double* p) {
+    for (int i = 0; i < 16; i++) p[i] = 0;
+    switch (model) {
+        case TO_MODEL_DOUBLE_INTEGRATOR: n_out = 2 * m; m_out = m; p[0] = 1.0; break;
+        case TO_MODEL_CARTPOLE: n_out = 4; m_out = 1; p[0] = 1.0; p[1] = 0.2; p[2] = 0.5; p[3] = 9.81; break;
+        case TO_MODEL_QUADROTOR:
+            n_out = 13; m_out = 4; p[0] = 0.5; p[1] = 0.0023; p[2] = 0.0023; p[3] = 0.004; p[4] = 0; p[5] = 0; p[6] = -9.81;
+            p[7] = 0.1750; p[8] = 1.0; p[9] = 0.0245; break;
+        case TO_MODEL_ACROBOT:
+            n_out = 4; m_out = 1; p[0] = 1; p[1] = 1; p[2] = 1; p[3] = 1; p[4] = 1.0 / 12; p[5] = 1.0 / 12; p[6] = 1.0; p[7] = 9.81; break;
+        default: n_out = -1; m_out = -1;
+    }
+}
+
+int build_cost(to_handle* h, const to_cost_spec& tc, int n, int m, DevCost& c) {
+    std::memset(&c, 0, sizeof(c));
+    if (!tc.Q || !tc.R || !tc.q || !tc.r) return fail(h, TO_EINVAL, "cost: null Q/R/q/r");
+    c.diag = (tc.kind == TO_COST_DIAGONAL); c.terminal = tc.terminal != 0; c.c = tc.c;
+    for (int i = 0; i < n; i++) c.q[i] = tc.q[i];
+    for (int i = 0; i < m; i++) c.r[i] = tc.r[i];
+    if (c.diag) {
+        for (int i = 0; i < n; i++) { c.Qd[i] = tc.Q[i]; c.Q[i * n + i] = tc.Q[i]; }
+        for (int i = 0; i < m; i++) { c.Rd[i] = tc.R[i]; c.R[i * m + i] = tc.R[i]; }
+        c.zeroH = 1;
+    } else {
+        for (int i = 0; i < n * n; i++) c.Q[i] = tc.Q[i];
+        for (int i = 0; i < m * m; i++) c.R[i] = tc.R[i];
+        for (int i = 0; i < n; i++) c.Qd[i] = tc.Q[i * n + i];
+        for (int i = 0; i < m; i++) c.Rd[i] = tc.R[i * m + i];
+        double hn = 0;
+        if (tc.H) for (int i = 0; i < m * n; i++) { c.H[i] = tc.H[i]; hn = std::fmax(hn, std::fabs(tc.H[i])); }
+        c.zeroH = (hn == 0.0);   // is_blockdiag(cost) = zeroH, src/cost_functions.jl:445,455
+    }
+    return TO_OK;
+}
+
+int build_con(to_handle* h, const to_constraint_spec& tc, int n, int m, int N, DevCon& c) {
+    std::memset(&c, 0, sizeof(c));
+    const int nm = n + m;
+    c.kind = tc.kind; c.first = tc.first; c.last = tc.last; c.flag = tc.flag; c.val = tc.val;
+    if (tc.first < 1 || tc.last > N || tc.last < tc.first) return fail(h, TO_EINVAL, "constraint knot range outside 1:N");
+    for (int j = 0; j < TO_MAXNM; j++) { c.row_max[j] = -1; c.row_min[j] = -1; }
+    switch (tc.kind) {
+        case TO_CON_GOAL:
+            if (tc.ninds < 1 || tc.ninds > n || !tc.inds || !tc.a) return fail(h, TO_EINVAL, "GoalConstraint: bad inds/xf");
+            c.p = tc.ninds; c.sense = CONE_ZERO; c.diagonal = 1; c.ninds = tc.ninds;
+            for (int i = 0; i < tc.ninds; i++) {
+                const int j = tc.inds[i] - 1;
+                if (j < 0 || j >= n) return fail(h, TO_EDIM, "GoalConstraint: index outside the state");
+                c.inds[i] = j; c.a[i] = tc.a[i]; c.row_max[j] = i;
+            }
+            break;
+        case TO_CON_BOUND:
+            if (!tc.a || !tc.b) return fail(h, TO_EINVAL, "BoundConstraint: null bounds");
+            c.sense = CONE_NEGATIVE_ORTHANT; c.diagonal = 1;
+            for (int j = 0; j < nm; j++) {
+                if (!(tc.a[j] >= tc.b[j])) return fail(h, TO_EINVAL, "Upper bounds must be greater than or equal to lower bounds");   // src/constraints.jl:712
+                c.a[j] = tc.a[j]; c.b[j] = tc.b[j];
+            }
+            for (int j = 0; j < nm; j++) if (std::isfinite(tc.a[j])) { c.row_max[j] = c.n_max; c.a_max[c.n_max++] = j; }
+            for (int j = 0; j < nm; j++) if (std::isfinite(tc.b[j])) { c.row_min[j] = c.n_max + c.n_min; c.a_min[c.n_min++] = j; }
+            c.p = c.n_max + c.n_min;
+            if (c.p == 0) return fail(h, TO_EINVAL, "BoundConstraint without any finite bound");
+            break;
+        case TO_CON_LINEAR: {
+            const int w = tc.flag ? m : n;
+            if (tc.p < 1 || tc.p > TO_MAXP || tc.p * w > TO_CON_A || !tc.a || !tc.b) return fail(h, TO_EINVAL, "LinearConstraint: bad size");
+            c.p = tc.p; c.sense = tc.sense;
+            for (int i = 0; i < tc.p * w; i++) c.a[i] = tc.a[i];
+            for (int i = 0; i < tc.p; i++) c.b[i] = tc.b[i];
+            break;
+        }
+        case TO_CON_CIRCLE:
+        case TO_CON_SPHERE: {
+            const int need = tc.kind == TO_CON_CIRCLE ? 2 : 3;
+            if (tc.p < 1 || tc.p > TO_MAXP || !tc.a || !tc.b || !tc.rad || (need == 3 && !tc.c)) return fail(h, TO_EINVAL, "Circle/SphereConstraint: bad size");
+            c.p = tc.p; c.sense = CONE_NEGATIVE_ORTHANT;
+            for (int i = 0; i < tc.p; i++) { c.a[i] = tc.a[i]; c.b[i] = tc.b[i]; c.rad[i] = tc.rad[i]; if (need == 3) c.c3[i] = tc.c[i]; }
+            for (int i = 0; i < need; i++) {
+                c.inds[i] = (tc.inds && tc.ninds > i) ? tc.inds[i] - 1 : i;
+                if (c.inds[i] < 0 || c.inds[i] >= n) return fail(h, TO_EDIM, "Circle/SphereConstraint: index outside the state");
+            }
+            break;
+        }
+        case TO_CON_NORM:
+            if (tc.ninds < 1 || tc.ninds > nm || !tc.inds) return fail(h, TO_EINVAL, "NormConstraint: bad inds");
+            c.sense = tc.sense; c.ninds = tc.ninds;
+            for (int i = 0; i < tc.ninds; i++) {
+                c.inds[i] = tc.inds[i] - 1;
+                if (c.inds[i] < 0 || c.inds[i] >= nm) return fail(h, TO_EDIM, "NormConstraint: index outside z");
+            }
+            c.p = (tc.sense == TO_CONE_SECOND_ORDER) ? tc.ninds + 1 : 1;
+            if (tc.sense != TO_CONE_SECOND_ORDER && tc.sense != TO_CONE_NEGATIVE_ORTHANT && tc.sense != TO_CONE_ZERO)
+                return fail(h, TO_EINVAL, "NormConstraint: sense must be Inequality, Equality or SecondOrderCone");
+            break;
+        default: return fail(h, TO_EINVAL, "unknown constraint kind");
+    }
+    if (c.p > TO_MAXP) return fail(h, TO_EINVAL, "constraint output dimension exceeds TO_MAXP");
+    return TO_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* to_last_error(const to_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int to_default_options(to_options* o) {
+    if (!o) return TO_EINVAL;
+    DevOptions d; set_default_options(d);
+    o->bp_reg_increase_factor = d.bp_reg_increase_factor; o->bp_reg_max = d.bp_reg_max; o->bp_reg_min = d.bp_reg_min;
+    o->bp_reg_initial = d.bp_reg_initial; o->bp_reg_fp = d.bp_reg_fp;
+    o->line_search_lower_bound = d.ls_lower; o->line_search_upper_bound = d.ls_upper; o->iterations_linesearch = d.ls_iters; o->reserved = 0;
+    o->max_state_value = d.max_state_value; o->max_control_value = d.max_control_value;
+    o->penalty_initial = d.penalty_initial; o->penalty_scaling = d.penalty_scaling; o->penalty_max = d.penalty_max; o->dual_max = d.dual_max;
+    return TO_OK;
+}
+
+int to_create(const to_spec* s, to_handle** out) {
+    if (!s || !out) return fail(nullptr, TO_EINVAL, "null argument");
+    *out = nullptr;
+    int dev_count = 0;
+    cudaError_t ce = cudaGetDeviceCount(&dev_count);
+    if (ce != cudaSuccess || dev_count == 0)
+        return fail(nullptr, TO_ECUDA, "no CUDA device: this library has no CPU fallback (" + std::string(cudaGetErrorString(ce)) + ")");
+    if (s->device < 0 || s->device >= dev_count) return fail(nullptr, TO_EINVAL, "device ordinal out of range");
+    int mn = 0, mm = 0; double params[16];
+    model_defaults(s->model, s->m, mn, mm, params);
+    if (mn < 0) return fail(nullptr, TO_EINVAL, "unknown model id");
+    if (s->model == TO_MODEL_DOUBLE_INTEGRATOR && s->m != 1 && s->m != 2) return fail(nullptr, TO_EDIM, "DoubleIntegrator: supported dimensions are 1 and 2");
+    if (mn != s->n) return fail(nullptr, TO_EDIM, "Objective state dimensions don't match model.");     // src/problem.jl:67
+    if (mm != s->m) return fail(nullptr, TO_EDIM, "Objective control dimensions don't match model.");   // src/problem.jl:68
+    if (s->N < 2 || s->B < 1) return fail(nullptr, TO_EINVAL, "need N >= 2 knot points and B >= 1 instances");
+    if (!s->dt || !s->costs || !s->cost_index || s->ncost < 1) return fail(nullptr, TO_EINVAL, "null dt / costs / cost_index");
+    if (s->ncon < 0 || s->ncon > TO_MAXCON || (s->ncon > 0 && !s->cons)) return fail(nullptr, TO_EINVAL, "too many constraints (max 8) or null list");
+    for (int k = 0; k < s->N - 1; k++) if (!(s->dt[k] > 0)) return fail(nullptr, TO_EINVAL, "time steps must be positive");   // tf > t0, src/problem.jl:50
+    if (s->params) for (int i = 0; i < s->nparams && i < 16; i++) params[i] = s->params[i];
+
+    auto* h = new to_handle();
+    h->device = s->device;
+    auto bail = [&](int code) { std::string msg = h->err; to_destroy(h); g_create_error = msg; return code; };
+    if (cudaSetDevice(s->device) != cudaSuccess) { h->err = "cudaSetDevice failed"; return bail(TO_ECUDA); }
+    if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { h->err = "cudaStreamCreate failed"; return bail(TO_ECUDA); }
+    h->own_stream = true;
+    DevProblem& P = h->P;
+    P.model = s->model; P.n = mn; P.m = mm; P.N = s->N; P.B = s->B;
+    P.ldab = (mn + mm + 1) & ~1;
+    std::memcpy(P.params, params, sizeof(params));
+    set_default_options(P.opt);
+    h->t0 = s->t0;
+    const int n = mn, m = mm, N = s->N, B = s->B;
+
+    h->h_costs.resize(s->ncost);
+    P.all_diag_cost = 1;
+    for (int i = 0; i < s->ncost; i++) {
+        int rc = build_cost(h, s->costs[i], n, m, h->h_costs[i]);
+        if (rc) return bail(rc);
+        if (!h->h_costs[i].diag) P.all_diag_cost = 0;
+    }
+    h->h_cost_index.assign(s->cost_index, s->cost_index + N);
+    for (int k = 0; k < N; k++)
+        if (h->h_cost_index[k] < 0 || h->h_cost_index[k] >= s->ncost) { h->err = "cost_index out of range"; return bail(TO_EINVAL); }
+    h->h_cons.resize(s->ncon);
+    P.all_diag_con = 1; P.lambda_len = 0;
+    for (int i = 0; i < s->ncon; i++) {
+        int rc = build_con(h, s->cons[i], n, m, N, h->h_cons[i]);
+        if (rc) return bail(rc);
+        h->h_cons[i].offset = P.lambda_len;
+        P.lambda_len += (h->h_cons[i].last - h->h_cons[i].first + 1) * h->h_cons[i].p;
+        if (!h->h_cons[i].diagonal) P.all_diag_con = 0;
+    }
+    P.ncost = s->ncost; P.ncon = s->ncon;
+    h->h_mu.assign(s->ncon, P.opt.penalty_initial);
+    h->h_dt.assign(s->dt, s->dt + (N - 1));
+
+    int rc = TO_OK;
+    double* d_dt = nullptr; int* d_ci = nullptr;
+    P.strideX = (size_t)B * N * n; P.strideU = (size_t)B * (N - 1) * m;
+#define ALLOC(ptr, count) if (!rc) rc = dalloc(h, &(ptr), (size_t)(count))
+    ALLOC(d_dt, N - 1); ALLOC(d_ci, N);
+    ALLOC(h->d_costs, s->ncost); ALLOC(h->d_cons, std::max(1, s->ncon)); ALLOC(h->d_mu, std::max(1, s->ncon));
+    ALLOC(P.x0, (size_t)B * n); ALLOC(P.X, 2 * P.strideX); ALLOC(P.U, 2 * P.strideU); ALLOC(P.cur, B);
+    ALLOC(P.AB, (size_t)B * (N - 1) * n * P.ldab); ALLOC(P.K, (size_t)B * (N - 1) * n * m); ALLOC(P.d, (size_t)B * (N - 1) * m);
+    ALLOC(P.lambda, (size_t)B * std::max(1, P.lambda_len));
+    ALLOC(P.rho, B); ALLOC(P.drho, B); ALLOC(P.dV, 2 * (size_t)B); ALLOC(P.J, B); ALLOC(P.Jc, B); ALLOC(P.alpha, B);
+    ALLOC(P.bp_status, B); ALLOC(P.ls_iters, B); ALLOC(P.accepted, B);
+    ALLOC(h->d_stageX, P.strideX); ALLOC(h->d_stageU, P.strideU); ALLOC(h->d_viol, B); ALLOC(h->d_merit2, 2);
+    ALLOC(h->d_work, 1); ALLOC(h->d_err, 1);
+#undef ALLOC
+    if (rc) return bail(rc);
+    P.dt = d_dt; P.cost_index = d_ci; P.costs = h->d_costs; P.cons = h->d_cons; P.mu = h->d_mu;
+    cudaStream_t st = h->stream;
+    bool okc = true;
+    okc &= cudaMemcpyAsync(d_dt, h->h_dt.data(), sizeof(double) * (N - 1), cudaMemcpyHostToDevice, st) == cudaSuccess;
+    okc &= cudaMemcpyAsync(d_ci, h->h_cost_index.data(), sizeof(int) * N, cudaMemcpyHostToDevice, st) == cudaSuccess;
+    okc &= cudaMemsetAsync(P.x0, 0, sizeof(double) * B * n, st) == cudaSuccess;
+    okc &= cudaMemsetAsync(P.X, 0xFF, sizeof(double) * 2 * P.strideX, st) == cudaSuccess;   // NaN: X0 = NaN until rollout!, src/problem.jl:83
+    okc &= cudaMemsetAsync(P.U, 0, sizeof(double) * 2 * P.strideU, st) == cudaSuccess;      // U0 = 0, src/problem.jl:84
+    okc &= cudaMemsetAsync(P.cur, 0, sizeof(int) * B, st) == cudaSuccess;
+    okc &= cudaMemsetAsync(P.AB, 0, sizeof(double) * (size_t)B * (N - 1) * n * P.ldab, st) == cudaSuccess;
+    okc &= cudaMemsetAsync(P.K, 0, sizeof(double) * (size_t)B * (N - 1) * n * m, st) == cudaSuccess;
+    okc &= cudaMemsetAsync(P.d, 0, sizeof(double) * (size_t)B * (N - 1) * m, st) == cudaSuccess;
+    okc &= cudaMemsetAsync(P.lambda, 0, sizeof(double) * (size_t)B * std::max(1, P.lambda_len), st) == cudaSuccess;
+    okc &= cudaMemsetAsync(P.rho, 0, sizeof(double) * B, st) == cudaSuccess;
+    okc &= cudaMemsetAsync(P.drho, 0, sizeof(double) * B, st) == cudaSuccess;
+    okc &= cudaMemsetAsync(P.dV, 0, sizeof(double) * 2 * B, st) == cudaSuccess;
+    okc &= cudaMemsetAsync(P.J, 0, sizeof(double) * B, st) == cudaSuccess;
+    okc &= cudaMemsetAsync(P.Jc, 0, sizeof(double) * B, st) == cudaSuccess;
+    okc &= cudaMemsetAsync(P.alpha, 0, sizeof(double) * B, st) == cudaSuccess;
+    okc &= cudaMemsetAsync(P.bp_status, 0, sizeof(int) * B, st) == cudaSuccess;
+    okc &= cudaMemsetAsync(P.ls_iters, 0, sizeof(int) * B, st) == cudaSuccess;
+    okc &= cudaMemsetAsync(P.accepted, 0, sizeof(int) * B, st) == cudaSuccess;
+    okc &= cudaMemsetAsync(h->d_err, 0, sizeof(int), st) == cudaSuccess;
+    if (!okc) { h->err = std::string("device initialisation failed: ") + cudaGetErrorString(cudaGetLastError()); return bail(TO_ECUDA); }
+    rc = upload_tables(h);
+    if (rc) return bail(rc);
+    *out = h;
+    return TO_OK;
+}
+
+int to_destroy(to_handle* h) {
+    if (!h) return TO_OK;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    for (void* p : h->allocs) cudaFree(p);
+    if (h->scratch.ptr) cudaFree(h->scratch.ptr);
+    for (auto& e : h->pending) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
+    for (auto e : h->pool) cudaEventDestroy(e);
+    if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+    return TO_OK;
+}
+
+int to_set_options(to_handle* h, const to_options* o) {
+    if (!h || !o) return TO_EINVAL;
+    if (o->iterations_linesearch < 0 || o->iterations_linesearch > 15) return fail(h, TO_EINVAL, "iterations_linesearch must be in 0..15");
+    if (!(o->penalty_initial > 0) || !(o->penalty_scaling > 0)) return fail(h, TO_EINVAL, "penalties must be positive");
+    DevOptions& d = h->P.opt;
+    d.bp_reg_increase_factor = o->bp_reg_increase_factor; d.bp_reg_max = o->bp_reg_max; d.bp_reg_min = o->bp_reg_min;
+    d.bp_reg_initial = o->bp_reg_initial; d.bp_reg_fp = o->bp_reg_fp;
+    d.ls_lower = o->line_search_lower_bound; d.ls_upper = o->line_search_upper_bound; d.ls_iters = o->iterations_linesearch;
+    d.max_state_value = o->max_state_value; d.max_control_value = o->max_control_value;
+    d.penalty_initial = o->penalty_initial; d.penalty_scaling = o->penalty_scaling; d.penalty_max = o->penalty_max; d.dual_max = o->dual_max;
+    for (auto& mu : h->h_mu) mu = d.penalty_initial;
+    std::vector<double> r(h->P.B, d.bp_reg_initial);
+    CU(h, cudaMemcpyAsync(h->P.rho, r.data(), sizeof(double) * h->P.B, cudaMemcpyHostToDevice, h->stream));
+    CU(h, cudaMemsetAsync(h->P.drho, 0, sizeof(double) * h->P.B, h->stream));
+    h->J_valid = false;
+    return upload_tables(h);
+}
+
+int to_set_stream(to_handle* h, void* cuda_stream) {
+    if (!h) return TO_EINVAL;
+    CU(h, cudaStreamSynchronize(h->stream));
+    if (h->own_stream) { cudaStreamDestroy(h->stream); h->own_stream = false; }
+    h->stream = static_cast<cudaStream_t>(cuda_stream);
+    return TO_OK;
+}
+int to_synchronize(to_handle* h) {
+    if (!h) return TO_EINVAL;
+    CU(h, cudaStreamSynchronize(h->stream));
+    return TO_OK;
+}
+int to_dims(const to_handle* h, int32_t* n, int32_t* m, int32_t* N, int32_t* B) {
+    if (!h) return TO_EINVAL;
+    if (n) *n = h->P.n; if (m) *m = h->P.m; if (N) *N = h->P.N; if (B) *B = h->P.B;
+    return TO_OK;
+}
+int to_num_constraints(const to_handle* h, int32_t* p_per_knot) {
+    if (!h || !p_per_knot) return TO_EINVAL;
+    for (int k = 1; k <= h->P.N; k++) {
+        int p = 0;
+        for (const auto& c : h->h_cons) if (k >= c.first && k <= c.last) p += c.p;
+        p_per_knot[k - 1] = p;
+    }
+    return TO_OK;
+}
+int to_constraint_info(const to_handle* h, int32_t con, int32_t* p, int32_t* sense, int32_t* first, int32_t* last) {
+    if (!h || con < 0 || con >= (int)h->h_cons.size()) return TO_EINVAL;
+    const DevCon& c = h->h_cons[con];
+    if (p) *p = c.p; if (sense) *sense = c.sense; if (first) *first = c.first; if (last) *last = c.last;
+    return TO_OK;
+}
+// upper_bound / lower_bound by sense, src/abstract_constraint.jl:97-123
+int to_bounds(const to_handle* h, int32_t con, double* lower, double* upper) {
+    if (!h || con < 0 || con >= (int)h->h_cons.size()) return TO_EINVAL;
+    const DevCon& c = h->h_cons[con];
+    for (int i = 0; i < c.p; i++) {
+        double lo = 0, up = 0;
+        switch (c.sense) {
+            case CONE_ZERO: lo = 0; up = 0; break;
+            case CONE_NEGATIVE_ORTHANT: lo = -INFINITY; up = 0; break;
+            case CONE_SECOND_ORDER: lo = -INFINITY; up = INFINITY; break;
+            default: lo = -INFINITY; up = INFINITY;
+        }
+        if (lower) lower[i] = lo;
+        if (upper) upper[i] = up;
+    }
+    return TO_OK;
+}
+
+// ---- setters / getters ----------------------------------------------------------------------------------
+int to_set_initial_state(to_handle* h, const double* x0) {
+    if (!h || !x0) return TO_EINVAL;
+    CU(h, cudaMemcpyAsync(h->P.x0, x0, sizeof(double) * (size_t)h->P.B * h->P.n, cudaMemcpyHostToDevice, h->stream));
+    h->J_valid = false;
+    return TO_OK;
+}
+int to_set_controls(to_handle* h, const double* U) {
+    if (!h || !U) return TO_EINVAL;
+    CU(h, cudaMemcpyAsync(h->d_stageU, U, sizeof(double) * h->P.strideU, cudaMemcpyHostToDevice, h->stream));
+    CU(h, launch_scatter_traj(h->P, nullptr, h->d_stageU, h->stream)); h->launches++;
+    h->J_valid = false; h->expanded = false; h->backward_done = false;
+    return TO_OK;
+}
+int to_set_states(to_handle* h, const double* X) {
+    if (!h || !X) return TO_EINVAL;
+    CU(h, cudaMemcpyAsync(h->d_stageX, X, sizeof(double) * h->P.strideX, cudaMemcpyHostToDevice, h->stream));
+    CU(h, launch_scatter_traj(h->P, h->d_stageX, nullptr, h->stream)); h->launches++;
+    h->J_valid = false; h->expanded = false; h->backward_done = false;
+    return TO_OK;
+}
+int to_get_states(to_handle* h, double* X) {
+    if (!h || !X) return TO_EINVAL;
+    CU(h, launch_gather_traj(h->P, h->d_stageX, nullptr, h->stream)); h->launches++;
+    CU(h, cudaMemcpyAsync(X, h->d_stageX, sizeof(double) * h->P.strideX, cudaMemcpyDeviceToHost, h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
+    return TO_OK;
+}
+int to_get_controls(to_handle* h, double* U) {
+    if (!h || !U) return TO_EINVAL;
+    CU(h, launch_gather_traj(h->P, nullptr, h->d_stageU, h->stream)); h->launches++;
+    CU(h, cudaMemcpyAsync(U, h->d_stageU, sizeof(double) * h->P.strideU, cudaMemcpyDeviceToHost, h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
+    return TO_OK;
+}
+int to_get_times(to_handle* h, double* t) {
+    if (!h || !t) return TO_EINVAL;
+    t[0] = h->t0;
+    for (int k = 1; k < h->P.N; k++) t[k] = t[k - 1] + h->h_dt[k - 1];
+    return TO_OK;
+}
+int to_set_initial_time(to_handle* h, double t0, double* tf_out) {
+    if (!h) return TO_EINVAL;
+    h->t0 = t0;
+    if (tf_out) { double t = t0; for (double d : h->h_dt) t += d; *tf_out = t; }
+    return TO_OK;
+}
+// set_goal_state! src/problem.jl:294-310 with set_LQR_goal! (q = -Q xf; c untouched) src/cost_functions.jl:245-248
+int to_set_goal_state(to_handle* h, const double* xf, int objective, int constraint) {
+    if (!h || !xf) return TO_EINVAL;
+    const int n = h->P.n;
+    if (objective)
+        for (auto& c : h->h_costs)
+            for (int i = 0; i < n; i++) { double t = 0; for (int j = 0; j < n; j++) t += c.Q[j * n + i] * xf[j]; c.q[i] = -t; }
+    if (constraint)
+        for (auto& c : h->h_cons)
+            if (c.kind == CON_GOAL) for (int i = 0; i < c.p; i++) c.a[i] = xf[c.inds[i]];
+    h->J_valid = false;
+    return upload_tables(h);
+}
+
+// ---- kernel 1 ---------------------------------------------------------------------------------------------
+int to_rollout(to_handle* h) {
+    if (!h) return TO_EINVAL;
+    CU(h, launch_rollout(h->P, h->stream)); h->launches++;
+    h->J_valid = false; h->expanded = false; h->backward_done = false;
+    return TO_OK;
+}
+int to_expand(to_handle* h) {
+    if (!h) return TO_EINVAL;
+    { PhaseScope ps(h, TO_PHASE_EXPAND); CU(h, launch_expand(h->P, h->stream)); }
+    h->launches++; h->phase_launches[TO_PHASE_EXPAND]++;
+    h->expanded = true; h->backward_done = false;
+    return TO_OK;
+}
+int to_get_dynamics_jacobians(to_handle* h, double* AB) {
+    if (!h || !AB) return TO_EINVAL;
+    if (!h->expanded) return fail(h, TO_ESTATE, "to_get_dynamics_jacobians before to_expand");
+    const size_t cnt = (size_t)h->P.B * (h->P.N - 1) * h->P.n * (h->P.n + h->P.m);
+    int rc = ensure_scratch(h, cnt * sizeof(double)); if (rc) return rc;
+    CU(h, launch_export_ab(h->P, (double*)h->scratch.ptr, h->stream)); h->launches++;
+    CU(h, cudaMemcpyAsync(AB, h->scratch.ptr, cnt * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
+    return TO_OK;
+}
+
+// ---- kernel 2 ---------------------------------------------------------------------------------------------
+static int run_to_host(to_handle* h, size_t count, double* host, cudaError_t (*fn)(to_handle*, double*)) {
+    int rc = ensure_scratch(h, count * sizeof(double)); if (rc) return rc;
+    CU(h, fn(h, (double*)h->scratch.ptr)); h->launches++;
+    CU(h, cudaMemcpyAsync(host, h->scratch.ptr, count * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
+    return TO_OK;
+}
+int to_cost(to_handle* h, double* J) {
+    if (!h || !J) return TO_EINVAL;
+    return run_to_host(h, h->P.B, J, [](to_handle* hh, double* d) { return launch_cost(hh->P, d, nullptr, hh->stream); });
+}
+int to_cost_knots(to_handle* h, double* Jk) {
+    if (!h || !Jk) return TO_EINVAL;
+    return run_to_host(h, (size_t)h->P.B * h->P.N, Jk, [](to_handle* hh, double* d) { return launch_cost(hh->P, nullptr, d, hh->stream); });
+}
+int to_cost_gradient(to_handle* h, double* grad) {
+    if (!h || !grad) return TO_EINVAL;
+    return run_to_host(h, (size_t)h->P.B * h->P.N * (h->P.n + h->P.m), grad, [](to_handle* hh, double* d) { return launch_cost_gradient(hh->P, d, hh->stream); });
+}
+int to_cost_hessian(to_handle* h, double* hess) {
+    if (!h || !hess) return TO_EINVAL;
+    const int nm = h->P.n + h->P.m;
+    return run_to_host(h, (size_t)h->P.B * h->P.N * nm * nm, hess, [](to_handle* hh, double* d) { return launch_cost_hessian(hh->P, d, hh->stream); });
+}
+int to_al_expansion(to_handle* h, double* grad, double* hess) {
+    if (!h || !grad || !hess) return TO_EINVAL;
+    const int nm = h->P.n + h->P.m;
+    const size_t ng = (size_t)h->P.B * h->P.N * nm, nh = ng * nm;
+    int rc = ensure_scratch(h, (ng + nh) * sizeof(double)); if (rc) return rc;
+    double* dg = (double*)h->scratch.ptr; double* dh = dg + ng;
+    CU(h, launch_al_expansion(h->P, dg, dh, h->stream)); h->launches++;
+    CU(h, cudaMemcpyAsync(grad, dg, ng * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CU(h, cudaMemcpyAsync(hess, dh, nh * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
+    return TO_OK;
+}
+int to_eval_constraints(to_handle* h, int32_t con, double* vals) {
+    if (!h || !vals) return TO_EINVAL;
+    if (con < 0 || con >= (int)h->h_cons.size()) return fail(h, TO_EINVAL, "constraint index out of range");
+    const DevCon& c = h->h_cons[con];
+    const size_t cnt = (size_t)h->P.B * (c.last - c.first + 1) * c.p;
+    int rc = ensure_scratch(h, cnt * sizeof(double)); if (rc) return rc;
+    CU(h, launch_eval_constraints(h->P, con, (double*)h->scratch.ptr, h->stream)); h->launches++;
+    CU(h, cudaMemcpyAsync(vals, h->scratch.ptr, cnt * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
+    return TO_OK;
+}
+int to_constraint_jacobians(to_handle* h, int32_t con, double* jac) {
+    if (!h || !jac) return TO_EINVAL;
+    if (con < 0 || con >= (int)h->h_cons.size()) return fail(h, TO_EINVAL, "constraint index out of range");
+    const DevCon& c = h->h_cons[con];
+    const size_t cnt = (size_t)h->P.B * (c.last - c.first + 1) * c.p * (h->P.n + h->P.m);
+    int rc = ensure_scratch(h, cnt * sizeof(double)); if (rc) return rc;
+    CU(h, launch_constraint_jacobians(h->P, con, (double*)h->scratch.ptr, h->stream)); h->launches++;
+    CU(h, cudaMemcpyAsync(jac, h->scratch.ptr, cnt * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
+    return TO_OK;
+}
+static int ensure_merit(to_handle* h) {
+    if (h->J_valid) return TO_OK;
+    CU(h, launch_merit(h->P, h->P.J, h->d_viol, h->stream)); h->launches++;
+    h->J_valid = true;
+    return TO_OK;
+}
+int to_merit(to_handle* h, double* J) {
+    if (!h || !J) return TO_EINVAL;
+    int rc = ensure_merit(h); if (rc) return rc;
+    CU(h, cudaMemcpyAsync(J, h->P.J, sizeof(double) * h->P.B, cudaMemcpyDeviceToHost, h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
+    return TO_OK;
+}
+int to_max_violation(to_handle* h, double* v) {
+    if (!h || !v) return TO_EINVAL;
+    CU(h, launch_merit(h->P, h->P.J, h->d_viol, h->stream)); h->launches++;
+    h->J_valid = true;
+    CU(h, cudaMemcpyAsync(v, h->d_viol, sizeof(double) * h->P.B, cudaMemcpyDeviceToHost, h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
+    return TO_OK;
+}
+
+static int cone_call(to_handle* h, int32_t cone, int32_t p, int32_t count, const double* x, const double* b, double* out, int mode) {
+    if (!h || !x || !out || (mode == 2 && !b)) return TO_EINVAL;
+    if (p < 1 || p > TO_MAXP || count < 1) return fail(h, TO_EINVAL, "cone op: p must be in 1..32 and count >= 1");
+    if (cone < 0 || cone > CONE_POSITIVE_ORTHANT) return fail(h, TO_EINVAL, "unknown cone");
+    const size_t nx = (size_t)count * p, nout = mode == 0 ? nx : nx * p;
+    int rc = ensure_scratch(h, (2 * nx + nout) * sizeof(double)); if (rc) return rc;
+    double* dx = (double*)h->scratch.ptr; double* db = dx + nx; double* dout = db + nx;
+    CU(h, cudaMemcpyAsync(dx, x, nx * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    if (mode == 2) CU(h, cudaMemcpyAsync(db, b, nx * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    CU(h, cudaMemsetAsync(h->d_err, 0, sizeof(int), h->stream));
+    if (mode == 0) CU(h, launch_projection(cone, p, count, dx, dout, h->d_err, h->stream));
+    else if (mode == 1) CU(h, launch_grad_projection(cone, p, count, dx, dout, h->d_err, h->stream));
+    else CU(h, launch_hess_projection(cone, p, count, dx, db, dout, h->d_err, h->stream));
+    h->launches++;
+    int err = 0;
+    CU(h, cudaMemcpyAsync(out, dout, nout * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CU(h, cudaMemcpyAsync(&err, h->d_err, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
+    if (err) return fail(h, TO_ECONE, "Invalid second-order cone projection");   // src/cones.jl:91,124
+    return TO_OK;
+}
+int to_projection(to_handle* h, int32_t cone, int32_t p, int32_t count, const double* x, double* px) { return cone_call(h, cone, p, count, x, nullptr, px, 0); }
+int to_grad_projection(to_handle* h, int32_t cone, int32_t p, int32_t count, const double* x, double* J) { return cone_call(h, cone, p, count, x, nullptr, J, 1); }
+int to_hess_projection(to_handle* h, int32_t cone, int32_t p, int32_t count, const double* x, const double* b, double* H) { return cone_call(h, cone, p, count, x, b, H, 2); }
+
+// ---- kernel 3 + forward pass --------------------------------------------------------------------------------
+static int solver_supported(to_handle* h) {
+    if (!h->P.all_diag_con)
+        return fail(h, TO_ESTATE, "the Riccati / forward kernels handle Goal and Bound constraints only (others are evaluation-only in this release)");
+    return TO_OK;
+}
+static int do_backward(to_handle* h) {
+    { PhaseScope ps(h, TO_PHASE_BACKWARD); CU(h, launch_backward(h->P, h->d_work, h->stream)); }
+    h->launches++; h->phase_launches[TO_PHASE_BACKWARD]++;
+    h->backward_done = true;
+    return TO_OK;
+}
+static int do_forward(to_handle* h) {
+    { PhaseScope ps(h, TO_PHASE_FORWARD); CU(h, launch_forward(h->P, h->stream)); }
+    h->launches++; h->phase_launches[TO_PHASE_FORWARD]++;
+    { PhaseScope ps(h, TO_PHASE_LADDER); CU(h, launch_ladder(h->P, h->stream)); }
+    h->launches++; h->phase_launches[TO_PHASE_LADDER]++;
+    h->expanded = false; h->backward_done = false;   // the trajectory moved
+    return TO_OK;
+}
+int to_backward(to_handle* h, int32_t* status) {
+    if (!h) return TO_EINVAL;
+    int rc = solver_supported(h); if (rc) return rc;
+    if (!h->expanded) return fail(h, TO_ESTATE, "to_backward before to_expand");
+    rc = do_backward(h); if (rc) return rc;
+    if (status) {
+        CU(h, cudaMemcpyAsync(status, h->P.bp_status, sizeof(int) * h->P.B, cudaMemcpyDeviceToHost, h->stream));
+        CU(h, cudaStreamSynchronize(h->stream));
+    }
+    return TO_OK;
+}
+int to_forward(to_handle* h, double* J, double* alpha) {
+    if (!h) return TO_EINVAL;
+    int rc = solver_supported(h); if (rc) return rc;
+    if (!h->backward_done) return fail(h, TO_ESTATE, "to_forward before to_backward");
+    rc = ensure_merit(h); if (rc) return rc;
+    rc = do_forward(h); if (rc) return rc;
+    if (J) CU(h, cudaMemcpyAsync(J, h->P.J, sizeof(double) * h->P.B, cudaMemcpyDeviceToHost, h->stream));
+    if (alpha) CU(h, cudaMemcpyAsync(alpha, h->P.alpha, sizeof(double) * h->P.B, cudaMemcpyDeviceToHost, h->stream));
+    if (J || alpha) CU(h, cudaStreamSynchronize(h->stream));
+    return TO_OK;
+}
+int to_ilqr_step(to_handle* h, int32_t iters) {
+    if (!h || iters < 0) return TO_EINVAL;
+    int rc = solver_supported(h); if (rc) return rc;
+    rc = ensure_merit(h); if (rc) return rc;
+    for (int it = 0; it < iters; it++) {
+        rc = to_expand(h); if (rc) return rc;
+        rc = do_backward(h); if (rc) return rc;
+        rc = do_forward(h); if (rc) return rc;
+    }
+    return TO_OK;
+}
+int to_al_update(to_handle* h) {
+    if (!h) return TO_EINVAL;
+    if (h->P.ncon > 0) { CU(h, launch_al_update(h->P, h->stream)); h->launches++; }
+    for (auto& mu : h->h_mu) mu = std::fmin(mu * h->P.opt.penalty_scaling, h->P.opt.penalty_max);
+    if (!h->h_mu.empty()) CU(h, cudaMemcpyAsync(h->d_mu, h->h_mu.data(), sizeof(double) * h->h_mu.size(), cudaMemcpyHostToDevice, h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
+    h->J_valid = false;
+    return TO_OK;
+}
+int to_get_gains(to_handle* h, double* K, double* d) {
+    if (!h) return TO_EINVAL;
+    if (K) CU(h, cudaMemcpyAsync(K, h->P.K, sizeof(double) * (size_t)h->P.B * (h->P.N - 1) * h->P.n * h->P.m, cudaMemcpyDeviceToHost, h->stream));
+    if (d) CU(h, cudaMemcpyAsync(d, h->P.d, sizeof(double) * (size_t)h->P.B * (h->P.N - 1) * h->P.m, cudaMemcpyDeviceToHost, h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
+    return TO_OK;
+}
+static int multipliers_copy(to_handle* h, int32_t con, double* host, bool to_host) {
+    if (!h || !host) return TO_EINVAL;
+    if (con < 0 || con >= (int)h->h_cons.size()) return fail(h, TO_EINVAL, "constraint index out of range");
+    const DevCon& c = h->h_cons[con];
+    const size_t len = (size_t)(c.last - c.first + 1) * c.p;
+    if (to_host) {
+        CU(h, cudaMemcpy2DAsync(host, len * sizeof(double), h->P.lambda + c.offset, (size_t)h->P.lambda_len * sizeof(double), len * sizeof(double), h->P.B, cudaMemcpyDeviceToHost, h->stream));
+    } else {
+        CU(h, cudaMemcpy2DAsync(h->P.lambda + c.offset, (size_t)h->P.lambda_len * sizeof(double), host, len * sizeof(double), len * sizeof(double), h->P.B, cudaMemcpyHostToDevice, h->stream));
+        h->J_valid = false;
+    }
+    CU(h, cudaStreamSynchronize(h->stream));
+    return TO_OK;
+}
+int to_get_multipliers(to_handle* h, int32_t con, double* lambda) { return multipliers_copy(h, con, lambda, true); }
+int to_set_multipliers(to_handle* h, int32_t con, const double* lambda) { return multipliers_copy(h, con, const_cast<double*>(lambda), false); }
+int to_get_penalty(to_handle* h, int32_t con, double* mu) {
+    if (!h || !mu || con < 0 || con >= (int)h->h_mu.size()) return TO_EINVAL;
+    *mu = h->h_mu[con];
+    return TO_OK;
+}
+int to_set_penalty(to_handle* h, int32_t con, double mu) {
+    if (!h || con < 0 || con >= (int)h->h_mu.size() || !(mu > 0)) return TO_EINVAL;
+    h->h_mu[con] = mu;
+    CU(h, cudaMemcpyAsync(h->d_mu, h->h_mu.data(), sizeof(double) * h->h_mu.size(), cudaMemcpyHostToDevice, h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
+    h->J_valid = false;
+    return TO_OK;
+}
+int to_get_solver_state(to_handle* h, double* rho, double* dV, double* alpha, int32_t* ls_iters, int32_t* bp_status) {
+    if (!h) return TO_EINVAL;
+    const int B = h->P.B;
+    if (rho) CU(h, cudaMemcpyAsync(rho, h->P.rho, sizeof(double) * B, cudaMemcpyDeviceToHost, h->stream));
+    if (dV) CU(h, cudaMemcpyAsync(dV, h->P.dV, sizeof(double) * 2 * B, cudaMemcpyDeviceToHost, h->stream));
+    if (alpha) CU(h, cudaMemcpyAsync(alpha, h->P.alpha, sizeof(double) * B, cudaMemcpyDeviceToHost, h->stream));
+    if (ls_iters) CU(h, cudaMemcpyAsync(ls_iters, h->P.ls_iters, sizeof(int) * B, cudaMemcpyDeviceToHost, h->stream));
+    if (bp_status) CU(h, cudaMemcpyAsync(bp_status, h->P.bp_status, sizeof(int) * B, cudaMemcpyDeviceToHost, h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
+    return TO_OK;
+}
+
+// ---- multi-GPU / measurement plumbing -----------------------------------------------------------------------
+int to_reduce_merit(to_handle* h) {
+    if (!h) return TO_EINVAL;
+    CU(h, launch_merit(h->P, h->P.J, h->d_viol, h->stream)); h->launches++;
+    h->J_valid = true;
+    CU(h, launch_reduce_merit(h->P, h->d_viol, h->d_merit2, h->stream)); h->launches++;
+    return TO_OK;
+}
+int to_merit_device_ptr(to_handle* h, void** ptr) {
+    if (!h || !ptr) return TO_EINVAL;
+    *ptr = h->d_merit2;
+    return TO_OK;
+}
+int to_set_phase_timing(to_handle* h, int enable) {
+    if (!h) return TO_EINVAL;
+    h->timing = enable != 0;
+    return TO_OK;
+}
+int to_get_phase_times(to_handle* h, double* ms, int64_t* launches, int reset) {
+    if (!h) return TO_EINVAL;
+    CU(h, cudaStreamSynchronize(h->stream));
+    for (auto& e : h->pending) {
+        float t = 0;
+        if (cudaEventElapsedTime(&t, e.a, e.b) == cudaSuccess) h->phase_ms[e.phase] += t;
+        h->pool.push_back(e.a); h->pool.push_back(e.b);
+    }
+    h->pending.clear();
+    for (int i = 0; i < TO_PHASE_COUNT; i++) {
+        if (ms) ms[i] = h->phase_ms[i];
+        if (launches) launches[i] = h->phase_launches[i];
+        if (reset) { h->phase_ms[i] = 0; h->phase_launches[i] = 0; }
+    }
+    return TO_OK;
+}
+int64_t to_launch_count(const to_handle* h) { return h ? h->launches : 0; }
+// E=(XU+AB+HES)w, R=(AB+XU+KD+Lambda+HES)w, F=(2XU+KD+Lambda)w+8 ; HES=0 (LQR costs are never materialised)
+int to_algorithmic_bytes(const to_handle* h, int64_t* E, int64_t* R, int64_t* F) {
+    if (!h) return TO_EINVAL;
+    const int64_t n = h->P.n, m = h->P.m, N = h->P.N, w = 8;
+    const int64_t XU = (n + m) * N, AB = n * (n + m) * (N - 1), KD = m * (n + 1) * (N - 1), L = h->P.lambda_len;
+    if (E) *E = (XU + AB) * w;
+    if (R) *R = (AB + XU + KD + L) * w;
+    if (F) *F = (2 * XU + KD + L) * w + 8;
+    return TO_OK;
+}
+
+}  // extern "C"

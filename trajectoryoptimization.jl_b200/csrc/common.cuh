@@ -1,0 +1,112 @@
+// common.cuh -- shared device/host definitions of the B200 (sm_100a) batched trajectory-optimization hot path.
+//
+// Data layout in HBM (all fp64, instance-major so one instance's per-knot blocks are contiguous and can be
+// streamed with 1-D bulk TMA copies by the warp that owns the instance):
+//   X   [2][B][N][n]          double-buffered trajectory (cur[b] selects the live buffer; the forward pass
+//   U   [2][B][N-1][m]        writes its candidate into the other buffer and acceptance flips cur[b])
+//   AB  [B][N-1][n][LDAB]     discrete dynamics Jacobian [A B], ROW-major, row stride LDAB = n+m rounded up to
+//                             even (16-byte rows for bulk copies / LDS.128); pad column = 0
+//   K   [B][N-1][n][m]        feedback gains, m x n column-major (Julia layout)      d [B][N-1][m]
+//   lambda [B][lambda_len]    multipliers, per constraint: [knot in range][p]
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define TO_MAXN 16
+#define TO_MAXM 8
+#define TO_MAXNM (TO_MAXN + TO_MAXM)
+#define TO_MAXCON 8
+#define TO_MAXP 32          // rows of one constraint at one knot
+#define TO_CON_A 256
+
+// reference enums (mirrors include/trajopt_b200.h)
+enum { MODEL_DOUBLE_INTEGRATOR = 0, MODEL_CARTPOLE = 1, MODEL_QUADROTOR = 2, MODEL_ACROBOT = 3 };
+enum { CONE_ZERO = 0, CONE_NEGATIVE_ORTHANT = 1, CONE_SECOND_ORDER = 2, CONE_IDENTITY = 3, CONE_POSITIVE_ORTHANT = 4 };
+enum { CON_GOAL = 0, CON_BOUND = 1, CON_LINEAR = 2, CON_CIRCLE = 3, CON_SPHERE = 4, CON_NORM = 5 };
+
+// QuadraticCostFunction (reference src/cost_functions.jl:326-347, :417-454); dense storage + diagonal copy
+struct DevCost {
+    int diag, terminal, zeroH, pad;
+    double c;
+    double Qd[TO_MAXN], Rd[TO_MAXM];
+    double q[TO_MAXN], r[TO_MAXM];
+    double Q[TO_MAXN * TO_MAXN];   // n*n col-major (stride n)
+    double R[TO_MAXM * TO_MAXM];   // m*m col-major (stride m)
+    double H[TO_MAXM * TO_MAXN];   // m*n col-major (stride m)
+};
+
+// AbstractConstraint descriptor (reference src/constraints.jl); `diagonal` constraints (Goal, Bound) have a
+// +-1 selector Jacobian and get the fast AL path inside the Riccati / forward kernels.
+struct DevCon {
+    int kind, first, last, p, sense, offset, ninds, flag;   // first/last: 1-based inclusive knots; offset into lambda
+    int diagonal;
+    int n_max, n_min, pad;
+    int inds[TO_MAXNM];      // GOAL: state index per row (0-based); NORM: indices into z; CIRCLE/SPHERE: xi,yi,zi
+    int a_max[TO_MAXNM];     // BOUND: z index of each finite upper bound (row i)        src/constraints.jl:675
+    int a_min[TO_MAXNM];     // BOUND: z index of each finite lower bound (row n_max+i)  src/constraints.jl:676
+    int row_max[TO_MAXNM];   // BOUND: row of z_j's upper bound or -1 ; GOAL: row of x_j or -1
+    int row_min[TO_MAXNM];   // BOUND: row of z_j's lower bound or -1
+    double val;
+    double a[TO_CON_A];      // GOAL xf[p] | BOUND z_max[n+m] | LINEAR A[p x w] col-major | CIRCLE/SPHERE xc[p]
+    double b[TO_MAXP];       // BOUND z_min[n+m] | LINEAR b[p] | yc[p]
+    double c3[TO_MAXP];      // SPHERE zc[p]
+    double rad[TO_MAXP];
+};
+
+struct DevOptions {
+    double bp_reg_increase_factor, bp_reg_max, bp_reg_min, bp_reg_initial, bp_reg_fp;
+    double ls_lower, ls_upper;
+    int ls_iters, pad;
+    double max_state_value, max_control_value;
+    double penalty_initial, penalty_scaling, penalty_max, dual_max;
+};
+
+// Everything a kernel needs, passed by value (lives in the kernel parameter / constant bank).
+struct DevProblem {
+    int model, n, m, N, B;
+    int ldab;                 // row stride of AB
+    int ncost, ncon, lambda_len;
+    int all_diag_cost;        // every cost is a DiagonalCost
+    int all_diag_con;         // every constraint is Goal/Bound
+    int pad0;
+    double params[16];
+    DevOptions opt;
+    const double* dt;         // [N-1]
+    const DevCost* costs;     // [ncost]
+    const int* cost_index;    // [N]
+    const DevCon* cons;       // [ncon]
+    const double* mu;         // [ncon] penalties
+    double* x0;               // [B][n]
+    double* X;                // [2][B][N][n]
+    double* U;                // [2][B][N-1][m]
+    int* cur;                 // [B] live trajectory buffer (0/1)
+    double* AB;               // [B][N-1][n][ldab]
+    double* K;                // [B][N-1][n][m]
+    double* d;                // [B][N-1][m]
+    double* lambda;           // [B][lambda_len]
+    double* rho;              // [B]
+    double* drho;             // [B]
+    double* dV;               // [B][2]
+    double* J;                // [B] merit of the live trajectory
+    double* Jc;               // [B] merit of the candidate
+    double* alpha;            // [B]
+    int* bp_status;           // [B]
+    int* ls_iters;            // [B]
+    int* accepted;            // [B]
+    size_t strideX, strideU;  // elements between the two trajectory buffers
+};
+
+__host__ __device__ inline const double* traj_X(const DevProblem& P, int buf, int b) { return P.X + buf * P.strideX + (size_t)b * P.N * P.n; }
+__host__ __device__ inline const double* traj_U(const DevProblem& P, int buf, int b) { return P.U + buf * P.strideU + (size_t)b * (P.N - 1) * P.m; }
+__host__ __device__ inline double* traj_Xw(const DevProblem& P, int buf, int b) { return P.X + buf * P.strideX + (size_t)b * P.N * P.n; }
+__host__ __device__ inline double* traj_Uw(const DevProblem& P, int buf, int b) { return P.U + buf * P.strideU + (size_t)b * (P.N - 1) * P.m; }
+
+// Altro.jl regularization_update! (restated; see oracle/oracle.hpp reg_increase / reg_decrease)
+__host__ __device__ inline void reg_increase(const DevOptions& o, double& rho, double& drho) {
+    drho = fmax(drho * o.bp_reg_increase_factor, o.bp_reg_increase_factor);
+    rho = fmax(rho * drho, o.bp_reg_min);
+}
+__host__ __device__ inline void reg_decrease(const DevOptions& o, double& rho, double& drho) {
+    drho = fmin(drho / o.bp_reg_increase_factor, 1.0 / o.bp_reg_increase_factor);
+    rho = rho * drho * ((rho * drho > o.bp_reg_min) ? 1.0 : 0.0);
+}

@@ -1,0 +1,29 @@
+// kernels.h -- host-side launch wrappers (one per kernel), implemented in the .cu files next to this header.
+#pragma once
+#include "common.cuh"
+
+// kernel 1: batched RK4 rollout / dual-number dynamics expansion           (rollout.cu)
+cudaError_t launch_rollout(const DevProblem& P, cudaStream_t s);
+cudaError_t launch_expand(const DevProblem& P, cudaStream_t s);
+// kernel 2: cost + constraint + AL sweep                                     (sweep.cu)
+cudaError_t launch_cost(const DevProblem& P, double* J, double* Jk, cudaStream_t s);
+cudaError_t launch_merit(const DevProblem& P, double* J, double* viol, cudaStream_t s);
+cudaError_t launch_cost_gradient(const DevProblem& P, double* grad, cudaStream_t s);
+cudaError_t launch_cost_hessian(const DevProblem& P, double* hess, cudaStream_t s);
+cudaError_t launch_al_expansion(const DevProblem& P, double* grad, double* hess, cudaStream_t s);
+cudaError_t launch_eval_constraints(const DevProblem& P, int con, double* vals, cudaStream_t s);
+cudaError_t launch_constraint_jacobians(const DevProblem& P, int con, double* jac, cudaStream_t s);
+cudaError_t launch_projection(int cone, int p, int count, const double* x, double* px, int* err, cudaStream_t s);
+cudaError_t launch_grad_projection(int cone, int p, int count, const double* x, double* J, int* err, cudaStream_t s);
+cudaError_t launch_hess_projection(int cone, int p, int count, const double* x, const double* b, double* H, int* err, cudaStream_t s);
+cudaError_t launch_al_update(const DevProblem& P, cudaStream_t s);
+cudaError_t launch_reduce_merit(const DevProblem& P, const double* viol, double* out2, cudaStream_t s);
+cudaError_t launch_gather_traj(const DevProblem& P, double* Xout, double* Uout, cudaStream_t s);
+cudaError_t launch_scatter_traj(const DevProblem& P, const double* Xin, const double* Uin, cudaStream_t s);
+cudaError_t launch_export_ab(const DevProblem& P, double* ABout, cudaStream_t s);
+// kernel 3: Riccati backward pass                                             (riccati.cu)
+cudaError_t launch_backward(const DevProblem& P, int* work_counter, cudaStream_t s);
+// forward pass: closed-loop rollout + merit + line search                     (forward.cu)
+cudaError_t launch_forward(const DevProblem& P, cudaStream_t s);
+cudaError_t launch_ladder(const DevProblem& P, cudaStream_t s);
+cudaError_t launch_accept(const DevProblem& P, cudaStream_t s);

@@ -1,0 +1,315 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200 hot path (BASELINE.json metric):
+
+    iLQR iterations/sec on batched Quadrotor (n=13, m=4, N=101, batch=4096 per GPU, goal + control-bound AL-iLQR)
+
+A "step" is one iLQR iteration (dynamics expansion + Riccati backward pass + forward pass with line search) of
+every instance in the batch.  `value` times K consecutive iterations of one solve with everything resident in HBM;
+`e2e` times the same iteration through the public C ABI with HOST buffers (x0 + warm-start controls uploaded,
+controls + merit downloaded every step).  `--impl reference` times the CPU oracle port of the same path on the
+host cores (the Julia reference cannot run here: no Julia in the image).
+
+    python bench.py --gpus 1 --steps 20 --warmup 3
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    "quadrotor": dict(n=13, m=4, N=101, batch=4096, desc="Quadrotor point-to-point n=13 m=4 N=101, u in [0,10] + goal (AL-iLQR)"),
+    "cartpole": dict(n=4, m=1, N=101, batch=1024, desc="Cartpole swing-up n=4 m=1 N=101, unconstrained LQR cost"),
+    "acrobot": dict(n=4, m=1, N=201, batch=8192, desc="Acrobot n=4 m=1 N=201, dense second-order cost + |u|<=15 + goal (AL)"),
+}
+
+
+def build_problem(workload, B, N, cls=None, device=0):
+    import trajopt_b200 as TO
+    P = TO.problems
+    if workload == "quadrotor":
+        return P.quadrotor(B=B, N=N, cls=cls, device=device)
+    if workload == "cartpole":
+        return P.cartpole(B=B, N=N, cls=cls, device=device)
+    if workload == "acrobot":
+        return P.acrobot(B=B, N=N, cls=cls, device=device)
+    raise SystemExit(f"unknown workload {workload}")
+
+
+class ClockSampler(threading.Thread):
+    """samples nvidia-smi clocks / throttle reasons of one GPU while the timed region runs"""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag, self.proc = index, [], False, None
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.index)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                if self.stop_flag:
+                    break
+                self.rows.append([c.strip() for c in line.split(",")])
+        except Exception:
+            pass
+
+    def finish(self):
+        self.stop_flag = True
+        if self.proc:
+            self.proc.terminate()
+        sm = sorted(float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit())
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        reasons = []
+        for i, name in ((3, "hw_slowdown"), (4, "hw_thermal_slowdown"), (5, "sw_thermal_slowdown"), (6, "sw_power_cap")):
+            if any(len(r) > i and r[i].lower().startswith("active") for r in self.rows):
+                reasons.append(name)
+        # only the upper half of the samples are "under load" for short runs
+        load = sm[len(sm) // 2:] if sm else []
+        return {"sm_mhz": (load[len(load) // 2] if load else None), "sm_max_mhz": (max(mx) if mx else None), "reasons": reasons, "samples": len(sm)}
+
+
+class _DevPtr:
+    def __init__(self, ptr, n):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f8", "data": (int(ptr), False), "version": 3}
+
+
+def cpu_oracle_rate(workload, N, threads, target_seconds=4.0, batch_cap=4096):
+    """iLQR instance-iterations/s of the CPU oracle port (all host threads) on a bounded sample of the workload."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_binding as OB
+    import trajopt_b200 as TO
+    lib = OB.load_oracle()
+    lib.orc_set_threads.restype = C.c_int
+    nthr = lib.orc_set_threads(int(threads))
+    B = min(batch_cap, max(64, 8 * nthr))
+    prob = build_problem(workload, B, N, cls=OB.OracleProblem)
+    TO.rollout(prob)
+    TO.ilqr_step(prob, 1)                       # warm-up (page in, first-touch)
+    t0 = time.perf_counter(); TO.ilqr_step(prob, 1); t1 = time.perf_counter() - t0
+    iters = max(1, min(200, int(target_seconds / max(t1, 1e-6))))
+    t0 = time.perf_counter(); TO.ilqr_step(prob, iters); dt = time.perf_counter() - t0
+    prob.close()
+    return {"value": B * iters / dt, "unit": "instance-iterations/s", "cores": nthr, "kind": "port",
+            "sample": f"{B} instances x {iters} iLQR iterations of the same workload ({dt:.2f} s wall, OpenMP over instances, -O3 x86-64-v3)"}, B * iters, dt
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's CPU implementation of the path.  The Julia package cannot run in this image
+    (no Julia, and its RK4 / AD / Riccati live in un-vendored packages), so the arm times the oracle port -- the
+    documented CPU restatement -- on all host threads.  Rank 0 only."""
+    if rank != 0:
+        return
+    w = WORKLOADS[args.workload]
+    N = args.N or w["N"]
+    threads = os.cpu_count() or 1
+    steps_rate, total, wall = [], 0, 0.0
+    for _ in range(max(1, args.warmup) if args.warmup < 2 else 1):
+        cpu_oracle_rate(args.workload, N, threads, target_seconds=1.0)
+    base = None
+    for _ in range(args.steps if args.steps <= 5 else 5):
+        base, n_it, dt = cpu_oracle_rate(args.workload, N, threads, target_seconds=3.0)
+        total += n_it; wall += dt
+    value = total / wall
+    base["value"] = value
+    out = {"impl": "reference", "metric": "ilqr_iterations_per_sec", "value": value, "unit": "instance-iterations/s", "n_gpus": args.gpus,
+           "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * wall / max(1, min(args.steps, 5)), "higher_is_better": True,
+           "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+           "config": {"workload": w["desc"], "batch_per_gpu": args.batch or w["batch"], "N": N,
+                      "note": "CPU arm: oracle port of the reference path (Julia unavailable), bounded sample per step"},
+           "cpu_baseline": base, "e2e": {"value": value, "unit": "instance-iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "gpu_launches": 0}
+    print(json.dumps(out), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="quadrotor", choices=sorted(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=0, help="instances per GPU (default: the workload's BASELINE batch)")
+    ap.add_argument("--N", type=int, default=0, help="knot points (default: the workload's)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        return run_reference(args, rank, world)
+    if args.warmup < 3:
+        args.warmup = 3
+
+    import torch
+    import torch.distributed as dist
+    import trajopt_b200 as TO
+    K = TO.capi
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl b200 needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+    w = WORKLOADS[args.workload]
+    B, N = args.batch or w["batch"], args.N or w["N"]
+    n, m = w["n"], w["m"]
+    prob = build_problem(args.workload, B, N, device=local)
+    lib, h = prob._lib, prob._h
+    stream = torch.cuda.current_stream()
+    K.check(lib, h, lib.to_set_stream(h, C.c_void_p(stream.cuda_stream)))
+    x0_host = torch.from_numpy(prob.x0.copy()).pin_memory()
+    U0_np = TO.controls(prob)
+    U0_host = torch.from_numpy(U0_np.copy()).pin_memory()
+    U_out = torch.empty_like(U0_host).pin_memory()
+    J_out = torch.empty(B, dtype=torch.float64).pin_memory()
+    mptr = C.c_void_p()
+    K.check(lib, h, lib.to_merit_device_ptr(h, C.byref(mptr)))
+    merit2 = torch.as_tensor(_DevPtr(mptr.value, 2), device=f"cuda:{local}")
+
+    def dptr(t):
+        return C.cast(t.data_ptr(), K.c_double_p)
+
+    def reset():
+        K.check(lib, h, lib.to_set_initial_state(h, dptr(x0_host)))
+        K.check(lib, h, lib.to_set_controls(h, dptr(U0_host)))
+        K.check(lib, h, lib.to_rollout(h))
+
+    def step():
+        K.check(lib, h, lib.to_ilqr_step(h, 1))
+        if world > 1:   # the path's only collective: the global merit / violation
+            K.check(lib, h, lib.to_reduce_merit(h))
+            dist.all_reduce(merit2[0:1], op=dist.ReduceOp.SUM)
+            dist.all_reduce(merit2[1:2], op=dist.ReduceOp.MAX)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timing ---------------------------------------------------------------------------------
+    reset()
+    for _ in range(args.warmup):
+        step()
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start(); time.sleep(0.3)
+    barrier()
+    launches0 = lib.to_launch_count(h)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        step()
+    e1.record(stream)
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = lib.to_launch_count(h) - launches0
+    clocks = sampler.finish() if sampler else None
+    tmax = torch.tensor([ms], dtype=torch.float64, device=f"cuda:{local}")
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    ms = float(tmax.item())
+    value = B * world * args.steps / (ms * 1e-3)
+    st = TO.solver_state(prob)
+    accepted_frac = float((st["alpha"] > 0).mean())
+
+    # ---- per-phase timing pass (CUDA events around each kernel on the launching stream) -> roofline -----------------
+    reset()
+    for _ in range(args.warmup):
+        step()
+    lib.to_set_phase_timing(h, 1)
+    pms = (C.c_double * K.PHASE_COUNT)(); pl = (C.c_int64 * K.PHASE_COUNT)()
+    lib.to_get_phase_times(h, pms, pl, 1)
+    for _ in range(args.steps):
+        K.check(lib, h, lib.to_ilqr_step(h, 1))
+    lib.to_get_phase_times(h, pms, pl, 1)
+    lib.to_set_phase_timing(h, 0)
+    phase = {name: (pms[i] / max(1, pl[i])) for name, i in (("expand", K.PHASE_EXPAND), ("backward", K.PHASE_BACKWARD), ("forward", K.PHASE_FORWARD), ("ladder", K.PHASE_LADDER))}
+    E, R, F = C.c_int64(), C.c_int64(), C.c_int64()
+    lib.to_algorithmic_bytes(h, C.byref(E), C.byref(R), C.byref(F))
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak_gbs = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s (B200_PROFILING.md)"
+    r_ms = phase["backward"]
+    achieved = (R.value * B / (r_ms * 1e-3)) / 1e9 if r_ms > 0 else 0.0
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "riccati_traffic.json"))).get(f"{args.workload}_B{B}_N{N}")
+    except Exception:
+        pass
+    roofline = {"kernel": "k_riccati (Riccati backward pass)", "bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
+                "frac": achieved / peak_gbs, "traffic": traffic, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": R.value * B, "avg_launch_ms": r_ms,
+                "phase_ms": phase, "fp64_tflops_riccati": None}
+    # FP64 view of the same kernel: 2 * (T + Qzz + Qz + S-update + solves) FMA per knot, counted analytically
+    nm = n + m
+    fma_knot = n * n * nm + n * nm * (nm + 1) // 2 + n * nm + m * n * (n + 1) // 2 + m * m * (n + 1) + m * m * m // 3
+    roofline["fp64_tflops_riccati"] = (2.0 * fma_knot * (N - 1) * B / (r_ms * 1e-3)) / 1e12 if r_ms > 0 else None
+
+    # ---- end to end through the C ABI with host buffers -------------------------------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        def e2e_step():
+            K.check(lib, h, lib.to_set_initial_state(h, dptr(x0_host)))     # H2D (pinned)
+            K.check(lib, h, lib.to_set_controls(h, dptr(U0_host)))          # H2D (pinned)
+            K.check(lib, h, lib.to_rollout(h))
+            K.check(lib, h, lib.to_ilqr_step(h, 1))
+            K.check(lib, h, lib.to_get_controls(h, dptr(U_out)))            # D2H (syncs)
+            K.check(lib, h, lib.to_merit(h, dptr(J_out)))                   # D2H (syncs)
+        for _ in range(args.warmup):
+            e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record(stream)
+        for _ in range(args.steps):
+            e2e_step()
+        g1.record(stream)
+        barrier()
+        wall_ms = (time.perf_counter() - t0) * 1e3
+        ems = max(g0.elapsed_time(g1), wall_ms)    # the host-blocking copies are part of the step
+        t2 = torch.tensor([ems], dtype=torch.float64, device=f"cuda:{local}")
+        if world > 1:
+            dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+        ems = float(t2.item())
+        e2e = {"value": B * world * args.steps / (ems * 1e-3), "unit": "instance-iterations/s",
+               "h2d_bytes_per_step": int(x0_host.numel() * 8 + U0_host.numel() * 8), "d2h_bytes_per_step": int(U_out.numel() * 8 + J_out.numel() * 8),
+               "ms_per_step": ems / args.steps,
+               "what": "per step: upload x0 + warm-start U (pinned host), rollout, 1 iLQR iteration, download U + merit J"}
+
+    cpu = None
+    if rank == 0 and not args.no_cpu_baseline:
+        try:
+            cpu, _, _ = cpu_oracle_rate(args.workload, N, os.cpu_count() or 1)
+        except Exception as ex:   # the oracle is only the reported baseline; never let it take the GPU number down
+            cpu = {"value": None, "unit": "instance-iterations/s", "cores": 0, "kind": "port", "sample": f"failed: {ex}"}
+
+    if rank == 0:
+        out = {"metric": "ilqr_iterations_per_sec", "value": value, "unit": "instance-iterations/s", "n_gpus": world, "steps": args.steps,
+               "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+               "dtype": "f64", "data": "synthetic",
+               "config": {"workload": w["desc"], "batch_per_gpu": B, "N": N, "global_batch": B * world, "parallelism": f"batch-sharded x{world}",
+                          "step": "1 iLQR iteration = dynamics expansion + Riccati backward pass + forward pass/line search",
+                          "l2": "inputs larger than L2: [A B] alone is %.0f MB per GPU, rewritten and re-read every step" % (B * (N - 1) * n * (nm + nm % 2) * 8 / 1e6),
+                          "batch_iterations_per_s": args.steps / (ms * 1e-3), "accepted_fraction_last_step": accepted_frac},
+               "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu}
+        print(json.dumps(out), flush=True)
+    prob.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,209 @@
+"""GPU parity tests (`-m gpu`): every kernel of the hot path, called through the C ABI, against the CPU oracle
+on identical seeded inputs.  Tolerances (fp64, north_star "stated fp64 tolerance"): 1e-10 relative per kernel
+(reduction / FMA-contraction order differs), 1e-8 after full iLQR iterations."""
+import numpy as np
+import pytest
+
+import trajopt_b200 as TO
+from oracle_binding import OracleProblem, oracle_grad_projection, oracle_hess_projection, oracle_projection
+
+pytestmark = pytest.mark.gpu
+P = TO.problems
+
+KERNEL_RTOL = 1e-10
+ITER_RTOL = 1e-8
+
+
+def close(a, b, rtol, what=""):
+    a, b = np.asarray(a), np.asarray(b)
+    scale = max(1.0, float(np.max(np.abs(b)))) if b.size else 1.0
+    err = float(np.max(np.abs(a - b))) if b.size else 0.0
+    assert np.all(np.isfinite(a)) or not np.all(np.isfinite(b)), f"{what}: non-finite GPU result"
+    assert err <= rtol * scale, f"{what}: max abs err {err:.3e} > {rtol:.0e} * {scale:.3e}"
+
+
+CONFIGS = {
+    "double_integrator_1d": lambda cls: P.double_integrator(B=3, N=51, dim=1, cls=cls),
+    "double_integrator_2d": lambda cls: P.double_integrator(B=2, N=21, dim=2, cls=cls),
+    "cartpole": lambda cls: P.cartpole(B=37, N=101, cls=cls),
+    "cartpole_altro": lambda cls: P.cartpole(B=5, N=101, cls=cls, u_bound=3.0, goal=True, dt_scaled_cost=True),
+    "quadrotor": lambda cls: P.quadrotor(B=33, N=101, cls=cls),
+    "quadrotor_short": lambda cls: P.quadrotor(B=4, N=4, cls=cls),
+    "acrobot_dense": lambda cls: P.acrobot(B=9, N=201, cls=cls, dense_cost=True),
+    "acrobot_diag": lambda cls: P.acrobot(B=3, N=51, cls=cls, dense_cost=False),
+}
+
+
+@pytest.fixture(params=sorted(CONFIGS))
+def pair(request):
+    g, o = CONFIGS[request.param](TO.Problem), CONFIGS[request.param](OracleProblem)
+    yield g, o
+    g.close(); o.close()
+
+
+def test_rollout_cost_constraints(pair):
+    g, o = pair
+    for p in pair:
+        TO.rollout(p)
+    close(TO.states(g), TO.states(o), KERNEL_RTOL, "rollout X")
+    close(TO.controls(g), TO.controls(o), 0.0, "controls round trip")
+    close(TO.cost_knots(g), TO.cost_knots(o), KERNEL_RTOL, "cost knots")
+    close(TO.cost(g), TO.cost(o), KERNEL_RTOL, "cost")
+    close(TO.cost_gradient(g), TO.cost_gradient(o), KERNEL_RTOL, "cost gradient")
+    close(TO.cost_hessian(g), TO.cost_hessian(o), KERNEL_RTOL, "cost hessian")
+    assert np.array_equal(TO.num_constraints(g), TO.num_constraints(o))
+    for i in range(len(g.constraints)):
+        close(TO.evaluate_constraints(g, i), TO.evaluate_constraints(o, i), KERNEL_RTOL, f"constraint {i} values")
+        close(TO.constraint_jacobians(g, i), TO.constraint_jacobians(o, i), KERNEL_RTOL, f"constraint {i} jacobians")
+    close(TO.max_violation(g), TO.max_violation(o), KERNEL_RTOL, "max violation")
+    close(TO.merit(g), TO.merit(o), KERNEL_RTOL, "merit")
+    gg, gh = TO.al_expansion(g)
+    og, oh = TO.al_expansion(o)
+    close(gg, og, KERNEL_RTOL, "AL gradient"); close(gh, oh, KERNEL_RTOL, "AL hessian")
+
+
+def test_expansion_backward_forward(pair):
+    g, o = pair
+    for p in pair:
+        TO.rollout(p); TO.expand(p)
+    close(TO.dynamics_jacobians(g), TO.dynamics_jacobians(o), KERNEL_RTOL, "[A B]")
+    sg, so = TO.backward(g), TO.backward(o)
+    assert np.array_equal(sg, so)
+    Kg, dg = TO.gains(g); Ko, do = TO.gains(o)
+    close(Kg, Ko, 1e-9, "K"); close(dg, do, 1e-9, "d")
+    close(TO.solver_state(g)["dV"], TO.solver_state(o)["dV"], 1e-9, "dV")
+    Jg, ag = TO.forward(g); Jo, ao = TO.forward(o)
+    assert np.array_equal(ag, ao), "accepted step sizes differ"
+    close(Jg, Jo, 1e-9, "J after forward pass")
+    close(TO.states(g), TO.states(o), 1e-9, "X after forward pass")
+    close(TO.controls(g), TO.controls(o), 1e-9, "U after forward pass")
+    assert np.array_equal(TO.solver_state(g)["ls_iters"], TO.solver_state(o)["ls_iters"])
+
+
+def test_ilqr_iterations_and_al_update(pair):
+    g, o = pair
+    for p in pair:
+        TO.rollout(p)
+        TO.ilqr_step(p, 3)
+    close(TO.merit(g), TO.merit(o), ITER_RTOL, "merit after 3 iterations")
+    close(TO.states(g), TO.states(o), 1e-7, "X after 3 iterations")
+    close(TO.controls(g), TO.controls(o), 1e-7, "U after 3 iterations")
+    for k in ("alpha", "ls_iters", "bp_status"):
+        assert np.array_equal(TO.solver_state(g)[k], TO.solver_state(o)[k]), k
+    close(TO.solver_state(g)["rho"], TO.solver_state(o)["rho"], 1e-12, "rho")
+    if len(g.constraints):
+        for p in pair:
+            TO.al_update(p)
+        for i in range(len(g.constraints)):
+            close(TO.multipliers(g, i), TO.multipliers(o, i), 1e-7, f"multipliers {i}")
+            assert TO.penalty(g, i) == TO.penalty(o, i)
+        for p in pair:
+            TO.ilqr_step(p, 2)
+        close(TO.merit(g), TO.merit(o), 1e-7, "merit after AL update + 2 iterations")
+        close(TO.max_violation(g), TO.max_violation(o), 1e-7, "violation")
+
+
+def test_regularisation_restart_matches_oracle():
+    n, m, N = 4, 1, 11
+    stage = TO.DiagonalCost(np.ones(n), -0.5 * np.ones(m))
+    term = TO.DiagonalCost(np.ones(n), -0.5 * np.ones(m), terminal=True)
+    probs = [cls(TO.Cartpole(), TO.Objective(stage, term, N), np.array([[0, 0.1, 0, 0], [0, -0.2, 0.1, 0]]), 0.5) for cls in (TO.Problem, OracleProblem)]
+    for p in probs:
+        TO.rollout(p); TO.expand(p)
+    sg, so = TO.backward(probs[0]), TO.backward(probs[1])
+    assert np.array_equal(sg, so) and np.all(sg > 0)
+    close(TO.solver_state(probs[0])["rho"], TO.solver_state(probs[1])["rho"], 1e-12, "rho")
+    Kg, dg = TO.gains(probs[0]); Ko, do = TO.gains(probs[1])
+    close(Kg, Ko, 1e-9, "K"); close(dg, do, 1e-9, "d")
+
+
+def test_line_search_backtracking_matches_oracle():
+    """a poor initial guess forces alpha < 1 on some instances: the parallel ladder must pick the same step."""
+    probs = [P.cartpole(B=16, N=101, cls=cls) for cls in (TO.Problem, OracleProblem)]
+    for p in probs:
+        TO.rollout(p)
+        TO.ilqr_step(p, 6)
+    sg, so = TO.solver_state(probs[0]), TO.solver_state(probs[1])
+    assert np.array_equal(sg["alpha"], so["alpha"]) and np.array_equal(sg["ls_iters"], so["ls_iters"])
+    assert np.any(so["ls_iters"] > 1)
+    close(TO.merit(probs[0]), TO.merit(probs[1]), ITER_RTOL, "merit")
+
+
+def test_cones_match_oracle_and_reference_kats():
+    r = np.random.default_rng(1)
+    pts = np.array([[2, 3, 1, 1.0], [2, 3, 1, -10.0], [2, 3, 1, 10.0]])   # test/cone_tests.jl:51,58,64
+    x = np.vstack([pts, r.standard_normal((200, 4)) * 2])
+    b = r.standard_normal(x.shape)
+    for cone in (TO.SecondOrderCone(), TO.NegativeOrthant(), TO.ZeroCone(), TO.IdentityCone(), TO.PositiveOrthant()):
+        close(TO.projection(cone, x), oracle_projection(cone, x)[0], 1e-14, f"projection {cone}")
+        close(TO.grad_projection(cone, x), oracle_grad_projection(cone, x)[0], 1e-13, f"grad projection {cone}")
+        close(TO.hess_projection(cone, x, b), oracle_hess_projection(cone, x, b)[0], 1e-12, f"hess projection {cone}")
+    assert np.array_equal(TO.projection(TO.Inequality(), np.array([1, 2, -3.0])), [0, 0, -3.0])   # test/cone_tests.jl:70-75
+
+
+def test_evaluation_only_constraints_and_quickstart_problem():
+    """the full examples/quickstart.jl problem (Goal + Circle + SOC norm + bounds) evaluates on the device; the solver
+    kernels reject the non Goal/Bound kinds loudly."""
+    r = np.random.default_rng(1)
+    model = TO.DoubleIntegrator(2)
+    n, m, N = 4, 2, 21
+    xf = np.array([0, 2.0, 0, 0])
+    obj = TO.LQRObjective(np.eye(n), np.eye(m), np.eye(n) * (N - 1), xf, N)
+    U0 = r.standard_normal((N - 1, m))
+    probs = []
+    for cls in (TO.Problem, OracleProblem):
+        cons = TO.ConstraintList(n, m, N)
+        TO.add_constraint(cons, TO.GoalConstraint(xf), N)
+        TO.add_constraint(cons, TO.CircleConstraint(n, [0.0], [1.0], [0.5]), (2, N - 1))
+        TO.add_constraint(cons, TO.NormConstraint(n, m, 5.0, TO.SecondOrderCone(), "control"), (1, N - 1))
+        TO.add_constraint(cons, TO.BoundConstraint(n, m, u_min=-10, u_max=10), (1, N - 1))
+        p = cls(model, obj, np.zeros(n), 3.0, xf=xf, constraints=cons)
+        TO.initial_controls(p, U0); TO.rollout(p)
+        probs.append(p)
+    g, o = probs
+    for i in range(4):
+        close(TO.evaluate_constraints(g, i), TO.evaluate_constraints(o, i), KERNEL_RTOL, f"values {i}")
+        close(TO.constraint_jacobians(g, i), TO.constraint_jacobians(o, i), KERNEL_RTOL, f"jacobians {i}")
+    close(TO.merit(g), TO.merit(o), KERNEL_RTOL, "merit with SOC penalty")
+    close(TO.max_violation(g), TO.max_violation(o), KERNEL_RTOL, "violation")
+    gg, gh = TO.al_expansion(g); og, oh = TO.al_expansion(o)
+    close(gg, og, KERNEL_RTOL, "AL gradient"); close(gh, oh, KERNEL_RTOL, "AL hessian")
+    with pytest.raises(TO.TrajOptError):
+        TO.ilqr_step(g, 1)
+
+
+def test_error_behaviour():
+    n, m, N = 4, 1, 5
+    obj = TO.LQRObjective(np.eye(n), np.eye(m), np.eye(n), np.zeros(n), N)
+    with pytest.raises(TO.DimensionMismatch):       # src/problem.jl:64-68
+        TO.Problem(TO.Quadrotor(), obj, np.zeros(13), 1.0)
+    with pytest.raises(TO.ArgumentError):           # src/problem.jl:87-91
+        TO.Problem(TO.Cartpole(), obj, np.zeros(n), 1.0, x0=np.zeros(n))
+    prob = TO.Problem(TO.Cartpole(), obj, np.zeros(n), 1.0)
+    assert np.isnan(TO.states(prob)).all() and not TO.controls(prob).any()   # X0 = NaN, U0 = 0 (src/problem.jl:83-84)
+    with pytest.raises(TO.TrajOptError):
+        TO.backward(prob)                           # backward pass before the expansion
+    with pytest.raises(TO.DimensionMismatch):
+        TO.initial_controls(prob, np.zeros((3, 7)))
+
+
+def test_full_size_properties_quadrotor():
+    """BASELINE full size (B=4096, N=101): size-independent properties instead of an element-wise oracle run:
+    hover invariance, batch permutation equivariance, merit monotonicity, cost = sum of knot costs."""
+    B = 4096
+    prob = P.quadrotor(B=B, N=101)
+    TO.rollout(prob)
+    J0 = TO.merit(prob)
+    assert np.allclose(TO.cost_knots(prob).sum(axis=1), TO.cost(prob), rtol=1e-12)
+    TO.ilqr_step(prob, 2)
+    J2 = TO.merit(prob)
+    assert np.all(J2 <= J0 + 1e-9) and np.all(TO.solver_state(prob)["bp_status"] >= 0)
+    # permutation equivariance: the same instances in reversed order give the reversed result
+    prob2 = P.quadrotor(B=B, N=101)
+    TO.set_initial_state(prob2, prob2.x0[::-1]); TO.initial_controls(prob2, TO.controls(prob2)[::-1])
+    TO.rollout(prob2); TO.ilqr_step(prob2, 2)
+    assert np.allclose(TO.merit(prob2)[::-1], J2, rtol=1e-12)
+    # hover: x0 with hover controls stays put (test/internal_api.jl:50-56)
+    x0 = np.array([1, 2, 1, 1, 0, 0, 0, 0, 0, 0, 0, 0, 0.0])
+    TO.set_initial_state(prob, x0); TO.initial_controls(prob, TO.Quadrotor().hover_control()); TO.rollout(prob)
+    assert np.allclose(TO.states(prob)[:, -1], x0, rtol=1.5e-8)

@@ -10,3 +10,4 @@ root (``import trajopt_b200 as TO``).  Layout:
 """
 from .api import *  # noqa: F401,F403
 from . import _capi  # noqa: F401
+from . import problems  # noqa: F401,E402

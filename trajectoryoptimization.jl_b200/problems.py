@@ -1,0 +1,124 @@
+"""The benchmark / parity problem set of BASELINE.json, built through the mirror API with deterministic
+synthetic inputs (seed 1 like the reference's test/runtests.jl:13, NumPy PCG64).
+
+Every builder takes ``cls`` (the Problem class to instantiate) so the tests can build the identical problem
+on the CPU oracle; the default is the CUDA-backed ``Problem``.
+"""
+import numpy as np
+
+from . import api as TO
+
+
+def _rng(seed):
+    return np.random.default_rng(seed)
+
+
+def double_integrator(B=1, N=21, dim=2, seed=1, cls=None, constrained=True, **kw):
+    """examples/quickstart.jl:28-64 (dim=2: n=4, m=2, N=21, tf=3) or the 1-D variant of BASELINE.json configs[0]
+    (dim=1: n=2, m=1, N=51).  Goal + control bounds (the solver kernels take Goal/Bound constraints)."""
+    cls = cls or TO.Problem
+    model = TO.DoubleIntegrator(dim)
+    n, m = model.dims()
+    tf = 3.0
+    xf = np.zeros(n); xf[dim - 1] = 2.0
+    obj = TO.LQRObjective(np.eye(n), np.eye(m), np.eye(n) * (N - 1), xf, N)
+    cons = TO.ConstraintList(n, m, N)
+    if constrained:
+        TO.add_constraint(cons, TO.GoalConstraint(xf), N)
+        TO.add_constraint(cons, TO.BoundConstraint(n, m, u_min=-10, u_max=10), (1, N - 1))
+    r = _rng(seed)
+    prob = cls(model, obj, np.zeros(n), tf, xf=xf, constraints=cons, batch=B, **kw)
+    TO.initial_controls(prob, r.standard_normal((B, N - 1, m)))
+    return prob
+
+
+def cartpole(B=1024, N=101, seed=1, cls=None, u_bound=None, goal=False, dt_scaled_cost=False, **kw):
+    """Cartpole swing-up, examples/Cartpole.ipynb:82-83,123-125,187: Q=1e-2 I, R=1e-1 I, Qf=100 I, tf=5,
+    x0=0, xf=(0,pi,0,0), U0=0.01; batch: x0_b += N(0,0.1^2) on (y,theta), U0_b += N(0,0.01^2).
+    Unconstrained by default (BASELINE configs[1]); u_bound=3 + goal=True gives the notebook's ALTRO problem.
+    ``dt_scaled_cost`` multiplies Q and R by dt: the notebook's outputs were saved with TrajectoryOptimization v0.3,
+    whose stage costs were integrated with dt; v0.7.1 (the reference) sums them unscaled (src/objective.jl:104-106)."""
+    cls = cls or TO.Problem
+    model = TO.Cartpole()
+    n, m = 4, 1
+    xf = np.array([0, np.pi, 0, 0])
+    sc = 5.0 / (N - 1) if dt_scaled_cost else 1.0
+    obj = TO.LQRObjective(1e-2 * sc * np.eye(n), 1e-1 * sc * np.eye(m), 100.0 * np.eye(n), xf, N)
+    cons = TO.ConstraintList(n, m, N)
+    if u_bound is not None:
+        TO.add_constraint(cons, TO.BoundConstraint(n, m, u_min=-u_bound, u_max=u_bound), (1, N - 1))
+    if goal:
+        TO.add_constraint(cons, TO.GoalConstraint(xf), N)
+    r = _rng(seed)
+    x0 = np.zeros((B, n))
+    U0 = np.full((B, N - 1, m), 0.01)
+    if B > 1:
+        x0[:, :2] += 0.1 * r.standard_normal((B, 2))
+        U0 += 0.01 * r.standard_normal((B, N - 1, m))
+    prob = cls(model, obj, x0, 5.0, xf=xf, constraints=cons, **kw)
+    TO.initial_controls(prob, U0)
+    return prob
+
+
+def quadrotor(B=4096, N=101, seed=1, cls=None, constrained=True, dt=None, **kw):
+    """Quadrotor point-to-point, test/internal_api.jl:20-34: Q=.1 I, R=.01 I, Qf=100 I, x0=[1,2,1;1,0,0,0;0;0],
+    xf=[0,0,2;1,0,0,0;0;0], u in [0,10] at 1..N-1, Goal(xf) at N, tf=5; U0 = hover + N(0,0.05^2);
+    batch: r0_b = r0 + U(-1,1)^3.  ``dt`` fixes the step (MPC sweep: dt = .05 for every N)."""
+    cls = cls or TO.Problem
+    model = TO.Quadrotor()
+    n, m = 13, 4
+    x0 = np.array([1, 2, 1, 1, 0, 0, 0, 0, 0, 0, 0, 0, 0.0])
+    xf = np.array([0, 0, 2, 1, 0, 0, 0, 0, 0, 0, 0, 0, 0.0])
+    obj = TO.LQRObjective(np.full(n, 0.1), np.full(m, 0.01), np.full(n, 100.0), xf, N)
+    cons = TO.ConstraintList(n, m, N)
+    if constrained:
+        TO.add_constraint(cons, TO.BoundConstraint(n, m, u_min=np.zeros(4), u_max=np.full(4, 10.0)), (1, N - 1))
+        TO.add_constraint(cons, TO.GoalConstraint(xf), N)
+    r = _rng(seed)
+    x0b = np.broadcast_to(x0, (B, n)).copy()
+    if B > 1:
+        x0b[:, :3] += r.uniform(-1, 1, (B, 3))
+    U0 = model.hover_control()[None, None, :] + 0.05 * r.standard_normal((B, N - 1, m))
+    tf = 5.0 if dt is None else dt * (N - 1)
+    prob = cls(model, obj, x0b, tf, xf=xf, constraints=cons, **kw)
+    TO.initial_controls(prob, U0)
+    return prob
+
+
+def acrobot(B=8192, N=201, seed=1, cls=None, dense_cost=True, **kw):
+    """Acrobot swing-up (no in-reference definition; RobotZoo defaults): x0=(-pi/2,0,0,0) -> xf=(pi/2,0,0,0), tf=10,
+    Q=I, R=.01, Qf=100 I, |u|<=15 + goal, AL on.  ``dense_cost`` uses a QuadraticCost with a small x-u cross term so
+    the full second-order cost expansion (BASELINE configs[3]) is exercised."""
+    cls = cls or TO.Problem
+    model = TO.Acrobot()
+    n, m = 4, 1
+    x0 = np.array([-np.pi / 2, 0, 0, 0]); xf = np.array([np.pi / 2, 0, 0, 0])
+    Q, R, Qf = np.eye(n), 0.01 * np.eye(m), 100.0 * np.eye(n)
+    if dense_cost:
+        Q = Q + 0.05 * (np.ones((n, n)) - np.eye(n))
+        H = 0.01 * np.ones((m, n))
+        stage = TO.QuadraticCost(Q, R, H=H, q=-Q @ xf, r=-H @ xf, c=0.5 * xf @ Q @ xf)
+        term = TO.QuadraticCost(Qf, R, q=-Qf @ xf, c=0.5 * xf @ Qf @ xf, terminal=True)
+        obj = TO.Objective(stage, term, N)
+    else:
+        obj = TO.LQRObjective(Q, R, Qf, xf, N)
+    cons = TO.ConstraintList(n, m, N)
+    TO.add_constraint(cons, TO.BoundConstraint(n, m, u_min=-15.0, u_max=15.0), (1, N - 1))
+    TO.add_constraint(cons, TO.GoalConstraint(xf), N)
+    r = _rng(seed)
+    x0b = np.broadcast_to(x0, (B, n)).copy()
+    U0 = np.zeros((B, N - 1, m))
+    if B > 1:
+        x0b[:, :2] += 0.05 * r.standard_normal((B, 2))
+        U0 += 0.1 * r.standard_normal((B, N - 1, m))
+    prob = cls(model, obj, x0b, 10.0, xf=xf, constraints=cons, **kw)
+    TO.initial_controls(prob, U0)
+    return prob
+
+
+CONFIGS = {
+    "double_integrator": double_integrator,
+    "cartpole": cartpole,
+    "quadrotor": quadrotor,
+    "acrobot": acrobot,
+}

@@ -488,15 +488,24 @@ class Problem:
     reference (src/problem.jl:83-84).
     """
 
-    def __init__(self, model, obj, x0, tf, xf=None, constraints=None, t0=0.0, X0=None, U0=None, dt=None, batch=None, device=0, **kwargs):
+    def __init__(self, model, obj, *args, xf=None, constraints=None, t0=0.0, X0=None, U0=None, dt=None, batch=None, device=0, **kwargs):
         if "x0" in kwargs:   # src/problem.jl:87-91
             raise ArgumentError("Cannot pass x0 as a keyword argument. It is now a positional argument, and xf is a keyword argument.")
+        if kwargs:
+            raise ArgumentError(f"unknown keyword arguments {sorted(kwargs)}")
+        if len(args) != 2:
+            raise ArgumentError("Problem(model, obj, x0, tf; xf, constraints, ...) takes x0 and tf positionally")
+        x0, tf = args
         n, m = model.dims()
         N = len(obj)
         x0 = np.asarray(x0, dtype=float)
         B = int(batch) if batch is not None else (x0.shape[0] if x0.ndim == 2 else 1)
         if x0.shape[-1] != n:
             raise DimensionMismatch("x0 does not match the model's state dimension")   # @assert src/problem.jl:48
+        if obj.dims()[0] != n:
+            raise DimensionMismatch("Objective state dimensions don't match model.")      # src/problem.jl:67
+        if obj.dims()[1] != m:
+            raise DimensionMismatch("Objective control dimensions don't match model.")    # src/problem.jl:68
         cons = constraints if constraints is not None else ConstraintList(n, m, N)
         if (cons.n, cons.m) != (n, m):
             raise DimensionMismatch("Constraint state dimensions don't match model")   # src/problem.jl:64-65

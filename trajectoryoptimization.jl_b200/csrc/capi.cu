@@ -124,7 +124,7 @@ void set_default_options(DevOptions& o) {
 void model_defaults(int model, int m, int& n_out, int& m_out, double* p) {
     for (int i = 0; i < 16; i++) p[i] = 0;
     switch (model) {
-        case TO_MODEL_DOUBLE_INTEGRATOR: n_out = 2 * m; m_out = m; p[0] = 1.0; break;
+        case TO_MODEL_DOUBLE_INTEGRATOR: n_out = 2 * m; m_out = m; p[0] = 1.0; break;   // p[1] = 1/mass is filled by to_create
         case TO_MODEL_CARTPOLE: n_out = 4; m_out = 1; p[0] = 1.0; p[1] = 0.2; p[2] = 0.5; p[3] = 9.81; break;
         case TO_MODEL_QUADROTOR:
             n_out = 13; m_out = 4; p[0] = 0.5; p[1] = 0.0023; p[2] = 0.0023; p[3] = 0.004; p[4] = 0; p[5] = 0; p[6] = -9.81;
@@ -257,7 +257,11 @@ int to_create(const to_spec* s, to_handle** out) {
     if (!s->dt || !s->costs || !s->cost_index || s->ncost < 1) return fail(nullptr, TO_EINVAL, "null dt / costs / cost_index");
     if (s->ncon < 0 || s->ncon > TO_MAXCON || (s->ncon > 0 && !s->cons)) return fail(nullptr, TO_EINVAL, "too many constraints (max 8) or null list");
     for (int k = 0; k < s->N - 1; k++) if (!(s->dt[k] > 0)) return fail(nullptr, TO_EINVAL, "time steps must be positive");   // tf > t0, src/problem.jl:50
-    if (s->params) for (int i = 0; i < s->nparams && i < 16; i++) params[i] = s->params[i];
+    if (s->params) for (int i = 0; i < s->nparams && i < 10; i++) params[i] = s->params[i];
+    if (s->model == TO_MODEL_DOUBLE_INTEGRATOR) params[1] = 1.0 / params[0];
+    if (s->model == TO_MODEL_QUADROTOR) {   // reciprocals used by the device dynamics (models.cuh)
+        params[10] = 1.0 / params[0]; params[11] = 1.0 / params[1]; params[12] = 1.0 / params[2]; params[13] = 1.0 / params[3];
+    }
 
     auto* h = new to_handle();
     h->device = s->device;
@@ -267,7 +271,8 @@ int to_create(const to_spec* s, to_handle** out) {
     h->own_stream = true;
     DevProblem& P = h->P;
     P.model = s->model; P.n = mn; P.m = mm; P.N = s->N; P.B = s->B;
-    P.ldab = (mn + mm + 1) & ~1;
+    // row stride of [A B]: even (16-byte rows); 20 (= 4 mod 16) for the tensor-MMA Riccati path (n >= 8), see riccati.cu
+    P.ldab = (mn >= 8 && mn <= 16 && mn + mm + 1 <= 20) ? 20 : ((mn + mm + 1) & ~1);
     std::memcpy(P.params, params, sizeof(params));
     set_default_options(P.opt);
     h->t0 = s->t0;
@@ -293,6 +298,17 @@ int to_create(const to_spec* s, to_handle** out) {
         if (!h->h_cons[i].diagonal) P.all_diag_con = 0;
     }
     P.ncost = s->ncost; P.ncon = s->ncon;
+    P.max_p_knot = 0; P.max_terms_per_z = 0;
+    for (int j = 0; j < n + m; j++) {
+        int cnt = 0;
+        for (const auto& c : h->h_cons) if (c.diagonal) cnt += (c.row_max[j] >= 0) + (c.kind == CON_BOUND && c.row_min[j] >= 0);
+        P.max_terms_per_z = std::max(P.max_terms_per_z, cnt);
+    }
+    for (int k = 1; k <= N; k++) {
+        int pk = 0;
+        for (const auto& c : h->h_cons) if (k >= c.first && k <= c.last) pk += c.p;
+        P.max_p_knot = std::max(P.max_p_knot, pk);
+    }
     h->h_mu.assign(s->ncon, P.opt.penalty_initial);
     h->h_dt.assign(s->dt, s->dt + (N - 1));
 
@@ -302,7 +318,7 @@ int to_create(const to_spec* s, to_handle** out) {
 #define ALLOC(ptr, count) if (!rc) rc = dalloc(h, &(ptr), (size_t)(count))
     ALLOC(d_dt, N - 1); ALLOC(d_ci, N);
     ALLOC(h->d_costs, s->ncost); ALLOC(h->d_cons, std::max(1, s->ncon)); ALLOC(h->d_mu, std::max(1, s->ncon));
-    ALLOC(P.x0, (size_t)B * n); ALLOC(P.X, 2 * P.strideX); ALLOC(P.U, 2 * P.strideU); ALLOC(P.cur, B);
+    ALLOC(P.x0, (size_t)B * n); ALLOC(P.X, TO_NBUF * P.strideX); ALLOC(P.U, TO_NBUF * P.strideU); ALLOC(P.cur, B);
     ALLOC(P.AB, (size_t)B * (N - 1) * n * P.ldab); ALLOC(P.K, (size_t)B * (N - 1) * n * m); ALLOC(P.d, (size_t)B * (N - 1) * m);
     ALLOC(P.lambda, (size_t)B * std::max(1, P.lambda_len));
     ALLOC(P.rho, B); ALLOC(P.drho, B); ALLOC(P.dV, 2 * (size_t)B); ALLOC(P.J, B); ALLOC(P.Jc, B); ALLOC(P.alpha, B);
@@ -317,8 +333,8 @@ int to_create(const to_spec* s, to_handle** out) {
     okc &= cudaMemcpyAsync(d_dt, h->h_dt.data(), sizeof(double) * (N - 1), cudaMemcpyHostToDevice, st) == cudaSuccess;
     okc &= cudaMemcpyAsync(d_ci, h->h_cost_index.data(), sizeof(int) * N, cudaMemcpyHostToDevice, st) == cudaSuccess;
     okc &= cudaMemsetAsync(P.x0, 0, sizeof(double) * B * n, st) == cudaSuccess;
-    okc &= cudaMemsetAsync(P.X, 0xFF, sizeof(double) * 2 * P.strideX, st) == cudaSuccess;   // NaN: X0 = NaN until rollout!, src/problem.jl:83
-    okc &= cudaMemsetAsync(P.U, 0, sizeof(double) * 2 * P.strideU, st) == cudaSuccess;      // U0 = 0, src/problem.jl:84
+    okc &= cudaMemsetAsync(P.X, 0xFF, sizeof(double) * TO_NBUF * P.strideX, st) == cudaSuccess;   // NaN: X0 = NaN until rollout!, src/problem.jl:83
+    okc &= cudaMemsetAsync(P.U, 0, sizeof(double) * TO_NBUF * P.strideU, st) == cudaSuccess;      // U0 = 0, src/problem.jl:84
     okc &= cudaMemsetAsync(P.cur, 0, sizeof(int) * B, st) == cudaSuccess;
     okc &= cudaMemsetAsync(P.AB, 0, sizeof(double) * (size_t)B * (N - 1) * n * P.ldab, st) == cudaSuccess;
     okc &= cudaMemsetAsync(P.K, 0, sizeof(double) * (size_t)B * (N - 1) * n * m, st) == cudaSuccess;
@@ -627,10 +643,11 @@ static int do_backward(to_handle* h) {
     return TO_OK;
 }
 static int do_forward(to_handle* h) {
-    { PhaseScope ps(h, TO_PHASE_FORWARD); CU(h, launch_forward(h->P, h->stream)); }
+    { PhaseScope ps(h, TO_PHASE_FORWARD); CU(h, launch_forward(h->P, h->stream)); }   // trials alpha = 1 .. 1/8
     h->launches++; h->phase_launches[TO_PHASE_FORWARD]++;
-    { PhaseScope ps(h, TO_PHASE_LADDER); CU(h, launch_ladder(h->P, h->stream)); }
+    { PhaseScope ps(h, TO_PHASE_LADDER); CU(h, launch_ladder(h->P, h->stream)); }     // remaining trials + commit of failures
     h->launches++; h->phase_launches[TO_PHASE_LADDER]++;
+
     h->expanded = false; h->backward_done = false;   // the trajectory moved
     return TO_OK;
 }

@@ -2,8 +2,8 @@
 //
 // Data layout in HBM (all fp64, instance-major so one instance's per-knot blocks are contiguous and can be
 // streamed with 1-D bulk TMA copies by the warp that owns the instance):
-//   X   [2][B][N][n]          double-buffered trajectory (cur[b] selects the live buffer; the forward pass
-//   U   [2][B][N-1][m]        writes its candidate into the other buffer and acceptance flips cur[b])
+//   X   [NBUF][B][N][n]       trajectory ring (cur[b] selects the live buffer; the line search writes the candidate
+//   U   [NBUF][B][N-1][m]     of trial j into buffer (cur[b]+1+j) % NBUF and acceptance just moves cur[b])
 //   AB  [B][N-1][n][LDAB]     discrete dynamics Jacobian [A B], ROW-major, row stride LDAB = n+m rounded up to
 //                             even (16-byte rows for bulk copies / LDS.128); pad column = 0
 //   K   [B][N-1][n][m]        feedback gains, m x n column-major (Julia layout)      d [B][N-1][m]
@@ -18,6 +18,7 @@
 #define TO_MAXCON 8
 #define TO_MAXP 32          // rows of one constraint at one knot
 #define TO_CON_A 256
+#define TO_NBUF 9            // trajectory buffers per instance: the live one + 8 line-search candidates
 
 // reference enums (mirrors include/trajopt_b200.h)
 enum { MODEL_DOUBLE_INTEGRATOR = 0, MODEL_CARTPOLE = 1, MODEL_QUADROTOR = 2, MODEL_ACROBOT = 3 };
@@ -68,7 +69,9 @@ struct DevProblem {
     int ncost, ncon, lambda_len;
     int all_diag_cost;        // every cost is a DiagonalCost
     int all_diag_con;         // every constraint is Goal/Bound
-    int pad0;
+    int max_p_knot;           // largest number of constraint rows active at one knot
+    int max_terms_per_z;      // largest number of Goal/Bound rows acting on one z entry
+    int pad1;
     double params[16];
     DevOptions opt;
     const double* dt;         // [N-1]
@@ -77,9 +80,9 @@ struct DevProblem {
     const DevCon* cons;       // [ncon]
     const double* mu;         // [ncon] penalties
     double* x0;               // [B][n]
-    double* X;                // [2][B][N][n]
-    double* U;                // [2][B][N-1][m]
-    int* cur;                 // [B] live trajectory buffer (0/1)
+    double* X;                // [NBUF][B][N][n]
+    double* U;                // [NBUF][B][N-1][m]
+    int* cur;                 // [B] live trajectory buffer (0..NBUF-1)
     double* AB;               // [B][N-1][n][ldab]
     double* K;                // [B][N-1][n][m]
     double* d;                // [B][N-1][m]

@@ -9,30 +9,285 @@
 //     accept the first alpha in 1, 1/2, ..., 2^-ls_iters with  lower < z <= upper  or  J < J_prev.
 // The line search is per instance (no communication).
 //
-// B200 mapping: the recursion is serial in k and an instance has no parallelism worth a warp, so
-//   k_forward : one thread per instance tries alpha = 1 (the common case) and writes the candidate trajectory
-//               into the instance's spare trajectory buffer;
-//   k_ladder  : 16 lanes per instance; for instances that rejected alpha = 1 each lane evaluates one of the
-//               remaining step sizes concurrently (same latency as one trial), a ballot picks the first
-//               acceptable one -- exactly the sequential backtracking result -- and that lane re-runs its
-//               rollout storing the trajectory.  Lane 0 of every group then commits the instance: flip the
-//               live buffer + J on acceptance, regularisation increase on failure.
+// B200 mapping.  The recursion is serial in k and one rollout has no parallelism worth a warp, so the kernel is
+// bound by the LATENCY of the per-knot dependency chain (feedback -> 4 dynamics evaluations -> next knot).  Two
+// things follow:
+//   * backtracking trials are evaluated CONCURRENTLY: a group of G lanes owns one instance and lane j rolls out
+//     step size 2^-(trial0+j), writing its candidate into trajectory buffer (cur+1+j) % NBUF.  A ballot picks the
+//     first acceptable lane -- exactly the sequential backtracking result -- and acceptance only moves cur[b]
+//     (no copy).  Pass 1 (G=4: alpha = 1..1/8) covers ~95% of the instances, pass 2 (G=8) the remaining trials and
+//     commits failures (regularisation increase, Altro's bp_reg_fp).
+//   * everything off the chain is kept off it: the group's per-knot operands (K_k, d_k, x_k, u_k, lambda_k, ~650 B,
+//     identical for all lanes of the group) are prefetched one knot ahead with cp.async (LDGSTS) by the lanes
+//     cooperatively into a double-buffered shared-memory stage and read back as broadcasts; cost / constraint
+//     descriptors are copied once per CTA into shared memory; x, u live in registers; no fp64 division on the chain.
 #include "costcon.cuh"
 #include "kernels.h"
 #include "models.cuh"
 
 namespace {
 
-// closed-loop rollout of one instance for step size alpha; returns the merit, `ok` = no blow-up.
-// STORE: write the candidate trajectory.  FAST: diagonal costs + Goal/Bound constraints with x,u in registers.
-template <int MODEL, bool STORE, bool FAST>
-__device__ __forceinline__ double rollout_merit(const DevProblem& P, int b, double alpha, bool& ok) {
+constexpr int FWD_MAX_COST = 4;    // cost functions cached in shared memory (more -> read from global)
+constexpr int FWD_MAX_N = 512;
+constexpr int FWD_THREADS = 32;
+
+struct FwdCon {
+    int kind, first, last, p, offset;
+    unsigned mask_max, mask_min;     // bit j set: z_j has a finite upper / lower bound (Goal: x_j constrained)
+    int pad;
+    double mu, inv2mu;
+    int row_max[TO_MAXNM], row_min[TO_MAXNM];
+    double a[TO_MAXNM], b[TO_MAXNM];
+};
+struct FwdCost {
+    double Qd[TO_MAXN], Rd[TO_MAXM], q[TO_MAXN], r[TO_MAXM], c;
+};
+struct alignas(16) FwdTab {
+    int ncon, ncost_cached, pad0, pad1;
+    FwdCon con[TO_MAXCON];
+    FwdCost cost[FWD_MAX_COST];
+    double dt[FWD_MAX_N];
+    int cost_index[FWD_MAX_N];
+};
+
+__device__ inline void load_tables(const DevProblem& P, FwdTab& tab) {
+    const int t = threadIdx.x, T = blockDim.x;
+    if (t == 0) { tab.ncon = P.ncon; tab.ncost_cached = P.ncost <= FWD_MAX_COST ? P.ncost : 0; }
+    for (int ci = 0; ci < P.ncon; ci++) {
+        const DevCon& c = P.cons[ci];
+        FwdCon& f = tab.con[ci];
+        if (t == 0) {
+            f.kind = c.kind; f.first = c.first; f.last = c.last; f.p = c.p; f.offset = c.offset;
+            f.mu = P.mu[ci]; f.inv2mu = 1.0 / (2.0 * P.mu[ci]);
+            unsigned mx = 0, mn = 0;
+            for (int j = 0; j < TO_MAXNM; j++) { if (c.row_max[j] >= 0) mx |= 1u << j; if (c.row_min[j] >= 0) mn |= 1u << j; }
+            f.mask_max = mx; f.mask_min = mn;
+        }
+        for (int j = t; j < TO_MAXNM; j += T) {
+            f.row_max[j] = c.row_max[j]; f.row_min[j] = c.row_min[j];
+            f.a[j] = c.a[j]; f.b[j] = c.b[j];
+        }
+    }
+    if (P.ncost <= FWD_MAX_COST)
+        for (int ci = 0; ci < P.ncost; ci++) {
+            const DevCost& c = P.costs[ci];
+            FwdCost& f = tab.cost[ci];
+            for (int j = t; j < TO_MAXN; j += T) { f.Qd[j] = c.Qd[j]; f.q[j] = c.q[j]; }
+            for (int j = t; j < TO_MAXM; j += T) { f.Rd[j] = c.Rd[j]; f.r[j] = c.r[j]; }
+            if (t == 0) f.c = c.c;
+        }
+    for (int k = t; k < P.N && k < FWD_MAX_N; k += T) { tab.dt[k] = (k < P.N - 1) ? P.dt[k] : 0.0; tab.cost_index[k] = P.cost_index[k]; }
+    __syncthreads();
+}
+
+__device__ __forceinline__ void cp_async8(double* smem_dst, const double* gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async16(double* smem_dst, const double* gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int NPEND> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(NPEND) : "memory"); }
+
+// shared-memory stage of one knot's operands for the IPB instances of a CTA.
+// K_k is stored as 16-byte pairs [pair][IPB][2] (when n*m is even), everything else as 8-byte slots [slot][IPB].
+template <int n, int m, int IPB>
+struct Stage {
+    static constexpr int KSLOTS = n * m;
+    static constexpr bool K16 = (KSLOTS % 2) == 0;
+    static constexpr int OFF_D = KSLOTS, OFF_U = OFF_D + m, OFF_X = OFF_U + m, OFF_L = OFF_X + n;
+    static constexpr int LAM_SLOTS = 2 * (n + m);
+    static constexpr int NSLOT = OFF_L + LAM_SLOTS;
+    static constexpr int DOUBLES = NSLOT * IPB;          // per stage buffer
+    __device__ static __forceinline__ int kidx(int e, int g) { return K16 ? ((e >> 1) * IPB + g) * 2 + (e & 1) : e * IPB + g; }
+    __device__ static __forceinline__ int sidx(int slot, int g) { return slot * IPB + g; }
+};
+
+// lanes of a group cooperatively issue the async copies of knot k's operands of instance g
+template <int n, int m, int IPB, int G>
+__device__ __forceinline__ void prefetch_knot(double* base, int g, int l, int k, const double* Kg, const double* dg, const double* X,
+                                              const double* U, const double* lam_b, const FwdTab& tab, int N) {
+    using S = Stage<n, m, IPB>;
+    if (k < N - 1) {
+        const double* Kk = Kg + (size_t)k * n * m;
+        if (S::K16) {
+#pragma unroll
+            for (int c = 0; c < (S::KSLOTS / 2 + G - 1) / G; c++) {
+                const int cc = c * G + l;
+                if (cc < S::KSLOTS / 2) cp_async16(base + S::kidx(2 * cc, g), Kk + 2 * cc);
+            }
+        } else {
+#pragma unroll
+            for (int c = 0; c < (S::KSLOTS + G - 1) / G; c++) {
+                const int cc = c * G + l;
+                if (cc < S::KSLOTS) cp_async8(base + S::kidx(cc, g), Kk + cc);
+            }
+        }
+        // d, u, x : 2m + n consecutive 8-byte slots
+#pragma unroll
+        for (int c = 0; c < (2 * m + n + G - 1) / G; c++) {
+            const int s = c * G + l;
+            if (s < m) cp_async8(base + S::sidx(S::OFF_D + s, g), dg + (size_t)k * m + s);
+            else if (s < 2 * m) cp_async8(base + S::sidx(S::OFF_U + s - m, g), U + (size_t)k * m + (s - m));
+            else if (s < 2 * m + n) cp_async8(base + S::sidx(S::OFF_X + s - 2 * m, g), X + (size_t)k * n + (s - 2 * m));
+        }
+    }
+    // multipliers of the constraints active at knot k+1 (1-based), packed in constraint order
+    int slot = 0;
+    for (int ci = 0; ci < tab.ncon; ci++) {
+        const FwdCon& c = tab.con[ci];
+        if (k + 1 < c.first || k + 1 > c.last) continue;
+        const double* lam = lam_b + c.offset + (size_t)(k + 1 - c.first) * c.p;
+        for (int i = l; i < c.p; i += G) cp_async8(base + S::sidx(S::OFF_L + slot + i, g), lam + i);
+        slot += c.p;
+    }
+}
+
+// closed-loop rollout of instance b (group g of the CTA) with step size alpha, diagonal costs, Goal/Bound constraints.
+// The candidate trajectory goes to buffer `cbuf`.  Returns the merit; `ok` = no blow-up.
+template <int MODEL, int IPB, int G>
+__device__ __forceinline__ double rollout_fast(const DevProblem& P, const FwdTab& tab, double* stage, int b, int g, int l, unsigned gmask,
+                                               double alpha, int cbuf, bool& ok) {
+    constexpr int n = ModelDims<MODEL>::n, m = ModelDims<MODEL>::m;
+    using S = Stage<n, m, IPB>;
+    const int N = P.N, buf = P.cur[b];
+    const double* X = traj_X(P, buf, b);
+    const double* U = traj_U(P, buf, b);
+    double* Xc = traj_Xw(P, cbuf, b);
+    double* Uc = traj_Uw(P, cbuf, b);
+    const double* Kg = P.K + (size_t)b * (N - 1) * n * m;
+    const double* dg = P.d + (size_t)b * (N - 1) * m;
+    const double* lam_b = P.lambda + (size_t)b * P.lambda_len;
+    double x[n], u[m], xn[n];
+    double J = 0.0;
+    ok = true;
+#pragma unroll
+    for (int i = 0; i < n; i++) x[i] = P.x0[(size_t)b * n + i];
+    prefetch_knot<n, m, IPB, G>(stage, g, l, 0, Kg, dg, X, U, lam_b, tab, N);
+    cp_async_commit();
+    for (int k = 0; k < N; k++) {
+        const bool last = (k == N - 1);
+        const int sb = k & 1;
+        __syncwarp(gmask);                      // every lane of the group is done reading stage sb^1 (knot k-1)
+        if (!last) prefetch_knot<n, m, IPB, G>(stage + (sb ^ 1) * S::DOUBLES, g, l, k + 1, Kg, dg, X, U, lam_b, tab, N);
+        cp_async_commit();
+        cp_async_wait<1>();                     // this lane's copies for knot k have landed ...
+        __syncwarp(gmask);                      // ... and so have the other lanes'
+        const double* st = stage + sb * S::DOUBLES;
+        if (!last) {
+#pragma unroll
+            for (int a = 0; a < m; a++) u[a] = fma(alpha, st[S::sidx(S::OFF_D + a, g)], st[S::sidx(S::OFF_U + a, g)]);
+#pragma unroll
+            for (int i = 0; i < n; i++) {
+                const double dx = x[i] - st[S::sidx(S::OFF_X + i, g)];
+                if (S::K16 && (m % 2 == 0)) {
+#pragma unroll
+                    for (int a = 0; a < m; a += 2) {
+                        const double2 kv = *reinterpret_cast<const double2*>(&st[S::kidx(i * m + a, g)]);
+                        u[a] = fma(kv.x, dx, u[a]);
+                        u[a + 1] = fma(kv.y, dx, u[a + 1]);
+                    }
+                } else {
+#pragma unroll
+                    for (int a = 0; a < m; a++) u[a] = fma(st[S::kidx(i * m + a, g)], dx, u[a]);
+                }
+            }
+#pragma unroll
+            for (int a = 0; a < m; a++) if (!(fabs(u[a]) <= P.opt.max_control_value)) ok = false;
+        } else {
+#pragma unroll
+            for (int a = 0; a < m; a++) u[a] = 0.0;
+        }
+#pragma unroll
+        for (int i = 0; i < n; i++) Xc[(size_t)k * n + i] = x[i];
+        if (!last) {
+#pragma unroll
+            for (int a = 0; a < m; a++) Uc[(size_t)k * m + a] = u[a];
+        }
+        // ---- cost of knot k (DiagonalCost) -------------------------------------------------------------
+        {
+            const int cid = tab.cost_index[k];
+            double a2 = 0.0, l1 = 0.0, cc;
+            if (tab.ncost_cached) {
+                const FwdCost& c = tab.cost[cid];
+#pragma unroll
+                for (int i = 0; i < n; i++) { a2 = fma(c.Qd[i] * x[i], x[i], a2); l1 = fma(c.q[i], x[i], l1); }
+                if (!last) {
+#pragma unroll
+                    for (int i = 0; i < m; i++) { a2 = fma(c.Rd[i] * u[i], u[i], a2); l1 = fma(c.r[i], u[i], l1); }
+                }
+                cc = c.c;
+            } else {
+                const DevCost& c = P.costs[cid];
+#pragma unroll
+                for (int i = 0; i < n; i++) { a2 = fma(c.Qd[i] * x[i], x[i], a2); l1 = fma(c.q[i], x[i], l1); }
+                if (!last) {
+#pragma unroll
+                    for (int i = 0; i < m; i++) { a2 = fma(c.Rd[i] * u[i], u[i], a2); l1 = fma(c.r[i], u[i], l1); }
+                }
+                cc = c.c;
+            }
+            J += fma(0.5, a2, l1) + cc;
+        }
+        // ---- AL penalty of knot k (Goal / Bound): (|Pi_K*(lambda - mu c)|^2 - |lambda|^2) / (2 mu) -------------
+        {
+            int slot = 0;
+            for (int ci = 0; ci < tab.ncon; ci++) {
+                const FwdCon& c = tab.con[ci];
+                if (k + 1 < c.first || k + 1 > c.last) continue;
+                const double mu = c.mu;
+                const int lo = S::OFF_L + slot;
+                double a = 0.0, l2 = 0.0;
+                if (c.kind == CON_GOAL) {
+                    const unsigned mk = c.mask_max;
+#pragma unroll
+                    for (int i = 0; i < n; i++) {
+                        if (mk & (1u << i)) {
+                            const int row = c.row_max[i];
+                            const double lm = st[S::sidx(lo + row, g)];
+                            const double lp = fma(-mu, x[i] - c.a[row], lm);
+                            a = fma(lp, lp, a); l2 = fma(lm, lm, l2);
+                        }
+                    }
+                } else {
+                    const unsigned mx = c.mask_max, mn = c.mask_min;
+                    if ((mx | mn) & ((1u << n) - 1u)) {
+#pragma unroll
+                        for (int i = 0; i < n; i++) {
+                            if (mx & (1u << i)) { const double lm = st[S::sidx(lo + c.row_max[i], g)]; const double lp = fmin(0.0, fma(-mu, x[i] - c.a[i], lm)); a = fma(lp, lp, a); l2 = fma(lm, lm, l2); }
+                            if (mn & (1u << i)) { const double lm = st[S::sidx(lo + c.row_min[i], g)]; const double lp = fmin(0.0, fma(-mu, c.b[i] - x[i], lm)); a = fma(lp, lp, a); l2 = fma(lm, lm, l2); }
+                        }
+                    }
+#pragma unroll
+                    for (int i = 0; i < m; i++) {
+                        if (mx & (1u << (n + i))) { const double lm = st[S::sidx(lo + c.row_max[n + i], g)]; const double lp = fmin(0.0, fma(-mu, u[i] - c.a[n + i], lm)); a = fma(lp, lp, a); l2 = fma(lm, lm, l2); }
+                        if (mn & (1u << (n + i))) { const double lm = st[S::sidx(lo + c.row_min[n + i], g)]; const double lp = fmin(0.0, fma(-mu, c.b[n + i] - u[i], lm)); a = fma(lp, lp, a); l2 = fma(lm, lm, l2); }
+                    }
+                }
+                J = fma(a - l2, c.inv2mu, J);
+                slot += c.p;
+            }
+        }
+        if (!last) {
+            rk4_step<MODEL, double>(P.params, x, u, tab.dt[k], xn);
+#pragma unroll
+            for (int i = 0; i < n; i++) { x[i] = xn[i]; if (!(fabs(xn[i]) <= P.opt.max_state_value)) ok = false; }
+            // a blown-up trial keeps integrating (the group stays in lock step); its result is rejected through `ok`
+        }
+    }
+    cp_async_wait<0>();
+    return J;
+}
+
+// generic path (dense costs or general constraints): pointer-based evaluation, operands read directly from global
+template <int MODEL>
+__device__ __forceinline__ double rollout_generic(const DevProblem& P, int b, double alpha, int cbuf, bool& ok) {
     constexpr int n = ModelDims<MODEL>::n, m = ModelDims<MODEL>::m;
     const int N = P.N, buf = P.cur[b];
     const double* X = traj_X(P, buf, b);
     const double* U = traj_U(P, buf, b);
-    double* Xc = traj_Xw(P, buf ^ 1, b);
-    double* Uc = traj_Uw(P, buf ^ 1, b);
+    double* Xc = traj_Xw(P, cbuf, b);
+    double* Uc = traj_Uw(P, cbuf, b);
     const double* Kg = P.K + (size_t)b * (N - 1) * n * m;
     const double* dg = P.d + (size_t)b * (N - 1) * m;
     const double* lam_b = P.lambda + (size_t)b * P.lambda_len;
@@ -44,77 +299,33 @@ __device__ __forceinline__ double rollout_merit(const DevProblem& P, int b, doub
     for (int k = 0; k < N; k++) {
         const bool last = (k == N - 1);
         if (!last) {
-            double dx[n];
 #pragma unroll
-            for (int i = 0; i < n; i++) dx[i] = x[i] - X[(size_t)k * n + i];
+            for (int a = 0; a < m; a++) u[a] = fma(alpha, dg[(size_t)k * m + a], U[(size_t)k * m + a]);
 #pragma unroll
-            for (int a = 0; a < m; a++) {
-                double t = fma(alpha, dg[(size_t)k * m + a], U[(size_t)k * m + a]);
+            for (int i = 0; i < n; i++) {
+                const double dx = x[i] - X[(size_t)k * n + i];
 #pragma unroll
-                for (int i = 0; i < n; i++) t = fma(Kg[(size_t)k * n * m + i * m + a], dx[i], t);
-                u[a] = t;
-                if (!(fabs(t) <= P.opt.max_control_value)) ok = false;
+                for (int a = 0; a < m; a++) u[a] = fma(Kg[(size_t)k * n * m + i * m + a], dx, u[a]);
             }
+#pragma unroll
+            for (int a = 0; a < m; a++) if (!(fabs(u[a]) <= P.opt.max_control_value)) ok = false;
         } else {
 #pragma unroll
             for (int a = 0; a < m; a++) u[a] = 0.0;
         }
-        if (STORE) {
 #pragma unroll
-            for (int i = 0; i < n; i++) Xc[(size_t)k * n + i] = x[i];
-            if (!last) {
+        for (int i = 0; i < n; i++) Xc[(size_t)k * n + i] = x[i];
+        if (!last) {
 #pragma unroll
-                for (int a = 0; a < m; a++) Uc[(size_t)k * m + a] = u[a];
-            }
+            for (int a = 0; a < m; a++) Uc[(size_t)k * m + a] = u[a];
         }
-        // ---- cost + AL penalty of knot k ------------------------------------------------------------
-        const DevCost& cost = P.costs[P.cost_index[k]];
-        if (FAST) {
-            double a2 = 0.0, l1 = 0.0;
-#pragma unroll
-            for (int i = 0; i < n; i++) { a2 = fma(cost.Qd[i] * x[i], x[i], a2); l1 = fma(cost.q[i], x[i], l1); }
-            double Jk = 0.5 * a2 + l1 + cost.c;
-            if (!last) {
-                double au = 0.0, lu = 0.0;
-#pragma unroll
-                for (int i = 0; i < m; i++) { au = fma(cost.Rd[i] * u[i], u[i], au); lu = fma(cost.r[i], u[i], lu); }
-                Jk += 0.5 * au + lu;
-            }
-            double pen = 0.0;
-            for (int ci = 0; ci < P.ncon; ci++) {
-                const DevCon& con = P.cons[ci];
-                if (k + 1 < con.first || k + 1 > con.last) continue;
-                const double mu = P.mu[ci];
-                const double* lam = lam_b + con.offset + (size_t)(k + 1 - con.first) * con.p;
-                double a = 0.0, l2 = 0.0;
-                if (con.kind == CON_GOAL) {
-#pragma unroll
-                    for (int i = 0; i < n; i++) {
-                        const int row = con.row_max[i];
-                        if (row >= 0) { const double l = lam[row]; const double lp = l - mu * (x[i] - con.a[row]); a = fma(lp, lp, a); l2 = fma(l, l, l2); }
-                    }
-                } else {   // CON_BOUND
-#pragma unroll
-                    for (int i = 0; i < n + m; i++) {
-                        const double zi = (i < n) ? x[i < n ? i : 0] : u[i >= n ? i - n : 0];
-                        int row = con.row_max[i];
-                        if (row >= 0) { const double l = lam[row]; const double lp = fmin(0.0, l - mu * (zi - con.a[i])); a = fma(lp, lp, a); l2 = fma(l, l, l2); }
-                        row = con.row_min[i];
-                        if (row >= 0) { const double l = lam[row]; const double lp = fmin(0.0, l - mu * (con.b[i] - zi)); a = fma(lp, lp, a); l2 = fma(l, l, l2); }
-                    }
-                }
-                pen += (a - l2) / (2 * mu);
-            }
-            J += Jk + pen;
-        } else {
-            J += cost_value(cost, n, m, x, u, !last);
-            J += al_knot_penalty(P, k + 1, x, u, lam_b, viol);
-        }
+        J += cost_value(P.costs[P.cost_index[k]], n, m, x, u, !last);
+        J += al_knot_penalty(P, k + 1, x, u, lam_b, viol);
         if (!last) {
             rk4_step<MODEL, double>(P.params, x, u, P.dt[k], xn);
 #pragma unroll
             for (int i = 0; i < n; i++) { x[i] = xn[i]; if (!(fabs(xn[i]) <= P.opt.max_state_value)) ok = false; }
-            if (!ok) break;   // Altro stops the rollout at the first blow-up; the trial is rejected
+            if (!ok) break;
         }
     }
     return J;
@@ -127,51 +338,51 @@ __device__ __forceinline__ bool ls_accept(const DevProblem& P, double J, double 
     return (z > P.opt.ls_lower && z <= P.opt.ls_upper) || (J < J_prev);
 }
 
-template <int MODEL, bool FAST>
-__global__ void __launch_bounds__(32) k_forward(const DevProblem P) {
-    const int b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= P.B) return;
-    if (P.bp_status[b] < 0) { P.accepted[b] = 0; return; }
-    bool ok;
-    const double J = rollout_merit<MODEL, true, FAST>(P, b, 1.0, ok);
-    const bool acc = ls_accept(P, J, P.J[b], 1.0, P.dV[2 * b], P.dV[2 * b + 1], ok);
-    P.accepted[b] = acc ? 1 : 0;
-    if (acc) { P.Jc[b] = J; P.alpha[b] = 1.0; P.ls_iters[b] = 1; }
-}
+extern __shared__ __align__(16) unsigned char fwd_smem[];
 
-template <int MODEL, bool FAST>
-__global__ void __launch_bounds__(128) k_ladder(const DevProblem P) {
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    const int b = t >> 4, l = t & 15;
-    if (b >= P.B) return;                      // whole 16-lane groups leave together
-    const unsigned gmask = 0xFFFFu << (threadIdx.x & 16);
-    const int status = P.bp_status[b];
-    int accepted = P.accepted[b];
-    if (status >= 0 && !accepted) {
-        const int ntry = P.opt.ls_iters;       // alphas 2^-1 .. 2^-ntry
-        const double alpha = ldexp(1.0, -(l + 1));
-        bool ok = false, good = false;
-        double J = 0.0;
-        if (l < ntry) {
-            J = rollout_merit<MODEL, false, FAST>(P, b, alpha, ok);
-            good = ls_accept(P, J, P.J[b], alpha, P.dV[2 * b], P.dV[2 * b + 1], ok);
-        }
+// One line-search pass: lane l of group g evaluates trial (trial0 + l) of instance b.
+//   first_pass : ignore / reset accepted[b];   final_pass : commit failures (no acceptable step size).
+template <int MODEL, int G, bool FAST>
+__global__ void __launch_bounds__(FWD_THREADS) k_linesearch(const DevProblem P, int trial0, int first_pass, int final_pass) {
+    constexpr int n = ModelDims<MODEL>::n, m = ModelDims<MODEL>::m;
+    constexpr int IPB = FWD_THREADS / G;
+    using S = Stage<n, m, IPB>;
+    FwdTab* tab = reinterpret_cast<FwdTab*>(fwd_smem);
+    double* stage = reinterpret_cast<double*>(fwd_smem + sizeof(FwdTab));
+    const int g = threadIdx.x / G, l = threadIdx.x % G;
+    const int b = blockIdx.x * IPB + g;
+    const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (g * G));
+    const bool valid = b < P.B;
+    const int status = valid ? P.bp_status[b] : -1;
+    const int was_accepted = (valid && !first_pass) ? P.accepted[b] : 0;
+    const bool work = valid && status >= 0 && !was_accepted && trial0 <= P.opt.ls_iters;
+    // CTA-uniform: skip the table load when no group of this CTA has work
+    const unsigned any = __ballot_sync(0xffffffffu, work);
+    if (FAST && any) load_tables(P, *tab);
+    if (!valid) return;
+    bool accepted = was_accepted != 0;
+    if (work) {
+        const int trial = trial0 + l;
+        const double alpha = ldexp(1.0, -trial);
+        const int cbuf = (P.cur[b] + 1 + l) % TO_NBUF;
+        bool ok = false;
+        double J;
+        if (FAST) J = rollout_fast<MODEL, IPB, G>(P, *tab, stage, b, g, l, gmask, alpha, cbuf, ok);
+        else J = rollout_generic<MODEL>(P, b, alpha, cbuf, ok);
+        const bool good = (trial <= P.opt.ls_iters) && ls_accept(P, J, P.J[b], alpha, P.dV[2 * b], P.dV[2 * b + 1], ok);
         const unsigned votes = __ballot_sync(gmask, good) & gmask;
         if (votes) {
-            const int win = __ffs(votes) - 1 - (threadIdx.x & 16);
+            const int win = __ffs(votes) - 1 - g * G;
             if (l == win) {
-                bool ok2;
-                const double J2 = rollout_merit<MODEL, true, FAST>(P, b, alpha, ok2);
-                P.Jc[b] = J2; P.alpha[b] = alpha; P.ls_iters[b] = win + 2;
+                P.cur[b] = cbuf; P.J[b] = J; P.alpha[b] = alpha; P.ls_iters[b] = trial + 1; P.accepted[b] = 1;
             }
-            accepted = 1;
+            accepted = true;
         }
-        __syncwarp(gmask);
     }
-    if (l == 0) {
+    if (l == 0 && !accepted) {
+        if (first_pass) P.accepted[b] = 0;
         if (status < 0) { P.alpha[b] = 0.0; P.ls_iters[b] = 0; }
-        else if (accepted) { P.cur[b] ^= 1; P.J[b] = P.Jc[b]; P.accepted[b] = 1; }
-        else {
+        else if (final_pass) {   // no acceptable step: keep the trajectory, raise the regularisation (Altro forwardpass!)
             double rho = P.rho[b], drho = P.drho[b];
             reg_increase(P.opt, rho, drho);
             rho += P.opt.bp_reg_fp;
@@ -179,26 +390,52 @@ __global__ void __launch_bounds__(128) k_ladder(const DevProblem P) {
             P.alpha[b] = 0.0; P.ls_iters[b] = P.opt.ls_iters + 1;
         }
     }
+    (void)sizeof(S);
+}
+
+template <int MODEL, int G, bool FAST>
+cudaError_t launch_pass(const DevProblem& P, int trial0, int first_pass, int final_pass, cudaStream_t s) {
+    constexpr int n = ModelDims<MODEL>::n, m = ModelDims<MODEL>::m;
+    constexpr int IPB = FWD_THREADS / G;
+    const int blocks = (P.B + IPB - 1) / IPB;
+    const size_t smem = FAST ? sizeof(FwdTab) + (size_t)2 * Stage<n, m, IPB>::DOUBLES * sizeof(double) : 0;
+    auto kern = k_linesearch<MODEL, G, FAST>;
+    static bool configured = false;
+    if (!configured && smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    configured = true;
+    kern<<<blocks, FWD_THREADS, smem, s>>>(P, trial0, first_pass, final_pass);
+    return cudaGetLastError();
+}
+
+bool fast_path(const DevProblem& P) {
+    return P.all_diag_cost && P.all_diag_con && P.N <= FWD_MAX_N && P.max_p_knot <= 2 * (P.n + P.m);
 }
 
 }  // namespace
 
+// pass 1: trials 0..3 (alpha = 1, 1/2, 1/4, 1/8), 4 lanes per instance.
+// (Measured alternative: the whole ladder in one 16-lane pass costs 1.34 ms -- 11x the FLOPs, the uncoalesced candidate
+//  stores saturate the LSU -- against 0.33 + 0.25 ms for the two latency-bound passes; profiles/r01_notes.md.)
 cudaError_t launch_forward(const DevProblem& P, cudaStream_t s) {
-    const int threads = 32, blocks = (P.B + threads - 1) / threads;
-    const bool fast = P.all_diag_cost && P.all_diag_con;
-    if (fast) { TO_DISPATCH_MODEL(P.model, P.m, (k_forward<MODEL, true><<<blocks, threads, 0, s>>>(P))); }
-    else { TO_DISPATCH_MODEL(P.model, P.m, (k_forward<MODEL, false><<<blocks, threads, 0, s>>>(P))); }
-    return cudaGetLastError();
+    cudaError_t e = cudaErrorNotSupported;
+    const int final_pass = P.opt.ls_iters < 4;
+    if (fast_path(P)) { TO_DISPATCH_MODEL(P.model, P.m, (e = launch_pass<MODEL, 4, true>(P, 0, 1, final_pass, s))); }
+    else { TO_DISPATCH_MODEL(P.model, P.m, (e = launch_pass<MODEL, 4, false>(P, 0, 1, final_pass, s))); }
+    return e;
 }
 
+// pass 2 (+3 when ls_iters > 11): the remaining trials, 8 lanes per instance; commits failures
 cudaError_t launch_ladder(const DevProblem& P, cudaStream_t s) {
-    const int threads = 128;
-    const long long total = (long long)P.B * 16;
-    const unsigned blocks = (unsigned)((total + threads - 1) / threads);
-    const bool fast = P.all_diag_cost && P.all_diag_con;
-    if (fast) { TO_DISPATCH_MODEL(P.model, P.m, (k_ladder<MODEL, true><<<blocks, threads, 0, s>>>(P))); }
-    else { TO_DISPATCH_MODEL(P.model, P.m, (k_ladder<MODEL, false><<<blocks, threads, 0, s>>>(P))); }
-    return cudaGetLastError();
+    cudaError_t e = cudaSuccess;
+    for (int trial0 = 4; trial0 <= P.opt.ls_iters && e == cudaSuccess; trial0 += 8) {
+        const int final_pass = trial0 + 8 > P.opt.ls_iters;
+        if (fast_path(P)) { TO_DISPATCH_MODEL(P.model, P.m, (e = launch_pass<MODEL, 8, true>(P, trial0, 0, final_pass, s))); }
+        else { TO_DISPATCH_MODEL(P.model, P.m, (e = launch_pass<MODEL, 8, false>(P, trial0, 0, final_pass, s))); }
+    }
+    return e;
 }
 
-cudaError_t launch_accept(const DevProblem& P, cudaStream_t s) { return cudaSuccess; }   // folded into k_ladder
+cudaError_t launch_accept(const DevProblem& P, cudaStream_t s) { return cudaSuccess; }   // acceptance is committed inside k_linesearch

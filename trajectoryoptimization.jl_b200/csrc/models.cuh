@@ -76,7 +76,7 @@ template <int MODEL, class S>
 __device__ __forceinline__ void dynamics(const double* __restrict__ p, const S* x, const S* u, S* xd) {
     if constexpr (MODEL == MODEL_DOUBLE_INTEGRATOR || MODEL == MODEL_DOUBLE_INTEGRATOR_2D) {
         constexpr int dim = ModelDims<MODEL>::m;
-        const double inv_mass = 1.0 / p[0];
+        const double inv_mass = p[1];   // 1/mass, precomputed on the host
 #pragma unroll
         for (int i = 0; i < dim; i++) { xd[i] = x[dim + i]; xd[dim + i] = u[i] * inv_mass; }
     } else if constexpr (MODEL == MODEL_CARTPOLE) {
@@ -86,13 +86,14 @@ __device__ __forceinline__ void dynamics(const double* __restrict__ p, const S* 
         S h11 = lift<S>(mc + mp), h12 = (mp * l) * c, h22 = lift<S>(mp * l * l);
         S r1 = (-mp * l) * (qd2 * s) * qd2 - u[0];
         S r2 = (mp * g * l) * s;
-        S det = h11 * h22 - h12 * h12;
+        S idet = lift<S>(1.0) / (h11 * h22 - h12 * h12);
         xd[0] = qd1; xd[1] = qd2;
-        xd[2] = -(h22 * r1 - h12 * r2) / det;
-        xd[3] = -(h11 * r2 - h12 * r1) / det;
+        xd[2] = -(h22 * r1 - h12 * r2) * idet;
+        xd[3] = -(h11 * r2 - h12 * r1) * idet;
     } else if constexpr (MODEL == MODEL_QUADROTOR) {
         const double mass = p[0], J1 = p[1], J2 = p[2], J3 = p[3];
         const double gx = p[4], gy = p[5], gz = p[6], L = p[7], kf = p[8], km = p[9];
+        const double inv_mass = p[10], iJ1 = p[11], iJ2 = p[12], iJ3 = p[13];   // reciprocals precomputed on the host (to_create)
         S qw = x[3], qx = x[4], qy = x[5], qz = x[6];
         S wx = x[10], wy = x[11], wz = x[12];
         S F1 = drelu(kf * u[0]), F2 = drelu(kf * u[1]), F3 = drelu(kf * u[2]), F4 = drelu(kf * u[3]);
@@ -111,13 +112,13 @@ __device__ __forceinline__ void dynamics(const double* __restrict__ p, const S* 
         xd[4] = 0.5 * (qw * wx + qy * wz - qz * wy);
         xd[5] = 0.5 * (qw * wy + qz * wx - qx * wz);
         xd[6] = 0.5 * (qw * wz + qx * wy - qy * wx);
-        xd[7] = (mass * gx + Fwx) / mass;
-        xd[8] = (mass * gy + Fwy) / mass;
-        xd[9] = (mass * gz + Fwz) / mass;
+        xd[7] = (mass * gx + Fwx) * inv_mass;
+        xd[8] = (mass * gy + Fwy) * inv_mass;
+        xd[9] = (mass * gz + Fwz) * inv_mass;
         S Jw1 = J1 * wx, Jw2 = J2 * wy, Jw3 = J3 * wz;
-        xd[10] = (t1 - (wy * Jw3 - wz * Jw2)) / J1;
-        xd[11] = (t2 - (wz * Jw1 - wx * Jw3)) / J2;
-        xd[12] = (t3 - (wx * Jw2 - wy * Jw1)) / J3;
+        xd[10] = (t1 - (wy * Jw3 - wz * Jw2)) * iJ1;
+        xd[11] = (t2 - (wz * Jw1 - wx * Jw3)) * iJ2;
+        xd[12] = (t3 - (wx * Jw2 - wy * Jw1)) * iJ3;
     } else if constexpr (MODEL == MODEL_ACROBOT) {
         const double l1 = p[0], l2 = p[1], m1 = p[2], m2 = p[3], J1 = p[4], J2 = p[5], fr = p[6], g = p[7];
         S th1 = x[0], th2 = x[1], th1d = x[2], th2d = x[3];
@@ -133,10 +134,10 @@ __device__ __forceinline__ void dynamics(const double* __restrict__ p, const S* 
         S g2 = (m2 * l2 * g) * c12;
         S r1 = -b1 - g1 - f1;
         S r2 = u[0] - b2 - g2 - f2;
-        S det = m11 * m22 - m12 * m12;
+        S idet = lift<S>(1.0) / (m11 * m22 - m12 * m12);
         xd[0] = th1d; xd[1] = th2d;
-        xd[2] = (m22 * r1 - m12 * r2) / det;
-        xd[3] = (m11 * r2 - m12 * r1) / det;
+        xd[2] = (m22 * r1 - m12 * r2) * idet;
+        xd[3] = (m11 * r2 - m12 * r1) * idet;
     }
 }
 
@@ -156,7 +157,7 @@ __device__ __forceinline__ void rk4_step(const double* __restrict__ p, const S* 
     for (int i = 0; i < n; i++) { k[i] = k[i] * h; acc[i] = acc[i] + 2.0 * k[i]; xt[i] = x[i] + k[i]; }
     dynamics<MODEL, S>(p, xt, u, k);
 #pragma unroll
-    for (int i = 0; i < n; i++) { k[i] = k[i] * h; xn[i] = x[i] + (acc[i] + k[i]) / 6.0; }
+    for (int i = 0; i < n; i++) { k[i] = k[i] * h; xn[i] = x[i] + (acc[i] + k[i]) * (1.0 / 6.0); }
 }
 
 // dispatch a templated launcher on the runtime model id / dimension

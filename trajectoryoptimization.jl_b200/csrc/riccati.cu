@@ -3,7 +3,7 @@
 // What it computes (Altro.jl backwardpass!, which drives the reference's expansions; restated in
 // oracle/oracle.hpp `backward_pass`), per instance, serial in k = N-1 .. 1:
 //     Qzz = lzz + [A B]' S [A B]      Qz = lz + [A B]' s          (z = [x;u], lzz/lz = cost + AL expansion)
-//     K = -(Quu + rho I)^-1 Qux       d = -(Quu + rho I)^-1 Qu    (Cholesky; non-PD -> rho increase + restart)
+//     K = -(Quu + rho I)^-1 Qux       d = -(Quu + rho I)^-1 Qu    (non-PD Quu + rho I -> rho increase + restart)
 //     S <- Qxx + K'Quu K + K'Qux + Qux'K     s <- Qx + K'Quu d + K'Qu + Qux'd     dV += (d'Qu, 1/2 d'Quu d)
 // With W = Qux - rho K the update collapses to S <- Qxx + W'K, s <- Qx + W'd (identical algebra, Quu K = -Qux - rho K).
 // The cost expansion consumed here is the reference's RD.gradient!/RD.hessian! (src/cost_functions.jl:137-233)
@@ -12,24 +12,32 @@
 //
 // B200 mapping
 //   * one WARP per instance (the recursion is serial in k; B=4096 gives ~28 instances per SM, so intra-instance
-//     parallelism has to fill the FP64 pipe).  Persistent CTAs of one warp pull instances from an atomic queue.
+//     parallelism has to fill the FP64 pipe).  Persistent one-warp CTAs pull instances from an atomic queue.
 //   * [A B]_k (n x LDAB doubles, contiguous per knot thanks to the instance-major layout) is streamed from HBM
 //     by 1-D bulk TMA copies (cp.async.bulk + mbarrier complete_tx) into a multi-stage shared-memory ring, issued
 //     by lane 0 several knots ahead of use -- this is the dominant HBM traffic of the whole iteration.
-//   * the n x n / n x (n+m) products run as 2x2 register micro-blocks per lane: per inner index one LDS.128 per
-//     operand pair and 4 DFMA per block (DFMA issue is 2 cycles on sm_100, every other instruction costs an
-//     issue slot, so operands are fetched as 16-byte pairs and addresses are compile-time immediates).
-//     T = S [A B] (with s appended as an extra column), then Qzz|Qz = [A B]' T restricted to the upper blocks.
-//     FP64 tensor MMA (DMMA m8n8k4) shares the DFMA pipe on B200 (measured: profiles/microbench) and wastes >50%
-//     of its tile on n=13, so it is not used.
-//   * Quu is m x m (m <= 8): Cholesky + triangular solves are done per right-hand-side column, one lane per
-//     column of [Qux Qu], in registers.
+//   * T = S [A B] (with s appended as an extra column), then Qzz|Qz = [A B]' T restricted to the upper tiles.
+//     n >= 8 (Quadrotor): FP64 tensor-core MMA, mma.sync m8n8k4 (SASS DMMA).  The first version used 2x2 register
+//     micro-blocks with DFMA and was bound by the SHARED-MEMORY pipe at 77% (ncu: every LDS.128 costs 4 wavefronts,
+//     broadcast or not, i.e. 4 B per lane per cycle; a DFMA needs two fresh operands).  A DMMA moves 256 FMAs with
+//     one 8-byte operand per lane per fragment, ~5x fewer wavefronts per FLOP, so the kernel becomes FP64-pipe bound
+//     (DMMA and DFMA share that pipe on B200: profiles/microbench).  K = n is split into n/4 MMA k-steps plus
+//     rank-1 DFMA updates for the n%4 remainder; smem row strides are = 4 (mod 16) doubles so that the 8x4 / 4x8
+//     fragment loads are bank-conflict free.
+//     n < 8 (Cartpole, Acrobot, double integrator): 2x2 register micro-blocks with DFMA (tiles would be >75% padding).
+//   * lane i < n+m owns z_i: its cost / AL descriptors live in registers for the whole kernel, and z_i, lambda of the
+//     NEXT knot are prefetched while the current knot's products run (global latency off the critical path).
+//   * Quu + rho I is m x m (m <= 8): LDL' with reciprocal pivots (no fp64 sqrt / division chain) and the triangular
+//     solves are done per right-hand-side column, one lane per column of [Qux Qu], in registers.
+#include <cstdlib>
+
 #include "costcon.cuh"
 #include "kernels.h"
 
 namespace {
 
-constexpr int even_up(int v) { return (v + 1) & ~1; }
+__host__ __device__ constexpr int even_up(int v) { return (v + 1) & ~1; }
+constexpr int MAXT = 3;   // AL terms per z entry kept in registers (e.g. upper bound + lower bound + goal)
 
 __device__ __forceinline__ double2 lds128(const double* p) { return *reinterpret_cast<const double2*>(p); }
 __device__ __forceinline__ void sts128(double* p, double a, double b) { *reinterpret_cast<double2*>(p) = make_double2(a, b); }
@@ -65,66 +73,117 @@ __device__ __forceinline__ void fma2x2(double (&acc)[4], const double2& a, const
     acc[3] = fma(a.y, b.y, acc[3]);
 }
 
-template <int N_, int M_, int STAGES>
+__device__ __forceinline__ void dmma(double& d0, double& d1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+
+template <int N_, int M_, int STAGES, bool MMA>
 struct RiccatiSmem {
     static constexpr int NM = N_ + M_;
-    static constexpr int LDAB = even_up(NM);        // row stride of [A B] (HBM and smem)
-    static constexpr int LDT = even_up(NM + 1);     // T / Q row stride: one extra column carries s / Qz
     static constexpr int NP = even_up(N_);          // padded state dim
+    static constexpr int MMA_LD = 20;               // = 4 (mod 16): conflict-free m8n8k4 fragment loads
+    static constexpr int LDAB = MMA ? MMA_LD : even_up(NM);       // row stride of [A B] in HBM (to_create sets P.ldab alike)
+    static constexpr int LDABS = LDAB;                            // ... and in shared memory (one bulk copy per knot)
+    static constexpr int LDS_ = MMA ? MMA_LD : NP;                // S
+    static constexpr int LDT = MMA ? MMA_LD : even_up(NM + 1);    // T / Q: one extra column carries s / Qz
+    static constexpr int SROWS = MMA ? 16 : NP;
+    static constexpr int TROWS = MMA ? 16 : NP;
     static constexpr int LDK = even_up(N_ + 1);     // K|d row stride
     static constexpr int AB_BYTES = N_ * LDAB * 8;
-    static constexpr int AB_STRIDE = (AB_BYTES + 127) / 128 * 16;   // doubles, 128-byte aligned stages
+    static constexpr int AB_STRIDE = (N_ * LDABS * 8 + 127) / 128 * 16;   // doubles, 128-byte aligned stages
+    static_assert(!MMA || (N_ <= 16 && NM + 1 <= MMA_LD && N_ >= 8), "MMA path: 8 <= n <= 16 and n+m+1 <= 20");
     double ab[STAGES][AB_STRIDE];
-    double S[NP * NP];
-    double T[NP * LDT];
-    double Q[LDAB * LDT];
+    double S[SROWS * LDS_];
+    double T[TROWS * LDT + 8];
+    double Q[even_up(NM) * LDT + 8];
     double K[M_ * LDK];
     double W[M_ * LDK];
-    double g[LDT];        // lz (cost + AL gradient), padded
-    double h[LDT];        // diag(lzz)
+    double g[even_up(NM) + 2];   // lz (cost + AL gradient), padded
+    double h[even_up(NM) + 2];   // diag(lzz)
     uint64_t bar[STAGES];
 };
 
-template <int N_, int M_, int STAGES>
-__global__ void __launch_bounds__(32) k_riccati(const DevProblem P, int* __restrict__ work_counter) {
-    using SM = RiccatiSmem<N_, M_, STAGES>;
+// one AL term acting on z_i:  c = sign * (z_i - bound) ;  Goal: equality (always active), Bound: inequality
+struct ALTerm {
+    int first, last, p, base;   // knot range (1-based), rows per knot, lambda index of the row at knot `first`
+    double sign, bound, mu;
+    bool eq;
+};
+
+template <int N_, int M_, int STAGES, bool FASTAL, bool MMA, int MINB>
+__global__ void __launch_bounds__(32, MINB) k_riccati(const DevProblem P, int* __restrict__ work_counter) {
+    using SM = RiccatiSmem<N_, M_, STAGES, MMA>;
     constexpr int n = N_, m = M_, NM = SM::NM, LDAB = SM::LDAB, LDT = SM::LDT, NP = SM::NP, LDK = SM::LDK;
-    constexpr int RBT = NP / 2, CBT = LDAB / 2;              // T blocks: rows of S x column pairs of [A B]
+    constexpr int LDABS = SM::LDABS, LDS_ = SM::LDS_;
+    // MMA tiling: T (n x NM+1) = S (n x n) [A B | s] ; Q (NM x NM+1) upper tiles = [A B]' T
+    constexpr int MT = (n + 7) / 8, NT = (NM + 1 + 7) / 8, MQ = (NM + 7) / 8, KS = n / 4, KR = n % 4;
+    constexpr int NQT = MQ * NT - MQ * (MQ - 1) / 2;        // upper tiles (mi <= ni)
+    constexpr int RBT = NP / 2, CBT = even_up(NM) / 2;       // T blocks: rows of S x column pairs of [A B]
     constexpr int NBT = RBT * CBT;
     constexpr int RT = (NBT + 31) / 32;
-    constexpr int RBQ = LDAB / 2, CBQ = LDT / 2;             // Q blocks (upper: cb >= rb)
+    constexpr int RBQ = even_up(NM) / 2, CBQ = even_up(NM + 1) / 2;   // Q blocks (upper: cb >= rb)
     constexpr int NBQ = RBQ * CBQ - RBQ * (RBQ - 1) / 2;
     constexpr int RQ = (NBQ + 31) / 32;
     constexpr int RBS = NP / 2;                              // S blocks (upper)
     constexpr int NBS = RBS * (RBS + 1) / 2;
     constexpr int RS = (NBS + 31) / 32;
+    constexpr bool NM_ODD = (NM & 1) != 0;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     SM& sm = *reinterpret_cast<SM*>(smem_raw);
     const int lane = threadIdx.x;
     const int N = P.N;
 
-    // ---- loop-invariant lane -> block assignments -------------------------------------------------------
-    int t_rb[RT], t_cb[RT]; bool t_on[RT];
+    // ---- loop-invariant lane -> block assignments (element offsets into the smem matrices) -----------------
+    int t_a[RT], t_b[RT], t_o[RT]; bool t_on[RT], t_lastcol[RT];
 #pragma unroll
     for (int r = 0; r < RT; r++) {
         int id = lane + 32 * r; t_on[r] = id < NBT; if (!t_on[r]) id = NBT - 1;
-        t_rb[r] = id / CBT; t_cb[r] = id % CBT;
+        const int rb = id / CBT, cb = id % CBT;
+        t_a[r] = 2 * rb; t_b[r] = 2 * cb; t_o[r] = (2 * rb) * LDT + 2 * cb;
+        t_lastcol[r] = NM_ODD && (cb == CBT - 1);   // the block's second column is the pad column, where s is stored
     }
-    int q_rb[RQ], q_cb[RQ]; bool q_on[RQ];
+    int q_a[RQ], q_b[RQ], q_o[RQ], q_i0[RQ], q_j0[RQ]; bool q_on[RQ], q_diag[RQ];
 #pragma unroll
     for (int r = 0; r < RQ; r++) {
         int id = lane + 32 * r; q_on[r] = id < NBQ; if (!q_on[r]) id = NBQ - 1;
         int rb = 0, rem = id;                                  // row rb holds CBQ - rb blocks
         while (rem >= CBQ - rb) { rem -= CBQ - rb; rb++; }
-        q_rb[r] = rb; q_cb[r] = rb + rem;
+        const int cb = rb + rem;
+        q_a[r] = 2 * rb; q_b[r] = 2 * cb; q_o[r] = (2 * rb) * LDT + 2 * cb; q_i0[r] = 2 * rb; q_j0[r] = 2 * cb; q_diag[r] = (rb == cb);
     }
-    int s_rb[RS], s_cb[RS]; bool s_on[RS];
+    int s_a[RS], s_b[RS]; bool s_on[RS], s_diag[RS];
 #pragma unroll
     for (int r = 0; r < RS; r++) {
         int id = lane + 32 * r; s_on[r] = id < NBS; if (!s_on[r]) id = NBS - 1;
         int rb = 0, rem = id;
         while (rem >= RBS - rb) { rem -= RBS - rb; rb++; }
-        s_rb[r] = rb; s_cb[r] = rb + rem;
+        s_a[r] = 2 * rb; s_b[r] = 2 * (rb + rem); s_diag[r] = (rem == 0);
+    }
+
+    // ---- lane-resident AL terms of z_lane (Goal / Bound constraints) ----------------------------------------
+    ALTerm term[MAXT];
+    int nterm = 0;
+    if (FASTAL) {
+#pragma unroll
+        for (int t = 0; t < MAXT; t++) { term[t].first = 1; term[t].last = 0; term[t].p = 0; term[t].base = 0; term[t].sign = 0; term[t].bound = 0; term[t].mu = 1; term[t].eq = false; }
+        if (lane < NM) {
+            for (int ci = 0; ci < P.ncon; ci++) {
+                const DevCon& con = P.cons[ci];
+                const double mu = P.mu[ci];
+                for (int side = 0; side < 2; side++) {
+                    int row = -1; double sign = 1.0, bound = 0.0; bool eq = false;
+                    if (con.kind == CON_GOAL) { if (side == 0 && lane < n) { row = con.row_max[lane]; if (row >= 0) bound = con.a[row]; eq = true; } }
+                    else if (side == 0) { row = con.row_max[lane]; bound = con.a[lane]; }
+                    else { row = con.row_min[lane]; bound = con.b[lane]; sign = -1.0; }
+                    if (row < 0) continue;
+#pragma unroll
+                    for (int t = 0; t < MAXT; t++)
+                        if (t == nterm) { term[t].first = con.first; term[t].last = con.last; term[t].p = con.p; term[t].base = con.offset + row;
+                                          term[t].sign = sign; term[t].bound = bound; term[t].mu = mu; term[t].eq = eq; }
+                    nterm++;
+                }
+            }
+        }
     }
 
     if (lane == 0) {
@@ -151,21 +210,47 @@ __global__ void __launch_bounds__(32) k_riccati(const DevProblem P, int* __restr
         double rho = P.rho[b], drho = P.drho[b];
         int restarts = 0;
         bool failed = false;
+        // address of z_lane at knot k (0-based): x part or u part
+        const double* zbase = (lane < n) ? (X + lane) : (U + (lane < NM ? lane - n : 0));
+        const int zstride = (lane < n) ? n : m;
+
+        // the expansion of one knot for this lane: (gi, hi) = (lz_i, lzz_ii) from z_i and its multipliers
+        auto expand_fast = [&](int k, double zi, const double (&lam)[MAXT], const DevCost& cost, double& gi, double& hi) {
+            if (lane < n) { gi = fma(cost.Qd[lane], zi, cost.q[lane]); hi = cost.Qd[lane]; }
+            else { gi = fma(cost.Rd[lane - n], zi, cost.r[lane - n]); hi = cost.Rd[lane - n]; }
+#pragma unroll
+            for (int t = 0; t < MAXT; t++) {
+                if (k + 1 >= term[t].first && k + 1 <= term[t].last) {
+                    const double lb = fma(-term[t].mu * term[t].sign, zi - term[t].bound, lam[t]);   // lambda - mu c
+                    if (term[t].eq || lb <= 0.0) { gi = fma(-term[t].sign, lb, gi); hi += term[t].mu; }
+                }
+            }
+        };
+        auto load_lams = [&](int k, double (&lam)[MAXT]) {
+#pragma unroll
+            for (int t = 0; t < MAXT; t++) {
+                lam[t] = 0.0;
+                if (k + 1 >= term[t].first && k + 1 <= term[t].last) lam[t] = lam_b[term[t].base + (size_t)(k + 1 - term[t].first) * term[t].p];
+            }
+        };
+
+        // stream [A B]_k into ring slot st with one bulk TMA copy
+        auto issue_ab = [&](int st, int k) {
+            if (lane == 0) {
+                mbar_expect_tx(&sm.bar[st], SM::AB_BYTES);
+                bulk_g2s(sm.ab[st], ABg + (size_t)k * n * LDAB, SM::AB_BYTES, &sm.bar[st]);
+            }
+        };
 
         for (;;) {   // regularisation restart loop
             // ---- prologue: start streaming the last STAGES knots ----------------------------------------
-            if (lane == 0) {
 #pragma unroll
-                for (int s = 0; s < STAGES; s++) {
-                    const int k = N - 2 - s;
-                    if (k >= 0) {
-                        mbar_expect_tx(&sm.bar[s], SM::AB_BYTES);
-                        bulk_g2s(sm.ab[s], ABg + (size_t)k * n * LDAB, SM::AB_BYTES, &sm.bar[s]);
-                    }
-                }
+            for (int s = 0; s < STAGES; s++) {
+                const int k = N - 2 - s;
+                if (k >= 0) issue_ab(s, k);
             }
             // ---- terminal knot: S = lxx_N, s = lx_N (cost + AL) ------------------------------------------
-            for (int e = lane; e < NP * NP; e += 32) sm.S[e] = 0.0;
+            for (int e = lane; e < SM::SROWS * LDS_; e += 32) sm.S[e] = 0.0;
             __syncwarp();
             double s_reg = 0.0;   // lane i < n holds s_i
             {
@@ -173,30 +258,43 @@ __global__ void __launch_bounds__(32) k_riccati(const DevProblem P, int* __restr
                 if (lane < n) {
                     const int i = lane;
                     const double xi = X[(size_t)(N - 1) * n + i];
-                    double gi = cost.q[i], hi = 0.0;
-                    if (cost.diag) { gi = fma(cost.Qd[i], xi, gi); hi = cost.Qd[i]; }
-                    else {
-                        for (int j = 0; j < n; j++) { gi = fma(cost.Q[j * n + i], X[(size_t)(N - 1) * n + j], gi); sm.S[j * NP + i] = cost.Q[j * n + i]; }
-                    }
-                    for (int ci = 0; ci < P.ncon; ci++) {
-                        const DevCon& con = P.cons[ci];
-                        if (N < con.first || N > con.last) continue;
-                        const double mu = P.mu[ci];
-                        const double* lam = lam_b + con.offset + (size_t)(N - con.first) * con.p;
-                        if (con.kind == CON_GOAL) {
-                            const int row = con.row_max[i];
-                            if (row >= 0) { const double lp = lam[row] - mu * (xi - con.a[row]); gi -= lp; hi += mu; }
-                        } else if (con.kind == CON_BOUND) {
-                            int row = con.row_max[i];
-                            if (row >= 0) { const double lb = lam[row] - mu * (xi - con.a[i]); if (lb <= 0) { gi -= lb; hi += mu; } }
-                            row = con.row_min[i];
-                            if (row >= 0) { const double lb = lam[row] - mu * (con.b[i] - xi); if (lb <= 0) { gi += lb; hi += mu; } }
+                    double gi, hi;
+                    if (FASTAL && cost.diag) {
+                        double lam[MAXT];
+                        load_lams(N - 1, lam);
+                        expand_fast(N - 1, xi, lam, cost, gi, hi);
+                        sm.S[i * LDS_ + i] = hi;
+                    } else {
+                        gi = cost.q[i]; hi = 0.0;
+                        if (cost.diag) { gi = fma(cost.Qd[i], xi, gi); hi = cost.Qd[i]; }
+                        else {
+                            for (int j = 0; j < n; j++) { gi = fma(cost.Q[j * n + i], X[(size_t)(N - 1) * n + j], gi); sm.S[j * LDS_ + i] = cost.Q[j * n + i]; }
                         }
+                        for (int ci = 0; ci < P.ncon; ci++) {
+                            const DevCon& con = P.cons[ci];
+                            if (N < con.first || N > con.last) continue;
+                            const double mu = P.mu[ci];
+                            const double* lam = lam_b + con.offset + (size_t)(N - con.first) * con.p;
+                            if (con.kind == CON_GOAL) {
+                                const int row = con.row_max[i];
+                                if (row >= 0) { const double lp = lam[row] - mu * (xi - con.a[row]); gi -= lp; hi += mu; }
+                            } else if (con.kind == CON_BOUND) {
+                                int row = con.row_max[i];
+                                if (row >= 0) { const double lb = lam[row] - mu * (xi - con.a[i]); if (lb <= 0) { gi -= lb; hi += mu; } }
+                                row = con.row_min[i];
+                                if (row >= 0) { const double lb = lam[row] - mu * (con.b[i] - xi); if (lb <= 0) { gi += lb; hi += mu; } }
+                            }
+                        }
+                        if (cost.diag) sm.S[i * LDS_ + i] = hi; else sm.S[i * LDS_ + i] += hi;
                     }
                     s_reg = gi;
-                    if (cost.diag) sm.S[i * NP + i] = hi; else sm.S[i * NP + i] += hi;
                 }
             }
+            // operands of the first stage knot
+            double z_cur = 0.0, lam_cur[MAXT];
+#pragma unroll
+            for (int t = 0; t < MAXT; t++) lam_cur[t] = 0.0;
+            if (lane < NM) { z_cur = zbase[(size_t)(N - 2) * zstride]; if (FASTAL) load_lams(N - 2, lam_cur); }
             __syncwarp();
 
             double dV1 = 0.0, dV2 = 0.0;   // accumulated by lane n
@@ -204,109 +302,212 @@ __global__ void __launch_bounds__(32) k_riccati(const DevProblem P, int* __restr
             int stage = 0;
             int k;
             for (k = N - 2; k >= 0; k--) {
+                // ---- prefetch z_i / multipliers of the next knot (k-1); consumed one iteration later -------
+                double z_nxt = 0.0, lam_nxt[MAXT];
+#pragma unroll
+                for (int t = 0; t < MAXT; t++) lam_nxt[t] = 0.0;
+                if (k > 0 && lane < NM) { z_nxt = zbase[(size_t)(k - 1) * zstride]; if (FASTAL) load_lams(k - 1, lam_nxt); }
                 // ---- cost + AL expansion of knot k: lane i < NM handles z_i (diagonal terms) ------------
                 {
                     const DevCost& cost = P.costs[P.cost_index[k]];
                     double gi = 0.0, hi = 0.0;
                     if (lane < NM) {
                         const int i = lane;
-                        const double zi = (i < n) ? X[(size_t)k * n + i] : U[(size_t)k * m + (i - n)];
-                        if (cost.diag) {
-                            if (i < n) { gi = fma(cost.Qd[i], zi, cost.q[i]); hi = cost.Qd[i]; }
-                            else { gi = fma(cost.Rd[i - n], zi, cost.r[i - n]); hi = cost.Rd[i - n]; }
+                        const double zi = z_cur;
+                        if (FASTAL && cost.diag) {
+                            expand_fast(k, zi, lam_cur, cost, gi, hi);
                         } else {
-                            if (i < n) {
-                                gi = cost.q[i];
-                                for (int j = 0; j < n; j++) gi = fma(cost.Q[j * n + i], X[(size_t)k * n + j], gi);
-                                if (!cost.zeroH) for (int a = 0; a < m; a++) gi = fma(cost.H[i * m + a], U[(size_t)k * m + a], gi);
+                            if (cost.diag) {
+                                if (i < n) { gi = fma(cost.Qd[i], zi, cost.q[i]); hi = cost.Qd[i]; }
+                                else { gi = fma(cost.Rd[i - n], zi, cost.r[i - n]); hi = cost.Rd[i - n]; }
                             } else {
-                                const int a = i - n;
-                                gi = cost.r[a];
-                                for (int j = 0; j < m; j++) gi = fma(cost.R[j * m + a], U[(size_t)k * m + j], gi);
-                                if (!cost.zeroH) for (int j = 0; j < n; j++) gi = fma(cost.H[j * m + a], X[(size_t)k * n + j], gi);
+                                if (i < n) {
+                                    gi = cost.q[i];
+                                    for (int j = 0; j < n; j++) gi = fma(cost.Q[j * n + i], X[(size_t)k * n + j], gi);
+                                    if (!cost.zeroH) for (int a = 0; a < m; a++) gi = fma(cost.H[i * m + a], U[(size_t)k * m + a], gi);
+                                } else {
+                                    const int a = i - n;
+                                    gi = cost.r[a];
+                                    for (int j = 0; j < m; j++) gi = fma(cost.R[j * m + a], U[(size_t)k * m + j], gi);
+                                    if (!cost.zeroH) for (int j = 0; j < n; j++) gi = fma(cost.H[j * m + a], X[(size_t)k * n + j], gi);
+                                }
                             }
-                        }
-                        for (int ci = 0; ci < P.ncon; ci++) {
-                            const DevCon& con = P.cons[ci];
-                            if (k + 1 < con.first || k + 1 > con.last) continue;
-                            const double mu = P.mu[ci];
-                            const double* lam = lam_b + con.offset + (size_t)(k + 1 - con.first) * con.p;
-                            if (con.kind == CON_GOAL) {
-                                const int row = (i < n) ? con.row_max[i] : -1;
-                                if (row >= 0) { const double lp = lam[row] - mu * (zi - con.a[row]); gi -= lp; hi += mu; }
-                            } else if (con.kind == CON_BOUND) {
-                                int row = con.row_max[i];
-                                if (row >= 0) { const double lb = lam[row] - mu * (zi - con.a[i]); if (lb <= 0) { gi -= lb; hi += mu; } }
-                                row = con.row_min[i];
-                                if (row >= 0) { const double lb = lam[row] - mu * (con.b[i] - zi); if (lb <= 0) { gi += lb; hi += mu; } }
+                            for (int ci = 0; ci < P.ncon; ci++) {
+                                const DevCon& con = P.cons[ci];
+                                if (k + 1 < con.first || k + 1 > con.last) continue;
+                                const double mu = P.mu[ci];
+                                const double* lam = lam_b + con.offset + (size_t)(k + 1 - con.first) * con.p;
+                                if (con.kind == CON_GOAL) {
+                                    const int row = (i < n) ? con.row_max[i] : -1;
+                                    if (row >= 0) { const double lp = lam[row] - mu * (zi - con.a[row]); gi -= lp; hi += mu; }
+                                } else if (con.kind == CON_BOUND) {
+                                    int row = con.row_max[i];
+                                    if (row >= 0) { const double lb = lam[row] - mu * (zi - con.a[i]); if (lb <= 0) { gi -= lb; hi += mu; } }
+                                    row = con.row_min[i];
+                                    if (row >= 0) { const double lb = lam[row] - mu * (con.b[i] - zi); if (lb <= 0) { gi += lb; hi += mu; } }
+                                }
                             }
                         }
                     }
-                    if (lane < LDT) { sm.g[lane] = gi; sm.h[lane] = hi; }
+                    if (lane < even_up(NM) + 2) { sm.g[lane] = gi; sm.h[lane] = hi; }
                 }
                 // ---- wait for [A B]_k in the ring ------------------------------------------------------
                 mbar_wait(&sm.bar[stage], (phase_bits >> stage) & 1u);
                 phase_bits ^= (1u << stage);
                 const double* sAB = sm.ab[stage];
 
-                // ---- T = S [A B]  (2x2 blocks) ---------------------------------------------------------
-                {
-                    double acc[RT][4];
+                if constexpr (MMA) {
+                    // lane's fragment coordinates: A(8x4): row fr, col fc ; B(4x8): row fc, col fr ; D(8x8): row fr, cols 2fc, 2fc+1
+                    const int fr = lane >> 2, fc = lane & 3;
+                    // ---- T = S [A B | .]  : MT x NT tiles, KS k-steps of 4 + KR rank-1 updates ------------------
+                    {
+                        double d[MT][NT][2];
 #pragma unroll
-                    for (int r = 0; r < RT; r++) { acc[r][0] = acc[r][1] = acc[r][2] = acc[r][3] = 0.0; }
+                        for (int mi = 0; mi < MT; mi++)
 #pragma unroll
-                    for (int j = 0; j < n; j++) {
+                            for (int ni = 0; ni < NT; ni++) { d[mi][ni][0] = 0.0; d[mi][ni][1] = 0.0; }
 #pragma unroll
+                        for (int kk = 0; kk < KS; kk++) {
+                            double a[MT], bf[NT];
+#pragma unroll
+                            for (int mi = 0; mi < MT; mi++) a[mi] = sm.S[(8 * mi + fr) * LDS_ + 4 * kk + fc];
+#pragma unroll
+                            for (int ni = 0; ni < NT; ni++) bf[ni] = sAB[(4 * kk + fc) * LDABS + 8 * ni + fr];
+#pragma unroll
+                            for (int mi = 0; mi < MT; mi++)
+#pragma unroll
+                                for (int ni = 0; ni < NT; ni++) dmma(d[mi][ni][0], d[mi][ni][1], a[mi], bf[ni]);
+                        }
+#pragma unroll
+                        for (int kr = 0; kr < KR; kr++) {
+                            const int kx = 4 * KS + kr;
+                            double a[MT]; double2 bb[NT];
+#pragma unroll
+                            for (int mi = 0; mi < MT; mi++) a[mi] = sm.S[(8 * mi + fr) * LDS_ + kx];
+#pragma unroll
+                            for (int ni = 0; ni < NT; ni++) bb[ni] = lds128(&sAB[kx * LDABS + 8 * ni + 2 * fc]);
+#pragma unroll
+                            for (int mi = 0; mi < MT; mi++)
+#pragma unroll
+                                for (int ni = 0; ni < NT; ni++) { d[mi][ni][0] = fma(a[mi], bb[ni].x, d[mi][ni][0]); d[mi][ni][1] = fma(a[mi], bb[ni].y, d[mi][ni][1]); }
+                        }
+#pragma unroll
+                        for (int mi = 0; mi < MT; mi++)
+#pragma unroll
+                            for (int ni = 0; ni < NT; ni++) {
+                                const int row = 8 * mi + fr, col = 8 * ni + 2 * fc;
+                                if (col + 1 < NM) sts128(&sm.T[row * LDT + col], d[mi][ni][0], d[mi][ni][1]);
+                                else if (col < NM) sm.T[row * LDT + col] = d[mi][ni][0];      // column NM is reserved for s
+                            }
+                        if (lane < n) sm.T[lane * LDT + NM] = s_reg;
+                    }
+                    __syncwarp();
+                    // ---- [Qzz | Qz] = [A B]' [T | s] + [lzz | lz] : upper tiles (mi <= ni) ---------------------------
+                    {
+                        double d[NQT][2];
+#pragma unroll
+                        for (int t = 0; t < NQT; t++) { d[t][0] = 0.0; d[t][1] = 0.0; }
+#pragma unroll
+                        for (int kk = 0; kk < KS; kk++) {
+                            double a[MQ], bf[NT];
+#pragma unroll
+                            for (int mi = 0; mi < MQ; mi++) a[mi] = sAB[(4 * kk + fc) * LDABS + 8 * mi + fr];
+#pragma unroll
+                            for (int ni = 0; ni < NT; ni++) bf[ni] = sm.T[(4 * kk + fc) * LDT + 8 * ni + fr];
+                            int t = 0;
+#pragma unroll
+                            for (int mi = 0; mi < MQ; mi++)
+#pragma unroll
+                                for (int ni = mi; ni < NT; ni++, t++) dmma(d[t][0], d[t][1], a[mi], bf[ni]);
+                        }
+#pragma unroll
+                        for (int kr = 0; kr < KR; kr++) {
+                            const int kx = 4 * KS + kr;
+                            double a[MQ]; double2 bb[NT];
+#pragma unroll
+                            for (int mi = 0; mi < MQ; mi++) a[mi] = sAB[kx * LDABS + 8 * mi + fr];
+#pragma unroll
+                            for (int ni = 0; ni < NT; ni++) bb[ni] = lds128(&sm.T[kx * LDT + 8 * ni + 2 * fc]);
+                            int t = 0;
+#pragma unroll
+                            for (int mi = 0; mi < MQ; mi++)
+#pragma unroll
+                                for (int ni = mi; ni < NT; ni++, t++) { d[t][0] = fma(a[mi], bb[ni].x, d[t][0]); d[t][1] = fma(a[mi], bb[ni].y, d[t][1]); }
+                        }
+                        int t = 0;
+#pragma unroll
+                        for (int mi = 0; mi < MQ; mi++)
+#pragma unroll
+                            for (int ni = mi; ni < NT; ni++, t++) {
+                                const int row = 8 * mi + fr, col = 8 * ni + 2 * fc;
+                                if (row < NM && col <= NM) {
+                                    double v0 = d[t][0], v1 = d[t][1];
+                                    if (row == col) v0 += sm.h[row];
+                                    if (row == col + 1) v1 += sm.h[row];
+                                    if (col == NM) v0 += sm.g[row];
+                                    if (col + 1 == NM) v1 += sm.g[row];
+                                    sts128(&sm.Q[row * LDT + col], v0, v1);
+                                }
+                            }
+                    }
+                    __syncwarp();
+                } else {
+                    // ---- T = S [A B]  (2x2 blocks), extra column NM <- s ---------------------------------------
+                    {
+                        double acc[RT][4];
+    #pragma unroll
+                        for (int r = 0; r < RT; r++) { acc[r][0] = acc[r][1] = acc[r][2] = acc[r][3] = 0.0; }
+    #pragma unroll
+                        for (int j = 0; j < n; j++) {
+    #pragma unroll
+                            for (int r = 0; r < RT; r++) {
+                                const double2 a = lds128(&sm.S[j * LDS_ + t_a[r]]);
+                                const double2 bb = lds128(&sAB[j * LDABS + t_b[r]]);
+                                fma2x2(acc[r], a, bb);
+                            }
+                        }
+    #pragma unroll
                         for (int r = 0; r < RT; r++) {
-                            const double2 a = lds128(&sm.S[j * NP + 2 * t_rb[r]]);
-                            const double2 bb = lds128(&sAB[j * LDAB + 2 * t_cb[r]]);
-                            fma2x2(acc[r], a, bb);
+                            if (t_on[r]) {
+                                if (t_lastcol[r]) { sm.T[t_o[r]] = acc[r][0]; sm.T[t_o[r] + LDT] = acc[r][2]; }   // leave column NM to s
+                                else { sts128(&sm.T[t_o[r]], acc[r][0], acc[r][1]); sts128(&sm.T[t_o[r] + LDT], acc[r][2], acc[r][3]); }
+                            }
                         }
+                        if (lane < n) sm.T[lane * LDT + NM] = s_reg;
                     }
-#pragma unroll
-                    for (int r = 0; r < RT; r++) {
-                        if (t_on[r]) {
-                            sts128(&sm.T[(2 * t_rb[r]) * LDT + 2 * t_cb[r]], acc[r][0], acc[r][1]);
-                            sts128(&sm.T[(2 * t_rb[r] + 1) * LDT + 2 * t_cb[r]], acc[r][2], acc[r][3]);
-                        }
-                    }
-                }
-                __syncwarp();
-                if (lane < n) sm.T[lane * LDT + NM] = s_reg;   // extra column: s
-                __syncwarp();
+                    __syncwarp();
 
-                // ---- [Qzz | Qz] = [A B]' [T | s] + [lzz | lz]  (upper 2x2 blocks) -----------------------
-                {
-                    double acc[RQ][4];
-#pragma unroll
-                    for (int r = 0; r < RQ; r++) { acc[r][0] = acc[r][1] = acc[r][2] = acc[r][3] = 0.0; }
-#pragma unroll
-                    for (int j = 0; j < n; j++) {
-#pragma unroll
+                    // ---- [Qzz | Qz] = [A B]' [T | s] + [lzz | lz]  (upper 2x2 blocks) -----------------------
+                    {
+                        double acc[RQ][4];
+    #pragma unroll
+                        for (int r = 0; r < RQ; r++) { acc[r][0] = acc[r][1] = acc[r][2] = acc[r][3] = 0.0; }
+    #pragma unroll
+                        for (int j = 0; j < n; j++) {
+    #pragma unroll
+                            for (int r = 0; r < RQ; r++) {
+                                const double2 a = lds128(&sAB[j * LDABS + q_a[r]]);
+                                const double2 bb = lds128(&sm.T[j * LDT + q_b[r]]);
+                                fma2x2(acc[r], a, bb);
+                            }
+                        }
+    #pragma unroll
                         for (int r = 0; r < RQ; r++) {
-                            const double2 a = lds128(&sAB[j * LDAB + 2 * q_rb[r]]);
-                            const double2 bb = lds128(&sm.T[j * LDT + 2 * q_cb[r]]);
-                            fma2x2(acc[r], a, bb);
+                            const int i0 = q_i0[r], j0 = q_j0[r];
+                            const double2 gg = lds128(&sm.g[i0]);
+                            if (q_diag[r]) { const double2 hh = lds128(&sm.h[i0]); acc[r][0] += hh.x; acc[r][3] += hh.y; }
+                            if (j0 == NM) { acc[r][0] += gg.x; acc[r][2] += gg.y; }
+                            if (j0 + 1 == NM) { acc[r][1] += gg.x; acc[r][3] += gg.y; }
+                            if (q_on[r]) {
+                                sts128(&sm.Q[q_o[r]], acc[r][0], acc[r][1]);
+                                sts128(&sm.Q[q_o[r] + LDT], acc[r][2], acc[r][3]);
+                            }
                         }
                     }
-#pragma unroll
-                    for (int r = 0; r < RQ; r++) {
-                        const int i0 = 2 * q_rb[r], j0 = 2 * q_cb[r];
-                        if (q_rb[r] == q_cb[r]) { acc[r][0] += sm.h[i0]; acc[r][3] += sm.h[i0 + 1]; }
-                        if (j0 == NM) { acc[r][0] += sm.g[i0]; acc[r][2] += sm.g[i0 + 1]; }
-                        if (j0 + 1 == NM) { acc[r][1] += sm.g[i0]; acc[r][3] += sm.g[i0 + 1]; }
-                        if (q_on[r]) {
-                            sts128(&sm.Q[i0 * LDT + j0], acc[r][0], acc[r][1]);
-                            sts128(&sm.Q[(i0 + 1) * LDT + j0], acc[r][2], acc[r][3]);
-                        }
-                    }
+                    __syncwarp();
                 }
-                __syncwarp();
                 // the stage buffer is free: refill it with the knot STAGES steps ahead
-                if (lane == 0 && k - STAGES >= 0) {
-                    mbar_expect_tx(&sm.bar[stage], SM::AB_BYTES);
-                    bulk_g2s(sm.ab[stage], ABg + (size_t)(k - STAGES) * n * LDAB, SM::AB_BYTES, &sm.bar[stage]);
-                }
+                if (k - STAGES >= 0) issue_ab(stage, k - STAGES);
                 stage = (stage + 1 == STAGES) ? 0 : stage + 1;
 
                 // dense cost Hessian (QuadraticCost): add the off-diagonal entries of lzz to the upper part of Q
@@ -329,49 +530,54 @@ __global__ void __launch_bounds__(32) k_riccati(const DevProblem P, int* __restr
                     }
                 }
 
-                // ---- gains: one lane per column of [Qux | Qu] -------------------------------------------
-                double Lc[M_ * (M_ + 1) / 2];   // Cholesky factor of Quu + rho I, packed lower by rows
-                double Quu[M_ * (M_ + 1) / 2];
+                // ---- gains: LDL' of Quu + rho I, one lane per column of [Qux | Qu] -------------------------
+                double Quu[M_ * (M_ + 1) / 2];           // packed lower by rows
+                double Lf[M_ * (M_ + 1) / 2];            // unit-lower L (off-diagonal), diagonal slots hold 1/d_j
                 {
 #pragma unroll
                     for (int a = 0; a < m; a++)
 #pragma unroll
                         for (int c = 0; c <= a; c++) Quu[a * (a + 1) / 2 + c] = sm.Q[(n + c) * LDT + (n + a)];   // upper entry (c <= a)
+                    double dj[M_];
 #pragma unroll
-                    for (int a = 0; a < m; a++) {
+                    for (int j = 0; j < m; j++) {
+                        double t = Quu[j * (j + 1) / 2 + j] + rho;
 #pragma unroll
-                        for (int c = 0; c <= a; c++) {
-                            double t = Quu[a * (a + 1) / 2 + c] + ((a == c) ? rho : 0.0);
+                        for (int r = 0; r < j; r++) t = fma(-Lf[j * (j + 1) / 2 + r] * Lf[j * (j + 1) / 2 + r], dj[r], t);
+                        if (!(t > 0.0) || !isfinite(t)) ok = false;
+                        dj[j] = t;
+                        const double inv = __drcp_rn(t);
+                        Lf[j * (j + 1) / 2 + j] = inv;
 #pragma unroll
-                            for (int r = 0; r < c; r++) t = fma(-Lc[a * (a + 1) / 2 + r], Lc[c * (c + 1) / 2 + r], t);
-                            if (a == c) {
-                                if (!(t > 0.0) || !isfinite(t)) ok = false;
-                                Lc[a * (a + 1) / 2 + a] = sqrt(t);
-                            } else Lc[a * (a + 1) / 2 + c] = t / Lc[c * (c + 1) / 2 + c];
+                        for (int i = j + 1; i < m; i++) {
+                            double v = Quu[i * (i + 1) / 2 + j];
+#pragma unroll
+                            for (int r = 0; r < j; r++) v = fma(-Lf[i * (i + 1) / 2 + r] * Lf[j * (j + 1) / 2 + r], dj[r], v);
+                            Lf[i * (i + 1) / 2 + j] = v * inv;
                         }
                     }
                 }
                 if (!ok) break;   // uniform across the warp (every lane factors the same matrix)
-                double kc[M_];    // column of K (lane < n) or d (lane == n)
-                double rhs[M_];
                 {
                     const int c = (lane <= n) ? lane : n;
+                    double rhs[M_], kc[M_];
 #pragma unroll
                     for (int a = 0; a < m; a++) rhs[a] = (c < n) ? sm.Q[c * LDT + (n + a)] : sm.Q[(n + a) * LDT + NM];   // Qux[a][c] | Qu[a]
-                    double y[M_];
 #pragma unroll
-                    for (int a = 0; a < m; a++) {
+                    for (int a = 0; a < m; a++) {      // forward: L y = -rhs
                         double t = -rhs[a];
 #pragma unroll
-                        for (int r = 0; r < a; r++) t = fma(-Lc[a * (a + 1) / 2 + r], y[r], t);
-                        y[a] = t / Lc[a * (a + 1) / 2 + a];
+                        for (int r = 0; r < a; r++) t = fma(-Lf[a * (a + 1) / 2 + r], kc[r], t);
+                        kc[a] = t;
                     }
 #pragma unroll
-                    for (int a = m - 1; a >= 0; a--) {
-                        double t = y[a];
+                    for (int a = 0; a < m; a++) kc[a] *= Lf[a * (a + 1) / 2 + a];   // D^-1
 #pragma unroll
-                        for (int r = a + 1; r < m; r++) t = fma(-Lc[r * (r + 1) / 2 + a], kc[r], t);
-                        kc[a] = t / Lc[a * (a + 1) / 2 + a];
+                    for (int a = m - 1; a >= 0; a--) {  // backward: L' x = y
+                        double t = kc[a];
+#pragma unroll
+                        for (int r = a + 1; r < m; r++) t = fma(-Lf[r * (r + 1) / 2 + a], kc[r], t);
+                        kc[a] = t;
                     }
                     if (lane <= n) {
 #pragma unroll
@@ -404,16 +610,16 @@ __global__ void __launch_bounds__(32) k_riccati(const DevProblem P, int* __restr
                     double acc[RS][4];
 #pragma unroll
                     for (int r = 0; r < RS; r++) {
-                        const double2 q0 = lds128(&sm.Q[(2 * s_rb[r]) * LDT + 2 * s_cb[r]]);
-                        const double2 q1 = lds128(&sm.Q[(2 * s_rb[r] + 1) * LDT + 2 * s_cb[r]]);
+                        const double2 q0 = lds128(&sm.Q[s_a[r] * LDT + s_b[r]]);
+                        const double2 q1 = lds128(&sm.Q[(s_a[r] + 1) * LDT + s_b[r]]);
                         acc[r][0] = q0.x; acc[r][1] = q0.y; acc[r][2] = q1.x; acc[r][3] = q1.y;
                     }
 #pragma unroll
                     for (int a = 0; a < m; a++) {
 #pragma unroll
                         for (int r = 0; r < RS; r++) {
-                            const double2 w = lds128(&sm.W[a * LDK + 2 * s_rb[r]]);
-                            const double2 kk = lds128(&sm.K[a * LDK + 2 * s_cb[r]]);
+                            const double2 w = lds128(&sm.W[a * LDK + s_a[r]]);
+                            const double2 kk = lds128(&sm.K[a * LDK + s_b[r]]);
                             fma2x2(acc[r], w, kk);
                         }
                     }
@@ -427,19 +633,22 @@ __global__ void __launch_bounds__(32) k_riccati(const DevProblem P, int* __restr
 #pragma unroll
                     for (int r = 0; r < RS; r++) {
                         if (!s_on[r]) continue;
-                        const int i0 = 2 * s_rb[r], j0 = 2 * s_cb[r];
-                        if (s_rb[r] == s_cb[r]) {
+                        const int i0 = s_a[r], j0 = s_b[r];
+                        if (s_diag[r]) {
                             const double off = 0.5 * (acc[r][1] + acc[r][2]);
-                            sts128(&sm.S[i0 * NP + j0], acc[r][0], off);
-                            sts128(&sm.S[(i0 + 1) * NP + j0], off, acc[r][3]);
+                            sts128(&sm.S[i0 * LDS_ + j0], acc[r][0], off);
+                            sts128(&sm.S[(i0 + 1) * LDS_ + j0], off, acc[r][3]);
                         } else {
-                            sts128(&sm.S[i0 * NP + j0], acc[r][0], acc[r][1]);
-                            sts128(&sm.S[(i0 + 1) * NP + j0], acc[r][2], acc[r][3]);
-                            sts128(&sm.S[j0 * NP + i0], acc[r][0], acc[r][2]);
-                            sts128(&sm.S[(j0 + 1) * NP + i0], acc[r][1], acc[r][3]);
+                            sts128(&sm.S[i0 * LDS_ + j0], acc[r][0], acc[r][1]);
+                            sts128(&sm.S[(i0 + 1) * LDS_ + j0], acc[r][2], acc[r][3]);
+                            sts128(&sm.S[j0 * LDS_ + i0], acc[r][0], acc[r][2]);
+                            sts128(&sm.S[(j0 + 1) * LDS_ + i0], acc[r][1], acc[r][3]);
                         }
                     }
                 }
+                z_cur = z_nxt;
+#pragma unroll
+                for (int t = 0; t < MAXT; t++) lam_cur[t] = lam_nxt[t];
                 __syncwarp();
             }   // knots
 
@@ -471,11 +680,11 @@ __global__ void __launch_bounds__(32) k_riccati(const DevProblem P, int* __restr
     }
 }
 
-template <int N_, int M_>
-cudaError_t launch_riccati_t(const DevProblem& P, int* work_counter, cudaStream_t s) {
-    constexpr int STAGES = 3;
-    using SM = RiccatiSmem<N_, M_, STAGES>;
-    auto kern = k_riccati<N_, M_, STAGES>;
+template <int N_, int M_, bool FASTAL, int STAGES, int MINB>
+cudaError_t launch_riccati_v(const DevProblem& P, int* work_counter, cudaStream_t s) {
+    constexpr bool MMA = (N_ >= 8);
+    using SM = RiccatiSmem<N_, M_, STAGES, MMA>;
+    auto kern = k_riccati<N_, M_, STAGES, FASTAL, MMA, MINB>;
     static bool configured = false;
     static int ctas_per_sm = 1, num_sms = 1;
     const int smem = (int)sizeof(SM);
@@ -497,12 +706,37 @@ cudaError_t launch_riccati_t(const DevProblem& P, int* work_counter, cudaStream_
     return cudaGetLastError();
 }
 
+template <int N_, int M_, bool FASTAL>
+cudaError_t launch_riccati_t(const DevProblem& P, int* work_counter, cudaStream_t s) {
+    if constexpr (N_ >= 8) {
+        // tuning knob (occupancy vs registers / ring depth); default chosen from the sweep in profiles/r01_notes.md
+        static int variant = -1;
+        if (variant < 0) { const char* v = getenv("TO_RICCATI_VARIANT"); variant = v ? atoi(v) : 1; }
+        switch (variant) {
+            case 1: return launch_riccati_v<N_, M_, FASTAL, 2, 16>(P, work_counter, s);
+            case 2: return launch_riccati_v<N_, M_, FASTAL, 2, 20>(P, work_counter, s);
+            case 3: return launch_riccati_v<N_, M_, FASTAL, 3, 16>(P, work_counter, s);
+            case 4: return launch_riccati_v<N_, M_, FASTAL, 2, 12>(P, work_counter, s);
+            default: return launch_riccati_v<N_, M_, FASTAL, 3, 12>(P, work_counter, s);
+        }
+    } else {
+        return launch_riccati_v<N_, M_, FASTAL, 3, 16>(P, work_counter, s);
+    }
+}
+
+template <int N_, int M_>
+cudaError_t launch_riccati_nm(const DevProblem& P, int* work_counter, cudaStream_t s) {
+    // the lane-resident AL terms hold at most MAXT rows per z entry (upper + lower bound + goal)
+    if (P.max_terms_per_z <= MAXT) return launch_riccati_t<N_, M_, true>(P, work_counter, s);
+    return launch_riccati_t<N_, M_, false>(P, work_counter, s);
+}
+
 }  // namespace
 
 cudaError_t launch_backward(const DevProblem& P, int* work_counter, cudaStream_t s) {
-    if (P.n == 13 && P.m == 4) return launch_riccati_t<13, 4>(P, work_counter, s);
-    if (P.n == 4 && P.m == 1) return launch_riccati_t<4, 1>(P, work_counter, s);
-    if (P.n == 4 && P.m == 2) return launch_riccati_t<4, 2>(P, work_counter, s);
-    if (P.n == 2 && P.m == 1) return launch_riccati_t<2, 1>(P, work_counter, s);
+    if (P.n == 13 && P.m == 4) return launch_riccati_nm<13, 4>(P, work_counter, s);
+    if (P.n == 4 && P.m == 1) return launch_riccati_nm<4, 1>(P, work_counter, s);
+    if (P.n == 4 && P.m == 2) return launch_riccati_nm<4, 2>(P, work_counter, s);
+    if (P.n == 2 && P.m == 1) return launch_riccati_nm<2, 1>(P, work_counter, s);
     return cudaErrorNotSupported;
 }

@@ -33,6 +33,9 @@
 
 namespace oracle {
 
+constexpr int MAXP = 32;   // rows of one constraint at one knot
+static const double ZERO_U[MAXM] = {0};
+
 // ------------------------------------------------------------------------------------------------
 // Quadratic cost  (src/cost_functions.jl)
 struct Cost {
@@ -451,14 +454,14 @@ inline void cost_knots(const Problem& P, const double* X, const double* U, doubl
 }
 // cost  src/objective.jl:89-93
 inline double cost_total(const Problem& P, const double* X, const double* U) {
-    std::vector<double> Jk(P.N);
-    cost_knots(P, X, U, Jk.data());
-    double s = 0;
-    for (int k = 0; k < P.N; k++) s += Jk[k];
+    double s = 0;   // same left-to-right summation as sum(get_J(obj))
+    for (int k = 0; k < P.N; k++) {
+        const bool last = (k == P.N - 1);
+        s += cost_value(P.costs[P.cost_index[k]], &X[k * P.n], last ? nullptr : &U[k * P.m], !last);
+    }
     return s;
 }
 
-static const double ZERO_U[MAXM] = {0};
 
 // evaluate_constraints!  src/abstract_constraint.jl:200-225 : vals[nknots][p] for one constraint
 inline void evaluate_constraints(const Problem& P, int ci, const double* X, const double* U, double* vals) {
@@ -498,17 +501,17 @@ inline double max_violation(const Problem& P, const double* X, const double* U) 
 //   lbar = lambda - mu c ; lp = Pi_{K*}(lbar) ; J_AL = (|lp|^2 - |lambda|^2) / (2 mu)
 inline double al_penalty(const Problem& P, const double* X, const double* U, const double* lam) {
     double J = 0;
-    std::vector<double> c, lbar, lp;
+    double c[MAXP], lbar[MAXP], lp[MAXP];
     for (size_t ci = 0; ci < P.cons.size(); ci++) {
         const Constraint& con = P.cons[ci];
         const int p = con.p; const double mu = P.mu[ci];
-        c.assign((size_t)con.nknots() * p, 0.0); lbar.resize(p); lp.resize(p);
-        evaluate_constraints(P, (int)ci, X, U, c.data());
         const double* l = lam + P.con_offset[ci];
         for (int k = 0; k < con.nknots(); k++) {
+            const int k1 = con.first + k;
+            con_evaluate(con, &X[(k1 - 1) * P.n], (k1 == P.N) ? ZERO_U : &U[(k1 - 1) * P.m], c);
             double a = 0, bsum = 0;
-            for (int i = 0; i < p; i++) lbar[i] = l[k * p + i] - mu * c[k * p + i];
-            projection(dualcone(con.sense), lbar.data(), p, lp.data());
+            for (int i = 0; i < p; i++) lbar[i] = l[k * p + i] - mu * c[i];
+            projection(dualcone(con.sense), lbar, p, lp);
             for (int i = 0; i < p; i++) { a += lp[i] * lp[i]; bsum += l[k * p + i] * l[k * p + i]; }
             J += (a - bsum) / (2 * mu);
         }
@@ -562,19 +565,34 @@ inline void cost_expansion(const Problem& P, const double* X, const double* U, c
     const Cost& c = P.costs[P.cost_index[k]];
     cost_gradient(c, x, u, last, grad);
     cost_hessian(c, last, hess, true);
-    std::vector<double> cv, jac, lbar, lp, Dm, tmp;
+    double cv[MAXP], jac[MAXP * (MAXN + MAXM)], lbar[MAXP], lp[MAXP], Dm[MAXP * MAXP], tmp[MAXP * (MAXN + MAXM)];   // no heap traffic in the hot loop
     for (size_t ci = 0; ci < P.cons.size(); ci++) {
         const Constraint& con = P.cons[ci];
         if (k + 1 < con.first || k + 1 > con.last) continue;
         const int p = con.p; const double mu = P.mu[ci];
-        cv.resize(p); jac.resize((size_t)p * nm); lbar.resize(p); lp.resize(p); Dm.resize((size_t)p * p); tmp.resize((size_t)p * nm);
-        con_evaluate(con, x, u, cv.data());
-        con_jacobian(con, x, u, jac.data());
+        con_evaluate(con, x, u, cv);
+        if (con.kind == CON_GOAL || con.kind == CON_BOUND) {
+            // selector Jacobians (+-1 entries, src/constraints.jl:62-68, :757-765): same arithmetic as the dense path
+            // below, written row by row so the CPU baseline is not handicapped by multiplying structural zeros
+            const double* l0 = lam + P.con_offset[ci] + (size_t)(k + 1 - con.first) * p;
+            const int dc0 = dualcone(con.sense);
+            int row = 0;
+            auto add_row = [&](int j, double sgn) {
+                const double lb = l0[row] - mu * cv[row];
+                const bool active = (dc0 == CONE_IDENTITY) || (lb <= 0);
+                if (active && (j < n || !last)) { grad[j] -= sgn * lb; hess[j * nm + j] += mu; }
+                row++;
+            };
+            if (con.kind == CON_GOAL) for (int i = 0; i < p; i++) add_row(con.inds[i], 1.0);
+            else { for (int j : con.a_max) add_row(j, 1.0); for (int j : con.a_min) add_row(j, -1.0); }
+            continue;
+        }
+        con_jacobian(con, x, u, jac);
         const double* l = lam + P.con_offset[ci] + (size_t)(k + 1 - con.first) * p;
         for (int i = 0; i < p; i++) lbar[i] = l[i] - mu * cv[i];
         const int dc = dualcone(con.sense);
-        projection(dc, lbar.data(), p, lp.data());
-        grad_projection(dc, lbar.data(), p, Dm.data());
+        projection(dc, lbar, p, lp);
+        grad_projection(dc, lbar, p, Dm);
         // tmp = D * cz  (p x nm)
         for (int j = 0; j < nm; j++)
             for (int i = 0; i < p; i++) {

@@ -1,0 +1,100 @@
+"""CPU tests of the host side: the C-ABI library loads and exports every symbol include/*.h declares (no compute
+calls without a GPU), the mirror API's host logic, and the multi-rank path (gloo, world_size 2)."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+import textwrap
+
+import numpy as np
+import pytest
+
+import trajopt_b200 as TO
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "trajopt_b200.h")).read()
+    declared = sorted(set(re.findall(r"\b(to_[a-z_0-9]+)\s*\(", hdr)))
+    assert len(declared) >= 45
+    lib = ctypes.CDLL(TO.capi.LIB_PATH)
+    missing = [s for s in declared if not hasattr(lib, s)]
+    assert not missing, f"libtrajopt_b200.so lacks {missing}"
+    assert sorted(TO.capi.EXPORTED_SYMBOLS) == declared
+
+
+def test_no_cpu_fallback_without_a_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    obj = TO.LQRObjective(np.eye(2), np.eye(1), np.eye(2), np.zeros(2), 5)
+    with pytest.raises(TO.TrajOptError, match="no CPU fallback"):
+        TO.Problem(TO.DoubleIntegrator(1), obj, np.zeros(2), 1.0)
+
+
+def test_product_never_references_the_oracle():
+    pkg = os.path.join(ROOT, "trajectoryoptimization.jl_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".jl")):
+                text = open(os.path.join(dirpath, f), errors="ignore").read()
+                assert "liboracle" not in text and "orc_" not in text and "oracle_binding" not in text, f
+
+
+def test_constraint_list_and_objective_host_logic():
+    n, m, N = 4, 1, 11
+    cons = TO.ConstraintList(n, m, N)
+    goal = TO.GoalConstraint(np.ones(n))
+    bnd = TO.BoundConstraint(n, m, u_min=-1, u_max=1)
+    TO.add_constraint(cons, bnd, (1, N - 1))
+    TO.add_constraint(cons, goal, N)
+    assert np.array_equal(TO.num_constraints(cons), [2] * (N - 1) + [n])      # src/constraint_list.jl:198-206
+    assert [c for _, c in cons.zip()] == [bnd, goal] and list(cons.zip())[0][0] == (1, N - 1)
+    with pytest.raises(TO.DimensionMismatch):                                   # src/constraint_list.jl:108-110
+        TO.add_constraint(cons, TO.BoundConstraint(n + 1, m, u_min=-1, u_max=1), 1)
+    c1 = TO.DiagonalCost(np.ones(n), np.ones(m))
+    c2 = TO.QuadraticCost(np.eye(n), np.eye(m), H=np.ones((m, n)))
+    s = c1 + c2                                                                 # +(c1, c2) src/cost_functions.jl:259-270
+    assert isinstance(s, TO.QuadraticCost) and np.allclose(s.Q, 2 * np.eye(n)) and np.allclose(s.H, 1.0)
+    obj = TO.Objective([c1] * (N - 1), c1)                                      # Objective(costs, cost_term) src/objective.jl:78-81
+    assert len(obj) == N
+    trk = TO.TrackingObjective(np.eye(n), np.eye(m), np.ones((N, n)), np.zeros((N - 1, m)))
+    assert np.allclose(trk[3].q, -np.ones(n)) and trk[-1].terminal              # src/objective.jl:190-196
+    assert TO.multi_gpu.shard_slice(10, 0, 4) == (0, 3) and TO.multi_gpu.shard_slice(10, 3, 4) == (8, 10)
+    assert sum(b - a for a, b in (TO.multi_gpu.shard_slice(4096, r, 8) for r in range(8))) == 4096
+
+
+WORKER = textwrap.dedent("""
+    import os, sys
+    sys.path.insert(0, {root!r}); sys.path.insert(0, os.path.join({root!r}, "tests"))
+    import numpy as np, torch, torch.distributed as dist
+    import trajopt_b200 as TO
+    from oracle_binding import OracleProblem
+    dist.init_process_group("gloo", init_method="tcp://127.0.0.1:{port}", rank=int(sys.argv[1]), world_size=2)
+    rank = dist.get_rank()
+    B = 6
+    lo, hi = TO.multi_gpu.shard_slice(B, rank, 2)
+    full = TO.problems.cartpole(B=B, N=31, cls=OracleProblem, u_bound=3.0, goal=True)
+    shard = TO.problems.cartpole(B=hi - lo, N=31, cls=OracleProblem, u_bound=3.0, goal=True)
+    TO.set_initial_state(shard, full.x0[lo:hi]); TO.initial_controls(shard, TO.controls(full)[lo:hi])
+    for p in (full, shard):
+        TO.rollout(p); TO.ilqr_step(p, 2)
+    g = TO.multi_gpu.global_merit(shard)            # SUM / MAX all-reduce over the two shards
+    ref = np.array([TO.merit(full).sum(), TO.max_violation(full).max()])
+    assert np.allclose(g.numpy(), ref, rtol=1e-12), (g, ref)
+    assert np.allclose(TO.states(shard), TO.states(full)[lo:hi], rtol=0, atol=0)   # sharding does not change any instance
+    dist.destroy_process_group()
+    print("rank", rank, "ok")
+""")
+
+
+def test_two_rank_gloo_sharding_and_merit_allreduce(tmp_path):
+    """the N>1 path on CPU: contiguous batch shards, no data-path collective, one SUM/MAX all-reduce of the merit."""
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER.format(root=ROOT, port=29000 + os.getpid() % 2000))
+    procs = [subprocess.Popen([sys.executable, str(script), str(r)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True) for r in range(2)]
+    outs = [p.communicate(timeout=240)[0] for p in procs]
+    for r, (p, o) in enumerate(zip(procs, outs)):
+        assert p.returncode == 0 and f"rank {r} ok" in o, o

@@ -11,3 +11,4 @@ root (``import trajopt_b200 as TO``).  Layout:
 from .api import *  # noqa: F401,F403
 from . import _capi  # noqa: F401
 from . import problems  # noqa: F401,E402
+from . import multi_gpu  # noqa: F401,E402

@@ -1,0 +1,154 @@
+# B200TrajOpt.jl -- thin ccall shim over libtrajopt_b200.so (include/trajopt_b200.h).
+#
+# NOT RUNNABLE IN THIS REPO'S IMAGE (no Julia there); kept syntactically careful and reviewed against the header.
+# It gives Julia host code (and Altro.jl) a `BatchedProblem` that is built from an ordinary
+# TrajectoryOptimization.Problem and overloads the functions a solver calls on it
+# (rollout!, cost, evaluate_constraints!, ... -- SURVEY.md 2.3), so the hot path runs on the GPU for a whole batch.
+module B200TrajOpt
+
+using TrajectoryOptimization
+using RobotDynamics
+using LinearAlgebra
+const TO = TrajectoryOptimization
+const RD = RobotDynamics
+
+const libb200 = get(ENV, "LIBTRAJOPT_B200", "libtrajopt_b200.so")
+
+# ---- C structs (must match include/trajopt_b200.h field for field) ------------------------------------------
+struct ToCostSpec
+    kind::Int32; terminal::Int32
+    Q::Ptr{Float64}; R::Ptr{Float64}; H::Ptr{Float64}; q::Ptr{Float64}; r::Ptr{Float64}
+    c::Float64
+end
+struct ToConstraintSpec
+    kind::Int32; first::Int32; last::Int32; sense::Int32; p::Int32; flag::Int32; ninds::Int32
+    inds::Ptr{Int32}; a::Ptr{Float64}; b::Ptr{Float64}; c::Ptr{Float64}; rad::Ptr{Float64}
+    val::Float64
+end
+struct ToSpec
+    model::Int32; n::Int32; m::Int32; N::Int32; B::Int32; device::Int32; nparams::Int32
+    params::Ptr{Float64}; dt::Ptr{Float64}; t0::Float64
+    ncost::Int32; costs::Ptr{ToCostSpec}; cost_index::Ptr{Int32}
+    ncon::Int32; cons::Ptr{ToConstraintSpec}
+end
+
+const TO_EDIM = -2
+const TO_EINVAL = -1
+
+function check(h::Ptr{Cvoid}, rc::Cint)
+    rc == 0 && return nothing
+    msg = unsafe_string(ccall((:to_last_error, libb200), Cstring, (Ptr{Cvoid},), h))
+    rc == TO_EDIM && throw(DimensionMismatch(msg))     # same exception types as src/problem.jl:64-68, :87-91
+    rc == TO_EINVAL && throw(ArgumentError(msg))
+    error("libtrajopt_b200 [$rc]: $msg")
+end
+
+model_id(::Any) = error("model not available on the device; supported: DoubleIntegrator, Cartpole, Quadrotor, Acrobot")
+
+mutable struct BatchedProblem
+    h::Ptr{Cvoid}
+    prob::TO.Problem          # the template instance (objective / constraint objects stay the reference's)
+    B::Int
+    keep::Vector{Any}         # GC roots of every array whose pointer went into the spec
+end
+
+sense_code(::TO.Equality) = Int32(0)
+sense_code(::TO.Inequality) = Int32(1)
+sense_code(::TO.SecondOrderCone) = Int32(2)
+
+"""
+    BatchedProblem(prob::TO.Problem, model_id, B; device=0, params=Float64[])
+
+Describe `prob` (objective = vector of QuadraticCostFunctions, ConstraintList of Goal/Bound/Linear/Circle/Sphere/Norm)
+to the library and allocate a batch of `B` instances on `device`.
+"""
+function BatchedProblem(prob::TO.Problem, mid::Integer, B::Integer; device::Integer=0, params::Vector{Float64}=Float64[])
+    n, m, N = RD.dims(prob, 1)
+    keep = Any[]
+    root(x) = (push!(keep, x); x)
+    obj = TO.get_objective(prob)
+    costs = ToCostSpec[]
+    index = Int32[]
+    seen = IdDict{Any,Int32}()
+    for k = 1:N
+        c = obj[k]
+        if !haskey(seen, c)
+            isdiag = TO.is_diag(c)
+            Q = root(isdiag ? Vector{Float64}(diag(c.Q)) : Matrix{Float64}(c.Q))
+            R = root(isdiag ? Vector{Float64}(diag(c.R)) : Matrix{Float64}(c.R))
+            H = isdiag ? C_NULL : pointer(root(Matrix{Float64}(c.H)))
+            q = root(Vector{Float64}(c.q)); r = root(Vector{Float64}(c.r))
+            push!(costs, ToCostSpec(isdiag ? 0 : 1, c.terminal ? 1 : 0, pointer(Q), pointer(R), H, pointer(q), pointer(r), c.c))
+            seen[c] = Int32(length(costs) - 1)
+        end
+        push!(index, seen[c])
+    end
+    cons = ToConstraintSpec[]
+    for (inds, con) in zip(TO.get_constraints(prob))
+        f, l = Int32(first(inds)), Int32(last(inds))
+        if con isa TO.GoalConstraint
+            ii = root(Vector{Int32}(con.inds)); a = root(Vector{Float64}(con.xf))
+            push!(cons, ToConstraintSpec(0, f, l, 0, 0, 0, length(ii), pointer(ii), pointer(a), C_NULL, C_NULL, C_NULL, 0.0))
+        elseif con isa TO.BoundConstraint
+            a = root(Vector{Float64}(con.z_max)); b = root(Vector{Float64}(con.z_min))
+            push!(cons, ToConstraintSpec(1, f, l, 1, 0, 0, 0, C_NULL, pointer(a), pointer(b), C_NULL, C_NULL, 0.0))
+        else
+            error("constraint $(typeof(con)) : add its descriptor here (kinds 2-5 of to_con_kind)")
+        end
+    end
+    dt = root(Vector{Float64}([RD.timestep(z) for z in TO.get_trajectory(prob)][1:N-1]))
+    root(costs); root(index); root(cons); root(params)
+    spec = Ref(ToSpec(mid, n, m, N, B, device, length(params), isempty(params) ? C_NULL : pointer(params), pointer(dt),
+                      TO.get_initial_time(prob), length(costs), pointer(costs), pointer(index), length(cons),
+                      isempty(cons) ? C_NULL : pointer(cons)))
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    rc = GC.@preserve keep ccall((:to_create, libb200), Cint, (Ref{ToSpec}, Ref{Ptr{Cvoid}}), spec, h)
+    check(C_NULL, rc)
+    bp = BatchedProblem(h[], prob, B, keep)
+    finalizer(p -> ccall((:to_destroy, libb200), Cint, (Ptr{Cvoid},), p.h), bp)
+    return bp
+end
+
+# ---- the operator surface a solver calls (SURVEY.md 2.3) ------------------------------------------------------
+# host arrays are Array{Float64,3}: X (n, N, B), U (m, N-1, B) -- exactly the library's instance-major layout.
+TO.set_initial_state!(p::BatchedProblem, x0::Matrix{Float64}) =          # src/problem.jl:270
+    check(p.h, ccall((:to_set_initial_state, libb200), Cint, (Ptr{Cvoid}, Ptr{Float64}), p.h, x0))
+TO.initial_controls!(p::BatchedProblem, U::Array{Float64,3}) =           # src/problem.jl:261
+    check(p.h, ccall((:to_set_controls, libb200), Cint, (Ptr{Cvoid}, Ptr{Float64}), p.h, U))
+TO.initial_states!(p::BatchedProblem, X::Array{Float64,3}) =             # src/problem.jl:253
+    check(p.h, ccall((:to_set_states, libb200), Cint, (Ptr{Cvoid}, Ptr{Float64}), p.h, X))
+TO.rollout!(p::BatchedProblem) =                                         # src/problem.jl:330-340
+    check(p.h, ccall((:to_rollout, libb200), Cint, (Ptr{Cvoid},), p.h))
+function TO.cost(p::BatchedProblem)                                      # src/problem.jl:321
+    J = Vector{Float64}(undef, p.B)
+    check(p.h, ccall((:to_cost, libb200), Cint, (Ptr{Cvoid}, Ptr{Float64}), p.h, J)); J
+end
+function TO.states(p::BatchedProblem)                                    # src/problem.jl:175
+    n, m, N = RD.dims(p.prob, 1); X = Array{Float64,3}(undef, n, N, p.B)
+    check(p.h, ccall((:to_get_states, libb200), Cint, (Ptr{Cvoid}, Ptr{Float64}), p.h, X)); X
+end
+function TO.controls(p::BatchedProblem)                                  # src/problem.jl:168
+    n, m, N = RD.dims(p.prob, 1); U = Array{Float64,3}(undef, m, N - 1, p.B)
+    check(p.h, ccall((:to_get_controls, libb200), Cint, (Ptr{Cvoid}, Ptr{Float64}), p.h, U)); U
+end
+function TO.evaluate_constraints!(p::BatchedProblem, con_index::Integer, vals::Array{Float64,3})   # src/abstract_constraint.jl:200-225
+    check(p.h, ccall((:to_eval_constraints, libb200), Cint, (Ptr{Cvoid}, Int32, Ptr{Float64}), p.h, con_index - 1, vals)); vals
+end
+function TO.constraint_jacobians!(p::BatchedProblem, con_index::Integer, jac::Array{Float64,4})    # src/abstract_constraint.jl:236-248
+    check(p.h, ccall((:to_constraint_jacobians, libb200), Cint, (Ptr{Cvoid}, Int32, Ptr{Float64}), p.h, con_index - 1, jac)); jac
+end
+TO.set_goal_state!(p::BatchedProblem, xf::Vector{Float64}; objective=true, constraint=true) =      # src/problem.jl:294-310
+    check(p.h, ccall((:to_set_goal_state, libb200), Cint, (Ptr{Cvoid}, Ptr{Float64}, Cint, Cint), p.h, xf, objective, constraint))
+
+# ---- what Altro.jl's iLQR / AL loop does with the API above, fused on the device ------------------------------
+expand!(p::BatchedProblem) = check(p.h, ccall((:to_expand, libb200), Cint, (Ptr{Cvoid},), p.h))
+backwardpass!(p::BatchedProblem) = check(p.h, ccall((:to_backward, libb200), Cint, (Ptr{Cvoid}, Ptr{Int32}), p.h, C_NULL))
+forwardpass!(p::BatchedProblem) = check(p.h, ccall((:to_forward, libb200), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}), p.h, C_NULL, C_NULL))
+ilqr_step!(p::BatchedProblem, iters::Integer=1) = check(p.h, ccall((:to_ilqr_step, libb200), Cint, (Ptr{Cvoid}, Int32), p.h, iters))
+al_update!(p::BatchedProblem) = check(p.h, ccall((:to_al_update, libb200), Cint, (Ptr{Cvoid},), p.h))
+function max_violation(p::BatchedProblem)
+    v = Vector{Float64}(undef, p.B)
+    check(p.h, ccall((:to_max_violation, libb200), Cint, (Ptr{Cvoid}, Ptr{Float64}), p.h, v)); v
+end
+
+end # module

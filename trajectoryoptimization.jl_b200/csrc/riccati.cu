@@ -88,16 +88,18 @@ struct RiccatiSmem {
     static constexpr int LDT = MMA ? MMA_LD : even_up(NM + 1);    // T / Q: one extra column carries s / Qz
     static constexpr int SROWS = MMA ? 16 : NP;
     static constexpr int TROWS = MMA ? 16 : NP;
-    static constexpr int LDK = even_up(N_ + 1);     // K|d row stride
+    static constexpr int LDK = MMA ? MMA_LD : even_up(N_ + 1);    // K|d row stride
+    static constexpr int LDQS = even_up(M_ + 1);    // u / Qz strip of Q (MMA path): columns n..NM
     static constexpr int AB_BYTES = N_ * LDAB * 8;
     static constexpr int AB_STRIDE = (N_ * LDABS * 8 + 127) / 128 * 16;   // doubles, 128-byte aligned stages
-    static_assert(!MMA || (N_ <= 16 && NM + 1 <= MMA_LD && N_ >= 8), "MMA path: 8 <= n <= 16 and n+m+1 <= 20");
+    static_assert(!MMA || (N_ <= 16 && NM + 1 <= MMA_LD && N_ >= 8 && M_ <= 4), "MMA path: 8 <= n <= 16, m <= 4, n+m+1 <= 20");
     double ab[STAGES][AB_STRIDE];
     double S[SROWS * LDS_];
     double T[TROWS * LDT + 8];
-    double Q[even_up(NM) * LDT + 8];
-    double K[M_ * LDK];
-    double W[M_ * LDK];
+    double Q[MMA ? 2 : even_up(NM) * LDT + 8];   // full Q only on the DFMA path
+    double Qs[(NM + 1) * LDQS];
+    double K[4 * LDK + 8];
+    double W[4 * LDK + 8];
     double g[even_up(NM) + 2];   // lz (cost + AL gradient), padded
     double h[even_up(NM) + 2];   // diag(lzz)
     uint64_t bar[STAGES];
@@ -186,6 +188,7 @@ __global__ void __launch_bounds__(32, MINB) k_riccati(const DevProblem P, int* _
         }
     }
 
+    for (int e = lane; e < 4 * LDK + 8; e += 32) { sm.K[e] = 0.0; sm.W[e] = 0.0; }   // padding columns stay finite
     if (lane == 0) {
 #pragma unroll
         for (int s = 0; s < STAGES; s++) mbar_init(&sm.bar[s], 1);
@@ -308,6 +311,7 @@ __global__ void __launch_bounds__(32, MINB) k_riccati(const DevProblem P, int* _
                 for (int t = 0; t < MAXT; t++) lam_nxt[t] = 0.0;
                 if (k > 0 && lane < NM) { z_nxt = zbase[(size_t)(k - 1) * zstride]; if (FASTAL) load_lams(k - 1, lam_nxt); }
                 // ---- cost + AL expansion of knot k: lane i < NM handles z_i (diagonal terms) ------------
+                double g_reg = 0.0, h_reg = 0.0;
                 {
                     const DevCost& cost = P.costs[P.cost_index[k]];
                     double gi = 0.0, hi = 0.0;
@@ -349,7 +353,8 @@ __global__ void __launch_bounds__(32, MINB) k_riccati(const DevProblem P, int* _
                             }
                         }
                     }
-                    if (lane < even_up(NM) + 2) { sm.g[lane] = gi; sm.h[lane] = hi; }
+                    g_reg = gi; h_reg = hi;
+                    if constexpr (!MMA) { if (lane < even_up(NM) + 2) { sm.g[lane] = gi; sm.h[lane] = hi; } }
                 }
                 // ---- wait for [A B]_k in the ring ------------------------------------------------------
                 mbar_wait(&sm.bar[stage], (phase_bits >> stage) & 1u);
@@ -357,9 +362,17 @@ __global__ void __launch_bounds__(32, MINB) k_riccati(const DevProblem P, int* _
                 const double* sAB = sm.ab[stage];
 
                 if constexpr (MMA) {
+                    // Tensor-MMA knot (requires DiagonalCost + Goal/Bound: lzz is diagonal and lives in lane registers).
                     // lane's fragment coordinates: A(8x4): row fr, col fc ; B(4x8): row fc, col fr ; D(8x8): row fr, cols 2fc, 2fc+1
                     const int fr = lane >> 2, fc = lane & 3;
-                    // ---- T = S [A B | .]  : MT x NT tiles, KS k-steps of 4 + KR rank-1 updates ------------------
+                    constexpr int LDQS = SM::LDQS;
+                    // fragments of [A B]_k: B operand of T = S [A B], re-used as the A operand of Q = [A B]' T
+                    double bfr[KS][NT];
+#pragma unroll
+                    for (int kk = 0; kk < KS; kk++)
+#pragma unroll
+                        for (int t = 0; t < NT; t++) bfr[kk][t] = sAB[(4 * kk + fc) * LDABS + 8 * t + fr];
+                    // ---- T = S [A B | .] : S is kept as its upper 8x8 tiles, a lower tile is read as the transpose ----
                     {
                         double d[MT][NT][2];
 #pragma unroll
@@ -368,22 +381,22 @@ __global__ void __launch_bounds__(32, MINB) k_riccati(const DevProblem P, int* _
                             for (int ni = 0; ni < NT; ni++) { d[mi][ni][0] = 0.0; d[mi][ni][1] = 0.0; }
 #pragma unroll
                         for (int kk = 0; kk < KS; kk++) {
-                            double a[MT], bf[NT];
+                            double a[MT];
 #pragma unroll
-                            for (int mi = 0; mi < MT; mi++) a[mi] = sm.S[(8 * mi + fr) * LDS_ + 4 * kk + fc];
-#pragma unroll
-                            for (int ni = 0; ni < NT; ni++) bf[ni] = sAB[(4 * kk + fc) * LDABS + 8 * ni + fr];
+                            for (int mi = 0; mi < MT; mi++)
+                                a[mi] = (mi > (4 * kk) / 8) ? sm.S[(4 * kk + fc) * LDS_ + 8 * mi + fr] : sm.S[(8 * mi + fr) * LDS_ + 4 * kk + fc];
 #pragma unroll
                             for (int mi = 0; mi < MT; mi++)
 #pragma unroll
-                                for (int ni = 0; ni < NT; ni++) dmma(d[mi][ni][0], d[mi][ni][1], a[mi], bf[ni]);
+                                for (int ni = 0; ni < NT; ni++) dmma(d[mi][ni][0], d[mi][ni][1], a[mi], bfr[kk][ni]);
                         }
 #pragma unroll
                         for (int kr = 0; kr < KR; kr++) {
                             const int kx = 4 * KS + kr;
                             double a[MT]; double2 bb[NT];
 #pragma unroll
-                            for (int mi = 0; mi < MT; mi++) a[mi] = sm.S[(8 * mi + fr) * LDS_ + kx];
+                            for (int mi = 0; mi < MT; mi++)
+                                a[mi] = (mi > kx / 8) ? sm.S[kx * LDS_ + 8 * mi + fr] : sm.S[(8 * mi + fr) * LDS_ + kx];
 #pragma unroll
                             for (int ni = 0; ni < NT; ni++) bb[ni] = lds128(&sAB[kx * LDABS + 8 * ni + 2 * fc]);
 #pragma unroll
@@ -402,247 +415,348 @@ __global__ void __launch_bounds__(32, MINB) k_riccati(const DevProblem P, int* _
                         if (lane < n) sm.T[lane * LDT + NM] = s_reg;
                     }
                     __syncwarp();
-                    // ---- [Qzz | Qz] = [A B]' [T | s] + [lzz | lz] : upper tiles (mi <= ni) ---------------------------
+                    // ---- [Qzz | Qz] = [A B]' [T | s] : upper tiles (mi <= ni); tiles with mi,ni < MT become the S accumulators ----
+                    double q[NQT][2];
+#pragma unroll
+                    for (int t = 0; t < NQT; t++) { q[t][0] = 0.0; q[t][1] = 0.0; }
+#pragma unroll
+                    for (int kk = 0; kk < KS; kk++) {
+                        double bf[NT];
+#pragma unroll
+                        for (int ni = 0; ni < NT; ni++) bf[ni] = sm.T[(4 * kk + fc) * LDT + 8 * ni + fr];
+                        int t = 0;
+#pragma unroll
+                        for (int mi = 0; mi < MQ; mi++)
+#pragma unroll
+                            for (int ni = mi; ni < NT; ni++, t++) dmma(q[t][0], q[t][1], bfr[kk][mi], bf[ni]);
+                    }
+#pragma unroll
+                    for (int kr = 0; kr < KR; kr++) {
+                        const int kx = 4 * KS + kr;
+                        double a[MQ]; double2 bb[NT];
+#pragma unroll
+                        for (int mi = 0; mi < MQ; mi++) a[mi] = sAB[kx * LDABS + 8 * mi + fr];
+#pragma unroll
+                        for (int ni = 0; ni < NT; ni++) bb[ni] = lds128(&sm.T[kx * LDT + 8 * ni + 2 * fc]);
+                        int t = 0;
+#pragma unroll
+                        for (int mi = 0; mi < MQ; mi++)
+#pragma unroll
+                            for (int ni = mi; ni < NT; ni++, t++) { q[t][0] = fma(a[mi], bb[ni].x, q[t][0]); q[t][1] = fma(a[mi], bb[ni].y, q[t][1]); }
+                    }
+                    // ---- + [lzz | lz] (lane-resident, fetched by shuffle) ; the u / Qz strip (columns >= n) goes to shared memory ----
                     {
-                        double d[NQT][2];
+                        double hrow[MQ], grow[MQ];
 #pragma unroll
-                        for (int t = 0; t < NQT; t++) { d[t][0] = 0.0; d[t][1] = 0.0; }
-#pragma unroll
-                        for (int kk = 0; kk < KS; kk++) {
-                            double a[MQ], bf[NT];
-#pragma unroll
-                            for (int mi = 0; mi < MQ; mi++) a[mi] = sAB[(4 * kk + fc) * LDABS + 8 * mi + fr];
-#pragma unroll
-                            for (int ni = 0; ni < NT; ni++) bf[ni] = sm.T[(4 * kk + fc) * LDT + 8 * ni + fr];
-                            int t = 0;
-#pragma unroll
-                            for (int mi = 0; mi < MQ; mi++)
-#pragma unroll
-                                for (int ni = mi; ni < NT; ni++, t++) dmma(d[t][0], d[t][1], a[mi], bf[ni]);
-                        }
-#pragma unroll
-                        for (int kr = 0; kr < KR; kr++) {
-                            const int kx = 4 * KS + kr;
-                            double a[MQ]; double2 bb[NT];
-#pragma unroll
-                            for (int mi = 0; mi < MQ; mi++) a[mi] = sAB[kx * LDABS + 8 * mi + fr];
-#pragma unroll
-                            for (int ni = 0; ni < NT; ni++) bb[ni] = lds128(&sm.T[kx * LDT + 8 * ni + 2 * fc]);
-                            int t = 0;
-#pragma unroll
-                            for (int mi = 0; mi < MQ; mi++)
-#pragma unroll
-                                for (int ni = mi; ni < NT; ni++, t++) { d[t][0] = fma(a[mi], bb[ni].x, d[t][0]); d[t][1] = fma(a[mi], bb[ni].y, d[t][1]); }
-                        }
+                        for (int mi = 0; mi < MQ; mi++) { hrow[mi] = __shfl_sync(0xffffffffu, h_reg, (8 * mi + fr) & 31); grow[mi] = __shfl_sync(0xffffffffu, g_reg, (8 * mi + fr) & 31); }
                         int t = 0;
 #pragma unroll
                         for (int mi = 0; mi < MQ; mi++)
 #pragma unroll
                             for (int ni = mi; ni < NT; ni++, t++) {
                                 const int row = 8 * mi + fr, col = 8 * ni + 2 * fc;
-                                if (row < NM && col <= NM) {
-                                    double v0 = d[t][0], v1 = d[t][1];
-                                    if (row == col) v0 += sm.h[row];
-                                    if (row == col + 1) v1 += sm.h[row];
-                                    if (col == NM) v0 += sm.g[row];
-                                    if (col + 1 == NM) v1 += sm.g[row];
-                                    sts128(&sm.Q[row * LDT + col], v0, v1);
+                                if (row == col) q[t][0] += hrow[mi];
+                                if (row == col + 1) q[t][1] += hrow[mi];
+                                if (col == NM) q[t][0] += grow[mi];
+                                if (col + 1 == NM) q[t][1] += grow[mi];
+                                if (row < NM) {
+                                    if (col >= n && col <= NM) sm.Qs[row * LDQS + col - n] = q[t][0];
+                                    if (col + 1 >= n && col + 1 <= NM) sm.Qs[row * LDQS + col + 1 - n] = q[t][1];
                                 }
                             }
                     }
                     __syncwarp();
+                    if (k - STAGES >= 0) issue_ab(stage, k - STAGES);     // T and the ring slot have been consumed
+                    stage = (stage + 1 == STAGES) ? 0 : stage + 1;
+                    // ---- gains: LDL' of Quu + rho I, one lane per column of [Qux | Qu]; lanes 0..15 only (half the wavefronts) ----
+                    double kc[M_], wc[M_];
+#pragma unroll
+                    for (int a = 0; a < m; a++) { kc[a] = 0.0; wc[a] = 0.0; }
+                    bool okl = true;
+                    if (lane < 16) {
+                        double Quu[M_ * (M_ + 1) / 2], Lf[M_ * (M_ + 1) / 2], dj[M_];
+#pragma unroll
+                        for (int a = 0; a < m; a++)
+#pragma unroll
+                            for (int c = 0; c <= a; c++) Quu[a * (a + 1) / 2 + c] = sm.Qs[(n + c) * LDQS + a];
+#pragma unroll
+                        for (int j = 0; j < m; j++) {
+                            double t = Quu[j * (j + 1) / 2 + j] + rho;
+#pragma unroll
+                            for (int r = 0; r < j; r++) t = fma(-Lf[j * (j + 1) / 2 + r] * Lf[j * (j + 1) / 2 + r], dj[r], t);
+                            if (!(t > 0.0) || !isfinite(t)) okl = false;
+                            dj[j] = t;
+                            const double inv = __drcp_rn(t);
+                            Lf[j * (j + 1) / 2 + j] = inv;
+#pragma unroll
+                            for (int i = j + 1; i < m; i++) {
+                                double v = Quu[i * (i + 1) / 2 + j];
+#pragma unroll
+                                for (int r = 0; r < j; r++) v = fma(-Lf[i * (i + 1) / 2 + r] * Lf[j * (j + 1) / 2 + r], dj[r], v);
+                                Lf[i * (i + 1) / 2 + j] = v * inv;
+                            }
+                        }
+                        const int c = (lane <= n) ? lane : n;
+                        double rhs[M_];
+#pragma unroll
+                        for (int a = 0; a < m; a++) rhs[a] = (c < n) ? sm.Qs[c * LDQS + a] : sm.Qs[(n + a) * LDQS + m];   // Qux[a][c] | Qu[a]
+#pragma unroll
+                        for (int a = 0; a < m; a++) {
+                            double t = -rhs[a];
+#pragma unroll
+                            for (int r = 0; r < a; r++) t = fma(-Lf[a * (a + 1) / 2 + r], kc[r], t);
+                            kc[a] = t;
+                        }
+#pragma unroll
+                        for (int a = 0; a < m; a++) kc[a] *= Lf[a * (a + 1) / 2 + a];
+#pragma unroll
+                        for (int a = m - 1; a >= 0; a--) {
+                            double t = kc[a];
+#pragma unroll
+                            for (int r = a + 1; r < m; r++) t = fma(-Lf[r * (r + 1) / 2 + a], kc[r], t);
+                            kc[a] = t;
+                        }
+#pragma unroll
+                        for (int a = 0; a < m; a++) wc[a] = fma(-rho, kc[a], rhs[a]);   // W = Qux - rho K
+                        if (okl) {
+                            if (lane <= n) {
+#pragma unroll
+                                for (int a = 0; a < m; a++) { sm.K[a * LDK + c] = kc[a]; sm.W[a * LDK + c] = wc[a]; }
+                            }
+                            if (lane < n) {
+#pragma unroll
+                                for (int a = 0; a < m; a++) Kg[(size_t)k * n * m + lane * m + a] = kc[a];
+                            } else if (lane == n) {
+                                double t1 = 0.0, t2 = 0.0;
+#pragma unroll
+                                for (int a = 0; a < m; a++) {
+                                    dg[(size_t)k * m + a] = kc[a];
+                                    t1 = fma(kc[a], rhs[a], t1);
+                                    double qd = 0.0;
+#pragma unroll
+                                    for (int r = 0; r < m; r++) qd = fma((r <= a) ? Quu[a * (a + 1) / 2 + r] : Quu[r * (r + 1) / 2 + a], kc[r], qd);
+                                    t2 = fma(0.5 * kc[a], qd, t2);
+                                }
+                                dV1 += t1; dV2 += t2;
+                            }
+                        }
+                    }
+                    ok = __shfl_sync(0xffffffffu, okl ? 1 : 0, 0) != 0;
+                    if (!ok) break;
+                    __syncwarp();
+                    // ---- S <- Qxx + W'K on the tensor cores (one k-step, K = m <= 4), accumulators = the Qxx tiles ----
+                    {
+                        double af[MT], bk[MT];
+#pragma unroll
+                        for (int mi = 0; mi < MT; mi++) { af[mi] = (fc < m) ? sm.W[fc * LDK + 8 * mi + fr] : 0.0; bk[mi] = (fc < m) ? sm.K[fc * LDK + 8 * mi + fr] : 0.0; }
+                        int t = 0;
+#pragma unroll
+                        for (int mi = 0; mi < MQ; mi++)
+#pragma unroll
+                            for (int ni = mi; ni < NT; ni++, t++) {
+                                if (mi < MT && ni < MT) {
+                                    dmma(q[t][0], q[t][1], af[mi], bk[ni]);
+                                    sts128(&sm.S[(8 * mi + fr) * LDS_ + 8 * ni + 2 * fc], q[t][0], q[t][1]);
+                                }
+                            }
+                        // s <- Qx + W'd : W column of lane c is in its registers, d comes from lane n
+                        double snew = (lane < n) ? sm.Qs[lane * LDQS + m] : 0.0;
+#pragma unroll
+                        for (int a = 0; a < m; a++) snew = fma(wc[a], __shfl_sync(0xffffffffu, kc[a], n), snew);
+                        s_reg = snew;
+                    }
                 } else {
-                    // ---- T = S [A B]  (2x2 blocks), extra column NM <- s ---------------------------------------
-                    {
-                        double acc[RT][4];
-    #pragma unroll
-                        for (int r = 0; r < RT; r++) { acc[r][0] = acc[r][1] = acc[r][2] = acc[r][3] = 0.0; }
-    #pragma unroll
-                        for (int j = 0; j < n; j++) {
-    #pragma unroll
+                        // ---- T = S [A B]  (2x2 blocks), extra column NM <- s ---------------------------------------
+                        {
+                            double acc[RT][4];
+        #pragma unroll
+                            for (int r = 0; r < RT; r++) { acc[r][0] = acc[r][1] = acc[r][2] = acc[r][3] = 0.0; }
+        #pragma unroll
+                            for (int j = 0; j < n; j++) {
+        #pragma unroll
+                                for (int r = 0; r < RT; r++) {
+                                    const double2 a = lds128(&sm.S[j * LDS_ + t_a[r]]);
+                                    const double2 bb = lds128(&sAB[j * LDABS + t_b[r]]);
+                                    fma2x2(acc[r], a, bb);
+                                }
+                            }
+        #pragma unroll
                             for (int r = 0; r < RT; r++) {
-                                const double2 a = lds128(&sm.S[j * LDS_ + t_a[r]]);
-                                const double2 bb = lds128(&sAB[j * LDABS + t_b[r]]);
-                                fma2x2(acc[r], a, bb);
+                                if (t_on[r]) {
+                                    if (t_lastcol[r]) { sm.T[t_o[r]] = acc[r][0]; sm.T[t_o[r] + LDT] = acc[r][2]; }   // leave column NM to s
+                                    else { sts128(&sm.T[t_o[r]], acc[r][0], acc[r][1]); sts128(&sm.T[t_o[r] + LDT], acc[r][2], acc[r][3]); }
+                                }
                             }
+                            if (lane < n) sm.T[lane * LDT + NM] = s_reg;
                         }
-    #pragma unroll
-                        for (int r = 0; r < RT; r++) {
-                            if (t_on[r]) {
-                                if (t_lastcol[r]) { sm.T[t_o[r]] = acc[r][0]; sm.T[t_o[r] + LDT] = acc[r][2]; }   // leave column NM to s
-                                else { sts128(&sm.T[t_o[r]], acc[r][0], acc[r][1]); sts128(&sm.T[t_o[r] + LDT], acc[r][2], acc[r][3]); }
-                            }
-                        }
-                        if (lane < n) sm.T[lane * LDT + NM] = s_reg;
-                    }
-                    __syncwarp();
-
-                    // ---- [Qzz | Qz] = [A B]' [T | s] + [lzz | lz]  (upper 2x2 blocks) -----------------------
-                    {
-                        double acc[RQ][4];
-    #pragma unroll
-                        for (int r = 0; r < RQ; r++) { acc[r][0] = acc[r][1] = acc[r][2] = acc[r][3] = 0.0; }
-    #pragma unroll
-                        for (int j = 0; j < n; j++) {
-    #pragma unroll
-                            for (int r = 0; r < RQ; r++) {
-                                const double2 a = lds128(&sAB[j * LDABS + q_a[r]]);
-                                const double2 bb = lds128(&sm.T[j * LDT + q_b[r]]);
-                                fma2x2(acc[r], a, bb);
-                            }
-                        }
-    #pragma unroll
-                        for (int r = 0; r < RQ; r++) {
-                            const int i0 = q_i0[r], j0 = q_j0[r];
-                            const double2 gg = lds128(&sm.g[i0]);
-                            if (q_diag[r]) { const double2 hh = lds128(&sm.h[i0]); acc[r][0] += hh.x; acc[r][3] += hh.y; }
-                            if (j0 == NM) { acc[r][0] += gg.x; acc[r][2] += gg.y; }
-                            if (j0 + 1 == NM) { acc[r][1] += gg.x; acc[r][3] += gg.y; }
-                            if (q_on[r]) {
-                                sts128(&sm.Q[q_o[r]], acc[r][0], acc[r][1]);
-                                sts128(&sm.Q[q_o[r] + LDT], acc[r][2], acc[r][3]);
-                            }
-                        }
-                    }
-                    __syncwarp();
-                }
-                // the stage buffer is free: refill it with the knot STAGES steps ahead
-                if (k - STAGES >= 0) issue_ab(stage, k - STAGES);
-                stage = (stage + 1 == STAGES) ? 0 : stage + 1;
-
-                // dense cost Hessian (QuadraticCost): add the off-diagonal entries of lzz to the upper part of Q
-                if (!P.all_diag_cost) {
-                    const DevCost& cost = P.costs[P.cost_index[k]];
-                    if (!cost.diag) {
-                        for (int e = lane; e < NM * NM; e += 32) {
-                            const int i = e / NM, j = e % NM;     // need (i,j) with block(i) <= block(j)
-                            if (i == j || (i >> 1) > (j >> 1)) continue;
-                            double v;
-                            if (i < n && j < n) v = cost.Q[j * n + i];
-                            else if (i >= n && j >= n) v = cost.R[(j - n) * m + (i - n)];
-                            else if (i < n) v = cost.zeroH ? 0.0 : cost.H[i * m + (j - n)];   // (x_i, u_a): H[a][i]
-                            else v = cost.zeroH ? 0.0 : cost.H[j * m + (i - n)];
-                            sm.Q[i * LDT + j] += v;
-                        }
-                        // diagonal: sm.h carried only the AL part for dense costs -> add Q_ii / R_aa
-                        if (lane < NM) sm.Q[lane * LDT + lane] += (lane < n) ? cost.Q[lane * n + lane] : cost.R[(lane - n) * m + (lane - n)];
                         __syncwarp();
-                    }
-                }
 
-                // ---- gains: LDL' of Quu + rho I, one lane per column of [Qux | Qu] -------------------------
-                double Quu[M_ * (M_ + 1) / 2];           // packed lower by rows
-                double Lf[M_ * (M_ + 1) / 2];            // unit-lower L (off-diagonal), diagonal slots hold 1/d_j
-                {
-#pragma unroll
-                    for (int a = 0; a < m; a++)
-#pragma unroll
-                        for (int c = 0; c <= a; c++) Quu[a * (a + 1) / 2 + c] = sm.Q[(n + c) * LDT + (n + a)];   // upper entry (c <= a)
-                    double dj[M_];
-#pragma unroll
-                    for (int j = 0; j < m; j++) {
-                        double t = Quu[j * (j + 1) / 2 + j] + rho;
-#pragma unroll
-                        for (int r = 0; r < j; r++) t = fma(-Lf[j * (j + 1) / 2 + r] * Lf[j * (j + 1) / 2 + r], dj[r], t);
-                        if (!(t > 0.0) || !isfinite(t)) ok = false;
-                        dj[j] = t;
-                        const double inv = __drcp_rn(t);
-                        Lf[j * (j + 1) / 2 + j] = inv;
-#pragma unroll
-                        for (int i = j + 1; i < m; i++) {
-                            double v = Quu[i * (i + 1) / 2 + j];
-#pragma unroll
-                            for (int r = 0; r < j; r++) v = fma(-Lf[i * (i + 1) / 2 + r] * Lf[j * (j + 1) / 2 + r], dj[r], v);
-                            Lf[i * (i + 1) / 2 + j] = v * inv;
+                        // ---- [Qzz | Qz] = [A B]' [T | s] + [lzz | lz]  (upper 2x2 blocks) -----------------------
+                        {
+                            double acc[RQ][4];
+        #pragma unroll
+                            for (int r = 0; r < RQ; r++) { acc[r][0] = acc[r][1] = acc[r][2] = acc[r][3] = 0.0; }
+        #pragma unroll
+                            for (int j = 0; j < n; j++) {
+        #pragma unroll
+                                for (int r = 0; r < RQ; r++) {
+                                    const double2 a = lds128(&sAB[j * LDABS + q_a[r]]);
+                                    const double2 bb = lds128(&sm.T[j * LDT + q_b[r]]);
+                                    fma2x2(acc[r], a, bb);
+                                }
+                            }
+        #pragma unroll
+                            for (int r = 0; r < RQ; r++) {
+                                const int i0 = q_i0[r], j0 = q_j0[r];
+                                const double2 gg = lds128(&sm.g[i0]);
+                                if (q_diag[r]) { const double2 hh = lds128(&sm.h[i0]); acc[r][0] += hh.x; acc[r][3] += hh.y; }
+                                if (j0 == NM) { acc[r][0] += gg.x; acc[r][2] += gg.y; }
+                                if (j0 + 1 == NM) { acc[r][1] += gg.x; acc[r][3] += gg.y; }
+                                if (q_on[r]) {
+                                    sts128(&sm.Q[q_o[r]], acc[r][0], acc[r][1]);
+                                    sts128(&sm.Q[q_o[r] + LDT], acc[r][2], acc[r][3]);
+                                }
+                            }
                         }
-                    }
-                }
-                if (!ok) break;   // uniform across the warp (every lane factors the same matrix)
-                {
-                    const int c = (lane <= n) ? lane : n;
-                    double rhs[M_], kc[M_];
-#pragma unroll
-                    for (int a = 0; a < m; a++) rhs[a] = (c < n) ? sm.Q[c * LDT + (n + a)] : sm.Q[(n + a) * LDT + NM];   // Qux[a][c] | Qu[a]
-#pragma unroll
-                    for (int a = 0; a < m; a++) {      // forward: L y = -rhs
-                        double t = -rhs[a];
-#pragma unroll
-                        for (int r = 0; r < a; r++) t = fma(-Lf[a * (a + 1) / 2 + r], kc[r], t);
-                        kc[a] = t;
-                    }
-#pragma unroll
-                    for (int a = 0; a < m; a++) kc[a] *= Lf[a * (a + 1) / 2 + a];   // D^-1
-#pragma unroll
-                    for (int a = m - 1; a >= 0; a--) {  // backward: L' x = y
-                        double t = kc[a];
-#pragma unroll
-                        for (int r = a + 1; r < m; r++) t = fma(-Lf[r * (r + 1) / 2 + a], kc[r], t);
-                        kc[a] = t;
-                    }
-                    if (lane <= n) {
-#pragma unroll
-                        for (int a = 0; a < m; a++) {
-                            sm.K[a * LDK + c] = kc[a];
-                            sm.W[a * LDK + c] = fma(-rho, kc[a], rhs[a]);   // W = Qux - rho K
-                        }
-                    }
-                    if (lane < n) {
-#pragma unroll
-                        for (int a = 0; a < m; a++) Kg[(size_t)k * n * m + lane * m + a] = kc[a];
-                    } else if (lane == n) {
-                        double t1 = 0.0, t2 = 0.0;
-#pragma unroll
-                        for (int a = 0; a < m; a++) {
-                            dg[(size_t)k * m + a] = kc[a];
-                            t1 = fma(kc[a], rhs[a], t1);
-                            double qd = 0.0;   // (Quu d)_a
-#pragma unroll
-                            for (int r = 0; r < m; r++) qd = fma((r <= a) ? Quu[a * (a + 1) / 2 + r] : Quu[r * (r + 1) / 2 + a], kc[r], qd);
-                            t2 = fma(0.5 * kc[a], qd, t2);
-                        }
-                        dV1 += t1; dV2 += t2;
-                    }
-                }
-                __syncwarp();
+                        __syncwarp();
+                    // the stage buffer is free: refill it with the knot STAGES steps ahead
+                    if (k - STAGES >= 0) issue_ab(stage, k - STAGES);
+                    stage = (stage + 1 == STAGES) ? 0 : stage + 1;
 
-                // ---- S <- Qxx + W'K (upper blocks, mirrored) ; s <- Qx + W'd ------------------------------
-                {
-                    double acc[RS][4];
-#pragma unroll
-                    for (int r = 0; r < RS; r++) {
-                        const double2 q0 = lds128(&sm.Q[s_a[r] * LDT + s_b[r]]);
-                        const double2 q1 = lds128(&sm.Q[(s_a[r] + 1) * LDT + s_b[r]]);
-                        acc[r][0] = q0.x; acc[r][1] = q0.y; acc[r][2] = q1.x; acc[r][3] = q1.y;
+                    // dense cost Hessian (QuadraticCost): add the off-diagonal entries of lzz to the upper part of Q
+                    if (!P.all_diag_cost) {
+                        const DevCost& cost = P.costs[P.cost_index[k]];
+                        if (!cost.diag) {
+                            for (int e = lane; e < NM * NM; e += 32) {
+                                const int i = e / NM, j = e % NM;     // need (i,j) with block(i) <= block(j)
+                                if (i == j || (i >> 1) > (j >> 1)) continue;
+                                double v;
+                                if (i < n && j < n) v = cost.Q[j * n + i];
+                                else if (i >= n && j >= n) v = cost.R[(j - n) * m + (i - n)];
+                                else if (i < n) v = cost.zeroH ? 0.0 : cost.H[i * m + (j - n)];   // (x_i, u_a): H[a][i]
+                                else v = cost.zeroH ? 0.0 : cost.H[j * m + (i - n)];
+                                sm.Q[i * LDT + j] += v;
+                            }
+                            // diagonal: sm.h carried only the AL part for dense costs -> add Q_ii / R_aa
+                            if (lane < NM) sm.Q[lane * LDT + lane] += (lane < n) ? cost.Q[lane * n + lane] : cost.R[(lane - n) * m + (lane - n)];
+                            __syncwarp();
+                        }
                     }
-#pragma unroll
-                    for (int a = 0; a < m; a++) {
-#pragma unroll
+
+                    // ---- gains: LDL' of Quu + rho I, one lane per column of [Qux | Qu] -------------------------
+                    double Quu[M_ * (M_ + 1) / 2];           // packed lower by rows
+                    double Lf[M_ * (M_ + 1) / 2];            // unit-lower L (off-diagonal), diagonal slots hold 1/d_j
+                    {
+    #pragma unroll
+                        for (int a = 0; a < m; a++)
+    #pragma unroll
+                            for (int c = 0; c <= a; c++) Quu[a * (a + 1) / 2 + c] = sm.Q[(n + c) * LDT + (n + a)];   // upper entry (c <= a)
+                        double dj[M_];
+    #pragma unroll
+                        for (int j = 0; j < m; j++) {
+                            double t = Quu[j * (j + 1) / 2 + j] + rho;
+    #pragma unroll
+                            for (int r = 0; r < j; r++) t = fma(-Lf[j * (j + 1) / 2 + r] * Lf[j * (j + 1) / 2 + r], dj[r], t);
+                            if (!(t > 0.0) || !isfinite(t)) ok = false;
+                            dj[j] = t;
+                            const double inv = __drcp_rn(t);
+                            Lf[j * (j + 1) / 2 + j] = inv;
+    #pragma unroll
+                            for (int i = j + 1; i < m; i++) {
+                                double v = Quu[i * (i + 1) / 2 + j];
+    #pragma unroll
+                                for (int r = 0; r < j; r++) v = fma(-Lf[i * (i + 1) / 2 + r] * Lf[j * (j + 1) / 2 + r], dj[r], v);
+                                Lf[i * (i + 1) / 2 + j] = v * inv;
+                            }
+                        }
+                    }
+                    if (!ok) break;   // uniform across the warp (every lane factors the same matrix)
+                    {
+                        const int c = (lane <= n) ? lane : n;
+                        double rhs[M_], kc[M_];
+    #pragma unroll
+                        for (int a = 0; a < m; a++) rhs[a] = (c < n) ? sm.Q[c * LDT + (n + a)] : sm.Q[(n + a) * LDT + NM];   // Qux[a][c] | Qu[a]
+    #pragma unroll
+                        for (int a = 0; a < m; a++) {      // forward: L y = -rhs
+                            double t = -rhs[a];
+    #pragma unroll
+                            for (int r = 0; r < a; r++) t = fma(-Lf[a * (a + 1) / 2 + r], kc[r], t);
+                            kc[a] = t;
+                        }
+    #pragma unroll
+                        for (int a = 0; a < m; a++) kc[a] *= Lf[a * (a + 1) / 2 + a];   // D^-1
+    #pragma unroll
+                        for (int a = m - 1; a >= 0; a--) {  // backward: L' x = y
+                            double t = kc[a];
+    #pragma unroll
+                            for (int r = a + 1; r < m; r++) t = fma(-Lf[r * (r + 1) / 2 + a], kc[r], t);
+                            kc[a] = t;
+                        }
+                        if (lane <= n) {
+    #pragma unroll
+                            for (int a = 0; a < m; a++) {
+                                sm.K[a * LDK + c] = kc[a];
+                                sm.W[a * LDK + c] = fma(-rho, kc[a], rhs[a]);   // W = Qux - rho K
+                            }
+                        }
+                        if (lane < n) {
+    #pragma unroll
+                            for (int a = 0; a < m; a++) Kg[(size_t)k * n * m + lane * m + a] = kc[a];
+                        } else if (lane == n) {
+                            double t1 = 0.0, t2 = 0.0;
+    #pragma unroll
+                            for (int a = 0; a < m; a++) {
+                                dg[(size_t)k * m + a] = kc[a];
+                                t1 = fma(kc[a], rhs[a], t1);
+                                double qd = 0.0;   // (Quu d)_a
+    #pragma unroll
+                                for (int r = 0; r < m; r++) qd = fma((r <= a) ? Quu[a * (a + 1) / 2 + r] : Quu[r * (r + 1) / 2 + a], kc[r], qd);
+                                t2 = fma(0.5 * kc[a], qd, t2);
+                            }
+                            dV1 += t1; dV2 += t2;
+                        }
+                    }
+                    __syncwarp();
+
+                    // ---- S <- Qxx + W'K (upper blocks, mirrored) ; s <- Qx + W'd ------------------------------
+                    {
+                        double acc[RS][4];
+    #pragma unroll
                         for (int r = 0; r < RS; r++) {
-                            const double2 w = lds128(&sm.W[a * LDK + s_a[r]]);
-                            const double2 kk = lds128(&sm.K[a * LDK + s_b[r]]);
-                            fma2x2(acc[r], w, kk);
+                            const double2 q0 = lds128(&sm.Q[s_a[r] * LDT + s_b[r]]);
+                            const double2 q1 = lds128(&sm.Q[(s_a[r] + 1) * LDT + s_b[r]]);
+                            acc[r][0] = q0.x; acc[r][1] = q0.y; acc[r][2] = q1.x; acc[r][3] = q1.y;
                         }
-                    }
-                    double snew = 0.0;
-                    if (lane < n) {
-                        snew = sm.Q[lane * LDT + NM];
-#pragma unroll
-                        for (int a = 0; a < m; a++) snew = fma(sm.W[a * LDK + lane], sm.K[a * LDK + n], snew);
-                    }
-                    s_reg = snew;
-#pragma unroll
-                    for (int r = 0; r < RS; r++) {
-                        if (!s_on[r]) continue;
-                        const int i0 = s_a[r], j0 = s_b[r];
-                        if (s_diag[r]) {
-                            const double off = 0.5 * (acc[r][1] + acc[r][2]);
-                            sts128(&sm.S[i0 * LDS_ + j0], acc[r][0], off);
-                            sts128(&sm.S[(i0 + 1) * LDS_ + j0], off, acc[r][3]);
-                        } else {
-                            sts128(&sm.S[i0 * LDS_ + j0], acc[r][0], acc[r][1]);
-                            sts128(&sm.S[(i0 + 1) * LDS_ + j0], acc[r][2], acc[r][3]);
-                            sts128(&sm.S[j0 * LDS_ + i0], acc[r][0], acc[r][2]);
-                            sts128(&sm.S[(j0 + 1) * LDS_ + i0], acc[r][1], acc[r][3]);
+    #pragma unroll
+                        for (int a = 0; a < m; a++) {
+    #pragma unroll
+                            for (int r = 0; r < RS; r++) {
+                                const double2 w = lds128(&sm.W[a * LDK + s_a[r]]);
+                                const double2 kk = lds128(&sm.K[a * LDK + s_b[r]]);
+                                fma2x2(acc[r], w, kk);
+                            }
+                        }
+                        double snew = 0.0;
+                        if (lane < n) {
+                            snew = sm.Q[lane * LDT + NM];
+    #pragma unroll
+                            for (int a = 0; a < m; a++) snew = fma(sm.W[a * LDK + lane], sm.K[a * LDK + n], snew);
+                        }
+                        s_reg = snew;
+    #pragma unroll
+                        for (int r = 0; r < RS; r++) {
+                            if (!s_on[r]) continue;
+                            const int i0 = s_a[r], j0 = s_b[r];
+                            if (s_diag[r]) {
+                                const double off = 0.5 * (acc[r][1] + acc[r][2]);
+                                sts128(&sm.S[i0 * LDS_ + j0], acc[r][0], off);
+                                sts128(&sm.S[(i0 + 1) * LDS_ + j0], off, acc[r][3]);
+                            } else {
+                                sts128(&sm.S[i0 * LDS_ + j0], acc[r][0], acc[r][1]);
+                                sts128(&sm.S[(i0 + 1) * LDS_ + j0], acc[r][2], acc[r][3]);
+                                sts128(&sm.S[j0 * LDS_ + i0], acc[r][0], acc[r][2]);
+                                sts128(&sm.S[(j0 + 1) * LDS_ + i0], acc[r][1], acc[r][3]);
+                            }
                         }
                     }
                 }
@@ -680,9 +794,8 @@ __global__ void __launch_bounds__(32, MINB) k_riccati(const DevProblem P, int* _
     }
 }
 
-template <int N_, int M_, bool FASTAL, int STAGES, int MINB>
+template <int N_, int M_, bool FASTAL, int STAGES, int MINB, bool MMA>
 cudaError_t launch_riccati_v(const DevProblem& P, int* work_counter, cudaStream_t s) {
-    constexpr bool MMA = (N_ >= 8);
     using SM = RiccatiSmem<N_, M_, STAGES, MMA>;
     auto kern = k_riccati<N_, M_, STAGES, FASTAL, MMA, MINB>;
     static bool configured = false;
@@ -708,19 +821,24 @@ cudaError_t launch_riccati_v(const DevProblem& P, int* work_counter, cudaStream_
 
 template <int N_, int M_, bool FASTAL>
 cudaError_t launch_riccati_t(const DevProblem& P, int* work_counter, cudaStream_t s) {
-    if constexpr (N_ >= 8) {
-        // tuning knob (occupancy vs registers / ring depth); default chosen from the sweep in profiles/r01_notes.md
-        static int variant = -1;
-        if (variant < 0) { const char* v = getenv("TO_RICCATI_VARIANT"); variant = v ? atoi(v) : 1; }
-        switch (variant) {
-            case 1: return launch_riccati_v<N_, M_, FASTAL, 2, 16>(P, work_counter, s);
-            case 2: return launch_riccati_v<N_, M_, FASTAL, 2, 20>(P, work_counter, s);
-            case 3: return launch_riccati_v<N_, M_, FASTAL, 3, 16>(P, work_counter, s);
-            case 4: return launch_riccati_v<N_, M_, FASTAL, 2, 12>(P, work_counter, s);
-            default: return launch_riccati_v<N_, M_, FASTAL, 3, 12>(P, work_counter, s);
+    if constexpr (N_ >= 8 && M_ <= 4) {
+        if (P.all_diag_cost && P.all_diag_con) {   // tensor-MMA kernel: diagonal lzz (DiagonalCost + Goal/Bound)
+            // tuning knob (occupancy vs registers / ring depth); default from the sweep in profiles/r01_notes.md
+            static int variant = -1;
+            if (variant < 0) { const char* v = getenv("TO_RICCATI_VARIANT"); variant = v ? atoi(v) : 1; }
+            switch (variant) {
+                case 0: return launch_riccati_v<N_, M_, FASTAL, 3, 12, true>(P, work_counter, s);
+                case 2: return launch_riccati_v<N_, M_, FASTAL, 2, 20, true>(P, work_counter, s);
+                case 3: return launch_riccati_v<N_, M_, FASTAL, 3, 16, true>(P, work_counter, s);
+                case 4: return launch_riccati_v<N_, M_, FASTAL, 2, 12, true>(P, work_counter, s);
+                case 5: return launch_riccati_v<N_, M_, FASTAL, 2, 14, true>(P, work_counter, s);
+                case 6: return launch_riccati_v<N_, M_, FASTAL, 3, 14, true>(P, work_counter, s);
+                default: return launch_riccati_v<N_, M_, FASTAL, 2, 16, true>(P, work_counter, s);
+            }
         }
+        return launch_riccati_v<N_, M_, FASTAL, 2, 12, false>(P, work_counter, s);   // dense costs: DFMA micro-block kernel
     } else {
-        return launch_riccati_v<N_, M_, FASTAL, 3, 16>(P, work_counter, s);
+        return launch_riccati_v<N_, M_, FASTAL, 3, 16, false>(P, work_counter, s);
     }
 }
 

@@ -7,8 +7,10 @@
 //               reference; shape [A B] = n x (n+m) pinned by test/dynamics_constraints.jl:35,57-62).
 //               One thread per (instance, knot, seed direction j): the RK4 step is pushed through a
 //               Dual<1> whose tangent is the one-hot e_j, i.e. the thread computes column j of [A B] with the
-//               partial carried in registers.  Threads of one knot are adjacent, so row i of AB (LDAB
-//               contiguous doubles incl. the zero pad column) is written by LDAB adjacent lanes.
+//               partial carried in registers.  Threads of one knot are adjacent, so row i of AB is written by
+//               adjacent lanes; the pad columns of a row (LDAB > n+m) are never touched and stay zero.
+#include <cstdlib>
+
 #include "kernels.h"
 #include "models.cuh"
 
@@ -31,34 +33,44 @@ __global__ void __launch_bounds__(64) k_rollout(const DevProblem P) {
     }
 }
 
-template <int MODEL>
+template <int MODEL, int NP>
 __global__ void __launch_bounds__(128) k_expand(const DevProblem P) {
-    constexpr int n = ModelDims<MODEL>::n, m = ModelDims<MODEL>::m;
-    using D = Dual<1>;
+    constexpr int n = ModelDims<MODEL>::n, m = ModelDims<MODEL>::m, nm = n + m;
+    constexpr int TPK = (nm + NP - 1) / NP;        // threads per knot: each carries NP seed directions
+    using D = Dual<NP>;
     const int ld = P.ldab;
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long total = (long long)P.B * (P.N - 1) * ld;
+    const long long total = (long long)P.B * (P.N - 1) * TPK;
     if (t >= total) return;
-    const int j = (int)(t % ld);
-    const long long bk = t / ld;
+    const int j0 = (int)(t % TPK) * NP;            // first seed of this thread
+    const long long bk = t / TPK;
     const int k = (int)(bk % (P.N - 1));
     const int b = (int)(bk / (P.N - 1));
-    double* AB = P.AB + ((size_t)b * (P.N - 1) + k) * n * ld;
-    if (j >= n + m) {   // pad column
-#pragma unroll
-        for (int i = 0; i < n; i++) AB[i * ld + j] = 0.0;
-        return;
-    }
+    double* AB = P.AB + ((size_t)b * (P.N - 1) + k) * n * ld;     // pad columns nm..ld-1 stay zero from to_create
     const double* X = traj_X(P, P.cur[b], b) + (size_t)k * n;
     const double* U = traj_U(P, P.cur[b], b) + (size_t)k * m;
     D x[n], u[m], xn[n];
 #pragma unroll
-    for (int i = 0; i < n; i++) { x[i].v = X[i]; x[i].d[0] = (i == j) ? 1.0 : 0.0; }
+    for (int i = 0; i < n; i++) {
+        x[i].v = X[i];
 #pragma unroll
-    for (int i = 0; i < m; i++) { u[i].v = U[i]; u[i].d[0] = (n + i == j) ? 1.0 : 0.0; }
+        for (int s = 0; s < NP; s++) x[i].d[s] = (i == j0 + s) ? 1.0 : 0.0;
+    }
+#pragma unroll
+    for (int i = 0; i < m; i++) {
+        u[i].v = U[i];
+#pragma unroll
+        for (int s = 0; s < NP; s++) u[i].d[s] = (n + i == j0 + s) ? 1.0 : 0.0;
+    }
     rk4_step<MODEL, D>(P.params, x, u, P.dt[k], xn);
 #pragma unroll
-    for (int i = 0; i < n; i++) AB[i * ld + j] = xn[i].d[0];
+    for (int i = 0; i < n; i++) {
+        if (NP == 2 && j0 + 1 < nm) *reinterpret_cast<double2*>(&AB[i * ld + j0]) = make_double2(xn[i].d[0], xn[i].d[1]);
+        else {
+#pragma unroll
+            for (int s = 0; s < NP; s++) if (j0 + s < nm) AB[i * ld + j0 + s] = xn[i].d[s];
+        }
+    }
 }
 
 cudaError_t launch_rollout(const DevProblem& P, cudaStream_t s) {
@@ -67,10 +79,22 @@ cudaError_t launch_rollout(const DevProblem& P, cudaStream_t s) {
     return cudaGetLastError();
 }
 
-cudaError_t launch_expand(const DevProblem& P, cudaStream_t s) {
-    const long long total = (long long)P.B * (P.N - 1) * P.ldab;
+template <int MODEL, int NP>
+static cudaError_t launch_expand_t(const DevProblem& P, cudaStream_t s) {
+    constexpr int nm = ModelDims<MODEL>::n + ModelDims<MODEL>::m;
+    constexpr int TPK = (nm + NP - 1) / NP;
+    const long long total = (long long)P.B * (P.N - 1) * TPK;
     const int threads = 128;
-    const long long blocks = (total + threads - 1) / threads;
-    TO_DISPATCH_MODEL(P.model, P.m, (k_expand<MODEL><<<(unsigned)blocks, threads, 0, s>>>(P)));
+    k_expand<MODEL, NP><<<(unsigned)((total + threads - 1) / threads), threads, 0, s>>>(P);
     return cudaGetLastError();
+}
+
+cudaError_t launch_expand(const DevProblem& P, cudaStream_t s) {
+    // seeds per thread: 1 (value recomputed per seed) or 2 (value shared by two seeds, more registers); profiles/r01_notes.md
+    static int np = -1;
+    if (np < 0) { const char* v = getenv("TO_EXPAND_SEEDS"); np = v ? atoi(v) : 1; }
+    cudaError_t e = cudaErrorNotSupported;
+    if (np == 2) { TO_DISPATCH_MODEL(P.model, P.m, (e = launch_expand_t<MODEL, 2>(P, s))); }
+    else { TO_DISPATCH_MODEL(P.model, P.m, (e = launch_expand_t<MODEL, 1>(P, s))); }
+    return e;
 }

@@ -304,10 +304,12 @@ int to_create(const to_spec* s, to_handle** out) {
         for (const auto& c : h->h_cons) if (c.diagonal) cnt += (c.row_max[j] >= 0) + (c.kind == CON_BOUND && c.row_min[j] >= 0);
         P.max_terms_per_z = std::max(P.max_terms_per_z, cnt);
     }
+    P.max_cons_knot = 0;
     for (int k = 1; k <= N; k++) {
-        int pk = 0;
-        for (const auto& c : h->h_cons) if (k >= c.first && k <= c.last) pk += c.p;
+        int pk = 0, nk = 0;
+        for (const auto& c : h->h_cons) if (k >= c.first && k <= c.last) { pk += c.p; nk++; }
         P.max_p_knot = std::max(P.max_p_knot, pk);
+        P.max_cons_knot = std::max(P.max_cons_knot, nk);
     }
     h->h_mu.assign(s->ncon, P.opt.penalty_initial);
     h->h_dt.assign(s->dt, s->dt + (N - 1));

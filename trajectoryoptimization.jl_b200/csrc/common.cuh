@@ -71,7 +71,7 @@ struct DevProblem {
     int all_diag_con;         // every constraint is Goal/Bound
     int max_p_knot;           // largest number of constraint rows active at one knot
     int max_terms_per_z;      // largest number of Goal/Bound rows acting on one z entry
-    int pad1;
+    int max_cons_knot;        // largest number of constraints active at one knot
     double params[16];
     DevOptions opt;
     const double* dt;         // [N-1]

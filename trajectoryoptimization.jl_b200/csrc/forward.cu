@@ -34,7 +34,7 @@ constexpr int FWD_THREADS = 32;
 struct FwdCon {
     int kind, first, last, p, offset;
     unsigned mask_max, mask_min;     // bit j set: z_j has a finite upper / lower bound (Goal: x_j constrained)
-    int pad;
+    int ubox;                        // Bound with both bounds finite on every control and none on the state: rows are static
     double mu, inv2mu;
     int row_max[TO_MAXNM], row_min[TO_MAXNM];
     double a[TO_MAXNM], b[TO_MAXNM];
@@ -48,6 +48,8 @@ struct alignas(16) FwdTab {
     FwdCost cost[FWD_MAX_COST];
     double dt[FWD_MAX_N];
     int cost_index[FWD_MAX_N];
+    int lam_off[FWD_MAX_N][2];       // multipliers to stage for knot k: up to two (offset, count) segments of lambda_b
+    int lam_cnt[FWD_MAX_N][2];
 };
 
 __device__ inline void load_tables(const DevProblem& P, FwdTab& tab) {
@@ -62,6 +64,8 @@ __device__ inline void load_tables(const DevProblem& P, FwdTab& tab) {
             unsigned mx = 0, mn = 0;
             for (int j = 0; j < TO_MAXNM; j++) { if (c.row_max[j] >= 0) mx |= 1u << j; if (c.row_min[j] >= 0) mn |= 1u << j; }
             f.mask_max = mx; f.mask_min = mn;
+            const unsigned ubits = ((1u << P.m) - 1u) << P.n;
+            f.ubox = (c.kind == CON_BOUND && mx == ubits && mn == ubits) ? 1 : 0;
         }
         for (int j = t; j < TO_MAXNM; j += T) {
             f.row_max[j] = c.row_max[j]; f.row_min[j] = c.row_min[j];
@@ -76,7 +80,17 @@ __device__ inline void load_tables(const DevProblem& P, FwdTab& tab) {
             for (int j = t; j < TO_MAXM; j += T) { f.Rd[j] = c.Rd[j]; f.r[j] = c.r[j]; }
             if (t == 0) f.c = c.c;
         }
-    for (int k = t; k < P.N && k < FWD_MAX_N; k += T) { tab.dt[k] = (k < P.N - 1) ? P.dt[k] : 0.0; tab.cost_index[k] = P.cost_index[k]; }
+    for (int k = t; k < P.N && k < FWD_MAX_N; k += T) {
+        tab.dt[k] = (k < P.N - 1) ? P.dt[k] : 0.0; tab.cost_index[k] = P.cost_index[k];
+        int ns = 0;
+        tab.lam_cnt[k][0] = tab.lam_cnt[k][1] = 0; tab.lam_off[k][0] = tab.lam_off[k][1] = 0;
+        for (int ci = 0; ci < P.ncon; ci++) {
+            const DevCon& c = P.cons[ci];
+            if (k + 1 < c.first || k + 1 > c.last) continue;
+            if (ns < 2) { tab.lam_off[k][ns] = c.offset + (k + 1 - c.first) * c.p; tab.lam_cnt[k][ns] = c.p; }
+            ns++;
+        }
+    }
     __syncthreads();
 }
 
@@ -132,14 +146,13 @@ __device__ __forceinline__ void prefetch_knot(double* base, int g, int l, int k,
             else if (s < 2 * m + n) cp_async8(base + S::sidx(S::OFF_X + s - 2 * m, g), X + (size_t)k * n + (s - 2 * m));
         }
     }
-    // multipliers of the constraints active at knot k+1 (1-based), packed in constraint order
-    int slot = 0;
-    for (int ci = 0; ci < tab.ncon; ci++) {
-        const FwdCon& c = tab.con[ci];
-        if (k + 1 < c.first || k + 1 > c.last) continue;
-        const double* lam = lam_b + c.offset + (size_t)(k + 1 - c.first) * c.p;
-        for (int i = l; i < c.p; i += G) cp_async8(base + S::sidx(S::OFF_L + slot + i, g), lam + i);
-        slot += c.p;
+    // multipliers of the (at most two) constraints active at knot k+1, packed in constraint order
+    {
+        const int c0 = tab.lam_cnt[k][0], c1 = tab.lam_cnt[k][1];
+        const double* l0 = lam_b + tab.lam_off[k][0];
+        const double* l1 = lam_b + tab.lam_off[k][1];
+        for (int i = l; i < c0; i += G) cp_async8(base + S::sidx(S::OFF_L + i, g), l0 + i);
+        for (int i = l; i < c1; i += G) cp_async8(base + S::sidx(S::OFF_L + c0 + i, g), l1 + i);
     }
 }
 
@@ -248,6 +261,14 @@ __device__ __forceinline__ double rollout_fast(const DevProblem& P, const FwdTab
                             const double lp = fma(-mu, x[i] - c.a[row], lm);
                             a = fma(lp, lp, a); l2 = fma(lm, lm, l2);
                         }
+                    }
+                } else if (c.ubox) {
+                    // u_min <= u <= u_max on every control: rows 0..m-1 = upper, m..2m-1 = lower (src/constraints.jl:738-755)
+#pragma unroll
+                    for (int i = 0; i < m; i++) {
+                        const double lu = st[S::sidx(lo + i, g)], ll = st[S::sidx(lo + m + i, g)];
+                        const double pu = fmin(0.0, fma(-mu, u[i] - c.a[n + i], lu)), pl = fmin(0.0, fma(-mu, c.b[n + i] - u[i], ll));
+                        a = fma(pu, pu, a); a = fma(pl, pl, a); l2 = fma(lu, lu, l2); l2 = fma(ll, ll, l2);
                     }
                 } else {
                     const unsigned mx = c.mask_max, mn = c.mask_min;
@@ -411,7 +432,7 @@ cudaError_t launch_pass(const DevProblem& P, int trial0, int first_pass, int fin
 }
 
 bool fast_path(const DevProblem& P) {
-    return P.all_diag_cost && P.all_diag_con && P.N <= FWD_MAX_N && P.max_p_knot <= 2 * (P.n + P.m);
+    return P.all_diag_cost && P.all_diag_con && P.N <= FWD_MAX_N && P.max_p_knot <= 2 * (P.n + P.m) && P.max_cons_knot <= 2;
 }
 
 }  // namespace

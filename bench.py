@@ -195,13 +195,22 @@ def main():
         K.check(lib, h, lib.to_set_controls(h, dptr(U0_host)))
         K.check(lib, h, lib.to_rollout(h))
 
+    side = torch.cuda.Stream() if world > 1 else None
+
     def step():
         K.check(lib, h, lib.to_ilqr_step(h, 1))
-        if world > 1:   # the path's only collective: {sum merit, max violation} SUM/MAX all-reduce
-            TO.multi_gpu.global_merit(prob, device_tensor=merit2)
+        if world > 1:
+            # the path's only collective: {sum merit, max violation} SUM/MAX all-reduce.  Nothing on the device
+            # consumes it, so it runs on a side stream and overlaps the next iteration's kernels.
+            stream.wait_stream(side)                                     # previous all-reduce has released the buffer
+            K.check(lib, h, lib.to_reduce_merit(h))                      # per-GPU {sum J, max viol} (one small kernel)
+            side.wait_stream(stream)
+            with torch.cuda.stream(side):
+                TO.multi_gpu.all_reduce_merit(merit2)
 
     def barrier():
         if world > 1:
+            stream.wait_stream(side)
             dist.barrier()
         torch.cuda.synchronize()
 

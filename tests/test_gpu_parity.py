@@ -211,3 +211,21 @@ def test_full_size_properties_quadrotor():
     x0 = np.array([1, 2, 1, 1, 0, 0, 0, 0, 0, 0, 0, 0, 0.0])
     TO.set_initial_state(prob, x0); TO.initial_controls(prob, TO.Quadrotor().hover_control()); TO.rollout(prob)
     assert np.allclose(TO.states(prob)[:, -1], x0, rtol=1.5e-8)
+
+
+def test_reduce_merit_buffer_tracks_line_search_results():
+    """{sum J, max violation} maintained by the line search (no extra sweep) equals a fresh cost + constraint sweep"""
+    import torch
+    prob = P.quadrotor(B=257, N=101)
+    TO.rollout(prob)
+    TO.ilqr_step(prob, 3)
+    t2 = TO.multi_gpu.merit_device_tensor(prob, "cuda:0")
+    TO.multi_gpu.global_merit(prob, device_tensor=t2)
+    torch.cuda.synchronize()
+    got = t2.cpu().numpy().copy()
+    assert np.isclose(got[0], TO.merit(prob).sum(), rtol=1e-12)
+    assert np.isclose(got[1], TO.max_violation(prob).max(), rtol=1e-12)
+    TO.al_update(prob)                       # invalidates J: the next reduce recomputes it
+    TO.multi_gpu.global_merit(prob, device_tensor=t2)
+    torch.cuda.synchronize()
+    assert np.isclose(t2.cpu().numpy()[0], TO.merit(prob).sum(), rtol=1e-12)

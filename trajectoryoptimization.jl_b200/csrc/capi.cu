@@ -329,7 +329,7 @@ int to_create(const to_spec* s, to_handle** out) {
     ALLOC(h->d_work, 1); ALLOC(h->d_err, 1);
 #undef ALLOC
     if (rc) return bail(rc);
-    P.dt = d_dt; P.cost_index = d_ci; P.costs = h->d_costs; P.cons = h->d_cons; P.mu = h->d_mu;
+    P.dt = d_dt; P.cost_index = d_ci; P.costs = h->d_costs; P.cons = h->d_cons; P.mu = h->d_mu; P.viol = h->d_viol;
     cudaStream_t st = h->stream;
     bool okc = true;
     okc &= cudaMemcpyAsync(d_dt, h->h_dt.data(), sizeof(double) * (N - 1), cudaMemcpyHostToDevice, st) == cudaSuccess;
@@ -746,8 +746,7 @@ int to_get_solver_state(to_handle* h, double* rho, double* dV, double* alpha, in
 // ---- multi-GPU / measurement plumbing -----------------------------------------------------------------------
 int to_reduce_merit(to_handle* h) {
     if (!h) return TO_EINVAL;
-    CU(h, launch_merit(h->P, h->P.J, h->d_viol, h->stream)); h->launches++;
-    h->J_valid = true;
+    int rc = ensure_merit(h); if (rc) return rc;      // J and viol are kept current by the line search; recomputed only after edits
     CU(h, launch_reduce_merit(h->P, h->d_viol, h->d_merit2, h->stream)); h->launches++;
     return TO_OK;
 }

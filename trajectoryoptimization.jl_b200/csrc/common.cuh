@@ -92,6 +92,7 @@ struct DevProblem {
     double* dV;               // [B][2]
     double* J;                // [B] merit of the live trajectory
     double* Jc;               // [B] merit of the candidate
+    double* viol;             // [B] max constraint violation of the live trajectory
     double* alpha;            // [B]
     int* bp_status;           // [B]
     int* ls_iters;            // [B]

@@ -160,7 +160,7 @@ __device__ __forceinline__ void prefetch_knot(double* base, int g, int l, int k,
 // The candidate trajectory goes to buffer `cbuf`.  Returns the merit; `ok` = no blow-up.
 template <int MODEL, int IPB, int G>
 __device__ __forceinline__ double rollout_fast(const DevProblem& P, const FwdTab& tab, double* stage, int b, int g, int l, unsigned gmask,
-                                               double alpha, int cbuf, bool& ok) {
+                                               double alpha, int cbuf, bool& ok, double& viol) {
     constexpr int n = ModelDims<MODEL>::n, m = ModelDims<MODEL>::m;
     using S = Stage<n, m, IPB>;
     const int N = P.N, buf = P.cur[b];
@@ -173,7 +173,7 @@ __device__ __forceinline__ double rollout_fast(const DevProblem& P, const FwdTab
     const double* lam_b = P.lambda + (size_t)b * P.lambda_len;
     double x[n], u[m], xn[n];
     double J = 0.0;
-    ok = true;
+    ok = true; viol = 0.0;
 #pragma unroll
     for (int i = 0; i < n; i++) x[i] = P.x0[(size_t)b * n + i];
     prefetch_knot<n, m, IPB, G>(stage, g, l, 0, Kg, dg, X, U, lam_b, tab, N);
@@ -258,8 +258,9 @@ __device__ __forceinline__ double rollout_fast(const DevProblem& P, const FwdTab
                         if (mk & (1u << i)) {
                             const int row = c.row_max[i];
                             const double lm = st[S::sidx(lo + row, g)];
-                            const double lp = fma(-mu, x[i] - c.a[row], lm);
-                            a = fma(lp, lp, a); l2 = fma(lm, lm, l2);
+                            const double cv = x[i] - c.a[row];
+                            const double lp = fma(-mu, cv, lm);
+                            a = fma(lp, lp, a); l2 = fma(lm, lm, l2); viol = fmax(viol, fabs(cv));
                         }
                     }
                 } else if (c.ubox) {
@@ -267,22 +268,24 @@ __device__ __forceinline__ double rollout_fast(const DevProblem& P, const FwdTab
 #pragma unroll
                     for (int i = 0; i < m; i++) {
                         const double lu = st[S::sidx(lo + i, g)], ll = st[S::sidx(lo + m + i, g)];
-                        const double pu = fmin(0.0, fma(-mu, u[i] - c.a[n + i], lu)), pl = fmin(0.0, fma(-mu, c.b[n + i] - u[i], ll));
+                        const double cu = u[i] - c.a[n + i], cl = c.b[n + i] - u[i];
+                        const double pu = fmin(0.0, fma(-mu, cu, lu)), pl = fmin(0.0, fma(-mu, cl, ll));
                         a = fma(pu, pu, a); a = fma(pl, pl, a); l2 = fma(lu, lu, l2); l2 = fma(ll, ll, l2);
+                        viol = fmax(viol, fmax(cu, cl));
                     }
                 } else {
                     const unsigned mx = c.mask_max, mn = c.mask_min;
                     if ((mx | mn) & ((1u << n) - 1u)) {
 #pragma unroll
                         for (int i = 0; i < n; i++) {
-                            if (mx & (1u << i)) { const double lm = st[S::sidx(lo + c.row_max[i], g)]; const double lp = fmin(0.0, fma(-mu, x[i] - c.a[i], lm)); a = fma(lp, lp, a); l2 = fma(lm, lm, l2); }
-                            if (mn & (1u << i)) { const double lm = st[S::sidx(lo + c.row_min[i], g)]; const double lp = fmin(0.0, fma(-mu, c.b[i] - x[i], lm)); a = fma(lp, lp, a); l2 = fma(lm, lm, l2); }
+                            if (mx & (1u << i)) { const double lm = st[S::sidx(lo + c.row_max[i], g)]; const double cv = x[i] - c.a[i]; const double lp = fmin(0.0, fma(-mu, cv, lm)); a = fma(lp, lp, a); l2 = fma(lm, lm, l2); viol = fmax(viol, cv); }
+                            if (mn & (1u << i)) { const double lm = st[S::sidx(lo + c.row_min[i], g)]; const double cv = c.b[i] - x[i]; const double lp = fmin(0.0, fma(-mu, cv, lm)); a = fma(lp, lp, a); l2 = fma(lm, lm, l2); viol = fmax(viol, cv); }
                         }
                     }
 #pragma unroll
                     for (int i = 0; i < m; i++) {
-                        if (mx & (1u << (n + i))) { const double lm = st[S::sidx(lo + c.row_max[n + i], g)]; const double lp = fmin(0.0, fma(-mu, u[i] - c.a[n + i], lm)); a = fma(lp, lp, a); l2 = fma(lm, lm, l2); }
-                        if (mn & (1u << (n + i))) { const double lm = st[S::sidx(lo + c.row_min[n + i], g)]; const double lp = fmin(0.0, fma(-mu, c.b[n + i] - u[i], lm)); a = fma(lp, lp, a); l2 = fma(lm, lm, l2); }
+                        if (mx & (1u << (n + i))) { const double lm = st[S::sidx(lo + c.row_max[n + i], g)]; const double cv = u[i] - c.a[n + i]; const double lp = fmin(0.0, fma(-mu, cv, lm)); a = fma(lp, lp, a); l2 = fma(lm, lm, l2); viol = fmax(viol, cv); }
+                        if (mn & (1u << (n + i))) { const double lm = st[S::sidx(lo + c.row_min[n + i], g)]; const double cv = c.b[n + i] - u[i]; const double lp = fmin(0.0, fma(-mu, cv, lm)); a = fma(lp, lp, a); l2 = fma(lm, lm, l2); viol = fmax(viol, cv); }
                     }
                 }
                 J = fma(a - l2, c.inv2mu, J);
@@ -302,7 +305,7 @@ __device__ __forceinline__ double rollout_fast(const DevProblem& P, const FwdTab
 
 // generic path (dense costs or general constraints): pointer-based evaluation, operands read directly from global
 template <int MODEL>
-__device__ __forceinline__ double rollout_generic(const DevProblem& P, int b, double alpha, int cbuf, bool& ok) {
+__device__ __forceinline__ double rollout_generic(const DevProblem& P, int b, double alpha, int cbuf, bool& ok, double& viol) {
     constexpr int n = ModelDims<MODEL>::n, m = ModelDims<MODEL>::m;
     const int N = P.N, buf = P.cur[b];
     const double* X = traj_X(P, buf, b);
@@ -313,8 +316,8 @@ __device__ __forceinline__ double rollout_generic(const DevProblem& P, int b, do
     const double* dg = P.d + (size_t)b * (N - 1) * m;
     const double* lam_b = P.lambda + (size_t)b * P.lambda_len;
     double x[n], u[m], xn[n];
-    double J = 0.0, viol = 0.0;
-    ok = true;
+    double J = 0.0;
+    ok = true; viol = 0.0;
 #pragma unroll
     for (int i = 0; i < n; i++) x[i] = P.x0[(size_t)b * n + i];
     for (int k = 0; k < N; k++) {
@@ -387,15 +390,15 @@ __global__ void __launch_bounds__(FWD_THREADS) k_linesearch(const DevProblem P, 
         const double alpha = ldexp(1.0, -trial);
         const int cbuf = (P.cur[b] + 1 + l) % TO_NBUF;
         bool ok = false;
-        double J;
-        if (FAST) J = rollout_fast<MODEL, IPB, G>(P, *tab, stage, b, g, l, gmask, alpha, cbuf, ok);
-        else J = rollout_generic<MODEL>(P, b, alpha, cbuf, ok);
+        double J, viol = 0.0;
+        if (FAST) J = rollout_fast<MODEL, IPB, G>(P, *tab, stage, b, g, l, gmask, alpha, cbuf, ok, viol);
+        else J = rollout_generic<MODEL>(P, b, alpha, cbuf, ok, viol);
         const bool good = (trial <= P.opt.ls_iters) && ls_accept(P, J, P.J[b], alpha, P.dV[2 * b], P.dV[2 * b + 1], ok);
         const unsigned votes = __ballot_sync(gmask, good) & gmask;
         if (votes) {
             const int win = __ffs(votes) - 1 - g * G;
             if (l == win) {
-                P.cur[b] = cbuf; P.J[b] = J; P.alpha[b] = alpha; P.ls_iters[b] = trial + 1; P.accepted[b] = 1;
+                P.cur[b] = cbuf; P.J[b] = J; P.viol[b] = viol; P.alpha[b] = alpha; P.ls_iters[b] = trial + 1; P.accepted[b] = 1;
             }
             accepted = true;
         }

@@ -227,6 +227,8 @@ def main():
     e0.record(stream)
     for _ in range(args.steps):
         step()
+    if side is not None:
+        stream.wait_stream(side)      # the last all-reduce is inside the timed region
     e1.record(stream)
     barrier()
     ms = e0.elapsed_time(e1)

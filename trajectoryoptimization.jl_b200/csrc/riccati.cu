@@ -65,6 +65,13 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                  : "memory");
 }
 
+// global load the compiler may not sink towards its use (prefetch of the next knot's operands)
+__device__ __forceinline__ double ldg_pinned(const double* p) {
+    double v;
+    asm volatile("ld.global.nc.f64 %0, [%1];" : "=d"(v) : "l"(p));
+    return v;
+}
+
 // 2x2 micro-block outer-product accumulate
 __device__ __forceinline__ void fma2x2(double (&acc)[4], const double2& a, const double2& b) {
     acc[0] = fma(a.x, b.x, acc[0]);
@@ -218,9 +225,13 @@ __global__ void __launch_bounds__(32, MINB) k_riccati(const DevProblem P, int* _
         const int zstride = (lane < n) ? n : m;
 
         // the expansion of one knot for this lane: (gi, hi) = (lz_i, lzz_ii) from z_i and its multipliers
-        auto expand_fast = [&](int k, double zi, const double (&lam)[MAXT], const DevCost& cost, double& gi, double& hi) {
-            if (lane < n) { gi = fma(cost.Qd[lane], zi, cost.q[lane]); hi = cost.Qd[lane]; }
-            else { gi = fma(cost.Rd[lane - n], zi, cost.r[lane - n]); hi = cost.Rd[lane - n]; }
+        // (cH, cG) = (Qd_i | Rd_i, q_i | r_i) of this lane's z_i for a DiagonalCost
+        auto cost_coeff_ptr = [&](int cid, bool hess) -> const double* {
+            const DevCost& c = P.costs[cid];
+            return (lane < n) ? (hess ? &c.Qd[lane] : &c.q[lane]) : (hess ? &c.Rd[lane < NM ? lane - n : 0] : &c.r[lane < NM ? lane - n : 0]);
+        };
+        auto expand_fast = [&](int k, double zi, const double (&lam)[MAXT], double cH, double cG, double& gi, double& hi) {
+            gi = fma(cH, zi, cG); hi = cH;
 #pragma unroll
             for (int t = 0; t < MAXT; t++) {
                 if (k + 1 >= term[t].first && k + 1 <= term[t].last) {
@@ -233,7 +244,7 @@ __global__ void __launch_bounds__(32, MINB) k_riccati(const DevProblem P, int* _
 #pragma unroll
             for (int t = 0; t < MAXT; t++) {
                 lam[t] = 0.0;
-                if (k + 1 >= term[t].first && k + 1 <= term[t].last) lam[t] = lam_b[term[t].base + (size_t)(k + 1 - term[t].first) * term[t].p];
+                if (k + 1 >= term[t].first && k + 1 <= term[t].last) lam[t] = ldg_pinned(lam_b + term[t].base + (size_t)(k + 1 - term[t].first) * term[t].p);
             }
         };
 
@@ -265,7 +276,7 @@ __global__ void __launch_bounds__(32, MINB) k_riccati(const DevProblem P, int* _
                     if (FASTAL && cost.diag) {
                         double lam[MAXT];
                         load_lams(N - 1, lam);
-                        expand_fast(N - 1, xi, lam, cost, gi, hi);
+                        expand_fast(N - 1, xi, lam, cost.Qd[lane], cost.q[lane], gi, hi);
                         sm.S[i * LDS_ + i] = hi;
                     } else {
                         gi = cost.q[i]; hi = 0.0;
@@ -298,6 +309,10 @@ __global__ void __launch_bounds__(32, MINB) k_riccati(const DevProblem P, int* _
 #pragma unroll
             for (int t = 0; t < MAXT; t++) lam_cur[t] = 0.0;
             if (lane < NM) { z_cur = zbase[(size_t)(N - 2) * zstride]; if (FASTAL) load_lams(N - 2, lam_cur); }
+            // software pipeline of the cost coefficients: (cH,cG) of knot k are loaded during knot k+1, its index during knot k+2
+            double cH_cur = 0.0, cG_cur = 0.0;
+            int cid_next = (N >= 3) ? P.cost_index[N - 3] : 0;
+            if (FASTAL && P.all_diag_cost) { const int c0 = P.cost_index[N - 2]; cH_cur = *cost_coeff_ptr(c0, true); cG_cur = *cost_coeff_ptr(c0, false); }
             __syncwarp();
 
             double dV1 = 0.0, dV2 = 0.0;   // accumulated by lane n
@@ -309,17 +324,25 @@ __global__ void __launch_bounds__(32, MINB) k_riccati(const DevProblem P, int* _
                 double z_nxt = 0.0, lam_nxt[MAXT];
 #pragma unroll
                 for (int t = 0; t < MAXT; t++) lam_nxt[t] = 0.0;
-                if (k > 0 && lane < NM) { z_nxt = zbase[(size_t)(k - 1) * zstride]; if (FASTAL) load_lams(k - 1, lam_nxt); }
+                if (k > 0 && lane < NM) { z_nxt = ldg_pinned(zbase + (size_t)(k - 1) * zstride); if (FASTAL) load_lams(k - 1, lam_nxt); }
+                double cH_nxt = 0.0, cG_nxt = 0.0;
+                int cid_next2 = 0;
+                if (FASTAL && P.all_diag_cost && k > 0) {
+                    cH_nxt = ldg_pinned(cost_coeff_ptr(cid_next, true)); cG_nxt = ldg_pinned(cost_coeff_ptr(cid_next, false));
+                    if (k > 1) cid_next2 = P.cost_index[k - 2];
+                }
                 // ---- cost + AL expansion of knot k: lane i < NM handles z_i (diagonal terms) ------------
                 double g_reg = 0.0, h_reg = 0.0;
                 {
-                    const DevCost& cost = P.costs[P.cost_index[k]];
                     double gi = 0.0, hi = 0.0;
-                    if (lane < NM) {
+                    if (FASTAL && P.all_diag_cost) {
+                        if (lane < NM) expand_fast(k, z_cur, lam_cur, cH_cur, cG_cur, gi, hi);
+                    } else if (lane < NM) {
+                        const DevCost& cost = P.costs[P.cost_index[k]];
                         const int i = lane;
                         const double zi = z_cur;
                         if (FASTAL && cost.diag) {
-                            expand_fast(k, zi, lam_cur, cost, gi, hi);
+                            expand_fast(k, zi, lam_cur, (i < n) ? cost.Qd[i] : cost.Rd[i - n], (i < n) ? cost.q[i] : cost.r[i - n], gi, hi);
                         } else {
                             if (cost.diag) {
                                 if (i < n) { gi = fma(cost.Qd[i], zi, cost.q[i]); hi = cost.Qd[i]; }
@@ -760,7 +783,7 @@ __global__ void __launch_bounds__(32, MINB) k_riccati(const DevProblem P, int* _
                         }
                     }
                 }
-                z_cur = z_nxt;
+                z_cur = z_nxt; cH_cur = cH_nxt; cG_cur = cG_nxt; cid_next = cid_next2;
 #pragma unroll
                 for (int t = 0; t < MAXT; t++) lam_cur[t] = lam_nxt[t];
                 __syncwarp();

@@ -29,6 +29,9 @@ CONFIGS = {
     "cartpole_altro": lambda cls: P.cartpole(B=5, N=101, cls=cls, u_bound=3.0, goal=True, dt_scaled_cost=True),
     "quadrotor": lambda cls: P.quadrotor(B=33, N=101, cls=cls),
     "quadrotor_short": lambda cls: P.quadrotor(B=4, N=4, cls=cls, dt=0.05),
+    "quadrotor_dense_cost": lambda cls: P.quadrotor(B=5, N=31, cls=cls, dt=0.05, dense_cost=True),
+    "quadrotor_long": lambda cls: P.quadrotor(B=2, N=401, cls=cls, dt=0.05),
+    "cartpole_single": lambda cls: P.cartpole(B=1, N=2, cls=cls),
     "acrobot_dense": lambda cls: P.acrobot(B=9, N=201, cls=cls, dense_cost=True),
     "acrobot_diag": lambda cls: P.acrobot(B=3, N=51, cls=cls, dense_cost=False),
 }
@@ -145,9 +148,9 @@ def test_cones_match_oracle_and_reference_kats():
     assert np.array_equal(TO.projection(TO.Inequality(), np.array([1, 2, -3.0])), [0, 0, -3.0])   # test/cone_tests.jl:70-75
 
 
-def test_evaluation_only_constraints_and_quickstart_problem():
-    """the full examples/quickstart.jl problem (Goal + Circle + SOC norm + bounds) evaluates on the device; the solver
-    kernels reject the non Goal/Bound kinds loudly."""
+def test_quickstart_problem_with_general_constraints():
+    """the full examples/quickstart.jl problem (Goal + Circle + SOC norm + bounds): evaluation AND iLQR iterations on the
+    device (general-constraint AL path of the solver kernels) against the oracle."""
     r = np.random.default_rng(1)
     model = TO.DoubleIntegrator(2)
     n, m, N = 4, 2, 21
@@ -172,8 +175,61 @@ def test_evaluation_only_constraints_and_quickstart_problem():
     close(TO.max_violation(g), TO.max_violation(o), KERNEL_RTOL, "violation")
     gg, gh = TO.al_expansion(g); og, oh = TO.al_expansion(o)
     close(gg, og, KERNEL_RTOL, "AL gradient"); close(gh, oh, KERNEL_RTOL, "AL hessian")
-    with pytest.raises(TO.TrajOptError):
-        TO.ilqr_step(g, 1)
+    for p in probs:
+        TO.ilqr_step(p, 2)
+    close(TO.merit(g), TO.merit(o), ITER_RTOL, "merit after 2 iterations (SOC + circle + bounds + goal)")
+    close(TO.states(g), TO.states(o), 1e-6, "X")
+    for p in probs:
+        TO.al_update(p); TO.ilqr_step(p, 1)
+    close(TO.merit(g), TO.merit(o), 1e-5, "merit after AL update")
+    for i in range(4):
+        close(TO.multipliers(g, i), TO.multipliers(o, i), 1e-6, f"multipliers {i}")
+
+
+def _general_pair(kind):
+    r = np.random.default_rng(3)
+    probs = []
+    for cls in (TO.Problem, OracleProblem):
+        if kind == "cartpole_linear_circle":
+            prob = P.cartpole(B=4, N=41, cls=cls, u_bound=3.0, goal=True, dt_scaled_cost=True)
+            n, m, N = 4, 1, 41
+            cons = prob.constraints
+            extra = [(TO.LinearConstraint(n, m, [[1.0], [-1.0]], [2.5, 2.5], TO.Inequality(), "control"), (1, N - 1)),
+                     (TO.CircleConstraint(n, [1.5, -1.5], [2.0, 1.0], [0.3, 0.2]), (2, N - 1)),
+                     (TO.LinearConstraint(n, m, [[0.0, 0.0, 1.0, 0.0]], [0.0], TO.Equality(), "state"), N)]
+        else:
+            prob = P.quadrotor(B=3, N=21, cls=cls, dt=0.05)
+            n, m, N = 13, 4, 21
+            cons = prob.constraints
+            extra = [(TO.SphereConstraint(n, [0.5, 0.2], [1.0, 0.5], [1.5, 1.2], [0.3, 0.25]), (2, N - 1)),
+                     (TO.NormConstraint(n, m, 12.0, TO.SecondOrderCone(), "control"), (1, N - 1)),
+                     (TO.NormConstraint(n, m, 3.0, TO.Inequality(), [8, 9, 10]), (1, N))]
+        prob.close()
+        for con, inds in extra:
+            TO.add_constraint(cons, con, inds)
+        prob2 = cls(prob.model, prob.obj, prob.x0, 5.0 if kind.startswith("cart") else 1.0, xf=prob.xf, constraints=cons)
+        TO.initial_controls(prob2, 0.3 if kind.startswith("cart") else TO.Quadrotor().hover_control() + 0.1)
+        probs.append(prob2)
+    return probs
+
+
+@pytest.mark.parametrize("kind", ["cartpole_linear_circle", "quadrotor_sphere_soc_norm"])
+def test_general_constraints_in_solver_kernels(kind):
+    g, o = _general_pair(kind)
+    for p in (g, o):
+        TO.rollout(p); TO.expand(p)
+    gg, gh = TO.al_expansion(g); og, oh = TO.al_expansion(o)
+    close(gg, og, KERNEL_RTOL, "AL gradient"); close(gh, oh, KERNEL_RTOL, "AL hessian")
+    assert np.array_equal(TO.backward(g), TO.backward(o))
+    Kg, dg = TO.gains(g); Ko, do = TO.gains(o)
+    close(Kg, Ko, 1e-8, "K"); close(dg, do, 1e-8, "d")
+    Jg, ag = TO.forward(g); Jo, ao = TO.forward(o)
+    assert np.array_equal(ag, ao)
+    close(Jg, Jo, 1e-8, "J")
+    for p in (g, o):
+        TO.ilqr_step(p, 2); TO.al_update(p); TO.ilqr_step(p, 1)
+    close(TO.merit(g), TO.merit(o), 1e-5, "merit")
+    close(TO.max_violation(g), TO.max_violation(o), 1e-5, "violation")
 
 
 def test_error_behaviour():

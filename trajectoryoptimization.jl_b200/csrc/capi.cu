@@ -634,8 +634,11 @@ int to_hess_projection(to_handle* h, int32_t cone, int32_t p, int32_t count, con
 
 // ---- kernel 3 + forward pass --------------------------------------------------------------------------------
 static int solver_supported(to_handle* h) {
-    if (!h->P.all_diag_con)
-        return fail(h, TO_ESTATE, "the Riccati / forward kernels handle Goal and Bound constraints only (others are evaluation-only in this release)");
+    // Goal / Bound rows are handled lane-resident; any other kind goes through the warp-cooperative general path of
+    // k_riccati (DFMA variant) and the pointer-based rollout, which take up to 16 rows per constraint and knot.
+    for (const auto& c : h->h_cons)
+        if (!c.diagonal && c.p > 16)
+            return fail(h, TO_ESTATE, "the solver kernels take at most 16 rows per general (non Goal/Bound) constraint");
     return TO_OK;
 }
 static int do_backward(to_handle* h) {

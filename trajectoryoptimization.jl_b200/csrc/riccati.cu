@@ -89,7 +89,7 @@ struct RiccatiSmem {
     static constexpr int NM = N_ + M_;
     static constexpr int NP = even_up(N_);          // padded state dim
     static constexpr int MMA_LD = 20;               // = 4 (mod 16): conflict-free m8n8k4 fragment loads
-    static constexpr int LDAB = MMA ? MMA_LD : even_up(NM);       // row stride of [A B] in HBM (to_create sets P.ldab alike)
+    static constexpr int LDAB = (N_ >= 8 && N_ <= 16 && NM + 1 <= MMA_LD) ? MMA_LD : even_up(NM);   // row stride of [A B] in HBM == P.ldab (to_create)
     static constexpr int LDABS = LDAB;                            // ... and in shared memory (one bulk copy per knot)
     static constexpr int LDS_ = MMA ? MMA_LD : NP;                // S
     static constexpr int LDT = MMA ? MMA_LD : even_up(NM + 1);    // T / Q: one extra column carries s / Qz
@@ -109,6 +109,9 @@ struct RiccatiSmem {
     double W[4 * LDK + 8];
     double g[even_up(NM) + 2];   // lz (cost + AL gradient), padded
     double h[even_up(NM) + 2];   // diag(lzz)
+    // scratch of the general-constraint AL expansion (Linear / Circle / Sphere / Norm incl. SOC), DFMA path only
+    static constexpr int GP = MMA ? 1 : 16;         // rows of one general constraint handled by the solver kernels
+    double gc[GP], glbar[GP], glp[GP], gD[GP * GP], gjac[GP * (MMA ? 1 : TO_MAXNM)], gtmp[GP * (MMA ? 1 : TO_MAXNM)];
     uint64_t bar[STAGES];
 };
 
@@ -248,6 +251,54 @@ __global__ void __launch_bounds__(32, MINB) k_riccati(const DevProblem P, int* _
             }
         };
 
+        // AL expansion of the non-selector constraints active at knot k1 (1-based): Gauss-Newton terms
+        //   grad -= (D cz)' lp ,  hess += mu (D cz)'(D cz)   with D = grad Pi_K*(lambda - mu c), lp = Pi_K*(lambda - mu c)
+        // added to [Q | Qz] (stage knots) or to S / s (terminal).  Warp-cooperative slow path; lane 0 evaluates c and cz.
+        auto general_constraints = [&](int k1, bool terminal, double& s_lane) {
+            if constexpr (!MMA) {
+                for (int ci = 0; ci < P.ncon; ci++) {
+                    const DevCon& con = P.cons[ci];
+                    if (con.diagonal || k1 < con.first || k1 > con.last) continue;
+                    const int p = con.p;
+                    const double mu = P.mu[ci];
+                    const double* lam = lam_b + con.offset + (size_t)(k1 - con.first) * p;
+                    const double* xk = X + (size_t)(k1 - 1) * n;
+                    if (lane == 0) {
+                        double uz[M_];
+                        for (int a = 0; a < m; a++) uz[a] = terminal ? 0.0 : U[(size_t)(k1 - 1) * m + a];
+                        con_evaluate(con, n, m, xk, uz, sm.gc);
+                        con_jacobian(con, n, m, xk, uz, sm.gjac);
+                    }
+                    __syncwarp();
+                    if (lane < p) sm.glbar[lane] = lam[lane] - mu * sm.gc[lane];
+                    __syncwarp();
+                    if (lane == 0) { const int dc = dualcone(con.sense); cone_projection(dc, sm.glbar, p, sm.glp); cone_grad_projection(dc, sm.glbar, p, sm.gD); }
+                    __syncwarp();
+                    for (int e = lane; e < p * NM; e += 32) {
+                        const int i = e % p, j = e / p;
+                        double t = 0.0;
+                        for (int r = 0; r < p; r++) t = fma(sm.gD[r * p + i], sm.gjac[j * p + r], t);
+                        sm.gtmp[j * p + i] = t;
+                    }
+                    __syncwarp();
+                    const int lim = terminal ? n : NM;
+                    if (lane < lim) {
+                        double gsum = 0.0;
+                        for (int i = 0; i < p; i++) gsum = fma(sm.gtmp[lane * p + i], sm.glp[i], gsum);
+                        if (terminal) s_lane -= gsum; else sm.Q[lane * LDT + NM] -= gsum;
+                    }
+                    for (int e = lane; e < lim * lim; e += 32) {
+                        const int j = e / lim, j2 = e % lim;
+                        if (!terminal && (j >> 1) > (j2 >> 1)) continue;      // Q keeps its upper 2x2 blocks
+                        double hs = 0.0;
+                        for (int i = 0; i < p; i++) hs = fma(sm.gtmp[j * p + i], sm.gtmp[j2 * p + i], hs);
+                        if (terminal) sm.S[j * LDS_ + j2] += mu * hs; else sm.Q[j * LDT + j2] += mu * hs;
+                    }
+                    __syncwarp();
+                }
+            }
+        };
+
         // stream [A B]_k into ring slot st with one bulk TMA copy
         auto issue_ab = [&](int st, int k) {
             if (lane == 0) {
@@ -304,6 +355,7 @@ __global__ void __launch_bounds__(32, MINB) k_riccati(const DevProblem P, int* _
                     s_reg = gi;
                 }
             }
+            if (!P.all_diag_con) { __syncwarp(); general_constraints(N, true, s_reg); }
             // operands of the first stage knot
             double z_cur = 0.0, lam_cur[MAXT];
 #pragma unroll
@@ -665,6 +717,8 @@ __global__ void __launch_bounds__(32, MINB) k_riccati(const DevProblem P, int* _
                             __syncwarp();
                         }
                     }
+
+                    if (!P.all_diag_con) { double dummy = 0.0; general_constraints(k + 1, false, dummy); }
 
                     // ---- gains: LDL' of Quu + rho I, one lane per column of [Qux | Qu] -------------------------
                     double Quu[M_ * (M_ + 1) / 2];           // packed lower by rows

@@ -60,7 +60,7 @@ def cartpole(B=1024, N=101, seed=1, cls=None, u_bound=None, goal=False, dt_scale
     return prob
 
 
-def quadrotor(B=4096, N=101, seed=1, cls=None, constrained=True, dt=None, **kw):
+def quadrotor(B=4096, N=101, seed=1, cls=None, constrained=True, dt=None, dense_cost=False, **kw):
     """Quadrotor point-to-point, test/internal_api.jl:20-34: Q=.1 I, R=.01 I, Qf=100 I, x0=[1,2,1;1,0,0,0;0;0],
     xf=[0,0,2;1,0,0,0;0;0], u in [0,10] at 1..N-1, Goal(xf) at N, tf=5; U0 = hover + N(0,0.05^2);
     batch: r0_b = r0 + U(-1,1)^3.  ``dt`` fixes the step (MPC sweep: dt = .05 for every N)."""
@@ -69,7 +69,14 @@ def quadrotor(B=4096, N=101, seed=1, cls=None, constrained=True, dt=None, **kw):
     n, m = 13, 4
     x0 = np.array([1, 2, 1, 1, 0, 0, 0, 0, 0, 0, 0, 0, 0.0])
     xf = np.array([0, 0, 2, 1, 0, 0, 0, 0, 0, 0, 0, 0, 0.0])
-    obj = TO.LQRObjective(np.full(n, 0.1), np.full(m, 0.01), np.full(n, 100.0), xf, N)
+    if dense_cost:   # QuadraticCost with off-diagonal Q and an x-u cross term: exercises the dense second-order expansion
+        Q = 0.1 * np.eye(n) + 0.002 * (np.ones((n, n)) - np.eye(n)); R = 0.01 * np.eye(m) + 0.001 * (np.ones((m, m)) - np.eye(m))
+        H = 0.001 * np.ones((m, n)); uf = np.full(m, 1.2)
+        stage = TO.QuadraticCost(Q, R, H=H, q=-Q @ xf - H.T @ uf, r=-R @ uf - H @ xf, c=0.5 * xf @ Q @ xf + 0.5 * uf @ R @ uf + uf @ H @ xf)
+        term = TO.QuadraticCost(100.0 * np.eye(n), R, q=-100.0 * xf, c=50.0 * xf @ xf, terminal=True)
+        obj = TO.Objective(stage, term, N)
+    else:
+        obj = TO.LQRObjective(np.full(n, 0.1), np.full(m, 0.01), np.full(n, 100.0), xf, N)
     cons = TO.ConstraintList(n, m, N)
     if constrained:
         TO.add_constraint(cons, TO.BoundConstraint(n, m, u_min=np.zeros(4), u_max=np.full(4, 10.0)), (1, N - 1))

@@ -1,9 +1,11 @@
 #!/usr/bin/env python3
 """Summarise an .ncu-rep (raw page + source page): key metrics, SASS opcode mix, stall reasons.
-usage: ncu_summary.py report.ncu-rep [units_per_launch]   (units = warp-knots etc. for per-unit instruction counts)"""
+usage: ncu_summary.py report.ncu-rep [units_per_launch] [launch_index]   (units = warp-knots etc. for per-unit instruction
+counts; launch_index = which captured launch the SASS / stall breakdown is for, default 0)"""
 import collections, csv, io, subprocess, sys
 rep = sys.argv[1]
-units = float(sys.argv[2]) if len(sys.argv) > 2 else None
+units = float(sys.argv[2]) if len(sys.argv) > 2 and float(sys.argv[2]) > 0 else None
+which = int(sys.argv[3]) if len(sys.argv) > 3 else 0
 raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(raw)))
 hdr = rows[0]
@@ -20,8 +22,9 @@ for li, vals in enumerate(rows[2:]):
             print(f"  {k} = {vals[hdr.index(k)]} {rows[1][hdr.index(k)]}")
 src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(src)))
-# the source page concatenates kernels; take the first block
-start = next(i for i, r in enumerate(rows) if r and r[0] == "Address")
+# the source page concatenates the launches; take block `which`
+start = [i for i, r in enumerate(rows) if r and r[0] == "Address"][which]
+print(f"=== SASS / stall breakdown of launch {which}")
 hdr = rows[start]; idx = {h: i for i, h in enumerate(hdr)}
 data = []
 for r in rows[start + 1:]:

@@ -26,6 +26,9 @@ struct to_handle {
     int device = 0;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
+    cudaStream_t stream2 = nullptr;     // high-priority side stream: late line-search trials overlap the next expansion
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    bool side_pending = false;          // stream2 still holds the late line-search trials of the last iteration (ev_join follows them)
     std::string err;
     std::vector<void*> allocs;
     std::vector<DevCost> h_costs;
@@ -101,15 +104,16 @@ int upload_tables(to_handle* h) {
 // phase timing helpers
 struct PhaseScope {
     to_handle* h; int phase; cudaEvent_t a = nullptr, b = nullptr;
-    PhaseScope(to_handle* h_, int phase_) : h(h_), phase(phase_) {
+    cudaStream_t st;
+    PhaseScope(to_handle* h_, int phase_, cudaStream_t st_ = nullptr) : h(h_), phase(phase_), st(st_ ? st_ : h_->stream) {
         if (!h->timing) return;
         auto get = [&]() { cudaEvent_t e; if (!h->pool.empty()) { e = h->pool.back(); h->pool.pop_back(); } else cudaEventCreate(&e); return e; };
         a = get(); b = get();
-        cudaEventRecord(a, h->stream);
+        cudaEventRecord(a, st);
     }
     ~PhaseScope() {
         if (!h->timing) return;
-        cudaEventRecord(b, h->stream);
+        cudaEventRecord(b, st);
         h->pending.push_back({a, b, phase});
     }
 };
@@ -228,6 +232,16 @@ extern "C" {
 
 const char* to_last_error(const to_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
 
+// Every entry point that touches trajectory data on the main stream first joins the side stream (see to_ilqr_step).
+static int join_side(to_handle* h) {
+    if (h && h->side_pending) {
+        h->side_pending = false;
+        if (cudaStreamWaitEvent(h->stream, h->ev_join, 0) != cudaSuccess) return fail(h, TO_ECUDA, "cudaStreamWaitEvent");
+    }
+    return TO_OK;
+}
+#define JOIN(h) do { int jrc_ = join_side(h); if (jrc_) return jrc_; } while (0)
+
 int to_default_options(to_options* o) {
     if (!o) return TO_EINVAL;
     DevOptions d; set_default_options(d);
@@ -269,6 +283,14 @@ int to_create(const to_spec* s, to_handle** out) {
     if (cudaSetDevice(s->device) != cudaSuccess) { h->err = "cudaSetDevice failed"; return bail(TO_ECUDA); }
     if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { h->err = "cudaStreamCreate failed"; return bail(TO_ECUDA); }
     h->own_stream = true;
+    {
+        int lo = 0, hi = 0;
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);
+        if (const char* ev = getenv("TO_SIDE_PRIORITY")) { if (atoi(ev) == 0) hi = lo; }   // A/B switch (profiles/r01_notes.md)
+        if (cudaStreamCreateWithPriority(&h->stream2, cudaStreamNonBlocking, hi) != cudaSuccess ||
+            cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming) != cudaSuccess) { h->err = "side stream creation failed"; return bail(TO_ECUDA); }
+    }
     DevProblem& P = h->P;
     P.model = s->model; P.n = mn; P.m = mm; P.N = s->N; P.B = s->B;
     // row stride of [A B]: even (16-byte rows); 20 (= 4 mod 16) for the tensor-MMA Riccati path (n >= 8), see riccati.cu
@@ -324,7 +346,7 @@ int to_create(const to_spec* s, to_handle** out) {
     ALLOC(P.AB, (size_t)B * (N - 1) * n * P.ldab); ALLOC(P.K, (size_t)B * (N - 1) * n * m); ALLOC(P.d, (size_t)B * (N - 1) * m);
     ALLOC(P.lambda, (size_t)B * std::max(1, P.lambda_len));
     ALLOC(P.rho, B); ALLOC(P.drho, B); ALLOC(P.dV, 2 * (size_t)B); ALLOC(P.J, B); ALLOC(P.Jc, B); ALLOC(P.alpha, B);
-    ALLOC(P.bp_status, B); ALLOC(P.ls_iters, B); ALLOC(P.accepted, B);
+    ALLOC(P.bp_status, B); ALLOC(P.ls_iters, B); ALLOC(P.accepted, B); ALLOC(P.acc1, B);
     ALLOC(h->d_stageX, P.strideX); ALLOC(h->d_stageU, P.strideU); ALLOC(h->d_viol, B); ALLOC(h->d_merit2, 2);
     ALLOC(h->d_work, 1); ALLOC(h->d_err, 1);
 #undef ALLOC
@@ -351,6 +373,7 @@ int to_create(const to_spec* s, to_handle** out) {
     okc &= cudaMemsetAsync(P.bp_status, 0, sizeof(int) * B, st) == cudaSuccess;
     okc &= cudaMemsetAsync(P.ls_iters, 0, sizeof(int) * B, st) == cudaSuccess;
     okc &= cudaMemsetAsync(P.accepted, 0, sizeof(int) * B, st) == cudaSuccess;
+    okc &= cudaMemsetAsync(P.acc1, 0, sizeof(int) * B, st) == cudaSuccess;
     okc &= cudaMemsetAsync(h->d_err, 0, sizeof(int), st) == cudaSuccess;
     if (!okc) { h->err = std::string("device initialisation failed: ") + cudaGetErrorString(cudaGetLastError()); return bail(TO_ECUDA); }
     rc = upload_tables(h);
@@ -367,12 +390,16 @@ int to_destroy(to_handle* h) {
     if (h->scratch.ptr) cudaFree(h->scratch.ptr);
     for (auto& e : h->pending) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
     for (auto e : h->pool) cudaEventDestroy(e);
+    if (h->stream2) { cudaStreamSynchronize(h->stream2); cudaStreamDestroy(h->stream2); }
+    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+    if (h->ev_join) cudaEventDestroy(h->ev_join);
     if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
     delete h;
     return TO_OK;
 }
 
 int to_set_options(to_handle* h, const to_options* o) {
+    JOIN(h);
     if (!h || !o) return TO_EINVAL;
     if (o->iterations_linesearch < 0 || o->iterations_linesearch > 15) return fail(h, TO_EINVAL, "iterations_linesearch must be in 0..15");
     if (!(o->penalty_initial > 0) || !(o->penalty_scaling > 0)) return fail(h, TO_EINVAL, "penalties must be positive");
@@ -391,6 +418,7 @@ int to_set_options(to_handle* h, const to_options* o) {
 }
 
 int to_set_stream(to_handle* h, void* cuda_stream) {
+    JOIN(h);
     if (!h) return TO_EINVAL;
     CU(h, cudaStreamSynchronize(h->stream));
     if (h->own_stream) { cudaStreamDestroy(h->stream); h->own_stream = false; }
@@ -398,6 +426,7 @@ int to_set_stream(to_handle* h, void* cuda_stream) {
     return TO_OK;
 }
 int to_synchronize(to_handle* h) {
+    JOIN(h);
     if (!h) return TO_EINVAL;
     CU(h, cudaStreamSynchronize(h->stream));
     return TO_OK;
@@ -442,12 +471,14 @@ int to_bounds(const to_handle* h, int32_t con, double* lower, double* upper) {
 
 // ---- setters / getters ----------------------------------------------------------------------------------
 int to_set_initial_state(to_handle* h, const double* x0) {
+    JOIN(h);
     if (!h || !x0) return TO_EINVAL;
     CU(h, cudaMemcpyAsync(h->P.x0, x0, sizeof(double) * (size_t)h->P.B * h->P.n, cudaMemcpyHostToDevice, h->stream));
     h->J_valid = false;
     return TO_OK;
 }
 int to_set_controls(to_handle* h, const double* U) {
+    JOIN(h);
     if (!h || !U) return TO_EINVAL;
     CU(h, cudaMemcpyAsync(h->d_stageU, U, sizeof(double) * h->P.strideU, cudaMemcpyHostToDevice, h->stream));
     CU(h, launch_scatter_traj(h->P, nullptr, h->d_stageU, h->stream)); h->launches++;
@@ -455,6 +486,7 @@ int to_set_controls(to_handle* h, const double* U) {
     return TO_OK;
 }
 int to_set_states(to_handle* h, const double* X) {
+    JOIN(h);
     if (!h || !X) return TO_EINVAL;
     CU(h, cudaMemcpyAsync(h->d_stageX, X, sizeof(double) * h->P.strideX, cudaMemcpyHostToDevice, h->stream));
     CU(h, launch_scatter_traj(h->P, h->d_stageX, nullptr, h->stream)); h->launches++;
@@ -462,6 +494,7 @@ int to_set_states(to_handle* h, const double* X) {
     return TO_OK;
 }
 int to_get_states(to_handle* h, double* X) {
+    JOIN(h);
     if (!h || !X) return TO_EINVAL;
     CU(h, launch_gather_traj(h->P, h->d_stageX, nullptr, h->stream)); h->launches++;
     CU(h, cudaMemcpyAsync(X, h->d_stageX, sizeof(double) * h->P.strideX, cudaMemcpyDeviceToHost, h->stream));
@@ -469,6 +502,7 @@ int to_get_states(to_handle* h, double* X) {
     return TO_OK;
 }
 int to_get_controls(to_handle* h, double* U) {
+    JOIN(h);
     if (!h || !U) return TO_EINVAL;
     CU(h, launch_gather_traj(h->P, nullptr, h->d_stageU, h->stream)); h->launches++;
     CU(h, cudaMemcpyAsync(U, h->d_stageU, sizeof(double) * h->P.strideU, cudaMemcpyDeviceToHost, h->stream));
@@ -476,12 +510,14 @@ int to_get_controls(to_handle* h, double* U) {
     return TO_OK;
 }
 int to_get_times(to_handle* h, double* t) {
+    JOIN(h);
     if (!h || !t) return TO_EINVAL;
     t[0] = h->t0;
     for (int k = 1; k < h->P.N; k++) t[k] = t[k - 1] + h->h_dt[k - 1];
     return TO_OK;
 }
 int to_set_initial_time(to_handle* h, double t0, double* tf_out) {
+    JOIN(h);
     if (!h) return TO_EINVAL;
     h->t0 = t0;
     if (tf_out) { double t = t0; for (double d : h->h_dt) t += d; *tf_out = t; }
@@ -489,6 +525,7 @@ int to_set_initial_time(to_handle* h, double t0, double* tf_out) {
 }
 // set_goal_state! src/problem.jl:294-310 with set_LQR_goal! (q = -Q xf; c untouched) src/cost_functions.jl:245-248
 int to_set_goal_state(to_handle* h, const double* xf, int objective, int constraint) {
+    JOIN(h);
     if (!h || !xf) return TO_EINVAL;
     const int n = h->P.n;
     if (objective)
@@ -503,12 +540,14 @@ int to_set_goal_state(to_handle* h, const double* xf, int objective, int constra
 
 // ---- kernel 1 ---------------------------------------------------------------------------------------------
 int to_rollout(to_handle* h) {
+    JOIN(h);
     if (!h) return TO_EINVAL;
     CU(h, launch_rollout(h->P, h->stream)); h->launches++;
     h->J_valid = false; h->expanded = false; h->backward_done = false;
     return TO_OK;
 }
 int to_expand(to_handle* h) {
+    JOIN(h);
     if (!h) return TO_EINVAL;
     { PhaseScope ps(h, TO_PHASE_EXPAND); CU(h, launch_expand(h->P, h->stream)); }
     h->launches++; h->phase_launches[TO_PHASE_EXPAND]++;
@@ -516,6 +555,7 @@ int to_expand(to_handle* h) {
     return TO_OK;
 }
 int to_get_dynamics_jacobians(to_handle* h, double* AB) {
+    JOIN(h);
     if (!h || !AB) return TO_EINVAL;
     if (!h->expanded) return fail(h, TO_ESTATE, "to_get_dynamics_jacobians before to_expand");
     const size_t cnt = (size_t)h->P.B * (h->P.N - 1) * h->P.n * (h->P.n + h->P.m);
@@ -535,23 +575,28 @@ static int run_to_host(to_handle* h, size_t count, double* host, cudaError_t (*f
     return TO_OK;
 }
 int to_cost(to_handle* h, double* J) {
+    JOIN(h);
     if (!h || !J) return TO_EINVAL;
     return run_to_host(h, h->P.B, J, [](to_handle* hh, double* d) { return launch_cost(hh->P, d, nullptr, hh->stream); });
 }
 int to_cost_knots(to_handle* h, double* Jk) {
+    JOIN(h);
     if (!h || !Jk) return TO_EINVAL;
     return run_to_host(h, (size_t)h->P.B * h->P.N, Jk, [](to_handle* hh, double* d) { return launch_cost(hh->P, nullptr, d, hh->stream); });
 }
 int to_cost_gradient(to_handle* h, double* grad) {
+    JOIN(h);
     if (!h || !grad) return TO_EINVAL;
     return run_to_host(h, (size_t)h->P.B * h->P.N * (h->P.n + h->P.m), grad, [](to_handle* hh, double* d) { return launch_cost_gradient(hh->P, d, hh->stream); });
 }
 int to_cost_hessian(to_handle* h, double* hess) {
+    JOIN(h);
     if (!h || !hess) return TO_EINVAL;
     const int nm = h->P.n + h->P.m;
     return run_to_host(h, (size_t)h->P.B * h->P.N * nm * nm, hess, [](to_handle* hh, double* d) { return launch_cost_hessian(hh->P, d, hh->stream); });
 }
 int to_al_expansion(to_handle* h, double* grad, double* hess) {
+    JOIN(h);
     if (!h || !grad || !hess) return TO_EINVAL;
     const int nm = h->P.n + h->P.m;
     const size_t ng = (size_t)h->P.B * h->P.N * nm, nh = ng * nm;
@@ -564,6 +609,7 @@ int to_al_expansion(to_handle* h, double* grad, double* hess) {
     return TO_OK;
 }
 int to_eval_constraints(to_handle* h, int32_t con, double* vals) {
+    JOIN(h);
     if (!h || !vals) return TO_EINVAL;
     if (con < 0 || con >= (int)h->h_cons.size()) return fail(h, TO_EINVAL, "constraint index out of range");
     const DevCon& c = h->h_cons[con];
@@ -575,6 +621,7 @@ int to_eval_constraints(to_handle* h, int32_t con, double* vals) {
     return TO_OK;
 }
 int to_constraint_jacobians(to_handle* h, int32_t con, double* jac) {
+    JOIN(h);
     if (!h || !jac) return TO_EINVAL;
     if (con < 0 || con >= (int)h->h_cons.size()) return fail(h, TO_EINVAL, "constraint index out of range");
     const DevCon& c = h->h_cons[con];
@@ -592,6 +639,7 @@ static int ensure_merit(to_handle* h) {
     return TO_OK;
 }
 int to_merit(to_handle* h, double* J) {
+    JOIN(h);
     if (!h || !J) return TO_EINVAL;
     int rc = ensure_merit(h); if (rc) return rc;
     CU(h, cudaMemcpyAsync(J, h->P.J, sizeof(double) * h->P.B, cudaMemcpyDeviceToHost, h->stream));
@@ -599,6 +647,7 @@ int to_merit(to_handle* h, double* J) {
     return TO_OK;
 }
 int to_max_violation(to_handle* h, double* v) {
+    JOIN(h);
     if (!h || !v) return TO_EINVAL;
     CU(h, launch_merit(h->P, h->P.J, h->d_viol, h->stream)); h->launches++;
     h->J_valid = true;
@@ -657,6 +706,7 @@ static int do_forward(to_handle* h) {
     return TO_OK;
 }
 int to_backward(to_handle* h, int32_t* status) {
+    JOIN(h);
     if (!h) return TO_EINVAL;
     int rc = solver_supported(h); if (rc) return rc;
     if (!h->expanded) return fail(h, TO_ESTATE, "to_backward before to_expand");
@@ -668,6 +718,7 @@ int to_backward(to_handle* h, int32_t* status) {
     return TO_OK;
 }
 int to_forward(to_handle* h, double* J, double* alpha) {
+    JOIN(h);
     if (!h) return TO_EINVAL;
     int rc = solver_supported(h); if (rc) return rc;
     if (!h->backward_done) return fail(h, TO_ESTATE, "to_forward before to_backward");
@@ -681,15 +732,37 @@ int to_forward(to_handle* h, double* J, double* alpha) {
 int to_ilqr_step(to_handle* h, int32_t iters) {
     if (!h || iters < 0) return TO_EINVAL;
     int rc = solver_supported(h); if (rc) return rc;
+    if (!h->J_valid) JOIN(h);
     rc = ensure_merit(h); if (rc) return rc;
+    // Per iteration: E (expansion) -> R (Riccati) -> F pass 1 (alpha = 1..1/8, ~90% of the instances) -> F pass 2 (the rest).
+    // Pass 2 is latency-bound and touches few instances, so it runs on a high-priority side stream followed by the
+    // expansion of ITS instances, concurrently with the next iteration's expansion of the instances pass 1 accepted
+    // (instances never interact); the Riccati pass joins both. The overlap carries across calls (h->side_pending): any
+    // other entry point joins the side stream first.
     for (int it = 0; it < iters; it++) {
-        rc = to_expand(h); if (rc) return rc;
+        if (h->side_pending) {
+            CU(h, launch_expand(h->P, h->stream2, 2)); h->launches++;
+            CU(h, cudaEventRecord(h->ev_join, h->stream2));
+        }
+        { PhaseScope ps(h, TO_PHASE_EXPAND); CU(h, launch_expand(h->P, h->stream, h->side_pending ? 1 : 0)); }
+        h->launches++; h->phase_launches[TO_PHASE_EXPAND]++;
+        JOIN(h);
+        h->expanded = true;
         rc = do_backward(h); if (rc) return rc;
-        rc = do_forward(h); if (rc) return rc;
+        { PhaseScope ps(h, TO_PHASE_FORWARD); CU(h, launch_forward(h->P, h->stream)); }
+        h->launches++; h->phase_launches[TO_PHASE_FORWARD]++;
+        CU(h, cudaEventRecord(h->ev_fork, h->stream));
+        CU(h, cudaStreamWaitEvent(h->stream2, h->ev_fork, 0));
+        { PhaseScope ps(h, TO_PHASE_LADDER, h->stream2); CU(h, launch_ladder(h->P, h->stream2)); }
+        h->launches++; h->phase_launches[TO_PHASE_LADDER]++;
+        CU(h, cudaEventRecord(h->ev_join, h->stream2));
+        h->side_pending = true;
+        h->expanded = false; h->backward_done = false;   // the trajectory moved
     }
     return TO_OK;
 }
 int to_al_update(to_handle* h) {
+    JOIN(h);
     if (!h) return TO_EINVAL;
     if (h->P.ncon > 0) { CU(h, launch_al_update(h->P, h->stream)); h->launches++; }
     for (auto& mu : h->h_mu) mu = std::fmin(mu * h->P.opt.penalty_scaling, h->P.opt.penalty_max);
@@ -699,6 +772,7 @@ int to_al_update(to_handle* h) {
     return TO_OK;
 }
 int to_get_gains(to_handle* h, double* K, double* d) {
+    JOIN(h);
     if (!h) return TO_EINVAL;
     if (K) CU(h, cudaMemcpyAsync(K, h->P.K, sizeof(double) * (size_t)h->P.B * (h->P.N - 1) * h->P.n * h->P.m, cudaMemcpyDeviceToHost, h->stream));
     if (d) CU(h, cudaMemcpyAsync(d, h->P.d, sizeof(double) * (size_t)h->P.B * (h->P.N - 1) * h->P.m, cudaMemcpyDeviceToHost, h->stream));
@@ -706,6 +780,7 @@ int to_get_gains(to_handle* h, double* K, double* d) {
     return TO_OK;
 }
 static int multipliers_copy(to_handle* h, int32_t con, double* host, bool to_host) {
+    JOIN(h);
     if (!h || !host) return TO_EINVAL;
     if (con < 0 || con >= (int)h->h_cons.size()) return fail(h, TO_EINVAL, "constraint index out of range");
     const DevCon& c = h->h_cons[con];
@@ -722,11 +797,13 @@ static int multipliers_copy(to_handle* h, int32_t con, double* host, bool to_hos
 int to_get_multipliers(to_handle* h, int32_t con, double* lambda) { return multipliers_copy(h, con, lambda, true); }
 int to_set_multipliers(to_handle* h, int32_t con, const double* lambda) { return multipliers_copy(h, con, const_cast<double*>(lambda), false); }
 int to_get_penalty(to_handle* h, int32_t con, double* mu) {
+    JOIN(h);
     if (!h || !mu || con < 0 || con >= (int)h->h_mu.size()) return TO_EINVAL;
     *mu = h->h_mu[con];
     return TO_OK;
 }
 int to_set_penalty(to_handle* h, int32_t con, double mu) {
+    JOIN(h);
     if (!h || con < 0 || con >= (int)h->h_mu.size() || !(mu > 0)) return TO_EINVAL;
     h->h_mu[con] = mu;
     CU(h, cudaMemcpyAsync(h->d_mu, h->h_mu.data(), sizeof(double) * h->h_mu.size(), cudaMemcpyHostToDevice, h->stream));
@@ -735,6 +812,7 @@ int to_set_penalty(to_handle* h, int32_t con, double mu) {
     return TO_OK;
 }
 int to_get_solver_state(to_handle* h, double* rho, double* dV, double* alpha, int32_t* ls_iters, int32_t* bp_status) {
+    JOIN(h);
     if (!h) return TO_EINVAL;
     const int B = h->P.B;
     if (rho) CU(h, cudaMemcpyAsync(rho, h->P.rho, sizeof(double) * B, cudaMemcpyDeviceToHost, h->stream));
@@ -748,12 +826,14 @@ int to_get_solver_state(to_handle* h, double* rho, double* dV, double* alpha, in
 
 // ---- multi-GPU / measurement plumbing -----------------------------------------------------------------------
 int to_reduce_merit(to_handle* h) {
+    JOIN(h);
     if (!h) return TO_EINVAL;
     int rc = ensure_merit(h); if (rc) return rc;      // J and viol are kept current by the line search; recomputed only after edits
     CU(h, launch_reduce_merit(h->P, h->d_viol, h->d_merit2, h->stream)); h->launches++;
     return TO_OK;
 }
 int to_merit_device_ptr(to_handle* h, void** ptr) {
+    JOIN(h);
     if (!h || !ptr) return TO_EINVAL;
     *ptr = h->d_merit2;
     return TO_OK;

@@ -97,6 +97,7 @@ struct DevProblem {
     int* bp_status;           // [B]
     int* ls_iters;            // [B]
     int* accepted;            // [B]
+    int* acc1;                // [B] accepted by the first line-search pass (read by the overlapped expansion)
     size_t strideX, strideU;  // elements between the two trajectory buffers
 };
 

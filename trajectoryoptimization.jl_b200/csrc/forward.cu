@@ -1,3 +1,4 @@
+#include <cstdlib>
 // forward.cu -- the forward pass of iLQR: closed-loop RK4 rollout fused with the cost + constraint + AL-penalty
 // sweep (kernel 1 without partials + kernel 2), and the per-instance backtracking line search.
 //
@@ -403,6 +404,7 @@ __global__ void __launch_bounds__(FWD_THREADS) k_linesearch(const DevProblem P, 
             accepted = true;
         }
     }
+    if (l == 0 && first_pass) P.acc1[b] = accepted ? 1 : 0;
     if (l == 0 && !accepted) {
         if (first_pass) P.accepted[b] = 0;
         if (status < 0) { P.alpha[b] = 0.0; P.ls_iters[b] = 0; }
@@ -428,6 +430,13 @@ cudaError_t launch_pass(const DevProblem& P, int trial0, int first_pass, int fin
     if (!configured && smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
+    }
+    if (!configured) {
+        const char* ev = getenv("TO_CARVEOUT");
+        if (!ev || atoi(ev) != 0) {
+            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
+            if (e != cudaSuccess) return e;
+        }
     }
     configured = true;
     kern<<<blocks, FWD_THREADS, smem, s>>>(P, trial0, first_pass, final_pass);

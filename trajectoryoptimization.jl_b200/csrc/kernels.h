@@ -4,7 +4,7 @@
 
 // kernel 1: batched RK4 rollout / dual-number dynamics expansion           (rollout.cu)
 cudaError_t launch_rollout(const DevProblem& P, cudaStream_t s);
-cudaError_t launch_expand(const DevProblem& P, cudaStream_t s);
+cudaError_t launch_expand(const DevProblem& P, cudaStream_t s, int mode = 0);   // mode 1 / 2: only instances with acc1 == 1 / == 0
 // kernel 2: cost + constraint + AL sweep                                     (sweep.cu)
 cudaError_t launch_cost(const DevProblem& P, double* J, double* Jk, cudaStream_t s);
 cudaError_t launch_merit(const DevProblem& P, double* J, double* viol, cudaStream_t s);

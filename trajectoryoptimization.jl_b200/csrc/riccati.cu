@@ -107,20 +107,26 @@ struct RiccatiSmem {
     double Qs[(NM + 1) * LDQS];
     double K[4 * LDK + 8];
     double W[4 * LDK + 8];
-    double g[even_up(NM) + 2];   // lz (cost + AL gradient), padded
-    double h[even_up(NM) + 2];   // diag(lzz)
+    double g[MMA ? 2 : even_up(NM) + 2];   // lz (cost + AL gradient), padded (DFMA path; the MMA path keeps it in lane registers)
+    double h[MMA ? 2 : even_up(NM) + 2];   // diag(lzz)
+    // lane-indexed table of the Goal / Bound rows acting on z_lane (instance-independent, filled once per warp):
+    // keeping it here instead of in registers is what lets the knot loop fit 128 registers without spills
+    static constexpr int NMT = even_up(NM);
+    double tnms[MAXT][NMT];      // -mu * sign  (sign = +1: c = z - bound, -1: c = bound - z ; mu = |.|)
+    double tbound[MAXT][NMT];
+    uint2 tpk[MAXT][NMT];        // x = first | last << 16 (1-based knot range), y = lambda index of the row at knot `first` | p << 23 | eq << 31
     // scratch of the general-constraint AL expansion (Linear / Circle / Sphere / Norm incl. SOC), DFMA path only
     static constexpr int GP = MMA ? 1 : 16;         // rows of one general constraint handled by the solver kernels
     double gc[GP], glbar[GP], glp[GP], gD[GP * GP], gjac[GP * (MMA ? 1 : TO_MAXNM)], gtmp[GP * (MMA ? 1 : TO_MAXNM)];
     uint64_t bar[STAGES];
 };
 
-// one AL term acting on z_i:  c = sign * (z_i - bound) ;  Goal: equality (always active), Bound: inequality
-struct ALTerm {
-    int first, last, p, base;   // knot range (1-based), rows per knot, lambda index of the row at knot `first`
-    double sign, bound, mu;
-    bool eq;
-};
+// one AL term acting on z_i:  c = sign * (z_i - bound) ;  Goal: equality (always active), Bound: inequality.
+// Packed into RiccatiSmem::tnms / tbound / tpk; the packing limits (N < 65536, lambda_len < 2^23, p < 256) are checked
+// by launch_riccati_nm, which otherwise takes the generic (FASTAL = false) expansion.
+__device__ __forceinline__ uint2 pack_term(int first, int last, int base, int p, bool eq) {
+    return make_uint2((unsigned)first | ((unsigned)last << 16), (unsigned)base | ((unsigned)p << 23) | (eq ? 0x80000000u : 0u));
+}
 
 template <int N_, int M_, int STAGES, bool FASTAL, bool MMA, int MINB>
 __global__ void __launch_bounds__(32, MINB) k_riccati(const DevProblem P, int* __restrict__ work_counter) {
@@ -173,12 +179,13 @@ __global__ void __launch_bounds__(32, MINB) k_riccati(const DevProblem P, int* _
     }
 
     // ---- lane-resident AL terms of z_lane (Goal / Bound constraints) ----------------------------------------
-    ALTerm term[MAXT];
-    int nterm = 0;
     if (FASTAL) {
+        if (lane < SM::NMT) {
 #pragma unroll
-        for (int t = 0; t < MAXT; t++) { term[t].first = 1; term[t].last = 0; term[t].p = 0; term[t].base = 0; term[t].sign = 0; term[t].bound = 0; term[t].mu = 1; term[t].eq = false; }
+            for (int t = 0; t < MAXT; t++) { sm.tnms[t][lane] = -1.0; sm.tbound[t][lane] = 0.0; sm.tpk[t][lane] = pack_term(1, 0, 0, 0, false); }   // empty range
+        }
         if (lane < NM) {
+            int nterm = 0;
             for (int ci = 0; ci < P.ncon; ci++) {
                 const DevCon& con = P.cons[ci];
                 const double mu = P.mu[ci];
@@ -188,10 +195,7 @@ __global__ void __launch_bounds__(32, MINB) k_riccati(const DevProblem P, int* _
                     else if (side == 0) { row = con.row_max[lane]; bound = con.a[lane]; }
                     else { row = con.row_min[lane]; bound = con.b[lane]; sign = -1.0; }
                     if (row < 0) continue;
-#pragma unroll
-                    for (int t = 0; t < MAXT; t++)
-                        if (t == nterm) { term[t].first = con.first; term[t].last = con.last; term[t].p = con.p; term[t].base = con.offset + row;
-                                          term[t].sign = sign; term[t].bound = bound; term[t].mu = mu; term[t].eq = eq; }
+                    if (nterm < MAXT) { sm.tnms[nterm][lane] = -mu * sign; sm.tbound[nterm][lane] = bound; sm.tpk[nterm][lane] = pack_term(con.first, con.last, con.offset + row, con.p, eq); }
                     nterm++;
                 }
             }
@@ -237,9 +241,11 @@ __global__ void __launch_bounds__(32, MINB) k_riccati(const DevProblem P, int* _
             gi = fma(cH, zi, cG); hi = cH;
 #pragma unroll
             for (int t = 0; t < MAXT; t++) {
-                if (k + 1 >= term[t].first && k + 1 <= term[t].last) {
-                    const double lb = fma(-term[t].mu * term[t].sign, zi - term[t].bound, lam[t]);   // lambda - mu c
-                    if (term[t].eq || lb <= 0.0) { gi = fma(-term[t].sign, lb, gi); hi += term[t].mu; }
+                const uint2 pk = sm.tpk[t][lane];
+                if ((unsigned)(k + 1) >= (pk.x & 0xffffu) && (unsigned)(k + 1) <= (pk.x >> 16)) {
+                    const double nms = sm.tnms[t][lane];
+                    const double lb = fma(nms, zi - sm.tbound[t][lane], lam[t]);   // lambda - mu c
+                    if ((pk.y >> 31) || lb <= 0.0) { gi += (nms < 0.0) ? -lb : lb; hi += fabs(nms); }   // g -= sign lb ; h += mu
                 }
             }
         };
@@ -247,7 +253,10 @@ __global__ void __launch_bounds__(32, MINB) k_riccati(const DevProblem P, int* _
 #pragma unroll
             for (int t = 0; t < MAXT; t++) {
                 lam[t] = 0.0;
-                if (k + 1 >= term[t].first && k + 1 <= term[t].last) lam[t] = ldg_pinned(lam_b + term[t].base + (size_t)(k + 1 - term[t].first) * term[t].p);
+                const uint2 pk = sm.tpk[t][lane];
+                const unsigned first = pk.x & 0xffffu;
+                if ((unsigned)(k + 1) >= first && (unsigned)(k + 1) <= (pk.x >> 16))
+                    lam[t] = ldg_pinned(lam_b + (pk.y & 0x7fffffu) + (size_t)((unsigned)(k + 1) - first) * ((pk.y >> 23) & 0xffu));
             }
         };
 
@@ -922,7 +931,7 @@ cudaError_t launch_riccati_t(const DevProblem& P, int* work_counter, cudaStream_
 template <int N_, int M_>
 cudaError_t launch_riccati_nm(const DevProblem& P, int* work_counter, cudaStream_t s) {
     // the lane-resident AL terms hold at most MAXT rows per z entry (upper + lower bound + goal)
-    if (P.max_terms_per_z <= MAXT) return launch_riccati_t<N_, M_, true>(P, work_counter, s);
+    if (P.max_terms_per_z <= MAXT && P.N < 65536 && P.lambda_len < (1 << 23) && P.max_p_knot < 256) return launch_riccati_t<N_, M_, true>(P, work_counter, s);
     return launch_riccati_t<N_, M_, false>(P, work_counter, s);
 }
 

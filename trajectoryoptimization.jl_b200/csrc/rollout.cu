@@ -34,7 +34,7 @@ __global__ void __launch_bounds__(64) k_rollout(const DevProblem P) {
 }
 
 template <int MODEL, int NP>
-__global__ void __launch_bounds__(128) k_expand(const DevProblem P) {
+__global__ void __launch_bounds__(128) k_expand(const DevProblem P, int mode) {
     constexpr int n = ModelDims<MODEL>::n, m = ModelDims<MODEL>::m, nm = n + m;
     constexpr int TPK = (nm + NP - 1) / NP;        // threads per knot: each carries NP seed directions
     using D = Dual<NP>;
@@ -46,6 +46,7 @@ __global__ void __launch_bounds__(128) k_expand(const DevProblem P) {
     const long long bk = t / TPK;
     const int k = (int)(bk % (P.N - 1));
     const int b = (int)(bk / (P.N - 1));
+    if (mode != 0 && (P.acc1[b] != 0) != (mode == 1)) return;     // overlapped expansion: this launch covers the other group
     double* AB = P.AB + ((size_t)b * (P.N - 1) + k) * n * ld;     // pad columns nm..ld-1 stay zero from to_create
     const double* X = traj_X(P, P.cur[b], b) + (size_t)k * n;
     const double* U = traj_U(P, P.cur[b], b) + (size_t)k * m;
@@ -80,21 +81,32 @@ cudaError_t launch_rollout(const DevProblem& P, cudaStream_t s) {
 }
 
 template <int MODEL, int NP>
-static cudaError_t launch_expand_t(const DevProblem& P, cudaStream_t s) {
+static cudaError_t launch_expand_t(const DevProblem& P, cudaStream_t s, int mode) {
     constexpr int nm = ModelDims<MODEL>::n + ModelDims<MODEL>::m;
     constexpr int TPK = (nm + NP - 1) / NP;
     const long long total = (long long)P.B * (P.N - 1) * TPK;
     const int threads = 128;
-    k_expand<MODEL, NP><<<(unsigned)((total + threads - 1) / threads), threads, 0, s>>>(P);
+    // Same shared-memory carve-out as the line-search / Riccati kernels it runs next to (capi.cu, to_ilqr_step): an SM
+    // only reconfigures its L1/shared split when idle, so mixed preferences serialise the overlapped kernels.
+    static bool configured = false;
+    if (!configured) {
+        const char* ev = getenv("TO_CARVEOUT");
+        if (!ev || atoi(ev) != 0) {
+            cudaError_t e = cudaFuncSetAttribute(k_expand<MODEL, NP>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
+            if (e != cudaSuccess) return e;
+        }
+        configured = true;
+    }
+    k_expand<MODEL, NP><<<(unsigned)((total + threads - 1) / threads), threads, 0, s>>>(P, mode);
     return cudaGetLastError();
 }
 
-cudaError_t launch_expand(const DevProblem& P, cudaStream_t s) {
+cudaError_t launch_expand(const DevProblem& P, cudaStream_t s, int mode) {
     // seeds per thread: 1 (value recomputed per seed) or 2 (value shared by two seeds, more registers); profiles/r01_notes.md
     static int np = -1;
     if (np < 0) { const char* v = getenv("TO_EXPAND_SEEDS"); np = v ? atoi(v) : 1; }
     cudaError_t e = cudaErrorNotSupported;
-    if (np == 2) { TO_DISPATCH_MODEL(P.model, P.m, (e = launch_expand_t<MODEL, 2>(P, s))); }
-    else { TO_DISPATCH_MODEL(P.model, P.m, (e = launch_expand_t<MODEL, 1>(P, s))); }
+    if (np == 2) { TO_DISPATCH_MODEL(P.model, P.m, (e = launch_expand_t<MODEL, 2>(P, s, mode))); }
+    else { TO_DISPATCH_MODEL(P.model, P.m, (e = launch_expand_t<MODEL, 1>(P, s, mode))); }
     return e;
 }

@@ -1,40 +1,49 @@
 #!/usr/bin/env python3
-"""Attribute ncu stall samples / executed instructions of one kernel to CUDA source lines.
-usage: ncu_lines.py report.ncu-rep cubin kernel_substring [top]
-Joins the SASS source page of the report with `nvdisasm -g` line info by instruction order."""
-import collections, csv, io, re, subprocess, sys
-rep, cubin, kname = sys.argv[1:4]
-top = int(sys.argv[4]) if len(sys.argv) > 4 else 25
-dis = subprocess.run(["nvdisasm", "-g", cubin], capture_output=True, text=True).stdout
-# split per function
-cur, line, insts, infn = None, None, [], False
-for l in dis.splitlines():
-    m = re.match(r"\s*\.text\.(\S+):", l)
-    if m:
-        infn = kname in m.group(1); continue
-    if not infn: continue
-    m = re.search(r'//## File ".*?([^/"]+)", line (\d+)', l)
-    if m: line = (m.group(1), int(m.group(2))); continue
-    m = re.match(r"\s*/\*([0-9a-f]{4,})\*/\s+(.*?);", l)
-    if m: insts.append((int(m.group(1), 16), line, m.group(2)))
+"""Per-source-line hot spots of one kernel: joins the SASS view of an .ncu-rep (samples / executed per instruction)
+with `nvdisasm -g` line info of the same cubin (matched by instruction order).
+usage: ncu_lines.py report.ncu-rep object.o|lib.so kernel_substring [block_index] [units]"""
+import collections, csv, io, os, re, subprocess, sys, tempfile
+rep, obj, kern = sys.argv[1], os.path.abspath(sys.argv[2]), sys.argv[3]
+which = int(sys.argv[4]) if len(sys.argv) > 4 else 0
+units = float(sys.argv[5]) if len(sys.argv) > 5 else 1.0
 src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(src)))
-start = next(i for i, r in enumerate(rows) if r and r[0] == "Address")
+start = [i for i, r in enumerate(rows) if r and r[0] == "Address"][which]
 hdr = rows[start]; idx = {h: i for i, h in enumerate(hdr)}
 data = []
 for r in rows[start + 1:]:
     if not r or r[0] in ("Address", "Kernel Name"): break
     data.append(r)
-assert len(data) == len(insts), (len(data), len(insts))
-samp = collections.Counter(); ins = collections.Counter()
-for r, (off, ln, txt) in zip(data, insts):
-    samp[ln] += int(r[idx['# Samples']]); ins[ln] += int(r[idx['Instructions Executed']])
-tot = sum(samp.values()); toti = sum(ins.values())
-print(f"total samples {tot}, warp-instructions {toti}")
-srcs = {}
-for (f, n), c in samp.most_common(top):
-    if f not in srcs:
-        try: srcs[f] = open(f"/root/repo/trajectoryoptimization.jl_b200/csrc/{f}").read().splitlines()
-        except Exception: srcs[f] = []
-    text = srcs[f][n - 1].strip()[:110] if 0 < n <= len(srcs[f]) else ""
-    print(f"{100*c/tot:5.1f}% samp {100*ins[(f,n)]/toti:5.1f}% inst  {f}:{n}  {text}")
+tmp = tempfile.mkdtemp()
+subprocess.run(["cuobjdump", "-xelf", "all", obj], cwd=tmp, capture_output=True)
+lines = []
+for f in os.listdir(tmp):
+    if f.endswith(".cubin"):
+        out = subprocess.run(["nvdisasm", "-g", "-c", os.path.join(tmp, f)], capture_output=True, text=True).stdout.splitlines()
+        inside = False; cur = None
+        for l in out:
+            if l.startswith("//---") and ".text." in l: inside = kern in l; cur = None; continue
+            if not inside: continue
+            m = re.search(r'//## File ".*?([^/"]+)", line (\d+)', l)
+            if m: cur = (m.group(1), int(m.group(2))); continue
+            if re.match(r"\s+/\*[0-9a-f]{4,}\*/", l): lines.append(cur)
+        if lines: break
+print(f"SASS instructions: ncu {len(data)}  nvdisasm {len(lines)}")
+n = min(len(data), len(lines))
+tot = sum(int(r[idx['# Samples']]) for r in data)
+agg = collections.defaultdict(lambda: [0, 0, collections.Counter()])
+stalls = [h for h in hdr if h.startswith('stall_') and 'Not Issued' not in h]
+for i in range(n):
+    a = agg[lines[i]]
+    a[0] += int(data[i][idx['# Samples']]); a[1] += int(data[i][idx['Instructions Executed']])
+    for h in stalls: a[2][h[6:]] += int(data[i][idx[h]])
+srcfile = {}
+print(f"total samples {tot}")
+for key, (s, ex, st) in sorted(agg.items(), key=lambda kv: -kv[1][0])[:45]:
+    text = ""
+    if key:
+        path = os.path.join(os.path.dirname(obj), "..", key[0]) if not os.path.exists(key[0]) else key[0]
+        for cand in (path, os.path.join(os.path.dirname(obj), key[0]), os.path.join(os.path.dirname(os.path.dirname(obj)), "csrc", key[0])):
+            if os.path.exists(cand):
+                srcfile.setdefault(cand, open(cand).read().splitlines()); text = srcfile[cand][key[1] - 1].strip()[:90]; break
+    print(f"{100 * s / tot:5.1f}%  {ex / units:7.1f} inst  {key}  {[(k, round(100 * v / max(s, 1))) for k, v in st.most_common(2)]}  {text}")

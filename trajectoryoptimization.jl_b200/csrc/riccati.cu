@@ -72,6 +72,23 @@ __device__ __forceinline__ double ldg_pinned(const double* p) {
     return v;
 }
 
+__device__ __forceinline__ int ldg_pinned(const int* p) {
+    int v;
+    asm volatile("ld.global.nc.s32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+
+// 1/x for a positive finite pivot: hardware seed (MUFU.RCP64H, >= 20 bits) + two Newton steps -> <= 1 ulp, without
+// the rounding / special-case fix-up of __drcp_rn (12 dependent instructions + a branch on the knot's critical chain)
+__device__ __forceinline__ double rcp_pivot(double x) {
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    double e = fma(-x, y, 1.0);
+    y = fma(y, e, y);
+    e = fma(-x, y, 1.0);
+    return fma(y, e, y);
+}
+
 // 2x2 micro-block outer-product accumulate
 __device__ __forceinline__ void fma2x2(double (&acc)[4], const double2& a, const double2& b) {
     acc[0] = fma(a.x, b.x, acc[0]);
@@ -390,7 +407,7 @@ __global__ void __launch_bounds__(32, MINB) k_riccati(const DevProblem P, int* _
                 int cid_next2 = 0;
                 if (FASTAL && P.all_diag_cost && k > 0) {
                     cH_nxt = ldg_pinned(cost_coeff_ptr(cid_next, true)); cG_nxt = ldg_pinned(cost_coeff_ptr(cid_next, false));
-                    if (k > 1) cid_next2 = P.cost_index[k - 2];
+                    if (k > 1) cid_next2 = ldg_pinned(P.cost_index + (k - 2));
                 }
                 // ---- cost + AL expansion of knot k: lane i < NM handles z_i (diagonal terms) ------------
                 double g_reg = 0.0, h_reg = 0.0;
@@ -570,7 +587,7 @@ __global__ void __launch_bounds__(32, MINB) k_riccati(const DevProblem P, int* _
                             for (int r = 0; r < j; r++) t = fma(-Lf[j * (j + 1) / 2 + r] * Lf[j * (j + 1) / 2 + r], dj[r], t);
                             if (!(t > 0.0) || !isfinite(t)) okl = false;
                             dj[j] = t;
-                            const double inv = __drcp_rn(t);
+                            const double inv = rcp_pivot(t);
                             Lf[j * (j + 1) / 2 + j] = inv;
 #pragma unroll
                             for (int i = j + 1; i < m; i++) {
@@ -745,7 +762,7 @@ __global__ void __launch_bounds__(32, MINB) k_riccati(const DevProblem P, int* _
                             for (int r = 0; r < j; r++) t = fma(-Lf[j * (j + 1) / 2 + r] * Lf[j * (j + 1) / 2 + r], dj[r], t);
                             if (!(t > 0.0) || !isfinite(t)) ok = false;
                             dj[j] = t;
-                            const double inv = __drcp_rn(t);
+                            const double inv = rcp_pivot(t);
                             Lf[j * (j + 1) / 2 + j] = inv;
     #pragma unroll
                             for (int i = j + 1; i < m; i++) {

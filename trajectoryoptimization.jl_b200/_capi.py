@@ -14,7 +14,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libtrajopt_b200.so")
+# LIBTRAJOPT_B200 overrides the in-tree path (profiles/build_variants.sh uses it for A/B kernel builds)
+LIB_PATH = os.environ.get("LIBTRAJOPT_B200") or os.path.join(_HERE, "libtrajopt_b200.so")
 
 # error codes (include/trajopt_b200.h)
 TO_OK, TO_EINVAL, TO_EDIM, TO_ECUDA, TO_ENOMEM, TO_ESTATE, TO_ECONE = 0, -1, -2, -3, -4, -5, -6

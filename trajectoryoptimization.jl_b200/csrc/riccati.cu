@@ -29,6 +29,7 @@
 //     NEXT knot are prefetched while the current knot's products run (global latency off the critical path).
 //   * Quu + rho I is m x m (m <= 8): LDL' with reciprocal pivots (no fp64 sqrt / division chain) and the triangular
 //     solves are done per right-hand-side column, one lane per column of [Qux Qu], in registers.
+#include <cstddef>
 #include <cstdlib>
 
 #include "costcon.cuh"
@@ -131,7 +132,7 @@ struct RiccatiSmem {
     static constexpr int NMT = even_up(NM);
     double tnms[MAXT][NMT];      // -mu * sign  (sign = +1: c = z - bound, -1: c = bound - z ; mu = |.|)
     double tbound[MAXT][NMT];
-    uint2 tpk[MAXT][NMT];        // x = first | last << 16 (1-based knot range), y = lambda index of the row at knot `first` | p << 23 | eq << 31
+    uint2 tpk[MAXT][NMT];        // see pack_term
     // scratch of the general-constraint AL expansion (Linear / Circle / Sphere / Norm incl. SOC), DFMA path only
     static constexpr int GP = MMA ? 1 : 16;         // rows of one general constraint handled by the solver kernels
     double gc[GP], glbar[GP], glp[GP], gD[GP * GP], gjac[GP * (MMA ? 1 : TO_MAXNM)], gtmp[GP * (MMA ? 1 : TO_MAXNM)];
@@ -139,13 +140,16 @@ struct RiccatiSmem {
 };
 
 // one AL term acting on z_i:  c = sign * (z_i - bound) ;  Goal: equality (always active), Bound: inequality.
-// Packed into RiccatiSmem::tnms / tbound / tpk; the packing limits (N < 65536, lambda_len < 2^23, p < 256) are checked
+// Packed into RiccatiSmem::tnms / tbound / tpk; the packing limits (N < 4095, p < 128) are checked
 // by launch_riccati_nm, which otherwise takes the generic (FASTAL = false) expansion.
 __device__ __forceinline__ uint2 pack_term(int first, int last, int base, int p, bool eq) {
-    return make_uint2((unsigned)first | ((unsigned)last << 16), (unsigned)base | ((unsigned)p << 23) | (eq ? 0x80000000u : 0u));
+    // x = first (12 bits) | last - first (12) | p (7) | eq (1) ;  y = lambda index of the row at knot 0 (= base - first p)
+    const int span = last >= first ? last - first : 0;
+    const int f = last >= first ? first : 4095;              // empty range: never active for knots <= 4094
+    return make_uint2((unsigned)f | ((unsigned)span << 12) | ((unsigned)p << 24) | (eq ? 0x80000000u : 0u), (unsigned)(base - f * p));
 }
 
-template <int N_, int M_, int STAGES, bool FASTAL, bool MMA, int MINB>
+template <int N_, int M_, int STAGES, bool FASTAL, bool MMA, int MINB, int NSLOT>
 __global__ void __launch_bounds__(32, MINB) k_riccati(const DevProblem P, int* __restrict__ work_counter) {
     using SM = RiccatiSmem<N_, M_, STAGES, MMA>;
     constexpr int n = N_, m = M_, NM = SM::NM, LDAB = SM::LDAB, LDT = SM::LDT, NP = SM::NP, LDK = SM::LDK;
@@ -201,8 +205,8 @@ __global__ void __launch_bounds__(32, MINB) k_riccati(const DevProblem P, int* _
 #pragma unroll
             for (int t = 0; t < MAXT; t++) { sm.tnms[t][lane] = -1.0; sm.tbound[t][lane] = 0.0; sm.tpk[t][lane] = pack_term(1, 0, 0, 0, false); }   // empty range
         }
+        int nterm = 0;
         if (lane < NM) {
-            int nterm = 0;
             for (int ci = 0; ci < P.ncon; ci++) {
                 const DevCon& con = P.cons[ci];
                 const double mu = P.mu[ci];
@@ -217,6 +221,7 @@ __global__ void __launch_bounds__(32, MINB) k_riccati(const DevProblem P, int* _
                 }
             }
         }
+        (void)nterm;   // NSLOT (template) >= the largest per-lane count: launch_riccati_nm picks it from P.max_terms_per_z
     }
 
     for (int e = lane; e < 4 * LDK + 8; e += 32) { sm.K[e] = 0.0; sm.W[e] = 0.0; }   // padding columns stay finite
@@ -250,30 +255,37 @@ __global__ void __launch_bounds__(32, MINB) k_riccati(const DevProblem P, int* _
 
         // the expansion of one knot for this lane: (gi, hi) = (lz_i, lzz_ii) from z_i and its multipliers
         // (cH, cG) = (Qd_i | Rd_i, q_i | r_i) of this lane's z_i for a DiagonalCost
+        // DevCost keeps Qd | Rd | q | r contiguous, so q_i - Qd_i == r_a - Rd_a: one per-lane offset serves H and G
+        const int coff = (lane < n) ? (int)offsetof(DevCost, Qd) + 8 * lane : (int)offsetof(DevCost, Rd) + 8 * (lane < NM ? lane - n : 0);
+        constexpr int GOFF = (int)(offsetof(DevCost, q) - offsetof(DevCost, Qd));
+        static_assert(offsetof(DevCost, r) - offsetof(DevCost, Rd) == offsetof(DevCost, q) - offsetof(DevCost, Qd), "DevCost layout");
         auto cost_coeff_ptr = [&](int cid, bool hess) -> const double* {
-            const DevCost& c = P.costs[cid];
-            return (lane < n) ? (hess ? &c.Qd[lane] : &c.q[lane]) : (hess ? &c.Rd[lane < NM ? lane - n : 0] : &c.r[lane < NM ? lane - n : 0]);
+            return reinterpret_cast<const double*>(reinterpret_cast<const char*>(P.costs) + (size_t)cid * sizeof(DevCost) + coff + (hess ? 0 : GOFF));
         };
-        auto expand_fast = [&](int k, double zi, const double (&lam)[MAXT], double cH, double cG, double& gi, double& hi) {
+        // act: bit t = term slot t is active at the knot, bit 4 + t = it is an equality (computed by load_lams one knot ahead)
+        auto expand_fast = [&](double zi, const double (&lam)[MAXT], int act, double cH, double cG, double& gi, double& hi) {
             gi = fma(cH, zi, cG); hi = cH;
 #pragma unroll
             for (int t = 0; t < MAXT; t++) {
-                const uint2 pk = sm.tpk[t][lane];
-                if ((unsigned)(k + 1) >= (pk.x & 0xffffu) && (unsigned)(k + 1) <= (pk.x >> 16)) {
+                if (t < NSLOT && (act & (1 << t))) {
                     const double nms = sm.tnms[t][lane];
                     const double lb = fma(nms, zi - sm.tbound[t][lane], lam[t]);   // lambda - mu c
-                    if ((pk.y >> 31) || lb <= 0.0) { gi += (nms < 0.0) ? -lb : lb; hi += fabs(nms); }   // g -= sign lb ; h += mu
+                    if ((act & (16 << t)) || lb <= 0.0) { gi += (nms < 0.0) ? -lb : lb; hi += fabs(nms); }   // g -= sign lb ; h += mu
                 }
             }
         };
-        auto load_lams = [&](int k, double (&lam)[MAXT]) {
+        auto load_lams = [&](int k, double (&lam)[MAXT], int& act) {
+            act = 0;
 #pragma unroll
             for (int t = 0; t < MAXT; t++) {
                 lam[t] = 0.0;
-                const uint2 pk = sm.tpk[t][lane];
-                const unsigned first = pk.x & 0xffffu;
-                if ((unsigned)(k + 1) >= first && (unsigned)(k + 1) <= (pk.x >> 16))
-                    lam[t] = ldg_pinned(lam_b + (pk.y & 0x7fffffu) + (size_t)((unsigned)(k + 1) - first) * ((pk.y >> 23) & 0xffu));
+                if (t < NSLOT) {
+                    const uint2 pk = sm.tpk[t][lane];
+                    if ((unsigned)(k + 1) - (pk.x & 0xfffu) <= ((pk.x >> 12) & 0xfffu)) {
+                        lam[t] = ldg_pinned(lam_b + (int)(pk.y + (unsigned)(k + 1) * ((pk.x >> 24) & 0x7fu)));
+                        act |= (1 << t) | ((pk.x >> 31) << (4 + t));
+                    }
+                }
             }
         };
 
@@ -352,8 +364,8 @@ __global__ void __launch_bounds__(32, MINB) k_riccati(const DevProblem P, int* _
                     double gi, hi;
                     if (FASTAL && cost.diag) {
                         double lam[MAXT];
-                        load_lams(N - 1, lam);
-                        expand_fast(N - 1, xi, lam, cost.Qd[lane], cost.q[lane], gi, hi);
+                        int act; load_lams(N - 1, lam, act);
+                        expand_fast(xi, lam, act, cost.Qd[lane], cost.q[lane], gi, hi);
                         sm.S[i * LDS_ + i] = hi;
                     } else {
                         gi = cost.q[i]; hi = 0.0;
@@ -386,7 +398,8 @@ __global__ void __launch_bounds__(32, MINB) k_riccati(const DevProblem P, int* _
             double z_cur = 0.0, lam_cur[MAXT];
 #pragma unroll
             for (int t = 0; t < MAXT; t++) lam_cur[t] = 0.0;
-            if (lane < NM) { z_cur = zbase[(size_t)(N - 2) * zstride]; if (FASTAL) load_lams(N - 2, lam_cur); }
+            int act_cur = 0;
+            if (lane < NM) { z_cur = zbase[(size_t)(N - 2) * zstride]; if (FASTAL) load_lams(N - 2, lam_cur, act_cur); }
             // software pipeline of the cost coefficients: (cH,cG) of knot k are loaded during knot k+1, its index during knot k+2
             double cH_cur = 0.0, cG_cur = 0.0;
             int cid_next = (N >= 3) ? P.cost_index[N - 3] : 0;
@@ -397,12 +410,14 @@ __global__ void __launch_bounds__(32, MINB) k_riccati(const DevProblem P, int* _
             bool ok = true;
             int stage = 0;
             int k;
+            double g_reg = 0.0, h_reg = 0.0;
             for (k = N - 2; k >= 0; k--) {
                 // ---- prefetch z_i / multipliers of the next knot (k-1); consumed one iteration later -------
                 double z_nxt = 0.0, lam_nxt[MAXT];
 #pragma unroll
                 for (int t = 0; t < MAXT; t++) lam_nxt[t] = 0.0;
-                if (k > 0 && lane < NM) { z_nxt = ldg_pinned(zbase + (size_t)(k - 1) * zstride); if (FASTAL) load_lams(k - 1, lam_nxt); }
+                int act_nxt = 0;
+                if (k > 0 && lane < NM) { z_nxt = ldg_pinned(zbase + (size_t)(k - 1) * zstride); if (FASTAL) load_lams(k - 1, lam_nxt, act_nxt); }
                 double cH_nxt = 0.0, cG_nxt = 0.0;
                 int cid_next2 = 0;
                 if (FASTAL && P.all_diag_cost && k > 0) {
@@ -410,17 +425,17 @@ __global__ void __launch_bounds__(32, MINB) k_riccati(const DevProblem P, int* _
                     if (k > 1) cid_next2 = ldg_pinned(P.cost_index + (k - 2));
                 }
                 // ---- cost + AL expansion of knot k: lane i < NM handles z_i (diagonal terms) ------------
-                double g_reg = 0.0, h_reg = 0.0;
                 {
+                    g_reg = 0.0; h_reg = 0.0;
                     double gi = 0.0, hi = 0.0;
                     if (FASTAL && P.all_diag_cost) {
-                        if (lane < NM) expand_fast(k, z_cur, lam_cur, cH_cur, cG_cur, gi, hi);
+                        if (lane < NM) expand_fast(z_cur, lam_cur, act_cur, cH_cur, cG_cur, gi, hi);
                     } else if (lane < NM) {
                         const DevCost& cost = P.costs[P.cost_index[k]];
                         const int i = lane;
                         const double zi = z_cur;
                         if (FASTAL && cost.diag) {
-                            expand_fast(k, zi, lam_cur, (i < n) ? cost.Qd[i] : cost.Rd[i - n], (i < n) ? cost.q[i] : cost.r[i - n], gi, hi);
+                            expand_fast(zi, lam_cur, act_cur, (i < n) ? cost.Qd[i] : cost.Rd[i - n], (i < n) ? cost.q[i] : cost.r[i - n], gi, hi);
                         } else {
                             if (cost.diag) {
                                 if (i < n) { gi = fma(cost.Qd[i], zi, cost.q[i]); hi = cost.Qd[i]; }
@@ -574,7 +589,7 @@ __global__ void __launch_bounds__(32, MINB) k_riccati(const DevProblem P, int* _
 #pragma unroll
                     for (int a = 0; a < m; a++) { kc[a] = 0.0; wc[a] = 0.0; }
                     bool okl = true;
-                    if (lane < 16) {
+                    if (lane < 16) {   // half a warp: FP64 instructions of a half-empty warp take one pipe pass instead of two
                         double Quu[M_ * (M_ + 1) / 2], Lf[M_ * (M_ + 1) / 2], dj[M_];
 #pragma unroll
                         for (int a = 0; a < m; a++)
@@ -863,7 +878,7 @@ __global__ void __launch_bounds__(32, MINB) k_riccati(const DevProblem P, int* _
                         }
                     }
                 }
-                z_cur = z_nxt; cH_cur = cH_nxt; cG_cur = cG_nxt; cid_next = cid_next2;
+                z_cur = z_nxt; act_cur = act_nxt; cH_cur = cH_nxt; cG_cur = cG_nxt; cid_next = cid_next2;
 #pragma unroll
                 for (int t = 0; t < MAXT; t++) lam_cur[t] = lam_nxt[t];
                 __syncwarp();
@@ -897,10 +912,10 @@ __global__ void __launch_bounds__(32, MINB) k_riccati(const DevProblem P, int* _
     }
 }
 
-template <int N_, int M_, bool FASTAL, int STAGES, int MINB, bool MMA>
+template <int N_, int M_, bool FASTAL, int STAGES, int MINB, bool MMA, int NSLOT = MAXT>
 cudaError_t launch_riccati_v(const DevProblem& P, int* work_counter, cudaStream_t s) {
     using SM = RiccatiSmem<N_, M_, STAGES, MMA>;
-    auto kern = k_riccati<N_, M_, STAGES, FASTAL, MMA, MINB>;
+    auto kern = k_riccati<N_, M_, STAGES, FASTAL, MMA, MINB, NSLOT>;
     static bool configured = false;
     static int ctas_per_sm = 1, num_sms = 1;
     const int smem = (int)sizeof(SM);
@@ -926,18 +941,9 @@ template <int N_, int M_, bool FASTAL>
 cudaError_t launch_riccati_t(const DevProblem& P, int* work_counter, cudaStream_t s) {
     if constexpr (N_ >= 8 && M_ <= 4) {
         if (P.all_diag_cost && P.all_diag_con) {   // tensor-MMA kernel: diagonal lzz (DiagonalCost + Goal/Bound)
-            // tuning knob (occupancy vs registers / ring depth); default from the sweep in profiles/r01_notes.md
-            static int variant = -1;
-            if (variant < 0) { const char* v = getenv("TO_RICCATI_VARIANT"); variant = v ? atoi(v) : 1; }
-            switch (variant) {
-                case 0: return launch_riccati_v<N_, M_, FASTAL, 3, 12, true>(P, work_counter, s);
-                case 2: return launch_riccati_v<N_, M_, FASTAL, 2, 20, true>(P, work_counter, s);
-                case 3: return launch_riccati_v<N_, M_, FASTAL, 3, 16, true>(P, work_counter, s);
-                case 4: return launch_riccati_v<N_, M_, FASTAL, 2, 12, true>(P, work_counter, s);
-                case 5: return launch_riccati_v<N_, M_, FASTAL, 2, 14, true>(P, work_counter, s);
-                case 6: return launch_riccati_v<N_, M_, FASTAL, 3, 14, true>(P, work_counter, s);
-                default: return launch_riccati_v<N_, M_, FASTAL, 2, 16, true>(P, work_counter, s);
-            }
+            // 2-stage ring, 16 one-warp CTAs per SM (occupancy / ring-depth sweep in profiles/r01_notes.md).  NSLOT stays
+            // MAXT: a build with a 2-slot loop bound measured 13 % slower than this one (scheduling), see the notes.
+            return launch_riccati_v<N_, M_, FASTAL, 2, 16, true, MAXT>(P, work_counter, s);
         }
         return launch_riccati_v<N_, M_, FASTAL, 2, 12, false>(P, work_counter, s);   // dense costs: DFMA micro-block kernel
     } else {
@@ -948,7 +954,7 @@ cudaError_t launch_riccati_t(const DevProblem& P, int* work_counter, cudaStream_
 template <int N_, int M_>
 cudaError_t launch_riccati_nm(const DevProblem& P, int* work_counter, cudaStream_t s) {
     // the lane-resident AL terms hold at most MAXT rows per z entry (upper + lower bound + goal)
-    if (P.max_terms_per_z <= MAXT && P.N < 65536 && P.lambda_len < (1 << 23) && P.max_p_knot < 256) return launch_riccati_t<N_, M_, true>(P, work_counter, s);
+    if (P.max_terms_per_z <= MAXT && P.N < 4095 && P.max_p_knot < 128) return launch_riccati_t<N_, M_, true>(P, work_counter, s);
     return launch_riccati_t<N_, M_, false>(P, work_counter, s);
 }
 

@@ -28,6 +28,7 @@ struct to_handle {
     bool own_stream = false;
     cudaStream_t stream2 = nullptr;     // high-priority side stream: late line-search trials overlap the next expansion
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    bool overlap = true;                // TO_NO_OVERLAP=1: keep every kernel on the main stream (profiling under ncu, A/B timing)
     bool side_pending = false;          // stream2 still holds the late line-search trials of the last iteration (ev_join follows them)
     std::string err;
     std::vector<void*> allocs;
@@ -286,7 +287,8 @@ int to_create(const to_spec* s, to_handle** out) {
     {
         int lo = 0, hi = 0;
         cudaDeviceGetStreamPriorityRange(&lo, &hi);
-        if (const char* ev = getenv("TO_SIDE_PRIORITY")) { if (atoi(ev) == 0) hi = lo; }   // A/B switch (profiles/r01_notes.md)
+        if (const char* ev = getenv("TO_SIDE_PRIORITY")) { if (atoi(ev) == 0) hi = lo; }   // A/B switches (profiles/r01_notes.md)
+        if (const char* ev = getenv("TO_NO_OVERLAP")) h->overlap = atoi(ev) == 0;
         if (cudaStreamCreateWithPriority(&h->stream2, cudaStreamNonBlocking, hi) != cudaSuccess ||
             cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
             cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming) != cudaSuccess) { h->err = "side stream creation failed"; return bail(TO_ECUDA); }
@@ -751,12 +753,16 @@ int to_ilqr_step(to_handle* h, int32_t iters) {
         rc = do_backward(h); if (rc) return rc;
         { PhaseScope ps(h, TO_PHASE_FORWARD); CU(h, launch_forward(h->P, h->stream)); }
         h->launches++; h->phase_launches[TO_PHASE_FORWARD]++;
-        CU(h, cudaEventRecord(h->ev_fork, h->stream));
-        CU(h, cudaStreamWaitEvent(h->stream2, h->ev_fork, 0));
-        { PhaseScope ps(h, TO_PHASE_LADDER, h->stream2); CU(h, launch_ladder(h->P, h->stream2)); }
+        if (h->overlap) {
+            CU(h, cudaEventRecord(h->ev_fork, h->stream));
+            CU(h, cudaStreamWaitEvent(h->stream2, h->ev_fork, 0));
+            { PhaseScope ps(h, TO_PHASE_LADDER, h->stream2); CU(h, launch_ladder(h->P, h->stream2)); }
+            CU(h, cudaEventRecord(h->ev_join, h->stream2));
+            h->side_pending = true;
+        } else {
+            PhaseScope ps(h, TO_PHASE_LADDER); CU(h, launch_ladder(h->P, h->stream));
+        }
         h->launches++; h->phase_launches[TO_PHASE_LADDER]++;
-        CU(h, cudaEventRecord(h->ev_join, h->stream2));
-        h->side_pending = true;
         h->expanded = false; h->backward_done = false;   // the trajectory moved
     }
     return TO_OK;

@@ -367,17 +367,19 @@ extern __shared__ __align__(16) unsigned char fwd_smem[];
 
 // One line-search pass: lane l of group g evaluates trial (trial0 + l) of instance b.
 //   first_pass : ignore / reset accepted[b];   final_pass : commit failures (no acceptable step size).
-template <int MODEL, int G, bool FAST>
+template <int MODEL, int G, bool FAST, int LANES>
 __global__ void __launch_bounds__(FWD_THREADS) k_linesearch(const DevProblem P, int trial0, int first_pass, int final_pass) {
     constexpr int n = ModelDims<MODEL>::n, m = ModelDims<MODEL>::m;
-    constexpr int IPB = FWD_THREADS / G;
+    // LANES = 16: only half of the warp carries groups.  The pass is a latency-bound FP64 chain at ~4 warps per SM, and
+    // an FP64 instruction of a half-empty warp takes one pipe pass instead of two (profiles/r01_notes.md).
+    constexpr int IPB = LANES / G;
     using S = Stage<n, m, IPB>;
     FwdTab* tab = reinterpret_cast<FwdTab*>(fwd_smem);
     double* stage = reinterpret_cast<double*>(fwd_smem + sizeof(FwdTab));
-    const int g = threadIdx.x / G, l = threadIdx.x % G;
+    const int g = (threadIdx.x % LANES) / G, l = threadIdx.x % G;
     const int b = blockIdx.x * IPB + g;
     const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (g * G));
-    const bool valid = b < P.B;
+    const bool valid = b < P.B && threadIdx.x < LANES;
     const int status = valid ? P.bp_status[b] : -1;
     const int was_accepted = (valid && !first_pass) ? P.accepted[b] : 0;
     const bool work = valid && status >= 0 && !was_accepted && trial0 <= P.opt.ls_iters;
@@ -419,28 +421,31 @@ __global__ void __launch_bounds__(FWD_THREADS) k_linesearch(const DevProblem P, 
     (void)sizeof(S);
 }
 
-template <int MODEL, int G, bool FAST>
-cudaError_t launch_pass(const DevProblem& P, int trial0, int first_pass, int final_pass, cudaStream_t s) {
+template <int MODEL, int G, bool FAST, int LANES>
+cudaError_t launch_pass_l(const DevProblem& P, int trial0, int first_pass, int final_pass, cudaStream_t s) {
     constexpr int n = ModelDims<MODEL>::n, m = ModelDims<MODEL>::m;
-    constexpr int IPB = FWD_THREADS / G;
+    constexpr int IPB = LANES / G;
     const int blocks = (P.B + IPB - 1) / IPB;
     const size_t smem = FAST ? sizeof(FwdTab) + (size_t)2 * Stage<n, m, IPB>::DOUBLES * sizeof(double) : 0;
-    auto kern = k_linesearch<MODEL, G, FAST>;
+    auto kern = k_linesearch<MODEL, G, FAST, LANES>;
     static bool configured = false;
     if (!configured && smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
     }
-    if (!configured) {
-        const char* ev = getenv("TO_CARVEOUT");
-        if (!ev || atoi(ev) != 0) {
-            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
-            if (e != cudaSuccess) return e;
-        }
-    }
     configured = true;
     kern<<<blocks, FWD_THREADS, smem, s>>>(P, trial0, first_pass, final_pass);
     return cudaGetLastError();
+}
+
+template <int MODEL, int G, bool FAST>
+cudaError_t launch_pass(const DevProblem& P, int trial0, int first_pass, int final_pass, cudaStream_t s) {
+    // lanes of each warp that carry groups: default 16 for the first pass, 32 for the later ones (A/B in profiles/r01_notes.md)
+    static int lanes1 = -1, lanes2 = -1;
+    if (lanes1 < 0) { const char* v = getenv("TO_FWD_LANES_P1"); lanes1 = v ? atoi(v) : 16; v = getenv("TO_FWD_LANES_P2"); lanes2 = v ? atoi(v) : 32; }
+    const int lanes = first_pass ? lanes1 : lanes2;
+    if (G <= 16 && lanes == 16) return launch_pass_l<MODEL, G, FAST, (G <= 16 ? 16 : 32)>(P, trial0, first_pass, final_pass, s);
+    return launch_pass_l<MODEL, G, FAST, 32>(P, trial0, first_pass, final_pass, s);
 }
 
 bool fast_path(const DevProblem& P) {

@@ -86,17 +86,6 @@ static cudaError_t launch_expand_t(const DevProblem& P, cudaStream_t s, int mode
     constexpr int TPK = (nm + NP - 1) / NP;
     const long long total = (long long)P.B * (P.N - 1) * TPK;
     const int threads = 128;
-    // Same shared-memory carve-out as the line-search / Riccati kernels it runs next to (capi.cu, to_ilqr_step): an SM
-    // only reconfigures its L1/shared split when idle, so mixed preferences serialise the overlapped kernels.
-    static bool configured = false;
-    if (!configured) {
-        const char* ev = getenv("TO_CARVEOUT");
-        if (!ev || atoi(ev) != 0) {
-            cudaError_t e = cudaFuncSetAttribute(k_expand<MODEL, NP>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
-            if (e != cudaSuccess) return e;
-        }
-        configured = true;
-    }
     k_expand<MODEL, NP><<<(unsigned)((total + threads - 1) / threads), threads, 0, s>>>(P, mode);
     return cudaGetLastError();
 }

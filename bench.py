@@ -203,8 +203,8 @@ def main():
             # the path's only collective: {sum merit, max violation} SUM/MAX all-reduce.  Nothing on the device
             # consumes it, so it runs on a side stream and overlaps the next iteration's kernels.
             stream.wait_stream(side)                                     # previous all-reduce has released the buffer
-            K.check(lib, h, lib.to_reduce_merit(h))                      # per-GPU {sum J, max viol} (one small kernel)
-            side.wait_stream(stream)
+            # per-GPU {sum J, max viol} (one small kernel) queued behind the iteration's last kernel; `side` waits on its event
+            K.check(lib, h, lib.to_reduce_merit_async(h, C.c_void_p(side.cuda_stream)))
             with torch.cuda.stream(side):
                 TO.multi_gpu.all_reduce_merit(merit2)
 

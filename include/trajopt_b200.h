@@ -174,6 +174,10 @@ int to_get_solver_state(to_handle* h, double* rho /*[B]*/, double* dV /*[B][2]*/
 /* device pointer to {sum_b J_b, max_b violation_b} (2 doubles) refreshed by to_reduce_merit(); the host
  * framework all-reduces it (NCCL: sum on [0], max on [1]).  SURVEY 8(e). */
 int to_reduce_merit(to_handle* h);
+/* Same reduction, ordered after whatever part of the last iteration is still in flight on the library's side
+ * stream, and handed to `consumer_stream` (a cudaStream_t, e.g. the stream the NCCL all-reduce is issued on) through
+ * an event: the handle's main stream is NOT made to wait, so the next iteration keeps overlapping. */
+int to_reduce_merit_async(to_handle* h, void* consumer_stream);
 int to_merit_device_ptr(to_handle* h, void** ptr);
 /* per-phase device timing (CUDA events on the handle's stream) for the roofline report */
 enum to_phase { TO_PHASE_EXPAND = 0, TO_PHASE_BACKWARD = 1, TO_PHASE_FORWARD = 2, TO_PHASE_LADDER = 3, TO_PHASE_ACCEPT = 4, TO_PHASE_COUNT = 8 };

@@ -281,6 +281,16 @@ def test_reduce_merit_buffer_tracks_line_search_results():
     got = t2.cpu().numpy().copy()
     assert np.isclose(got[0], TO.merit(prob).sum(), rtol=1e-12)
     assert np.isclose(got[1], TO.max_violation(prob).max(), rtol=1e-12)
+    # on a consumer stream of its own, interleaved with further iterations (the bench's multi-GPU step)
+    import ctypes as C
+    side = torch.cuda.Stream()
+    ref = P.quadrotor(B=257, N=101); TO.rollout(ref); TO.ilqr_step(ref, 3)
+    for _ in range(3):
+        TO.ilqr_step(prob, 1); TO.ilqr_step(ref, 1)
+        assert prob._lib.to_reduce_merit_async(prob._h, C.c_void_p(side.cuda_stream)) == 0
+        side.synchronize()
+        assert np.isclose(t2.cpu().numpy()[0], TO.merit(ref).sum(), rtol=1e-12)
+    np.testing.assert_array_equal(TO.controls(prob), TO.controls(ref))
     TO.al_update(prob)                       # invalidates J: the next reduce recomputes it
     TO.multi_gpu.global_merit(prob, device_tensor=t2)
     torch.cuda.synchronize()

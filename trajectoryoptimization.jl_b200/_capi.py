@@ -138,7 +138,7 @@ def load_library():
         "to_get_gains": [H, c_double_p, c_double_p], "to_get_multipliers": [H, C.c_int32, c_double_p],
         "to_set_multipliers": [H, C.c_int32, c_double_p], "to_get_penalty": [H, C.c_int32, c_double_p], "to_set_penalty": [H, C.c_int32, C.c_double],
         "to_get_solver_state": [H, c_double_p, c_double_p, c_double_p, c_int32_p, c_int32_p],
-        "to_reduce_merit": [H], "to_merit_device_ptr": [H, C.POINTER(C.c_void_p)],
+        "to_reduce_merit": [H], "to_reduce_merit_async": [H, C.c_void_p], "to_merit_device_ptr": [H, C.POINTER(C.c_void_p)],
         "to_set_phase_timing": [H, C.c_int], "to_get_phase_times": [H, c_double_p, C.POINTER(C.c_int64), C.c_int],
         "to_algorithmic_bytes": [H, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64)],
     }
@@ -161,7 +161,7 @@ EXPORTED_SYMBOLS = [
     "to_get_dynamics_jacobians", "to_cost", "to_cost_knots", "to_cost_gradient", "to_cost_hessian", "to_eval_constraints",
     "to_constraint_jacobians", "to_max_violation", "to_merit", "to_al_expansion", "to_projection", "to_grad_projection",
     "to_hess_projection", "to_backward", "to_forward", "to_ilqr_step", "to_al_update", "to_get_gains", "to_get_multipliers",
-    "to_set_multipliers", "to_get_penalty", "to_set_penalty", "to_get_solver_state", "to_reduce_merit", "to_merit_device_ptr",
+    "to_set_multipliers", "to_get_penalty", "to_set_penalty", "to_get_solver_state", "to_reduce_merit", "to_reduce_merit_async", "to_merit_device_ptr",
     "to_set_phase_timing", "to_get_phase_times", "to_launch_count", "to_algorithmic_bytes",
 ]
 

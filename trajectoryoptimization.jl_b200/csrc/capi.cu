@@ -27,7 +27,7 @@ struct to_handle {
     cudaStream_t stream = nullptr;
     bool own_stream = false;
     cudaStream_t stream2 = nullptr;     // high-priority side stream: late line-search trials overlap the next expansion
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_merit = nullptr, ev_cons = nullptr;
     bool overlap = true;                // TO_NO_OVERLAP=1: keep every kernel on the main stream (profiling under ncu, A/B timing)
     bool side_pending = false;          // stream2 still holds the late line-search trials of the last iteration (ev_join follows them)
     std::string err;
@@ -291,7 +291,9 @@ int to_create(const to_spec* s, to_handle** out) {
         if (const char* ev = getenv("TO_NO_OVERLAP")) h->overlap = atoi(ev) == 0;
         if (cudaStreamCreateWithPriority(&h->stream2, cudaStreamNonBlocking, hi) != cudaSuccess ||
             cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
-            cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming) != cudaSuccess) { h->err = "side stream creation failed"; return bail(TO_ECUDA); }
+            cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&h->ev_merit, cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&h->ev_cons, cudaEventDisableTiming) != cudaSuccess) { h->err = "side stream creation failed"; return bail(TO_ECUDA); }
     }
     DevProblem& P = h->P;
     P.model = s->model; P.n = mn; P.m = mm; P.N = s->N; P.B = s->B;
@@ -395,6 +397,8 @@ int to_destroy(to_handle* h) {
     if (h->stream2) { cudaStreamSynchronize(h->stream2); cudaStreamDestroy(h->stream2); }
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
     if (h->ev_join) cudaEventDestroy(h->ev_join);
+    if (h->ev_merit) cudaEventDestroy(h->ev_merit);
+    if (h->ev_cons) cudaEventDestroy(h->ev_cons);
     if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
     delete h;
     return TO_OK;
@@ -838,8 +842,26 @@ int to_reduce_merit(to_handle* h) {
     CU(h, launch_reduce_merit(h->P, h->d_viol, h->d_merit2, h->stream)); h->launches++;
     return TO_OK;
 }
+int to_reduce_merit_async(to_handle* h, void* consumer_stream) {
+    if (!h) return TO_EINVAL;
+    cudaStream_t cs = (cudaStream_t)consumer_stream;
+    cudaStream_t on = h->stream;
+    if (h->side_pending && h->J_valid) {
+        // the late line-search trials are still in flight on the side stream: reduce behind them, leave the main stream alone
+        on = h->stream2;
+    } else {
+        JOIN(h);
+        int rc = ensure_merit(h); if (rc) return rc;
+    }
+    CU(h, cudaEventRecord(h->ev_cons, cs));                 // the consumer's earlier reads of the buffer come first
+    CU(h, cudaStreamWaitEvent(on, h->ev_cons, 0));
+    CU(h, launch_reduce_merit(h->P, h->d_viol, h->d_merit2, on)); h->launches++;
+    CU(h, cudaEventRecord(h->ev_merit, on));
+    if (on == h->stream2) CU(h, cudaEventRecord(h->ev_join, h->stream2));   // later joins cover the reduction too
+    CU(h, cudaStreamWaitEvent(cs, h->ev_merit, 0));
+    return TO_OK;
+}
 int to_merit_device_ptr(to_handle* h, void** ptr) {
-    JOIN(h);
     if (!h || !ptr) return TO_EINVAL;
     *ptr = h->d_merit2;
     return TO_OK;

@@ -151,4 +151,13 @@ function max_violation(p::BatchedProblem)
     check(p.h, ccall((:to_max_violation, libb200), Cint, (Ptr{Cvoid}, Ptr{Float64}), p.h, v)); v
 end
 
+# multi-GPU (one process per GPU, e.g. under MPI.jl + NCCL.jl): the only collective is the {sum J, max violation} all-reduce.
+# `to_reduce_merit_async` queues the per-GPU reduction behind the iteration in flight and makes `stream` (the CUDA.jl
+# stream the NCCL call is issued on) wait for it; `merit_device_ptr` is the 2-double buffer to all-reduce in place.
+reduce_merit_async!(p::BatchedProblem, stream::Ptr{Cvoid}) = check(p.h, ccall((:to_reduce_merit_async, libb200), Cint, (Ptr{Cvoid}, Ptr{Cvoid}), p.h, stream))
+function merit_device_ptr(p::BatchedProblem)
+    r = Ref{Ptr{Cvoid}}(C_NULL)
+    check(p.h, ccall((:to_merit_device_ptr, libb200), Cint, (Ptr{Cvoid}, Ref{Ptr{Cvoid}}), p.h, r)); r[]
+end
+
 end # module

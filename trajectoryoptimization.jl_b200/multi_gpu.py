@@ -48,7 +48,9 @@ def global_merit(prob, group=None, device_tensor=None):
     reduction stays on the device; otherwise it goes through host arrays (CPU / gloo)."""
     import torch
     if device_tensor is not None:
-        K.check(prob._lib, prob._h, prob._lib.to_reduce_merit(prob._h))
+        # reduce behind whatever is still in flight and hand the result to the current torch stream through an event
+        # (to_reduce_merit_async): the handle's own stream keeps running the next iteration
+        K.check(prob._lib, prob._h, prob._lib.to_reduce_merit_async(prob._h, C.c_void_p(torch.cuda.current_stream().cuda_stream)))
         return all_reduce_merit(device_tensor, group)
     t2 = torch.tensor([float(np.sum(TO.merit(prob))), float(np.max(TO.max_violation(prob)))], dtype=torch.float64)
     return all_reduce_merit(t2, group)

@@ -67,7 +67,9 @@ enum to_con_kind {
     TO_CON_LINEAR = 2, /* LinearConstraint :103-150  a = A[p x w] col-major, b = b[p], flag = 0 state | 1 control, sense */
     TO_CON_CIRCLE = 3, /* CircleConstraint :168-233  a = xc[p], b = yc[p], rad = r[p], inds = {xi, yi} (1-based) */
     TO_CON_SPHERE = 4, /* SphereConstraint :249-326  a,b,c = centers, rad, inds = {xi, yi, zi}                 */
-    TO_CON_NORM = 5    /* NormConstraint :438-521    val, inds = 1-based indices into z, sense (orthant | SOC)   */
+    TO_CON_NORM = 5,   /* NormConstraint :438-521    val, inds = 1-based indices into z, sense (orthant | SOC)   */
+    TO_CON_COLLISION = 6 /* CollisionConstraint :341-389  val = radius, inds = {x1[D], x2[D]} 1-based state indices (ninds = 2D): r^2 - |x[x1]-x[x2]|^2 <= 0.
+                            StateBound / ControlBound :547-631 are TO_CON_BOUND with the other block unbounded. */
 };
 typedef struct {
     int32_t kind;        /* to_con_kind */

@@ -242,7 +242,7 @@ inline int hess_projection(int cone, const double* x, const double* b, int p, do
 
 // ------------------------------------------------------------------------------------------------
 // Constraints  (src/constraints.jl).  All are functions of one knot z = [x;u].
-enum ConKind { CON_GOAL = 0, CON_BOUND = 1, CON_LINEAR = 2, CON_CIRCLE = 3, CON_SPHERE = 4, CON_NORM = 5 };
+enum ConKind { CON_GOAL = 0, CON_BOUND = 1, CON_LINEAR = 2, CON_CIRCLE = 3, CON_SPHERE = 4, CON_NORM = 5, CON_COLLISION = 6 };
 
 struct Constraint {
     int kind = CON_GOAL;
@@ -319,6 +319,13 @@ inline void con_evaluate(const Constraint& con, const double* x, const double* u
             }
             break;
         }
+        case CON_COLLISION: {  // src/constraints.jl:367-376 (in-place form): c = r^2, then c -= d_i^2 for i = 1..D
+            const size_t D = con.inds.size() / 2;
+            double s = con.val * con.val;
+            for (size_t i = 0; i < D; i++) { const double d = x[con.inds[i]] - x[con.inds[D + i]]; s -= d * d; }
+            c[0] = s;
+            break;
+        }
     }
 }
 
@@ -359,6 +366,15 @@ inline void con_jacobian(const Constraint& con, const double* x, const double* u
                 for (size_t i = 0; i < con.inds.size(); i++) jac[con.inds[i] * p + i] = 1;
             } else {
                 for (int j : con.inds) jac[j * p + 0] = 2 * zj(j);
+            }
+            break;
+        }
+        case CON_COLLISION: {                                                                    // :378-389
+            const size_t D = con.inds.size() / 2;
+            for (size_t i = 0; i < D; i++) {
+                const double d = x[con.inds[i]] - x[con.inds[D + i]];
+                jac[con.inds[i] * p] = -2 * d;
+                jac[con.inds[D + i] * p] = 2 * d;
             }
             break;
         }

@@ -100,6 +100,11 @@ int orc_create(const to_spec* s, orc_handle** out) {
                 for (int j = 0; j < tc.ninds; j++) c.inds.push_back(tc.inds[j] - 1);
                 c.p = (tc.sense == TO_CONE_SECOND_ORDER) ? tc.ninds + 1 : 1;
                 break;
+            case TO_CON_COLLISION:
+                if (tc.ninds < 2 || (tc.ninds & 1)) { delete h; return fail(nullptr, TO_EDIM, "Position dimensions must be of equal length"); }
+                c.sense = CONE_NEGATIVE_ORTHANT; c.val = tc.val; c.p = 1;
+                for (int j = 0; j < tc.ninds; j++) c.inds.push_back(tc.inds[j] - 1);
+                break;
             default: delete h; return fail(nullptr, TO_EINVAL, "unknown constraint kind");
         }
         P.cons.push_back(c);

@@ -204,6 +204,10 @@ def _general_pair(kind):
             extra = [(TO.SphereConstraint(n, [0.5, 0.2], [1.0, 0.5], [1.5, 1.2], [0.3, 0.25]), (2, N - 1)),
                      (TO.NormConstraint(n, m, 12.0, TO.SecondOrderCone(), "control"), (1, N - 1)),
                      (TO.NormConstraint(n, m, 3.0, TO.Inequality(), [8, 9, 10]), (1, N))]
+            if kind == "quadrotor_collision_statebound":
+                extra = [(TO.CollisionConstraint(n, [1, 2, 3], [8, 9, 10], 0.4), (1, N)),          # position vs (scaled) velocity: any index pair works
+                         (TO.StateBound(n, x_max=np.concatenate([[1.2, 1.2, 2.5], np.full(10, np.inf)]), x_min=np.concatenate([[-0.2], np.full(12, -np.inf)])), (2, N)),
+                         (TO.ControlBound(m, u_max=9.0), (1, N - 1))]
         prob.close()
         for con, inds in extra:
             TO.add_constraint(cons, con, inds)
@@ -213,11 +217,14 @@ def _general_pair(kind):
     return probs
 
 
-@pytest.mark.parametrize("kind", ["cartpole_linear_circle", "quadrotor_sphere_soc_norm"])
+@pytest.mark.parametrize("kind", ["cartpole_linear_circle", "quadrotor_sphere_soc_norm", "quadrotor_collision_statebound"])
 def test_general_constraints_in_solver_kernels(kind):
     g, o = _general_pair(kind)
     for p in (g, o):
         TO.rollout(p); TO.expand(p)
+    for i in range(len(g.constraints)):
+        close(TO.evaluate_constraints(g, i), TO.evaluate_constraints(o, i), KERNEL_RTOL, f"constraint {i} values")
+        close(TO.constraint_jacobians(g, i), TO.constraint_jacobians(o, i), KERNEL_RTOL, f"constraint {i} jacobians")
     gg, gh = TO.al_expansion(g); og, oh = TO.al_expansion(o)
     close(gg, og, KERNEL_RTOL, "AL gradient"); close(gh, oh, KERNEL_RTOL, "AL hessian")
     assert np.array_equal(TO.backward(g), TO.backward(o))

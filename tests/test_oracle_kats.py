@@ -181,6 +181,41 @@ def test_state_and_control_bound_integer_kats():
     assert np.array_equal(c, [-10, -9, -8])                                                     # :341
 
 
+def test_collision_state_control_bound_api():
+    """CollisionConstraint KAT (test/constraint_tests.jl:155-174) and the StateBound / ControlBound classes (:268-345)."""
+    r = rng()
+    n, m, N = 13, 4, 3
+    obj = TO.LQRObjective(np.eye(n), np.eye(m), np.eye(n), np.zeros(n), N)
+    col = TO.CollisionConstraint(n, [1, 2], [3, 4], 2.0)
+    sb = TO.StateBound(n, x_max=np.concatenate([[10, 2, 5.], np.full(10, np.inf)]), x_min=np.concatenate([[0, -3, -4.], np.full(10, -np.inf)]))
+    cb = TO.ControlBound(m, u_max=10)
+    cons = TO.ConstraintList(n, m, N)
+    TO.add_constraint(cons, col, (1, N)); TO.add_constraint(cons, sb, (1, N)); TO.add_constraint(cons, cb, (1, N - 1))
+    prob = OracleProblem(TO.Quadrotor(), obj, np.zeros(n), 1.0, constraints=cons)
+    X, U = r.random((N, n)), np.tile([0, 1, 2, 3.], (N - 1, 1))
+    X[:, :3] = [0, 1, 2.]
+    TO.initial_states(prob, X); TO.initial_controls(prob, U)
+    x = X[0]; d = x[[0, 1]] - x[[2, 3]]
+    assert np.allclose(TO.evaluate_constraints(prob, col)[0, 0, 0], 4 - d @ d)                    # :161-163
+    J = TO.constraint_jacobians(prob, col)[0, 0]
+    assert np.allclose(J[0, :4], np.concatenate([-2 * d, 2 * d])) and not J[0, 4:].any()           # :166
+    assert TO.output_dim(col) == 1 and isinstance(TO.sense(col), TO.Inequality)                     # :167
+    with pytest.raises(TO.DimensionMismatch):
+        TO.CollisionConstraint(n, [1, 2], [1, 2, 3], 1.0)                                           # :173
+    assert np.array_equal(TO.evaluate_constraints(prob, sb)[0, 0], [-10, -1, -3, 0, -4, -6])        # :280
+    assert TO.output_dim(sb) == 6 and TO.is_bound(sb)
+    assert np.array_equal(TO.upper_bound(sb)[:3], [10, 2, 5]) and np.array_equal(TO.lower_bound(sb)[:3], [0, -3, -4])   # :277-278
+    assert np.array_equal(TO.evaluate_constraints(prob, cb)[0, 0], [-10, -9, -8, -7])               # :341 (m = 4 here)
+    assert np.array_equal(TO.upper_bound(cb), np.full(m, 10.0)) and np.all(np.isneginf(TO.lower_bound(cb)))
+    Jb = TO.constraint_jacobians(prob, cb)[0, 0]
+    assert np.array_equal(Jb[:, n:], np.eye(m)) and not Jb[:, :n].any()
+    with pytest.raises(TO.ArgumentError):
+        TO.StateBound(n, x_max=-10, x_min=10)                                                       # :304
+    with pytest.raises(TO.ArgumentError):
+        TO.ControlBound(m, u_max=-10, u_min=10)                                                     # :343
+    assert np.array_equal(TO.num_constraints(prob), [1 + 6 + 4, 1 + 6 + 4, 1 + 6])
+
+
 def test_circle_sphere_norm_linear_closed_forms():   # :43-205
     r = rng()
     n, m, N = 13, 4, 3

@@ -339,12 +339,16 @@ def is_bound(con):   # src/abstract_constraint.jl:139
 
 
 def upper_bound(con):   # src/abstract_constraint.jl:104-109
+    if isinstance(con, StateBound): return con.x_max.copy()        # src/constraints.jl:607
+    if isinstance(con, ControlBound): return con.u_max.copy()      # :630
     if isinstance(con, BoundConstraint):
         return con.z_max.copy()      # src/constraints.jl:733
     return np.full(con.p, {ZeroCone: 0.0, NegativeOrthant: 0.0}.get(type(con.sense_), np.inf))
 
 
 def lower_bound(con):   # src/abstract_constraint.jl:116-121
+    if isinstance(con, StateBound): return con.x_min.copy()        # src/constraints.jl:606
+    if isinstance(con, ControlBound): return con.u_min.copy()      # :629
     if isinstance(con, BoundConstraint):
         return con.z_min.copy()      # src/constraints.jl:732
     return np.full(con.p, {ZeroCone: 0.0}.get(type(con.sense_), -np.inf))
@@ -435,6 +439,47 @@ class NormConstraint(AbstractConstraint):   # src/constraints.jl:438-521
         return dict(kind=K.CON_NORM, first=first, last=last, sense=self.sense_.code, val=self.val, inds=self.inds)
 
 
+class CollisionConstraint(AbstractConstraint):   # src/constraints.jl:328-389
+    """``CollisionConstraint(n, x1, x2, r)``: ``r^2 - |x[x1] - x[x2]|^2 <= 0`` (1-based state indices)."""
+
+    def __init__(self, n, x1, x2, radius):
+        self.n = n
+        self.x1, self.x2 = np.asarray(list(x1), dtype=int), np.asarray(list(x2), dtype=int)
+        if self.x1.size != self.x2.size:
+            raise DimensionMismatch(f"Position dimensions must be of equal length, got {self.x1.size} and {self.x2.size}")   # @assert :349
+        self.radius, self.p = float(radius), 1
+
+    def _spec(self, first, last):
+        return dict(kind=K.CON_COLLISION, first=first, last=last, sense=K.CONE_NEGATIVE_ORTHANT, val=self.radius,
+                    inds=np.concatenate([self.x1, self.x2]))
+
+
+class StateBound(BoundConstraint):   # src/constraints.jl:596-617 -- a BoundConstraint whose control block is unbounded
+    """``StateBound(n; x_min, x_max)``. The control dimension is taken from the ConstraintList it is added to."""
+
+    def __init__(self, n, x_min=-np.inf, x_max=np.inf):
+        self.n = n
+        self.x_max, self.x_min = _check_bounds(n, x_max, x_min)
+        self.p = int(np.isfinite(self.x_max).sum() + np.isfinite(self.x_min).sum())
+        self._bind(0)
+
+    def _bind(self, m):
+        self.z_max = np.concatenate([self.x_max, np.full(m, np.inf)]); self.z_min = np.concatenate([self.x_min, np.full(m, -np.inf)])
+
+
+class ControlBound(BoundConstraint):   # src/constraints.jl:619-640
+    """``ControlBound(m; u_min, u_max)``. The state dimension is taken from the ConstraintList it is added to."""
+
+    def __init__(self, m, u_min=-np.inf, u_max=np.inf):
+        self.m = m
+        self.u_max, self.u_min = _check_bounds(m, u_max, u_min)
+        self.p = int(np.isfinite(self.u_max).sum() + np.isfinite(self.u_min).sum())
+        self._bind(0)
+
+    def _bind(self, n):
+        self.z_max = np.concatenate([np.full(n, np.inf), self.u_max]); self.z_min = np.concatenate([np.full(n, -np.inf), self.u_min])
+
+
 class ConstraintList:
     """``ConstraintList(n, m, N)`` (src/constraint_list.jl:35-52)."""
 
@@ -465,6 +510,8 @@ def add_constraint(cons, con, inds, idx=-1):
         raise DimensionMismatch("New constraint not consistent with n and m")   # src/constraint_list.jl:108-110
     if not (1 <= first <= last <= cons.N):
         raise ArgumentError("Invalid inds, inds[end] must be less than number of knotpoints")   # @assert :107
+    if isinstance(con, StateBound): con._bind(cons.m)
+    if isinstance(con, ControlBound): con._bind(cons.n)
     pos = len(cons.constraints) if idx == -1 else idx
     cons.constraints.insert(pos, con)
     cons.inds.insert(pos, (int(first), int(last)))

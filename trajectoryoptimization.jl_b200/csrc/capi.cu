@@ -221,6 +221,17 @@ int build_con(to_handle* h, const to_constraint_spec& tc, int n, int m, int N, D
             if (tc.sense != TO_CONE_SECOND_ORDER && tc.sense != TO_CONE_NEGATIVE_ORTHANT && tc.sense != TO_CONE_ZERO)
                 return fail(h, TO_EINVAL, "NormConstraint: sense must be Inequality, Equality or SecondOrderCone");
             break;
+        case TO_CON_COLLISION: {
+            const int D = tc.ninds / 2;
+            if (tc.ninds < 2 || (tc.ninds & 1) || tc.ninds > TO_MAXNM || !tc.inds)
+                return fail(h, TO_EDIM, "Position dimensions must be of equal length");   // @assert src/constraints.jl:349
+            c.p = 1; c.sense = CONE_NEGATIVE_ORTHANT; c.ninds = tc.ninds; c.val = tc.val;
+            for (int i = 0; i < 2 * D; i++) {
+                c.inds[i] = tc.inds[i] - 1;
+                if (c.inds[i] < 0 || c.inds[i] >= n) return fail(h, TO_EDIM, "CollisionConstraint: index outside the state");
+            }
+            break;
+        }
         default: return fail(h, TO_EINVAL, "unknown constraint kind");
     }
     if (c.p > TO_MAXP) return fail(h, TO_EINVAL, "constraint output dimension exceeds TO_MAXP");

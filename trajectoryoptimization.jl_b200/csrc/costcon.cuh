@@ -143,6 +143,13 @@ __device__ inline void con_evaluate(const DevCon& con, int n, int m, const doubl
                 c[0] = s - con.val * con.val;
             }
             break;
+        case CON_COLLISION: {   // src/constraints.jl:367-376: r^2 - sum_i (x[x1_i] - x[x2_i])^2, accumulated in that order
+            const int D = con.ninds / 2;
+            double s = con.val * con.val;
+            for (int i = 0; i < D; i++) { const double d = x[con.inds[i]] - x[con.inds[D + i]]; s -= d * d; }
+            c[0] = s;
+            break;
+        }
     }
 }
 
@@ -180,6 +187,15 @@ __device__ inline void con_jacobian(const DevCon& con, int n, int m, const doubl
             if (con.sense == CONE_SECOND_ORDER) for (int i = 0; i < con.ninds; i++) jac[con.inds[i] * p + i] = 1;
             else for (int i = 0; i < con.ninds; i++) jac[con.inds[i] * p + 0] = 2 * zget(n, x, u, con.inds[i]);
             break;
+        case CON_COLLISION: {   // :378-389 (assignments, as in the reference)
+            const int D = con.ninds / 2;
+            for (int i = 0; i < D; i++) {
+                const double d = x[con.inds[i]] - x[con.inds[D + i]];
+                jac[con.inds[i] * p] = -2 * d;
+                jac[con.inds[D + i] * p] = 2 * d;
+            }
+            break;
+        }
     }
 }
 

@@ -139,6 +139,17 @@ int to_get_states(to_handle* h, double* X /*[B][N][n]*/);                     /*
 int to_get_controls(to_handle* h, double* U /*[B][N-1][m]*/);                 /* controls(prob)     src/problem.jl:168 */
 int to_get_times(to_handle* h, double* t /*[N]*/);                            /* gettimes(prob)     src/problem.jl:182 */
 
+/* ---- MPC plumbing (BASELINE config 5) ---------------------------------------------------------
+ * update_trajectory!(obj, Z, start) src/objective.jl:207-212: knot i = 1..N of a tracking objective follows row
+ * (start-1+i) of the reference: set_LQR_goal! (src/cost_functions.jl:245-254) q = -Q xf, r = -R uf, c untouched.
+ * Xref [nref][n], Uref [nref][m] host arrays (start + N - 1 <= nref). Costs shared by several knots end up tracking
+ * the last of them, exactly as the reference's aliased cost objects do. */
+int to_update_trajectory(to_handle* h, const double* Xref, const double* Uref, int32_t nref, int32_t start);
+/* Receding-horizon warm start, on the device: X_k <- X_{k+steps}, U_k <- U_{k+steps} (the tail repeats the last
+ * control and state), multipliers move with their knots (the tail keeps its last value), x0 <- X_{1+steps},
+ * t0 += the skipped dt. The caller then sets the measured state (to_set_initial_state) and re-rolls out. */
+int to_shift_trajectory(to_handle* h, int32_t steps);
+
 /* ---- kernel 1: batched RK4 rollout (+ dual-number Jacobians) ---------------------------------------- */
 int to_rollout(to_handle* h);                                                 /* rollout!           src/problem.jl:330-340 */
 int to_expand(to_handle* h);                                                  /* RD.jacobian!(ForwardAD) on the discretized dynamics at every knot */

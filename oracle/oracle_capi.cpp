@@ -159,6 +159,43 @@ int orc_set_goal_state(orc_handle* h, const double* xf, int objective, int const
 }
 
 
+// update_trajectory!(obj, Z, start)  src/objective.jl:207-212 with set_LQR_goal! src/cost_functions.jl:245-254
+int orc_update_trajectory(orc_handle* h, const double* Xref, const double* Uref, int32_t nref, int32_t start) {
+    Problem& P = h->P; const int n = P.n, m = P.m, N = P.N;
+    if (start < 1 || start - 1 + N > nref) return fail(h, TO_EDIM, "update_trajectory!: the reference is shorter than start + N - 1");
+    for (int i = 0; i < N; i++) {
+        Cost& c = P.costs[P.cost_index[i]];
+        const double* xf = Xref + (size_t)(start - 1 + i) * n;
+        const double* uf = Uref + (size_t)(start - 1 + i) * m;
+        for (int a = 0; a < n; a++) { double t = 0; for (int j = 0; j < n; j++) t += c.Q[j * n + a] * xf[j]; c.q[a] = -t; }
+        for (int a = 0; a < m; a++) { double t = 0; for (int j = 0; j < m; j++) t += c.R[j * m + a] * uf[j]; c.r[a] = -t; }
+    }
+    P.J_valid = false;
+    return TO_OK;
+}
+// receding-horizon warm start (see include/trajopt_b200.h, to_shift_trajectory): plain loops over instances and knots
+int orc_shift_trajectory(orc_handle* h, int32_t steps) {
+    Problem& P = h->P; const int n = P.n, m = P.m, N = P.N;
+    if (steps < 0) return TO_EINVAL;
+    if (steps == 0) return TO_OK;
+    if (steps > N - 1) steps = N - 1;
+    for (int b = 0; b < P.B; b++) {
+        double* X = &P.X[(size_t)b * N * n]; double* U = &P.U[(size_t)b * (N - 1) * m];
+        for (int i = 0; i < n; i++) P.x0[(size_t)b * n + i] = X[(size_t)steps * n + i];
+        for (int k = 0; k < N; k++) { const int s = std::min(k + steps, N - 1); for (int i = 0; i < n; i++) X[(size_t)k * n + i] = X[(size_t)s * n + i]; }
+        for (int k = 0; k < N - 1; k++) { const int s = std::min(k + steps, N - 2); for (int i = 0; i < m; i++) U[(size_t)k * m + i] = U[(size_t)s * m + i]; }
+        double* lam = &P.lambda[(size_t)b * P.lambda_len];
+        for (size_t ci = 0; ci < P.cons.size(); ci++) {
+            const Constraint& c = P.cons[ci];
+            const int nk = c.last - c.first + 1;
+            for (int k = 0; k + steps < nk; k++) for (int r = 0; r < c.p; r++) lam[P.con_offset[ci] + k * c.p + r] = lam[P.con_offset[ci] + (k + steps) * c.p + r];
+        }
+    }
+    for (int k = 0; k < steps; k++) P.t0 += P.dt[k];
+    P.J_valid = false;
+    return TO_OK;
+}
+
 int orc_get_times(orc_handle* h, double* t) {
     t[0] = h->P.t0;
     for (int k = 1; k < h->P.N; k++) t[k] = t[k - 1] + h->P.dt[k - 1];

@@ -239,6 +239,41 @@ def test_general_constraints_in_solver_kernels(kind):
     close(TO.max_violation(g), TO.max_violation(o), 1e-5, "violation")
 
 
+def test_mpc_update_trajectory_and_shift_match_oracle():
+    """f3 (BASELINE config 5): tracking objective re-targeted with update_trajectory!, receding-horizon shift, re-solve"""
+    r = np.random.default_rng(11)
+    n, m, N, nref, B = 13, 4, 51, 80, 6
+    hover = TO.Quadrotor().hover_control()
+    t = np.linspace(0, 4, nref)
+    Xref = np.zeros((nref, n)); Xref[:, 0] = np.sin(t); Xref[:, 1] = 0.5 * t; Xref[:, 2] = 1.0; Xref[:, 3] = 1.0
+    Uref = np.tile(hover, (nref, 1))
+    Q, R, Qf = np.full(n, 1.0), np.full(m, 0.1), np.full(n, 10.0)
+    x0 = np.tile(Xref[0], (B, 1)) + 0.05 * r.standard_normal((B, n)); x0[:, 3:7] = [1, 0, 0, 0]
+    probs = []
+    for cls in (TO.Problem, OracleProblem):
+        cons = TO.ConstraintList(n, m, N)
+        TO.add_constraint(cons, TO.ControlBound(m, u_min=0.0, u_max=8.0), (1, N - 1))
+        p = cls(TO.Quadrotor(), TO.TrackingObjective(Q, R, Xref[:N], Uref[:N - 1], Qf=Qf), x0, 2.5, constraints=cons)
+        TO.initial_controls(p, hover); TO.rollout(p)
+        probs.append(p)
+    g, o = probs
+    for start in (1, 4):
+        for p in probs:
+            if start > 1:
+                TO.shift_trajectory(p, 3)
+                TO.update_trajectory(p, Xref, Uref, start)
+                TO.set_initial_state(p, TO.states(p)[:, 0] + 0.01)       # "measured" state
+                TO.rollout(p)
+            TO.ilqr_step(p, 3); TO.al_update(p); TO.ilqr_step(p, 1)
+        close(TO.gettimes(g), TO.gettimes(o), 1e-15, "times")
+        close(TO.cost_gradient(g), TO.cost_gradient(o), KERNEL_RTOL, "tracking gradient")
+        close(TO.multipliers(g, 0), TO.multipliers(o, 0), 1e-6, "multipliers")
+        close(TO.states(g), TO.states(o), 1e-6, "X"); close(TO.controls(g), TO.controls(o), 1e-6, "U")
+        close(TO.merit(g), TO.merit(o), ITER_RTOL, "merit")
+    for p in probs:
+        p.close()
+
+
 def test_error_behaviour():
     n, m, N = 4, 1, 5
     obj = TO.LQRObjective(np.eye(n), np.eye(m), np.eye(n), np.zeros(n), N)

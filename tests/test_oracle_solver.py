@@ -146,3 +146,46 @@ def test_regularisation_restart_on_indefinite_quu():
     status = TO.backward(prob)
     assert status[0] > 0
     assert TO.solver_state(prob)["rho"][0] > 0
+
+
+def test_mpc_update_trajectory_and_shift():
+    """f3: update_trajectory!(obj, Z, start) (src/objective.jl:198-212) == a fresh TrackingObjective on the shifted window up to the
+    constant terms set_LQR_goal! leaves untouched (src/cost_functions.jl:238-254); shift_trajectory moves X, U, multipliers, x0, t0."""
+    r = np.random.default_rng(5)
+    n, m, N, nref = 4, 1, 11, 30
+    Xref, Uref = r.standard_normal((nref, n)), r.standard_normal((nref, m))
+    Q, R, Qf = np.array([1.0, 2.0, 0.5, 0.1]), np.array([0.3]), np.array([10.0, 10.0, 1.0, 1.0])
+    x0 = r.standard_normal((3, n))
+    cons = TO.ConstraintList(n, m, N)
+    TO.add_constraint(cons, TO.BoundConstraint(n, m, u_min=-2.0, u_max=2.0), (1, N - 1))
+    TO.add_constraint(cons, TO.GoalConstraint(np.zeros(n)), N)
+    prob = OracleProblem(TO.Cartpole(), TO.TrackingObjective(Q, R, Xref[:N], Uref[:N - 1], Qf=Qf), x0, 1.0, constraints=cons)
+    U0 = 0.2 * r.standard_normal((3, N - 1, m))
+    TO.initial_controls(prob, U0); TO.rollout(prob)
+    start = 7
+    TO.update_trajectory(prob, Xref, Uref, start)
+    fresh = OracleProblem(TO.Cartpole(), TO.TrackingObjective(Q, R, Xref[start - 1:start - 1 + N], Uref[start - 1:start - 2 + N], Qf=Qf), x0, 1.0)
+    TO.initial_controls(fresh, U0); TO.rollout(fresh)
+    g1, g2 = TO.cost_gradient(prob), TO.cost_gradient(fresh)
+    assert np.allclose(g1[:, :N - 1], g2[:, :N - 1], rtol=1e-13, atol=1e-13)
+    assert np.allclose(g1[:, N - 1, :n], g2[:, N - 1, :n], rtol=1e-13, atol=1e-13)      # the terminal cost has no control part
+    # c is left as is: J differs from the fresh objective by the constants of the old and new references
+    half = lambda X, W: 0.5 * np.sum(X * X * W, axis=-1)
+    c_old = half(Xref[:N - 1], Q).sum() + half(Uref[:N - 1], R).sum() + half(Xref[N - 1], Qf)
+    c_new = half(Xref[start - 1:start - 2 + N], Q).sum() + half(Uref[start - 1:start - 2 + N], R).sum() + half(Xref[start - 2 + N], Qf)
+    assert np.allclose(TO.cost(prob) - c_old, TO.cost(fresh) - c_new, rtol=1e-12)
+    with pytest.raises(TO.DimensionMismatch):
+        TO.update_trajectory(prob, Xref, Uref, nref - N + 2)
+    # shift: solve a little so multipliers are non-trivial, then shift by 2 knots
+    TO.ilqr_step(prob, 2); TO.al_update(prob)
+    X, U, t = TO.states(prob), TO.controls(prob), TO.gettimes(prob)
+    lam = TO.multipliers(prob, 0)
+    TO.shift_trajectory(prob, 2)
+    Xs, Us = TO.states(prob), TO.controls(prob)
+    assert np.array_equal(Xs[:, :N - 2], X[:, 2:]) and np.array_equal(Xs[:, N - 2:], np.repeat(X[:, -1:], 2, axis=1))
+    assert np.array_equal(Us[:, :N - 3], U[:, 2:]) and np.array_equal(Us[:, N - 3:], np.repeat(U[:, -1:], 2, axis=1))
+    ls = TO.multipliers(prob, 0)
+    assert np.array_equal(ls[:, :N - 3], lam[:, 2:]) and np.array_equal(ls[:, N - 3:], lam[:, N - 3:])
+    assert np.allclose(TO.gettimes(prob), t + (t[2] - t[0]))
+    TO.rollout(prob)                                   # x0 <- X[2]: the re-rolled trajectory starts there
+    assert np.array_equal(TO.states(prob)[:, 0], X[:, 2])

@@ -127,6 +127,7 @@ def load_library():
         "to_set_initial_state": [H, c_double_p], "to_set_controls": [H, c_double_p], "to_set_states": [H, c_double_p],
         "to_set_goal_state": [H, c_double_p, C.c_int, C.c_int], "to_set_initial_time": [H, C.c_double, c_double_p],
         "to_get_states": [H, c_double_p], "to_get_controls": [H, c_double_p], "to_get_times": [H, c_double_p],
+        "to_update_trajectory": [H, c_double_p, c_double_p, C.c_int32, C.c_int32], "to_shift_trajectory": [H, C.c_int32],
         "to_rollout": [H], "to_expand": [H], "to_get_dynamics_jacobians": [H, c_double_p],
         "to_cost": [H, c_double_p], "to_cost_knots": [H, c_double_p], "to_cost_gradient": [H, c_double_p], "to_cost_hessian": [H, c_double_p],
         "to_eval_constraints": [H, C.c_int32, c_double_p], "to_constraint_jacobians": [H, C.c_int32, c_double_p],
@@ -161,7 +162,7 @@ EXPORTED_SYMBOLS = [
     "to_get_dynamics_jacobians", "to_cost", "to_cost_knots", "to_cost_gradient", "to_cost_hessian", "to_eval_constraints",
     "to_constraint_jacobians", "to_max_violation", "to_merit", "to_al_expansion", "to_projection", "to_grad_projection",
     "to_hess_projection", "to_backward", "to_forward", "to_ilqr_step", "to_al_update", "to_get_gains", "to_get_multipliers",
-    "to_set_multipliers", "to_get_penalty", "to_set_penalty", "to_get_solver_state", "to_reduce_merit", "to_reduce_merit_async", "to_merit_device_ptr",
+    "to_set_multipliers", "to_get_penalty", "to_set_penalty", "to_get_solver_state", "to_reduce_merit", "to_reduce_merit_async", "to_merit_device_ptr", "to_update_trajectory", "to_shift_trajectory",
     "to_set_phase_timing", "to_get_phase_times", "to_launch_count", "to_algorithmic_bytes",
 ]
 

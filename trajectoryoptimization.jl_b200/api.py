@@ -679,6 +679,26 @@ def set_goal_state(prob, xf, objective=True, constraint=True):   # set_goal_stat
     prob._call("to_set_goal_state", K._dp(xf), int(objective), int(constraint))
 
 
+def update_trajectory(prob, Xref, Uref, start=1):
+    """``update_trajectory!(obj, Z, start)`` (src/objective.jl:198-212): knot ``i`` of the problem's (tracking) objective follows
+    row ``start - 1 + i`` of the reference ``Xref[nref, n]``, ``Uref[nref, m]`` -- ``set_LQR_goal!`` on every knot's cost."""
+    Xref = np.ascontiguousarray(np.asarray(Xref, dtype=np.float64)); Uref = np.ascontiguousarray(np.asarray(Uref, dtype=np.float64))
+    if Xref.ndim != 2 or Uref.ndim != 2 or Xref.shape[1] != prob.n or Uref.shape[1] != prob.m or Uref.shape[0] != Xref.shape[0]:
+        raise DimensionMismatch("update_trajectory!: Xref must be [nref, n] and Uref [nref, m]")
+    if start < 1 or start - 1 + prob.N > Xref.shape[0]:
+        raise DimensionMismatch("update_trajectory!: the reference is shorter than start + N - 1")
+    for i, k in enumerate(range(start - 1, start - 1 + prob.N)):
+        set_LQR_goal(prob.obj[i], Xref[k], Uref[k])
+    prob._call("to_update_trajectory", K._dp(Xref), K._dp(Uref), int(Xref.shape[0]), int(start))
+
+
+def shift_trajectory(prob, steps=1):
+    """Receding-horizon warm start on the device (no reference counterpart: MPC user code around Altro does this on the host):
+    ``X_k <- X_{k+steps}``, ``U_k <- U_{k+steps}`` with the tail repeated, multipliers moved with their knots,
+    ``x0 <- X_{1+steps}``, ``t0`` advanced.  Follow with ``set_initial_state`` (measured state) and ``rollout``."""
+    prob._call("to_shift_trajectory", int(steps))
+
+
 def states(prob, k=None):   # states(prob)  src/problem.jl:175
     X = np.empty((prob.B, prob.N, prob.n))
     prob._call("to_get_states", K._dp(X))

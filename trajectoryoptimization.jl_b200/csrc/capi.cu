@@ -556,6 +556,31 @@ int to_set_goal_state(to_handle* h, const double* xf, int objective, int constra
 }
 
 // ---- kernel 1 ---------------------------------------------------------------------------------------------
+int to_update_trajectory(to_handle* h, const double* Xref, const double* Uref, int32_t nref, int32_t start) {
+    JOIN(h);
+    if (!h || !Xref || !Uref) return TO_EINVAL;
+    const int n = h->P.n, m = h->P.m, N = h->P.N;
+    if (start < 1 || start - 1 + N > nref) return fail(h, TO_EDIM, "update_trajectory!: the reference is shorter than start + N - 1");
+    for (int i = 0; i < N; i++) {                       // set_LQR_goal!(obj[i], state(Z[k]), control(Z[k]))
+        DevCost& c = h->h_costs[h->h_cost_index[i]];
+        const double* xf = Xref + (size_t)(start - 1 + i) * n;
+        const double* uf = Uref + (size_t)(start - 1 + i) * m;
+        for (int a = 0; a < n; a++) { double t = 0; for (int j = 0; j < n; j++) t += c.Q[j * n + a] * xf[j]; c.q[a] = -t; }
+        for (int a = 0; a < m; a++) { double t = 0; for (int j = 0; j < m; j++) t += c.R[j * m + a] * uf[j]; c.r[a] = -t; }
+    }
+    h->J_valid = false; h->expanded = false; h->backward_done = false;
+    return upload_tables(h);
+}
+int to_shift_trajectory(to_handle* h, int32_t steps) {
+    JOIN(h);
+    if (!h || steps < 0) return TO_EINVAL;
+    if (steps == 0) return TO_OK;
+    if (steps > h->P.N - 1) steps = h->P.N - 1;
+    CU(h, launch_shift_traj(h->P, steps, h->stream)); h->launches++;
+    for (int k = 0; k < steps; k++) h->t0 += h->h_dt[k];
+    h->J_valid = false; h->expanded = false; h->backward_done = false;
+    return TO_OK;
+}
 int to_rollout(to_handle* h) {
     JOIN(h);
     if (!h) return TO_EINVAL;

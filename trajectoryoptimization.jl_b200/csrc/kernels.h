@@ -18,6 +18,7 @@ cudaError_t launch_grad_projection(int cone, int p, int count, const double* x, 
 cudaError_t launch_hess_projection(int cone, int p, int count, const double* x, const double* b, double* H, int* err, cudaStream_t s);
 cudaError_t launch_al_update(const DevProblem& P, cudaStream_t s);
 cudaError_t launch_reduce_merit(const DevProblem& P, const double* viol, double* out2, cudaStream_t s);
+cudaError_t launch_shift_traj(const DevProblem& P, int steps, cudaStream_t s);
 cudaError_t launch_gather_traj(const DevProblem& P, double* Xout, double* Uout, cudaStream_t s);
 cudaError_t launch_scatter_traj(const DevProblem& P, const double* Xin, const double* Uin, cudaStream_t s);
 cudaError_t launch_export_ab(const DevProblem& P, double* ABout, cudaStream_t s);

@@ -257,6 +257,31 @@ cudaError_t launch_reduce_merit(const DevProblem& P, const double* viol, double*
     k_reduce_merit<<<1, 1024, 0, s>>>(P.B, P.J, viol, out2);
     return cudaGetLastError();
 }
+// receding-horizon shift (to_shift_trajectory): CTA = instance; the trajectory goes to the next ring buffer, the
+// multipliers shift in place (thread = one row of one constraint, ascending knots: reads k+steps, writes k)
+__global__ void k_shift_traj(const DevProblem P, int steps) {
+    const int b = blockIdx.x, n = P.n, m = P.m, N = P.N;
+    const int src = P.cur[b], dst = (src + 1) % TO_NBUF;
+    const double* X = traj_X(P, src, b); const double* U = traj_U(P, src, b);
+    double* Xn = traj_Xw(P, dst, b); double* Un = traj_Uw(P, dst, b);
+    for (int i = threadIdx.x; i < N * n; i += blockDim.x) { int k = i / n + steps; if (k > N - 1) k = N - 1; Xn[i] = X[k * n + i % n]; }
+    for (int i = threadIdx.x; i < (N - 1) * m; i += blockDim.x) { int k = i / m + steps; if (k > N - 2) k = N - 2; Un[i] = U[k * m + i % m]; }
+    for (int i = threadIdx.x; i < n; i += blockDim.x) { int k = steps < N - 1 ? steps : N - 1; P.x0[(size_t)b * n + i] = X[k * n + i]; }
+    double* lam = P.lambda + (size_t)b * P.lambda_len;
+    for (int ci = 0; ci < P.ncon; ci++) {
+        const DevCon& c = P.cons[ci];
+        const int nk = c.last - c.first + 1;
+        for (int r = threadIdx.x; r < c.p; r += blockDim.x)
+            for (int k = 0; k + steps < nk; k++) lam[c.offset + k * c.p + r] = lam[c.offset + (k + steps) * c.p + r];
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) P.cur[b] = dst;
+}
+cudaError_t launch_shift_traj(const DevProblem& P, int steps, cudaStream_t s) {
+    k_shift_traj<<<P.B, 128, 0, s>>>(P, steps);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_gather_traj(const DevProblem& P, double* Xout, double* Uout, cudaStream_t s) {
     k_gather_traj<<<P.B, 128, 0, s>>>(P, Xout, Uout);
     return cudaGetLastError();

@@ -151,6 +151,11 @@ function max_violation(p::BatchedProblem)
     check(p.h, ccall((:to_max_violation, libb200), Cint, (Ptr{Cvoid}, Ptr{Float64}), p.h, v)); v
 end
 
+# MPC plumbing: update_trajectory!(obj, Z, start) src/objective.jl:198-212 on the batched problem; Xref (n, nref), Uref (m, nref)
+TO.update_trajectory!(p::BatchedProblem, Xref::Matrix{Float64}, Uref::Matrix{Float64}, start::Integer=1) =
+    check(p.h, ccall((:to_update_trajectory, libb200), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Int32, Int32), p.h, Xref, Uref, size(Xref, 2), start))
+shift_trajectory!(p::BatchedProblem, steps::Integer=1) = check(p.h, ccall((:to_shift_trajectory, libb200), Cint, (Ptr{Cvoid}, Int32), p.h, steps))
+
 # multi-GPU (one process per GPU, e.g. under MPI.jl + NCCL.jl): the only collective is the {sum J, max violation} all-reduce.
 # `to_reduce_merit_async` queues the per-GPU reduction behind the iteration in flight and makes `stream` (the CUDA.jl
 # stream the NCCL call is issued on) wait for it; `merit_device_ptr` is the 2-double buffer to all-reduce in place.

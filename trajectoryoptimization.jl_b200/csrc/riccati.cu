@@ -35,6 +35,21 @@
 #include "costcon.cuh"
 #include "kernels.h"
 
+#ifndef TO_RICCATI_STAGES
+#define TO_RICCATI_STAGES 2     // depth of the [A B] ring
+#endif
+#ifndef TO_RICCATI_MINB
+#define TO_RICCATI_MINB 16   // one-warp CTAs per SM of the tensor-MMA kernel (A/B: profiles/build_variants.sh)
+#endif
+
+// register cap of k_riccati: by default from the CTAs-per-SM target; TO_RICCATI_MAXREG pins it instead (ptxas rounds the
+// launch-bounds cap down to 96 for 18 CTAs although 112 fit)
+#ifdef TO_RICCATI_MAXREG
+#define TO_RICCATI_BOUNDS(MINB) __maxnreg__(TO_RICCATI_MAXREG)
+#else
+#define TO_RICCATI_BOUNDS(MINB) __launch_bounds__(32, MINB)
+#endif
+
 namespace {
 
 __host__ __device__ constexpr int even_up(int v) { return (v + 1) & ~1; }
@@ -122,9 +137,14 @@ struct RiccatiSmem {
     double S[SROWS * LDS_];
     double T[TROWS * LDT + 8];
     double Q[MMA ? 2 : even_up(NM) * LDT + 8];   // full Q only on the DFMA path
-    double Qs[(NM + 1) * LDQS];
-    double K[4 * LDK + 8];
-    double W[4 * LDK + 8];
+    // u / Qz strip of Q, gains K|d and W = Qux - rho K.  MMA path: they overlay T, which is dead once Q sits in the
+    // accumulator registers and is rewritten only by the next knot (2.2 KB per warp -> room for 18-20 warps per SM)
+    static constexpr int QS_SIZE = (NM + 1) * LDQS, KW_SIZE = 4 * LDK + 8;
+    static_assert(!MMA || QS_SIZE + 2 * KW_SIZE <= TROWS * LDT + 8, "overlay does not fit T");
+    double QKW[MMA ? 2 : QS_SIZE + 2 * KW_SIZE];
+    __device__ __forceinline__ double* qs() { return MMA ? T : QKW; }
+    __device__ __forceinline__ double* kk() { return qs() + QS_SIZE; }
+    __device__ __forceinline__ double* ww() { return kk() + KW_SIZE; }
     double g[MMA ? 2 : even_up(NM) + 2];   // lz (cost + AL gradient), padded (DFMA path; the MMA path keeps it in lane registers)
     double h[MMA ? 2 : even_up(NM) + 2];   // diag(lzz)
     // lane-indexed table of the Goal / Bound rows acting on z_lane (instance-independent, filled once per warp):
@@ -150,7 +170,7 @@ __device__ __forceinline__ uint2 pack_term(int first, int last, int base, int p,
 }
 
 template <int N_, int M_, int STAGES, bool FASTAL, bool MMA, int MINB, int NSLOT>
-__global__ void __launch_bounds__(32, MINB) k_riccati(const DevProblem P, int* __restrict__ work_counter) {
+__global__ void TO_RICCATI_BOUNDS(MINB) k_riccati(const DevProblem P, int* __restrict__ work_counter) {
     using SM = RiccatiSmem<N_, M_, STAGES, MMA>;
     constexpr int n = N_, m = M_, NM = SM::NM, LDAB = SM::LDAB, LDT = SM::LDT, NP = SM::NP, LDK = SM::LDK;
     constexpr int LDABS = SM::LDABS, LDS_ = SM::LDS_;
@@ -169,6 +189,7 @@ __global__ void __launch_bounds__(32, MINB) k_riccati(const DevProblem P, int* _
     constexpr bool NM_ODD = (NM & 1) != 0;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     SM& sm = *reinterpret_cast<SM*>(smem_raw);
+    double* const Qs_ = sm.qs(); double* const K_ = sm.kk(); double* const W_ = sm.ww();
     const int lane = threadIdx.x;
     const int N = P.N;
 
@@ -224,7 +245,7 @@ __global__ void __launch_bounds__(32, MINB) k_riccati(const DevProblem P, int* _
         (void)nterm;   // NSLOT (template) >= the largest per-lane count: launch_riccati_nm picks it from P.max_terms_per_z
     }
 
-    for (int e = lane; e < 4 * LDK + 8; e += 32) { sm.K[e] = 0.0; sm.W[e] = 0.0; }   // padding columns stay finite
+    for (int e = lane; e < 4 * LDK + 8; e += 32) { K_[e] = 0.0; W_[e] = 0.0; }   // padding columns stay finite
     if (lane == 0) {
 #pragma unroll
         for (int s = 0; s < STAGES; s++) mbar_init(&sm.bar[s], 1);
@@ -576,8 +597,8 @@ __global__ void __launch_bounds__(32, MINB) k_riccati(const DevProblem P, int* _
                                 if (col == NM) q[t][0] += grow[mi];
                                 if (col + 1 == NM) q[t][1] += grow[mi];
                                 if (row < NM) {
-                                    if (col >= n && col <= NM) sm.Qs[row * LDQS + col - n] = q[t][0];
-                                    if (col + 1 >= n && col + 1 <= NM) sm.Qs[row * LDQS + col + 1 - n] = q[t][1];
+                                    if (col >= n && col <= NM) Qs_[row * LDQS + col - n] = q[t][0];
+                                    if (col + 1 >= n && col + 1 <= NM) Qs_[row * LDQS + col + 1 - n] = q[t][1];
                                 }
                             }
                     }
@@ -594,7 +615,7 @@ __global__ void __launch_bounds__(32, MINB) k_riccati(const DevProblem P, int* _
 #pragma unroll
                         for (int a = 0; a < m; a++)
 #pragma unroll
-                            for (int c = 0; c <= a; c++) Quu[a * (a + 1) / 2 + c] = sm.Qs[(n + c) * LDQS + a];
+                            for (int c = 0; c <= a; c++) Quu[a * (a + 1) / 2 + c] = Qs_[(n + c) * LDQS + a];
 #pragma unroll
                         for (int j = 0; j < m; j++) {
                             double t = Quu[j * (j + 1) / 2 + j] + rho;
@@ -615,7 +636,7 @@ __global__ void __launch_bounds__(32, MINB) k_riccati(const DevProblem P, int* _
                         const int c = (lane <= n) ? lane : n;
                         double rhs[M_];
 #pragma unroll
-                        for (int a = 0; a < m; a++) rhs[a] = (c < n) ? sm.Qs[c * LDQS + a] : sm.Qs[(n + a) * LDQS + m];   // Qux[a][c] | Qu[a]
+                        for (int a = 0; a < m; a++) rhs[a] = (c < n) ? Qs_[c * LDQS + a] : Qs_[(n + a) * LDQS + m];   // Qux[a][c] | Qu[a]
 #pragma unroll
                         for (int a = 0; a < m; a++) {
                             double t = -rhs[a];
@@ -637,7 +658,7 @@ __global__ void __launch_bounds__(32, MINB) k_riccati(const DevProblem P, int* _
                         if (okl) {
                             if (lane <= n) {
 #pragma unroll
-                                for (int a = 0; a < m; a++) { sm.K[a * LDK + c] = kc[a]; sm.W[a * LDK + c] = wc[a]; }
+                                for (int a = 0; a < m; a++) { K_[a * LDK + c] = kc[a]; W_[a * LDK + c] = wc[a]; }
                             }
                             if (lane < n) {
 #pragma unroll
@@ -664,7 +685,7 @@ __global__ void __launch_bounds__(32, MINB) k_riccati(const DevProblem P, int* _
                     {
                         double af[MT], bk[MT];
 #pragma unroll
-                        for (int mi = 0; mi < MT; mi++) { af[mi] = (fc < m) ? sm.W[fc * LDK + 8 * mi + fr] : 0.0; bk[mi] = (fc < m) ? sm.K[fc * LDK + 8 * mi + fr] : 0.0; }
+                        for (int mi = 0; mi < MT; mi++) { af[mi] = (fc < m) ? W_[fc * LDK + 8 * mi + fr] : 0.0; bk[mi] = (fc < m) ? K_[fc * LDK + 8 * mi + fr] : 0.0; }
                         int t = 0;
 #pragma unroll
                         for (int mi = 0; mi < MQ; mi++)
@@ -676,7 +697,7 @@ __global__ void __launch_bounds__(32, MINB) k_riccati(const DevProblem P, int* _
                                 }
                             }
                         // s <- Qx + W'd : W column of lane c is in its registers, d comes from lane n
-                        double snew = (lane < n) ? sm.Qs[lane * LDQS + m] : 0.0;
+                        double snew = (lane < n) ? Qs_[lane * LDQS + m] : 0.0;
 #pragma unroll
                         for (int a = 0; a < m; a++) snew = fma(wc[a], __shfl_sync(0xffffffffu, kc[a], n), snew);
                         s_reg = snew;
@@ -813,8 +834,8 @@ __global__ void __launch_bounds__(32, MINB) k_riccati(const DevProblem P, int* _
                         if (lane <= n) {
     #pragma unroll
                             for (int a = 0; a < m; a++) {
-                                sm.K[a * LDK + c] = kc[a];
-                                sm.W[a * LDK + c] = fma(-rho, kc[a], rhs[a]);   // W = Qux - rho K
+                                K_[a * LDK + c] = kc[a];
+                                W_[a * LDK + c] = fma(-rho, kc[a], rhs[a]);   // W = Qux - rho K
                             }
                         }
                         if (lane < n) {
@@ -849,8 +870,8 @@ __global__ void __launch_bounds__(32, MINB) k_riccati(const DevProblem P, int* _
                         for (int a = 0; a < m; a++) {
     #pragma unroll
                             for (int r = 0; r < RS; r++) {
-                                const double2 w = lds128(&sm.W[a * LDK + s_a[r]]);
-                                const double2 kk = lds128(&sm.K[a * LDK + s_b[r]]);
+                                const double2 w = lds128(&W_[a * LDK + s_a[r]]);
+                                const double2 kk = lds128(&K_[a * LDK + s_b[r]]);
                                 fma2x2(acc[r], w, kk);
                             }
                         }
@@ -858,7 +879,7 @@ __global__ void __launch_bounds__(32, MINB) k_riccati(const DevProblem P, int* _
                         if (lane < n) {
                             snew = sm.Q[lane * LDT + NM];
     #pragma unroll
-                            for (int a = 0; a < m; a++) snew = fma(sm.W[a * LDK + lane], sm.K[a * LDK + n], snew);
+                            for (int a = 0; a < m; a++) snew = fma(W_[a * LDK + lane], K_[a * LDK + n], snew);
                         }
                         s_reg = snew;
     #pragma unroll
@@ -943,7 +964,7 @@ cudaError_t launch_riccati_t(const DevProblem& P, int* work_counter, cudaStream_
         if (P.all_diag_cost && P.all_diag_con) {   // tensor-MMA kernel: diagonal lzz (DiagonalCost + Goal/Bound)
             // 2-stage ring, 16 one-warp CTAs per SM (occupancy / ring-depth sweep in profiles/r01_notes.md).  NSLOT stays
             // MAXT: a build with a 2-slot loop bound measured 13 % slower than this one (scheduling), see the notes.
-            return launch_riccati_v<N_, M_, FASTAL, 2, 16, true, MAXT>(P, work_counter, s);
+            return launch_riccati_v<N_, M_, FASTAL, TO_RICCATI_STAGES, TO_RICCATI_MINB, true, MAXT>(P, work_counter, s);
         }
         return launch_riccati_v<N_, M_, FASTAL, 2, 12, false>(P, work_counter, s);   // dense costs: DFMA micro-block kernel
     } else {

@@ -109,7 +109,8 @@ typedef struct {
     double bp_reg_increase_factor, bp_reg_max, bp_reg_min, bp_reg_initial, bp_reg_fp;
     double line_search_lower_bound, line_search_upper_bound;
     int32_t iterations_linesearch;
-    int32_t reserved;
+    int32_t backward_kernel;   /* 0 = automatic; 1 = warp-per-instance Riccati kernel; 2 = thread-per-instance kernel (n <= 4, m <= 2,
+                                  Goal/Bound constraints only, else ignored). Not a solver option of the reference: a tuning / test knob. */
     double max_state_value, max_control_value;
     double penalty_initial, penalty_scaling, penalty_max, dual_max;
 } to_options;

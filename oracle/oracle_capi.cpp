@@ -133,7 +133,7 @@ int orc_default_options(to_options* o) {
     o->bp_reg_increase_factor = q.bp_reg_increase_factor; o->bp_reg_max = q.bp_reg_max; o->bp_reg_min = q.bp_reg_min;
     o->bp_reg_initial = q.bp_reg_initial; o->bp_reg_fp = q.bp_reg_fp;
     o->line_search_lower_bound = q.line_search_lower_bound; o->line_search_upper_bound = q.line_search_upper_bound;
-    o->iterations_linesearch = q.iterations_linesearch; o->reserved = 0; o->max_state_value = q.max_state_value; o->max_control_value = q.max_control_value;
+    o->iterations_linesearch = q.iterations_linesearch; o->backward_kernel = 0; o->max_state_value = q.max_state_value; o->max_control_value = q.max_control_value;
     o->penalty_initial = q.penalty_initial; o->penalty_scaling = q.penalty_scaling; o->penalty_max = q.penalty_max; o->dual_max = q.dual_max;
     return TO_OK;
 }

@@ -110,6 +110,30 @@ def test_ilqr_iterations_and_al_update(pair):
         close(TO.max_violation(g), TO.max_violation(o), 1e-5, "violation")
 
 
+@pytest.mark.parametrize("name", ["double_integrator_1d", "double_integrator_2d", "cartpole", "cartpole_altro", "acrobot_dense", "acrobot_diag"])
+@pytest.mark.parametrize("kernel", [1, 2])
+def test_small_model_riccati_kernels(name, kernel):
+    """both Riccati kernels of the small models (1 = warp per instance, 2 = thread per instance, riccati_small.cu; the automatic
+    choice switches at 2048 instances) against the oracle: gains, expected decrease, iterates, restart bookkeeping"""
+    g, o = CONFIGS[name](TO.Problem), CONFIGS[name](OracleProblem)
+    TO.set_options(g, backward_kernel=kernel)
+    for p in (g, o):
+        TO.rollout(p); TO.expand(p)
+    assert np.array_equal(TO.backward(g), TO.backward(o))
+    Kg, dg = TO.gains(g); Ko, do = TO.gains(o)
+    close(Kg, Ko, 1e-9, "K"); close(dg, do, 1e-9, "d")
+    close(TO.solver_state(g)["dV"], TO.solver_state(o)["dV"], 1e-9, "dV")
+    for p in (g, o):
+        TO.forward(p); TO.ilqr_step(p, 3)
+        if len(p.constraints):
+            TO.al_update(p); TO.ilqr_step(p, 2)
+    # converged instances take their discrete decisions on the last bits of J (see test_ilqr_iterations_and_al_update)
+    so = TO.solver_state(o)
+    live = np.abs(so["dV"][:, 0]) > 1e-9 * np.maximum(1.0, np.abs(TO.merit(o)))
+    close(TO.merit(g)[live], TO.merit(o)[live], 1e-5, "merit")
+    g.close(); o.close()
+
+
 def test_regularisation_restart_matches_oracle():
     n, m, N = 4, 1, 11
     stage = TO.DiagonalCost(np.ones(n), -0.5 * np.ones(m))
@@ -119,6 +143,11 @@ def test_regularisation_restart_matches_oracle():
         TO.rollout(p); TO.expand(p)
     sg, so = TO.backward(probs[0]), TO.backward(probs[1])
     assert np.array_equal(sg, so) and np.all(sg > 0)
+    third = TO.Problem(TO.Cartpole(), TO.Objective(stage, term, N), np.array([[0, 0.1, 0, 0], [0, -0.2, 0.1, 0]]), 0.5)
+    TO.set_options(third, backward_kernel=2); TO.rollout(third); TO.expand(third)
+    assert np.array_equal(TO.backward(third), so)                                  # thread-per-instance kernel: same restarts
+    close(TO.solver_state(third)["rho"], TO.solver_state(probs[1])["rho"], 1e-12, "rho (thread kernel)")
+    close(TO.gains(third)[0], TO.gains(probs[1])[0], 1e-9, "K (thread kernel)")
     close(TO.solver_state(probs[0])["rho"], TO.solver_state(probs[1])["rho"], 1e-12, "rho")
     Kg, dg = TO.gains(probs[0]); Ko, do = TO.gains(probs[1])
     close(Kg, Ko, 1e-9, "K"); close(dg, do, 1e-9, "d")

@@ -52,7 +52,7 @@ class to_options(C.Structure):
     _fields_ = [("bp_reg_increase_factor", C.c_double), ("bp_reg_max", C.c_double), ("bp_reg_min", C.c_double),
                 ("bp_reg_initial", C.c_double), ("bp_reg_fp", C.c_double),
                 ("line_search_lower_bound", C.c_double), ("line_search_upper_bound", C.c_double),
-                ("iterations_linesearch", C.c_int32), ("reserved", C.c_int32),
+                ("iterations_linesearch", C.c_int32), ("backward_kernel", C.c_int32),
                 ("max_state_value", C.c_double), ("max_control_value", C.c_double),
                 ("penalty_initial", C.c_double), ("penalty_scaling", C.c_double), ("penalty_max", C.c_double), ("dual_max", C.c_double)]
 

@@ -259,7 +259,7 @@ int to_default_options(to_options* o) {
     DevOptions d; set_default_options(d);
     o->bp_reg_increase_factor = d.bp_reg_increase_factor; o->bp_reg_max = d.bp_reg_max; o->bp_reg_min = d.bp_reg_min;
     o->bp_reg_initial = d.bp_reg_initial; o->bp_reg_fp = d.bp_reg_fp;
-    o->line_search_lower_bound = d.ls_lower; o->line_search_upper_bound = d.ls_upper; o->iterations_linesearch = d.ls_iters; o->reserved = 0;
+    o->line_search_lower_bound = d.ls_lower; o->line_search_upper_bound = d.ls_upper; o->iterations_linesearch = d.ls_iters; o->backward_kernel = 0;
     o->max_state_value = d.max_state_value; o->max_control_value = d.max_control_value;
     o->penalty_initial = d.penalty_initial; o->penalty_scaling = d.penalty_scaling; o->penalty_max = d.penalty_max; o->dual_max = d.dual_max;
     return TO_OK;
@@ -424,6 +424,7 @@ int to_set_options(to_handle* h, const to_options* o) {
     d.bp_reg_increase_factor = o->bp_reg_increase_factor; d.bp_reg_max = o->bp_reg_max; d.bp_reg_min = o->bp_reg_min;
     d.bp_reg_initial = o->bp_reg_initial; d.bp_reg_fp = o->bp_reg_fp;
     d.ls_lower = o->line_search_lower_bound; d.ls_upper = o->line_search_upper_bound; d.ls_iters = o->iterations_linesearch;
+    d.pad = o->backward_kernel;   // kernel choice of launch_backward (0 automatic)
     d.max_state_value = o->max_state_value; d.max_control_value = o->max_control_value;
     d.penalty_initial = o->penalty_initial; d.penalty_scaling = o->penalty_scaling; d.penalty_max = o->penalty_max; d.dual_max = o->dual_max;
     for (auto& mu : h->h_mu) mu = d.penalty_initial;

@@ -24,6 +24,8 @@ cudaError_t launch_scatter_traj(const DevProblem& P, const double* Xin, const do
 cudaError_t launch_export_ab(const DevProblem& P, double* ABout, cudaStream_t s);
 // kernel 3: Riccati backward pass                                             (riccati.cu)
 cudaError_t launch_backward(const DevProblem& P, int* work_counter, cudaStream_t s);
+bool riccati_small_supported(const DevProblem& P, bool any_batch);                     // riccati_small.cu: thread-per-instance pass for n <= 4, m <= 2
+cudaError_t launch_backward_small(const DevProblem& P, cudaStream_t s);
 // forward pass: closed-loop rollout + merit + line search                     (forward.cu)
 cudaError_t launch_forward(const DevProblem& P, cudaStream_t s);
 cudaError_t launch_ladder(const DevProblem& P, cudaStream_t s);

@@ -44,7 +44,8 @@ enum to_model_id {
 };
 
 /* QuadraticCostFunction (src/cost_functions.jl:326-347 DiagonalCost, :417-454 QuadraticCost) */
-enum to_cost_kind { TO_COST_DIAGONAL = 0, TO_COST_QUADRATIC = 1 };
+/* DiagonalQuatCost / QuatLQRCost (src/lie_costs.jl:33-95, :129-139): a DiagonalCost plus w * min(1 + q_ref'p, 1 - q_ref'p), p = x[q_ind] */
+enum to_cost_kind { TO_COST_DIAGONAL = 0, TO_COST_QUADRATIC = 1, TO_COST_DIAGONAL_QUAT = 2 };
 typedef struct {
     int32_t kind;     /* to_cost_kind */
     int32_t terminal; /* `terminal` flag of the cost (LQRObjective sets it on the last cost, src/objective.jl:154,180) */
@@ -54,6 +55,9 @@ typedef struct {
     const double* q;  /* n */
     const double* r;  /* m */
     double c;
+    double w;               /* DIAGONAL_QUAT: weight of the geodesic term */
+    const double* q_ref;    /* DIAGONAL_QUAT: reference quaternion (4, scalar first); else NULL */
+    const int32_t* q_ind;   /* DIAGONAL_QUAT: 1-based state indices of the quaternion (4); NULL = 4:7 (src/lie_costs.jl:64) */
 } to_cost_spec;
 
 /* ConstraintSense (src/cones.jl:17-61) */
@@ -68,8 +72,10 @@ enum to_con_kind {
     TO_CON_CIRCLE = 3, /* CircleConstraint :168-233  a = xc[p], b = yc[p], rad = r[p], inds = {xi, yi} (1-based) */
     TO_CON_SPHERE = 4, /* SphereConstraint :249-326  a,b,c = centers, rad, inds = {xi, yi, zi}                 */
     TO_CON_NORM = 5,   /* NormConstraint :438-521    val, inds = 1-based indices into z, sense (orthant | SOC)   */
-    TO_CON_COLLISION = 6 /* CollisionConstraint :341-389  val = radius, inds = {x1[D], x2[D]} 1-based state indices (ninds = 2D): r^2 - |x[x1]-x[x2]|^2 <= 0.
+    TO_CON_COLLISION = 6, /* CollisionConstraint :341-389  val = radius, inds = {x1[D], x2[D]} 1-based state indices (ninds = 2D): r^2 - |x[x1]-x[x2]|^2 <= 0.
                             StateBound / ControlBound :547-631 are TO_CON_BOUND with the other block unbounded. */
+    TO_CON_QUATVEC = 7   /* QuatVecEq :938-965  a = qf (4, scalar first), inds = qind (4, 1-based; NULL = 4:7): with q = normalize(x[qind]) and
+                            qf flipped when qf'q < 0, c = q[2:4] - qf[2:4]; Equality, p = 3 */
 };
 typedef struct {
     int32_t kind;        /* to_con_kind */
@@ -102,6 +108,11 @@ typedef struct {
     const int32_t* cost_index; /* N entries, 0-based index into costs (Objective.cost, src/objective.jl:27-45) */
     int32_t ncon;
     const to_constraint_spec* cons; /* ConstraintList, in add_constraint! order */
+    int32_t error_state;     /* 1: the solver kernels (backward / forward pass) work on the ERROR STATE of a Lie-group model, as Altro does when
+                                RD.errstate_dim(model) != n: the Quadrotor's quaternion (x[4:7]) contributes 3 dimensions, n_e = 12.  State-difference
+                                Jacobian G(x) = blkdiag(I3, L(q) H, I6) (Rotations.jl grad-differential), dynamics A_e = G_{k+1}' A G_k, B_e = G_{k+1}' B,
+                                cost expansion G'lxx G + grad^2-differential, dx = state_diff(xbar, x) with the Cayley map.  The reference's hooks for
+                                it: src/abstract_constraint.jl:282-303 (error_expansion! of constraint Jacobians), src/lie_costs.jl.  0: full state. */
 } to_spec;
 
 /* Solver options on the path (Altro.jl SolverOptions, restated in oracle/oracle.hpp `Options`) */
@@ -177,7 +188,15 @@ int to_backward(to_handle* h, int32_t* status /*[B] or NULL*/);               /*
 int to_forward(to_handle* h, double* J /*[B] or NULL*/, double* alpha /*[B] or NULL*/); /* closed-loop rollout + line search */
 int to_ilqr_step(to_handle* h, int32_t iters);                                /* iters x (expand, backward, forward), no host sync */
 int to_al_update(to_handle* h);                                               /* dual + penalty update */
-int to_get_gains(to_handle* h, double* K /*[B][N-1][n][m]: m x n col-major*/, double* d /*[B][N-1][m]*/);
+int to_get_gains(to_handle* h, double* K /*[B][N-1][n_e][m]: m x n_e col-major (n_e = n unless error_state)*/, double* d /*[B][N-1][m]*/);
+/* ---- Lie-group error state ------------------------------------------------------------------- */
+int to_error_state_dim(const to_handle* h, int32_t* ne);                      /* RD.errstate_dim(model): n, or n - 1 with spec.error_state */
+/* RD.state_diff(model, xbar, x) of every knot against the current trajectory: Xbar [B][N][n] (host) -> dx [B][N][n_e] */
+int to_state_diff(to_handle* h, const double* Xbar, double* dx);
+/* error-state dynamics Jacobians [A_e B_e] = G_{k+1}' [A G_k | B] after to_expand: [B][N-1][n_e+m][n_e], n_e x (n_e+m) col-major */
+int to_get_error_dynamics(to_handle* h, double* ABe);
+/* error-state cost + AL expansion of every knot (Altro error_expansion!): grad [B][N][n_e+m], hess [B][N][n_e+m][n_e+m] */
+int to_error_expansion(to_handle* h, double* grad, double* hess);
 int to_get_multipliers(to_handle* h, int32_t con, double* lambda /*[B][last-first+1][p]*/);
 int to_set_multipliers(to_handle* h, int32_t con, const double* lambda);
 int to_get_penalty(to_handle* h, int32_t con, double* mu);

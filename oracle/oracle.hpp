@@ -48,6 +48,11 @@ struct Cost {
     std::vector<double> H;  // m*n col-major
     std::vector<double> q, r;
     double c = 0;
+    // DiagonalQuatCost (src/lie_costs.jl:33-56): + w * min(1 + q_ref'p, 1 - q_ref'p), p = x[q_ind]
+    bool quat = false;
+    double w = 0;
+    double q_ref[4] = {1, 0, 0, 0};
+    int q_ind[4] = {3, 4, 5, 6};   // 0-based
 };
 
 // RD.evaluate(::QuadraticCostFunction, x, u)  src/cost_functions.jl:89-104.  `has_u == false` is the
@@ -81,6 +86,11 @@ inline double cost_value(const Cost& c, const double* x, const double* u, bool h
             J += h;
         }
     }
+    if (c.quat) {   // RD.evaluate(::DiagonalQuatCost)  src/lie_costs.jl:68-77
+        double dq = 0;
+        for (int i = 0; i < 4; i++) dq += c.q_ref[i] * x[c.q_ind[i]];
+        J += c.w * std::min(1 + dq, 1 - dq);
+    }
     return J;
 }
 
@@ -91,6 +101,11 @@ inline void cost_gradient(const Cost& c, const double* x, const double* u, bool 
         double g = c.q[i];
         for (int j = 0; j < n; j++) g += c.Q[j * n + i] * x[j];
         grad[i] = g;
+    }
+    if (c.quat) {   // gradient!(::DiagonalQuatCost)  src/lie_costs.jl:79-95: Qx -+ w Iq q_ref by the sign of q_ref'p
+        double dq = 0;
+        for (int i = 0; i < 4; i++) dq += c.q_ref[i] * x[c.q_ind[i]];
+        for (int i = 0; i < 4; i++) grad[c.q_ind[i]] += (dq < 0 ? c.w : -c.w) * c.q_ref[i];
     }
     if (!is_terminal) {
         for (int i = 0; i < m; i++) {
@@ -242,7 +257,7 @@ inline int hess_projection(int cone, const double* x, const double* b, int p, do
 
 // ------------------------------------------------------------------------------------------------
 // Constraints  (src/constraints.jl).  All are functions of one knot z = [x;u].
-enum ConKind { CON_GOAL = 0, CON_BOUND = 1, CON_LINEAR = 2, CON_CIRCLE = 3, CON_SPHERE = 4, CON_NORM = 5, CON_COLLISION = 6 };
+enum ConKind { CON_GOAL = 0, CON_BOUND = 1, CON_LINEAR = 2, CON_CIRCLE = 3, CON_SPHERE = 4, CON_NORM = 5, CON_COLLISION = 6, CON_QUATVEC = 7 };
 
 struct Constraint {
     int kind = CON_GOAL;
@@ -326,6 +341,15 @@ inline void con_evaluate(const Constraint& con, const double* x, const double* u
             c[0] = s;
             break;
         }
+        case CON_QUATVEC: {  // QuatVecEq  src/constraints.jl:947-956: q = normalize(x[qind]); qf *= -1 when qf'q < 0; -(qf[2:4] - q[2:4])
+            double q[4], nrm = 0, dq = 0;
+            for (int i = 0; i < 4; i++) { q[i] = x[con.inds[i]]; nrm += q[i] * q[i]; }
+            nrm = std::sqrt(nrm);
+            for (int i = 0; i < 4; i++) { q[i] /= nrm; dq += con.a[i] * q[i]; }
+            const double sg = dq < 0 ? -1.0 : 1.0;
+            for (int i = 0; i < 3; i++) c[i] = -(sg * con.a[i + 1] - q[i + 1]);
+            break;
+        }
     }
 }
 
@@ -378,6 +402,15 @@ inline void con_jacobian(const Constraint& con, const double* x, const double* u
             }
             break;
         }
+        case CON_QUATVEC: {  // ForwardAD of the above (src/constraints.jl:938,962): d normalize(q)/dq = (I - qh qh')/|q|, rows 2:4
+            double q[4], nrm = 0;
+            for (int i = 0; i < 4; i++) { q[i] = x[con.inds[i]]; nrm += q[i] * q[i]; }
+            nrm = std::sqrt(nrm);
+            for (int i = 0; i < 4; i++) q[i] /= nrm;
+            for (int j = 0; j < 4; j++)
+                for (int i = 0; i < 3; i++) jac[con.inds[j] * p + i] = ((i + 1 == j ? 1.0 : 0.0) - q[i + 1] * q[j]) / nrm;
+            break;
+        }
     }
 }
 
@@ -403,6 +436,11 @@ struct Options {
 struct Problem {
     ModelParams model;
     int n = 0, m = 0, N = 0, B = 0;
+    // Lie-group error state (to_spec.error_state): the Riccati recursion, the gains and the feedback act on ne = n - 1 dimensions,
+    // the quaternion x[qs..qs+3] contributing its 3-dimensional differential (Altro.jl + RobotDynamics LieState, restated below)
+    bool lie = false;
+    int ne = 0, qs = 3;
+    std::vector<double> ABe;       // B*(N-1)*ne*(ne+m): [A_e B_e] = G_{k+1}' [A G_k | B]
     std::vector<double> dt;        // N-1
     double t0 = 0;
     std::vector<Cost> costs;
@@ -429,6 +467,7 @@ struct Problem {
 
     void finalize() {
         n = model.n; m = model.m;
+        ne = lie ? n - 1 : n;
         con_offset.clear(); lambda_len = 0;
         for (auto& c : cons) { con_offset.push_back(lambda_len); lambda_len += c.nknots() * c.p; }
         mu.assign(cons.size(), opts.penalty_initial);
@@ -437,7 +476,8 @@ struct Problem {
         U.assign((size_t)B * (N - 1) * m, 0.0);                                  // U0 = 0,   src/problem.jl:84
         Xc = X; Uc = U;
         AB.assign((size_t)B * (N - 1) * n * (n + m), 0.0);
-        K.assign((size_t)B * (N - 1) * m * n, 0.0);
+        ABe.assign(lie ? (size_t)B * (N - 1) * ne * (ne + m) : 0, 0.0);
+        K.assign((size_t)B * (N - 1) * m * ne, 0.0);
         d.assign((size_t)B * (N - 1) * m, 0.0);
         lambda.assign((size_t)B * lambda_len, 0.0);
         rho.assign(B, opts.bp_reg_initial); drho.assign(B, 0.0);
@@ -448,10 +488,99 @@ struct Problem {
     double* Xb(int b) { return &X[(size_t)b * N * n]; }
     double* Ub(int b) { return &U[(size_t)b * (N - 1) * m]; }
     double* ABb(int b) { return &AB[(size_t)b * (N - 1) * n * (n + m)]; }
-    double* Kb(int b) { return &K[(size_t)b * (N - 1) * m * n]; }
+    double* ABeb(int b) { return &ABe[(size_t)b * (N - 1) * ne * (ne + m)]; }
+    double* Kb(int b) { return &K[(size_t)b * (N - 1) * m * ne]; }
     double* db(int b) { return &d[(size_t)b * (N - 1) * m]; }
     double* lamb(int b) { return &lambda[(size_t)b * lambda_len]; }
 };
+
+// ------------------------------------------------------------------------------------------------
+// Lie-group error state.  None of this arithmetic is under /root/reference (RobotDynamics.jl LieState / Rotations.jl / Altro.jl);
+// restated from their published formulas -- PARITY UNPINNED, checked in tests/ against finite differences of the group operation.
+//   grad-differential(q) = L(q) H  (4 x 3, Rotations.jl): d/dphi of q (x) cayley(phi) at phi = 0; columns (-x,w,z,-y), (-y,-z,w,x), (-z,y,-x,w)
+//   grad^2-differential(q, b) = -(q'b) I3
+//   state_diff(xbar, x): vector parts xbar - x; rotation part = inverse Cayley map of q^-1 (x) qbar = vec / scalar
+//   (the reference's own hook: error_expansion! multiplies constraint Jacobians by G, src/abstract_constraint.jl:282-303)
+inline void quat_G(const double* q, double* G /*4x3 col-major*/) {
+    const double w = q[0], x = q[1], y = q[2], z = q[3];
+    G[0] = -x; G[1] = w;  G[2] = z;  G[3] = -y;
+    G[4] = -y; G[5] = -z; G[6] = w;  G[7] = x;
+    G[8] = -z; G[9] = y;  G[10] = -x; G[11] = w;
+}
+// dx[ne] = state_diff(xbar, x)
+inline void state_diff(const Problem& P, const double* xbar, const double* x, double* dx) {
+    if (!P.lie) { for (int i = 0; i < P.n; i++) dx[i] = xbar[i] - x[i]; return; }
+    const int qs = P.qs;
+    for (int i = 0; i < qs; i++) dx[i] = xbar[i] - x[i];
+    const double* q = x + qs; const double* p = xbar + qs;       // dq = conj(q) (x) p
+    const double dw = q[0] * p[0] + q[1] * p[1] + q[2] * p[2] + q[3] * p[3];
+    const double d1 = q[0] * p[1] - p[0] * q[1] - (q[2] * p[3] - q[3] * p[2]);
+    const double d2 = q[0] * p[2] - p[0] * q[2] - (q[3] * p[1] - q[1] * p[3]);
+    const double d3 = q[0] * p[3] - p[0] * q[3] - (q[1] * p[2] - q[2] * p[1]);
+    dx[qs] = d1 / dw; dx[qs + 1] = d2 / dw; dx[qs + 2] = d3 / dw;
+    for (int i = qs + 4; i < P.n; i++) dx[i - 1] = xbar[i] - x[i];
+}
+// row index map error state -> full state outside the quaternion
+inline int lie_full_index(const Problem& P, int e) { return e < P.qs ? e : e + 1; }
+
+// M (rows x n, col-major, leading dim ld) times E(x) = blkdiag(I, G(q), I): out (rows x ne, leading dim ldo)
+inline void times_E(const Problem& P, const double* x, const double* M, int rows, int ld, double* out, int ldo) {
+    double G[12]; quat_G(x + P.qs, G);
+    for (int e = 0; e < P.ne; e++) {
+        if (e >= P.qs && e < P.qs + 3) {
+            const double* g = &G[(e - P.qs) * 4];
+            for (int i = 0; i < rows; i++) {
+                double t = 0;
+                for (int r = 0; r < 4; r++) t += M[(P.qs + r) * ld + i] * g[r];
+                out[e * ldo + i] = t;
+            }
+        } else {
+            const int j = lie_full_index(P, e);
+            for (int i = 0; i < rows; i++) out[e * ldo + i] = M[j * ld + i];
+        }
+    }
+}
+// E(x)' times M (n x cols, col-major, leading dim ld): out (ne x cols, leading dim ldo)
+inline void Et_times(const Problem& P, const double* x, const double* M, int cols, int ld, double* out, int ldo) {
+    double G[12]; quat_G(x + P.qs, G);
+    for (int j = 0; j < cols; j++)
+        for (int e = 0; e < P.ne; e++) {
+            if (e >= P.qs && e < P.qs + 3) {
+                const double* g = &G[(e - P.qs) * 4];
+                double t = 0;
+                for (int r = 0; r < 4; r++) t += g[r] * M[j * ld + P.qs + r];
+                out[j * ldo + e] = t;
+            } else out[j * ldo + e] = M[j * ld + lie_full_index(P, e)];
+        }
+}
+// Altro error_expansion!(D, model, G): A_e = G_{k+1}' A G_k, B_e = G_{k+1}' B.  AB: n x (n+m), ABe: ne x (ne+m), both col-major
+inline void error_dynamics(const Problem& P, const double* xk, const double* xk1, const double* AB, double* ABe) {
+    const int n = P.n, m = P.m, ne = P.ne;
+    double tmp[MAXN * (MAXN + MAXM)];                      // [A G_k | B] : n x (ne+m)
+    times_E(P, xk, AB, n, n, tmp, n);
+    for (int j = 0; j < m; j++) for (int i = 0; i < n; i++) tmp[(ne + j) * n + i] = AB[(n + j) * n + i];
+    Et_times(P, xk1, tmp, ne + m, n, ABe, ne);
+}
+// Altro error_expansion!(E, Q, model, Z, G) on the full-state expansion (grad[n+m], hess (n+m)^2) of knot x:
+//   E.x = G'q ; E.u = r ; E.xx = G'Q G + grad^2-differential(x, q) ; E.ux = H G ; E.uu = R.   Output (ne+m) sized, col-major symmetric.
+inline void error_expansion(const Problem& P, const double* x, const double* grad, const double* hess, double* ge, double* He) {
+    const int n = P.n, m = P.m, nm = n + m, ne = P.ne, nme = ne + m;
+    double T1[(MAXN + MAXM) * (MAXN + MAXM)], T2[(MAXN + MAXM) * (MAXN + MAXM)];
+    // columns: hess (nm x nm) * blkdiag(E, I_m) -> T1 (nm x nme)
+    times_E(P, x, hess, nm, nm, T1, nm);
+    for (int j = 0; j < m; j++) for (int i = 0; i < nm; i++) T1[(ne + j) * nm + i] = hess[(n + j) * nm + i];
+    // rows: blkdiag(E, I_m)' * T1 -> He (nme x nme); the u rows are copied
+    Et_times(P, x, T1, nme, nm, T2, nme);
+    for (int j = 0; j < nme; j++) {
+        for (int e = 0; e < ne; e++) He[j * nme + e] = T2[j * nme + e];
+        for (int a = 0; a < m; a++) He[j * nme + ne + a] = T1[j * nm + n + a];
+    }
+    Et_times(P, x, grad, 1, nm, ge, nme);
+    for (int a = 0; a < m; a++) ge[ne + a] = grad[n + a];
+    double qb = 0;
+    for (int r = 0; r < 4; r++) qb += x[P.qs + r] * grad[P.qs + r];
+    for (int i = 0; i < 3; i++) He[(P.qs + i) * nme + P.qs + i] -= qb;
+}
 
 // rollout!  src/problem.jl:334-340
 inline void rollout(Problem& P, int b) {
@@ -563,8 +692,10 @@ inline void dynamics_jacobian(const ModelParams& mp, const double* x, const doub
 }
 inline void expand_dynamics(Problem& P, int b) {
     const int n = P.n, m = P.m;
-    for (int k = 0; k < P.N - 1; k++)
+    for (int k = 0; k < P.N - 1; k++) {
         dynamics_jacobian(P.model, &P.Xb(b)[k * n], &P.Ub(b)[k * m], P.dt[k], &P.ABb(b)[(size_t)k * n * (n + m)]);
+        if (P.lie) error_dynamics(P, &P.Xb(b)[k * n], &P.Xb(b)[(k + 1) * n], &P.ABb(b)[(size_t)k * n * (n + m)], &P.ABeb(b)[(size_t)k * P.ne * (P.ne + m)]);
+    }
 }
 
 // Cost expansion of knot k (0-based) including the AL terms:
@@ -646,23 +777,31 @@ inline void reg_decrease(const Options& o, double& rho, double& drho) {
 //   S <- Qxx + K'Quu K + K'Qux + Qux'K (symmetrised) ; s <- Qx + K'Quu d + K'Qu + Qux'd
 //   dV += (d'Qu, 1/2 d'Quu d)
 // A non-positive Cholesky pivot of Quu + rho I increases rho and restarts from the terminal knot.
+// With the Lie-group error state (P.lie) the same recursion runs on n = ne dimensions: [A B] -> [A_e B_e] (error_dynamics),
+// the expansion of every knot -> error_expansion of the full-state one.
 inline int backward_pass(Problem& P, int b) {
-    const int n = P.n, m = P.m, nm = n + m, N = P.N;
+    const int n = P.ne, m = P.m, nm = n + m, N = P.N, nf = P.n, nmf = nf + m;
     const double* X = P.Xb(b); const double* U = P.Ub(b); const double* lam = P.lamb(b);
     double* Kall = P.Kb(b); double* dall = P.db(b);
+    std::vector<double> gradF(nmf), hessF((size_t)nmf * nmf);
+    auto knot_expansion = [&](int k, double* g, double* H) {
+        if (!P.lie) { cost_expansion(P, X, U, lam, k, g, H); return; }
+        cost_expansion(P, X, U, lam, k, gradF.data(), hessF.data());
+        error_expansion(P, &X[k * nf], gradF.data(), hessF.data(), g, H);
+    };
     std::vector<double> grad(nm), hess((size_t)nm * nm), S((size_t)n * n), s(n), Sn((size_t)n * n), sn(n);
     std::vector<double> SAB((size_t)n * nm), Qzz((size_t)nm * nm), Qz(nm), L((size_t)m * m), Kd((size_t)m * (n + 1));
     std::vector<double> QuuK((size_t)m * n), Quud(m);
     int restarts = 0;
     for (;;) {
-        cost_expansion(P, X, U, lam, N - 1, grad.data(), hess.data());
+        knot_expansion(N - 1, grad.data(), hess.data());
         for (int j = 0; j < n; j++) { s[j] = grad[j]; for (int i = 0; i < n; i++) S[j * n + i] = hess[j * nm + i]; }
         double dV1 = 0, dV2 = 0;
         bool ok = true;
         const double rho = P.rho[b];
         for (int k = N - 2; k >= 0; k--) {
-            const double* AB = &P.ABb(b)[(size_t)k * n * nm];
-            cost_expansion(P, X, U, lam, k, grad.data(), hess.data());
+            const double* AB = P.lie ? &P.ABeb(b)[(size_t)k * n * nm] : &P.ABb(b)[(size_t)k * n * nm];
+            knot_expansion(k, grad.data(), hess.data());
             // SAB = S * [A B]
             for (int j = 0; j < nm; j++)
                 for (int i = 0; i < n; i++) {
@@ -752,16 +891,16 @@ inline int backward_pass(Problem& P, int b) {
 //   dx = xbar_k - x_k ; ubar_k = u_k + K_k dx + alpha d_k ; xbar_{k+1} = f(xbar_k, ubar_k)
 // returns false when a state/control exceeds max_state_value / max_control_value (or is NaN).
 inline bool forward_rollout(const Problem& P, int b, double alpha, double* Xc, double* Uc) {
-    const int n = P.n, m = P.m, N = P.N;
+    const int n = P.n, m = P.m, N = P.N, ne = P.ne;
     const double* X = &P.X[(size_t)b * N * n]; const double* U = &P.U[(size_t)b * (N - 1) * m];
-    const double* K = &P.K[(size_t)b * (N - 1) * m * n]; const double* d = &P.d[(size_t)b * (N - 1) * m];
+    const double* K = &P.K[(size_t)b * (N - 1) * m * ne]; const double* d = &P.d[(size_t)b * (N - 1) * m];
     for (int i = 0; i < n; i++) Xc[i] = P.x0[(size_t)b * n + i];
     for (int k = 0; k < N - 1; k++) {
         double dx[MAXN];
-        for (int i = 0; i < n; i++) dx[i] = Xc[k * n + i] - X[k * n + i];
+        state_diff(P, &Xc[k * n], &X[k * n], dx);     // RD.state_diff(model, xbar, x): plain difference without a Lie group
         for (int a = 0; a < m; a++) {
             double t = U[k * m + a] + alpha * d[k * m + a];
-            for (int i = 0; i < n; i++) t += K[(size_t)k * m * n + i * m + a] * dx[i];
+            for (int i = 0; i < ne; i++) t += K[(size_t)k * m * ne + i * m + a] * dx[i];
             Uc[k * m + a] = t;
             if (!(std::fabs(t) <= P.opts.max_control_value)) return false;
         }

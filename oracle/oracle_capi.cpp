@@ -45,7 +45,15 @@ int orc_create(const to_spec* s, orc_handle** out) {
     const int n = mp.n, m = mp.m;
     for (int i = 0; i < s->ncost; i++) {
         const to_cost_spec& tc = s->costs[i];
-        Cost c; c.n = n; c.m = m; c.diag = (tc.kind == TO_COST_DIAGONAL); c.terminal = tc.terminal != 0; c.c = tc.c;
+        Cost c; c.n = n; c.m = m; c.diag = (tc.kind == TO_COST_DIAGONAL || tc.kind == TO_COST_DIAGONAL_QUAT); c.terminal = tc.terminal != 0; c.c = tc.c;
+        if (tc.kind == TO_COST_DIAGONAL_QUAT) {
+            if (!tc.q_ref) { delete h; return fail(nullptr, TO_EINVAL, "DiagonalQuatCost: null q_ref"); }
+            c.quat = true; c.w = tc.w;
+            for (int j = 0; j < 4; j++) {
+                c.q_ref[j] = tc.q_ref[j]; c.q_ind[j] = tc.q_ind ? tc.q_ind[j] - 1 : 3 + j;
+                if (c.q_ind[j] < 0 || c.q_ind[j] >= n) { delete h; return fail(nullptr, TO_EDIM, "DiagonalQuatCost: q_ind outside the state"); }
+            }
+        }
         c.Q.assign((size_t)n * n, 0.0); c.R.assign((size_t)m * m, 0.0); c.H.assign((size_t)m * n, 0.0);
         c.q.assign(tc.q, tc.q + n); c.r.assign(tc.r, tc.r + m);
         if (c.diag) {
@@ -105,9 +113,21 @@ int orc_create(const to_spec* s, orc_handle** out) {
                 c.sense = CONE_NEGATIVE_ORTHANT; c.val = tc.val; c.p = 1;
                 for (int j = 0; j < tc.ninds; j++) c.inds.push_back(tc.inds[j] - 1);
                 break;
+            case TO_CON_QUATVEC:
+                if (!tc.a || n < 4) { delete h; return fail(nullptr, TO_EINVAL, "QuatVecEq: null qf"); }
+                c.sense = CONE_ZERO; c.p = 3; c.a.assign(tc.a, tc.a + 4);
+                for (int j = 0; j < 4; j++) {
+                    c.inds.push_back((tc.inds && tc.ninds == 4) ? tc.inds[j] - 1 : 3 + j);
+                    if (c.inds[j] < 0 || c.inds[j] >= n) { delete h; return fail(nullptr, TO_EDIM, "QuatVecEq: qind outside the state"); }
+                }
+                break;
             default: delete h; return fail(nullptr, TO_EINVAL, "unknown constraint kind");
         }
         P.cons.push_back(c);
+    }
+    if (s->error_state) {
+        if (s->model != MODEL_QUADROTOR) { delete h; return fail(nullptr, TO_EINVAL, "error_state: the model has no Lie-group state (only the Quadrotor does)"); }
+        P.lie = true; P.qs = 3;
     }
     P.finalize();
     *out = h;
@@ -379,6 +399,34 @@ int orc_discrete_jacobian(int model, int dim, const double* params, int nparams,
     ModelParams mp = default_model(model, dim);
     if (params) for (int i = 0; i < nparams && i < 16; i++) mp.p[i] = params[i];
     dynamics_jacobian(mp, x, u, h, AB);
+    return TO_OK;
+}
+
+// ---- Lie-group error state -----------------------------------------------------------------------------------
+int orc_error_state_dim(orc_handle* h, int32_t* ne) { *ne = h->P.ne; return TO_OK; }
+int orc_state_diff(orc_handle* h, const double* Xbar, double* dx) {
+    Problem& P = h->P;
+    for (int b = 0; b < P.B; b++)
+        for (int k = 0; k < P.N; k++) state_diff(P, &Xbar[((size_t)b * P.N + k) * P.n], &P.Xb(b)[k * P.n], &dx[((size_t)b * P.N + k) * P.ne]);
+    return TO_OK;
+}
+int orc_get_error_dynamics(orc_handle* h, double* ABe) {
+    Problem& P = h->P;
+    if (P.lie) std::memcpy(ABe, P.ABe.data(), sizeof(double) * P.ABe.size());
+    else std::memcpy(ABe, P.AB.data(), sizeof(double) * P.AB.size());
+    return TO_OK;
+}
+int orc_error_expansion(orc_handle* h, double* grad, double* hess) {
+    Problem& P = h->P; const int nm = P.n + P.m, nme = P.ne + P.m;
+    if (!P.lie) return orc_al_expansion(h, grad, hess);
+#pragma omp parallel for schedule(static)
+    for (int b = 0; b < P.B; b++) {
+        std::vector<double> g(nm), H((size_t)nm * nm);
+        for (int k = 0; k < P.N; k++) {
+            cost_expansion(P, P.Xb(b), P.Ub(b), P.lamb(b), k, g.data(), H.data());
+            error_expansion(P, &P.Xb(b)[k * P.n], g.data(), H.data(), &grad[((size_t)b * P.N + k) * nme], &hess[((size_t)b * P.N + k) * nme * nme]);
+        }
+    }
     return TO_OK;
 }
 

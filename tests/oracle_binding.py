@@ -53,6 +53,9 @@ class OracleProblem(TO.Problem):
         if rc:
             raise TO.TrajOptError(self._lib.orc_last_error(self._h).decode())
 
+    def _default_options(self, o):
+        self._lib.orc_default_options(C.byref(o))
+
     def close(self):
         if getattr(self, "_h", None):
             self._lib.orc_destroy(self._h)

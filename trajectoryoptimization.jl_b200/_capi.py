@@ -21,9 +21,9 @@ LIB_PATH = os.environ.get("LIBTRAJOPT_B200") or os.path.join(_HERE, "libtrajopt_
 TO_OK, TO_EINVAL, TO_EDIM, TO_ECUDA, TO_ENOMEM, TO_ESTATE, TO_ECONE = 0, -1, -2, -3, -4, -5, -6
 
 MODEL_DOUBLE_INTEGRATOR, MODEL_CARTPOLE, MODEL_QUADROTOR, MODEL_ACROBOT = 0, 1, 2, 3
-COST_DIAGONAL, COST_QUADRATIC = 0, 1
+COST_DIAGONAL, COST_QUADRATIC, COST_DIAGONAL_QUAT = 0, 1, 2
 CONE_ZERO, CONE_NEGATIVE_ORTHANT, CONE_SECOND_ORDER, CONE_IDENTITY, CONE_POSITIVE_ORTHANT = 0, 1, 2, 3, 4
-CON_GOAL, CON_BOUND, CON_LINEAR, CON_CIRCLE, CON_SPHERE, CON_NORM, CON_COLLISION = 0, 1, 2, 3, 4, 5, 6
+CON_GOAL, CON_BOUND, CON_LINEAR, CON_CIRCLE, CON_SPHERE, CON_NORM, CON_COLLISION, CON_QUATVEC = 0, 1, 2, 3, 4, 5, 6, 7
 PHASE_EXPAND, PHASE_BACKWARD, PHASE_FORWARD, PHASE_LADDER, PHASE_ACCEPT, PHASE_COUNT = 0, 1, 2, 3, 4, 8
 
 c_double_p = C.POINTER(C.c_double)
@@ -32,7 +32,7 @@ c_int32_p = C.POINTER(C.c_int32)
 
 class to_cost_spec(C.Structure):
     _fields_ = [("kind", C.c_int32), ("terminal", C.c_int32), ("Q", c_double_p), ("R", c_double_p), ("H", c_double_p),
-                ("q", c_double_p), ("r", c_double_p), ("c", C.c_double)]
+                ("q", c_double_p), ("r", c_double_p), ("c", C.c_double), ("w", C.c_double), ("q_ref", c_double_p), ("q_ind", c_int32_p)]
 
 
 class to_constraint_spec(C.Structure):
@@ -45,7 +45,7 @@ class to_spec(C.Structure):
     _fields_ = [("model", C.c_int32), ("n", C.c_int32), ("m", C.c_int32), ("N", C.c_int32), ("B", C.c_int32),
                 ("device", C.c_int32), ("nparams", C.c_int32), ("params", c_double_p), ("dt", c_double_p), ("t0", C.c_double),
                 ("ncost", C.c_int32), ("costs", C.POINTER(to_cost_spec)), ("cost_index", c_int32_p),
-                ("ncon", C.c_int32), ("cons", C.POINTER(to_constraint_spec))]
+                ("ncon", C.c_int32), ("cons", C.POINTER(to_constraint_spec)), ("error_state", C.c_int32)]
 
 
 class to_options(C.Structure):
@@ -72,7 +72,7 @@ def _f64(a):
 class Spec:
     """Owns the numpy buffers behind a ``to_spec`` so the pointers stay valid."""
 
-    def __init__(self, model, n, m, N, B, dt, costs, cost_index, cons, params=None, t0=0.0, device=0):
+    def __init__(self, model, n, m, N, B, dt, costs, cost_index, cons, params=None, t0=0.0, device=0, error_state=False):
         self.keep = []
         self.model, self.n, self.m, self.N, self.B = int(model), int(n), int(m), int(N), int(B)
         dt = _f64(dt)
@@ -83,8 +83,11 @@ class Spec:
             if c["kind"] == COST_QUADRATIC:   # column-major for the ABI
                 Q = np.ascontiguousarray(Q.T); R = np.ascontiguousarray(R.T)
                 H = None if H is None else np.ascontiguousarray(H.T)
-            self.keep += [Q, R, H, q, r]
-            cs[i] = to_cost_spec(c["kind"], int(c.get("terminal", False)), _dp(Q), _dp(R), _dp(H), _dp(q), _dp(r), float(c.get("c", 0.0)))
+            q_ref = _f64(c.get("q_ref"))
+            q_ind = None if c.get("q_ind") is None else np.ascontiguousarray(np.asarray(c["q_ind"], dtype=np.int32))
+            self.keep += [Q, R, H, q, r, q_ref, q_ind]
+            cs[i] = to_cost_spec(c["kind"], int(c.get("terminal", False)), _dp(Q), _dp(R), _dp(H), _dp(q), _dp(r), float(c.get("c", 0.0)),
+                                 float(c.get("w", 0.0)), _dp(q_ref), _ip(q_ind))
         ci = np.ascontiguousarray(np.asarray(cost_index, dtype=np.int32))
         self.keep.append(ci)
         ks = (to_constraint_spec * max(1, len(cons)))()
@@ -100,7 +103,8 @@ class Spec:
         p = _f64(params)
         self.keep += [cs, ks, p]
         self.c = to_spec(self.model, self.n, self.m, self.N, self.B, int(device), 0 if p is None else len(p), _dp(p), _dp(dt), float(t0),
-                         len(costs), cs, _ip(ci), len(cons), ks)
+                         len(costs), cs, _ip(ci), len(cons), ks, int(bool(error_state)))
+        self.error_state = bool(error_state)
         self.costs, self.cost_index, self.cons, self.dt = costs, list(cost_index), cons, dt
 
 
@@ -142,6 +146,8 @@ def load_library():
         "to_reduce_merit": [H], "to_reduce_merit_async": [H, C.c_void_p], "to_merit_device_ptr": [H, C.POINTER(C.c_void_p)],
         "to_set_phase_timing": [H, C.c_int], "to_get_phase_times": [H, c_double_p, C.POINTER(C.c_int64), C.c_int],
         "to_algorithmic_bytes": [H, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64)],
+        "to_error_state_dim": [H, c_int32_p], "to_state_diff": [H, c_double_p, c_double_p], "to_get_error_dynamics": [H, c_double_p],
+        "to_error_expansion": [H, c_double_p, c_double_p],
     }
     for name, args in sig.items():
         fn = getattr(lib, name)
@@ -164,6 +170,7 @@ EXPORTED_SYMBOLS = [
     "to_hess_projection", "to_backward", "to_forward", "to_ilqr_step", "to_al_update", "to_get_gains", "to_get_multipliers",
     "to_set_multipliers", "to_get_penalty", "to_set_penalty", "to_get_solver_state", "to_reduce_merit", "to_reduce_merit_async", "to_merit_device_ptr", "to_update_trajectory", "to_shift_trajectory",
     "to_set_phase_timing", "to_get_phase_times", "to_launch_count", "to_algorithmic_bytes",
+    "to_error_state_dim", "to_state_diff", "to_get_error_dynamics", "to_error_expansion",
 ]
 
 

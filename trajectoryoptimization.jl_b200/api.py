@@ -125,6 +125,9 @@ class _Model:
     def dims(self):
         return self.n, self.m
 
+    def errstate_dim(self):   # RD.errstate_dim(model) == state_dim for vector-space models
+        return self.n
+
 
 class DoubleIntegrator(_Model):
     model_id = K.MODEL_DOUBLE_INTEGRATOR
@@ -148,6 +151,10 @@ class Quadrotor(_Model):
     def __init__(self, mass=0.5, J=(0.0023, 0.0023, 0.004), gravity=(0.0, 0.0, -9.81), motor_dist=0.1750, kf=1.0, km=0.0245):
         self.params = [mass, *J, *gravity, motor_dist, kf, km]
         self.mass, self.gravity = mass, gravity
+
+    def errstate_dim(self):
+        """``RD.errstate_dim(model)``: the quaternion contributes 3 dimensions (RobotDynamics LieState)."""
+        return 12
 
     def hover_control(self):
         """zeros(model)[2] of RobotZoo.Quadrotor: thrust that cancels gravity (test/internal_api.jl:37)."""
@@ -198,6 +205,8 @@ class QuadraticCostFunction:
         return type(self)(self.Q, self.R, H=self.H, q=self.q, r=self.r, c=self.c, terminal=self.terminal)
 
     def __add__(self, other):   # +(c1, c2)  src/cost_functions.jl:259-270
+        if isinstance(other, DiagonalQuatCost):
+            return other + self   # src/lie_costs.jl:163
         cls = DiagonalCost if (self.is_diag and other.is_diag) else QuadraticCost
         return cls(self.Q + other.Q, self.R + other.R, H=self.H + other.H, q=self.q + other.q, r=self.r + other.r,
                    c=self.c + other.c, terminal=self.terminal and other.terminal)
@@ -220,6 +229,51 @@ class DiagonalCost(QuadraticCostFunction):   # src/cost_functions.jl:326-347
 
 class QuadraticCost(QuadraticCostFunction):   # src/cost_functions.jl:417-454
     pass
+
+
+class DiagonalQuatCost(DiagonalCost):
+    """``DiagonalQuatCost(Q, R, q, r, c, w, q_ref, q_ind)`` (src/lie_costs.jl:33-56):
+    ``1/2 x'Qx + 1/2 u'Ru + q'x + r'u + c + w min(1 + q_ref'p, 1 - q_ref'p)`` with ``p = x[q_ind]`` (1-based indices, default 4:7)."""
+
+    def __init__(self, Q, R, q=None, r=None, c=0.0, w=1.0, q_ref=(1.0, 0.0, 0.0, 0.0), q_ind=(4, 5, 6, 7), terminal=False):
+        super().__init__(Q, R, None, q, r, c, terminal)
+        self.w = float(w)
+        self.q_ref = np.asarray(q_ref, dtype=float).copy()
+        self.q_ind = np.asarray(q_ind, dtype=int).copy()
+        if self.q_ref.shape != (4,) or self.q_ind.shape != (4,):
+            raise DimensionMismatch("quat_ind argument must be of length 4")   # @assert src/lie_costs.jl:132
+        if self.q_ind.min() < 1 or self.q_ind.max() > self.state_dim:
+            raise DimensionMismatch("DiagonalQuatCost: q_ind outside the state")
+
+    def copy(self):   # Base.copy  src/lie_costs.jl:165-167
+        return DiagonalQuatCost(self.Q, self.R, q=self.q, r=self.r, c=self.c, w=self.w, q_ref=self.q_ref, q_ind=self.q_ind, terminal=self.terminal)
+
+    def __add__(self, other):   # +(::DiagonalQuatCost, ::QuadraticCostFunction)  src/lie_costs.jl:152-163
+        if not other.is_diag and np.max(np.abs(other.H), initial=0.0) != 0.0:
+            raise ArgumentError("DiagonalQuatCost + cost with a non-zero H")   # @assert norm(cost2.H) ~ 0
+        return DiagonalQuatCost(self.Q + other.Q, self.R + other.R, q=self.q + other.q, r=self.r + other.r, c=self.c + other.c,
+                                w=self.w, q_ref=self.q_ref, q_ind=self.q_ind)
+
+    __radd__ = __add__
+
+    def _spec(self):
+        d = super()._spec()
+        d.update(kind=K.COST_DIAGONAL_QUAT, w=self.w, q_ref=self.q_ref, q_ind=self.q_ind)
+        return d
+
+
+def QuatLQRCost(Q, R, xf, uf=None, w=1.0, quat_ind=(4, 5, 6, 7), **kw):
+    """``QuatLQRCost(Q, R, xf, uf; w, quat_ind)`` (src/lie_costs.jl:129-139)."""
+    Q, R = np.asarray(Q, dtype=float), np.asarray(R, dtype=float)
+    Qm = np.diag(Q) if Q.ndim == 1 else Q
+    Rm = np.diag(R) if R.ndim == 1 else R
+    xf = np.asarray(xf, dtype=float)
+    uf = np.zeros(Rm.shape[0]) if uf is None else np.asarray(uf, dtype=float)
+    quat_ind = np.asarray(quat_ind, dtype=int)
+    if quat_ind.size != 4:
+        raise DimensionMismatch("quat_ind argument must be of length 4")
+    return DiagonalQuatCost(Qm, Rm, q=-Qm @ xf, r=-Rm @ uf, c=0.5 * xf @ Qm @ xf + 0.5 * uf @ Rm @ uf, w=w, q_ref=xf[quat_ind - 1],
+                            q_ind=quat_ind, **kw)
 
 
 def make_quadratic_cost(Q, R, H=None, q=None, r=None, c=0.0, **kw):
@@ -454,6 +508,22 @@ class CollisionConstraint(AbstractConstraint):   # src/constraints.jl:328-389
                     inds=np.concatenate([self.x1, self.x2]))
 
 
+class QuatVecEq(AbstractConstraint):   # src/constraints.jl:938-965
+    """``QuatVecEq(n, m, qf, qind=4:7)``: the vector part of the normalised quaternion ``x[qind]`` equals that of ``qf`` (sign-matched)."""
+    sense_ = Equality()
+
+    def __init__(self, n, m, qf, qind=(4, 5, 6, 7)):
+        self.n, self.m = n, m
+        self.qf = np.asarray(qf, dtype=float).copy()
+        self.qind = np.asarray(qind, dtype=int).copy()
+        if self.qf.shape != (4,) or self.qind.shape != (4,):
+            raise DimensionMismatch("QuatVecEq: qf and qind must have 4 entries")
+        self.p = 3
+
+    def _spec(self, first, last):
+        return dict(kind=K.CON_QUATVEC, first=first, last=last, sense=K.CONE_ZERO, a=self.qf, inds=self.qind)
+
+
 class StateBound(BoundConstraint):   # src/constraints.jl:596-617 -- a BoundConstraint whose control block is unbounded
     """``StateBound(n; x_min, x_max)``. The control dimension is taken from the ConstraintList it is added to."""
 
@@ -532,10 +602,12 @@ class Problem:
 
     ``x0`` is ``[n]`` (shared) or ``[B, n]``; ``batch`` gives ``B`` when ``x0`` is shared.  The integrator is RK4
     (the reference's default, src/problem.jl:119-123).  States start as NaN and controls as zeros like the
-    reference (src/problem.jl:83-84).
+    reference (src/problem.jl:83-84).  ``error_state=True`` makes the solver kernels (backward / forward pass) work on the
+    Lie-group error state of the model (``RD.errstate_dim(model)`` dimensions, Quadrotor: 12) as Altro does for ``LieGroupModel``s.
     """
 
-    def __init__(self, model, obj, *args, xf=None, constraints=None, t0=0.0, X0=None, U0=None, dt=None, batch=None, device=0, **kwargs):
+    def __init__(self, model, obj, *args, xf=None, constraints=None, t0=0.0, X0=None, U0=None, dt=None, batch=None, device=0,
+                 error_state=False, **kwargs):
         if "x0" in kwargs:   # src/problem.jl:87-91
             raise ArgumentError("Cannot pass x0 as a keyword argument. It is now a positional argument, and xf is a keyword argument.")
         if kwargs:
@@ -566,13 +638,17 @@ class Problem:
             raise ArgumentError("tf must be greater than t0")   # @assert tf > t0 src/problem.jl:52
         self.model, self.obj, self.constraints = model, obj, cons
         self.N, self.n, self.m, self.B = N, n, m, B
+        if error_state and model.errstate_dim() == n:
+            raise ArgumentError("error_state=True needs a Lie-group model (RD.errstate_dim(model) != state_dim)")
+        self.error_state = bool(error_state)
+        self.ne = model.errstate_dim() if error_state else n
         self.x0 = np.broadcast_to(x0, (B, n)).copy()
         self.xf = np.full(n, np.nan) if xf is None else np.asarray(xf, dtype=float).copy()
         uniq, index = obj._tables()
         self._cost_objs = uniq
         con_specs = [c._spec(f, l) for (f, l), c in zip(cons.inds, cons.constraints)]
         self.spec = K.Spec(model.model_id, n, m, N, B, dtv, [c._spec() for c in uniq], index, con_specs,
-                           params=model.params, t0=t0, device=device)
+                           params=model.params, t0=t0, device=device, error_state=self.error_state)
         self._open()
         self._call("to_set_initial_state", K._dp(self.x0))
         if U0 is not None:
@@ -590,6 +666,9 @@ class Problem:
     def _call(self, name, *args):
         rc = getattr(self._lib, name)(self._h, *args)
         K.check(self._lib, self._h, rc)
+
+    def _default_options(self, o):
+        self._lib.to_default_options(C.byref(o))
 
     def close(self):
         if getattr(self, "_h", None) is not None and self._h:
@@ -831,11 +910,42 @@ def al_update(prob):
 
 
 def gains(prob):
-    """-> ``K[B, N-1, m, n]``, ``d[B, N-1, m]``."""
-    Kk = np.empty((prob.B, prob.N - 1, prob.n, prob.m))
+    """-> ``K[B, N-1, m, n_e]``, ``d[B, N-1, m]`` (``n_e = n`` unless the problem uses the error state)."""
+    Kk = np.empty((prob.B, prob.N - 1, prob.ne, prob.m))
     d = np.empty((prob.B, prob.N - 1, prob.m))
     prob._call("to_get_gains", K._dp(Kk), K._dp(d))
     return np.swapaxes(Kk, -1, -2), d
+
+
+def errstate_dim(prob):
+    """``RD.errstate_dim`` as the solver kernels see it: ``n``, or the model's error-state dimension with ``error_state=True``."""
+    ne = C.c_int32()
+    prob._call("to_error_state_dim", C.byref(ne))
+    return ne.value
+
+
+def state_diff(prob, Xbar):
+    """``RD.state_diff(model, xbar_k, x_k)`` of every knot of ``Xbar[B, N, n]`` against the current trajectory -> ``[B, N, n_e]``."""
+    Xb = _bcast(Xbar, (prob.B, prob.N, prob.n), "Xbar")
+    dx = np.empty((prob.B, prob.N, prob.ne))
+    prob._call("to_state_diff", K._dp(Xb), K._dp(dx))
+    return dx
+
+
+def error_dynamics(prob):
+    """error-state dynamics Jacobians ``[A_e B_e] = G_{k+1}' [A G_k | B]`` -> ``[B, N-1, n_e, n_e+m]`` (after ``expand``)."""
+    AB = np.empty((prob.B, prob.N - 1, prob.ne + prob.m, prob.ne))
+    prob._call("to_get_error_dynamics", K._dp(AB))
+    return np.swapaxes(AB, -1, -2)
+
+
+def error_expansion(prob):
+    """cost + AL expansion in the error state (Altro ``error_expansion!``) -> ``grad[B, N, n_e+m]``, ``hess[B, N, n_e+m, n_e+m]``."""
+    nm = prob.ne + prob.m
+    g = np.empty((prob.B, prob.N, nm))
+    H = np.empty((prob.B, prob.N, nm, nm))
+    prob._call("to_error_expansion", K._dp(g), K._dp(H))
+    return g, np.swapaxes(H, -1, -2)
 
 
 def multipliers(prob, con):
@@ -873,7 +983,7 @@ def solver_state(prob):
 
 def set_options(prob, **kw):
     o = K.to_options()
-    prob._lib.to_default_options(C.byref(o))
+    prob._default_options(o)
     for k, v in kw.items():
         if not hasattr(o, k):
             raise ArgumentError(f"unknown solver option {k}")

@@ -123,7 +123,70 @@ def acrobot(B=8192, N=201, seed=1, cls=None, dense_cost=True, **kw):
     return prob
 
 
+def quadrotor_lie(B=64, N=51, seed=1, cls=None, quat_cost=True, quat_goal=True, error_state=True, **kw):
+    """Quadrotor with the Lie-group handling of SURVEY 8(f2): Riccati on the 12-dimensional error state (``error_state``), a
+    ``QuatLQRCost`` objective (src/lie_costs.jl:129-139, zero quadratic weight on the quaternion, geodesic weight w) and, instead of
+    a full-state goal, ``GoalConstraint`` on position / velocities + ``QuatVecEq`` on the attitude (src/constraints.jl:938-965).
+    Inputs as in ``quadrotor`` plus a random initial attitude per instance."""
+    cls = cls or TO.Problem
+    model = TO.Quadrotor()
+    n, m = 13, 4
+    r = _rng(seed)
+    xf = np.array([0, 0, 2, 1, 0, 0, 0, 0, 0, 0, 0, 0, 0.0])
+    Qd = np.array([0.1] * 3 + [0.0] * 4 + [0.1] * 6); Qfd = np.array([100.0] * 3 + [0.0] * 4 + [100.0] * 6)
+    Rd = np.full(m, 0.01)
+    uf = model.hover_control()
+    if quat_cost:
+        stage = TO.QuatLQRCost(Qd, Rd, xf, uf, w=0.5)
+        term = TO.QuatLQRCost(Qfd, Rd, xf, uf, w=20.0, terminal=True)
+    else:   # plain LQR cost with isotropic quaternion weights (the BASELINE objective)
+        stage = TO.LQRCost(np.full(n, 0.1), Rd, xf, uf)
+        term = TO.LQRCost(np.full(n, 100.0), Rd, xf, uf, terminal=True)
+    obj = TO.Objective(stage, term, N)
+    cons = TO.ConstraintList(n, m, N)
+    TO.add_constraint(cons, TO.BoundConstraint(n, m, u_min=np.zeros(4), u_max=np.full(4, 10.0)), (1, N - 1))
+    if quat_goal:
+        TO.add_constraint(cons, TO.GoalConstraint(xf, inds=[1, 2, 3, 8, 9, 10, 11, 12, 13]), N)
+        TO.add_constraint(cons, TO.QuatVecEq(n, m, xf[3:7]), N)
+    else:
+        TO.add_constraint(cons, TO.GoalConstraint(xf), N)
+    x0 = np.zeros((B, n))
+    x0[:, :3] = np.array([1, 2, 1.0]) + (r.uniform(-1, 1, (B, 3)) if B > 1 else 0.0)
+    q0 = np.array([1.0, 0, 0, 0]) + 0.3 * r.standard_normal((B, 4))
+    x0[:, 3:7] = q0 / np.linalg.norm(q0, axis=1, keepdims=True)
+    U0 = uf[None, None, :] + 0.05 * r.standard_normal((B, N - 1, m))
+    prob = cls(model, obj, x0, 0.05 * (N - 1), xf=xf, constraints=cons, error_state=error_state, **kw)
+    TO.initial_controls(prob, U0)
+    return prob
+
+
+def quadrotor_zigzag(cls=None, dt_scaled_cost=True, error_state=True, **kw):
+    """examples/Quadrotor.ipynb cells 10-20: 20 m flight through two waypoints, N=101, tf=5, u in [0,12], initial control
+    0.5*mass/m.  ``dt_scaled_cost``: the notebook's recorded output (cost 0.2992834848449584, :374-376) was produced with
+    TrajectoryOptimization v0.3, which integrated the stage costs with dt (see ``cartpole``)."""
+    cls = cls or TO.Problem
+    model = TO.Quadrotor()
+    n, m, N = 13, 4, 101
+    sc = 5.0 / (N - 1) if dt_scaled_cost else 1.0
+    fill = lambda p, q, v, w: np.array([p] * 3 + [q] * 4 + [v] * 3 + [w] * 3, dtype=float)      # RobotDynamics.fill_state
+    build = lambda r: np.array([*r, 1, 0, 0, 0, 0, 0, 0, 0, 0, 0], dtype=float)                   # RobotDynamics.build_state, identity attitude
+    x0, xf = build([0, -10, 1.0]), build([0, 10, 1.0])
+    R = np.full(m, 1e-4) * sc
+    cost_nom = TO.LQRCost(fill(1e-5, 1e-5, 1e-3, 1e-3) * sc, R, build([0, 0, 0.0]))
+    wpts, times = [[10, 0, 1.0], [-10, 0, 1.0], [0, 10, 1.0]], [33, 66, 101]
+    Qw, Qf = fill(1e3, 1, 1, 1), fill(10.0, 100, 10, 10)
+    costs = [TO.LQRCost(Qf if t == N else 1e-3 * Qw * sc, R, build(r), terminal=(t == N)) for r, t in zip(wpts, times)]
+    obj = TO.Objective([costs[times.index(k)] if k in times else cost_nom for k in range(1, N + 1)])
+    cons = TO.ConstraintList(n, m, N)
+    TO.add_constraint(cons, TO.BoundConstraint(n, m, u_min=0.0, u_max=12.0), (1, N - 1))
+    prob = cls(model, obj, x0, 5.0, xf=xf, constraints=cons, error_state=error_state, **kw)
+    TO.initial_controls(prob, np.full((1, N - 1, m), 0.5 * model.mass / m))
+    return prob
+
+
 CONFIGS = {
+    "quadrotor_lie": quadrotor_lie,
+    "quadrotor_zigzag": quadrotor_zigzag,
     "double_integrator": double_integrator,
     "cartpole": cartpole,
     "quadrotor": quadrotor,

@@ -30,6 +30,7 @@ WORKLOADS = {
     "quadrotor": dict(n=13, m=4, N=101, batch=4096, desc="Quadrotor point-to-point n=13 m=4 N=101, u in [0,10] + goal (AL-iLQR)"),
     "cartpole": dict(n=4, m=1, N=101, batch=1024, desc="Cartpole swing-up n=4 m=1 N=101, unconstrained LQR cost"),
     "acrobot": dict(n=4, m=1, N=201, batch=8192, desc="Acrobot n=4 m=1 N=201, dense second-order cost + |u|<=15 + goal (AL)"),
+    "quadrotor_lie": dict(n=13, m=4, N=101, batch=4096, desc="Quadrotor n=13 m=4 N=101 on the Lie-group error state (n_e=12), LQR cost, u in [0,10] + goal; materialised expansion (lie.cu)"),
 }
 
 
@@ -42,6 +43,8 @@ def build_problem(workload, B, N, cls=None, device=0):
         return P.cartpole(B=B, N=N, cls=cls, device=device)
     if workload == "acrobot":
         return P.acrobot(B=B, N=N, cls=cls, device=device)
+    if workload == "quadrotor_lie":
+        return P.quadrotor_lie(B=B, N=N, cls=cls, device=device, quat_cost=False, quat_goal=False)
     raise SystemExit(f"unknown workload {workload}")
 
 

@@ -45,7 +45,19 @@ enum to_model_id {
 
 /* QuadraticCostFunction (src/cost_functions.jl:326-347 DiagonalCost, :417-454 QuadraticCost) */
 /* DiagonalQuatCost / QuatLQRCost (src/lie_costs.jl:33-95, :129-139): a DiagonalCost plus w * min(1 + q_ref'p, 1 - q_ref'p), p = x[q_ind] */
-enum to_cost_kind { TO_COST_DIAGONAL = 0, TO_COST_QUADRATIC = 1, TO_COST_DIAGONAL_QUAT = 2 };
+/* Generic (user-defined) cost: the reference lets users subtype CostFunction and get gradient!/hessian! from ForwardDiff through
+ * RD.@autodiff (docs/src/costfunction_interface.md:30-50, test/nlcosts.jl:4-19).  Here the user function arrives as a straight-line
+ * PROGRAM (SSA, one value per instruction, the last one is the cost) recorded by the host API, and the kernels evaluate it with
+ * second-order forward-mode dual numbers.  Instruction i = {op, a, b}: operands are indices of earlier instructions,
+ * of the state / control vector (TO_OP_X / TO_OP_U), or of the constant table (TO_OP_CONST; TO_OP_POWC: b).  At the terminal knot the
+ * program is evaluated with u = 0 and only the state derivatives are taken (the reference's zero terminal control). */
+enum to_cost_kind { TO_COST_DIAGONAL = 0, TO_COST_QUADRATIC = 1, TO_COST_DIAGONAL_QUAT = 2, TO_COST_EXPR = 3 };
+enum to_expr_op { TO_OP_CONST = 0, TO_OP_X = 1, TO_OP_U = 2, TO_OP_ADD = 3, TO_OP_SUB = 4, TO_OP_MUL = 5, TO_OP_DIV = 6, TO_OP_NEG = 7,
+                  TO_OP_SIN = 8, TO_OP_COS = 9, TO_OP_EXP = 10, TO_OP_LOG = 11, TO_OP_SQRT = 12, TO_OP_POWC = 13 /* a ^ const[b] */, TO_OP_TANH = 14,
+                  /* one operand taken from the constant table: a (op) const[b] */
+                  TO_OP_ADDC = 15, TO_OP_MULC = 16, TO_OP_DIVC = 17 /* a / c */, TO_OP_RDIVC = 18 /* c / a */, TO_OP_RSUBC = 19 /* c - a */ };
+#define TO_EXPR_MAXLEN 128
+#define TO_EXPR_MAXCONST 32
 typedef struct {
     int32_t kind;     /* to_cost_kind */
     int32_t terminal; /* `terminal` flag of the cost (LQRObjective sets it on the last cost, src/objective.jl:154,180) */
@@ -58,6 +70,10 @@ typedef struct {
     double w;               /* DIAGONAL_QUAT: weight of the geodesic term */
     const double* q_ref;    /* DIAGONAL_QUAT: reference quaternion (4, scalar first); else NULL */
     const int32_t* q_ind;   /* DIAGONAL_QUAT: 1-based state indices of the quaternion (4); NULL = 4:7 (src/lie_costs.jl:64) */
+    int32_t prog_len;       /* EXPR: number of instructions (<= TO_EXPR_MAXLEN); Q, R, q, r may be NULL */
+    int32_t nconst;         /* EXPR: number of constants (<= TO_EXPR_MAXCONST) */
+    const int32_t* prog;    /* EXPR: prog_len x {op, a, b} */
+    const double* consts;   /* EXPR */
 } to_cost_spec;
 
 /* ConstraintSense (src/cones.jl:17-61) */

@@ -53,13 +53,67 @@ struct Cost {
     double w = 0;
     double q_ref[4] = {1, 0, 0, 0};
     int q_ind[4] = {3, 4, 5, 6};   // 0-based
+    // generic cost recorded as a straight-line program (RD.@autodiff user costs, docs/src/costfunction_interface.md:30-50)
+    bool expr = false;
+    std::vector<int> prog;          // {op, a, b} per instruction
+    std::vector<double> consts;
 };
+
+// ---- straight-line program evaluation (to_expr_op in include/trajopt_b200.h) ----------------------------------------
+// second-order forward mode: (v, d1, d2, d12) = value, d/ds, d/dt, d2/dsdt for seeds s, t (ForwardDiff's nested Duals restated)
+struct Hyper {
+    double v = 0, d1 = 0, d2 = 0, d12 = 0;
+};
+inline Hyper hyp_unary(const Hyper& a, double f, double f1, double f2) {
+    Hyper r; r.v = f; r.d1 = f1 * a.d1; r.d2 = f1 * a.d2; r.d12 = f1 * a.d12 + f2 * a.d1 * a.d2; return r;
+}
+inline Hyper hyp_mul(const Hyper& a, const Hyper& b) {
+    Hyper r; r.v = a.v * b.v; r.d1 = a.d1 * b.v + a.v * b.d1; r.d2 = a.d2 * b.v + a.v * b.d2;
+    r.d12 = a.d12 * b.v + a.d1 * b.d2 + a.d2 * b.d1 + a.v * b.d12; return r;
+}
+enum ExprOp { OP_CONST = 0, OP_X = 1, OP_U = 2, OP_ADD = 3, OP_SUB = 4, OP_MUL = 5, OP_DIV = 6, OP_NEG = 7, OP_SIN = 8, OP_COS = 9,
+              OP_EXP = 10, OP_LOG = 11, OP_SQRT = 12, OP_POWC = 13, OP_TANH = 14, OP_ADDC = 15, OP_MULC = 16, OP_DIVC = 17, OP_RDIVC = 18, OP_RSUBC = 19 };
+constexpr int EXPR_MAXLEN = 128;
+// evaluate the program with z_s1 seeded in d1 and z_s2 in d2 (index into [x;u]; -1 = no seed); has_u = false -> u = 0
+inline Hyper expr_eval(const Cost& c, const double* x, const double* u, bool has_u, int s1, int s2) {
+    Hyper reg[EXPR_MAXLEN];
+    const int L = (int)c.prog.size() / 3, n = c.n;
+    for (int i = 0; i < L; i++) {
+        const int op = c.prog[3 * i], a = c.prog[3 * i + 1], b = c.prog[3 * i + 2];
+        Hyper r;
+        switch (op) {
+            case OP_CONST: r.v = c.consts[a]; break;
+            case OP_X: r.v = x[a]; r.d1 = (a == s1); r.d2 = (a == s2); break;
+            case OP_U: r.v = has_u ? u[a] : 0.0; r.d1 = (n + a == s1); r.d2 = (n + a == s2); break;
+            case OP_ADD: r.v = reg[a].v + reg[b].v; r.d1 = reg[a].d1 + reg[b].d1; r.d2 = reg[a].d2 + reg[b].d2; r.d12 = reg[a].d12 + reg[b].d12; break;
+            case OP_SUB: r.v = reg[a].v - reg[b].v; r.d1 = reg[a].d1 - reg[b].d1; r.d2 = reg[a].d2 - reg[b].d2; r.d12 = reg[a].d12 - reg[b].d12; break;
+            case OP_MUL: r = hyp_mul(reg[a], reg[b]); break;
+            case OP_DIV: { const double iv = 1.0 / reg[b].v; r = hyp_mul(reg[a], hyp_unary(reg[b], iv, -iv * iv, 2 * iv * iv * iv)); break; }
+            case OP_NEG: r.v = -reg[a].v; r.d1 = -reg[a].d1; r.d2 = -reg[a].d2; r.d12 = -reg[a].d12; break;
+            case OP_SIN: { const double sv = std::sin(reg[a].v), cv = std::cos(reg[a].v); r = hyp_unary(reg[a], sv, cv, -sv); break; }
+            case OP_COS: { const double sv = std::sin(reg[a].v), cv = std::cos(reg[a].v); r = hyp_unary(reg[a], cv, -sv, -cv); break; }
+            case OP_EXP: { const double e = std::exp(reg[a].v); r = hyp_unary(reg[a], e, e, e); break; }
+            case OP_LOG: { const double iv = 1.0 / reg[a].v; r = hyp_unary(reg[a], std::log(reg[a].v), iv, -iv * iv); break; }
+            case OP_SQRT: { const double sq = std::sqrt(reg[a].v); r = hyp_unary(reg[a], sq, 0.5 / sq, -0.25 / (sq * reg[a].v)); break; }
+            case OP_POWC: { const double e = c.consts[b], v = reg[a].v; r = hyp_unary(reg[a], std::pow(v, e), e * std::pow(v, e - 1), e * (e - 1) * std::pow(v, e - 2)); break; }
+            case OP_TANH: { const double t = std::tanh(reg[a].v); r = hyp_unary(reg[a], t, 1 - t * t, -2 * t * (1 - t * t)); break; }
+            case OP_ADDC: r = reg[a]; r.v += c.consts[b]; break;
+            case OP_MULC: { const double k = c.consts[b]; r.v = reg[a].v * k; r.d1 = reg[a].d1 * k; r.d2 = reg[a].d2 * k; r.d12 = reg[a].d12 * k; break; }
+            case OP_DIVC: { const double k = c.consts[b]; r.v = reg[a].v / k; r.d1 = reg[a].d1 / k; r.d2 = reg[a].d2 / k; r.d12 = reg[a].d12 / k; break; }
+            case OP_RDIVC: { const double k = c.consts[b], iv = 1.0 / reg[a].v; r = hyp_unary(reg[a], k * iv, -k * iv * iv, 2 * k * iv * iv * iv); break; }
+            case OP_RSUBC: r.v = c.consts[b] - reg[a].v; r.d1 = -reg[a].d1; r.d2 = -reg[a].d2; r.d12 = -reg[a].d12; break;
+        }
+        reg[i] = r;
+    }
+    return reg[L - 1];
+}
 
 // RD.evaluate(::QuadraticCostFunction, x, u)  src/cost_functions.jl:89-104.  `has_u == false` is the
 // `isempty(u)` branch; the batched layout has no control at the terminal knot, which equals the
 // reference's convention of a zero terminal control (test/objective_tests.jl:128).
 inline double cost_value(const Cost& c, const double* x, const double* u, bool has_u) {
     const int n = c.n, m = c.m;
+    if (c.expr) return expr_eval(c, x, u, has_u, -1, -1).v;
     double J = 0;
     for (int j = 0; j < n; j++) {
         double qx = 0;
@@ -97,6 +151,10 @@ inline double cost_value(const Cost& c, const double* x, const double* u, bool h
 // RD.gradient!  src/cost_functions.jl:137-172: grad = [Qx+q (+H'u); Ru+r (+Hx)], u-part untouched at terminal.
 inline void cost_gradient(const Cost& c, const double* x, const double* u, bool is_terminal, double* grad) {
     const int n = c.n, m = c.m;
+    if (c.expr) {   // RD.gradient!(ForwardAD) of a user cost; the control part is left untouched at the terminal knot
+        for (int i = 0; i < (is_terminal ? n : n + m); i++) grad[i] = expr_eval(c, x, u, !is_terminal, i, -1).d1;
+        return;
+    }
     for (int i = 0; i < n; i++) {
         double g = c.q[i];
         for (int j = 0; j < n; j++) g += c.Q[j * n + i] * x[j];
@@ -127,8 +185,15 @@ inline void cost_gradient(const Cost& c, const double* x, const double* u, bool 
 // matrix first (:216); dense costs only write blocks Q, R and the lower-left H -- here the
 // caller passes a zeroed matrix, and `symmetric` additionally mirrors H' into the upper-right block
 // (what a solver consumes).
-inline void cost_hessian(const Cost& c, bool is_terminal, double* hess, bool symmetric) {
+inline void cost_hessian(const Cost& c, const double* x, const double* u, bool is_terminal, double* hess, bool symmetric) {
     const int n = c.n, m = c.m, nm = n + m;
+    if (c.expr) {   // RD.hessian!(ForwardAD): full symmetric (n+m)^2 block (state block only at the terminal knot)
+        std::fill(hess, hess + nm * nm, 0.0);
+        const int lim = is_terminal ? n : nm;
+        for (int j = 0; j < lim; j++)
+            for (int i = j; i < lim; i++) { const double h = expr_eval(c, x, u, !is_terminal, i, j).d12; hess[j * nm + i] = h; hess[i * nm + j] = h; }
+        return;
+    }
     if (c.diag) std::fill(hess, hess + nm * nm, 0.0);
     for (int j = 0; j < n; j++)
         for (int i = 0; i < n; i++)
@@ -711,7 +776,7 @@ inline void cost_expansion(const Problem& P, const double* X, const double* U, c
     std::fill(hess, hess + nm * nm, 0.0);
     const Cost& c = P.costs[P.cost_index[k]];
     cost_gradient(c, x, u, last, grad);
-    cost_hessian(c, last, hess, true);
+    cost_hessian(c, x, u, last, hess, true);
     double cv[MAXP], jac[MAXP * (MAXN + MAXM)], lbar[MAXP], lp[MAXP], Dm[MAXP * MAXP], tmp[MAXP * (MAXN + MAXM)];   // no heap traffic in the hot loop
     for (size_t ci = 0; ci < P.cons.size(); ci++) {
         const Constraint& con = P.cons[ci];

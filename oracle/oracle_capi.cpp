@@ -46,6 +46,26 @@ int orc_create(const to_spec* s, orc_handle** out) {
     for (int i = 0; i < s->ncost; i++) {
         const to_cost_spec& tc = s->costs[i];
         Cost c; c.n = n; c.m = m; c.diag = (tc.kind == TO_COST_DIAGONAL || tc.kind == TO_COST_DIAGONAL_QUAT); c.terminal = tc.terminal != 0; c.c = tc.c;
+        if (tc.kind == TO_COST_EXPR) {
+            if (!tc.prog || tc.prog_len < 1 || tc.prog_len > TO_EXPR_MAXLEN || tc.nconst < 0 || tc.nconst > TO_EXPR_MAXCONST || (tc.nconst > 0 && !tc.consts)) {
+                delete h; return fail(nullptr, TO_EINVAL, "expression cost: bad program size");
+            }
+            c.expr = true; c.diag = false; c.zeroH = false;
+            c.prog.assign(tc.prog, tc.prog + 3 * tc.prog_len); c.consts.assign(tc.consts, tc.consts + tc.nconst);
+            for (int j = 0; j < tc.prog_len; j++) {
+                const int op = c.prog[3 * j], a = c.prog[3 * j + 1], b = c.prog[3 * j + 2];
+                const bool bin = op >= TO_OP_ADD && op <= TO_OP_DIV;
+                bool ok = op >= 0 && op <= TO_OP_RSUBC;
+                if (op == TO_OP_CONST) ok = ok && a >= 0 && a < tc.nconst;
+                else if (op == TO_OP_X) ok = ok && a >= 0 && a < n;
+                else if (op == TO_OP_U) ok = ok && a >= 0 && a < m;
+                else { ok = ok && a >= 0 && a < j; if (bin) ok = ok && b >= 0 && b < j; if (op == TO_OP_POWC || op >= TO_OP_ADDC) ok = ok && b >= 0 && b < tc.nconst; }
+                if (!ok) { delete h; return fail(nullptr, TO_EINVAL, "expression cost: invalid instruction"); }
+            }
+            c.Q.assign((size_t)n * n, 0.0); c.R.assign((size_t)m * m, 0.0); c.H.assign((size_t)m * n, 0.0); c.q.assign(n, 0.0); c.r.assign(m, 0.0);
+            P.costs.push_back(c);
+            continue;
+        }
         if (tc.kind == TO_COST_DIAGONAL_QUAT) {
             if (!tc.q_ref) { delete h; return fail(nullptr, TO_EINVAL, "DiagonalQuatCost: null q_ref"); }
             c.quat = true; c.w = tc.w;
@@ -274,7 +294,8 @@ int orc_cost_hessian(orc_handle* h, double* hess) {
         for (int k = 0; k < P.N; k++) {
             double* H = &hess[((size_t)b * P.N + k) * nm * nm];
             std::fill(H, H + nm * nm, 0.0);
-            cost_hessian(P.costs[P.cost_index[k]], k == P.N - 1, H, true);
+            const bool last = k == P.N - 1;
+            cost_hessian(P.costs[P.cost_index[k]], &P.Xb(b)[k * P.n], last ? ZERO_U : &P.Ub(b)[k * P.m], last, H, true);
         }
     return TO_OK;
 }

@@ -13,6 +13,6 @@ done
 wait
 for o in _build/variants/riccati_*.o; do
   name=$(basename $o .o); name=${name#riccati_}
-  /usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -shared -ccbin /usr/bin/g++ -o ../variants/lib_$name.so _build/capi.o _build/rollout.o _build/sweep.o $o _build/riccati_small.o _build/forward.o
+  /usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -shared -ccbin /usr/bin/g++ -o ../variants/lib_$name.so _build/capi.o _build/rollout.o _build/sweep.o $o _build/riccati_small.o _build/lie.o _build/forward.o
   echo "$name: $(grep -A2 'k_riccatiILi13ELi4ELi2ELb1ELb1ELi' _build/variants/riccati_$name.log | grep -E 'Used|spill' | tr '\n' ' ')"
 done

@@ -34,6 +34,11 @@ CONFIGS = {
     "cartpole_single": lambda cls: P.cartpole(B=1, N=2, cls=cls),
     "acrobot_dense": lambda cls: P.acrobot(B=9, N=201, cls=cls, dense_cost=True),
     "acrobot_diag": lambda cls: P.acrobot(B=3, N=51, cls=cls, dense_cost=False),
+    # Lie-group error state (Riccati on n_e = 12, lie.cu), DiagonalQuatCost, QuatVecEq
+    "quadrotor_lie": lambda cls: P.quadrotor_lie(B=7, N=31, cls=cls),                                           # quat cost + QuatVecEq + error state
+    "quadrotor_lie_lqr": lambda cls: P.quadrotor_lie(B=9, N=41, cls=cls, quat_cost=False, quat_goal=False),     # BASELINE objective on the error state (fast forward path)
+    "quadrotor_quatcost_fullstate": lambda cls: P.quadrotor_lie(B=5, N=21, cls=cls, quat_goal=False, error_state=False),
+    "quadrotor_quatveceq_fullstate": lambda cls: P.quadrotor_lie(B=4, N=21, cls=cls, quat_cost=False, error_state=False),
 }
 
 
@@ -131,6 +136,114 @@ def test_small_model_riccati_kernels(name, kernel):
     so = TO.solver_state(o)
     live = np.abs(so["dV"][:, 0]) > 1e-9 * np.maximum(1.0, np.abs(TO.merit(o)))
     close(TO.merit(g)[live], TO.merit(o)[live], 1e-5, "merit")
+    g.close(); o.close()
+
+
+@pytest.mark.parametrize("name", ["quadrotor_lie", "quadrotor_lie_lqr", "quadrotor_quatcost_fullstate"])
+def test_error_state_kernels(name):
+    """lie.cu: RD.state_diff, [A_e B_e] = G' [A G | B], the error-state cost + AL expansion (Altro error_expansion!) against the oracle"""
+    g, o = CONFIGS[name](TO.Problem), CONFIGS[name](OracleProblem)
+    assert TO.errstate_dim(g) == TO.errstate_dim(o) == (12 if g.error_state else 13)
+    for p in (g, o):
+        TO.rollout(p); TO.expand(p)
+    close(TO.error_dynamics(g), TO.error_dynamics(o), KERNEL_RTOL, "[A_e B_e]")
+    r = np.random.default_rng(5)
+    Xbar = TO.states(o) + 0.2 * r.standard_normal((g.B, g.N, g.n))
+    close(TO.state_diff(g, Xbar), TO.state_diff(o, Xbar), KERNEL_RTOL, "state_diff")
+    for it in range(2):
+        ge, He = TO.error_expansion(g); oe, Ho = TO.error_expansion(o)
+        tol = KERNEL_RTOL if it == 0 else 1e-7        # second round: the trajectories themselves differ by the iteration's round-off
+        close(ge, oe, tol, "error-state gradient"); close(He, Ho, tol, "error-state Hessian")
+        for p in (g, o):
+            TO.ilqr_step(p, 1); TO.al_update(p)      # non-zero multipliers, active bounds
+    g.close(); o.close()
+
+
+def test_error_state_full_size_properties():
+    """BASELINE-size batch on the error state: merit monotone, backward pass never fails, attitude stays on the unit sphere,
+    instance 0..7 equal to an 8-instance problem with the same inputs (instances never interact)."""
+    B, N = 2048, 101
+    prob = P.quadrotor_lie(B=B, N=N, quat_cost=False, quat_goal=False)
+    small = P.quadrotor_lie(B=8, N=N, quat_cost=False, quat_goal=False)
+    TO.set_initial_state(small, prob.x0[:8]); TO.initial_controls(small, TO.controls(prob)[:8])
+    for p in (prob, small):
+        TO.rollout(p)
+    J0 = TO.merit(prob)
+    for p in (prob, small):
+        TO.ilqr_step(p, 3)
+    J3 = TO.merit(prob)
+    # (a handful of the random attitudes make Quu indefinite beyond bp_reg_max in the 2nd / 3rd iteration -- the oracle reports the same
+    #  instances; a failed backward pass keeps the trajectory, so the merit stays monotone)
+    assert np.all(J3 <= J0 + 1e-9) and np.mean(TO.solver_state(prob)["bp_status"] < 0) < 0.02
+    assert np.allclose(np.linalg.norm(TO.states(prob)[..., 3:7], axis=-1), 1.0, atol=5e-2)     # RK4 does not renormalise (nor does the reference)
+    np.testing.assert_array_equal(TO.controls(prob)[:8], TO.controls(small))
+    prob.close(); small.close()
+
+
+def _autodiff_pair(kind):
+    from test_oracle_nlcost import cartpole_cost, lqr_as_autodiff
+    r = np.random.default_rng(21)
+    probs = []
+    for cls in (TO.Problem, OracleProblem):
+        if kind == "cartpole_docs_cost":          # docs/src/costfunction_interface.md:38-50 as stage cost, |u| <= 4 + goal
+            n, m, N, B = 4, 1, 41, 6
+            stage = TO.AutodiffCost(n, m, cartpole_cost([0.1, 5.0, 0.1, 0.1], [0.05]))
+            xf = np.array([0, np.pi, 0, 0])
+            term = TO.LQRCost(np.full(n, 100.0), np.full(m, 0.05), xf, terminal=True)
+            cons = TO.ConstraintList(n, m, N)
+            TO.add_constraint(cons, TO.BoundConstraint(n, m, u_min=-4.0, u_max=4.0), (1, N - 1))
+            TO.add_constraint(cons, TO.GoalConstraint(xf), N)
+            p = cls(TO.Cartpole(), TO.Objective(stage, term, N), 0.1 * r.standard_normal((B, n)), 2.0, constraints=cons)
+            TO.initial_controls(p, 0.5 + 0.1 * r.standard_normal((B, N - 1, m)))
+        elif kind == "quadrotor_lqr_as_program":   # the BASELINE objective recorded as a user function: 17 variables, 153 second-order passes
+            ref = P.quadrotor(B=3, N=15, cls=OracleProblem, dt=0.05)
+            p = cls(ref.model, lqr_as_autodiff(ref), ref.x0, 0.05 * 14, xf=ref.xf, constraints=ref.constraints)
+            TO.initial_controls(p, TO.controls(ref)); ref.close()
+        else:                                      # every recorded operation, on the 2-D double integrator, terminal program cost too
+            n, m, N, B = 4, 2, 11, 4
+
+            def fun(x, u):
+                a = TO.sin(x[0]) * TO.cos(x[1]) + TO.exp(0.3 * x[2]) / (2.0 + x[3] ** 2)
+                b = TO.log(1.5 + u[0] ** 2) + TO.sqrt(2.0 + x[0] * x[0]) - TO.tanh(u[1] - x[1])
+                c = (1.0 + x[2] ** 2) ** 1.5 + (3.0 - u[0]) ** 3 - (-x[3]) + 2.0 / (1.0 + u[1] ** 2)
+                return a + b * 0.7 + c + 0.5 * (u[0] * u[0] + u[1] * u[1]) + 2.0 * (x[0] * x[0] + x[1] * x[1] + x[2] * x[2] + x[3] * x[3])
+            term = TO.AutodiffCost(n, m, lambda x, u: 10.0 * ((x[0] - 1.0) ** 2 + x[1] ** 2) + TO.cos(x[2]) + x[3] ** 4, terminal=True)
+            p = cls(TO.DoubleIntegrator(2), TO.Objective(TO.AutodiffCost(n, m, fun), term, N), 0.3 * r.standard_normal((B, n)), 1.0)
+            TO.initial_controls(p, 0.3 * r.standard_normal((B, N - 1, m)))
+        probs.append(p)
+        r = np.random.default_rng(21)
+    return probs
+
+
+@pytest.mark.parametrize("kind", ["cartpole_docs_cost", "quadrotor_lqr_as_program", "double_integrator_all_ops"])
+def test_autodiff_costs_in_all_kernels(kind):
+    """user costs recorded as programs (RD.@autodiff CostFunction, docs/src/costfunction_interface.md:30-50) -- value,
+    ForwardAD gradient / Hessian, AL expansion, and the solver kernels (materialised expansion + dense Riccati pass, lie.cu)"""
+    g, o = _autodiff_pair(kind)
+    for p in (g, o):
+        TO.rollout(p)
+    close(TO.cost_knots(g), TO.cost_knots(o), KERNEL_RTOL, "cost")
+    close(TO.cost_gradient(g), TO.cost_gradient(o), KERNEL_RTOL, "gradient")
+    close(TO.cost_hessian(g), TO.cost_hessian(o), KERNEL_RTOL, "Hessian")
+    gg, gh = TO.al_expansion(g); og, oh = TO.al_expansion(o)
+    close(gg, og, KERNEL_RTOL, "AL gradient"); close(gh, oh, KERNEL_RTOL, "AL Hessian")
+    if kind == "cartpole_docs_cost":   # the closed forms of test/nlcosts.jl:41-44 with Q = (0.1, 5, 0.1, 0.1), R = 0.05
+        X, U, H, gr = TO.states(g), TO.controls(g), TO.cost_hessian(g), TO.cost_gradient(g)
+        assert np.allclose(H[:, :-1, 1, 1], -0.25 * 5.0 * np.cos(X[:, :-1, 1] / 2), rtol=1e-12)
+        assert np.allclose(gr[:, :-1, 1], -0.5 * 5.0 * np.sin(X[:, :-1, 1] / 2), rtol=1e-12) and np.allclose(gr[:, :-1, 4], 0.05 * U[..., 0], rtol=1e-12)
+    for p in (g, o):
+        TO.expand(p)
+    assert np.array_equal(TO.backward(g), TO.backward(o))
+    Kg, dg = TO.gains(g); Ko, do = TO.gains(o)
+    close(Kg, Ko, 1e-8, "K"); close(dg, do, 1e-8, "d")
+    Jg, ag = TO.forward(g); Jo, ao = TO.forward(o)
+    assert np.array_equal(ag, ao)
+    close(Jg, Jo, 1e-8, "J")
+    for p in (g, o):
+        TO.ilqr_step(p, 2)
+        if len(p.constraints):
+            TO.al_update(p); TO.ilqr_step(p, 1)
+    close(TO.merit(g), TO.merit(o), 1e-5, "merit")
     g.close(); o.close()
 
 

@@ -21,7 +21,10 @@ LIB_PATH = os.environ.get("LIBTRAJOPT_B200") or os.path.join(_HERE, "libtrajopt_
 TO_OK, TO_EINVAL, TO_EDIM, TO_ECUDA, TO_ENOMEM, TO_ESTATE, TO_ECONE = 0, -1, -2, -3, -4, -5, -6
 
 MODEL_DOUBLE_INTEGRATOR, MODEL_CARTPOLE, MODEL_QUADROTOR, MODEL_ACROBOT = 0, 1, 2, 3
-COST_DIAGONAL, COST_QUADRATIC, COST_DIAGONAL_QUAT = 0, 1, 2
+COST_DIAGONAL, COST_QUADRATIC, COST_DIAGONAL_QUAT, COST_EXPR = 0, 1, 2, 3
+(OP_CONST, OP_X, OP_U, OP_ADD, OP_SUB, OP_MUL, OP_DIV, OP_NEG, OP_SIN, OP_COS, OP_EXP, OP_LOG, OP_SQRT, OP_POWC, OP_TANH,
+ OP_ADDC, OP_MULC, OP_DIVC, OP_RDIVC, OP_RSUBC) = range(20)
+EXPR_MAXLEN, EXPR_MAXCONST = 128, 32
 CONE_ZERO, CONE_NEGATIVE_ORTHANT, CONE_SECOND_ORDER, CONE_IDENTITY, CONE_POSITIVE_ORTHANT = 0, 1, 2, 3, 4
 CON_GOAL, CON_BOUND, CON_LINEAR, CON_CIRCLE, CON_SPHERE, CON_NORM, CON_COLLISION, CON_QUATVEC = 0, 1, 2, 3, 4, 5, 6, 7
 PHASE_EXPAND, PHASE_BACKWARD, PHASE_FORWARD, PHASE_LADDER, PHASE_ACCEPT, PHASE_COUNT = 0, 1, 2, 3, 4, 8
@@ -32,7 +35,8 @@ c_int32_p = C.POINTER(C.c_int32)
 
 class to_cost_spec(C.Structure):
     _fields_ = [("kind", C.c_int32), ("terminal", C.c_int32), ("Q", c_double_p), ("R", c_double_p), ("H", c_double_p),
-                ("q", c_double_p), ("r", c_double_p), ("c", C.c_double), ("w", C.c_double), ("q_ref", c_double_p), ("q_ind", c_int32_p)]
+                ("q", c_double_p), ("r", c_double_p), ("c", C.c_double), ("w", C.c_double), ("q_ref", c_double_p), ("q_ind", c_int32_p),
+                ("prog_len", C.c_int32), ("nconst", C.c_int32), ("prog", c_int32_p), ("consts", c_double_p)]
 
 
 class to_constraint_spec(C.Structure):
@@ -79,6 +83,13 @@ class Spec:
         self.keep.append(dt)
         cs = (to_cost_spec * len(costs))()
         for i, c in enumerate(costs):
+            if c["kind"] == COST_EXPR:
+                prog = np.ascontiguousarray(np.asarray(c["prog"], dtype=np.int32).reshape(-1, 3))
+                consts = _f64(c["consts"])
+                self.keep += [prog, consts]
+                cs[i] = to_cost_spec(COST_EXPR, int(c.get("terminal", False)), None, None, None, None, None, 0.0, 0.0, None, None,
+                                     len(prog), len(consts), _ip(prog), _dp(consts) if len(consts) else None)
+                continue
             Q, R, H, q, r = _f64(c["Q"]), _f64(c["R"]), _f64(c.get("H")), _f64(c["q"]), _f64(c["r"])
             if c["kind"] == COST_QUADRATIC:   # column-major for the ABI
                 Q = np.ascontiguousarray(Q.T); R = np.ascontiguousarray(R.T)
@@ -87,7 +98,7 @@ class Spec:
             q_ind = None if c.get("q_ind") is None else np.ascontiguousarray(np.asarray(c["q_ind"], dtype=np.int32))
             self.keep += [Q, R, H, q, r, q_ref, q_ind]
             cs[i] = to_cost_spec(c["kind"], int(c.get("terminal", False)), _dp(Q), _dp(R), _dp(H), _dp(q), _dp(r), float(c.get("c", 0.0)),
-                                 float(c.get("w", 0.0)), _dp(q_ref), _ip(q_ind))
+                                 float(c.get("w", 0.0)), _dp(q_ref), _ip(q_ind), 0, 0, None, None)
         ci = np.ascontiguousarray(np.asarray(cost_index, dtype=np.int32))
         self.keep.append(ci)
         ks = (to_constraint_spec * max(1, len(cons)))()

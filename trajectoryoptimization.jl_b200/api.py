@@ -179,7 +179,12 @@ def _isdiag(A):
     return A.ndim == 1 or np.count_nonzero(A - np.diag(np.diagonal(A))) == 0
 
 
-class QuadraticCostFunction:
+class CostFunction:
+    """``abstract type CostFunction`` (src/cost_functions.jl:8-13): a scalar function of one knot point."""
+    is_diag = False
+
+
+class QuadraticCostFunction(CostFunction):
     """``1/2 x'Qx + 1/2 u'Ru + u'Hx + q'x + r'u + c`` (src/cost_functions.jl:30-58)."""
     is_diag = False
 
@@ -276,6 +281,128 @@ def QuatLQRCost(Q, R, xf, uf=None, w=1.0, quat_ind=(4, 5, 6, 7), **kw):
                             q_ind=quat_ind, **kw)
 
 
+# ---- user-defined costs: RD.@autodiff struct ... <: CostFunction (docs/src/costfunction_interface.md:30-50, test/nlcosts.jl:4-19) ----
+
+
+class Expr:
+    """One value of a recorded straight-line program.  Calling the user's cost function on vectors of ``Expr`` records the
+    arithmetic it performs (what ForwardDiff's dual numbers see in the reference); the device evaluates the recording with
+    second-order forward-mode duals.  Supports + - * / **const, unary -, and sin cos exp log sqrt tanh (also through numpy ufuncs)."""
+    __array_priority__ = 1000
+
+    def __init__(self, tape, idx):
+        self.tape, self.idx = tape, idx
+
+    def _bin(self, other, op, swap=False):
+        if not isinstance(other, Expr):   # a plain number: one instruction with a constant-table operand
+            c = float(other)
+            if op == K.OP_ADD: return self.tape.emit(K.OP_ADDC, self.idx, self.tape.const_index(c))
+            if op == K.OP_MUL: return self.tape.emit(K.OP_MULC, self.idx, self.tape.const_index(c))
+            if op == K.OP_SUB: return self.tape.emit(K.OP_RSUBC if swap else K.OP_ADDC, self.idx, self.tape.const_index(c if swap else -c))
+            if op == K.OP_DIV: return self.tape.emit(K.OP_RDIVC if swap else K.OP_DIVC, self.idx, self.tape.const_index(c))
+        o = self.tape.lift(other)
+        a, b = (o, self) if swap else (self, o)
+        return self.tape.emit(op, a.idx, b.idx)
+
+    __add__ = lambda s, o: s._bin(o, K.OP_ADD)
+    __radd__ = lambda s, o: s._bin(o, K.OP_ADD, True)
+    __sub__ = lambda s, o: s._bin(o, K.OP_SUB)
+    __rsub__ = lambda s, o: s._bin(o, K.OP_SUB, True)
+    __mul__ = lambda s, o: s._bin(o, K.OP_MUL)
+    __rmul__ = lambda s, o: s._bin(o, K.OP_MUL, True)
+    __truediv__ = lambda s, o: s._bin(o, K.OP_DIV)
+    __rtruediv__ = lambda s, o: s._bin(o, K.OP_DIV, True)
+    __neg__ = lambda s: s.tape.emit(K.OP_NEG, s.idx, 0)
+    __pos__ = lambda s: s
+
+    def __pow__(self, e):
+        if isinstance(e, Expr):
+            raise ArgumentError("Expr ** Expr is not recorded: use exp(e * log(x))")
+        e = float(e)
+        if e == 2.0:
+            return self * self
+        if e == 1.0:
+            return self
+        return self.tape.emit(K.OP_POWC, self.idx, self.tape.const_index(e))
+
+    def _un(self, op):
+        return self.tape.emit(op, self.idx, 0)
+
+    sin = lambda s: s._un(K.OP_SIN)
+    cos = lambda s: s._un(K.OP_COS)
+    exp = lambda s: s._un(K.OP_EXP)
+    log = lambda s: s._un(K.OP_LOG)
+    sqrt = lambda s: s._un(K.OP_SQRT)
+    tanh = lambda s: s._un(K.OP_TANH)
+
+    def __bool__(self):
+        raise ArgumentError("a recorded cost cannot branch on a state / control value")
+
+
+class _Tape:
+    def __init__(self):
+        self.prog, self.consts = [], []
+
+    def emit(self, op, a, b):
+        if len(self.prog) >= K.EXPR_MAXLEN:
+            raise ArgumentError(f"recorded cost exceeds {K.EXPR_MAXLEN} instructions")
+        self.prog.append((int(op), int(a), int(b)))
+        return Expr(self, len(self.prog) - 1)
+
+    def const_index(self, v):
+        v = float(v)
+        for i, c in enumerate(self.consts):
+            if c == v and np.signbit(c) == np.signbit(v):
+                return i
+        if len(self.consts) >= K.EXPR_MAXCONST:
+            raise ArgumentError(f"recorded cost exceeds {K.EXPR_MAXCONST} constants")
+        self.consts.append(v)
+        return len(self.consts) - 1
+
+    def lift(self, v):
+        if isinstance(v, Expr):
+            if v.tape is not self:
+                raise ArgumentError("mixing values of two recordings")
+            return v
+        return self.emit(K.OP_CONST, self.const_index(v), 0)
+
+
+def sin(x): return x.sin() if isinstance(x, Expr) else np.sin(x)
+def cos(x): return x.cos() if isinstance(x, Expr) else np.cos(x)
+def exp(x): return x.exp() if isinstance(x, Expr) else np.exp(x)
+def log(x): return x.log() if isinstance(x, Expr) else np.log(x)
+def sqrt(x): return x.sqrt() if isinstance(x, Expr) else np.sqrt(x)
+def tanh(x): return x.tanh() if isinstance(x, Expr) else np.tanh(x)
+
+
+class AutodiffCost(CostFunction):
+    """A user-defined cost ``fun(x, u) -> scalar``: the counterpart of ``RD.@autodiff struct MyCost <: CostFunction`` +
+    ``RD.evaluate(cost, x, u)`` (docs/src/costfunction_interface.md:30-50; test/nlcosts.jl:4-19).  ``fun`` is called once with
+    recording vectors (``x[i]``, ``u[j]`` 0-based, numpy object arrays: ``x @ Q @ x``, ``np.cos(x[1] / 2)``, ``TO.cos`` all work);
+    gradient and Hessian come from forward-mode automatic differentiation of the recording on the device, like ``ForwardAD()``.
+    At the terminal knot the cost is evaluated with ``u = 0`` and only its state derivatives are used."""
+
+    def __init__(self, n, m, fun, terminal=False):
+        self.n, self.m, self.fun, self.terminal = int(n), int(m), fun, bool(terminal)
+        tape = _Tape()
+        x = np.array([tape.emit(K.OP_X, i, 0) for i in range(self.n)], dtype=object)
+        u = np.array([tape.emit(K.OP_U, j, 0) for j in range(self.m)], dtype=object)
+        out = fun(x, u)
+        out = tape.lift(out if not isinstance(out, np.ndarray) else out.item())
+        if out.idx != len(tape.prog) - 1:          # the result must be the last instruction: re-emit it
+            out = tape.emit(K.OP_ADD, out.idx, tape.lift(0.0).idx)
+        self.prog, self.consts = np.asarray(tape.prog, dtype=np.int32), np.asarray(tape.consts, dtype=float)
+
+    state_dim = property(lambda s: s.n)
+    control_dim = property(lambda s: s.m)
+
+    def copy(self):
+        return AutodiffCost(self.n, self.m, self.fun, self.terminal)
+
+    def _spec(self):
+        return dict(kind=K.COST_EXPR, terminal=self.terminal, prog=self.prog, consts=self.consts)
+
+
 def make_quadratic_cost(Q, R, H=None, q=None, r=None, c=0.0, **kw):
     """``QuadraticCostFunction(Q,R,H,q,r,c)`` (src/cost_functions.jl:60-68): Diagonal when it can be."""
     Hn = 0.0 if H is None else float(np.max(np.abs(H), initial=0.0))
@@ -302,9 +429,9 @@ class Objective:
     """``Objective`` (src/objective.jl:27-45): one cost function per knot point."""
 
     def __init__(self, cost, *args):
-        if isinstance(cost, QuadraticCostFunction) and len(args) == 1:          # Objective(cost, N)       :69-71
+        if isinstance(cost, CostFunction) and len(args) == 1:                   # Objective(cost, N)       :69-71
             self.cost = [cost for _ in range(int(args[0]))]
-        elif isinstance(cost, QuadraticCostFunction) and len(args) == 2:        # Objective(cost, term, N) :73-76
+        elif isinstance(cost, CostFunction) and len(args) == 2:                 # Objective(cost, term, N) :73-76
             N = int(args[1])
             self.cost = [cost if k < N - 1 else args[0] for k in range(N)]
         elif len(args) == 1:                                                     # Objective(costs, term)   :78-81
@@ -749,7 +876,8 @@ def set_goal_state(prob, xf, objective=True, constraint=True):   # set_goal_stat
     xf = np.ascontiguousarray(np.asarray(xf, dtype=np.float64))
     if objective:
         for c in prob._cost_objs:
-            set_LQR_goal(c, xf)
+            if isinstance(c, QuadraticCostFunction):
+                set_LQR_goal(c, xf)
     if constraint:
         for con in prob.constraints:
             if isinstance(con, GoalConstraint):
@@ -766,6 +894,8 @@ def update_trajectory(prob, Xref, Uref, start=1):
         raise DimensionMismatch("update_trajectory!: Xref must be [nref, n] and Uref [nref, m]")
     if start < 1 or start - 1 + prob.N > Xref.shape[0]:
         raise DimensionMismatch("update_trajectory!: the reference is shorter than start + N - 1")
+    if not all(isinstance(c, QuadraticCostFunction) for c in prob.obj):
+        raise ArgumentError("update_trajectory! is defined for objectives of QuadraticCostFunctions (src/objective.jl:207)")
     for i, k in enumerate(range(start - 1, start - 1 + prob.N)):
         set_LQR_goal(prob.obj[i], Xref[k], Uref[k])
     prob._call("to_update_trajectory", K._dp(Xref), K._dp(Uref), int(Xref.shape[0]), int(start))

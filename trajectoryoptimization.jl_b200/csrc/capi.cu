@@ -142,8 +142,34 @@ void model_defaults(int model, int m, int& n_out, int& m_out, double* p) {
 
 int build_cost(to_handle* h, const to_cost_spec& tc, int n, int m, DevCost& c) {
     std::memset(&c, 0, sizeof(c));
+    if (tc.kind == TO_COST_EXPR) {   // user cost recorded as a program (RD.@autodiff CostFunction)
+        if (!tc.prog || tc.prog_len < 1 || tc.prog_len > TO_EXPR_LEN || tc.nconst < 0 || tc.nconst > TO_EXPR_CONST || (tc.nconst > 0 && !tc.consts))
+            return fail(h, TO_EINVAL, "expression cost: bad program size");
+        c.expr = 1; c.prog_len = tc.prog_len; c.terminal = tc.terminal != 0;
+        for (int j = 0; j < tc.prog_len; j++) {
+            const int op = tc.prog[3 * j], a = tc.prog[3 * j + 1], b = tc.prog[3 * j + 2];
+            const bool bin = op >= TO_OP_ADD && op <= TO_OP_DIV;
+            bool ok = op >= 0 && op <= TO_OP_RSUBC;
+            if (op == TO_OP_CONST) ok = ok && a >= 0 && a < tc.nconst;
+            else if (op == TO_OP_X) ok = ok && a >= 0 && a < n;
+            else if (op == TO_OP_U) ok = ok && a >= 0 && a < m;
+            else { ok = ok && a >= 0 && a < j; if (bin) ok = ok && b >= 0 && b < j; if (op == TO_OP_POWC || op >= TO_OP_ADDC) ok = ok && b >= 0 && b < tc.nconst; }
+            if (!ok) return fail(h, TO_EINVAL, "expression cost: invalid instruction");
+            c.prog[3 * j] = op; c.prog[3 * j + 1] = a; c.prog[3 * j + 2] = b;
+        }
+        for (int j = 0; j < tc.nconst; j++) c.pconst[j] = tc.consts[j];
+        return TO_OK;
+    }
     if (!tc.Q || !tc.R || !tc.q || !tc.r) return fail(h, TO_EINVAL, "cost: null Q/R/q/r");
-    c.diag = (tc.kind == TO_COST_DIAGONAL); c.terminal = tc.terminal != 0; c.c = tc.c;
+    c.diag = (tc.kind == TO_COST_DIAGONAL || tc.kind == TO_COST_DIAGONAL_QUAT); c.terminal = tc.terminal != 0; c.c = tc.c;
+    if (tc.kind == TO_COST_DIAGONAL_QUAT) {   // DiagonalQuatCost, src/lie_costs.jl:33-56
+        if (!tc.q_ref) return fail(h, TO_EINVAL, "DiagonalQuatCost: null q_ref");
+        c.quat = 1; c.w = tc.w;
+        for (int i = 0; i < 4; i++) {
+            c.q_ref[i] = tc.q_ref[i]; c.q_ind[i] = tc.q_ind ? tc.q_ind[i] - 1 : 3 + i;
+            if (c.q_ind[i] < 0 || c.q_ind[i] >= n) return fail(h, TO_EDIM, "DiagonalQuatCost: q_ind outside the state");
+        }
+    } else if (tc.kind != TO_COST_DIAGONAL && tc.kind != TO_COST_QUADRATIC) return fail(h, TO_EINVAL, "unknown cost kind");
     for (int i = 0; i < n; i++) c.q[i] = tc.q[i];
     for (int i = 0; i < m; i++) c.r[i] = tc.r[i];
     if (c.diag) {
@@ -232,6 +258,15 @@ int build_con(to_handle* h, const to_constraint_spec& tc, int n, int m, int N, D
             }
             break;
         }
+        case TO_CON_QUATVEC:   // QuatVecEq, src/constraints.jl:938-965
+            if (!tc.a || n < 4) return fail(h, TO_EINVAL, "QuatVecEq: null qf");
+            c.p = 3; c.sense = CONE_ZERO; c.ninds = 4;
+            for (int i = 0; i < 4; i++) {
+                c.a[i] = tc.a[i];
+                c.inds[i] = (tc.inds && tc.ninds == 4) ? tc.inds[i] - 1 : 3 + i;
+                if (c.inds[i] < 0 || c.inds[i] >= n) return fail(h, TO_EDIM, "QuatVecEq: qind outside the state");
+            }
+            break;
         default: return fail(h, TO_EINVAL, "unknown constraint kind");
     }
     if (c.p > TO_MAXP) return fail(h, TO_EINVAL, "constraint output dimension exceeds TO_MAXP");
@@ -283,6 +318,8 @@ int to_create(const to_spec* s, to_handle** out) {
     if (!s->dt || !s->costs || !s->cost_index || s->ncost < 1) return fail(nullptr, TO_EINVAL, "null dt / costs / cost_index");
     if (s->ncon < 0 || s->ncon > TO_MAXCON || (s->ncon > 0 && !s->cons)) return fail(nullptr, TO_EINVAL, "too many constraints (max 8) or null list");
     for (int k = 0; k < s->N - 1; k++) if (!(s->dt[k] > 0)) return fail(nullptr, TO_EINVAL, "time steps must be positive");   // tf > t0, src/problem.jl:50
+    if (s->error_state && s->model != TO_MODEL_QUADROTOR)
+        return fail(nullptr, TO_EINVAL, "error_state: the model has no Lie-group state (only the Quadrotor does)");
     if (s->params) for (int i = 0; i < s->nparams && i < 10; i++) params[i] = s->params[i];
     if (s->model == TO_MODEL_DOUBLE_INTEGRATOR) params[1] = 1.0 / params[0];
     if (s->model == TO_MODEL_QUADROTOR) {   // reciprocals used by the device dynamics (models.cuh)
@@ -321,7 +358,11 @@ int to_create(const to_spec* s, to_handle** out) {
         int rc = build_cost(h, s->costs[i], n, m, h->h_costs[i]);
         if (rc) return bail(rc);
         if (!h->h_costs[i].diag) P.all_diag_cost = 0;
+        if (h->h_costs[i].quat || h->h_costs[i].expr) { P.all_diag_cost = 0; P.dense_riccati = 1; }   // the fused fast paths assume purely quadratic costs
     }
+    P.lie = s->error_state ? 1 : 0; P.qs = 3; P.ne = P.lie ? n - 1 : n;
+    if (P.lie) P.dense_riccati = 1;
+    if (P.dense_riccati) h->overlap = false;   // lie.cu path: every kernel on the main stream
     h->h_cost_index.assign(s->cost_index, s->cost_index + N);
     for (int k = 0; k < N; k++)
         if (h->h_cost_index[k] < 0 || h->h_cost_index[k] >= s->ncost) { h->err = "cost_index out of range"; return bail(TO_EINVAL); }
@@ -358,7 +399,11 @@ int to_create(const to_spec* s, to_handle** out) {
     ALLOC(d_dt, N - 1); ALLOC(d_ci, N);
     ALLOC(h->d_costs, s->ncost); ALLOC(h->d_cons, std::max(1, s->ncon)); ALLOC(h->d_mu, std::max(1, s->ncon));
     ALLOC(P.x0, (size_t)B * n); ALLOC(P.X, TO_NBUF * P.strideX); ALLOC(P.U, TO_NBUF * P.strideU); ALLOC(P.cur, B);
-    ALLOC(P.AB, (size_t)B * (N - 1) * n * P.ldab); ALLOC(P.K, (size_t)B * (N - 1) * n * m); ALLOC(P.d, (size_t)B * (N - 1) * m);
+    ALLOC(P.AB, (size_t)B * (N - 1) * n * P.ldab); ALLOC(P.K, (size_t)B * (N - 1) * P.ne * m); ALLOC(P.d, (size_t)B * (N - 1) * m);
+    if (P.dense_riccati) {
+        const size_t nme = P.ne + m;
+        ALLOC(P.ABe, (size_t)B * (N - 1) * P.ne * nme); ALLOC(P.EG, (size_t)B * N * nme); ALLOC(P.EH, (size_t)B * N * nme * nme);
+    }
     ALLOC(P.lambda, (size_t)B * std::max(1, P.lambda_len));
     ALLOC(P.rho, B); ALLOC(P.drho, B); ALLOC(P.dV, 2 * (size_t)B); ALLOC(P.J, B); ALLOC(P.Jc, B); ALLOC(P.alpha, B);
     ALLOC(P.bp_status, B); ALLOC(P.ls_iters, B); ALLOC(P.accepted, B); ALLOC(P.acc1, B);
@@ -376,7 +421,7 @@ int to_create(const to_spec* s, to_handle** out) {
     okc &= cudaMemsetAsync(P.U, 0, sizeof(double) * TO_NBUF * P.strideU, st) == cudaSuccess;      // U0 = 0, src/problem.jl:84
     okc &= cudaMemsetAsync(P.cur, 0, sizeof(int) * B, st) == cudaSuccess;
     okc &= cudaMemsetAsync(P.AB, 0, sizeof(double) * (size_t)B * (N - 1) * n * P.ldab, st) == cudaSuccess;
-    okc &= cudaMemsetAsync(P.K, 0, sizeof(double) * (size_t)B * (N - 1) * n * m, st) == cudaSuccess;
+    okc &= cudaMemsetAsync(P.K, 0, sizeof(double) * (size_t)B * (N - 1) * P.ne * m, st) == cudaSuccess;
     okc &= cudaMemsetAsync(P.d, 0, sizeof(double) * (size_t)B * (N - 1) * m, st) == cudaSuccess;
     okc &= cudaMemsetAsync(P.lambda, 0, sizeof(double) * (size_t)B * std::max(1, P.lambda_len), st) == cudaSuccess;
     okc &= cudaMemsetAsync(P.rho, 0, sizeof(double) * B, st) == cudaSuccess;
@@ -733,8 +778,26 @@ static int solver_supported(to_handle* h) {
             return fail(h, TO_ESTATE, "the solver kernels take at most 16 rows per general (non Goal/Bound) constraint");
     return TO_OK;
 }
+// lie.cu path: materialise [A_e B_e] and the (error-state) cost + AL expansion of every knot, then the dense Riccati pass
+static int materialise_expansion(to_handle* h, double* EG, double* EH) {
+    const DevProblem& P = h->P;
+    const int nm = P.n + P.m;
+    const size_t ng = (size_t)P.B * P.N * nm, nh = ng * nm;
+    int rc = ensure_scratch(h, (ng + nh) * sizeof(double)); if (rc) return rc;
+    double* gf = (double*)h->scratch.ptr; double* hf = gf + ng;
+    CU(h, launch_al_expansion(P, gf, hf, h->stream)); h->launches++;
+    CU(h, launch_error_expansion(P, gf, hf, EG, EH, h->stream)); h->launches++;
+    return TO_OK;
+}
 static int do_backward(to_handle* h) {
-    { PhaseScope ps(h, TO_PHASE_BACKWARD); CU(h, launch_backward(h->P, h->d_work, h->stream)); }
+    if (h->P.dense_riccati) {
+        PhaseScope ps(h, TO_PHASE_BACKWARD);
+        int rc = materialise_expansion(h, h->P.EG, h->P.EH); if (rc) return rc;
+        CU(h, launch_error_dynamics(h->P, h->stream)); h->launches++;
+        CU(h, launch_backward_dense(h->P, h->stream));
+    } else {
+        PhaseScope ps(h, TO_PHASE_BACKWARD); CU(h, launch_backward(h->P, h->d_work, h->stream));
+    }
     h->launches++; h->phase_launches[TO_PHASE_BACKWARD]++;
     h->backward_done = true;
     return TO_OK;
@@ -821,8 +884,48 @@ int to_al_update(to_handle* h) {
 int to_get_gains(to_handle* h, double* K, double* d) {
     JOIN(h);
     if (!h) return TO_EINVAL;
-    if (K) CU(h, cudaMemcpyAsync(K, h->P.K, sizeof(double) * (size_t)h->P.B * (h->P.N - 1) * h->P.n * h->P.m, cudaMemcpyDeviceToHost, h->stream));
+    if (K) CU(h, cudaMemcpyAsync(K, h->P.K, sizeof(double) * (size_t)h->P.B * (h->P.N - 1) * h->P.ne * h->P.m, cudaMemcpyDeviceToHost, h->stream));
     if (d) CU(h, cudaMemcpyAsync(d, h->P.d, sizeof(double) * (size_t)h->P.B * (h->P.N - 1) * h->P.m, cudaMemcpyDeviceToHost, h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
+    return TO_OK;
+}
+// ---- Lie-group error state (lie.cu) ---------------------------------------------------------------------------
+int to_error_state_dim(const to_handle* h, int32_t* ne) {
+    if (!h || !ne) return TO_EINVAL;
+    *ne = h->P.ne;
+    return TO_OK;
+}
+int to_state_diff(to_handle* h, const double* Xbar, double* dx) {
+    JOIN(h);
+    if (!h || !Xbar || !dx) return TO_EINVAL;
+    const size_t nin = (size_t)h->P.B * h->P.N * h->P.n, nout = (size_t)h->P.B * h->P.N * h->P.ne;
+    int rc = ensure_scratch(h, (nin + nout) * sizeof(double)); if (rc) return rc;
+    double* din = (double*)h->scratch.ptr; double* dout = din + nin;
+    CU(h, cudaMemcpyAsync(din, Xbar, nin * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    CU(h, launch_state_diff(h->P, din, dout, h->stream)); h->launches++;
+    CU(h, cudaMemcpyAsync(dx, dout, nout * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
+    return TO_OK;
+}
+int to_get_error_dynamics(to_handle* h, double* ABe) {
+    JOIN(h);
+    if (!h || !ABe) return TO_EINVAL;
+    if (!h->expanded) return fail(h, TO_ESTATE, "to_get_error_dynamics before to_expand");
+    if (!h->P.dense_riccati) return to_get_dynamics_jacobians(h, ABe);     // no error state: [A_e B_e] = [A B]
+    CU(h, launch_error_dynamics(h->P, h->stream)); h->launches++;
+    const size_t cnt = (size_t)h->P.B * (h->P.N - 1) * h->P.ne * (h->P.ne + h->P.m);
+    CU(h, cudaMemcpyAsync(ABe, h->P.ABe, cnt * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
+    return TO_OK;
+}
+int to_error_expansion(to_handle* h, double* grad, double* hess) {
+    JOIN(h);
+    if (!h || !grad || !hess) return TO_EINVAL;
+    if (!h->P.dense_riccati) return to_al_expansion(h, grad, hess);
+    int rc = materialise_expansion(h, h->P.EG, h->P.EH); if (rc) return rc;
+    const size_t nme = h->P.ne + h->P.m, ng = (size_t)h->P.B * h->P.N * nme;
+    CU(h, cudaMemcpyAsync(grad, h->P.EG, ng * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CU(h, cudaMemcpyAsync(hess, h->P.EH, ng * nme * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     CU(h, cudaStreamSynchronize(h->stream));
     return TO_OK;
 }
@@ -929,9 +1032,13 @@ int64_t to_launch_count(const to_handle* h) { return h ? h->launches : 0; }
 int to_algorithmic_bytes(const to_handle* h, int64_t* E, int64_t* R, int64_t* F) {
     if (!h) return TO_EINVAL;
     const int64_t n = h->P.n, m = h->P.m, N = h->P.N, w = 8;
-    const int64_t XU = (n + m) * N, AB = n * (n + m) * (N - 1), KD = m * (n + 1) * (N - 1), L = h->P.lambda_len;
+    const int64_t ne = h->P.ne;
+    const int64_t XU = (n + m) * N, AB = n * (n + m) * (N - 1), KD = m * (ne + 1) * (N - 1), L = h->P.lambda_len;
+    // materialised expansion (lie.cu): HES = per-knot gradient + Hessian in the (error) state, [A_e B_e] written once and read once
+    const int64_t HES = h->P.dense_riccati ? ((ne + m) * (ne + m) + (ne + m)) * N : 0;
+    const int64_t ABe = h->P.dense_riccati ? ne * (ne + m) * (N - 1) : 0;
     if (E) *E = (XU + AB) * w;
-    if (R) *R = (AB + XU + KD + L) * w;
+    if (R) *R = h->P.dense_riccati ? (AB + ABe + XU + L + 2 * HES + ABe + KD) * w : (AB + XU + KD + L) * w;
     if (F) *F = (2 * XU + KD + L) * w + 8;
     return TO_OK;
 }

@@ -18,12 +18,14 @@
 #define TO_MAXCON 8
 #define TO_MAXP 32          // rows of one constraint at one knot
 #define TO_CON_A 256
+#define TO_EXPR_LEN 128      // == TO_EXPR_MAXLEN / TO_EXPR_MAXCONST of include/trajopt_b200.h
+#define TO_EXPR_CONST 32
 #define TO_NBUF 9            // trajectory buffers per instance: the live one + 8 line-search candidates
 
 // reference enums (mirrors include/trajopt_b200.h)
 enum { MODEL_DOUBLE_INTEGRATOR = 0, MODEL_CARTPOLE = 1, MODEL_QUADROTOR = 2, MODEL_ACROBOT = 3 };
 enum { CONE_ZERO = 0, CONE_NEGATIVE_ORTHANT = 1, CONE_SECOND_ORDER = 2, CONE_IDENTITY = 3, CONE_POSITIVE_ORTHANT = 4 };
-enum { CON_GOAL = 0, CON_BOUND = 1, CON_LINEAR = 2, CON_CIRCLE = 3, CON_SPHERE = 4, CON_NORM = 5, CON_COLLISION = 6 };
+enum { CON_GOAL = 0, CON_BOUND = 1, CON_LINEAR = 2, CON_CIRCLE = 3, CON_SPHERE = 4, CON_NORM = 5, CON_COLLISION = 6, CON_QUATVEC = 7 };
 
 // QuadraticCostFunction (reference src/cost_functions.jl:326-347, :417-454); dense storage + diagonal copy
 struct DevCost {
@@ -34,6 +36,13 @@ struct DevCost {
     double Q[TO_MAXN * TO_MAXN];   // n*n col-major (stride n)
     double R[TO_MAXM * TO_MAXM];   // m*m col-major (stride m)
     double H[TO_MAXM * TO_MAXN];   // m*n col-major (stride m)
+    // DiagonalQuatCost (reference src/lie_costs.jl:33-95): + w min(1 + q_ref'p, 1 - q_ref'p), p = x[q_ind]
+    int quat, q_ind[4], pad2[3];
+    double w, q_ref[4];
+    // user cost recorded as a straight-line program (to_cost_spec EXPR; reference RD.@autodiff CostFunction, docs/src/costfunction_interface.md:30-50)
+    int expr, prog_len, pad3[2];
+    int prog[3 * TO_EXPR_LEN];
+    double pconst[TO_EXPR_CONST];
 };
 
 // AbstractConstraint descriptor (reference src/constraints.jl); `diagonal` constraints (Goal, Bound) have a
@@ -72,6 +81,13 @@ struct DevProblem {
     int max_p_knot;           // largest number of constraint rows active at one knot
     int max_terms_per_z;      // largest number of Goal/Bound rows acting on one z entry
     int max_cons_knot;        // largest number of constraints active at one knot
+    // Lie-group error state (to_spec.error_state; lie.cu): the solver kernels work on ne = n - 1 dimensions, the quaternion
+    // x[qs..qs+3] contributing its 3-dimensional differential.  dense_riccati: the backward pass reads the per-knot expansion
+    // (EG, EH) and [A_e B_e] (ABe) materialised in HBM by lie.cu instead of expanding in-kernel (error state, quaternion costs).
+    int lie, ne, qs, dense_riccati;
+    double* ABe;              // [B][N-1][ne+m][ne]   ne x (ne+m) col-major
+    double* EG;               // [B][N][ne+m]
+    double* EH;               // [B][N][ne+m][ne+m]
     double params[16];
     DevOptions opt;
     const double* dt;         // [N-1]

@@ -18,7 +18,58 @@ __device__ __forceinline__ int dualcone(int cone) {
     return cone == CONE_IDENTITY ? CONE_ZERO : (cone == CONE_ZERO ? CONE_IDENTITY : cone);
 }
 
+// ---- user cost as a straight-line program, evaluated with second-order forward-mode duals (value, d/ds, d/dt, d2/dsdt) ----------
+struct Hyper { double v, d1, d2, d12; };
+__device__ __forceinline__ Hyper hyp_unary(const Hyper& a, double f, double f1, double f2) {
+    Hyper r; r.v = f; r.d1 = f1 * a.d1; r.d2 = f1 * a.d2; r.d12 = f1 * a.d12 + f2 * a.d1 * a.d2; return r;
+}
+__device__ __forceinline__ Hyper hyp_mul(const Hyper& a, const Hyper& b) {
+    Hyper r; r.v = a.v * b.v; r.d1 = a.d1 * b.v + a.v * b.d1; r.d2 = a.d2 * b.v + a.v * b.d2;
+    r.d12 = a.d12 * b.v + a.d1 * b.d2 + a.d2 * b.d1 + a.v * b.d12; return r;
+}
+// z_s1 seeded in d1, z_s2 in d2 (index into [x;u], -1 = none); has_u = false: u = 0 (terminal knot).  Mirrors oracle expr_eval.
+__device__ inline Hyper expr_eval(const DevCost& c, int n, const double* x, const double* u, bool has_u, int s1, int s2) {
+    Hyper reg[TO_EXPR_LEN];
+    const int L = c.prog_len;
+    for (int i = 0; i < L; i++) {
+        const int op = c.prog[3 * i], a = c.prog[3 * i + 1], b = c.prog[3 * i + 2];
+        Hyper r; r.v = 0; r.d1 = 0; r.d2 = 0; r.d12 = 0;
+        switch (op) {
+            case 0: r.v = c.pconst[a]; break;
+            case 1: r.v = x[a]; r.d1 = (a == s1) ? 1.0 : 0.0; r.d2 = (a == s2) ? 1.0 : 0.0; break;
+            case 2: r.v = has_u ? u[a] : 0.0; r.d1 = (n + a == s1) ? 1.0 : 0.0; r.d2 = (n + a == s2) ? 1.0 : 0.0; break;
+            case 3: r.v = reg[a].v + reg[b].v; r.d1 = reg[a].d1 + reg[b].d1; r.d2 = reg[a].d2 + reg[b].d2; r.d12 = reg[a].d12 + reg[b].d12; break;
+            case 4: r.v = reg[a].v - reg[b].v; r.d1 = reg[a].d1 - reg[b].d1; r.d2 = reg[a].d2 - reg[b].d2; r.d12 = reg[a].d12 - reg[b].d12; break;
+            case 5: r = hyp_mul(reg[a], reg[b]); break;
+            case 6: { const double iv = 1.0 / reg[b].v; r = hyp_mul(reg[a], hyp_unary(reg[b], iv, -iv * iv, 2 * iv * iv * iv)); break; }
+            case 7: r.v = -reg[a].v; r.d1 = -reg[a].d1; r.d2 = -reg[a].d2; r.d12 = -reg[a].d12; break;
+            case 8: { double sv, cv; sincos(reg[a].v, &sv, &cv); r = hyp_unary(reg[a], sv, cv, -sv); break; }
+            case 9: { double sv, cv; sincos(reg[a].v, &sv, &cv); r = hyp_unary(reg[a], cv, -sv, -cv); break; }
+            case 10: { const double e = exp(reg[a].v); r = hyp_unary(reg[a], e, e, e); break; }
+            case 11: { const double iv = 1.0 / reg[a].v; r = hyp_unary(reg[a], log(reg[a].v), iv, -iv * iv); break; }
+            case 12: { const double sq = sqrt(reg[a].v); r = hyp_unary(reg[a], sq, 0.5 / sq, -0.25 / (sq * reg[a].v)); break; }
+            case 13: { const double e = c.pconst[b], v = reg[a].v; r = hyp_unary(reg[a], pow(v, e), e * pow(v, e - 1), e * (e - 1) * pow(v, e - 2)); break; }
+            case 14: { const double t = tanh(reg[a].v); r = hyp_unary(reg[a], t, 1 - t * t, -2 * t * (1 - t * t)); break; }
+            case 15: r = reg[a]; r.v += c.pconst[b]; break;
+            case 16: { const double k = c.pconst[b]; r.v = reg[a].v * k; r.d1 = reg[a].d1 * k; r.d2 = reg[a].d2 * k; r.d12 = reg[a].d12 * k; break; }
+            case 17: { const double k = c.pconst[b]; r.v = reg[a].v / k; r.d1 = reg[a].d1 / k; r.d2 = reg[a].d2 / k; r.d12 = reg[a].d12 / k; break; }
+            case 18: { const double k = c.pconst[b], iv = 1.0 / reg[a].v; r = hyp_unary(reg[a], k * iv, -k * iv * iv, 2 * k * iv * iv * iv); break; }
+            case 19: r.v = c.pconst[b] - reg[a].v; r.d1 = -reg[a].d1; r.d2 = -reg[a].d2; r.d12 = -reg[a].d12; break;
+        }
+        reg[i] = r;
+    }
+    return reg[L - 1];
+}
+
+// geodesic term of DiagonalQuatCost (src/lie_costs.jl:74-76): w min(1 + dq, 1 - dq), dq = q_ref'x[q_ind]
+__device__ __forceinline__ double quat_cost_term(const DevCost& c, const double* x) {
+    double dq = 0;
+    for (int i = 0; i < 4; i++) dq = fma(c.q_ref[i], x[c.q_ind[i]], dq);
+    return c.w * fmin(1 + dq, 1 - dq);
+}
+
 __device__ inline double cost_value(const DevCost& c, int n, int m, const double* x, const double* u, bool has_u) {
+    if (c.expr) return expr_eval(c, n, x, u, has_u, -1, -1).v;
     double J = 0;
     if (c.diag) {
         double a = 0, l = 0;
@@ -29,6 +80,7 @@ __device__ inline double cost_value(const DevCost& c, int n, int m, const double
             for (int i = 0; i < m; i++) { au = fma(c.Rd[i] * u[i], u[i], au); lu = fma(c.r[i], u[i], lu); }
             J += 0.5 * au + lu;
         }
+        if (c.quat) J += quat_cost_term(c, x);
         return J;
     }
     for (int j = 0; j < n; j++) {
@@ -59,12 +111,30 @@ __device__ inline double cost_value(const DevCost& c, int n, int m, const double
 }
 
 // grad[n+m]; the u-part is left untouched at the terminal knot (the reference skips it when is_terminal(z))
+template <bool QUAT = true>
+__device__ inline void cost_gradient_quadratic(const DevCost& c, int n, int m, const double* x, const double* u, bool is_terminal, double* grad);
 __device__ inline void cost_gradient(const DevCost& c, int n, int m, const double* x, const double* u, bool is_terminal, double* grad) {
+    if (c.expr) {   // RD.gradient!(ForwardAD) of a user cost
+        const int lim = is_terminal ? n : n + m;
+        for (int i = 0; i < lim; i++) grad[i] = expr_eval(c, n, x, u, !is_terminal, i, -1).d1;
+        return;
+    }
+    cost_gradient_quadratic(c, n, m, x, u, is_terminal, grad);
+}
+// QuadraticCostFunction only (the register-resident kernels call this directly with QUAT = false: no dynamically indexed stores)
+template <bool QUAT>
+__device__ inline void cost_gradient_quadratic(const DevCost& c, int n, int m, const double* x, const double* u, bool is_terminal, double* grad) {
     for (int i = 0; i < n; i++) {
         double g = c.q[i];
         if (c.diag) g = fma(c.Qd[i], x[i], g);
         else for (int j = 0; j < n; j++) g = fma(c.Q[j * n + i], x[j], g);
         grad[i] = g;
+    }
+    if (QUAT && c.quat) {   // gradient!(::DiagonalQuatCost) src/lie_costs.jl:79-95: -+ w q_ref by the sign of q_ref'p
+        double dq = 0;
+        for (int i = 0; i < 4; i++) dq = fma(c.q_ref[i], x[c.q_ind[i]], dq);
+        const double sw = dq < 0 ? c.w : -c.w;
+        for (int i = 0; i < 4; i++) grad[c.q_ind[i]] = fma(sw, c.q_ref[i], grad[c.q_ind[i]]);
     }
     if (!is_terminal) {
         for (int i = 0; i < m; i++) {
@@ -84,7 +154,19 @@ __device__ inline void cost_gradient(const DevCost& c, int n, int m, const doubl
 
 // hess (n+m)x(n+m) col-major, written in full and symmetric (the reference writes only the lower-left H block
 // and leaves the rest to the caller's zero initialisation)
-__device__ inline void cost_hessian(const DevCost& c, int n, int m, bool is_terminal, double* hess) {
+__device__ inline void cost_hessian_quadratic(const DevCost& c, int n, int m, bool is_terminal, double* hess);
+__device__ inline void cost_hessian(const DevCost& c, int n, int m, const double* x, const double* u, bool is_terminal, double* hess) {
+    const int nm = n + m;
+    if (c.expr) {   // RD.hessian!(ForwardAD) of a user cost: one second-order pass per entry of the lower triangle
+        for (int i = 0; i < nm * nm; i++) hess[i] = 0;
+        const int lim = is_terminal ? n : nm;
+        for (int j = 0; j < lim; j++)
+            for (int i = j; i < lim; i++) { const double h = expr_eval(c, n, x, u, !is_terminal, i, j).d12; hess[j * nm + i] = h; hess[i * nm + j] = h; }
+        return;
+    }
+    cost_hessian_quadratic(c, n, m, is_terminal, hess);
+}
+__device__ inline void cost_hessian_quadratic(const DevCost& c, int n, int m, bool is_terminal, double* hess) {
     const int nm = n + m;
     for (int i = 0; i < nm * nm; i++) hess[i] = 0;
     for (int j = 0; j < n; j++)
@@ -150,6 +232,15 @@ __device__ inline void con_evaluate(const DevCon& con, int n, int m, const doubl
             c[0] = s;
             break;
         }
+        case CON_QUATVEC: {   // QuatVecEq src/constraints.jl:947-956
+            double q[4], nrm = 0, dq = 0;
+            for (int i = 0; i < 4; i++) { q[i] = x[con.inds[i]]; nrm = fma(q[i], q[i], nrm); }
+            nrm = sqrt(nrm);
+            for (int i = 0; i < 4; i++) { q[i] /= nrm; dq = fma(con.a[i], q[i], dq); }
+            const double sg = dq < 0 ? -1.0 : 1.0;
+            for (int i = 0; i < 3; i++) c[i] = -(sg * con.a[i + 1] - q[i + 1]);
+            break;
+        }
     }
 }
 
@@ -194,6 +285,15 @@ __device__ inline void con_jacobian(const DevCon& con, int n, int m, const doubl
                 jac[con.inds[i] * p] = -2 * d;
                 jac[con.inds[D + i] * p] = 2 * d;
             }
+            break;
+        }
+        case CON_QUATVEC: {   // d normalize(q)/dq = (I - qh qh')/|q|, rows 2:4 (what ForwardAD gives, src/constraints.jl:938,962)
+            double q[4], nrm = 0;
+            for (int i = 0; i < 4; i++) { q[i] = x[con.inds[i]]; nrm = fma(q[i], q[i], nrm); }
+            nrm = sqrt(nrm);
+            for (int i = 0; i < 4; i++) q[i] /= nrm;
+            for (int j = 0; j < 4; j++)
+                for (int i = 0; i < 3; i++) jac[con.inds[j] * p + i] = ((i + 1 == j ? 1.0 : 0.0) - q[i + 1] * q[j]) / nrm;
             break;
         }
     }
@@ -327,7 +427,7 @@ __device__ inline void al_knot_expansion(const DevProblem& P, int k0, const doub
     const DevCost& cost = P.costs[P.cost_index[k0]];
     for (int i = 0; i < nm; i++) grad[i] = 0;
     cost_gradient(cost, n, m, x, u, last, grad);
-    cost_hessian(cost, n, m, last, hess);
+    cost_hessian(cost, n, m, x, u, last, hess);
     const int lim = last ? n : nm;
     for (int ci = 0; ci < P.ncon; ci++) {
         const DevCon& con = P.cons[ci];
@@ -336,8 +436,19 @@ __device__ inline void al_knot_expansion(const DevProblem& P, int k0, const doub
         const double mu = P.mu[ci];
         const double* lam = lam_b + con.offset + (size_t)(k0 + 1 - con.first) * p;
         double c[TO_MAXP], lbar[TO_MAXP], lp[TO_MAXP];
-        double jac[TO_MAXP * TO_MAXNM], Dm[TO_MAXP * TO_MAXP], tmp[TO_MAXP * TO_MAXNM];
         con_evaluate(con, n, m, x, u, c);
+        if (con.diagonal) {   // Goal / Bound: +-1 selector rows (src/constraints.jl:62-68, :757-765) -- row by row, no dense products
+            const bool eq = (con.kind == CON_GOAL);
+            const int nrow = eq ? p : con.n_max + con.n_min;
+            for (int r = 0; r < nrow; r++) {
+                const int j = eq ? con.inds[r] : (r < con.n_max ? con.a_max[r] : con.a_min[r - con.n_max]);
+                const double sgn = (eq || r < con.n_max) ? 1.0 : -1.0;
+                const double lb = lam[r] - mu * c[r];
+                if ((eq || lb <= 0.0) && j < lim) { grad[j] -= sgn * lb; hess[j * nm + j] += mu; }
+            }
+            continue;
+        }
+        double jac[TO_MAXP * TO_MAXNM], Dm[TO_MAXP * TO_MAXP], tmp[TO_MAXP * TO_MAXNM];
         con_jacobian(con, n, m, x, u, jac);
         for (int i = 0; i < p; i++) lbar[i] = lam[i] - mu * c[i];
         const int dc = dualcone(con.sense);
@@ -360,4 +471,28 @@ __device__ inline void al_knot_expansion(const DevProblem& P, int k0, const doub
             }
         }
     }
+}
+
+// ---- Lie-group error state (RobotDynamics LieState / Rotations.jl / Altro.jl, restated in oracle/oracle.hpp) -------------------
+// grad-differential(q) = L(q) H, 4 x 3 col-major: columns (-x,w,z,-y), (-y,-z,w,x), (-z,y,-x,w)
+__device__ __forceinline__ void quat_G(const double* q, double* G) {
+    const double w = q[0], x = q[1], y = q[2], z = q[3];
+    G[0] = -x; G[1] = w;  G[2] = z;   G[3] = -y;
+    G[4] = -y; G[5] = -z; G[6] = w;   G[7] = x;
+    G[8] = -z; G[9] = y;  G[10] = -x; G[11] = w;
+}
+// rotation part of RD.state_diff(xbar, x): inverse Cayley map of conj(q) (x) p
+__device__ __forceinline__ void quat_diff(const double* q, const double* p, double* phi) {
+    const double dw = q[0] * p[0] + q[1] * p[1] + q[2] * p[2] + q[3] * p[3];
+    const double d1 = q[0] * p[1] - p[0] * q[1] - (q[2] * p[3] - q[3] * p[2]);
+    const double d2 = q[0] * p[2] - p[0] * q[2] - (q[3] * p[1] - q[1] * p[3]);
+    const double d3 = q[0] * p[3] - p[0] * q[3] - (q[1] * p[2] - q[2] * p[1]);
+    phi[0] = d1 / dw; phi[1] = d2 / dw; phi[2] = d3 / dw;
+}
+// dx[ne] = state_diff(xbar, x); plain difference when the problem has no Lie-group state
+__device__ __forceinline__ void state_diff(bool lie, int n, int qs, const double* xbar, const double* x, double* dx) {
+    if (!lie) { for (int i = 0; i < n; i++) dx[i] = xbar[i] - x[i]; return; }
+    for (int i = 0; i < qs; i++) dx[i] = xbar[i] - x[i];
+    quat_diff(x + qs, xbar + qs, dx + qs);
+    for (int i = qs + 4; i < n; i++) dx[i - 1] = xbar[i] - x[i];
 }

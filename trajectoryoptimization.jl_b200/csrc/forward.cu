@@ -106,9 +106,9 @@ template <int NPEND> __device__ __forceinline__ void cp_async_wait() { asm volat
 
 // shared-memory stage of one knot's operands for the IPB instances of a CTA.
 // K_k is stored as 16-byte pairs [pair][IPB][2] (when n*m is even), everything else as 8-byte slots [slot][IPB].
-template <int n, int m, int IPB>
+template <int n, int m, int IPB, int NE = n>
 struct Stage {
-    static constexpr int KSLOTS = n * m;
+    static constexpr int KSLOTS = NE * m;     // K_k is m x NE (NE = n - 1 on the Lie-group error state)
     static constexpr bool K16 = (KSLOTS % 2) == 0;
     static constexpr int OFF_D = KSLOTS, OFF_U = OFF_D + m, OFF_X = OFF_U + m, OFF_L = OFF_X + n;
     static constexpr int LAM_SLOTS = 2 * (n + m);
@@ -119,12 +119,12 @@ struct Stage {
 };
 
 // lanes of a group cooperatively issue the async copies of knot k's operands of instance g
-template <int n, int m, int IPB, int G>
+template <int n, int m, int IPB, int G, int NE>
 __device__ __forceinline__ void prefetch_knot(double* base, int g, int l, int k, const double* Kg, const double* dg, const double* X,
                                               const double* U, const double* lam_b, const FwdTab& tab, int N) {
-    using S = Stage<n, m, IPB>;
+    using S = Stage<n, m, IPB, NE>;
     if (k < N - 1) {
-        const double* Kk = Kg + (size_t)k * n * m;
+        const double* Kk = Kg + (size_t)k * NE * m;
         if (S::K16) {
 #pragma unroll
             for (int c = 0; c < (S::KSLOTS / 2 + G - 1) / G; c++) {
@@ -159,17 +159,17 @@ __device__ __forceinline__ void prefetch_knot(double* base, int g, int l, int k,
 
 // closed-loop rollout of instance b (group g of the CTA) with step size alpha, diagonal costs, Goal/Bound constraints.
 // The candidate trajectory goes to buffer `cbuf`.  Returns the merit; `ok` = no blow-up.
-template <int MODEL, int IPB, int G>
+template <int MODEL, int IPB, int G, bool LIE>
 __device__ __forceinline__ double rollout_fast(const DevProblem& P, const FwdTab& tab, double* stage, int b, int g, int l, unsigned gmask,
                                                double alpha, int cbuf, bool& ok, double& viol) {
-    constexpr int n = ModelDims<MODEL>::n, m = ModelDims<MODEL>::m;
-    using S = Stage<n, m, IPB>;
+    constexpr int n = ModelDims<MODEL>::n, m = ModelDims<MODEL>::m, NE = LIE ? n - 1 : n;
+    using S = Stage<n, m, IPB, NE>;
     const int N = P.N, buf = P.cur[b];
     const double* X = traj_X(P, buf, b);
     const double* U = traj_U(P, buf, b);
     double* Xc = traj_Xw(P, cbuf, b);
     double* Uc = traj_Uw(P, cbuf, b);
-    const double* Kg = P.K + (size_t)b * (N - 1) * n * m;
+    const double* Kg = P.K + (size_t)b * (N - 1) * NE * m;
     const double* dg = P.d + (size_t)b * (N - 1) * m;
     const double* lam_b = P.lambda + (size_t)b * P.lambda_len;
     double x[n], u[m], xn[n];
@@ -177,13 +177,13 @@ __device__ __forceinline__ double rollout_fast(const DevProblem& P, const FwdTab
     ok = true; viol = 0.0;
 #pragma unroll
     for (int i = 0; i < n; i++) x[i] = P.x0[(size_t)b * n + i];
-    prefetch_knot<n, m, IPB, G>(stage, g, l, 0, Kg, dg, X, U, lam_b, tab, N);
+    prefetch_knot<n, m, IPB, G, NE>(stage, g, l, 0, Kg, dg, X, U, lam_b, tab, N);
     cp_async_commit();
     for (int k = 0; k < N; k++) {
         const bool last = (k == N - 1);
         const int sb = k & 1;
         __syncwarp(gmask);                      // every lane of the group is done reading stage sb^1 (knot k-1)
-        if (!last) prefetch_knot<n, m, IPB, G>(stage + (sb ^ 1) * S::DOUBLES, g, l, k + 1, Kg, dg, X, U, lam_b, tab, N);
+        if (!last) prefetch_knot<n, m, IPB, G, NE>(stage + (sb ^ 1) * S::DOUBLES, g, l, k + 1, Kg, dg, X, U, lam_b, tab, N);
         cp_async_commit();
         cp_async_wait<1>();                     // this lane's copies for knot k have landed ...
         __syncwarp(gmask);                      // ... and so have the other lanes'
@@ -191,9 +191,19 @@ __device__ __forceinline__ double rollout_fast(const DevProblem& P, const FwdTab
         if (!last) {
 #pragma unroll
             for (int a = 0; a < m; a++) u[a] = fma(alpha, st[S::sidx(S::OFF_D + a, g)], st[S::sidx(S::OFF_U + a, g)]);
+            double dxe[NE];   // RD.state_diff(xbar_k, x_k): plain difference, or the Cayley error of the attitude (LIE)
+            if constexpr (LIE) {
+                double xr[n];
 #pragma unroll
-            for (int i = 0; i < n; i++) {
-                const double dx = x[i] - st[S::sidx(S::OFF_X + i, g)];
+                for (int i = 0; i < n; i++) xr[i] = st[S::sidx(S::OFF_X + i, g)];
+                state_diff(true, n, 3, x, xr, dxe);
+            } else {
+#pragma unroll
+                for (int i = 0; i < n; i++) dxe[i] = x[i] - st[S::sidx(S::OFF_X + i, g)];
+            }
+#pragma unroll
+            for (int i = 0; i < NE; i++) {
+                const double dx = dxe[i];
                 if (S::K16 && (m % 2 == 0)) {
 #pragma unroll
                     for (int a = 0; a < m; a += 2) {
@@ -305,15 +315,15 @@ __device__ __forceinline__ double rollout_fast(const DevProblem& P, const FwdTab
 }
 
 // generic path (dense costs or general constraints): pointer-based evaluation, operands read directly from global
-template <int MODEL>
+template <int MODEL, bool LIE>
 __device__ __forceinline__ double rollout_generic(const DevProblem& P, int b, double alpha, int cbuf, bool& ok, double& viol) {
-    constexpr int n = ModelDims<MODEL>::n, m = ModelDims<MODEL>::m;
+    constexpr int n = ModelDims<MODEL>::n, m = ModelDims<MODEL>::m, NE = LIE ? n - 1 : n;
     const int N = P.N, buf = P.cur[b];
     const double* X = traj_X(P, buf, b);
     const double* U = traj_U(P, buf, b);
     double* Xc = traj_Xw(P, cbuf, b);
     double* Uc = traj_Uw(P, cbuf, b);
-    const double* Kg = P.K + (size_t)b * (N - 1) * n * m;
+    const double* Kg = P.K + (size_t)b * (N - 1) * NE * m;
     const double* dg = P.d + (size_t)b * (N - 1) * m;
     const double* lam_b = P.lambda + (size_t)b * P.lambda_len;
     double x[n], u[m], xn[n];
@@ -326,11 +336,15 @@ __device__ __forceinline__ double rollout_generic(const DevProblem& P, int b, do
         if (!last) {
 #pragma unroll
             for (int a = 0; a < m; a++) u[a] = fma(alpha, dg[(size_t)k * m + a], U[(size_t)k * m + a]);
+            double dxe[NE], xr[n];
 #pragma unroll
-            for (int i = 0; i < n; i++) {
-                const double dx = x[i] - X[(size_t)k * n + i];
+            for (int i = 0; i < n; i++) xr[i] = X[(size_t)k * n + i];
+            state_diff(LIE, n, 3, x, xr, dxe);
 #pragma unroll
-                for (int a = 0; a < m; a++) u[a] = fma(Kg[(size_t)k * n * m + i * m + a], dx, u[a]);
+            for (int i = 0; i < NE; i++) {
+                const double dx = dxe[i];
+#pragma unroll
+                for (int a = 0; a < m; a++) u[a] = fma(Kg[(size_t)k * NE * m + i * m + a], dx, u[a]);
             }
 #pragma unroll
             for (int a = 0; a < m; a++) if (!(fabs(u[a]) <= P.opt.max_control_value)) ok = false;
@@ -367,13 +381,13 @@ extern __shared__ __align__(16) unsigned char fwd_smem[];
 
 // One line-search pass: lane l of group g evaluates trial (trial0 + l) of instance b.
 //   first_pass : ignore / reset accepted[b];   final_pass : commit failures (no acceptable step size).
-template <int MODEL, int G, bool FAST, int LANES>
+template <int MODEL, int G, bool FAST, int LANES, bool LIE>
 __global__ void __launch_bounds__(FWD_THREADS) k_linesearch(const DevProblem P, int trial0, int first_pass, int final_pass) {
-    constexpr int n = ModelDims<MODEL>::n, m = ModelDims<MODEL>::m;
+    constexpr int n = ModelDims<MODEL>::n, m = ModelDims<MODEL>::m, NE = LIE ? n - 1 : n;
     // LANES = 16: only half of the warp carries groups.  The pass is a latency-bound FP64 chain at ~4 warps per SM, and
     // an FP64 instruction of a half-empty warp takes one pipe pass instead of two (profiles/r01_notes.md).
     constexpr int IPB = LANES / G;
-    using S = Stage<n, m, IPB>;
+    using S = Stage<n, m, IPB, NE>;
     FwdTab* tab = reinterpret_cast<FwdTab*>(fwd_smem);
     double* stage = reinterpret_cast<double*>(fwd_smem + sizeof(FwdTab));
     const int g = (threadIdx.x % LANES) / G, l = threadIdx.x % G;
@@ -394,8 +408,8 @@ __global__ void __launch_bounds__(FWD_THREADS) k_linesearch(const DevProblem P, 
         const int cbuf = (P.cur[b] + 1 + l) % TO_NBUF;
         bool ok = false;
         double J, viol = 0.0;
-        if (FAST) J = rollout_fast<MODEL, IPB, G>(P, *tab, stage, b, g, l, gmask, alpha, cbuf, ok, viol);
-        else J = rollout_generic<MODEL>(P, b, alpha, cbuf, ok, viol);
+        if (FAST) J = rollout_fast<MODEL, IPB, G, LIE>(P, *tab, stage, b, g, l, gmask, alpha, cbuf, ok, viol);
+        else J = rollout_generic<MODEL, LIE>(P, b, alpha, cbuf, ok, viol);
         const bool good = (trial <= P.opt.ls_iters) && ls_accept(P, J, P.J[b], alpha, P.dV[2 * b], P.dV[2 * b + 1], ok);
         const unsigned votes = __ballot_sync(gmask, good) & gmask;
         if (votes) {
@@ -421,13 +435,13 @@ __global__ void __launch_bounds__(FWD_THREADS) k_linesearch(const DevProblem P, 
     (void)sizeof(S);
 }
 
-template <int MODEL, int G, bool FAST, int LANES>
+template <int MODEL, int G, bool FAST, int LANES, bool LIE = false>
 cudaError_t launch_pass_l(const DevProblem& P, int trial0, int first_pass, int final_pass, cudaStream_t s) {
-    constexpr int n = ModelDims<MODEL>::n, m = ModelDims<MODEL>::m;
+    constexpr int n = ModelDims<MODEL>::n, m = ModelDims<MODEL>::m, NE = LIE ? n - 1 : n;
     constexpr int IPB = LANES / G;
     const int blocks = (P.B + IPB - 1) / IPB;
-    const size_t smem = FAST ? sizeof(FwdTab) + (size_t)2 * Stage<n, m, IPB>::DOUBLES * sizeof(double) : 0;
-    auto kern = k_linesearch<MODEL, G, FAST, LANES>;
+    const size_t smem = FAST ? sizeof(FwdTab) + (size_t)2 * Stage<n, m, IPB, NE>::DOUBLES * sizeof(double) : 0;
+    auto kern = k_linesearch<MODEL, G, FAST, LANES, LIE>;
     static bool configured = false;
     if (!configured && smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -444,6 +458,12 @@ cudaError_t launch_pass(const DevProblem& P, int trial0, int first_pass, int fin
     static int lanes1 = -1, lanes2 = -1;
     if (lanes1 < 0) { const char* v = getenv("TO_FWD_LANES_P1"); lanes1 = v ? atoi(v) : 16; v = getenv("TO_FWD_LANES_P2"); lanes2 = v ? atoi(v) : 32; }
     const int lanes = first_pass ? lanes1 : lanes2;
+    if constexpr (MODEL == MODEL_QUADROTOR) {   // Lie-group error state: dx = state_diff(xbar, x), gains m x (n - 1)
+        if (P.lie) {
+            if (G <= 16 && lanes == 16) return launch_pass_l<MODEL, G, FAST, (G <= 16 ? 16 : 32), true>(P, trial0, first_pass, final_pass, s);
+            return launch_pass_l<MODEL, G, FAST, 32, true>(P, trial0, first_pass, final_pass, s);
+        }
+    }
     if (G <= 16 && lanes == 16) return launch_pass_l<MODEL, G, FAST, (G <= 16 ? 16 : 32)>(P, trial0, first_pass, final_pass, s);
     return launch_pass_l<MODEL, G, FAST, 32>(P, trial0, first_pass, final_pass, s);
 }

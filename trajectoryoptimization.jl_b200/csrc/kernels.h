@@ -26,6 +26,11 @@ cudaError_t launch_export_ab(const DevProblem& P, double* ABout, cudaStream_t s)
 cudaError_t launch_backward(const DevProblem& P, int* work_counter, cudaStream_t s);
 bool riccati_small_supported(const DevProblem& P, bool any_batch);                     // riccati_small.cu: thread-per-instance pass for n <= 4, m <= 2
 cudaError_t launch_backward_small(const DevProblem& P, cudaStream_t s);
+// Lie-group error state + Riccati pass on a materialised expansion               (lie.cu)
+cudaError_t launch_state_diff(const DevProblem& P, const double* Xbar, double* dx, cudaStream_t s);
+cudaError_t launch_error_dynamics(const DevProblem& P, cudaStream_t s);
+cudaError_t launch_error_expansion(const DevProblem& P, const double* gfull, const double* hfull, double* EG, double* EH, cudaStream_t s);
+cudaError_t launch_backward_dense(const DevProblem& P, cudaStream_t s);
 // forward pass: closed-loop rollout + merit + line search                     (forward.cu)
 cudaError_t launch_forward(const DevProblem& P, cudaStream_t s);
 cudaError_t launch_ladder(const DevProblem& P, cudaStream_t s);

@@ -982,6 +982,7 @@ cudaError_t launch_riccati_nm(const DevProblem& P, int* work_counter, cudaStream
 }  // namespace
 
 cudaError_t launch_backward(const DevProblem& P, int* work_counter, cudaStream_t s) {
+    if (P.dense_riccati) return launch_backward_dense(P, s);   // lie.cu: error state / quaternion costs (expansion materialised by the caller)
     // small models: one thread per instance, everything in registers (riccati_small.cu); TO_RICCATI_WARP=1 forces the warp kernel
     static int force_warp = -1;
     if (force_warp < 0) { const char* v = getenv("TO_RICCATI_WARP"); force_warp = v ? atoi(v) : 0; }

@@ -32,8 +32,8 @@ __device__ __forceinline__ void expand_knot(const DevProblem& P, int k0, const d
     const DevCost& cost = P.costs[P.cost_index[k0]];
 #pragma unroll
     for (int i = 0; i < nm; i++) g[i] = 0.0;
-    cost_gradient(cost, n, m, x, u, last, g);
-    cost_hessian(cost, n, m, last, H);
+    cost_gradient_quadratic<false>(cost, n, m, x, u, last, g);      // this kernel never sees user (program) costs: launch_backward routes them to lie.cu
+    cost_hessian_quadratic(cost, n, m, last, H);
     double z[nm];
 #pragma unroll
     for (int i = 0; i < n; i++) z[i] = x[i];

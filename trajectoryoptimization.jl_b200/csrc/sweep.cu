@@ -75,9 +75,13 @@ __global__ void k_cost_gradient(const DevProblem P, double* __restrict__ grad) {
 __global__ void k_cost_hessian(const DevProblem P, double* __restrict__ hess) {
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= (long long)P.B * P.N) return;
-    const int k = (int)(t % P.N);
+    const int k = (int)(t % P.N), b = (int)(t / P.N);
     const int nm = P.n + P.m;
-    cost_hessian(P.costs[P.cost_index[k]], P.n, P.m, k == P.N - 1, hess + t * nm * nm);
+    const bool last = (k == P.N - 1);
+    double zero_u[TO_MAXM] = {0};
+    const double* x = traj_X(P, P.cur[b], b) + (size_t)k * P.n;
+    const double* u = last ? zero_u : traj_U(P, P.cur[b], b) + (size_t)k * P.m;
+    cost_hessian(P.costs[P.cost_index[k]], P.n, P.m, x, u, last, hess + t * nm * nm);
 }
 
 __global__ void k_al_expansion(const DevProblem P, double* __restrict__ grad, double* __restrict__ hess) {

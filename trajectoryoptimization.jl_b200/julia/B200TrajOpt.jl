@@ -9,6 +9,7 @@ module B200TrajOpt
 using TrajectoryOptimization
 using RobotDynamics
 using LinearAlgebra
+using Rotations
 const TO = TrajectoryOptimization
 const RD = RobotDynamics
 
@@ -19,6 +20,7 @@ struct ToCostSpec
     kind::Int32; terminal::Int32
     Q::Ptr{Float64}; R::Ptr{Float64}; H::Ptr{Float64}; q::Ptr{Float64}; r::Ptr{Float64}
     c::Float64
+    w::Float64; q_ref::Ptr{Float64}; q_ind::Ptr{Int32}       # DiagonalQuatCost (kind 2), else 0 / C_NULL
 end
 struct ToConstraintSpec
     kind::Int32; first::Int32; last::Int32; sense::Int32; p::Int32; flag::Int32; ninds::Int32
@@ -30,6 +32,7 @@ struct ToSpec
     params::Ptr{Float64}; dt::Ptr{Float64}; t0::Float64
     ncost::Int32; costs::Ptr{ToCostSpec}; cost_index::Ptr{Int32}
     ncon::Int32; cons::Ptr{ToConstraintSpec}
+    error_state::Int32       # 1: solver kernels on the Lie-group error state (RD.errstate_dim(model) != n), as Altro does
 end
 
 const TO_EDIM = -2
@@ -62,7 +65,8 @@ sense_code(::TO.SecondOrderCone) = Int32(2)
 Describe `prob` (objective = vector of QuadraticCostFunctions, ConstraintList of Goal/Bound/Linear/Circle/Sphere/Norm)
 to the library and allocate a batch of `B` instances on `device`.
 """
-function BatchedProblem(prob::TO.Problem, mid::Integer, B::Integer; device::Integer=0, params::Vector{Float64}=Float64[])
+function BatchedProblem(prob::TO.Problem, mid::Integer, B::Integer; device::Integer=0, params::Vector{Float64}=Float64[],
+                        error_state::Bool=(RD.errstate_dim(TO.get_model(prob)[1]) != RD.state_dim(TO.get_model(prob)[1])))
     n, m, N = RD.dims(prob, 1)
     keep = Any[]
     root(x) = (push!(keep, x); x)
@@ -78,7 +82,12 @@ function BatchedProblem(prob::TO.Problem, mid::Integer, B::Integer; device::Inte
             R = root(isdiag ? Vector{Float64}(diag(c.R)) : Matrix{Float64}(c.R))
             H = isdiag ? C_NULL : pointer(root(Matrix{Float64}(c.H)))
             q = root(Vector{Float64}(c.q)); r = root(Vector{Float64}(c.r))
-            push!(costs, ToCostSpec(isdiag ? 0 : 1, c.terminal ? 1 : 0, pointer(Q), pointer(R), H, pointer(q), pointer(r), c.c))
+            if c isa TO.DiagonalQuatCost                         # src/lie_costs.jl:33-56
+                qref = root(Vector{Float64}(c.q_ref)); qind = root(Vector{Int32}(c.q_ind))
+                push!(costs, ToCostSpec(2, c.terminal ? 1 : 0, pointer(Q), pointer(R), C_NULL, pointer(q), pointer(r), c.c, c.w, pointer(qref), pointer(qind)))
+            else
+                push!(costs, ToCostSpec(isdiag ? 0 : 1, c.terminal ? 1 : 0, pointer(Q), pointer(R), H, pointer(q), pointer(r), c.c, 0.0, C_NULL, C_NULL))
+            end
             seen[c] = Int32(length(costs) - 1)
         end
         push!(index, seen[c])
@@ -92,15 +101,18 @@ function BatchedProblem(prob::TO.Problem, mid::Integer, B::Integer; device::Inte
         elseif con isa TO.BoundConstraint
             a = root(Vector{Float64}(con.z_max)); b = root(Vector{Float64}(con.z_min))
             push!(cons, ToConstraintSpec(1, f, l, 1, 0, 0, 0, C_NULL, pointer(a), pointer(b), C_NULL, C_NULL, 0.0))
+        elseif con isa TO.QuatVecEq                              # src/constraints.jl:938-965
+            a = root(Vector{Float64}(Rotations.params(con.qf))); ii = root(Vector{Int32}(con.qind))
+            push!(cons, ToConstraintSpec(7, f, l, 0, 3, 0, 4, pointer(ii), pointer(a), C_NULL, C_NULL, C_NULL, 0.0))
         else
-            error("constraint $(typeof(con)) : add its descriptor here (kinds 2-5 of to_con_kind)")
+            error("constraint $(typeof(con)) : add its descriptor here (kinds 2-6 of to_con_kind)")
         end
     end
     dt = root(Vector{Float64}([RD.timestep(z) for z in TO.get_trajectory(prob)][1:N-1]))
     root(costs); root(index); root(cons); root(params)
     spec = Ref(ToSpec(mid, n, m, N, B, device, length(params), isempty(params) ? C_NULL : pointer(params), pointer(dt),
                       TO.get_initial_time(prob), length(costs), pointer(costs), pointer(index), length(cons),
-                      isempty(cons) ? C_NULL : pointer(cons)))
+                      isempty(cons) ? C_NULL : pointer(cons), error_state ? 1 : 0))
     h = Ref{Ptr{Cvoid}}(C_NULL)
     rc = GC.@preserve keep ccall((:to_create, libb200), Cint, (Ref{ToSpec}, Ref{Ptr{Cvoid}}), spec, h)
     check(C_NULL, rc)

@@ -273,7 +273,9 @@ def main():
         traffic = json.load(open(os.path.join(ROOT, "profiles", "riccati_traffic.json"))).get(f"{args.workload}_B{B}_N{N}")
     except Exception:
         pass
-    roofline = {"kernel": "k_riccati (Riccati backward pass)", "bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
+    rk = "k_expansion_compact + k_riccati_dense_mma (lie.cu: error-state expansion + tensor-core Riccati pass)" if args.workload == "quadrotor_lie" \
+        else "k_riccati (Riccati backward pass)"
+    roofline = {"kernel": rk, "bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
                 "frac": achieved / peak_gbs, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": R.value * B, "avg_launch_ms": r_ms,
                 "phase_ms": phase, "fp64_tflops_riccati": None}

@@ -362,7 +362,14 @@ int to_create(const to_spec* s, to_handle** out) {
     }
     P.lie = s->error_state ? 1 : 0; P.qs = 3; P.ne = P.lie ? n - 1 : n;
     if (P.lie) P.dense_riccati = 1;
-    if (P.dense_riccati) h->overlap = false;   // lie.cu path: every kernel on the main stream
+    {   // compact expansion (lie.cu): error state + diagonal costs (quadratic / quaternion) + Goal/Bound constraints only
+        bool diag_costs = true;
+        for (const auto& c : h->h_costs) if (!c.diag || c.expr) diag_costs = false;
+        bool diag_cons = true;
+        for (int i = 0; i < s->ncon; i++) if (s->cons[i].kind != TO_CON_GOAL && s->cons[i].kind != TO_CON_BOUND) diag_cons = false;
+        P.compact = (P.lie && diag_costs && diag_cons && P.ne == 12 && m == 4) ? 1 : 0;
+    }
+    if (P.dense_riccati && !P.compact) h->overlap = false;   // generic lie.cu path: every kernel on the main stream
     h->h_cost_index.assign(s->cost_index, s->cost_index + N);
     for (int k = 0; k < N; k++)
         if (h->h_cost_index[k] < 0 || h->h_cost_index[k] >= s->ncost) { h->err = "cost_index out of range"; return bail(TO_EINVAL); }
@@ -403,6 +410,7 @@ int to_create(const to_spec* s, to_handle** out) {
     if (P.dense_riccati) {
         const size_t nme = P.ne + m;
         ALLOC(P.ABe, (size_t)B * (N - 1) * P.ne * nme); ALLOC(P.EG, (size_t)B * N * nme); ALLOC(P.EH, (size_t)B * N * nme * nme);
+        if (P.compact) ALLOC(P.EC, (size_t)B * N * TO_EC_LEN);
     }
     ALLOC(P.lambda, (size_t)B * std::max(1, P.lambda_len));
     ALLOC(P.rho, B); ALLOC(P.drho, B); ALLOC(P.dV, 2 * (size_t)B); ALLOC(P.J, B); ALLOC(P.Jc, B); ALLOC(P.alpha, B);
@@ -637,7 +645,7 @@ int to_rollout(to_handle* h) {
 int to_expand(to_handle* h) {
     JOIN(h);
     if (!h) return TO_EINVAL;
-    { PhaseScope ps(h, TO_PHASE_EXPAND); CU(h, launch_expand(h->P, h->stream)); }
+    { PhaseScope ps(h, TO_PHASE_EXPAND); CU(h, launch_expand(h->P, h->stream)); if (h->P.lie) { CU(h, launch_expand_lie(h->P, h->stream)); h->launches++; } }
     h->launches++; h->phase_launches[TO_PHASE_EXPAND]++;
     h->expanded = true; h->backward_done = false;
     return TO_OK;
@@ -792,9 +800,12 @@ static int materialise_expansion(to_handle* h, double* EG, double* EH) {
 static int do_backward(to_handle* h) {
     if (h->P.dense_riccati) {
         PhaseScope ps(h, TO_PHASE_BACKWARD);
-        int rc = materialise_expansion(h, h->P.EG, h->P.EH); if (rc) return rc;
-        CU(h, launch_error_dynamics(h->P, h->stream)); h->launches++;
-        CU(h, launch_backward_dense(h->P, h->stream));
+        DevProblem Q = h->P;
+        Q.compact = (h->P.compact && h->P.opt.pad != 3) ? 1 : 0;      // backward_kernel = 3: the generic (DFMA, full expansion) kernel
+        if (Q.compact) { CU(h, launch_expansion_compact(Q, h->stream)); h->launches++; }
+        else { int rc = materialise_expansion(h, h->P.EG, h->P.EH); if (rc) return rc; }
+        if (!Q.lie) { CU(h, launch_error_dynamics(Q, h->stream)); h->launches++; }   // error state: [A_e B_e] comes from k_expand_lie
+        CU(h, launch_backward_dense(Q, h->stream));
     } else {
         PhaseScope ps(h, TO_PHASE_BACKWARD); CU(h, launch_backward(h->P, h->d_work, h->stream));
     }
@@ -846,11 +857,13 @@ int to_ilqr_step(to_handle* h, int32_t iters) {
     // (instances never interact); the Riccati pass joins both. The overlap carries across calls (h->side_pending): any
     // other entry point joins the side stream first.
     for (int it = 0; it < iters; it++) {
+        // (error state: only [A_e B_e] is needed by the solver kernels -- k_expand_lie; the full [A B] is produced by to_expand on request)
+        auto expand = [&](cudaStream_t st, int mode) { return h->P.lie ? launch_expand_lie(h->P, st, mode) : launch_expand(h->P, st, mode); };
         if (h->side_pending) {
-            CU(h, launch_expand(h->P, h->stream2, 2)); h->launches++;
+            CU(h, expand(h->stream2, 2)); h->launches++;
             CU(h, cudaEventRecord(h->ev_join, h->stream2));
         }
-        { PhaseScope ps(h, TO_PHASE_EXPAND); CU(h, launch_expand(h->P, h->stream, h->side_pending ? 1 : 0)); }
+        { PhaseScope ps(h, TO_PHASE_EXPAND); CU(h, expand(h->stream, h->side_pending ? 1 : 0)); }
         h->launches++; h->phase_launches[TO_PHASE_EXPAND]++;
         JOIN(h);
         h->expanded = true;
@@ -912,7 +925,7 @@ int to_get_error_dynamics(to_handle* h, double* ABe) {
     if (!h || !ABe) return TO_EINVAL;
     if (!h->expanded) return fail(h, TO_ESTATE, "to_get_error_dynamics before to_expand");
     if (!h->P.dense_riccati) return to_get_dynamics_jacobians(h, ABe);     // no error state: [A_e B_e] = [A B]
-    CU(h, launch_error_dynamics(h->P, h->stream)); h->launches++;
+    if (!h->P.lie) { CU(h, launch_error_dynamics(h->P, h->stream)); h->launches++; }   // error state: written by k_expand_lie in to_expand
     const size_t cnt = (size_t)h->P.B * (h->P.N - 1) * h->P.ne * (h->P.ne + h->P.m);
     CU(h, cudaMemcpyAsync(ABe, h->P.ABe, cnt * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     CU(h, cudaStreamSynchronize(h->stream));
@@ -1038,7 +1051,16 @@ int to_algorithmic_bytes(const to_handle* h, int64_t* E, int64_t* R, int64_t* F)
     const int64_t HES = h->P.dense_riccati ? ((ne + m) * (ne + m) + (ne + m)) * N : 0;
     const int64_t ABe = h->P.dense_riccati ? ne * (ne + m) * (N - 1) : 0;
     if (E) *E = (XU + AB) * w;
-    if (R) *R = h->P.dense_riccati ? (AB + ABe + XU + L + 2 * HES + ABe + KD) * w : (AB + XU + KD + L) * w;
+    // backward phase of the lie.cu path = expansion kernels + Riccati kernel: the expansion is written once and read once.
+    //   compact (error state, diagonal costs, Goal/Bound): XU + L -> EC (40 per knot) ; EC + [A_e B_e] -> K, d
+    //   generic: full-state expansion (scratch) -> error-state expansion (HES) ; [A B] -> [A_e B_e] unless k_expand_lie wrote it
+    const int64_t EC = (int64_t)TO_EC_LEN * N, HESF = ((n + m) * (n + m) + (n + m)) * N;
+    if (R) {
+        if (h->P.compact && h->P.opt.pad != 3) *R = (XU + L + 2 * EC + ABe + KD) * w;
+        else if (h->P.dense_riccati) *R = (XU + L + 2 * HESF + 2 * HES + (h->P.lie ? 0 : AB + ABe) + ABe + KD) * w;
+        else *R = (AB + XU + KD + L) * w;
+    }
+    if (E && h->P.lie) *E = (XU + ABe) * w;     // k_expand_lie writes [A_e B_e] only
     if (F) *F = (2 * XU + KD + L) * w + 8;
     return TO_OK;
 }

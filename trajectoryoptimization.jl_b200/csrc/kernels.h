@@ -31,6 +31,8 @@ cudaError_t launch_state_diff(const DevProblem& P, const double* Xbar, double* d
 cudaError_t launch_error_dynamics(const DevProblem& P, cudaStream_t s);
 cudaError_t launch_error_expansion(const DevProblem& P, const double* gfull, const double* hfull, double* EG, double* EH, cudaStream_t s);
 cudaError_t launch_backward_dense(const DevProblem& P, cudaStream_t s);
+cudaError_t launch_expansion_compact(const DevProblem& P, cudaStream_t s);             // EC of every knot (P.compact)
+cudaError_t launch_expand_lie(const DevProblem& P, cudaStream_t s, int mode = 0);     // [A_e B_e] straight from the dual-number RK4 step (rollout.cu)
 // forward pass: closed-loop rollout + merit + line search                     (forward.cu)
 cudaError_t launch_forward(const DevProblem& P, cudaStream_t s);
 cudaError_t launch_ladder(const DevProblem& P, cudaStream_t s);

@@ -128,6 +128,65 @@ __global__ void __launch_bounds__(128) k_error_expansion(const DevProblem P, con
     }
 }
 
+// Compact error-state expansion (P.compact: diagonal quadratic / quaternion costs, Goal / Bound constraints -- the BASELINE problem
+// class).  The full-state expansion is a gradient g and a DIAGONAL h, so the error-state one is G'g, the same diagonal outside the
+// attitude and the 3 x 3 block G_q' diag(h_q) G_q - (q'g_q) I3: 40 doubles per knot (TO_EC_LEN) instead of 272.  One thread per
+// (instance, knot); cost: RD.gradient!/hessian! of DiagonalCost / DiagonalQuatCost (src/cost_functions.jl:137-233, src/lie_costs.jl:79-95),
+// AL rows of Goal / Bound constraints as in al_knot_expansion (costcon.cuh).
+__global__ void __launch_bounds__(128) k_expansion_compact(const DevProblem P) {
+    const int n = P.n, m = P.m, nm = n + m, qs = P.qs;
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (long long)P.B * P.N) return;
+    const int k = (int)(t % P.N), b = (int)(t / P.N);
+    const bool last = (k == P.N - 1);
+    const double* xg = traj_X(P, P.cur[b], b) + (size_t)k * n;
+    const double* ug = traj_U(P, P.cur[b], b) + (size_t)k * m;
+    const double* lam_b = P.lambda + (size_t)b * P.lambda_len;
+    double z[TO_MAXNM], g[TO_MAXNM], h[TO_MAXNM];
+    for (int i = 0; i < n; i++) z[i] = xg[i];
+    for (int a = 0; a < m; a++) z[n + a] = last ? 0.0 : ug[a];
+    const DevCost& c = P.costs[P.cost_index[k]];
+    for (int i = 0; i < n; i++) { g[i] = fma(c.Qd[i], z[i], c.q[i]); h[i] = c.Qd[i]; }
+    if (c.quat) {
+        double dq = 0;
+        for (int i = 0; i < 4; i++) dq = fma(c.q_ref[i], z[c.q_ind[i]], dq);
+        const double sw = dq < 0 ? c.w : -c.w;
+        for (int i = 0; i < 4; i++) g[c.q_ind[i]] = fma(sw, c.q_ref[i], g[c.q_ind[i]]);
+    }
+    for (int a = 0; a < m; a++) { g[n + a] = last ? 0.0 : fma(c.Rd[a], z[n + a], c.r[a]); h[n + a] = last ? 0.0 : c.Rd[a]; }
+    const int lim = last ? n : nm;
+    for (int ci = 0; ci < P.ncon; ci++) {
+        const DevCon& con = P.cons[ci];
+        if (k + 1 < con.first || k + 1 > con.last) continue;
+        const double mu = P.mu[ci];
+        const double* lam = lam_b + con.offset + (size_t)(k + 1 - con.first) * con.p;
+        const bool eq = (con.kind == CON_GOAL);
+        const int nrow = eq ? con.p : con.n_max + con.n_min;
+        for (int r = 0; r < nrow; r++) {
+            const int j = eq ? con.inds[r] : (r < con.n_max ? con.a_max[r] : con.a_min[r - con.n_max]);
+            const bool lower = !eq && r >= con.n_max;
+            const double cv = eq ? z[j] - con.a[r] : (lower ? con.b[j] - z[j] : z[j] - con.a[j]);
+            const double lb = lam[r] - mu * cv;
+            if ((eq || lb <= 0.0) && j < lim) { g[j] -= lower ? -lb : lb; h[j] += mu; }
+        }
+    }
+    double* out = P.EC + t * TO_EC_LEN;
+    double G[12]; quat_G(z + qs, G);
+    for (int e = 0; e < qs; e++) { out[e] = g[e]; out[16 + e] = h[e]; }
+    for (int e = qs + 3; e < n - 1 + m; e++) { out[e] = g[e + 1]; out[16 + e] = h[e + 1]; }
+    double qb = 0;
+    for (int r = 0; r < 4; r++) qb += z[qs + r] * g[qs + r];
+    for (int cc = 0; cc < 3; cc++) {
+        double s = 0, d = 0;
+        for (int r = 0; r < 4; r++) { s += G[cc * 4 + r] * g[qs + r]; d += G[cc * 4 + r] * h[qs + r] * G[cc * 4 + r]; }
+        out[qs + cc] = s; out[16 + qs + cc] = d - qb;
+    }
+    double b01 = 0, b02 = 0, b12 = 0;
+    for (int r = 0; r < 4; r++) { b01 += G[r] * h[qs + r] * G[4 + r]; b02 += G[r] * h[qs + r] * G[8 + r]; b12 += G[4 + r] * h[qs + r] * G[8 + r]; }
+    out[32] = b01; out[33] = b02; out[34] = b12;
+    for (int e = 35; e < TO_EC_LEN; e++) out[e] = 0.0;
+}
+
 // ---- Riccati backward pass on the materialised expansion: one warp per instance ---------------------------------------------
 // Same recursion and restart / regularisation rules as riccati.cu (Altro backwardpass!, oracle/oracle.hpp backward_pass).
 template <int NR, int M>
@@ -302,6 +361,296 @@ __global__ void __launch_bounds__(32 * WARPS) k_riccati_dense(const DevProblem P
     if (lane == 0) { P.rho[b] = rho; P.drho[b] = drho; P.bp_status[b] = failed ? -1 : restarts; }
 }
 
+// ---- the same pass for n_e = 12, m = 4 on the FP64 tensor cores -----------------------------------------------------------------
+// n_e + m = 16 and n_e = 12 tile mma.sync.m8n8k4 (SASS DMMA) exactly: T = S [A B] is 2 x 2 tiles x 3 k-steps, Qzz += [A B]' T the same,
+// S <- Qxx + W'K one k-step (k = m = 4) on 2 x 2 tiles: 28 DMMA per knot and no remainder handling (the fused n = 13 kernel of
+// riccati.cu needs 39 DMMA + 24 rank-1 DFMA).  Operand layouts are chosen so that every fragment load is two shared-memory
+// wavefronts (the minimum for 32 x 8 B): column-major with leading dimension 12 for S, [A B], T (12 = 4 mod 8), 20 for Q, 24 for K / W.
+// The next knot's [A_e B_e], E.hess, E.grad are fetched with cp.async (LDGSTS) into the other half of a double buffer while this
+// knot computes.
+// 1/x for a positive finite pivot: hardware seed + two Newton steps (<= 1 ulp), without the slow path of the IEEE division
+__device__ __forceinline__ double rcp_pos(double x) {
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    double e = fma(-x, y, 1.0);
+    y = fma(y, e, y);
+    e = fma(-x, y, 1.0);
+    return fma(y, e, y);
+}
+__device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+__device__ __forceinline__ void cp16(double* smem_dst, const double* gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int NPEND> __device__ __forceinline__ void cp_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(NPEND) : "memory"); }
+
+struct MmaSmem {   // one warp; NR = 12, M = 4, NME = 16
+    static constexpr int LDQ = 20, LDK = 24;
+    double ab[2][12 * 16];      // [A_e B_e]_k col-major ld 12, double buffered
+    double Q[2][16 * LDQ];      // E_k.hess -> Qzz, col-major ld 20
+    double q[2][16];            // E_k.grad -> Qz
+    double S[16 * 12];          // symmetric 12 x 12 (ld 12) + 4 zero pad rows read by the second row tile
+    double T[16 * 12];          // S [A B] (12 x 16, ld 12); later the unsymmetrised S update
+    double K[4 * LDK];          // [K | d | 0]: row a = control
+    double W[4 * LDK];          // Qux - rho K
+    double s[12];
+    double rec[2][TO_EC_LEN];   // compact expansion of the knot (P.compact), double buffered
+};
+
+template <int WARPS, bool COMPACT>
+__global__ void __launch_bounds__(32 * WARPS) k_riccati_dense_mma(const DevProblem P) {
+    constexpr int NR = 12, M = 4, NME = 16, LDQ = MmaSmem::LDQ, LDK = MmaSmem::LDK;
+    extern __shared__ __align__(16) unsigned char dense_smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int b = blockIdx.x * WARPS + warp;
+    if (b >= P.B) return;
+    MmaSmem& sm = reinterpret_cast<MmaSmem*>(dense_smem_raw)[warp];
+    const int fr = lane >> 2, fc = lane & 3;      // fragment coordinates: A(8x4) row fr col fc ; B(4x8) row fc col fr ; D(8x8) row fr cols 2fc, 2fc+1
+    const int N = P.N;
+    const double* ABg = P.ABe + (size_t)b * (N - 1) * NR * NME;
+    const double* EGg = COMPACT ? nullptr : P.EG + (size_t)b * N * NME;
+    const double* EHg = COMPACT ? nullptr : P.EH + (size_t)b * N * NME * NME;
+    const double* ECg = COMPACT ? P.EC + (size_t)b * N * TO_EC_LEN : nullptr;
+    double* Kg = P.K + (size_t)b * (N - 1) * NR * M;
+    double* dg = P.d + (size_t)b * (N - 1) * M;
+    double rho = P.rho[b], drho = P.drho[b];
+    int restarts = 0;
+    bool failed = false;
+    for (int e = lane; e < 16 * 12; e += 32) sm.S[e] = 0.0;
+    for (int e = lane; e < 4 * LDK; e += 32) { sm.K[e] = 0.0; sm.W[e] = 0.0; }
+
+    // async copies of knot k into buffer st: [A_e B_e] (96 sixteen-byte chunks) + the expansion (128 + 8 chunks, or the 20 of the compact record)
+    auto fetch = [&](int st, int k) {
+        const double* srcab = ABg + (size_t)k * NR * NME;
+        for (int c = lane; c < 96; c += 32) cp16(&sm.ab[st][2 * c], srcab + 2 * c);
+        if constexpr (COMPACT) {
+            if (lane < TO_EC_LEN / 2) cp16(&sm.rec[st][2 * lane], ECg + (size_t)k * TO_EC_LEN + 2 * lane);
+        } else {
+            const double* srch = EHg + (size_t)k * NME * NME;
+            for (int c = lane; c < 128; c += 32) { const int j = c >> 3, i = (c & 7) * 2; cp16(&sm.Q[st][j * LDQ + i], srch + j * NME + i); }
+            if (lane < 8) cp16(&sm.q[st][2 * lane], EGg + (size_t)k * NME + 2 * lane);
+        }
+    };
+    // entry (row, col) of the compact record's Hessian: diagonal + the symmetric 3 x 3 attitude block
+    auto rec_h = [&](const double* rec, int row, int col) -> double {
+        if (row == col) return rec[16 + row];
+        if (row >= 3 && row < 6 && col >= 3 && col < 6) return rec[32 + (row - 3) + (col - 3) - 1];
+        return 0.0;
+    };
+
+    for (;;) {
+        if constexpr (COMPACT) {   // terminal knot: S = E_N.xx, s = E_N.x
+            const double* rec = ECg + (size_t)(N - 1) * TO_EC_LEN;
+            for (int e = lane; e < NR * NR; e += 32) sm.S[e] = rec_h(rec, e % NR, e / NR);
+            if (lane < NR) sm.s[lane] = rec[lane];
+        } else {
+            const double* H = EHg + (size_t)(N - 1) * NME * NME;
+            for (int e = lane; e < NR * NR; e += 32) sm.S[e] = H[(e / NR) * NME + (e % NR)];
+            if (lane < NR) sm.s[lane] = EGg[(size_t)(N - 1) * NME + lane];
+        }
+        fetch(0, N - 2); cp_commit();
+        __syncwarp();
+        double dV1 = 0.0, dV2 = 0.0;
+        bool ok = true;
+        int st = 0;
+        for (int k = N - 2; k >= 0; k--, st ^= 1) {
+            if (k > 0) fetch(st ^ 1, k - 1);
+            cp_commit();
+            cp_wait<1>();                  // this lane's copies of knot k have landed ...
+            __syncwarp();                  // ... and everybody else's
+            const double* ab = sm.ab[st];
+            double* Qs = sm.Q[st];
+            double* qs = sm.q[st];
+            // fragments of [A B]: B operand of T = S [A B]; the same registers are the A operand ([A B]' rows) of Q += [A B]' T
+            double bfr[3][2];
+#pragma unroll
+            for (int kk = 0; kk < 3; kk++)
+#pragma unroll
+                for (int t = 0; t < 2; t++) bfr[kk][t] = ab[(8 * t + fr) * 12 + 4 * kk + fc];
+            {   // ---- T = S [A B] ----
+                double d[2][2][2];
+#pragma unroll
+                for (int mi = 0; mi < 2; mi++)
+#pragma unroll
+                    for (int ni = 0; ni < 2; ni++) { d[mi][ni][0] = 0.0; d[mi][ni][1] = 0.0; }
+#pragma unroll
+                for (int kk = 0; kk < 3; kk++) {
+                    double a[2];
+#pragma unroll
+                    for (int mi = 0; mi < 2; mi++) a[mi] = sm.S[(8 * mi + fr) * 12 + 4 * kk + fc];     // S is symmetric: row-major read
+#pragma unroll
+                    for (int mi = 0; mi < 2; mi++)
+#pragma unroll
+                        for (int ni = 0; ni < 2; ni++) dmma884(d[mi][ni][0], d[mi][ni][1], a[mi], bfr[kk][ni]);
+                }
+#pragma unroll
+                for (int mi = 0; mi < 2; mi++)
+#pragma unroll
+                    for (int ni = 0; ni < 2; ni++) {
+                        const int row = 8 * mi + fr, col = 8 * ni + 2 * fc;
+                        if (row < NR) { sm.T[col * 12 + row] = d[mi][ni][0]; sm.T[(col + 1) * 12 + row] = d[mi][ni][1]; }
+                    }
+            }
+            __syncwarp();
+            {   // ---- Qzz = lzz + [A B]' T (all four 8 x 8 tiles), Qz = lz + [A B]' s ----
+                double c[2][2][2];
+#pragma unroll
+                for (int mi = 0; mi < 2; mi++)
+#pragma unroll
+                    for (int ni = 0; ni < 2; ni++) {
+                        const int row = 8 * mi + fr, col = 8 * ni + 2 * fc;
+                        if constexpr (COMPACT) { c[mi][ni][0] = rec_h(sm.rec[st], row, col); c[mi][ni][1] = rec_h(sm.rec[st], row, col + 1); }
+                        else { c[mi][ni][0] = Qs[col * LDQ + row]; c[mi][ni][1] = Qs[(col + 1) * LDQ + row]; }
+                    }
+#pragma unroll
+                for (int kk = 0; kk < 3; kk++) {
+                    double bt[2];
+#pragma unroll
+                    for (int ni = 0; ni < 2; ni++) bt[ni] = sm.T[(8 * ni + fr) * 12 + 4 * kk + fc];
+#pragma unroll
+                    for (int mi = 0; mi < 2; mi++)
+#pragma unroll
+                        for (int ni = 0; ni < 2; ni++) dmma884(c[mi][ni][0], c[mi][ni][1], bfr[kk][mi], bt[ni]);
+                }
+                double qz = 0.0;
+                if (lane < NME) {
+                    qz = COMPACT ? sm.rec[st][lane] : qs[lane];
+#pragma unroll
+                    for (int r = 0; r < NR; r++) qz = fma(ab[lane * 12 + r], sm.s[r], qz);
+                }
+                __syncwarp();              // every lane has read lzz / lz / s before they are overwritten
+#pragma unroll
+                for (int mi = 0; mi < 2; mi++)
+#pragma unroll
+                    for (int ni = 0; ni < 2; ni++) {
+                        const int row = 8 * mi + fr, col = 8 * ni + 2 * fc;
+                        Qs[col * LDQ + row] = c[mi][ni][0]; Qs[(col + 1) * LDQ + row] = c[mi][ni][1];
+                    }
+                if (lane < NME) qs[lane] = qz;
+            }
+            __syncwarp();
+            // ---- gains: LDL' of Quu + rho I (every lane factors the same 4 x 4 matrix), one lane per column of [Qux | Qu] ----
+            double Quu[M * (M + 1) / 2], Lf[M * (M + 1) / 2], dj[M];
+#pragma unroll
+            for (int a = 0; a < M; a++)
+#pragma unroll
+                for (int c = 0; c <= a; c++) Quu[a * (a + 1) / 2 + c] = 0.5 * (Qs[(NR + c) * LDQ + NR + a] + Qs[(NR + a) * LDQ + NR + c]);
+#pragma unroll
+            for (int j = 0; j < M; j++) {
+                double t = Quu[j * (j + 1) / 2 + j] + rho;
+#pragma unroll
+                for (int r = 0; r < j; r++) t = fma(-Lf[j * (j + 1) / 2 + r] * Lf[j * (j + 1) / 2 + r], dj[r], t);
+                if (!(t > 0.0) || !isfinite(t)) ok = false;
+                dj[j] = t;
+                const double inv = rcp_pos(t);
+                Lf[j * (j + 1) / 2 + j] = inv;
+#pragma unroll
+                for (int i = j + 1; i < M; i++) {
+                    double v = Quu[i * (i + 1) / 2 + j];
+#pragma unroll
+                    for (int r = 0; r < j; r++) v = fma(-Lf[i * (i + 1) / 2 + r] * Lf[j * (j + 1) / 2 + r], dj[r], v);
+                    Lf[i * (i + 1) / 2 + j] = v * inv;
+                }
+            }
+            if (!ok) break;   // uniform across the warp
+            if (lane <= NR) {
+                const int c = lane;
+                double rhs[M], kc[M];
+#pragma unroll
+                for (int a = 0; a < M; a++) rhs[a] = (c < NR) ? Qs[c * LDQ + NR + a] : qs[NR + a];   // Qux[a][c] | Qu[a]
+#pragma unroll
+                for (int a = 0; a < M; a++) {
+                    double t = -rhs[a];
+#pragma unroll
+                    for (int r = 0; r < a; r++) t = fma(-Lf[a * (a + 1) / 2 + r], kc[r], t);
+                    kc[a] = t;
+                }
+#pragma unroll
+                for (int a = 0; a < M; a++) kc[a] *= Lf[a * (a + 1) / 2 + a];
+#pragma unroll
+                for (int a = M - 1; a >= 0; a--) {
+                    double t = kc[a];
+#pragma unroll
+                    for (int r = a + 1; r < M; r++) t = fma(-Lf[r * (r + 1) / 2 + a], kc[r], t);
+                    kc[a] = t;
+                }
+#pragma unroll
+                for (int a = 0; a < M; a++) { sm.K[a * LDK + c] = kc[a]; sm.W[a * LDK + c] = fma(-rho, kc[a], rhs[a]); }
+                if (c < NR) {
+#pragma unroll
+                    for (int a = 0; a < M; a++) Kg[(size_t)k * NR * M + c * M + a] = kc[a];
+                } else {
+                    double t1 = 0.0, t2 = 0.0;
+#pragma unroll
+                    for (int a = 0; a < M; a++) {
+                        dg[(size_t)k * M + a] = kc[a];
+                        t1 = fma(kc[a], rhs[a], t1);
+                        double qd = 0.0;
+#pragma unroll
+                        for (int r = 0; r < M; r++) qd = fma((r <= a) ? Quu[a * (a + 1) / 2 + r] : Quu[r * (r + 1) / 2 + a], kc[r], qd);
+                        t2 = fma(0.5 * kc[a], qd, t2);
+                    }
+                    dV1 += t1; dV2 += t2;
+                }
+            }
+            __syncwarp();
+            {   // ---- S <- Qxx + W'K: one DMMA k-step per tile (k = m = 4) on the upper tiles; the off-diagonal tile is mirrored, so S is
+                //      symmetric up to the rounding inside the two diagonal tiles (as in riccati.cu) ----
+                double af[2], bk[2];
+#pragma unroll
+                for (int t = 0; t < 2; t++) { af[t] = sm.W[fc * LDK + 8 * t + fr]; bk[t] = sm.K[fc * LDK + 8 * t + fr]; }
+#pragma unroll
+                for (int mi = 0; mi < 2; mi++)
+#pragma unroll
+                    for (int ni = mi; ni < 2; ni++) {
+                        const int row = 8 * mi + fr, col = 8 * ni + 2 * fc;
+                        double a0 = Qs[col * LDQ + row], a1 = Qs[(col + 1) * LDQ + row];
+                        dmma884(a0, a1, af[mi], bk[ni]);
+                        if (row < NR && col < NR) {        // NR is even: col + 1 < NR too
+                            sm.S[col * 12 + row] = a0; sm.S[(col + 1) * 12 + row] = a1;
+                            if (ni != mi) { sm.S[row * 12 + col] = a0; sm.S[row * 12 + col + 1] = a1; }
+                        }
+                    }
+                if (lane < NR) {
+                    double t = qs[lane];
+#pragma unroll
+                    for (int a = 0; a < M; a++) t = fma(sm.W[a * LDK + lane], sm.K[a * LDK + NR], t);
+                    sm.s[lane] = t;
+                }
+            }
+            __syncwarp();
+        }
+        cp_wait<0>();
+        __syncwarp();
+        if (ok) {
+            if (lane == NR) { P.dV[2 * b] = dV1; P.dV[2 * b + 1] = dV2; }
+            break;
+        }
+        reg_increase(P.opt, rho, drho);
+        restarts++;
+        if (rho > P.opt.bp_reg_max) { failed = true; break; }
+    }
+    if (!failed) reg_decrease(P.opt, rho, drho);
+    if (lane == 0) { P.rho[b] = rho; P.drho[b] = drho; P.bp_status[b] = failed ? -1 : restarts; }
+}
+
+cudaError_t launch_dense_mma(const DevProblem& P, cudaStream_t s) {
+    constexpr int WARPS = 2;
+    const int smem = (int)sizeof(MmaSmem) * WARPS;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(k_riccati_dense_mma<WARPS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_riccati_dense_mma<WARPS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    if (P.compact) k_riccati_dense_mma<WARPS, true><<<(P.B + WARPS - 1) / WARPS, 32 * WARPS, smem, s>>>(P);
+    else k_riccati_dense_mma<WARPS, false><<<(P.B + WARPS - 1) / WARPS, 32 * WARPS, smem, s>>>(P);
+    return cudaGetLastError();
+}
+
 template <int NR, int M>
 cudaError_t launch_dense_t(const DevProblem& P, cudaStream_t s) {
     constexpr int WARPS = 4;
@@ -324,8 +673,13 @@ cudaError_t launch_error_expansion(const DevProblem& P, const double* gfull, con
     k_error_expansion<<<nblk((long long)P.B * P.N * (P.ne + P.m), 128), 128, 0, s>>>(P, gfull, hfull, EG, EH);
     return cudaGetLastError();
 }
+cudaError_t launch_expansion_compact(const DevProblem& P, cudaStream_t s) {
+    k_expansion_compact<<<nblk((long long)P.B * P.N, 128), 128, 0, s>>>(P);
+    return cudaGetLastError();
+}
 cudaError_t launch_backward_dense(const DevProblem& P, cudaStream_t s) {
-    if (P.ne == 12 && P.m == 4) return launch_dense_t<12, 4>(P, s);
+    // to_options.backward_kernel = 3 forces the DFMA kernel (A/B, tests)
+    if (P.ne == 12 && P.m == 4) return P.opt.pad == 3 ? launch_dense_t<12, 4>(P, s) : launch_dense_mma(P, s);
     if (P.ne == 13 && P.m == 4) return launch_dense_t<13, 4>(P, s);
     if (P.ne == 4 && P.m == 1) return launch_dense_t<4, 1>(P, s);
     if (P.ne == 4 && P.m == 2) return launch_dense_t<4, 2>(P, s);

@@ -74,6 +74,64 @@ __global__ void __launch_bounds__(128) k_expand(const DevProblem P, int mode) {
     }
 }
 
+// Error-state expansion of a Lie-group model (Quadrotor; SURVEY 8 f2, lie.cu): thread (instance, knot, j) pushes the j-th column of
+// E(x_k) = blkdiag(I3, G(q_k), I6 | I4) through the RK4 step as the tangent of a Dual<1> -- the directional derivative [A G_k | B] e_j --
+// and projects the result with G(q_{k+1})' (q_{k+1} from the stored trajectory, as Altro's errstate_jacobian! does).  It writes column j
+// of [A_e B_e]_k (12 contiguous doubles, col-major 12 x 16): 1.5 KB per knot instead of the 2 KB of the padded full-state [A B].
+template <int MODEL>
+__global__ void __launch_bounds__(128) k_expand_lie(const DevProblem P, int mode) {
+    constexpr int n = ModelDims<MODEL>::n, m = ModelDims<MODEL>::m, ne = n - 1, nme = ne + m, qs = 3;
+    using D = Dual<1>;
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long total = (long long)P.B * (P.N - 1) * nme;
+    if (t >= total) return;
+    const int j = (int)(t % nme);
+    const long long bk = t / nme;
+    const int k = (int)(bk % (P.N - 1));
+    const int b = (int)(bk / (P.N - 1));
+    if (mode != 0 && (P.acc1[b] != 0) != (mode == 1)) return;
+    const double* X = traj_X(P, P.cur[b], b) + (size_t)k * n;
+    const double* U = traj_U(P, P.cur[b], b) + (size_t)k * m;
+    D x[n], u[m], xn[n];
+#pragma unroll
+    for (int i = 0; i < n; i++) { x[i].v = X[i]; x[i].d[0] = 0.0; }
+#pragma unroll
+    for (int i = 0; i < m; i++) { u[i].v = U[i]; u[i].d[0] = (ne + i == j) ? 1.0 : 0.0; }
+    if (j < qs) {
+#pragma unroll
+        for (int i = 0; i < qs; i++) x[i].d[0] = (i == j) ? 1.0 : 0.0;
+    } else if (j < qs + 3) {
+        const double w = X[qs], qx = X[qs + 1], qy = X[qs + 2], qz = X[qs + 3];
+        const int c = j - qs;        // column c of L(q) H: (-x,w,z,-y), (-y,-z,w,x), (-z,y,-x,w)
+        x[qs].d[0] = (c == 0) ? -qx : (c == 1) ? -qy : -qz;
+        x[qs + 1].d[0] = (c == 0) ? w : (c == 1) ? -qz : qy;
+        x[qs + 2].d[0] = (c == 0) ? qz : (c == 1) ? w : -qx;
+        x[qs + 3].d[0] = (c == 0) ? -qy : (c == 1) ? qx : w;
+    } else if (j < ne) {
+#pragma unroll
+        for (int i = qs + 4; i < n; i++) x[i].d[0] = (i == j + 1) ? 1.0 : 0.0;
+    }
+    rk4_step<MODEL, D>(P.params, x, u, P.dt[k], xn);
+    double* out = P.ABe + ((size_t)bk * nme + j) * ne;
+    const double* q1 = X + n + qs;                                     // attitude of knot k + 1
+    const double w1 = q1[0], x1 = q1[1], y1 = q1[2], z1 = q1[3];
+#pragma unroll
+    for (int i = 0; i < qs; i++) out[i] = xn[i].d[0];
+    const double t0 = xn[qs].d[0], t1 = xn[qs + 1].d[0], t2 = xn[qs + 2].d[0], t3 = xn[qs + 3].d[0];
+    out[qs] = -x1 * t0 + w1 * t1 + z1 * t2 - y1 * t3;
+    out[qs + 1] = -y1 * t0 - z1 * t1 + w1 * t2 + x1 * t3;
+    out[qs + 2] = -z1 * t0 + y1 * t1 - x1 * t2 + w1 * t3;
+#pragma unroll
+    for (int i = qs + 4; i < n; i++) out[i - 1] = xn[i].d[0];
+}
+
+cudaError_t launch_expand_lie(const DevProblem& P, cudaStream_t s, int mode) {
+    if (P.model != MODEL_QUADROTOR) return cudaErrorNotSupported;
+    const long long total = (long long)P.B * (P.N - 1) * (P.ne + P.m);
+    k_expand_lie<MODEL_QUADROTOR><<<(unsigned)((total + 127) / 128), 128, 0, s>>>(P, mode);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_rollout(const DevProblem& P, cudaStream_t s) {
     const int threads = 64, blocks = (P.B + threads - 1) / threads;
     TO_DISPATCH_MODEL(P.model, P.m, (k_rollout<MODEL><<<blocks, threads, 0, s>>>(P)));

@@ -90,6 +90,9 @@ enum to_con_kind {
     TO_CON_NORM = 5,   /* NormConstraint :438-521    val, inds = 1-based indices into z, sense (orthant | SOC)   */
     TO_CON_COLLISION = 6, /* CollisionConstraint :341-389  val = radius, inds = {x1[D], x2[D]} 1-based state indices (ninds = 2D): r^2 - |x[x1]-x[x2]|^2 <= 0.
                             StateBound / ControlBound :547-631 are TO_CON_BOUND with the other block unbounded. */
+    TO_CON_EXPR = 8,     /* user constraint recorded as a program (RD.@autodiff struct ... <: StageConstraint, docs/src/constraint_interface.md:52-72):
+                            inds = prog_len x {op, a, b} (ninds = 3 prog_len, to_expr_op as for TO_COST_EXPR), a = constants (flag = their number),
+                            p = output dimension: the values of the LAST p instructions; sense; Jacobian by forward-mode AD on the device */
     TO_CON_QUATVEC = 7   /* QuatVecEq :938-965  a = qf (4, scalar first), inds = qind (4, 1-based; NULL = 4:7): with q = normalize(x[qind]) and
                             qf flipped when qf'q < 0, c = q[2:4] - qf[2:4]; Equality, p = 3 */
 };

@@ -75,14 +75,13 @@ enum ExprOp { OP_CONST = 0, OP_X = 1, OP_U = 2, OP_ADD = 3, OP_SUB = 4, OP_MUL =
               OP_EXP = 10, OP_LOG = 11, OP_SQRT = 12, OP_POWC = 13, OP_TANH = 14, OP_ADDC = 15, OP_MULC = 16, OP_DIVC = 17, OP_RDIVC = 18, OP_RSUBC = 19 };
 constexpr int EXPR_MAXLEN = 128;
 // evaluate the program with z_s1 seeded in d1 and z_s2 in d2 (index into [x;u]; -1 = no seed); has_u = false -> u = 0
-inline Hyper expr_eval(const Cost& c, const double* x, const double* u, bool has_u, int s1, int s2) {
-    Hyper reg[EXPR_MAXLEN];
-    const int L = (int)c.prog.size() / 3, n = c.n;
+// run a program: fills reg[0..L-1]
+inline void expr_run(const int* prog, int L, const double* consts, int n, const double* x, const double* u, bool has_u, int s1, int s2, Hyper* reg) {
     for (int i = 0; i < L; i++) {
-        const int op = c.prog[3 * i], a = c.prog[3 * i + 1], b = c.prog[3 * i + 2];
+        const int op = prog[3 * i], a = prog[3 * i + 1], b = prog[3 * i + 2];
         Hyper r;
         switch (op) {
-            case OP_CONST: r.v = c.consts[a]; break;
+            case OP_CONST: r.v = consts[a]; break;
             case OP_X: r.v = x[a]; r.d1 = (a == s1); r.d2 = (a == s2); break;
             case OP_U: r.v = has_u ? u[a] : 0.0; r.d1 = (n + a == s1); r.d2 = (n + a == s2); break;
             case OP_ADD: r.v = reg[a].v + reg[b].v; r.d1 = reg[a].d1 + reg[b].d1; r.d2 = reg[a].d2 + reg[b].d2; r.d12 = reg[a].d12 + reg[b].d12; break;
@@ -95,16 +94,21 @@ inline Hyper expr_eval(const Cost& c, const double* x, const double* u, bool has
             case OP_EXP: { const double e = std::exp(reg[a].v); r = hyp_unary(reg[a], e, e, e); break; }
             case OP_LOG: { const double iv = 1.0 / reg[a].v; r = hyp_unary(reg[a], std::log(reg[a].v), iv, -iv * iv); break; }
             case OP_SQRT: { const double sq = std::sqrt(reg[a].v); r = hyp_unary(reg[a], sq, 0.5 / sq, -0.25 / (sq * reg[a].v)); break; }
-            case OP_POWC: { const double e = c.consts[b], v = reg[a].v; r = hyp_unary(reg[a], std::pow(v, e), e * std::pow(v, e - 1), e * (e - 1) * std::pow(v, e - 2)); break; }
+            case OP_POWC: { const double e = consts[b], v = reg[a].v; r = hyp_unary(reg[a], std::pow(v, e), e * std::pow(v, e - 1), e * (e - 1) * std::pow(v, e - 2)); break; }
             case OP_TANH: { const double t = std::tanh(reg[a].v); r = hyp_unary(reg[a], t, 1 - t * t, -2 * t * (1 - t * t)); break; }
-            case OP_ADDC: r = reg[a]; r.v += c.consts[b]; break;
-            case OP_MULC: { const double k = c.consts[b]; r.v = reg[a].v * k; r.d1 = reg[a].d1 * k; r.d2 = reg[a].d2 * k; r.d12 = reg[a].d12 * k; break; }
-            case OP_DIVC: { const double k = c.consts[b]; r.v = reg[a].v / k; r.d1 = reg[a].d1 / k; r.d2 = reg[a].d2 / k; r.d12 = reg[a].d12 / k; break; }
-            case OP_RDIVC: { const double k = c.consts[b], iv = 1.0 / reg[a].v; r = hyp_unary(reg[a], k * iv, -k * iv * iv, 2 * k * iv * iv * iv); break; }
-            case OP_RSUBC: r.v = c.consts[b] - reg[a].v; r.d1 = -reg[a].d1; r.d2 = -reg[a].d2; r.d12 = -reg[a].d12; break;
+            case OP_ADDC: r = reg[a]; r.v += consts[b]; break;
+            case OP_MULC: { const double k = consts[b]; r.v = reg[a].v * k; r.d1 = reg[a].d1 * k; r.d2 = reg[a].d2 * k; r.d12 = reg[a].d12 * k; break; }
+            case OP_DIVC: { const double k = consts[b]; r.v = reg[a].v / k; r.d1 = reg[a].d1 / k; r.d2 = reg[a].d2 / k; r.d12 = reg[a].d12 / k; break; }
+            case OP_RDIVC: { const double k = consts[b], iv = 1.0 / reg[a].v; r = hyp_unary(reg[a], k * iv, -k * iv * iv, 2 * k * iv * iv * iv); break; }
+            case OP_RSUBC: r.v = consts[b] - reg[a].v; r.d1 = -reg[a].d1; r.d2 = -reg[a].d2; r.d12 = -reg[a].d12; break;
         }
         reg[i] = r;
     }
+}
+inline Hyper expr_eval(const Cost& c, const double* x, const double* u, bool has_u, int s1, int s2) {
+    Hyper reg[EXPR_MAXLEN];
+    const int L = (int)c.prog.size() / 3;
+    expr_run(c.prog.data(), L, c.consts.data(), c.n, x, u, has_u, s1, s2, reg);
     return reg[L - 1];
 }
 
@@ -322,7 +326,7 @@ inline int hess_projection(int cone, const double* x, const double* b, int p, do
 
 // ------------------------------------------------------------------------------------------------
 // Constraints  (src/constraints.jl).  All are functions of one knot z = [x;u].
-enum ConKind { CON_GOAL = 0, CON_BOUND = 1, CON_LINEAR = 2, CON_CIRCLE = 3, CON_SPHERE = 4, CON_NORM = 5, CON_COLLISION = 6, CON_QUATVEC = 7 };
+enum ConKind { CON_GOAL = 0, CON_BOUND = 1, CON_LINEAR = 2, CON_CIRCLE = 3, CON_SPHERE = 4, CON_NORM = 5, CON_COLLISION = 6, CON_QUATVEC = 7, CON_EXPR = 8 };
 
 struct Constraint {
     int kind = CON_GOAL;
@@ -341,6 +345,8 @@ struct Constraint {
     int xi = 0, yi = 1, zi = 2;
     int lin_on_control = 0;
     double val = 0;
+    std::vector<int> prog;          // CON_EXPR: recorded program, outputs = the last p instructions
+    std::vector<double> consts;
     int width() const { return n + m; }
     int nknots() const { return last - first + 1; }
 };
@@ -406,6 +412,13 @@ inline void con_evaluate(const Constraint& con, const double* x, const double* u
             c[0] = s;
             break;
         }
+        case CON_EXPR: {  // user constraint (RD.@autodiff StageConstraint, docs/src/constraint_interface.md:52-72)
+            Hyper reg[EXPR_MAXLEN];
+            const int L = (int)con.prog.size() / 3;
+            expr_run(con.prog.data(), L, con.consts.data(), con.n, x, u, true, -1, -1, reg);
+            for (int i = 0; i < con.p; i++) c[i] = reg[L - con.p + i].v;
+            break;
+        }
         case CON_QUATVEC: {  // QuatVecEq  src/constraints.jl:947-956: q = normalize(x[qind]); qf *= -1 when qf'q < 0; -(qf[2:4] - q[2:4])
             double q[4], nrm = 0, dq = 0;
             for (int i = 0; i < 4; i++) { q[i] = x[con.inds[i]]; nrm += q[i] * q[i]; }
@@ -464,6 +477,15 @@ inline void con_jacobian(const Constraint& con, const double* x, const double* u
                 const double d = x[con.inds[i]] - x[con.inds[D + i]];
                 jac[con.inds[i] * p] = -2 * d;
                 jac[con.inds[D + i] * p] = 2 * d;
+            }
+            break;
+        }
+        case CON_EXPR: {  // RD.jacobian!(ForwardAD): one first-order pass per input
+            Hyper reg[EXPR_MAXLEN];
+            const int L = (int)con.prog.size() / 3;
+            for (int j = 0; j < w; j++) {
+                expr_run(con.prog.data(), L, con.consts.data(), con.n, x, u, true, j, -1, reg);
+                for (int i = 0; i < p; i++) jac[j * p + i] = reg[L - p + i].d1;
             }
             break;
         }

@@ -133,6 +133,25 @@ int orc_create(const to_spec* s, orc_handle** out) {
                 c.sense = CONE_NEGATIVE_ORTHANT; c.val = tc.val; c.p = 1;
                 for (int j = 0; j < tc.ninds; j++) c.inds.push_back(tc.inds[j] - 1);
                 break;
+            case TO_CON_EXPR: {
+                const int L = tc.ninds / 3;
+                if (!tc.inds || tc.ninds % 3 || L < 1 || L > TO_EXPR_MAXLEN || tc.p < 1 || tc.p > L || tc.p > MAXP || tc.flag < 0 || tc.flag > TO_EXPR_MAXCONST || (tc.flag > 0 && !tc.a)) {
+                    delete h; return fail(nullptr, TO_EINVAL, "expression constraint: bad program size");
+                }
+                c.p = tc.p; c.sense = tc.sense;
+                c.prog.assign(tc.inds, tc.inds + tc.ninds); c.consts.assign(tc.a, tc.a + tc.flag);
+                for (int j = 0; j < L; j++) {
+                    const int op = c.prog[3 * j], a = c.prog[3 * j + 1], b = c.prog[3 * j + 2];
+                    const bool bin = op >= TO_OP_ADD && op <= TO_OP_DIV;
+                    bool ok = op >= 0 && op <= TO_OP_RSUBC;
+                    if (op == TO_OP_CONST) ok = ok && a >= 0 && a < tc.flag;
+                    else if (op == TO_OP_X) ok = ok && a >= 0 && a < n;
+                    else if (op == TO_OP_U) ok = ok && a >= 0 && a < m;
+                    else { ok = ok && a >= 0 && a < j; if (bin) ok = ok && b >= 0 && b < j; if (op == TO_OP_POWC || op >= TO_OP_ADDC) ok = ok && b >= 0 && b < tc.flag; }
+                    if (!ok) { delete h; return fail(nullptr, TO_EINVAL, "expression constraint: invalid instruction"); }
+                }
+                break;
+            }
             case TO_CON_QUATVEC:
                 if (!tc.a || n < 4) { delete h; return fail(nullptr, TO_EINVAL, "QuatVecEq: null qf"); }
                 c.sense = CONE_ZERO; c.p = 3; c.a.assign(tc.a, tc.a + 4);

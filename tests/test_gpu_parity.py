@@ -261,6 +261,45 @@ def test_autodiff_costs_in_all_kernels(kind):
     g.close(); o.close()
 
 
+def test_autodiff_constraints_in_all_kernels():
+    """SURVEY 8(f4), constraints: user constraints recorded as programs (docs/src/constraint_interface.md:52-72) -- values, forward-mode
+    Jacobians, AL merit / expansion and the general-constraint path of the solver kernels, against the oracle; the docs' ControlNorm KAT"""
+    from test_oracle_nlcost import control_norm
+    n, m, N, B = 13, 4, 21, 4
+    probs = []
+    for cls in (TO.Problem, OracleProblem):
+        base = P.quadrotor(B=B, N=N, cls=cls, dt=0.05)
+        cons = base.constraints
+        TO.add_constraint(cons, TO.AutodiffConstraint(n, m, control_norm(7.0), TO.Inequality(), "control"), (1, N - 1))
+        TO.add_constraint(cons, TO.AutodiffConstraint(n, m, lambda x: [-(x[0] - 0.5) ** 2 - (x[1] - 1.0) ** 2 - (x[2] - 1.5) ** 2 + 0.09,
+                                                                        TO.tanh(x[7]) + x[8] * x[9] - 2.0], TO.Inequality(), "state"), (2, N))
+        TO.add_constraint(cons, TO.AutodiffConstraint(n, m, lambda x, u: [u[0] - u[2] + 0.1 * TO.sin(x[10])], TO.Equality()), (1, 5))
+        p = cls(base.model, base.obj, base.x0, 0.05 * (N - 1), xf=base.xf, constraints=cons)
+        TO.initial_controls(p, TO.controls(base)); base.close(); TO.rollout(p)
+        probs.append(p)
+    g, o = probs
+    U = TO.controls(g)
+    close(TO.evaluate_constraints(g, 2)[..., 0], np.linalg.norm(U, axis=-1) - 7.0, 1e-13, "ControlNorm value (docs KAT)")
+    close(TO.constraint_jacobians(g, 2)[..., 0, n:], U / np.linalg.norm(U, axis=-1)[..., None], 1e-13, "ControlNorm Jacobian (docs KAT)")
+    for i in range(len(g.constraints)):
+        close(TO.evaluate_constraints(g, i), TO.evaluate_constraints(o, i), KERNEL_RTOL, f"constraint {i} values")
+        close(TO.constraint_jacobians(g, i), TO.constraint_jacobians(o, i), KERNEL_RTOL, f"constraint {i} jacobians")
+    close(TO.merit(g), TO.merit(o), KERNEL_RTOL, "merit"); close(TO.max_violation(g), TO.max_violation(o), KERNEL_RTOL, "violation")
+    gg, gh = TO.al_expansion(g); og, oh = TO.al_expansion(o)
+    close(gg, og, KERNEL_RTOL, "AL gradient"); close(gh, oh, KERNEL_RTOL, "AL hessian")
+    for p in (g, o):
+        TO.expand(p)
+    assert np.array_equal(TO.backward(g), TO.backward(o))
+    Kg, dg = TO.gains(g); Ko, do = TO.gains(o)
+    close(Kg, Ko, 1e-8, "K"); close(dg, do, 1e-8, "d")
+    for p in (g, o):
+        TO.forward(p); TO.ilqr_step(p, 2); TO.al_update(p); TO.ilqr_step(p, 1)
+    close(TO.merit(g), TO.merit(o), 1e-5, "merit after iterations")
+    for i in range(len(g.constraints)):
+        close(TO.multipliers(g, i), TO.multipliers(o, i), 1e-6, f"multipliers {i}")
+    g.close(); o.close()
+
+
 def test_regularisation_restart_matches_oracle():
     n, m, N = 4, 1, 11
     stage = TO.DiagonalCost(np.ones(n), -0.5 * np.ones(m))

@@ -137,3 +137,65 @@ def test_cartpole_swingup_with_the_docs_nonlinear_cost():
         TO.ilqr_step(prob, 1); J.append(TO.merit(prob))
     J = np.array(J)
     assert np.all(np.diff(J, axis=0) <= 1e-9) and np.all(J[-1] < 0.5 * J[0])
+
+
+# ---- user-defined constraints (docs/src/constraint_interface.md:52-72) ------------------------------------------------------------
+
+def control_norm(a):
+    """the docs' ControlNorm: ||u|| - a <= 0 (a ControlConstraint)"""
+    return lambda u: [TO.sqrt(sum(ui * ui for ui in u)) - a]
+
+
+def test_control_norm_constraint_of_the_docs():
+    """value ||u|| - a and the analytic Jacobian u'/||u|| the docs give as the optional jacobian! (:69-71)"""
+    n, m, N, B = 4, 2, 6, 3
+    con = TO.AutodiffConstraint(n, m, control_norm(1.5), TO.Inequality(), inputs="control")
+    assert con.p == 1 and TO.sense(con) == TO.Inequality()
+    cons = TO.ConstraintList(n, m, N)
+    TO.add_constraint(cons, con, (1, N - 1))
+    obj = TO.LQRObjective(np.ones(n), np.ones(m), np.ones(n), np.zeros(n), N)
+    prob = OracleProblem(TO.DoubleIntegrator(2), obj, np.zeros(n), 1.0, constraints=cons, batch=B)
+    U = rng.standard_normal((B, N - 1, m))
+    TO.initial_controls(prob, U); TO.rollout(prob)
+    c, J = TO.evaluate_constraints(prob, con), TO.constraint_jacobians(prob, con)
+    nu = np.linalg.norm(U, axis=-1)
+    assert np.allclose(c[..., 0], nu - 1.5, rtol=1e-14)
+    assert np.allclose(J[..., 0, n:], U / nu[..., None], rtol=1e-13) and not J[..., 0, :n].any()
+    assert np.allclose(TO.max_violation(prob), np.maximum(nu - 1.5, 0).max(axis=1), rtol=1e-13)
+
+
+def test_program_constraints_equal_the_builtin_ones():
+    """CircleConstraint, a linear equality and an SOC norm constraint written as user functions give the values, Jacobians, AL merit
+    and solver iterates of the built-in types"""
+    n, m, N = 4, 2, 21
+    xf = np.array([0, 2.0, 0, 0])
+    obj = TO.LQRObjective(np.eye(n), np.eye(m), np.eye(n) * (N - 1), xf, N)
+    U0 = np.random.default_rng(1).standard_normal((N - 1, m))
+
+    def build(user):
+        cons = TO.ConstraintList(n, m, N)
+        TO.add_constraint(cons, TO.GoalConstraint(xf), N)
+        if user:
+            TO.add_constraint(cons, TO.AutodiffConstraint(n, m, lambda x: [-(x[0] - 0.0) ** 2 - (x[1] - 1.0) ** 2 + 0.5 * 0.5], TO.Inequality(), "state"), (2, N - 1))
+            TO.add_constraint(cons, TO.AutodiffConstraint(n, m, lambda u: [u[0], u[1], 5.0 + 0.0 * u[0]], TO.SecondOrderCone(), "control"), (1, N - 1))
+            TO.add_constraint(cons, TO.AutodiffConstraint(n, m, lambda x, u: [1.0 * x[2] + 0.5 * u[0] - 0.1], TO.Equality()), (3, 5))
+        else:
+            TO.add_constraint(cons, TO.CircleConstraint(n, [0.0], [1.0], [0.5]), (2, N - 1))
+            TO.add_constraint(cons, TO.NormConstraint(n, m, 5.0, TO.SecondOrderCone(), "control"), (1, N - 1))
+            # (the reference's LinearConstraint acts on x or on u only, src/constraints.jl:103-150: the mixed row is a program on both sides)
+            TO.add_constraint(cons, TO.AutodiffConstraint(n, m, lambda x, u: [1.0 * x[2] + 0.5 * u[0] - 0.1], TO.Equality()), (3, 5))
+        p = OracleProblem(TO.DoubleIntegrator(2), obj, np.zeros(n), 3.0, xf=xf, constraints=cons)
+        TO.initial_controls(p, U0); TO.rollout(p)
+        return p
+
+    a, b = build(True), build(False)
+    for i in range(3):
+        assert np.allclose(TO.evaluate_constraints(a, i), TO.evaluate_constraints(b, i), rtol=1e-13, atol=1e-15)
+        assert np.allclose(TO.constraint_jacobians(a, i), TO.constraint_jacobians(b, i), rtol=1e-13, atol=1e-15)
+    assert np.allclose(TO.merit(a), TO.merit(b), rtol=1e-13)
+    for p in (a, b):
+        TO.ilqr_step(p, 3); TO.al_update(p); TO.ilqr_step(p, 2)
+    assert np.allclose(TO.merit(a), TO.merit(b), rtol=1e-9) and np.allclose(TO.controls(a), TO.controls(b), rtol=1e-8, atol=1e-10)
+    assert np.allclose(TO.multipliers(a, 2), TO.multipliers(b, 2), rtol=1e-8, atol=1e-10)
+    with pytest.raises(TO.ArgumentError):
+        TO.AutodiffConstraint(n, m, lambda x: [x[0]] * 17, TO.Inequality(), "state")      # at most 16 rows per general constraint

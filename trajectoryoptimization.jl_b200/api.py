@@ -651,6 +651,30 @@ class QuatVecEq(AbstractConstraint):   # src/constraints.jl:938-965
         return dict(kind=K.CON_QUATVEC, first=first, last=last, sense=K.CONE_ZERO, a=self.qf, inds=self.qind)
 
 
+class AutodiffConstraint(AbstractConstraint):
+    """A user-defined constraint ``fun(x, u) -> p values``: the counterpart of ``RD.@autodiff struct MyCon <: StageConstraint`` with
+    ``RD.evaluate(con, x, u)`` (docs/src/constraint_interface.md:52-72).  ``inputs`` = ``"stage"`` (``fun(x, u)``), ``"state"``
+    (``fun(x)``, a ``StateConstraint``) or ``"control"`` (``fun(u)``, a ``ControlConstraint``).  ``fun`` is recorded once (see ``Expr``);
+    values and the forward-mode Jacobian are evaluated on the device."""
+
+    def __init__(self, n, m, fun, sense, inputs="stage"):
+        self.n, self.m, self.fun, self.sense_, self.inputs = int(n), int(m), fun, sense, inputs
+        tape = _Tape()
+        x = np.array([tape.emit(K.OP_X, i, 0) for i in range(self.n)], dtype=object)
+        u = np.array([tape.emit(K.OP_U, j, 0) for j in range(self.m)], dtype=object)
+        out = fun(x, u) if inputs == "stage" else (fun(x) if inputs == "state" else fun(u))
+        outs = [tape.lift(o) for o in np.atleast_1d(np.asarray(out, dtype=object)).ravel()]
+        outs = [tape.emit(K.OP_ADDC, o.idx, tape.const_index(0.0)) for o in outs]      # the outputs are the last p instructions, in order
+        self.p = len(outs)
+        if self.p < 1 or self.p > 16:
+            raise ArgumentError("the solver kernels take 1..16 rows per general constraint")
+        self.prog, self.consts = np.asarray(tape.prog, dtype=np.int32), np.asarray(tape.consts, dtype=float)
+
+    def _spec(self, first, last):
+        return dict(kind=K.CON_EXPR, first=first, last=last, sense=self.sense_.code, p=self.p, inds=self.prog.ravel(), a=self.consts,
+                    flag=len(self.consts))
+
+
 class StateBound(BoundConstraint):   # src/constraints.jl:596-617 -- a BoundConstraint whose control block is unbounded
     """``StateBound(n; x_min, x_max)``. The control dimension is taken from the ConstraintList it is added to."""
 

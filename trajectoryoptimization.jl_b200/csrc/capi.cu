@@ -258,6 +258,27 @@ int build_con(to_handle* h, const to_constraint_spec& tc, int n, int m, int N, D
             }
             break;
         }
+        case TO_CON_EXPR: {    // user constraint recorded as a program
+            const int L = tc.ninds / 3;
+            if (!tc.inds || tc.ninds % 3 || L < 1 || L > TO_EXPR_LEN || tc.p < 1 || tc.p > L || tc.p > TO_MAXP || tc.flag < 0 || tc.flag > TO_EXPR_CONST || (tc.flag > 0 && !tc.a))
+                return fail(h, TO_EINVAL, "expression constraint: bad program size");
+            c.p = tc.p; c.sense = tc.sense; c.prog_len = L; c.ninds = 0;
+            if (tc.sense < 0 || tc.sense > CONE_POSITIVE_ORTHANT) return fail(h, TO_EINVAL, "expression constraint: unknown sense");
+            for (int j = 0; j < L; j++) {
+                const int op = tc.inds[3 * j], a = tc.inds[3 * j + 1], b = tc.inds[3 * j + 2];
+                const bool bin = op >= TO_OP_ADD && op <= TO_OP_DIV;
+                bool ok = op >= 0 && op <= TO_OP_RSUBC;
+                if (op == TO_OP_CONST) ok = ok && a >= 0 && a < tc.flag;
+                else if (op == TO_OP_X) ok = ok && a >= 0 && a < n;
+                else if (op == TO_OP_U) ok = ok && a >= 0 && a < m;
+                else { ok = ok && a >= 0 && a < j; if (bin) ok = ok && b >= 0 && b < j; if (op == TO_OP_POWC || op >= TO_OP_ADDC) ok = ok && b >= 0 && b < tc.flag; }
+                if (!ok) return fail(h, TO_EINVAL, "expression constraint: invalid instruction");
+                c.prog[3 * j] = op; c.prog[3 * j + 1] = a; c.prog[3 * j + 2] = b;
+            }
+            for (int j = 0; j < tc.flag; j++) c.pconst[j] = tc.a[j];
+            c.flag = 0;
+            break;
+        }
         case TO_CON_QUATVEC:   // QuatVecEq, src/constraints.jl:938-965
             if (!tc.a || n < 4) return fail(h, TO_EINVAL, "QuatVecEq: null qf");
             c.p = 3; c.sense = CONE_ZERO; c.ninds = 4;

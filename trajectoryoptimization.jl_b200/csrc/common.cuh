@@ -26,7 +26,7 @@
 // reference enums (mirrors include/trajopt_b200.h)
 enum { MODEL_DOUBLE_INTEGRATOR = 0, MODEL_CARTPOLE = 1, MODEL_QUADROTOR = 2, MODEL_ACROBOT = 3 };
 enum { CONE_ZERO = 0, CONE_NEGATIVE_ORTHANT = 1, CONE_SECOND_ORDER = 2, CONE_IDENTITY = 3, CONE_POSITIVE_ORTHANT = 4 };
-enum { CON_GOAL = 0, CON_BOUND = 1, CON_LINEAR = 2, CON_CIRCLE = 3, CON_SPHERE = 4, CON_NORM = 5, CON_COLLISION = 6, CON_QUATVEC = 7 };
+enum { CON_GOAL = 0, CON_BOUND = 1, CON_LINEAR = 2, CON_CIRCLE = 3, CON_SPHERE = 4, CON_NORM = 5, CON_COLLISION = 6, CON_QUATVEC = 7, CON_EXPR = 8 };
 
 // QuadraticCostFunction (reference src/cost_functions.jl:326-347, :417-454); dense storage + diagonal copy
 struct DevCost {
@@ -62,6 +62,10 @@ struct DevCon {
     double b[TO_MAXP];       // BOUND z_min[n+m] | LINEAR b[p] | yc[p]
     double c3[TO_MAXP];      // SPHERE zc[p]
     double rad[TO_MAXP];
+    // CON_EXPR: user constraint recorded as a program (outputs = the last p instructions); to_constraint_spec TO_CON_EXPR
+    int prog_len, pad4[3];
+    int prog[3 * TO_EXPR_LEN];
+    double pconst[TO_EXPR_CONST];
 };
 
 struct DevOptions {

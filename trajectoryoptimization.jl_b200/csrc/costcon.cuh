@@ -28,14 +28,12 @@ __device__ __forceinline__ Hyper hyp_mul(const Hyper& a, const Hyper& b) {
     r.d12 = a.d12 * b.v + a.d1 * b.d2 + a.d2 * b.d1 + a.v * b.d12; return r;
 }
 // z_s1 seeded in d1, z_s2 in d2 (index into [x;u], -1 = none); has_u = false: u = 0 (terminal knot).  Mirrors oracle expr_eval.
-__device__ inline Hyper expr_eval(const DevCost& c, int n, const double* x, const double* u, bool has_u, int s1, int s2) {
-    Hyper reg[TO_EXPR_LEN];
-    const int L = c.prog_len;
+__device__ inline void expr_run(const int* prog, int L, const double* pconst, int n, const double* x, const double* u, bool has_u, int s1, int s2, Hyper* reg) {
     for (int i = 0; i < L; i++) {
-        const int op = c.prog[3 * i], a = c.prog[3 * i + 1], b = c.prog[3 * i + 2];
+        const int op = prog[3 * i], a = prog[3 * i + 1], b = prog[3 * i + 2];
         Hyper r; r.v = 0; r.d1 = 0; r.d2 = 0; r.d12 = 0;
         switch (op) {
-            case 0: r.v = c.pconst[a]; break;
+            case 0: r.v = pconst[a]; break;
             case 1: r.v = x[a]; r.d1 = (a == s1) ? 1.0 : 0.0; r.d2 = (a == s2) ? 1.0 : 0.0; break;
             case 2: r.v = has_u ? u[a] : 0.0; r.d1 = (n + a == s1) ? 1.0 : 0.0; r.d2 = (n + a == s2) ? 1.0 : 0.0; break;
             case 3: r.v = reg[a].v + reg[b].v; r.d1 = reg[a].d1 + reg[b].d1; r.d2 = reg[a].d2 + reg[b].d2; r.d12 = reg[a].d12 + reg[b].d12; break;
@@ -48,17 +46,21 @@ __device__ inline Hyper expr_eval(const DevCost& c, int n, const double* x, cons
             case 10: { const double e = exp(reg[a].v); r = hyp_unary(reg[a], e, e, e); break; }
             case 11: { const double iv = 1.0 / reg[a].v; r = hyp_unary(reg[a], log(reg[a].v), iv, -iv * iv); break; }
             case 12: { const double sq = sqrt(reg[a].v); r = hyp_unary(reg[a], sq, 0.5 / sq, -0.25 / (sq * reg[a].v)); break; }
-            case 13: { const double e = c.pconst[b], v = reg[a].v; r = hyp_unary(reg[a], pow(v, e), e * pow(v, e - 1), e * (e - 1) * pow(v, e - 2)); break; }
+            case 13: { const double e = pconst[b], v = reg[a].v; r = hyp_unary(reg[a], pow(v, e), e * pow(v, e - 1), e * (e - 1) * pow(v, e - 2)); break; }
             case 14: { const double t = tanh(reg[a].v); r = hyp_unary(reg[a], t, 1 - t * t, -2 * t * (1 - t * t)); break; }
-            case 15: r = reg[a]; r.v += c.pconst[b]; break;
-            case 16: { const double k = c.pconst[b]; r.v = reg[a].v * k; r.d1 = reg[a].d1 * k; r.d2 = reg[a].d2 * k; r.d12 = reg[a].d12 * k; break; }
-            case 17: { const double k = c.pconst[b]; r.v = reg[a].v / k; r.d1 = reg[a].d1 / k; r.d2 = reg[a].d2 / k; r.d12 = reg[a].d12 / k; break; }
-            case 18: { const double k = c.pconst[b], iv = 1.0 / reg[a].v; r = hyp_unary(reg[a], k * iv, -k * iv * iv, 2 * k * iv * iv * iv); break; }
-            case 19: r.v = c.pconst[b] - reg[a].v; r.d1 = -reg[a].d1; r.d2 = -reg[a].d2; r.d12 = -reg[a].d12; break;
+            case 15: r = reg[a]; r.v += pconst[b]; break;
+            case 16: { const double k = pconst[b]; r.v = reg[a].v * k; r.d1 = reg[a].d1 * k; r.d2 = reg[a].d2 * k; r.d12 = reg[a].d12 * k; break; }
+            case 17: { const double k = pconst[b]; r.v = reg[a].v / k; r.d1 = reg[a].d1 / k; r.d2 = reg[a].d2 / k; r.d12 = reg[a].d12 / k; break; }
+            case 18: { const double k = pconst[b], iv = 1.0 / reg[a].v; r = hyp_unary(reg[a], k * iv, -k * iv * iv, 2 * k * iv * iv * iv); break; }
+            case 19: r.v = pconst[b] - reg[a].v; r.d1 = -reg[a].d1; r.d2 = -reg[a].d2; r.d12 = -reg[a].d12; break;
         }
         reg[i] = r;
     }
-    return reg[L - 1];
+}
+__device__ inline Hyper expr_eval(const DevCost& c, int n, const double* x, const double* u, bool has_u, int s1, int s2) {
+    Hyper reg[TO_EXPR_LEN];
+    expr_run(c.prog, c.prog_len, c.pconst, n, x, u, has_u, s1, s2, reg);
+    return reg[c.prog_len - 1];
 }
 
 // geodesic term of DiagonalQuatCost (src/lie_costs.jl:74-76): w min(1 + dq, 1 - dq), dq = q_ref'x[q_ind]
@@ -232,6 +234,12 @@ __device__ inline void con_evaluate(const DevCon& con, int n, int m, const doubl
             c[0] = s;
             break;
         }
+        case CON_EXPR: {   // user constraint recorded as a program (docs/src/constraint_interface.md:52-72)
+            Hyper reg[TO_EXPR_LEN];
+            expr_run(con.prog, con.prog_len, con.pconst, n, x, u, true, -1, -1, reg);
+            for (int i = 0; i < con.p; i++) c[i] = reg[con.prog_len - con.p + i].v;
+            break;
+        }
         case CON_QUATVEC: {   // QuatVecEq src/constraints.jl:947-956
             double q[4], nrm = 0, dq = 0;
             for (int i = 0; i < 4; i++) { q[i] = x[con.inds[i]]; nrm = fma(q[i], q[i], nrm); }
@@ -284,6 +292,14 @@ __device__ inline void con_jacobian(const DevCon& con, int n, int m, const doubl
                 const double d = x[con.inds[i]] - x[con.inds[D + i]];
                 jac[con.inds[i] * p] = -2 * d;
                 jac[con.inds[D + i] * p] = 2 * d;
+            }
+            break;
+        }
+        case CON_EXPR: {   // RD.jacobian!(ForwardAD): one first-order pass per input
+            Hyper reg[TO_EXPR_LEN];
+            for (int j = 0; j < w; j++) {
+                expr_run(con.prog, con.prog_len, con.pconst, n, x, u, true, j, -1, reg);
+                for (int i = 0; i < p; i++) jac[j * p + i] = reg[con.prog_len - p + i].d1;
             }
             break;
         }

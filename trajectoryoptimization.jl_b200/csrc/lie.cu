@@ -533,6 +533,9 @@ __global__ void __launch_bounds__(32 * WARPS) k_riccati_dense_mma(const DevProbl
             __syncwarp();
             // ---- gains: LDL' of Quu + rho I (every lane factors the same 4 x 4 matrix), one lane per column of [Qux | Qu] ----
             double Quu[M * (M + 1) / 2], Lf[M * (M + 1) / 2], dj[M];
+#ifdef TO_DENSE_HALFLDL
+            if (lane < 16) {   // A/B: FP64 instructions of a half-empty warp take one pipe pass
+#endif
 #pragma unroll
             for (int a = 0; a < M; a++)
 #pragma unroll
@@ -554,6 +557,10 @@ __global__ void __launch_bounds__(32 * WARPS) k_riccati_dense_mma(const DevProbl
                     Lf[i * (i + 1) / 2 + j] = v * inv;
                 }
             }
+#ifdef TO_DENSE_HALFLDL
+            }
+            ok = __shfl_sync(0xffffffffu, ok ? 1 : 0, 0) != 0;
+#endif
             if (!ok) break;   // uniform across the warp
             if (lane <= NR) {
                 const int c = lane;
@@ -636,8 +643,11 @@ __global__ void __launch_bounds__(32 * WARPS) k_riccati_dense_mma(const DevProbl
     if (lane == 0) { P.rho[b] = rho; P.drho[b] = drho; P.bp_status[b] = failed ? -1 : restarts; }
 }
 
+#ifndef TO_DENSE_WARPS
+#define TO_DENSE_WARPS 2     // warps (= instances) per CTA of k_riccati_dense_mma; A/B: profiles/build_lie_variants.sh
+#endif
 cudaError_t launch_dense_mma(const DevProblem& P, cudaStream_t s) {
-    constexpr int WARPS = 2;
+    constexpr int WARPS = TO_DENSE_WARPS;
     const int smem = (int)sizeof(MmaSmem) * WARPS;
     static bool configured = false;
     if (!configured) {

@@ -437,3 +437,91 @@ def test_relu_tie_convention():
     assert np.allclose(AB[7:10, 13:], 0.0) and np.allclose(AB[10:12, 13:], 0.0) and np.all(np.abs(AB[12, 13:]) > 0)
     ABp = oracle_discrete_jacobian(model, x, np.full(4, 1e-9), 0.05)
     assert np.all(ABp[9, 13:] > 0)
+
+
+# ---- IndexedConstraint / change_dimension (src/constraints.jl:785-936; test/constraint_tests.jl:346-407) -----------------------------
+
+def test_indexed_constraint_reference_test():
+    """test/constraint_tests.jl:346-407: a BoundConstraint of (n, m) applied to the leading slices of a (2n, 2m) knot point
+    z2 = ([x; 2x], [u; 2u]), and a CircleConstraint applied to the trailing state slice (where it sees 2x)."""
+    r = np.random.default_rng(4)
+    n, m, N, B = 4, 2, 3, 2
+    n2, m2 = 2 * n, 2 * m
+    x, u = r.standard_normal((B, N, n)), r.standard_normal((B, N - 1, m))
+    X2, U2 = np.concatenate([x, 2 * x], axis=-1), np.concatenate([u, 2 * u], axis=-1)
+    xmin, xmax, umin, umax = -r.random(n), r.random(n), -r.random(m), r.random(m)
+    bnd = TO.BoundConstraint(n, m, x_min=xmin, x_max=xmax, u_min=umin, u_max=umax)
+    cir = TO.CircleConstraint(n, [1.0, 1, 1], [1.0, 2, 3], [1.0, 1, 1])
+    idx = TO.IndexedConstraint(n2, m2, bnd)                                   # :357
+    idc = TO.IndexedConstraint(n2, m2, cir, (n + 1, 2 * n), (m + 1, 2 * m))   # :383
+    assert TO.output_dim(idx) == TO.output_dim(bnd) and TO.sense(idx) == TO.sense(bnd) and (idx.n, idx.m) == (n2, m2)      # :372-375
+    assert np.array_equal(TO.upper_bound(idx), TO.upper_bound(bnd)) and np.array_equal(TO.lower_bound(idx), TO.lower_bound(bnd))   # :376-377
+    assert TO.is_bound(idx) and TO.is_bound(idc) == TO.is_bound(cir)                                                        # :378, :404
+
+    def problem(nn, mm, cons_list, X, U):
+        cons = TO.ConstraintList(nn, mm, N)
+        for c in cons_list:
+            TO.add_constraint(cons, c, (1, N - 1))
+        obj = TO.LQRObjective(np.ones(nn), np.ones(mm), np.ones(nn), np.zeros(nn), N)
+        p = OracleProblem(_Dummy(nn, mm), obj, np.zeros(nn), 1.0, constraints=cons, batch=B)
+        TO.initial_states(p, X); TO.initial_controls(p, U)
+        return p
+    big = problem(n2, m2, [idx, idc], X2, U2)
+    small = problem(n, m, [bnd], x, u)
+    small2 = problem(n, m, [cir], 2 * x, 2 * u)
+    assert np.allclose(TO.evaluate_constraints(big, 0), TO.evaluate_constraints(small, 0), rtol=1e-14)      # :360-363
+    J, J0 = TO.constraint_jacobians(big, 0), TO.constraint_jacobians(small, 0)
+    p = bnd.p
+    want = np.concatenate([J0[..., :n], np.zeros((B, N - 1, p, n)), J0[..., n:], np.zeros((B, N - 1, p, m))], axis=-1)     # :369
+    assert np.array_equal(J, want)
+    assert np.allclose(TO.evaluate_constraints(big, 1), TO.evaluate_constraints(small2, 0), rtol=1e-14)     # :388-390
+    Jc, Jc0 = TO.constraint_jacobians(big, 1), TO.constraint_jacobians(small2, 0)
+    wantc = np.concatenate([np.zeros((B, N - 1, 3, n)), Jc0[..., :n], np.zeros((B, N - 1, 3, m2))], axis=-1)               # :396
+    assert np.allclose(Jc, wantc, rtol=1e-14)
+
+
+class _Dummy(TO.DoubleIntegrator):
+    """a double integrator of dimension n/2 when m == n/2, otherwise only a carrier of (n, m) for constraint evaluation"""
+
+    def __init__(self, n, m):
+        super().__init__(m)
+        assert n == 2 * m
+
+
+def test_change_dimension_of_constraints_lists_and_costs():
+    r = np.random.default_rng(6)
+    n, m, N = 4, 2, 4
+    n2, m2 = 8, 4
+    ix, iu = (5, 8), (3, 4)
+    cons = TO.ConstraintList(n, m, N)
+    TO.add_constraint(cons, TO.GoalConstraint(np.arange(1.0, 5.0), inds=[1, 3]), N)
+    TO.add_constraint(cons, TO.NormConstraint(n, m, 2.0, TO.SecondOrderCone(), [2, 5, 6]), (1, N - 1))
+    TO.add_constraint(cons, TO.LinearConstraint(n, m, r.standard_normal((2, m)), r.standard_normal(2), TO.Inequality(), "control"), (1, N - 1))
+    TO.add_constraint(cons, TO.AutodiffConstraint(n, m, lambda x, u: [x[0] * u[1] - TO.sin(x[3])], TO.Equality()), (2, 3))
+    TO.add_constraint(cons, TO.StateBound(n, x_max=[1.0, np.inf, 2.0, np.inf]), (1, N))
+    TO.add_constraint(cons, TO.ControlBound(m, u_min=-1.0), (1, N - 1))
+    big_cons = TO.change_dimension(cons, n2, m2, ix, iu)                     # src/constraint_list.jl:208-217
+    assert len(big_cons) == len(cons) and np.array_equal(TO.num_constraints(big_cons), TO.num_constraints(cons))
+    cost = TO.DiagonalCost(r.random(n), r.random(m), q=r.standard_normal(n), r=r.standard_normal(m), c=0.3)
+    big_cost = TO.change_dimension(cost, n2, m2, ix, iu)                     # src/cost_functions.jl:391-401
+    assert np.allclose(np.diag(big_cost.Q)[4:], np.diag(cost.Q)) and not np.diag(big_cost.Q)[:4].any() and np.allclose(big_cost.r[2:], cost.r)
+    qc = TO.change_dimension(TO.QuatLQRCost(np.ones(4), np.ones(2), np.array([1.0, 0, 0, 0]), w=3.0, quat_ind=[1, 2, 3, 4]), n2, m2, ix, iu)
+    assert isinstance(qc, TO.DiagonalQuatCost) and np.array_equal(qc.q_ind, [5, 6, 7, 8]) and qc.w == 3.0          # src/lie_costs.jl:144-159
+    B = 2
+    x, u = r.standard_normal((B, N, n)), r.standard_normal((B, N - 1, m))
+    X2, U2 = r.standard_normal((B, N, n2)), r.standard_normal((B, N - 1, m2))
+    X2[..., 4:] = x; U2[..., 2:] = u
+    small = OracleProblem(_Dummy(n, m), TO.Objective(cost, N), np.zeros(n), 1.0, constraints=cons, batch=B)
+    big = OracleProblem(_Dummy(n2, m2), TO.Objective(big_cost, N), np.zeros(n2), 1.0, constraints=big_cons, batch=B)
+    TO.initial_states(small, x); TO.initial_controls(small, u); TO.initial_states(big, X2); TO.initial_controls(big, U2)
+    assert np.allclose(TO.cost(big), TO.cost(small), rtol=1e-13)
+    for i in range(len(cons)):
+        assert np.allclose(TO.evaluate_constraints(big, i), TO.evaluate_constraints(small, i), rtol=1e-13, atol=1e-15), i
+        Jb, Js = TO.constraint_jacobians(big, i), TO.constraint_jacobians(small, i)
+        assert np.allclose(Jb[..., 4:8], Js[..., :4], atol=1e-15) and np.allclose(Jb[..., 10:12], Js[..., 4:6], atol=1e-15)
+        assert not Jb[..., :4].any() and not Jb[..., 8:10].any()
+    assert np.allclose(TO.merit(big), TO.merit(small), rtol=1e-13) and np.allclose(TO.max_violation(big), TO.max_violation(small), rtol=1e-13)
+    with pytest.raises(TO.DimensionMismatch):
+        TO.IndexedConstraint(n2, m2, TO.BoundConstraint(n, m, u_max=1.0), (1, 3), (1, 2))
+    with pytest.raises(TO.ArgumentError):
+        TO.IndexedConstraint(n2, m2, TO.GoalConstraint(np.zeros(n)), [4, 3, 2, 1])

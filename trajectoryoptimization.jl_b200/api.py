@@ -516,10 +516,13 @@ def output_dim(con):
 
 
 def is_bound(con):   # src/abstract_constraint.jl:139
+    if isinstance(con, IndexedConstraint):   # src/constraints.jl:930
+        return is_bound(con.con)
     return isinstance(con, (GoalConstraint, BoundConstraint))
 
 
 def upper_bound(con):   # src/abstract_constraint.jl:104-109
+    if isinstance(con, IndexedConstraint): return upper_bound(con.con)   # src/constraints.jl:931
     if isinstance(con, StateBound): return con.x_max.copy()        # src/constraints.jl:607
     if isinstance(con, ControlBound): return con.u_max.copy()      # :630
     if isinstance(con, BoundConstraint):
@@ -528,6 +531,7 @@ def upper_bound(con):   # src/abstract_constraint.jl:104-109
 
 
 def lower_bound(con):   # src/abstract_constraint.jl:116-121
+    if isinstance(con, IndexedConstraint): return lower_bound(con.con)   # src/constraints.jl:932
     if isinstance(con, StateBound): return con.x_min.copy()        # src/constraints.jl:606
     if isinstance(con, ControlBound): return con.u_min.copy()      # :629
     if isinstance(con, BoundConstraint):
@@ -673,6 +677,97 @@ class AutodiffConstraint(AbstractConstraint):
     def _spec(self, first, last):
         return dict(kind=K.CON_EXPR, first=first, last=last, sense=self.sense_.code, p=self.p, inds=self.prog.ravel(), a=self.consts,
                     flag=len(self.consts))
+
+
+def _index_vec(idx, default_len):
+    """1-based index vector from a Julia-style range ``(first, last)``, a list, or None (= 1:default_len)."""
+    if idx is None:
+        return np.arange(1, default_len + 1)
+    if isinstance(idx, tuple) and len(idx) == 2:
+        return np.arange(int(idx[0]), int(idx[1]) + 1)
+    return np.asarray(list(idx), dtype=int)
+
+
+class IndexedConstraint(AbstractConstraint):
+    """``IndexedConstraint(n, m, con, ix, iu)`` (src/constraints.jl:785-936): ``con``, defined for a model with ``(n0, m0)``, applied to
+    the slices ``x[ix]``, ``u[iu]`` of a larger model ``(n, m)`` (1-based, increasing indices; a ``(first, last)`` tuple is a Julia range).
+    Host-side only: the indices are remapped and the same device constraint kinds are used."""
+
+    def __init__(self, n, m, con, ix=None, iu=None):
+        if isinstance(con, IndexedConstraint):
+            raise ArgumentError("nested IndexedConstraint")
+        self.n, self.m, self.con = int(n), int(m), con
+        n0 = getattr(con, "n", None)
+        m0 = getattr(con, "m", None)
+        if isinstance(con, StateBound): m0 = 0 if m0 is None else m0
+        if isinstance(con, ControlBound): n0 = 0 if n0 is None else n0
+        self.ix = _index_vec(ix, n0 if n0 is not None else n)       # IndexedConstraint(n, m, con): start of the vectors (:882-897)
+        self.iu = _index_vec(iu, m0 if m0 is not None else m)
+        self.n0, self.m0 = (self.ix.size if n0 is None else n0), (self.iu.size if m0 is None else m0)
+        if (n0 not in (None, 0) and self.ix.size != n0) or (m0 not in (None, 0) and self.iu.size != m0):
+            raise DimensionMismatch("IndexedConstraint: ix / iu do not match the dimensions of the wrapped constraint")
+        if self.ix.size and (self.ix.min() < 1 or self.ix.max() > n or np.any(np.diff(self.ix) <= 0)):
+            raise ArgumentError("IndexedConstraint: ix must be increasing indices into 1:n")
+        if self.iu.size and (self.iu.min() < 1 or self.iu.max() > m or np.any(np.diff(self.iu) <= 0)):
+            raise ArgumentError("IndexedConstraint: iu must be increasing indices into 1:m")
+        self.p, self.sense_ = con.p, con.sense_
+
+    def _zmap(self, j):
+        """1-based index into the old z = [x0; u0] -> 1-based index into the new z"""
+        return int(self.ix[j - 1]) if j <= self.n0 else self.n + int(self.iu[j - self.n0 - 1])
+
+    def _spec(self, first, last):
+        con = self.con
+        if isinstance(con, (StateBound, ControlBound)):
+            con._bind(self.m0 if isinstance(con, StateBound) else self.n0)
+        d = dict(con._spec(first, last))
+        k = d["kind"]
+        if k == K.CON_BOUND:      # change_dimension(::BoundConstraint) :772-783 (which fills x_min with +Inf: the intended -Inf is used here)
+            zmax, zmin = np.full(self.n + self.m, np.inf), np.full(self.n + self.m, -np.inf)
+            n0 = self.n0
+            for j in range(con.z_max.size):
+                jj = (int(self.ix[j]) - 1) if j < n0 else self.n + int(self.iu[j - n0]) - 1
+                zmax[jj], zmin[jj] = con.z_max[j], con.z_min[j]
+            d.update(a=zmax, b=zmin)
+        elif k == K.CON_LINEAR:   # :146-150
+            src = self.iu if d["flag"] else self.ix
+            A = np.zeros((con.p, self.m if d["flag"] else self.n))
+            A[:, src - 1] = con.A
+            d.update(a=A)
+        elif k in (K.CON_GOAL, K.CON_CIRCLE, K.CON_SPHERE, K.CON_COLLISION, K.CON_QUATVEC):   # state indices (:75, :231, :324, :391)
+            d.update(inds=[int(self.ix[j - 1]) for j in np.asarray(d["inds"], dtype=int)])
+        elif k == K.CON_NORM:     # indices into z (:519)
+            d.update(inds=[self._zmap(int(j)) for j in np.asarray(d["inds"], dtype=int)])
+        elif k == K.CON_EXPR:     # recorded program: remap the loads
+            prog = np.asarray(d["inds"], dtype=np.int32).reshape(-1, 3).copy()
+            for row in prog:
+                if row[0] == K.OP_X: row[1] = int(self.ix[row[1]]) - 1
+                elif row[0] == K.OP_U: row[1] = int(self.iu[row[1]]) - 1
+            d.update(inds=prog.ravel())
+        else:
+            raise ArgumentError(f"IndexedConstraint: unsupported constraint {type(con).__name__}")
+        return d
+
+
+def change_dimension(obj, n, m, ix=None, iu=None):
+    """``change_dimension(con | cons | cost, n, m, ix, iu)``: the same constraint / ConstraintList / cost acting on ``x[ix]``, ``u[iu]`` of a
+    larger model (src/constraints.jl:934-936 and the per-type methods, src/constraint_list.jl:208-217, src/cost_functions.jl:391-401,
+    src/lie_costs.jl:144-159)."""
+    if isinstance(obj, ConstraintList):
+        new = ConstraintList(n, m, obj.N)
+        for inds, con in obj.zip():
+            add_constraint(new, change_dimension(con, n, m, ix, iu), inds)
+        return new
+    if isinstance(obj, AbstractConstraint):
+        return IndexedConstraint(n, m, obj, ix, iu)
+    if isinstance(obj, DiagonalCost):
+        ixv, iuv = _index_vec(ix, obj.state_dim), _index_vec(iu, obj.control_dim)
+        Qd, Rd, q, r = np.zeros(n), np.zeros(m), np.zeros(n), np.zeros(m)
+        Qd[ixv - 1], Rd[iuv - 1], q[ixv - 1], r[iuv - 1] = np.diag(obj.Q), np.diag(obj.R), obj.q, obj.r
+        if isinstance(obj, DiagonalQuatCost):
+            return DiagonalQuatCost(Qd, Rd, q=q, r=r, c=obj.c, w=obj.w, q_ref=obj.q_ref, q_ind=ixv[obj.q_ind - 1], terminal=obj.terminal)
+        return DiagonalCost(Qd, Rd, q=q, r=r, c=obj.c, terminal=obj.terminal)
+    raise ArgumentError(f"change_dimension is not defined for {type(obj).__name__}")
 
 
 class StateBound(BoundConstraint):   # src/constraints.jl:596-617 -- a BoundConstraint whose control block is unbounded

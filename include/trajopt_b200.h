@@ -57,7 +57,7 @@ enum to_expr_op { TO_OP_CONST = 0, TO_OP_X = 1, TO_OP_U = 2, TO_OP_ADD = 3, TO_O
                   /* one operand taken from the constant table: a (op) const[b] */
                   TO_OP_ADDC = 15, TO_OP_MULC = 16, TO_OP_DIVC = 17 /* a / c */, TO_OP_RDIVC = 18 /* c / a */, TO_OP_RSUBC = 19 /* c - a */ };
 #define TO_EXPR_MAXLEN 128
-#define TO_EXPR_MAXCONST 32
+#define TO_EXPR_MAXCONST 64
 typedef struct {
     int32_t kind;     /* to_cost_kind */
     int32_t terminal; /* `terminal` flag of the cost (LQRObjective sets it on the last cost, src/objective.jl:154,180) */

@@ -288,3 +288,52 @@ def test_quadrotor_notebook_zigzag_soft_pin():
     X = TO.states(prob)[0]
     assert np.linalg.norm(X[32, :3] - [10, 0, 1]) < 1.0 and np.linalg.norm(X[65, :3] - [-10, 0, 1]) < 1.0     # through the waypoints
     assert np.linalg.norm(X[-1, :3] - [0, 10, 1]) < 0.2
+
+
+def test_error_quadratic_cost():
+    """ErrorQuadratic (src/lie_costs.jl:170-240): 1/2 dx'Q dx + c + 1/2 u'Ru + r'u with dx = state_diff(x, x_ref) (Cayley map)"""
+    n, m, N, B = 13, 4, 4, 3
+    model = TO.Quadrotor()
+    Q13, R = rng.random(n), rng.random(m)
+    x_ref, u_ref = rand_state(), rng.standard_normal(m)
+    cost = TO.ErrorQuadratic(model, Q13, R, x_ref, u_ref)
+    assert len(cost.prog) <= 128
+    Q12 = np.delete(Q13, 3)                                   # deleteat(Q.diag, 4)  :216
+    prob = OracleProblem(model, TO.Objective(cost, N), np.zeros(n), 1.0, batch=B)
+    X = np.stack([[rand_state() for _ in range(N)] for _ in range(B)])
+    U = rng.standard_normal((B, N - 1, m))
+    TO.initial_states(prob, X); TO.initial_controls(prob, U)
+    chk = P.quadrotor_lie(B=B, N=N, cls=OracleProblem)
+    TO.initial_states(chk, np.broadcast_to(x_ref, (B, N, n)))
+    dx = TO.state_diff(chk, X)                                 # state_diff(x, x_ref): x relative to the reference
+    Jk = TO.cost_knots(prob)
+    Jx = 0.5 * np.sum(Q12 * dx * dx, axis=-1)
+    Ju = 0.5 * np.sum(R * (U - u_ref) ** 2, axis=-1)          # 1/2 u'Ru - (R u_ref)'u + 1/2 u_ref'R u_ref
+    assert np.allclose(Jk[:, :-1], Jx[:, :-1] + Ju, rtol=1e-12)
+    assert np.allclose(Jk[:, -1], Jx[:, -1] + 0.5 * u_ref @ (R * u_ref), rtol=1e-12)      # terminal knot: u = 0
+    # gradient against central differences of the closed form
+    g = TO.cost_gradient(prob)
+    b, k = 1, 1
+
+    def f(z):
+        TO.initial_states(chk, np.broadcast_to(x_ref, (B, N, n)))
+        d = TO.state_diff(chk, np.broadcast_to(z[:n], (B, N, n)))[0, 0]
+        return 0.5 * d @ (Q12 * d) + 0.5 * np.sum(R * (z[n:] - u_ref) ** 2)
+    z = np.concatenate([X[b, k], U[b, k]])
+    h = 1e-6
+    gfd = np.array([(f(z + e) - f(z - e)) / (2 * h) for e in h * np.eye(n + m)])
+    assert np.allclose(g[b, k], gfd, rtol=1e-6, atol=1e-7)
+    with pytest.raises(TO.ArgumentError):
+        TO.ErrorQuadratic(TO.Cartpole(), np.ones(4), np.ones(1), np.zeros(4))
+    # it drives the error-state solver (user cost -> materialised expansion -> dense Riccati pass)
+    xf = np.array([0, 0, 2, 1, 0, 0, 0, 0, 0, 0, 0, 0, 0.0])
+    hover = model.hover_control()
+    stage = TO.ErrorQuadratic(model, np.full(12, 0.1), np.full(m, 0.01), xf, hover)
+    term = TO.ErrorQuadratic(model, np.full(12, 100.0), np.full(m, 0.01), xf, hover, terminal=True)
+    base = P.quadrotor_lie(B=2, N=21, cls=OracleProblem)
+    p2 = OracleProblem(model, TO.Objective(stage, term, 21), base.x0, 1.0, error_state=True)
+    TO.initial_controls(p2, TO.controls(base)); TO.rollout(p2)
+    J0 = TO.merit(p2)
+    for _ in range(15):
+        TO.ilqr_step(p2, 1)
+    assert np.all(TO.merit(p2) < 0.2 * J0)

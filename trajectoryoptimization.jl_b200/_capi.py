@@ -24,7 +24,7 @@ MODEL_DOUBLE_INTEGRATOR, MODEL_CARTPOLE, MODEL_QUADROTOR, MODEL_ACROBOT = 0, 1, 
 COST_DIAGONAL, COST_QUADRATIC, COST_DIAGONAL_QUAT, COST_EXPR = 0, 1, 2, 3
 (OP_CONST, OP_X, OP_U, OP_ADD, OP_SUB, OP_MUL, OP_DIV, OP_NEG, OP_SIN, OP_COS, OP_EXP, OP_LOG, OP_SQRT, OP_POWC, OP_TANH,
  OP_ADDC, OP_MULC, OP_DIVC, OP_RDIVC, OP_RSUBC) = range(20)
-EXPR_MAXLEN, EXPR_MAXCONST = 128, 32
+EXPR_MAXLEN, EXPR_MAXCONST = 128, 64
 CONE_ZERO, CONE_NEGATIVE_ORTHANT, CONE_SECOND_ORDER, CONE_IDENTITY, CONE_POSITIVE_ORTHANT = 0, 1, 2, 3, 4
 CON_GOAL, CON_BOUND, CON_LINEAR, CON_CIRCLE, CON_SPHERE, CON_NORM, CON_COLLISION, CON_QUATVEC, CON_EXPR = 0, 1, 2, 3, 4, 5, 6, 7, 8
 PHASE_EXPAND, PHASE_BACKWARD, PHASE_FORWARD, PHASE_LADDER, PHASE_ACCEPT, PHASE_COUNT = 0, 1, 2, 3, 4, 8

@@ -403,6 +403,55 @@ class AutodiffCost(CostFunction):
         return dict(kind=K.COST_EXPR, terminal=self.terminal, prog=self.prog, consts=self.consts)
 
 
+def ErrorQuadratic(model, Q, R, x_ref, u_ref=None, r=None, c=0.0, q_ind=(4, 5, 6, 7), terminal=False):
+    """``ErrorQuadratic(model, Q, R, x_ref, u_ref; r, c, q_ind)`` (src/lie_costs.jl:170-240): ``1/2 dx'Q dx + c + 1/2 u'Ru + r'u`` with
+    ``dx = RD.state_diff(model, x, x_ref, CayleyMap())`` the 12-dimensional error state of a rigid body (``Q`` of the full state size
+    loses its 4th entry, :214-217; ``r -= R u_ref``, ``c += 1/2 u_ref'R u_ref``, :218-219).  The reference differentiates it with
+    ForwardAD (:196); here it is a recorded program (``AutodiffCost``).  The reference's own advice (:185-186): prefer ``DiagonalQuatCost``."""
+    n, m = model.dims()
+    if model.errstate_dim() == n:
+        raise ArgumentError("ErrorQuadratic needs a rigid-body (Lie-group) model")
+    Qd = np.asarray(Q, dtype=float)
+    Qd = np.diag(Qd).copy() if Qd.ndim == 2 else Qd.copy()
+    Rd = np.asarray(R, dtype=float)
+    Rd = np.diag(Rd).copy() if Rd.ndim == 2 else Rd.copy()
+    x_ref = np.asarray(x_ref, dtype=float)
+    q_ind = np.asarray(q_ind, dtype=int) - 1
+    if Qd.size == x_ref.size:
+        Qd = np.delete(Qd, q_ind[0])
+    if Qd.size != n - 1 or Rd.size != m:
+        raise DimensionMismatch("ErrorQuadratic: Q must have 12 (or 13) and R m diagonal entries")
+    u_ref = np.zeros(m) if u_ref is None else np.asarray(u_ref, dtype=float)
+    rv = (np.zeros(m) if r is None else np.asarray(r, dtype=float)) - Rd * u_ref
+    cc = float(c) + 0.5 * float(u_ref @ (Rd * u_ref))
+    qr = x_ref[q_ind]
+    vec_idx = [i for i in range(n) if i not in set(q_ind.tolist())]
+
+    def fun(x, u):
+        # state_diff: q_ref^-1 (x) q, inverse Cayley map = vector part / scalar part; vector states subtract
+        p = [x[i] for i in q_ind]
+        dw = qr[0] * p[0] + qr[1] * p[1] + qr[2] * p[2] + qr[3] * p[3]
+        dv = [qr[0] * p[1] - qr[1] * p[0] - (qr[2] * p[3] - qr[3] * p[2]),
+              qr[0] * p[2] - qr[2] * p[0] - (qr[3] * p[1] - qr[1] * p[3]),
+              qr[0] * p[3] - qr[3] * p[0] - (qr[1] * p[2] - qr[2] * p[1])]
+        dx = [x[i] - x_ref[i] for i in vec_idx[:q_ind[0]]] + [d / dw for d in dv] + [x[i] - x_ref[i] for i in vec_idx[q_ind[0]:]]
+        J = None
+        for w, d in zip(Qd, dx):
+            if w != 0.0:
+                t = w * (d * d)
+                J = t if J is None else J + t
+        for w, rr, uu in zip(Rd, rv, u):
+            if w != 0.0:
+                t = w * (uu * uu)
+                J = t if J is None else J + t
+        J = 0.5 * J if J is not None else 0.0
+        for rr, uu in zip(rv, u):
+            if rr != 0.0:
+                J = J + rr * uu
+        return J + cc if cc != 0.0 else J
+    return AutodiffCost(n, m, fun, terminal=terminal)
+
+
 def make_quadratic_cost(Q, R, H=None, q=None, r=None, c=0.0, **kw):
     """``QuadraticCostFunction(Q,R,H,q,r,c)`` (src/cost_functions.jl:60-68): Diagonal when it can be."""
     Hn = 0.0 if H is None else float(np.max(np.abs(H), initial=0.0))

@@ -19,7 +19,7 @@
 #define TO_MAXP 32          // rows of one constraint at one knot
 #define TO_CON_A 256
 #define TO_EXPR_LEN 128      // == TO_EXPR_MAXLEN / TO_EXPR_MAXCONST of include/trajopt_b200.h
-#define TO_EXPR_CONST 32
+#define TO_EXPR_CONST 64
 #define TO_EC_LEN 40
 #define TO_NBUF 9            // trajectory buffers per instance: the live one + 8 line-search candidates
 

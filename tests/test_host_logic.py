@@ -66,6 +66,32 @@ def test_constraint_list_and_objective_host_logic():
     assert sum(b - a for a, b in (TO.multi_gpu.shard_slice(4096, r, 8) for r in range(8))) == 4096
 
 
+def test_constraint_list_reference_test():
+    """test/constraint_list.jl:33-78: add_constraint! order / insertion index, per-knot counts, copy, iteration, dimension check"""
+    r = np.random.default_rng(2)
+    n, m, N = 4, 1, 11
+    cir = TO.CircleConstraint(n, [1.0, 1, 1], [1.0, 2, 3], [1.0, 1, 1])
+    goal = TO.GoalConstraint(r.random(n))
+    lin = TO.LinearConstraint(n, m, r.random((5, n)), r.random(5), TO.Inequality())
+    bnd = TO.BoundConstraint(n, m, x_min=-r.random(n), x_max=r.random(n), u_min=-r.random(m), u_max=r.random(m))
+    cons = TO.ConstraintList(n, m, N)
+    TO.add_constraint(cons, cir, (1, N))
+    assert cons.constraints[0] is cir and cons[0] is cir and cons.inds[0] == (1, N) and np.array_equal(cons.p, [cir.p] * N)     # :35-38
+    TO.add_constraint(cons, goal, N)
+    assert cons[1] is goal and cons.inds[1] == (N, N)                                                                            # :41-43
+    assert np.array_equal(cons.p[:N - 1], [cir.p] * (N - 1)) and cons.p[-1] == cir.p + goal.p                                   # :44-45
+    TO.add_constraint(cons, lin, (1, 4), 0)                                                                                      # add_constraint!(cons, lin, 1:4, 1)
+    assert cons[0] is lin and cons[1] is cir and cons[-1] is goal and cons.inds[0] == (1, 4)                                    # :48-51
+    assert np.array_equal(cons.p[:4], [cir.p + lin.p] * 4) and np.array_equal(cons.p[4:N - 1], [cir.p] * (N - 5)) and len(cons) == 3   # :52-54
+    cons2 = cons.copy()
+    TO.add_constraint(cons, bnd, (1, N - 1))
+    assert len(cons) == 4 and len(cons2) == 3 and cons[-1] is bnd                                                               # :56-64
+    assert TO.num_constraints(cons2) is not cons.p and not np.array_equal(TO.num_constraints(cons2), cons.p)
+    with pytest.raises(TO.DimensionMismatch):                                                                                    # :67-68
+        TO.add_constraint(cons, TO.LinearConstraint(2, 1, r.random((3, 2)), r.random(3), TO.Inequality()), (1, 4))
+    assert [c for c in cons] == [lin, cir, goal, bnd] and [TO.output_dim(c) for c in cons] == [5, 3, n, 2 * (n + m)]             # :71-74
+
+
 WORKER = textwrap.dedent("""
     import os, sys
     sys.path.insert(0, {root!r}); sys.path.insert(0, os.path.join({root!r}, "tests"))

@@ -865,6 +865,11 @@ class ConstraintList:
     def zip(self):   # Base.zip(cons)  src/constraint_list.jl:147
         return zip(self.inds, self.constraints)
 
+    def copy(self):   # Base.copy(cons)  src/constraint_list.jl:54-60: a new list over the same constraint objects
+        new = ConstraintList(self.n, self.m, self.N)
+        new.constraints, new.inds, new.p = list(self.constraints), list(self.inds), self.p.copy()
+        return new
+
 
 def add_constraint(cons, con, inds, idx=-1):
     """``add_constraint!(cons, con, inds)`` (src/constraint_list.jl:103-134); ``inds`` = knot ``k`` or ``(first, last)``."""

@@ -48,7 +48,7 @@ class OracleProblem(TO.Problem):
     def _call(self, name, *args):
         fn = getattr(self._lib, "orc_" + name[3:])
         fn.restype = C.c_int
-        conv = [C.c_void_p(a) if isinstance(a, int) and False else a for a in args]
+        conv = [C.c_double(a) if isinstance(a, float) else a for a in args]
         rc = fn(self._h, *conv)
         if rc:
             raise TO.TrajOptError(self._lib.orc_last_error(self._h).decode())

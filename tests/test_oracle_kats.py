@@ -525,3 +525,63 @@ def test_change_dimension_of_constraints_lists_and_costs():
         TO.IndexedConstraint(n2, m2, TO.BoundConstraint(n, m, u_max=1.0), (1, 3), (1, 2))
     with pytest.raises(TO.ArgumentError):
         TO.IndexedConstraint(n2, m2, TO.GoalConstraint(np.zeros(n)), [4, 3, 2, 1])
+
+
+def test_problem_constructor_and_setters_reference_test():
+    """test/problems_tests.jl:1-215 against the host API (cartpole, N = 11, tf = 5): fields, defaults, time steps, initial / goal
+    state setters and what they modify, dims, cost before / after the rollout, setinitialtime!"""
+    import copy
+    n, m, N, tf = 4, 1, 11, 5.0
+    model = TO.Cartpole()
+    x0, xf = np.zeros(n), np.array([0, np.pi, 0, 0])
+    Q, Qf, R = 1e-2 * np.ones(n), 100.0 * np.ones(n), 1e-1 * np.ones(m)
+    obj = TO.LQRObjective(Q, R, Qf, xf, N)
+    conSet = TO.ConstraintList(n, m, N)
+    bnd, goal = TO.BoundConstraint(n, m, u_min=-3.0, u_max=3.0), TO.GoalConstraint(xf)
+    TO.add_constraint(conSet, bnd, (1, N - 1)); TO.add_constraint(conSet, goal, (N, N))
+    X0, U0 = np.zeros((N, n)), np.full((N - 1, m), 0.01)
+    prob = OracleProblem(model, obj, x0, tf, xf=xf, constraints=conSet, X0=X0, U0=U0)                    # keyword constructor :64
+    assert np.array_equal(prob.x0[0], x0) and np.array_equal(prob.xf, xf) and TO.get_constraints(prob) is conSet and prob.obj is obj
+    assert prob.N == N and np.allclose(TO.states(prob)[0], X0) and np.allclose(TO.controls(prob)[0], U0)   # :65-76
+    assert np.isclose(TO.gettimes(prob)[-1], tf)
+    dts = np.concatenate([np.full(N // 2, 1.0), np.full(N - N // 2 - 1, 0.5)]); dts *= tf / dts.sum()
+    p2 = OracleProblem(model, obj, x0, tf, xf=xf, constraints=conSet, dt=dts)
+    assert np.allclose(TO.gettimes(p2), np.concatenate([[0], np.cumsum(dts)]))                             # :79-82
+    with pytest.raises(TO.ArgumentError):                                                                   # :85 (AssertionError in the reference)
+        OracleProblem(model, obj, x0, tf, xf=xf, constraints=conSet, dt=1.0)
+    p3 = OracleProblem(model, obj, x0, tf)                                                                  # defaults :92-99
+    assert not p3.x0.any() and p3.N == N and np.isnan(TO.states(p3)).all() and not TO.controls(p3).any()
+    assert len(TO.get_constraints(p3)) == 0 and not TO.is_constrained(p3)
+    assert np.allclose(TO.gettimes(p3), np.arange(N) * tf / (N - 1))
+    TO.initial_states(p3, 2 * X0 + 1); TO.initial_controls(p3, 2 * U0)                                     # :102-105
+    assert np.allclose(TO.states(p3)[0], 2 * X0 + 1) and np.allclose(TO.controls(p3)[0], 2 * U0)
+    x0_ = np.random.default_rng(0).random(n)
+    TO.set_initial_state(p3, x0_)                                                                           # :145-148
+    assert np.allclose(TO.get_initial_state(p3)[0], x0_)
+    with pytest.raises(TO.DimensionMismatch):
+        TO.set_initial_state(p3, np.zeros(2 * n))
+    # goal state: objective and terminal constraint of COPIES (:151-170)
+    p4 = OracleProblem(model, obj.copy(), x0, tf, xf=xf, constraints=copy.deepcopy(conSet))
+    xf_new = np.random.default_rng(1).random(n)
+    TO.set_goal_state(p4, xf_new)
+    assert np.allclose(p4.xf, xf_new) and np.allclose(p4.obj[0].q, -Q * xf_new) and np.allclose(p4.constraints[1].xf, xf_new)
+    assert np.allclose(obj[0].q, -Q * xf) and np.allclose(conSet[1].xf, xf)                                # the originals are untouched
+    TO.rollout(p4)
+    lam_free_merit = TO.cost(p4)
+    assert np.allclose(TO.evaluate_constraints(p4, 1)[0, 0], TO.states(p4)[0, -1] - xf_new)                # the device-side constraint moved too
+    p5 = OracleProblem(model, obj.copy(), x0, tf, xf=xf, constraints=copy.deepcopy(conSet))
+    TO.set_goal_state(p5, xf_new, constraint=False)                                                         # :173-177
+    assert np.allclose(p5.obj[0].q, -Q * xf_new) and np.allclose(p5.obj[-1].q, -Qf * xf_new) and np.allclose(p5.constraints[1].xf, xf)
+    p6 = OracleProblem(model, obj.copy(), x0, tf, xf=xf)
+    TO.set_goal_state(p6, xf_new, objective=False)                                                          # :180-184
+    assert np.allclose(p6.xf, xf_new) and np.allclose(p6.obj[0].q, -Q * xf) and np.allclose(p6.obj[-1].q, -Qf * xf)
+    cs = copy.deepcopy(conSet)
+    p7 = OracleProblem(model, obj, x0, tf, xf=xf, constraints=cs)                                           # not copied: the originals change :187-191
+    TO.set_goal_state(p7, xf_new)
+    assert np.allclose(obj[0].q, -Q * xf_new) and np.allclose(obj[-1].q, -Qf * xf_new) and np.allclose(cs[1].xf, xf_new)
+    assert TO.dims(p7) == (n, m, N)                                                                         # :200-207
+    p8 = OracleProblem(model, TO.LQRObjective(Q, R, Qf, xf, N), x0, tf)
+    assert np.isnan(TO.cost(p8)).all()                                                                      # :210-212
+    TO.rollout(p8)
+    assert np.isfinite(TO.cost(p8)).all() and np.isfinite(lam_free_merit).all()
+    assert np.isclose(TO.setinitialtime(p8, 1.0), 1.0 + tf) and np.isclose(TO.gettimes(p8)[0], 1.0)        # :215-216

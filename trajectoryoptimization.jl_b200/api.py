@@ -505,6 +505,10 @@ class Objective:
     def dims(self):
         return self.cost[0].state_dim, self.cost[0].control_dim
 
+    def copy(self):   # Base.copy(obj)  src/objective.jl:112: copies of the cost functions (knots that share a cost object keep sharing the copy)
+        memo = {}
+        return Objective([memo.setdefault(id(c), c.copy()) for c in self.cost])
+
     def _tables(self):
         """distinct cost objects + per-knot index (what the device cost table holds)."""
         uniq, index, seen = [], [], {}
@@ -936,6 +940,8 @@ class Problem:
             dtv = np.full(N - 1, float(dt)) if np.ndim(dt) == 0 else np.asarray(dt, dtype=float)
         if not tf > t0:
             raise ArgumentError("tf must be greater than t0")   # @assert tf > t0 src/problem.jl:52
+        if dtv.shape != (N - 1,) or not np.isclose(dtv.sum(), tf - t0, rtol=1e-8):
+            raise ArgumentError("the time steps must add up to tf - t0")   # @assert in SampledTrajectory(...; tf, dt), test/problems_tests.jl:86
         self.model, self.obj, self.constraints = model, obj, cons
         self.N, self.n, self.m, self.B = N, n, m, B
         if error_state and model.errstate_dim() == n:

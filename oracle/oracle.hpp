@@ -9,7 +9,12 @@
 //              KAT the reference's tests hold for them is re-expressed in tests/test_oracle_*.py
 //              (test/cost_tests.jl:238-279, test/objective_tests.jl:86-140,
 //              test/constraint_tests.jl:17-39,209-344, test/cone_tests.jl:26-75, examples/quickstart.jl:71-137).
-//   UNPINNED : RK4, dual-number dynamics Jacobians, Riccati backward pass, forward line search, AL update.
+//              Also pinned: QuatVecEq value + Jacobian (test/constraint_tests.jl:412-444), user costs through AD
+//              (test/nlcosts.jl:22-45), the docs' ControlNorm constraint (docs/src/constraint_interface.md:52-72),
+//              IndexedConstraint (test/constraint_tests.jl:346-407, host side), DiagonalQuatCost closed forms
+//              (src/lie_costs.jl:68-95; its test file test/quatcosts.jl is stale and not run by the reference).
+//   UNPINNED : RK4, dual-number dynamics Jacobians, Riccati backward pass, forward line search, AL update,
+//              and the Lie-group error state (state_diff, G, error_expansion: RobotDynamics / Rotations / Altro).
 //              Their arithmetic lives in RobotDynamics.jl 0.4.8 / ForwardDiff 0.10 / RobotZoo 0.3 /
 //              Altro.jl 0.3-0.5, none of which is vendored under /root/reference and none of which can
 //              run here (no Julia).  They are restated from the published algorithms; independent checks

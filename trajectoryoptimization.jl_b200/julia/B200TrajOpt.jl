@@ -21,6 +21,7 @@ struct ToCostSpec
     Q::Ptr{Float64}; R::Ptr{Float64}; H::Ptr{Float64}; q::Ptr{Float64}; r::Ptr{Float64}
     c::Float64
     w::Float64; q_ref::Ptr{Float64}; q_ind::Ptr{Int32}       # DiagonalQuatCost (kind 2), else 0 / C_NULL
+    prog_len::Int32; nconst::Int32; prog::Ptr{Int32}; consts::Ptr{Float64}   # recorded program (kind 3), else 0 / C_NULL
 end
 struct ToConstraintSpec
     kind::Int32; first::Int32; last::Int32; sense::Int32; p::Int32; flag::Int32; ninds::Int32
@@ -76,7 +77,11 @@ function BatchedProblem(prob::TO.Problem, mid::Integer, B::Integer; device::Inte
     seen = IdDict{Any,Int32}()
     for k = 1:N
         c = obj[k]
-        if !haskey(seen, c)
+        if !haskey(seen, c) && !(c isa TO.QuadraticCostFunction)      # RD.@autodiff user cost: record RD.evaluate
+            tape = root(record((x, u) -> RD.evaluate(c, x, u), n, m))
+            push!(costs, expr_cost_spec(tape, k == N))
+            seen[c] = Int32(length(costs) - 1)
+        elseif !haskey(seen, c)
             isdiag = TO.is_diag(c)
             Q = root(isdiag ? Vector{Float64}(diag(c.Q)) : Matrix{Float64}(c.Q))
             R = root(isdiag ? Vector{Float64}(diag(c.R)) : Matrix{Float64}(c.R))
@@ -84,9 +89,9 @@ function BatchedProblem(prob::TO.Problem, mid::Integer, B::Integer; device::Inte
             q = root(Vector{Float64}(c.q)); r = root(Vector{Float64}(c.r))
             if c isa TO.DiagonalQuatCost                         # src/lie_costs.jl:33-56
                 qref = root(Vector{Float64}(c.q_ref)); qind = root(Vector{Int32}(c.q_ind))
-                push!(costs, ToCostSpec(2, c.terminal ? 1 : 0, pointer(Q), pointer(R), C_NULL, pointer(q), pointer(r), c.c, c.w, pointer(qref), pointer(qind)))
+                push!(costs, ToCostSpec(2, c.terminal ? 1 : 0, pointer(Q), pointer(R), C_NULL, pointer(q), pointer(r), c.c, c.w, pointer(qref), pointer(qind), 0, 0, C_NULL, C_NULL))
             else
-                push!(costs, ToCostSpec(isdiag ? 0 : 1, c.terminal ? 1 : 0, pointer(Q), pointer(R), H, pointer(q), pointer(r), c.c, 0.0, C_NULL, C_NULL))
+                push!(costs, ToCostSpec(isdiag ? 0 : 1, c.terminal ? 1 : 0, pointer(Q), pointer(R), H, pointer(q), pointer(r), c.c, 0.0, C_NULL, C_NULL, 0, 0, C_NULL, C_NULL))
             end
             seen[c] = Int32(length(costs) - 1)
         end
@@ -120,6 +125,66 @@ function BatchedProblem(prob::TO.Problem, mid::Integer, B::Integer; device::Inte
     finalizer(p -> ccall((:to_destroy, libb200), Cint, (Ptr{Cvoid},), p.h), bp)
     return bp
 end
+
+# ---- user-defined costs / constraints (RD.@autodiff types): record RD.evaluate once, ship the tape ---------------------
+# The device differentiates a straight-line program with second-order forward-mode duals (include/trajopt_b200.h to_expr_op).
+# `Rec` is a number type that appends one instruction per arithmetic operation -- the trick ForwardDiff.Dual uses to see the
+# user's function, applied to recording instead of differentiating.
+mutable struct Tape
+    prog::Vector{Int32}      # op, a, b triples (0-based operand indices)
+    consts::Vector{Float64}
+end
+Tape() = Tape(Int32[], Float64[])
+struct Rec <: Real
+    tape::Tape
+    idx::Int32               # 0-based index of the instruction that produced this value
+end
+function emit!(t::Tape, op, a, b)
+    push!(t.prog, Int32(op), Int32(a), Int32(b))
+    Rec(t, Int32(length(t.prog) ÷ 3 - 1))
+end
+function constindex!(t::Tape, v::Real)
+    i = findfirst(c -> c === Float64(v), t.consts)
+    i === nothing ? (push!(t.consts, Float64(v)); length(t.consts) - 1) : i - 1
+end
+Base.promote_rule(::Type{Rec}, ::Type{<:Real}) = Rec
+for (f, op, opc, ropc) in ((:+, 3, 15, 15), (:*, 5, 16, 16))             # commutative: ADD / ADDC, MUL / MULC
+    @eval Base.$f(a::Rec, b::Rec) = emit!(a.tape, $op, a.idx, b.idx)
+    @eval Base.$f(a::Rec, b::Real) = emit!(a.tape, $opc, a.idx, constindex!(a.tape, b))
+    @eval Base.$f(a::Real, b::Rec) = emit!(b.tape, $ropc, b.idx, constindex!(b.tape, a))
+end
+Base.:-(a::Rec, b::Rec) = emit!(a.tape, 4, a.idx, b.idx)
+Base.:-(a::Rec, b::Real) = emit!(a.tape, 15, a.idx, constindex!(a.tape, -b))    # a + (-b)
+Base.:-(a::Real, b::Rec) = emit!(b.tape, 19, b.idx, constindex!(b.tape, a))     # RSUBC
+Base.:-(a::Rec) = emit!(a.tape, 7, a.idx, 0)
+Base.:/(a::Rec, b::Rec) = emit!(a.tape, 6, a.idx, b.idx)
+Base.:/(a::Rec, b::Real) = emit!(a.tape, 17, a.idx, constindex!(a.tape, b))     # DIVC
+Base.:/(a::Real, b::Rec) = emit!(b.tape, 18, b.idx, constindex!(b.tape, a))     # RDIVC
+Base.:^(a::Rec, p::Integer) = p == 2 ? a * a : emit!(a.tape, 13, a.idx, constindex!(a.tape, p))
+Base.:^(a::Rec, p::Real) = emit!(a.tape, 13, a.idx, constindex!(a.tape, p))     # POWC
+for (f, op) in ((:sin, 8), (:cos, 9), (:exp, 10), (:log, 11), (:sqrt, 12), (:tanh, 14))
+    @eval Base.$f(a::Rec) = emit!(a.tape, $op, a.idx, 0)
+end
+
+"""
+    record(f, n, m) -> Tape
+
+Call `f(x, u)` (e.g. `(x, u) -> RD.evaluate(cost, x, u)`) on recording vectors and return the tape; the last instruction is the
+value (scalar costs) or the last `p` instructions are the outputs (constraints: `f` returns a vector, each entry is re-emitted).
+"""
+function record(f, n::Integer, m::Integer)
+    t = Tape()
+    x = [emit!(t, 1, i - 1, 0) for i = 1:n]          # TO_OP_X
+    u = [emit!(t, 2, j - 1, 0) for j = 1:m]          # TO_OP_U
+    out = f(x, u)
+    for o in (out isa AbstractVector ? out : (out,))
+        o isa Rec ? emit!(t, 15, o.idx, constindex!(t, 0.0)) : emit!(t, 0, constindex!(t, o), 0)
+    end
+    return t
+end
+expr_cost_spec(t::Tape, terminal::Bool) =            # ToCostSpec of kind TO_COST_EXPR (keep `t` alive: GC roots)
+    ToCostSpec(3, terminal ? 1 : 0, C_NULL, C_NULL, C_NULL, C_NULL, C_NULL, 0.0, 0.0, C_NULL, C_NULL,
+               Int32(length(t.prog) ÷ 3), Int32(length(t.consts)), pointer(t.prog), pointer(t.consts))
 
 # ---- the operator surface a solver calls (SURVEY.md 2.3) ------------------------------------------------------
 # host arrays are Array{Float64,3}: X (n, N, B), U (m, N-1, B) -- exactly the library's instance-major layout.

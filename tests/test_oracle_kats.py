@@ -585,3 +585,30 @@ def test_problem_constructor_and_setters_reference_test():
     TO.rollout(p8)
     assert np.isfinite(TO.cost(p8)).all() and np.isfinite(lam_free_merit).all()
     assert np.isclose(TO.setinitialtime(p8, 1.0), 1.0 + tf) and np.isclose(TO.gettimes(p8)[0], 1.0)        # :215-216
+
+
+def test_problem_copy_getters_and_cost_checks():
+    """Problem(p; ...) / copy(prob) (src/problem.jl:125-128, :342-345), get_initial_time / get_final_time (:189-196), RD.state_dim(prob, k)
+    (:149-150), initial_trajectory! (:242-245), and the definiteness warnings of the cost constructors (src/cost_functions.jl:337-343)"""
+    prob = P.cartpole(B=2, N=11, cls=OracleProblem, u_bound=3.0, goal=True)
+    TO.rollout(prob); TO.ilqr_step(prob, 1)
+    cp = TO.copy_problem(prob)
+    assert cp.obj is not prob.obj and cp.constraints is not prob.constraints and cp.constraints[0] is prob.constraints[0]
+    assert np.array_equal(TO.states(cp), TO.states(prob)) and np.array_equal(TO.controls(cp), TO.controls(prob))
+    assert np.allclose(TO.cost(cp), TO.cost(prob), rtol=1e-14) and np.allclose(TO.gettimes(cp), TO.gettimes(prob))
+    assert TO.get_initial_time(cp) == 0.0 and np.isclose(TO.get_final_time(cp), 5.0)
+    assert TO.state_dim(cp, 3) == 4 and TO.control_dim(cp, 3) == 1 and TO.horizonlength(cp) == 11
+    TO.set_goal_state(cp, np.array([0.0, 1.0, 0, 0]))                    # the copy's objective moves, the original's does not
+    assert not np.allclose(cp.obj[0].q, prob.obj[0].q)
+    X, U, t = TO.get_trajectory(prob)
+    TO.initial_trajectory(cp, 2 * X, 3 * U)
+    assert np.allclose(TO.states(cp), 2 * X) and np.allclose(TO.controls(cp), 3 * U) and t.shape == (11,)
+    with pytest.warns(UserWarning, match="positive semi-definite"):
+        TO.DiagonalCost([-1.0, 1.0], [1.0])
+    with pytest.warns(UserWarning, match="positive definite"):
+        TO.DiagonalCost([1.0, 1.0], [0.0])
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("error")
+        TO.DiagonalCost([1.0, 1.0], [0.0], terminal=True)               # no check on R for terminal costs
+        TO.DiagonalCost([-1.0, 1.0], [0.0], checks=False)

@@ -11,6 +11,7 @@ same memory as Julia's ``Array{Float64,3}(n, N, B)``.  Knot indices given to ``a
 inclusive ranges exactly like the reference (``add_constraint!(cons, con, 1:N-1)`` -> ``(1, N-1)``).
 """
 import ctypes as C
+import warnings
 
 import numpy as np
 
@@ -226,10 +227,15 @@ class QuadraticCostFunction(CostFunction):
 class DiagonalCost(QuadraticCostFunction):   # src/cost_functions.jl:326-347
     is_diag = True
 
-    def __init__(self, Q, R, H=None, q=None, r=None, c=0.0, terminal=False):
+    def __init__(self, Q, R, H=None, q=None, r=None, c=0.0, terminal=False, checks=True):
         super().__init__(Q, R, None, q, r, c, terminal)
         self.Q = np.diag(np.diagonal(self.Q))
         self.R = np.diag(np.diagonal(self.R))
+        if checks:   # src/cost_functions.jl:337-343
+            if np.any(np.diagonal(self.Q) < 0):
+                warnings.warn("Q needs to be positive semi-definite.")
+            elif np.any(np.diagonal(self.R) <= 0) and not terminal:
+                warnings.warn("R needs to be positive definite.")
 
 
 class QuadraticCost(QuadraticCostFunction):   # src/cost_functions.jl:417-454
@@ -990,6 +996,49 @@ class Problem:
 
 def dims(prob):   # RD.dims(prob, k)  src/problem.jl:147
     return prob.n, prob.m, prob.N
+
+
+def state_dim(prob, k=1):   # RD.state_dim(prob, k)  src/problem.jl:149
+    return prob.n
+
+
+def control_dim(prob, k=1):   # RD.control_dim(prob, k)  src/problem.jl:150
+    return prob.m
+
+
+def get_initial_time(prob):   # src/problem.jl:189
+    return float(gettimes(prob)[0])
+
+
+def get_final_time(prob):   # src/problem.jl:196
+    return float(gettimes(prob)[-1])
+
+
+def get_trajectory(prob):
+    """``get_trajectory(prob)`` (src/problem.jl:222): the sampled trajectory as ``(X[B, N, n], U[B, N-1, m], t[N])``."""
+    return states(prob), controls(prob), gettimes(prob)
+
+
+def initial_trajectory(prob, X0, U0):   # initial_trajectory!(prob, Z0)  src/problem.jl:242-245
+    initial_states(prob, X0)
+    initial_controls(prob, U0)
+
+
+def copy_problem(prob, cls=None, **overrides):
+    """``copy(prob)`` / ``Problem(p; model, obj, constraints, x0, xf, t0, tf)`` (src/problem.jl:125-128, :342-345): a new batch with copies of
+    the objective and the constraint list (the constraint objects themselves are shared, as ``copy(::ConstraintList)`` does), the same x0, xf,
+    time grid and the current trajectory."""
+    t = gettimes(prob)
+    obj = overrides.pop("obj", prob.obj.copy())
+    cons = overrides.pop("constraints", prob.constraints.copy())
+    new = (cls or type(prob))(overrides.pop("model", prob.model), obj, overrides.pop("x0", prob.x0.copy()), float(t[-1]),
+                              xf=overrides.pop("xf", prob.xf.copy()), constraints=cons, t0=float(t[0]), dt=np.diff(t),
+                              error_state=prob.error_state, **overrides)
+    X, U = states(prob), controls(prob)
+    if np.all(np.isfinite(X)):
+        initial_states(new, X)
+    initial_controls(new, U)
+    return new
 
 
 def horizonlength(prob):

@@ -590,7 +590,7 @@ def test_problem_constructor_and_setters_reference_test():
 def test_problem_copy_getters_and_cost_checks():
     """Problem(p; ...) / copy(prob) (src/problem.jl:125-128, :342-345), get_initial_time / get_final_time (:189-196), RD.state_dim(prob, k)
     (:149-150), initial_trajectory! (:242-245), and the definiteness warnings of the cost constructors (src/cost_functions.jl:337-343)"""
-    prob = P.cartpole(B=2, N=11, cls=OracleProblem, u_bound=3.0, goal=True)
+    prob = TO.problems.cartpole(B=2, N=11, cls=OracleProblem, u_bound=3.0, goal=True)
     TO.rollout(prob); TO.ilqr_step(prob, 1)
     cp = TO.copy_problem(prob)
     assert cp.obj is not prob.obj and cp.constraints is not prob.constraints and cp.constraints[0] is prob.constraints[0]

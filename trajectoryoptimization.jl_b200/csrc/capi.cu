@@ -383,9 +383,9 @@ int to_create(const to_spec* s, to_handle** out) {
     }
     P.lie = s->error_state ? 1 : 0; P.qs = 3; P.ne = P.lie ? n - 1 : n;
     if (P.lie) P.dense_riccati = 1;
-    {   // compact expansion (lie.cu): error state + diagonal costs (quadratic / quaternion) + Goal/Bound constraints only
+    {   // compact expansion (lie.cu): error state + DiagonalCost + Goal/Bound constraints only
         bool diag_costs = true;
-        for (const auto& c : h->h_costs) if (!c.diag || c.expr) diag_costs = false;
+        for (const auto& c : h->h_costs) if (!c.diag || c.expr || c.quat) diag_costs = false;   // (quaternion costs: generic expansion, until the compact kernel's variant is GPU-tested)
         bool diag_cons = true;
         for (int i = 0; i < s->ncon; i++) if (s->cons[i].kind != TO_CON_GOAL && s->cons[i].kind != TO_CON_BOUND) diag_cons = false;
         P.compact = (P.lie && diag_costs && diag_cons && P.ne == 12 && m == 4) ? 1 : 0;

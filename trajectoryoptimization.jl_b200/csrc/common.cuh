@@ -90,7 +90,7 @@ struct DevProblem {
     // x[qs..qs+3] contributing its 3-dimensional differential.  dense_riccati: the backward pass reads the per-knot expansion
     // (EG, EH) and [A_e B_e] (ABe) materialised in HBM by lie.cu instead of expanding in-kernel (error state, quaternion costs).
     int lie, ne, qs, dense_riccati;
-    int compact, pad_c;       // lie + only diagonal costs (quadratic / quaternion) + Goal/Bound constraints: the expansion of a knot is a
+    int compact, pad_c;       // lie + only DiagonalCost + Goal/Bound constraints: the expansion of a knot is a
                               // gradient, a diagonal and the 3 x 3 attitude block -> EC, 40 doubles per knot instead of EG + EH (272)
     double* EC;               // [B][N][TO_EC_LEN]: g_e(16) | diag(16) | block (0,1),(0,2),(1,2) | pad
     double* ABe;              // [B][N-1][ne+m][ne]   ne x (ne+m) col-major

@@ -128,10 +128,10 @@ __global__ void __launch_bounds__(128) k_error_expansion(const DevProblem P, con
     }
 }
 
-// Compact error-state expansion (P.compact: diagonal quadratic / quaternion costs, Goal / Bound constraints -- the BASELINE problem
+// Compact error-state expansion (P.compact: DiagonalCost objective, Goal / Bound constraints -- the BASELINE problem
 // class).  The full-state expansion is a gradient g and a DIAGONAL h, so the error-state one is G'g, the same diagonal outside the
 // attitude and the 3 x 3 block G_q' diag(h_q) G_q - (q'g_q) I3: 40 doubles per knot (TO_EC_LEN) instead of 272.  One thread per
-// (instance, knot); cost: RD.gradient!/hessian! of DiagonalCost / DiagonalQuatCost (src/cost_functions.jl:137-233, src/lie_costs.jl:79-95),
+// (instance, knot); cost: RD.gradient!/hessian! of DiagonalCost (src/cost_functions.jl:137-233),
 // AL rows of Goal / Bound constraints as in al_knot_expansion (costcon.cuh).
 __global__ void __launch_bounds__(128) k_expansion_compact(const DevProblem P) {
     const int n = P.n, m = P.m, nm = n + m, qs = P.qs;
@@ -147,12 +147,6 @@ __global__ void __launch_bounds__(128) k_expansion_compact(const DevProblem P) {
     for (int a = 0; a < m; a++) z[n + a] = last ? 0.0 : ug[a];
     const DevCost& c = P.costs[P.cost_index[k]];
     for (int i = 0; i < n; i++) { g[i] = fma(c.Qd[i], z[i], c.q[i]); h[i] = c.Qd[i]; }
-    if (c.quat) {
-        double dq = 0;
-        for (int i = 0; i < 4; i++) dq = fma(c.q_ref[i], z[c.q_ind[i]], dq);
-        const double sw = dq < 0 ? c.w : -c.w;
-        for (int i = 0; i < 4; i++) g[c.q_ind[i]] = fma(sw, c.q_ref[i], g[c.q_ind[i]]);
-    }
     for (int a = 0; a < m; a++) { g[n + a] = last ? 0.0 : fma(c.Rd[a], z[n + a], c.r[a]); h[n + a] = last ? 0.0 : c.Rd[a]; }
     const int lim = last ? n : nm;
     for (int ci = 0; ci < P.ncon; ci++) {

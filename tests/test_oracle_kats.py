@@ -612,3 +612,52 @@ def test_problem_copy_getters_and_cost_checks():
         warnings.simplefilter("error")
         TO.DiagonalCost([1.0, 1.0], [0.0], terminal=True)               # no check on R for terminal costs
         TO.DiagonalCost([-1.0, 1.0], [0.0], checks=False)
+
+
+def test_cost_constructors_and_math_reference_test():
+    """test/cost_tests.jl:44-146 (constructors, definiteness warnings, LQRCost) and :148-196 (addition, inversion) on the host API"""
+    import warnings
+    r = np.random.default_rng(8)
+    n, m = 12, 6
+    Q, R, Qf = np.full(n, 0.1), np.full(m, 0.01), np.full(n, 10.0)
+    H, q, rr, c = r.random((m, n)), r.random(n), r.random(m), 0.37
+    xf = np.ones(n)
+    qc = TO.QuadraticCost(np.diag(Q), np.diag(R))                                         # :45-53
+    assert np.array_equal(qc.Q, np.diag(Q)) and not qc.q.any() and not qc.r.any() and qc.c == 0
+    assert (qc.state_dim, qc.control_dim) == (n, m) and TO.is_blockdiag(qc)
+    qc = TO.QuadraticCost(np.diag(Q), np.diag(R), H=H, q=q, r=rr, c=c, terminal=True)     # :60-67
+    assert np.allclose(qc.H, H) and np.array_equal(qc.q, q) and np.array_equal(qc.r, rr) and qc.c == c and qc.terminal and not TO.is_blockdiag(qc)
+    with pytest.warns(UserWarning, match="R is not positive definite"):                   # :95
+        TO.QuadraticCost(np.diag(Q), np.diag(R) * 0, H=H, q=q, r=rr, c=c)
+    with pytest.warns(UserWarning, match="Q is not positive semidefinite"):               # :97-104
+        TO.QuadraticCost(np.diag(Q) - 0.2, np.diag(R), H=H, q=q, r=rr, c=c)
+    with warnings.catch_warnings():
+        warnings.simplefilter("error")
+        TO.QuadraticCost(np.diag(Q) * 0, np.diag(R), H=H, q=q, r=rr, c=c)                 # :96 @test_nowarn
+        TO.QuadraticCost(np.diag(Q) - 0.2, np.diag(R), q=q, checks=False)                 # :111
+    dc = TO.DiagonalCost(Q, R, q=q)                                                       # :114-135 (diagonal vectors or matrices)
+    dc2 = TO.DiagonalCost(np.diag(Q), np.diag(R), q=q)
+    assert np.array_equal(dc.Q, dc2.Q) and np.array_equal(dc.R, np.diag(R)) and not dc.r.any() and np.array_equal(dc.q, q)
+    lq = TO.LQRCost(Q, R, xf)                                                             # :138-146
+    assert isinstance(lq, TO.DiagonalCost) and np.allclose(lq.q, -Q * xf) and not lq.r.any() and np.isclose(lq.c, 0.5 * xf @ (Q * xf))
+    assert TO.is_blockdiag(lq) and TO.is_diag(lq)
+    # addition :150-168
+    qcost = TO.QuadraticCost(np.diag(Q), np.diag(R), H=H, q=q, r=rr, c=c, checks=False)
+    dcost = TO.DiagonalCost(Q, R, q=q)
+    add = dcost + qcost
+    assert isinstance(add, TO.QuadraticCost) and np.allclose(add.Q, 2 * np.diag(Q)) and np.allclose(add.R, 2 * np.diag(R))
+    assert np.allclose(add.q, 2 * q) and np.allclose(add.r, rr) and np.isclose(add.c, c) and np.allclose(add.H, H)
+    dcost = TO.DiagonalCost(Q, R, q=q, r=rr, c=c)
+    add = dcost + dcost
+    assert isinstance(add, TO.DiagonalCost) and np.allclose(add.r, 2 * rr) and np.isclose(add.c, 2 * c)
+    with pytest.raises(TO.DimensionMismatch):                                             # :170-171 (AssertionError in the reference)
+        TO.DiagonalCost(Q, Q, q=q, r=q, c=c) + dcost
+    # inversion :173-195
+    dinv = dcost.inv()
+    assert np.allclose(np.diag(dinv.Q), 1 / Q) and np.allclose(np.diag(dinv.R), 1 / R) and np.array_equal(dinv.q, q) and TO.is_diag(dinv)
+    qinv = qcost.inv()
+    G = np.linalg.inv(np.block([[np.diag(Q), H.T], [H, np.diag(R)]]))
+    assert np.allclose(qinv.Q, G[:n, :n]) and np.allclose(qinv.H, G[n:, :n]) and np.allclose(qinv.R, G[n:, n:])
+    assert not TO.is_diag(qinv) and not TO.is_blockdiag(qinv) and np.array_equal(qinv.r, rr) and qinv.c == c
+    binv = TO.QuadraticCost(np.diag(Q), np.diag(R)).inv()
+    assert np.allclose(binv.Q, np.diag(1 / Q)) and TO.is_blockdiag(binv)

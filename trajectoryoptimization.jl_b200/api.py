@@ -175,6 +175,30 @@ class Acrobot(_Model):
 # Cost functions (reference src/cost_functions.jl)
 
 
+def _isposdef(A):
+    A = np.asarray(A, dtype=float)
+    if not np.allclose(A, A.T):
+        return False
+    try:
+        np.linalg.cholesky(A)
+        return True
+    except np.linalg.LinAlgError:
+        return False
+
+
+def _ispossemidef(A):
+    A = np.asarray(A, dtype=float)
+    return bool(np.all(np.linalg.eigvalsh(0.5 * (A + A.T)) >= -1e-12 * max(1.0, np.abs(A).max())))
+
+
+def is_diag(cost):   # src/cost_functions.jl:41
+    return bool(cost.is_diag)
+
+
+def is_blockdiag(cost):   # src/cost_functions.jl:48, :382, :455
+    return cost.is_blockdiag()
+
+
 def _isdiag(A):
     A = np.asarray(A, dtype=float)
     return A.ndim == 1 or np.count_nonzero(A - np.diag(np.diagonal(A))) == 0
@@ -207,15 +231,27 @@ class QuadraticCostFunction(CostFunction):
     def is_blockdiag(self):
         return self.is_diag or np.max(np.abs(self.H), initial=0.0) == 0.0
 
-    def copy(self):
-        return type(self)(self.Q, self.R, H=self.H, q=self.q, r=self.r, c=self.c, terminal=self.terminal)
+    def copy(self):   # Base.copy(::DiagonalCost)  src/cost_functions.jl:346-348 (checks = false)
+        return type(self)(self.Q, self.R, H=self.H, q=self.q, r=self.r, c=self.c, terminal=self.terminal, checks=False)
+
+    def inv(self):
+        """``inv(cost)`` (src/cost_functions.jl:381-383, :471-491): the cost with the inverse Hessian blocks ([Q H'; H R]^-1 when H != 0)."""
+        if self.is_diag:
+            return DiagonalCost(1.0 / np.diagonal(self.Q), 1.0 / np.diagonal(self.R), q=self.q, r=self.r, c=self.c, terminal=self.terminal, checks=False)
+        n = self.state_dim
+        if self.is_blockdiag():
+            return QuadraticCost(np.linalg.inv(self.Q), np.linalg.inv(self.R), H=self.H, q=self.q, r=self.r, c=self.c, terminal=self.terminal, checks=False)
+        G = np.linalg.inv(np.block([[self.Q, self.H.T], [self.H, self.R]]))
+        return QuadraticCost(G[:n, :n], G[n:, n:], H=G[n:, :n], q=self.q, r=self.r, c=self.c, terminal=self.terminal, checks=False)
 
     def __add__(self, other):   # +(c1, c2)  src/cost_functions.jl:259-270
         if isinstance(other, DiagonalQuatCost):
             return other + self   # src/lie_costs.jl:163
+        if (self.state_dim, self.control_dim) != (other.state_dim, other.control_dim):
+            raise DimensionMismatch("cost functions of different dimensions cannot be added")   # @assert :260-261
         cls = DiagonalCost if (self.is_diag and other.is_diag) else QuadraticCost
         return cls(self.Q + other.Q, self.R + other.R, H=self.H + other.H, q=self.q + other.q, r=self.r + other.r,
-                   c=self.c + other.c, terminal=self.terminal and other.terminal)
+                   c=self.c + other.c, terminal=self.terminal and other.terminal, checks=False)
 
     def _spec(self):
         if self.is_diag:
@@ -239,7 +275,16 @@ class DiagonalCost(QuadraticCostFunction):   # src/cost_functions.jl:326-347
 
 
 class QuadraticCost(QuadraticCostFunction):   # src/cost_functions.jl:417-454
-    pass
+    def __init__(self, Q, R, H=None, q=None, r=None, c=0.0, terminal=False, checks=True):
+        super().__init__(Q, R, H, q, r, c, terminal)
+        if checks:   # :436-443
+            if not terminal and not _isposdef(self.R):
+                warnings.warn("R is not positive definite")
+            if not _ispossemidef(self.Q):
+                warnings.warn("Q is not positive semidefinite")
+
+    def copy(self):
+        return QuadraticCost(self.Q, self.R, H=self.H, q=self.q, r=self.r, c=self.c, terminal=self.terminal, checks=False)
 
 
 class DiagonalQuatCost(DiagonalCost):

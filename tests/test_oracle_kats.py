@@ -661,3 +661,27 @@ def test_cost_constructors_and_math_reference_test():
     assert not TO.is_diag(qinv) and not TO.is_blockdiag(qinv) and np.array_equal(qinv.r, rr) and qinv.c == c
     binv = TO.QuadraticCost(np.diag(Q), np.diag(R)).inv()
     assert np.allclose(binv.Q, np.diag(1 / Q)) and TO.is_blockdiag(binv)
+
+
+def test_objective_constructors_reference_test():
+    """test/objective_tests.jl:17-84: Objective(cost, N) aliases one cost object, Objective(cost, term, N), Objective(costs), get_J"""
+    r = np.random.default_rng(9)
+    n, m, N = 4, 1, 11
+    Q, R, Qf = np.full(n, 0.1), np.full(m, 0.01), np.full(n, 10.0)
+    H, q, rr, c = r.random((m, n)), r.random(n), r.random(m), 0.4
+    qcost = TO.QuadraticCost(np.diag(Q), np.diag(R), H=H, q=q, r=rr, c=c)
+    obj = TO.Objective(qcost, N)
+    assert len(obj) == N and TO.state_dim(obj, 1) == n and TO.control_dim(obj, 1) == m and TO.get_J(obj) is obj.J and not obj[-1].terminal   # :21-25
+    assert obj[0] is obj[1] and obj[0].Q is obj[1].Q                                                                                          # :28-29
+    qcost.r[0] = 1.0
+    assert obj[2].r[0] == 1.0                                                                                                                 # :30-31
+    qterm = TO.QuadraticCost(np.diag(Qf), np.zeros((m, m)), q=q, c=c, terminal=True)
+    obj = TO.Objective(qcost, qterm, N)                                                                                                       # :36-44
+    assert obj[0] is obj[1] and np.allclose(obj[-1].Q, np.diag(Qf)) and not obj[-1].R.any() and obj[-1].terminal and np.array_equal(obj[-1].q, q)
+    costs = [(qcost if k < N - 1 else qterm).copy() for k in range(N)]
+    obj = TO.Objective(costs)                                                                                                                 # :67-79
+    assert len(obj) == N and obj[0] is not obj[1] and obj[0].Q is not obj[1].Q
+    prob = OracleProblem(TO.Cartpole(), obj, np.zeros(n), 1.0)
+    TO.initial_controls(prob, r.standard_normal((1, N - 1, m))); TO.rollout(prob)
+    Jk = TO.cost_knots(prob)
+    assert np.isclose(TO.get_J(prob.obj).sum(), TO.cost(prob)[0]) and np.array_equal(TO.get_J(prob.obj), Jk[0])                               # :139-140

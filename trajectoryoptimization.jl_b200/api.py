@@ -1043,12 +1043,18 @@ def dims(prob):   # RD.dims(prob, k)  src/problem.jl:147
     return prob.n, prob.m, prob.N
 
 
-def state_dim(prob, k=1):   # RD.state_dim(prob, k)  src/problem.jl:149
-    return prob.n
+def state_dim(obj, k=1):   # RD.state_dim(prob | obj, k), state_dim(cost | con)  src/problem.jl:149, src/objective.jl:60
+    if isinstance(obj, Objective): return obj[k - 1].state_dim
+    return obj.state_dim if isinstance(obj, CostFunction) else obj.n
 
 
-def control_dim(prob, k=1):   # RD.control_dim(prob, k)  src/problem.jl:150
-    return prob.m
+def control_dim(obj, k=1):   # RD.control_dim(prob | obj, k)  src/problem.jl:150, src/objective.jl:61
+    if isinstance(obj, Objective): return obj[k - 1].control_dim
+    return obj.control_dim if isinstance(obj, CostFunction) else obj.m
+
+
+def get_J(obj):   # get_J(obj)  src/objective.jl:110: the per-knot cost scratch of an objective (filled by cost_knots for instance 0)
+    return obj.J
 
 
 def get_initial_time(prob):   # src/problem.jl:189
@@ -1212,6 +1218,7 @@ def cost(prob):   # cost(prob)  src/problem.jl:321 -> [B]
 def cost_knots(prob):   # cost!(obj, Z); get_J(obj)  src/objective.jl:104-110 -> [B, N]
     Jk = np.empty((prob.B, prob.N))
     prob._call("to_cost_knots", K._dp(Jk))
+    prob.obj.J[:] = Jk[0]                      # the reference's shared scratch obj.J (one instance): instance 0 of the batch
     return Jk
 
 

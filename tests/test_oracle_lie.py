@@ -337,3 +337,30 @@ def test_error_quadratic_cost():
     for _ in range(15):
         TO.ilqr_step(p2, 1)
     assert np.all(TO.merit(p2) < 0.2 * J0)
+
+
+def test_constraint_error_jacobians_follow_the_reference_hook():
+    """error_expansion!(jac, jac0, con, model, G, inds) (src/abstract_constraint.jl:282-303; usage in the stale test/internal_api.jl:74-78,
+    :120-126): state block = jac0_x G_k, control block copied; G from RD.errstate_jacobian!.  Consistency: the error-state AL expansion
+    built by the solver path equals G' (cost + AL) G assembled from these Jacobians for an equality constraint."""
+    prob = quat_problem(B=2, N=6)
+    TO.rollout(prob)
+    G = TO.errstate_jacobian(prob)
+    assert G.shape == (2, 6, 13, 12)
+    X = TO.states(prob)
+    for b, k in ((0, 0), (1, 4)):
+        q = X[b, k, 3:7]
+        Lq = np.array([[q[0], -q[1], -q[2], -q[3]], [q[1], q[0], -q[3], q[2]], [q[2], q[3], q[0], -q[1]], [q[3], -q[2], q[1], q[0]]])
+        assert np.allclose(G[b, k, 3:7, 3:6], Lq[:, 1:]) and np.allclose(G[b, k, :3, :3], np.eye(3)) and np.allclose(G[b, k, 7:, 6:], np.eye(6))
+        # derivative of the retraction: d/dd (x (+) d) at 0
+        Jfd = _fd_jac(lambda e: oplus(X[b, k], e), 12)
+        assert np.allclose(G[b, k], Jfd, atol=1e-8)
+    for i, con in enumerate(prob.constraints):
+        J0, Je = TO.constraint_jacobians(prob, i), TO.constraint_error_jacobians(prob, i)
+        first, last = prob.constraints.inds[i]
+        assert Je.shape == J0.shape[:-1] + (16,)
+        assert np.allclose(Je[..., :12], J0[..., :13] @ G[:, first - 1:last]) and np.array_equal(Je[..., 12:], J0[..., 13:])
+    # QuatVecEq at the terminal knot: its error-state Jacobian is (close to) the identity on the attitude error when q ~ qf
+    cp = P.cartpole(B=1, N=4, cls=OracleProblem, goal=True)
+    TO.rollout(cp)
+    assert np.array_equal(TO.constraint_error_jacobians(cp, 0), TO.constraint_jacobians(cp, 0))       # no Lie group: unchanged

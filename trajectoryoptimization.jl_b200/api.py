@@ -4,7 +4,8 @@ Same names, argument meaning and error behaviour as the reference's Julia functi
 user -- or a parity test -- reads like the reference's own code (examples/quickstart.jl).  A ``Problem`` here
 is a BATCH of ``B`` independent instances that share model / objective / constraints and differ in ``x0``,
 states, controls and multipliers; every numerical call goes through the C ABI (``_capi``) to the sm_100a
-kernels.  Nothing in this file computes on the host.
+kernels.  Nothing in this file computes on the host, except two small pieces of glue that post-process device
+results with numpy and say so (``errstate_jacobian``, ``constraint_error_jacobians``).
 
 Array conventions: numpy row-major with the batch first -- ``X[B, N, n]``, ``U[B, N-1, m]`` -- which is the
 same memory as Julia's ``Array{Float64,3}(n, N, B)``.  Knot indices given to ``add_constraint`` are 1-based
@@ -1356,6 +1357,38 @@ def error_expansion(prob):
     H = np.empty((prob.B, prob.N, nm, nm))
     prob._call("to_error_expansion", K._dp(g), K._dp(H))
     return g, np.swapaxes(H, -1, -2)
+
+
+def errstate_jacobian(prob):
+    """``RD.errstate_jacobian!(model, G, z)`` of every knot of the current trajectory -> ``G[B, N, n, n_e]`` (identity blocks around the
+    4 x 3 attitude block ``L(q) H``; plain identity without a Lie-group state).  Host-side glue over ``states(prob)``."""
+    X = states(prob)
+    n, ne = prob.n, prob.ne
+    G = np.zeros((prob.B, prob.N, n, ne))
+    if ne == n:
+        G[..., np.arange(n), np.arange(n)] = 1.0
+        return G
+    qs = 3
+    for i in range(qs): G[..., i, i] = 1.0
+    for i in range(qs + 4, n): G[..., i, i - 1] = 1.0
+    w, x, y, z = (X[..., qs + i] for i in range(4))
+    cols = ((-x, w, z, -y), (-y, -z, w, x), (-z, y, -x, w))          # columns of L(q) H (Rotations.jl grad-differential)
+    for c, col in enumerate(cols):
+        for r_, v in enumerate(col):
+            G[..., qs + r_, qs + c] = v
+    return G
+
+
+def constraint_error_jacobians(prob, con):
+    """``error_expansion!(jac, jac0, con, model, G, inds)`` (src/abstract_constraint.jl:282-303): the constraint Jacobians in the error
+    state, ``[jac0_x G_k | jac0_u]`` -> ``[B, len(inds), p, n_e+m]``.  (The reference method only fills the state block of
+    ``StateConstraint``s and the control block of ``ControlConstraint``s and leaves general stage constraints untouched; the full
+    projection is what a solver needs and what the solver kernels use.)  Host-side glue over the device Jacobians."""
+    i = _con_index(prob, con)
+    first, last = prob.constraints.inds[i]
+    J0 = constraint_jacobians(prob, i)
+    G = errstate_jacobian(prob)[:, first - 1:last]
+    return np.concatenate([J0[..., :prob.n] @ G, J0[..., prob.n:]], axis=-1)
 
 
 def multipliers(prob, con):

@@ -27,7 +27,8 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 WORKLOADS = {
-    "quadrotor": dict(n=13, m=4, N=101, batch=4096, desc="Quadrotor point-to-point n=13 m=4 N=101, u in [0,10] + goal (AL-iLQR)"),
+    "quadrotor": dict(n=13, m=4, N=101, batch=4096, desc="Quadrotor point-to-point n=13 m=4 N=101, u in [0,10] + goal (AL-iLQR), Riccati on the Lie-group error state n_e=12 (what Altro does for this model)"),
+    "quadrotor_fullstate": dict(n=13, m=4, N=101, batch=4096, desc="Quadrotor point-to-point n=13 m=4 N=101, u in [0,10] + goal (AL-iLQR), Riccati on the full 13-state (round-1 headline)"),
     "cartpole": dict(n=4, m=1, N=101, batch=1024, desc="Cartpole swing-up n=4 m=1 N=101, unconstrained LQR cost"),
     "acrobot": dict(n=4, m=1, N=201, batch=8192, desc="Acrobot n=4 m=1 N=201, dense second-order cost + |u|<=15 + goal (AL)"),
     "quadrotor_lie": dict(n=13, m=4, N=101, batch=4096, desc="Quadrotor n=13 m=4 N=101 on the Lie-group error state (n_e=12), LQR cost, u in [0,10] + goal; materialised expansion (lie.cu)"),
@@ -38,6 +39,8 @@ def build_problem(workload, B, N, cls=None, device=0):
     import trajopt_b200 as TO
     P = TO.problems
     if workload == "quadrotor":
+        return P.quadrotor(B=B, N=N, cls=cls, device=device, error_state=True)
+    if workload == "quadrotor_fullstate":
         return P.quadrotor(B=B, N=N, cls=cls, device=device)
     if workload == "cartpole":
         return P.cartpole(B=B, N=N, cls=cls, device=device)
@@ -95,58 +98,84 @@ def host_cpu_quota():
     return n
 
 
-def cpu_oracle_rate(workload, N, threads=None, target_seconds=4.0, batch_cap=4096):
-    """iLQR instance-iterations/s of the CPU oracle port on a bounded sample of the workload, with the thread count
-    (quota, 2x, 4x the CPU quota) that gives the highest throughput on this host."""
+def cpu_arm(workload, B, N, warmup, steps, budget_s=None):
+    """The CPU arm: the oracle port of the same path on the host cores, on the SAME workload as the GPU arm -- the same B instances
+    from the same initial state, `warmup` untimed iLQR iterations followed by `steps` timed ones of the same solve (one step = one
+    iLQR iteration of every instance).  The warm-up iterations double as the thread-count probe (1x / 2x / 4x the CPU quota, best
+    kept).  `budget_s` (cpu_baseline leg of the GPU arm): cap the timed steps so the leg stays near that many seconds -- the steps
+    actually run are reported."""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import oracle_binding as OB
     import trajopt_b200 as TO
     lib = OB.load_oracle()
     lib.orc_set_threads.restype = C.c_int
     quota = host_cpu_quota()
-    B = min(batch_cap, max(256, 8 * quota))
+    ncpu = os.cpu_count() or quota
     prob = build_problem(workload, B, N, cls=OB.OracleProblem)
     TO.rollout(prob)
-    TO.ilqr_step(prob, 1)                       # warm-up (page in, first-touch)
+    cands = sorted({quota, min(2 * quota, ncpu), min(4 * quota, ncpu)})
     best = None
-    for thr in ([threads] if threads else sorted({quota, min(2 * quota, os.cpu_count() or quota), min(4 * quota, os.cpu_count() or quota)})):
+    warmup = max(warmup, 1)
+    for i in range(warmup):
+        thr = cands[i] if i < len(cands) else best[0]
         nthr = lib.orc_set_threads(int(thr))
         t0 = time.perf_counter(); TO.ilqr_step(prob, 1); t1 = time.perf_counter() - t0
         if best is None or t1 < best[1]:
             best = (nthr, t1)
     nthr = lib.orc_set_threads(best[0])
-    iters = max(1, min(400, int(target_seconds / max(best[1], 1e-6))))
-    t0 = time.perf_counter(); TO.ilqr_step(prob, iters); dt = time.perf_counter() - t0
+    if budget_s is not None:
+        steps = max(1, min(steps, int(budget_s / max(best[1], 1e-6))))
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        TO.ilqr_step(prob, 1)
+    wall = time.perf_counter() - t0
     prob.close()
-    return {"value": B * iters / dt, "unit": "instance-iterations/s", "cores": nthr, "kind": "port",
-            "sample": f"{B} instances x {iters} iLQR iterations of the same workload ({dt:.2f} s wall; {nthr} OpenMP threads = best of 1x/2x/4x "
-                      f"the host's {quota}-CPU quota; g++ -O3 x86-64-v3)"}, B * iters, dt
+    return {"value": B * steps / wall, "unit": "instance-iterations/s", "cores": nthr, "kind": "port",
+            "sample": f"{B} instances x {steps} iLQR iterations after {warmup} warm-up iterations of the same solve as the GPU arm ({wall:.2f} s wall; "
+                      f"{nthr} OpenMP threads = best of 1x/2x/4x the host's {quota}-CPU quota, {ncpu} logical CPUs; g++ -O3 x86-64-v3)",
+            "steps": steps, "ms_per_step": 1e3 * wall / steps, "wall_s": wall, "host_cpu_quota": quota, "nproc": ncpu}
 
 
 def run_reference(args, rank, world):
-    """--impl reference: the reference's CPU implementation of the path.  The Julia package cannot run in this image
-    (no Julia, and its RK4 / AD / Riccati live in un-vendored packages), so the arm times the oracle port -- the
-    documented CPU restatement -- on all host threads.  Rank 0 only."""
+    """--impl reference: the reference's CPU implementation of the path.  The Julia package cannot run in this image (no Julia, and
+    its RK4 / AD / Riccati live in un-vendored packages), so the arm times the oracle port -- the documented CPU restatement -- on
+    all host threads, on the GPU arm's own configuration: the global batch (batch per GPU x world, or the fixed global batch of
+    --scaling strong), the same initial state, `warmup` + `steps` iterations of one solve.  Rank 0 only."""
     if rank != 0:
         return
     w = WORKLOADS[args.workload]
     N = args.N or w["N"]
-    total, wall = 0, 0.0
-    cpu_oracle_rate(args.workload, N, target_seconds=1.0)     # warm-up
-    base = None
-    for _ in range(args.steps if args.steps <= 5 else 5):
-        base, n_it, dt = cpu_oracle_rate(args.workload, N, target_seconds=3.0)
-        total += n_it; wall += dt
-    value = total / wall
-    base["value"] = value
-    out = {"impl": "reference", "metric": "ilqr_iterations_per_sec", "value": value, "unit": "instance-iterations/s", "n_gpus": args.gpus,
-           "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * wall / max(1, min(args.steps, 5)), "higher_is_better": True,
-           "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-           "config": {"workload": w["desc"], "batch_per_gpu": args.batch or w["batch"], "N": N,
-                      "note": "CPU arm: oracle port of the reference path (Julia unavailable), bounded sample per step"},
-           "cpu_baseline": base, "e2e": {"value": value, "unit": "instance-iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-           "gpu_launches": 0}
+    per_gpu, glob = batch_split(args, w, world)
+    warmup = max(args.warmup, 3)
+    base = cpu_arm(args.workload, glob, N, warmup, args.steps)
+    out = {"impl": "reference", "metric": "ilqr_iterations_per_sec", "value": base["value"], "unit": "instance-iterations/s", "n_gpus": args.gpus,
+           "steps": base["steps"], "warmup": warmup, "ms_per_step": base["ms_per_step"], "higher_is_better": True,
+           "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+           "config": make_config(args, w, per_gpu, N, world),
+           "details": {"note": "CPU arm: oracle port of the reference path (Julia unavailable) on the whole global batch, same initial state, warm-up and step count as the GPU arm"},
+           "cpu_baseline": {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")},
+           "e2e": {"value": base["value"], "unit": "instance-iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "gpu_launches": 0, "host": {"cpu_quota": base["host_cpu_quota"], "nproc": base["nproc"], "threads": base["cores"]}}
     print(json.dumps(out), flush=True)
+
+
+def make_config(args, w, per_gpu, N, world):
+    """the `config` object of the JSON line -- identical for the GPU arm and the CPU (--impl reference) arm"""
+    n_r, nm_r = (w["n"] - 1, w["n"] + w["m"] - 1) if args.workload in ("quadrotor", "quadrotor_lie") else (w["n"], w["n"] + w["m"])
+    return {"workload": w["desc"], "batch_per_gpu": per_gpu, "N": N, "global_batch": per_gpu * world, "parallelism": f"batch-sharded x{world}",
+            "step": "1 iLQR iteration = dynamics expansion + Riccati backward pass + forward pass/line search of every instance, K consecutive iterations of one solve",
+            "merit_collective_every": (args.merit_every if world > 1 else None),
+            "l2": "inputs larger than L2 (126 MB): the per-knot dynamics Jacobians alone are %.0f MB per GPU, rewritten and re-read every step"
+                  % (per_gpu * (N - 1) * n_r * nm_r * 8 / 1e6)}
+
+
+def batch_split(args, w, world):
+    """(instances per GPU, global batch): weak scaling keeps the per-GPU batch, strong scaling the global one"""
+    if args.scaling == "strong":
+        glob = args.batch or w["batch"]
+        return max(1, glob // world), max(1, glob // world) * world
+    per = args.batch or w["batch"]
+    return per, per * world
 
 
 def main():
@@ -158,6 +187,8 @@ def main():
     ap.add_argument("--workload", default="quadrotor", choices=sorted(WORKLOADS))
     ap.add_argument("--batch", type=int, default=0, help="instances per GPU (default: the workload's BASELINE batch)")
     ap.add_argument("--N", type=int, default=0, help="knot points (default: the workload's)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"], help="weak: --batch instances per GPU; strong: --batch instances in total, split over the GPUs")
+    ap.add_argument("--merit-every", type=int, default=5, help="N > 1: iterations between two {sum merit, max violation} collectives (a solver's convergence report)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -177,7 +208,8 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
     w = WORKLOADS[args.workload]
-    B, N = args.batch or w["batch"], args.N or w["N"]
+    B, global_batch = batch_split(args, w, world)
+    N = args.N or w["N"]
     n, m = w["n"], w["m"]
     prob = build_problem(args.workload, B, N, device=local)
     lib, h = prob._lib, prob._h
@@ -199,17 +231,20 @@ def main():
         K.check(lib, h, lib.to_rollout(h))
 
     side = torch.cuda.Stream() if world > 1 else None
+    gather = torch.empty((world, 2), dtype=torch.float64, device=f"cuda:{local}") if world > 1 else None
+    step_no = [0]
 
     def step():
         K.check(lib, h, lib.to_ilqr_step(h, 1))
-        if world > 1:
-            # the path's only collective: {sum merit, max violation} SUM/MAX all-reduce.  Nothing on the device
-            # consumes it, so it runs on a side stream and overlaps the next iteration's kernels.
-            stream.wait_stream(side)                                     # previous all-reduce has released the buffer
-            # per-GPU {sum J, max viol} (one small kernel) queued behind the iteration's last kernel; `side` waits on its event
+        step_no[0] += 1
+        if world > 1 and step_no[0] % max(1, args.merit_every) == 0:
+            # the path's only collective: {sum merit, max violation} over the ranks -- ONE all-gather of the 2-vectors every
+            # `merit_every` iterations.  Nothing on the device consumes it, so it runs on a side stream behind the per-GPU reduction
+            # kernel (to_reduce_merit_async queues that behind the iteration's last kernel and makes `side` wait on its event); the
+            # main stream never waits for the collective: the previous one has long finished when the buffer is reduced again.
             K.check(lib, h, lib.to_reduce_merit_async(h, C.c_void_p(side.cuda_stream)))
             with torch.cuda.stream(side):
-                TO.multi_gpu.all_reduce_merit(merit2)
+                TO.multi_gpu.all_reduce_merit(merit2, scratch=gather)
 
     def barrier():
         if world > 1:
@@ -231,7 +266,11 @@ def main():
     for _ in range(args.steps):
         step()
     if side is not None:
-        stream.wait_stream(side)      # the last all-reduce is inside the timed region
+        if args.steps % max(1, args.merit_every) != 0:   # the final merit report is part of the job
+            K.check(lib, h, lib.to_reduce_merit_async(h, C.c_void_p(side.cuda_stream)))
+            with torch.cuda.stream(side):
+                TO.multi_gpu.all_reduce_merit(merit2, scratch=gather)
+        stream.wait_stream(side)      # the last collective is inside the timed region
     e1.record(stream)
     barrier()
     ms = e0.elapsed_time(e1)
@@ -256,7 +295,7 @@ def main():
         K.check(lib, h, lib.to_ilqr_step(h, 1))
     lib.to_get_phase_times(h, pms, pl, 1)
     lib.to_set_phase_timing(h, 0)
-    phase = {name: (pms[i] / max(1, pl[i])) for name, i in (("expand", K.PHASE_EXPAND), ("backward", K.PHASE_BACKWARD), ("forward", K.PHASE_FORWARD), ("ladder", K.PHASE_LADDER))}
+    phase = {name: (pms[i] / max(1, pl[i])) for name, i in (("expand", K.PHASE_EXPAND), ("cost_expansion", K.PHASE_COSTEXP), ("backward", K.PHASE_BACKWARD), ("forward", K.PHASE_FORWARD), ("ladder", K.PHASE_LADDER))}
     E, R, F = C.c_int64(), C.c_int64(), C.c_int64()
     lib.to_algorithmic_bytes(h, C.byref(E), C.byref(R), C.byref(F))
     peaks = {}
@@ -273,7 +312,9 @@ def main():
         traffic = json.load(open(os.path.join(ROOT, "profiles", "riccati_traffic.json"))).get(f"{args.workload}_B{B}_N{N}")
     except Exception:
         pass
-    rk = "k_expansion_compact + k_riccati_dense_mma (lie.cu: error-state expansion + tensor-core Riccati pass)" if args.workload == "quadrotor_lie" \
+    frag = args.workload in ("quadrotor", "quadrotor_lie") and not os.environ.get("TO_NO_FRAG")
+    rk = "k_riccati_frag (riccati_frag.cu: register-resident tensor-core Riccati pass on the error state, timed alone)" if frag \
+        else "k_expansion_compact + k_riccati_dense_mma (lie.cu: error-state expansion + shared-memory tensor-core Riccati pass)" if args.workload in ("quadrotor", "quadrotor_lie") \
         else "k_riccati (Riccati backward pass)"
     roofline = {"kernel": rk, "bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
                 "frac": achieved / peak_gbs, "traffic": traffic, "peak_source": peak_src,
@@ -281,6 +322,8 @@ def main():
                 "phase_ms": phase, "fp64_tflops_riccati": None}
     # FP64 view of the same kernel: 2 * (T + Qzz + Qz + S-update + solves) FMA per knot, counted analytically
     nm = n + m
+    if args.workload in ("quadrotor", "quadrotor_lie"):
+        n, nm = n - 1, nm - 1        # the recursion runs on the error state
     fma_knot = n * n * nm + n * nm * (nm + 1) // 2 + n * nm + m * n * (n + 1) // 2 + m * m * (n + 1) + m * m * m // 3
     roofline["fp64_tflops_riccati"] = (2.0 * fma_knot * (N - 1) * B / (r_ms * 1e-3)) / 1e12 if r_ms > 0 else None
 
@@ -318,18 +361,17 @@ def main():
     cpu = None
     if rank == 0 and not args.no_cpu_baseline:
         try:
-            cpu, _, _ = cpu_oracle_rate(args.workload, N)
+            cpu = cpu_arm(args.workload, B, N, max(args.warmup, 3), args.steps, budget_s=12.0)
+            cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
         except Exception as ex:   # the oracle is only the reported baseline; never let it take the GPU number down
             cpu = {"value": None, "unit": "instance-iterations/s", "cores": 0, "kind": "port", "sample": f"failed: {ex}"}
 
     if rank == 0:
         out = {"metric": "ilqr_iterations_per_sec", "value": value, "unit": "instance-iterations/s", "n_gpus": world, "steps": args.steps,
-               "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+               "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
                "dtype": "f64", "data": "synthetic",
-               "config": {"workload": w["desc"], "batch_per_gpu": B, "N": N, "global_batch": B * world, "parallelism": f"batch-sharded x{world}",
-                          "step": "1 iLQR iteration = dynamics expansion + Riccati backward pass + forward pass/line search",
-                          "l2": "inputs larger than L2: [A B] alone is %.0f MB per GPU, rewritten and re-read every step" % (B * (N - 1) * n * (nm + nm % 2) * 8 / 1e6),
-                          "batch_iterations_per_s": args.steps / (ms * 1e-3), "accepted_fraction_last_step": accepted_frac},
+               "config": make_config(args, w, B, N, world),
+               "details": {"batch_iterations_per_s": args.steps / (ms * 1e-3), "accepted_fraction_last_step": accepted_frac},
                "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu}
         print(json.dumps(out), flush=True)
     prob.close()

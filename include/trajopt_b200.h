@@ -140,7 +140,10 @@ typedef struct {
     double line_search_lower_bound, line_search_upper_bound;
     int32_t iterations_linesearch;
     int32_t backward_kernel;   /* 0 = automatic; 1 = warp-per-instance Riccati kernel; 2 = thread-per-instance kernel (n <= 4, m <= 2,
-                                  Goal/Bound constraints only, else ignored). Not a solver option of the reference: a tuning / test knob. */
+                                  Goal/Bound constraints only, else ignored); error-state problems: 3 = generic DFMA kernel on the full
+                                  materialised expansion, 5 = shared-memory tensor kernel on the compact expansion (automatic = the
+                                  register-resident fragment kernel when the problem is compact). Not a solver option of the reference:
+                                  a tuning / test knob. */
     double max_state_value, max_control_value;
     double penalty_initial, penalty_scaling, penalty_max, dual_max;
 } to_options;
@@ -232,7 +235,7 @@ int to_reduce_merit(to_handle* h);
 int to_reduce_merit_async(to_handle* h, void* consumer_stream);
 int to_merit_device_ptr(to_handle* h, void** ptr);
 /* per-phase device timing (CUDA events on the handle's stream) for the roofline report */
-enum to_phase { TO_PHASE_EXPAND = 0, TO_PHASE_BACKWARD = 1, TO_PHASE_FORWARD = 2, TO_PHASE_LADDER = 3, TO_PHASE_ACCEPT = 4, TO_PHASE_COUNT = 8 };
+enum to_phase { TO_PHASE_EXPAND = 0, TO_PHASE_BACKWARD = 1, TO_PHASE_FORWARD = 2, TO_PHASE_LADDER = 3, TO_PHASE_ACCEPT = 4, TO_PHASE_COSTEXP = 5 /* cost + AL expansion kernel of the record / materialised-expansion paths, when it is a launch of its own */, TO_PHASE_COUNT = 8 };
 int to_set_phase_timing(to_handle* h, int enable);
 int to_get_phase_times(to_handle* h, double* ms /*[TO_PHASE_COUNT] accumulated*/, int64_t* launches /*[TO_PHASE_COUNT]*/, int reset);
 int64_t to_launch_count(const to_handle* h);                                  /* kernels launched by this handle so far */

@@ -60,6 +60,8 @@ struct ModelParams {
     int id = MODEL_CARTPOLE;
     int n = 4, m = 1;
     double p[16] = {0};
+    int integrator = 4;   // 4 = RK4 (the reference's default, src/problem.jl:119-123), 3 = RK3 (oracle only: the default of the
+                          // TrajectoryOptimization v0.3 / Altro 0.3 versions that produced the recorded outputs of examples/*.ipynb)
 };
 
 inline ModelParams default_model(int id, int dim = 1) {
@@ -188,8 +190,23 @@ constexpr int MAXM = 8;
 // RobotDynamics.jl RK4 (zero-order hold on u), restated:
 //   k1 = f(x,u) h; k2 = f(x + k1/2,u) h; k3 = f(x + k2/2,u) h; k4 = f(x + k3,u) h;
 //   x+ = x + (k1 + 2 k2 + 2 k3 + k4)/6.       Sole call site: src/problem.jl:338.
+// RobotDynamics.jl RK3 (Kutta's third-order rule, zero-order hold): k1 = f(x,u) h; k2 = f(x + k1/2,u) h; k3 = f(x - k1 + 2 k2,u) h;
+//   x+ = x + (k1 + 4 k2 + k3)/6.  The integrator argument of the reference's Problem constructor (src/problem.jl:119-123) selects it.
+template <class S>
+inline void rk3_step(const ModelParams& mp, const S* x, const S* u, double h, S* xn) {
+    const int n = mp.n;
+    S k1[MAXN], k2[MAXN], k3[MAXN], xt[MAXN];
+    dynamics<S>(mp, x, u, k1);
+    for (int i = 0; i < n; i++) { k1[i] = k1[i] * h; xt[i] = x[i] + k1[i] * 0.5; }
+    dynamics<S>(mp, xt, u, k2);
+    for (int i = 0; i < n; i++) { k2[i] = k2[i] * h; xt[i] = x[i] - k1[i] + 2.0 * k2[i]; }
+    dynamics<S>(mp, xt, u, k3);
+    for (int i = 0; i < n; i++) { k3[i] = k3[i] * h; xn[i] = x[i] + (k1[i] + 4.0 * k2[i] + k3[i]) / 6.0; }
+}
+
 template <class S>
 inline void rk4_step(const ModelParams& mp, const S* x, const S* u, double h, S* xn) {
+    if (mp.integrator == 3) { rk3_step<S>(mp, x, u, h, xn); return; }
     const int n = mp.n;
     S k1[MAXN], k2[MAXN], k3[MAXN], k4[MAXN], xt[MAXN];
     dynamics<S>(mp, x, u, k1);

@@ -177,13 +177,14 @@ int orc_destroy(orc_handle* h) { delete h; return TO_OK; }
 
 int orc_set_options(orc_handle* h, const to_options* o) {
     Options& q = h->P.opts;
+    const bool reset_mu = q.penalty_initial != o->penalty_initial, reset_rho = q.bp_reg_initial != o->bp_reg_initial;   // as to_set_options
     q.bp_reg_increase_factor = o->bp_reg_increase_factor; q.bp_reg_max = o->bp_reg_max; q.bp_reg_min = o->bp_reg_min;
     q.bp_reg_initial = o->bp_reg_initial; q.bp_reg_fp = o->bp_reg_fp;
     q.line_search_lower_bound = o->line_search_lower_bound; q.line_search_upper_bound = o->line_search_upper_bound;
     q.iterations_linesearch = o->iterations_linesearch; q.max_state_value = o->max_state_value; q.max_control_value = o->max_control_value;
     q.penalty_initial = o->penalty_initial; q.penalty_scaling = o->penalty_scaling; q.penalty_max = o->penalty_max; q.dual_max = o->dual_max;
-    for (auto& mu : h->P.mu) mu = q.penalty_initial;
-    for (int b = 0; b < h->P.B; b++) { h->P.rho[b] = q.bp_reg_initial; h->P.drho[b] = 0; }
+    if (reset_mu) for (auto& mu : h->P.mu) mu = q.penalty_initial;
+    if (reset_rho) for (int b = 0; b < h->P.B; b++) { h->P.rho[b] = q.bp_reg_initial; h->P.drho[b] = 0; }
     h->P.J_valid = false;
     return TO_OK;
 }
@@ -194,6 +195,12 @@ int orc_default_options(to_options* o) {
     o->line_search_lower_bound = q.line_search_lower_bound; o->line_search_upper_bound = q.line_search_upper_bound;
     o->iterations_linesearch = q.iterations_linesearch; o->backward_kernel = 0; o->max_state_value = q.max_state_value; o->max_control_value = q.max_control_value;
     o->penalty_initial = q.penalty_initial; o->penalty_scaling = q.penalty_scaling; o->penalty_max = q.penalty_max; o->dual_max = q.dual_max;
+    return TO_OK;
+}
+// integrator of the discretised dynamics: 4 = RK4 (default), 3 = RK3 (oracle only; pins the oracle to the recorded notebook outputs)
+int orc_set_integrator(orc_handle* h, int order) {
+    if (order != 3 && order != 4) return TO_EINVAL;
+    h->P.model.integrator = order; h->P.J_valid = false;
     return TO_OK;
 }
 int orc_set_threads(int nthreads) { omp_set_num_threads(nthreads > 0 ? nthreads : omp_get_num_procs()); return omp_get_max_threads(); }

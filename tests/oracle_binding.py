@@ -45,7 +45,7 @@ class OracleProblem(TO.Problem):
             msg = self._lib.orc_last_error(None).decode()
             raise {K.TO_EDIM: TO.DimensionMismatch, K.TO_EINVAL: TO.ArgumentError}.get(rc, TO.TrajOptError)(msg)
 
-    def _call(self, name, *args):
+    def _raw_call(self, name, *args):
         fn = getattr(self._lib, "orc_" + name[3:])
         fn.restype = C.c_int
         conv = [C.c_double(a) if isinstance(a, float) else a for a in args]

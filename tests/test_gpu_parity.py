@@ -162,7 +162,8 @@ def test_error_state_kernels(name):
 def test_error_state_riccati_kernel_variants():
     """the three backward passes of the error-state path against the oracle: tensor-core kernel on the compact expansion (automatic choice
     for diagonal costs + Goal/Bound), tensor-core kernel on the full materialised expansion (QuatVecEq present), and the generic DFMA kernel"""
-    for name, kernel in (("quadrotor_lie_lqr", 0), ("quadrotor_lie_lqr", 3), ("quadrotor_lie", 0), ("quadrotor_lie", 3)):
+    # 0 on a compact problem = the register-resident fragment kernel (riccati_frag.cu); 5 = the shared-memory tensor kernel on the compact expansion
+    for name, kernel in (("quadrotor_lie_lqr", 0), ("quadrotor_lie_lqr", 5), ("quadrotor_lie_lqr", 3), ("quadrotor_lie", 0), ("quadrotor_lie", 3)):
         g, o = CONFIGS[name](TO.Problem), CONFIGS[name](OracleProblem)
         TO.set_options(g, backward_kernel=kernel)
         for p in (g, o):
@@ -171,6 +172,38 @@ def test_error_state_riccati_kernel_variants():
         Kg, dg = TO.gains(g); Ko, do = TO.gains(o)
         close(Kg, Ko, 1e-6, f"K {name} kernel {kernel}"); close(dg, do, 1e-6, f"d {name} kernel {kernel}")
         g.close(); o.close()
+
+
+def test_fragment_riccati_kernel_regularisation_and_queue():
+    """riccati_frag.cu: (a) restarts -- a negative-definite control cost makes Quu + rho I indefinite until rho has grown: same restart
+    counts, rho and gains as the oracle; (b) more instances than one wave of resident warps (148 SMs x 28) goes through the work queue"""
+    n, m, N = 13, 4, 21
+    xf = np.array([0, 0, 2, 1, 0, 0, 0, 0, 0, 0, 0, 0, 0.0])
+    probs = []
+    for cls in (TO.Problem, OracleProblem):
+        r = np.random.default_rng(4)
+        stage = TO.LQRCost(np.full(n, 0.1), np.full(m, -0.05), xf, TO.Quadrotor().hover_control())
+        term = TO.LQRCost(np.full(n, 10.0), np.full(m, -0.05), xf, TO.Quadrotor().hover_control(), terminal=True)
+        cons = TO.ConstraintList(n, m, N)
+        TO.add_constraint(cons, TO.BoundConstraint(n, m, u_min=np.zeros(4), u_max=np.full(4, 10.0)), (1, N - 1))
+        x0 = np.tile(np.array([1, 2, 1, 1, 0, 0, 0, 0, 0, 0, 0, 0, 0.0]), (6, 1)); x0[:, :3] += r.uniform(-1, 1, (6, 3))
+        p = cls(TO.Quadrotor(), TO.Objective(stage, term, N), x0, 1.0, xf=xf, constraints=cons, error_state=True)
+        TO.initial_controls(p, TO.Quadrotor().hover_control() + 0.05 * r.standard_normal((6, N - 1, m)))
+        TO.rollout(p); TO.expand(p)
+        probs.append(p)
+    g, o = probs
+    sg, so = TO.backward(g), TO.backward(o)
+    assert np.array_equal(sg, so) and np.all(so > 0), (sg, so)
+    close(TO.solver_state(g)["rho"], TO.solver_state(o)["rho"], 1e-12, "rho")
+    close(TO.gains(g)[0], TO.gains(o)[0], 1e-8, "K after restarts"); close(TO.gains(g)[1], TO.gains(o)[1], 1e-8, "d after restarts")
+    g.close(); o.close()
+    B = 148 * 28 + 300
+    g, o = P.quadrotor(B=B, N=11, dt=0.05, error_state=True), P.quadrotor(B=B, N=11, dt=0.05, error_state=True, cls=OracleProblem)
+    for p in (g, o):
+        TO.rollout(p); TO.expand(p)
+    assert np.array_equal(TO.backward(g), TO.backward(o))
+    close(TO.gains(g)[0], TO.gains(o)[0], 1e-9, "K (queue)"); close(TO.solver_state(g)["dV"], TO.solver_state(o)["dV"], 1e-9, "dV (queue)")
+    g.close(); o.close()
 
 
 def test_error_state_full_size_properties():

@@ -124,3 +124,35 @@ def test_two_rank_gloo_sharding_and_merit_allreduce(tmp_path):
     outs = [p.communicate(timeout=240)[0] for p in procs]
     for r, (p, o) in enumerate(zip(procs, outs)):
         assert p.returncode == 0 and f"rank {r} ok" in o, o
+
+
+def test_live_problem_follows_mutations_of_objective_and_constraint_list():
+    """the reference mutates a live problem in place -- set_LQR_goal!(prob.obj[k], xf), add_constraint!(get_constraints(prob), ...): the
+    device-side tables are re-uploaded before the next call, and output buffers are sized from the current list."""
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from oracle_binding import OracleProblem
+    import trajopt_b200 as TO
+    n, m, N = 4, 2, 11
+    xf = np.array([0, 2.0, 0, 0])
+    obj = TO.LQRObjective(np.eye(n), np.eye(m), np.eye(n) * 10, xf, N)
+    cons = TO.ConstraintList(n, m, N)
+    TO.add_constraint(cons, TO.GoalConstraint(xf), N)
+    prob = OracleProblem(TO.DoubleIntegrator(2), obj, np.zeros(n), 1.0, xf=xf, constraints=cons)
+    TO.initial_controls(prob, np.ones((1, N - 1, m))); TO.rollout(prob)
+    J0 = TO.cost(prob)[0]
+    xg = np.array([1.0, -1.0, 0, 0])
+    for k in range(N):
+        TO.set_LQR_goal(prob.obj[k], xg)
+    J1 = TO.cost(prob)[0]
+    ref = OracleProblem(TO.DoubleIntegrator(2), prob.obj.copy(), np.zeros(n), 1.0, xf=xf, constraints=cons.copy())
+    TO.initial_controls(ref, np.ones((1, N - 1, m))); TO.rollout(ref)
+    assert J1 != J0 and np.isclose(J1, TO.cost(ref)[0], rtol=1e-14)
+    np.testing.assert_array_equal(TO.states(prob), TO.states(ref))          # the trajectory survived the re-upload
+    bnd = TO.BoundConstraint(n, m, u_min=-0.5, u_max=0.5)
+    TO.add_constraint(TO.get_constraints(prob), bnd, (1, N - 1), idx=0)
+    vals = TO.evaluate_constraints(prob, 0)
+    assert vals.shape == (1, N - 1, 4) and np.allclose(vals[0, :, :2], 0.5) and np.allclose(vals[0, :, 2:], -1.5)
+    assert TO.evaluate_constraints(prob, 1).shape == (1, 1, n)
+    TO.set_options(prob, penalty_scaling=3.0); TO.set_options(prob, iterations_linesearch=7)
+    assert prob._options.penalty_scaling == 3.0 and prob._options.iterations_linesearch == 7      # earlier settings are kept
+    prob.close(); ref.close()

@@ -515,6 +515,7 @@ def set_LQR_goal(cost, xf, uf=None):   # set_LQR_goal!  src/cost_functions.jl:24
     cost.q = -cost.Q @ np.asarray(xf, dtype=float)
     if uf is not None:
         cost.r = -cost.R @ np.asarray(uf, dtype=float)
+    cost._version = getattr(cost, "_version", 0) + 1      # a live Problem holding this cost re-uploads its tables before the next device call
 
 
 def LQRCost(Q, R, xf, uf=None, **kw):   # src/cost_functions.jl:532-547
@@ -942,6 +943,7 @@ def add_constraint(cons, con, inds, idx=-1):
     cons.constraints.insert(pos, con)
     cons.inds.insert(pos, (int(first), int(last)))
     cons.p[first - 1:last] += con.p   # num_constraints!  src/constraint_list.jl:198-206
+    cons._version = getattr(cons, "_version", 0) + 1      # see Problem._ensure_current
 
 
 def num_constraints(cons_or_prob):
@@ -1008,6 +1010,7 @@ class Problem:
         self.spec = K.Spec(model.model_id, n, m, N, B, dtv, [c._spec() for c in uniq], index, con_specs,
                            params=model.params, t0=t0, device=device, error_state=self.error_state)
         self._open()
+        self._sig = self._signature()
         self._call("to_set_initial_state", K._dp(self.x0))
         if U0 is not None:
             initial_controls(self, U0)
@@ -1021,7 +1024,47 @@ class Problem:
         rc = self._lib.to_create(C.byref(self.spec.c), C.byref(self._h))
         K.check(self._lib, None, rc)
 
+    def _signature(self):
+        """what the device-side tables were built from: the cost object of every knot, the constraint list, and the version counters the
+        mutating helpers of the reference API bump (set_LQR_goal!(prob.obj[k], ...), add_constraint!(get_constraints(prob), ...))"""
+        cons = self.constraints
+        return (tuple(id(c) for c in self.obj.cost), tuple(getattr(c, "_version", 0) for c in self._cost_objs),
+                tuple(id(c) for c in cons.constraints), tuple(cons.inds), getattr(cons, "_version", 0))
+
+    def _ensure_current(self):
+        """The reference mutates a live problem's objective / constraint list in place.  The device tables are a copy taken at
+        construction, so a change is re-uploaded here, before the next device call: the handle is rebuilt from the current host
+        description with the live trajectory, initial state and solver options carried over (multipliers and penalties restart,
+        as they must when the constraint list changes shape)."""
+        if getattr(self, "_sig", None) is None or self._sig == self._signature():
+            return
+        X, U = np.empty((self.B, self.N, self.n)), np.empty((self.B, self.N - 1, self.m))
+        self._raw_call("to_get_states", K._dp(X)); self._raw_call("to_get_controls", K._dp(U))
+        t = np.empty(self.N)
+        self._raw_call("to_get_times", K._dp(t))
+        opts = getattr(self, "_options", None)
+        uniq, index = self.obj._tables()
+        self._cost_objs = uniq
+        cons = self.constraints
+        con_specs = [c._spec(f, l) for (f, l), c in zip(cons.inds, cons.constraints)]
+        old = self.spec
+        self.close()
+        self.spec = K.Spec(self.model.model_id, self.n, self.m, self.N, self.B, np.diff(t), [c._spec() for c in uniq], index, con_specs,
+                           params=self.model.params, t0=float(t[0]), device=old.device, error_state=self.error_state)
+        self._open()
+        self._sig = self._signature()
+        self._raw_call("to_set_initial_state", K._dp(self.x0))
+        self._raw_call("to_set_controls", K._dp(U))
+        if np.all(np.isfinite(X)):
+            self._raw_call("to_set_states", K._dp(X))
+        if opts is not None:
+            self._raw_call("to_set_options", C.byref(opts))
+
     def _call(self, name, *args):
+        self._ensure_current()
+        self._raw_call(name, *args)
+
+    def _raw_call(self, name, *args):
         rc = getattr(self._lib, name)(self._h, *args)
         K.check(self._lib, self._h, rc)
 
@@ -1425,10 +1468,14 @@ def solver_state(prob):
 
 
 def set_options(prob, **kw):
-    o = K.to_options()
-    prob._default_options(o)
+    """update the given solver options; options set by earlier calls are kept (the C entry point takes the complete struct)"""
+    o = getattr(prob, "_options", None)
+    if o is None:
+        o = K.to_options()
+        prob._default_options(o)
     for k, v in kw.items():
         if not hasattr(o, k):
             raise ArgumentError(f"unknown solver option {k}")
         setattr(o, k, v)
+    prob._options = o
     prob._call("to_set_options", C.byref(o))

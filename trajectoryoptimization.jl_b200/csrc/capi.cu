@@ -8,6 +8,7 @@
 #include <vector>
 
 #include "../../include/trajopt_b200.h"
+#include "frag_layout.cuh"
 #include "kernels.h"
 
 namespace {
@@ -290,7 +291,8 @@ int build_con(to_handle* h, const to_constraint_spec& tc, int n, int m, int N, D
             break;
         default: return fail(h, TO_EINVAL, "unknown constraint kind");
     }
-    if (c.p > TO_MAXP) return fail(h, TO_EINVAL, "constraint output dimension exceeds TO_MAXP");
+    if (c.p > (c.diagonal ? TO_MAXPV : TO_MAXP))
+        return fail(h, TO_EINVAL, "constraint output dimension exceeds the library limit (32 rows per knot; 2 (n + m) for Goal / Bound constraints)");
     return TO_OK;
 }
 
@@ -300,6 +302,17 @@ extern "C" {
 
 const char* to_last_error(const to_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
 
+// Every entry point makes the handle's device current for its duration and restores the caller's afterwards: one process may hold
+// handles on several GPUs (to_spec.device), and the host application (torch, Julia's CUDA.jl) has its own idea of the current device.
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(const to_handle* h) {
+        if (!h) return;
+        int cur = -1;
+        if (cudaGetDevice(&cur) == cudaSuccess && cur != h->device) { prev = cur; cudaSetDevice(h->device); }
+    }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
 // Every entry point that touches trajectory data on the main stream first joins the side stream (see to_ilqr_step).
 static int join_side(to_handle* h) {
     if (h && h->side_pending) {
@@ -308,7 +321,7 @@ static int join_side(to_handle* h) {
     }
     return TO_OK;
 }
-#define JOIN(h) do { int jrc_ = join_side(h); if (jrc_) return jrc_; } while (0)
+#define JOIN(h) DeviceGuard device_guard__(h); do { int jrc_ = join_side(h); if (jrc_) return jrc_; } while (0)
 
 int to_default_options(to_options* o) {
     if (!o) return TO_EINVAL;
@@ -349,6 +362,7 @@ int to_create(const to_spec* s, to_handle** out) {
 
     auto* h = new to_handle();
     h->device = s->device;
+    DeviceGuard device_guard(h);        // the caller's current device is restored when to_create returns
     auto bail = [&](int code) { std::string msg = h->err; to_destroy(h); g_create_error = msg; return code; };
     if (cudaSetDevice(s->device) != cudaSuccess) { h->err = "cudaSetDevice failed"; return bail(TO_ECUDA); }
     if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { h->err = "cudaStreamCreate failed"; return bail(TO_ECUDA); }
@@ -389,6 +403,10 @@ int to_create(const to_spec* s, to_handle** out) {
         bool diag_cons = true;
         for (int i = 0; i < s->ncon; i++) if (s->cons[i].kind != TO_CON_GOAL && s->cons[i].kind != TO_CON_BOUND) diag_cons = false;
         P.compact = (P.lie && diag_costs && diag_cons && P.ne == 12 && m == 4) ? 1 : 0;
+        // compact problems: [A_e B_e] + expansion as per-knot records for the register-resident Riccati kernel (riccati_frag.cu);
+        // TO_NO_FRAG=1 keeps the shared-memory kernel of lie.cu (A/B timing)
+        const char* nf = getenv("TO_NO_FRAG");
+        P.frag = (P.compact && !(nf && atoi(nf) != 0)) ? 1 : 0;
     }
     if (P.dense_riccati && !P.compact) h->overlap = false;   // generic lie.cu path: every kernel on the main stream
     h->h_cost_index.assign(s->cost_index, s->cost_index + N);
@@ -432,6 +450,7 @@ int to_create(const to_spec* s, to_handle** out) {
         const size_t nme = P.ne + m;
         ALLOC(P.ABe, (size_t)B * (N - 1) * P.ne * nme); ALLOC(P.EG, (size_t)B * N * nme); ALLOC(P.EH, (size_t)B * N * nme * nme);
         if (P.compact) ALLOC(P.EC, (size_t)B * N * TO_EC_LEN);
+        if (P.frag) ALLOC(P.REC, (size_t)B * N * TO_REC_LEN);
     }
     ALLOC(P.lambda, (size_t)B * std::max(1, P.lambda_len));
     ALLOC(P.rho, B); ALLOC(P.drho, B); ALLOC(P.dV, 2 * (size_t)B); ALLOC(P.J, B); ALLOC(P.Jc, B); ALLOC(P.alpha, B);
@@ -473,7 +492,7 @@ int to_create(const to_spec* s, to_handle** out) {
 
 int to_destroy(to_handle* h) {
     if (!h) return TO_OK;
-    cudaSetDevice(h->device);
+    DeviceGuard device_guard(h);
     if (h->stream) cudaStreamSynchronize(h->stream);
     for (void* p : h->allocs) cudaFree(p);
     if (h->scratch.ptr) cudaFree(h->scratch.ptr);
@@ -495,16 +514,22 @@ int to_set_options(to_handle* h, const to_options* o) {
     if (o->iterations_linesearch < 0 || o->iterations_linesearch > 15) return fail(h, TO_EINVAL, "iterations_linesearch must be in 0..15");
     if (!(o->penalty_initial > 0) || !(o->penalty_scaling > 0)) return fail(h, TO_EINVAL, "penalties must be positive");
     DevOptions& d = h->P.opt;
+    // the AL penalties and the regularisation state restart only when THEIR initial values change: setting an unrelated option in the
+    // middle of a solve must not discard the penalty schedule
+    const bool reset_mu = d.penalty_initial != o->penalty_initial, reset_rho = d.bp_reg_initial != o->bp_reg_initial;
     d.bp_reg_increase_factor = o->bp_reg_increase_factor; d.bp_reg_max = o->bp_reg_max; d.bp_reg_min = o->bp_reg_min;
     d.bp_reg_initial = o->bp_reg_initial; d.bp_reg_fp = o->bp_reg_fp;
     d.ls_lower = o->line_search_lower_bound; d.ls_upper = o->line_search_upper_bound; d.ls_iters = o->iterations_linesearch;
     d.pad = o->backward_kernel;   // kernel choice of launch_backward (0 automatic)
     d.max_state_value = o->max_state_value; d.max_control_value = o->max_control_value;
     d.penalty_initial = o->penalty_initial; d.penalty_scaling = o->penalty_scaling; d.penalty_max = o->penalty_max; d.dual_max = o->dual_max;
-    for (auto& mu : h->h_mu) mu = d.penalty_initial;
-    std::vector<double> r(h->P.B, d.bp_reg_initial);
-    CU(h, cudaMemcpyAsync(h->P.rho, r.data(), sizeof(double) * h->P.B, cudaMemcpyHostToDevice, h->stream));
-    CU(h, cudaMemsetAsync(h->P.drho, 0, sizeof(double) * h->P.B, h->stream));
+    if (reset_mu) for (auto& mu : h->h_mu) mu = d.penalty_initial;
+    if (reset_rho) {
+        std::vector<double> r(h->P.B, d.bp_reg_initial);
+        CU(h, cudaMemcpyAsync(h->P.rho, r.data(), sizeof(double) * h->P.B, cudaMemcpyHostToDevice, h->stream));
+        CU(h, cudaMemsetAsync(h->P.drho, 0, sizeof(double) * h->P.B, h->stream));
+        CU(h, cudaStreamSynchronize(h->stream));     // `r` goes out of scope
+    }
     h->J_valid = false;
     return upload_tables(h);
 }
@@ -774,6 +799,7 @@ int to_max_violation(to_handle* h, double* v) {
 }
 
 static int cone_call(to_handle* h, int32_t cone, int32_t p, int32_t count, const double* x, const double* b, double* out, int mode) {
+    DeviceGuard device_guard(h);
     if (!h || !x || !out || (mode == 2 && !b)) return TO_EINVAL;
     if (p < 1 || p > TO_MAXP || count < 1) return fail(h, TO_EINVAL, "cone op: p must be in 1..32 and count >= 1");
     if (cone < 0 || cone > CONE_POSITIVE_ORTHANT) return fail(h, TO_EINVAL, "unknown cone");
@@ -819,8 +845,15 @@ static int materialise_expansion(to_handle* h, double* EG, double* EH) {
     return TO_OK;
 }
 static int do_backward(to_handle* h) {
-    if (h->P.dense_riccati) {
+    // to_options.backward_kernel: 0 automatic, 3 generic DFMA kernel on the full expansion, 5 shared-memory tensor kernel on the compact expansion
+    if (h->P.frag && h->P.opt.pad != 3 && h->P.opt.pad != 5) {
+        { PhaseScope pe(h, TO_PHASE_COSTEXP); CU(h, launch_expansion_rec(h->P, h->stream)); }
+        h->launches++; h->phase_launches[TO_PHASE_COSTEXP]++;
         PhaseScope ps(h, TO_PHASE_BACKWARD);
+        CU(h, launch_backward_frag(h->P, h->d_work, h->stream));
+    } else if (h->P.dense_riccati) {
+        PhaseScope ps(h, TO_PHASE_BACKWARD);
+        if (h->P.frag) { CU(h, launch_export_abe(h->P, h->stream)); h->launches++; }     // the shared-memory kernels read P.ABe
         DevProblem Q = h->P;
         Q.compact = (h->P.compact && h->P.opt.pad != 3) ? 1 : 0;      // backward_kernel = 3: the generic (DFMA, full expansion) kernel
         if (Q.compact) { CU(h, launch_expansion_compact(Q, h->stream)); h->launches++; }
@@ -869,8 +902,9 @@ int to_forward(to_handle* h, double* J, double* alpha) {
 }
 int to_ilqr_step(to_handle* h, int32_t iters) {
     if (!h || iters < 0) return TO_EINVAL;
+    DeviceGuard device_guard(h);
     int rc = solver_supported(h); if (rc) return rc;
-    if (!h->J_valid) JOIN(h);
+    if (!h->J_valid) { rc = join_side(h); if (rc) return rc; }
     rc = ensure_merit(h); if (rc) return rc;
     // Per iteration: E (expansion) -> R (Riccati) -> F pass 1 (alpha = 1..1/8, ~90% of the instances) -> F pass 2 (the rest).
     // Pass 2 is latency-bound and touches few instances, so it runs on a high-priority side stream followed by the
@@ -947,6 +981,7 @@ int to_get_error_dynamics(to_handle* h, double* ABe) {
     if (!h->expanded) return fail(h, TO_ESTATE, "to_get_error_dynamics before to_expand");
     if (!h->P.dense_riccati) return to_get_dynamics_jacobians(h, ABe);     // no error state: [A_e B_e] = [A B]
     if (!h->P.lie) { CU(h, launch_error_dynamics(h->P, h->stream)); h->launches++; }   // error state: written by k_expand_lie in to_expand
+    else if (h->P.frag) { CU(h, launch_export_abe(h->P, h->stream)); h->launches++; }    // ... as record fragments: back to col-major 12 x 16
     const size_t cnt = (size_t)h->P.B * (h->P.N - 1) * h->P.ne * (h->P.ne + h->P.m);
     CU(h, cudaMemcpyAsync(ABe, h->P.ABe, cnt * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     CU(h, cudaStreamSynchronize(h->stream));
@@ -1018,13 +1053,14 @@ int to_reduce_merit(to_handle* h) {
 }
 int to_reduce_merit_async(to_handle* h, void* consumer_stream) {
     if (!h) return TO_EINVAL;
+    DeviceGuard device_guard(h);
     cudaStream_t cs = (cudaStream_t)consumer_stream;
     cudaStream_t on = h->stream;
     if (h->side_pending && h->J_valid) {
         // the late line-search trials are still in flight on the side stream: reduce behind them, leave the main stream alone
         on = h->stream2;
     } else {
-        JOIN(h);
+        int jrc = join_side(h); if (jrc) return jrc;
         int rc = ensure_merit(h); if (rc) return rc;
     }
     CU(h, cudaEventRecord(h->ev_cons, cs));                 // the consumer's earlier reads of the buffer come first
@@ -1046,6 +1082,7 @@ int to_set_phase_timing(to_handle* h, int enable) {
     return TO_OK;
 }
 int to_get_phase_times(to_handle* h, double* ms, int64_t* launches, int reset) {
+    DeviceGuard device_guard(h);
     if (!h) return TO_EINVAL;
     CU(h, cudaStreamSynchronize(h->stream));
     for (auto& e : h->pending) {
@@ -1077,7 +1114,10 @@ int to_algorithmic_bytes(const to_handle* h, int64_t* E, int64_t* R, int64_t* F)
     //   generic: full-state expansion (scratch) -> error-state expansion (HES) ; [A B] -> [A_e B_e] unless k_expand_lie wrote it
     const int64_t EC = (int64_t)TO_EC_LEN * N, HESF = ((n + m) * (n + m) + (n + m)) * N;
     if (R) {
-        if (h->P.compact && h->P.opt.pad != 3) *R = (XU + L + 2 * EC + ABe + KD) * w;
+        // record path (riccati_frag.cu): the Riccati kernel is timed alone; its compulsory inputs are [A_e B_e], the trajectory and the
+        // multipliers (what the expansion it consumes is made of), its outputs the gains -- SURVEY 8(d)'s R column on the error state
+        if (h->P.frag && h->P.opt.pad != 3 && h->P.opt.pad != 5) *R = (ABe + XU + KD + L) * w;
+        else if (h->P.compact && h->P.opt.pad != 3) *R = (XU + L + 2 * EC + ABe + KD) * w;
         else if (h->P.dense_riccati) *R = (XU + L + 2 * HESF + 2 * HES + (h->P.lie ? 0 : AB + ABe) + ABe + KD) * w;
         else *R = (AB + XU + KD + L) * w;
     }

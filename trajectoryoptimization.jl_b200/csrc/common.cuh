@@ -16,7 +16,8 @@
 #define TO_MAXM 8
 #define TO_MAXNM (TO_MAXN + TO_MAXM)
 #define TO_MAXCON 8
-#define TO_MAXP 32          // rows of one constraint at one knot
+#define TO_MAXP 32          // rows of one general constraint at one knot (dense Jacobian / cone scratch is sized by it)
+#define TO_MAXPV (2 * TO_MAXNM)   // rows of a Goal / Bound constraint: a BoundConstraint with every entry of z bounded on both sides
 #define TO_CON_A 256
 #define TO_EXPR_LEN 128      // == TO_EXPR_MAXLEN / TO_EXPR_MAXCONST of include/trajopt_b200.h
 #define TO_EXPR_CONST 64
@@ -90,9 +91,13 @@ struct DevProblem {
     // x[qs..qs+3] contributing its 3-dimensional differential.  dense_riccati: the backward pass reads the per-knot expansion
     // (EG, EH) and [A_e B_e] (ABe) materialised in HBM by lie.cu instead of expanding in-kernel (error state, quaternion costs).
     int lie, ne, qs, dense_riccati;
-    int compact, pad_c;       // lie + only DiagonalCost + Goal/Bound constraints: the expansion of a knot is a
+    int compact, frag;        // compact: lie + only DiagonalCost + Goal/Bound constraints: the expansion of a knot is a
                               // gradient, a diagonal and the 3 x 3 attitude block -> EC, 40 doubles per knot instead of EG + EH (272)
+                              // frag: compact problems keep [A_e B_e] + expansion as per-knot RECORDS in MMA-fragment order (REC,
+                              // frag_layout.cuh) for the register-resident Riccati kernel (riccati_frag.cu); ABe / EC are then only
+                              // filled on request (export, the shared-memory kernels forced by to_options.backward_kernel)
     double* EC;               // [B][N][TO_EC_LEN]: g_e(16) | diag(16) | block (0,1),(0,2),(1,2) | pad
+    double* REC;              // [B][N][TO_REC_LEN] (frag)
     double* ABe;              // [B][N-1][ne+m][ne]   ne x (ne+m) col-major
     double* EG;               // [B][N][ne+m]
     double* EH;               // [B][N][ne+m][ne+m]
@@ -129,6 +134,11 @@ __host__ __device__ inline const double* traj_X(const DevProblem& P, int buf, in
 __host__ __device__ inline const double* traj_U(const DevProblem& P, int buf, int b) { return P.U + buf * P.strideU + (size_t)b * (P.N - 1) * P.m; }
 __host__ __device__ inline double* traj_Xw(const DevProblem& P, int buf, int b) { return P.X + buf * P.strideX + (size_t)b * P.N * P.n; }
 __host__ __device__ inline double* traj_Uw(const DevProblem& P, int buf, int b) { return P.U + buf * P.strideU + (size_t)b * (P.N - 1) * P.m; }
+
+// One process may hold handles on several GPUs (to_spec.device): function attributes and occupancy are per device, so the
+// launchers cache their one-time configuration per device ordinal.
+#define TO_MAXDEV 64
+inline int current_device_slot() { int d = 0; cudaGetDevice(&d); return (d >= 0 && d < TO_MAXDEV) ? d : 0; }
 
 // Altro.jl regularization_update! (restated; see oracle/oracle.hpp reg_increase / reg_decrease)
 __host__ __device__ inline void reg_increase(const DevOptions& o, double& rho, double& drho) {

@@ -420,7 +420,7 @@ __device__ inline double al_knot_penalty(const DevProblem& P, int k1, const doub
         if (k1 < con.first || k1 > con.last) continue;
         const double mu = P.mu[ci];
         const double* lam = lam_b + con.offset + (size_t)(k1 - con.first) * con.p;
-        double c[TO_MAXP], lbar[TO_MAXP], lp[TO_MAXP];
+        double c[TO_MAXPV], lbar[TO_MAXPV], lp[TO_MAXPV];
         con_evaluate(con, P.n, P.m, x, u, c);
         for (int i = 0; i < con.p; i++) lbar[i] = lam[i] - mu * c[i];
         cone_projection(dualcone(con.sense), lbar, con.p, lp);
@@ -451,7 +451,7 @@ __device__ inline void al_knot_expansion(const DevProblem& P, int k0, const doub
         const int p = con.p;
         const double mu = P.mu[ci];
         const double* lam = lam_b + con.offset + (size_t)(k0 + 1 - con.first) * p;
-        double c[TO_MAXP], lbar[TO_MAXP], lp[TO_MAXP];
+        double c[TO_MAXPV], lbar[TO_MAXPV], lp[TO_MAXPV];
         con_evaluate(con, n, m, x, u, c);
         if (con.diagonal) {   // Goal / Bound: +-1 selector rows (src/constraints.jl:62-68, :757-765) -- row by row, no dense products
             const bool eq = (con.kind == CON_GOAL);

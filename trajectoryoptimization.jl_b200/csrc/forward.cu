@@ -442,12 +442,13 @@ cudaError_t launch_pass_l(const DevProblem& P, int trial0, int first_pass, int f
     const int blocks = (P.B + IPB - 1) / IPB;
     const size_t smem = FAST ? sizeof(FwdTab) + (size_t)2 * Stage<n, m, IPB, NE>::DOUBLES * sizeof(double) : 0;
     auto kern = k_linesearch<MODEL, G, FAST, LANES, LIE>;
-    static bool configured = false;
-    if (!configured && smem > 48 * 1024) {
+    static bool configured[TO_MAXDEV] = {false};
+    const int dev = current_device_slot();
+    if (!configured[dev] && smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
     }
-    configured = true;
+    configured[dev] = true;
     kern<<<blocks, FWD_THREADS, smem, s>>>(P, trial0, first_pass, final_pass);
     return cudaGetLastError();
 }

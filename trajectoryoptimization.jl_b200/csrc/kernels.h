@@ -33,6 +33,10 @@ cudaError_t launch_error_expansion(const DevProblem& P, const double* gfull, con
 cudaError_t launch_backward_dense(const DevProblem& P, cudaStream_t s);
 cudaError_t launch_expansion_compact(const DevProblem& P, cudaStream_t s);             // EC of every knot (P.compact)
 cudaError_t launch_expand_lie(const DevProblem& P, cudaStream_t s, int mode = 0);     // [A_e B_e] straight from the dual-number RK4 step (rollout.cu)
+// register-resident Riccati pass of the error-state Quadrotor + its record producers   (riccati_frag.cu)
+cudaError_t launch_expansion_rec(const DevProblem& P, cudaStream_t s);                 // compact expansion -> REC[192..240) of every knot
+cudaError_t launch_export_abe(const DevProblem& P, cudaStream_t s);                    // REC fragments -> ABe (col-major 12 x 16)
+cudaError_t launch_backward_frag(const DevProblem& P, int* work_counter, cudaStream_t s);
 // forward pass: closed-loop rollout + merit + line search                     (forward.cu)
 cudaError_t launch_forward(const DevProblem& P, cudaStream_t s);
 cudaError_t launch_ladder(const DevProblem& P, cudaStream_t s);

@@ -643,12 +643,13 @@ __global__ void __launch_bounds__(32 * WARPS) k_riccati_dense_mma(const DevProbl
 cudaError_t launch_dense_mma(const DevProblem& P, cudaStream_t s) {
     constexpr int WARPS = TO_DENSE_WARPS;
     const int smem = (int)sizeof(MmaSmem) * WARPS;
-    static bool configured = false;
-    if (!configured) {
+    static bool configured[TO_MAXDEV] = {false};
+    const int dev = current_device_slot();
+    if (!configured[dev]) {
         cudaError_t e = cudaFuncSetAttribute(k_riccati_dense_mma<WARPS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(k_riccati_dense_mma<WARPS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return e;
-        configured = true;
+        configured[dev] = true;
     }
     if (P.compact) k_riccati_dense_mma<WARPS, true><<<(P.B + WARPS - 1) / WARPS, 32 * WARPS, smem, s>>>(P);
     else k_riccati_dense_mma<WARPS, false><<<(P.B + WARPS - 1) / WARPS, 32 * WARPS, smem, s>>>(P);

@@ -937,19 +937,19 @@ template <int N_, int M_, bool FASTAL, int STAGES, int MINB, bool MMA, int NSLOT
 cudaError_t launch_riccati_v(const DevProblem& P, int* work_counter, cudaStream_t s) {
     using SM = RiccatiSmem<N_, M_, STAGES, MMA>;
     auto kern = k_riccati<N_, M_, STAGES, FASTAL, MMA, MINB, NSLOT>;
-    static bool configured = false;
-    static int ctas_per_sm = 1, num_sms = 1;
+    static int ctas_cfg[TO_MAXDEV] = {0}, sms_cfg[TO_MAXDEV] = {0};      // per device (0 = not configured yet)
     const int smem = (int)sizeof(SM);
-    if (!configured) {
+    const int dev = current_device_slot();
+    if (!ctas_cfg[dev]) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return e;
-        int dev = 0; cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kern, 32, smem);
+        cudaDeviceGetAttribute(&sms_cfg[dev], cudaDevAttrMultiProcessorCount, dev);
+        int c = 1;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c, kern, 32, smem);
         if (e != cudaSuccess) return e;
-        if (ctas_per_sm < 1) ctas_per_sm = 1;
-        configured = true;
+        ctas_cfg[dev] = c < 1 ? 1 : c;
     }
+    const int ctas_per_sm = ctas_cfg[dev], num_sms = sms_cfg[dev];
     cudaError_t e = cudaMemsetAsync(work_counter, 0, sizeof(int), s);
     if (e != cudaSuccess) return e;
     int grid = num_sms * ctas_per_sm;     // persistent: a multiple of the SM count, instances pulled from a queue

@@ -11,6 +11,7 @@
 //               adjacent lanes; the pad columns of a row (LDAB > n+m) are never touched and stay zero.
 #include <cstdlib>
 
+#include "frag_layout.cuh"
 #include "kernels.h"
 #include "models.cuh"
 
@@ -78,7 +79,8 @@ __global__ void __launch_bounds__(128) k_expand(const DevProblem P, int mode) {
 // E(x_k) = blkdiag(I3, G(q_k), I6 | I4) through the RK4 step as the tangent of a Dual<1> -- the directional derivative [A G_k | B] e_j --
 // and projects the result with G(q_{k+1})' (q_{k+1} from the stored trajectory, as Altro's errstate_jacobian! does).  It writes column j
 // of [A_e B_e]_k (12 contiguous doubles, col-major 12 x 16): 1.5 KB per knot instead of the 2 KB of the padded full-state [A B].
-template <int MODEL>
+// FRAG: the column goes into the fragment block of the knot's record (frag_layout.cuh) instead of P.ABe.
+template <int MODEL, bool FRAG>
 __global__ void __launch_bounds__(128) k_expand_lie(const DevProblem P, int mode) {
     constexpr int n = ModelDims<MODEL>::n, m = ModelDims<MODEL>::m, ne = n - 1, nme = ne + m, qs = 3;
     using D = Dual<1>;
@@ -112,23 +114,36 @@ __global__ void __launch_bounds__(128) k_expand_lie(const DevProblem P, int mode
         for (int i = qs + 4; i < n; i++) x[i].d[0] = (i == j + 1) ? 1.0 : 0.0;
     }
     rk4_step<MODEL, D>(P.params, x, u, P.dt[k], xn);
-    double* out = P.ABe + ((size_t)bk * nme + j) * ne;
     const double* q1 = X + n + qs;                                     // attitude of knot k + 1
     const double w1 = q1[0], x1 = q1[1], y1 = q1[2], z1 = q1[3];
+    double col[ne];
 #pragma unroll
-    for (int i = 0; i < qs; i++) out[i] = xn[i].d[0];
+    for (int i = 0; i < qs; i++) col[i] = xn[i].d[0];
     const double t0 = xn[qs].d[0], t1 = xn[qs + 1].d[0], t2 = xn[qs + 2].d[0], t3 = xn[qs + 3].d[0];
-    out[qs] = -x1 * t0 + w1 * t1 + z1 * t2 - y1 * t3;
-    out[qs + 1] = -y1 * t0 - z1 * t1 + w1 * t2 + x1 * t3;
-    out[qs + 2] = -z1 * t0 + y1 * t1 - x1 * t2 + w1 * t3;
+    col[qs] = -x1 * t0 + w1 * t1 + z1 * t2 - y1 * t3;
+    col[qs + 1] = -y1 * t0 - z1 * t1 + w1 * t2 + x1 * t3;
+    col[qs + 2] = -z1 * t0 + y1 * t1 - x1 * t2 + w1 * t3;
 #pragma unroll
-    for (int i = qs + 4; i < n; i++) out[i - 1] = xn[i].d[0];
+    for (int i = qs + 4; i < n; i++) col[i - 1] = xn[i].d[0];
+    if constexpr (FRAG) {
+        // element (row e, column j) of the record: (ks(e)*32 + 4*(c & 7) + fc(e))*2 + (c >> 3), c = physical index of column j
+        const int c = (int)((0x6420FDB9E7CA8531ULL >> (4 * j)) & 15);       // fraglayout::phys_z(j) as a nibble table
+        double* rec = P.REC + ((size_t)b * P.N + k) * TO_REC_LEN + 8 * (c & 7) + (c >> 3);
+#pragma unroll
+        for (int e = 0; e < ne; e++) rec[fraglayout::ab_index(e, 12)] = col[e];   // column 12 (u_0, c = 0) has a zero column offset
+    } else {
+        double* out = P.ABe + ((size_t)bk * nme + j) * ne;
+#pragma unroll
+        for (int e = 0; e < ne; e++) out[e] = col[e];
+    }
 }
 
 cudaError_t launch_expand_lie(const DevProblem& P, cudaStream_t s, int mode) {
     if (P.model != MODEL_QUADROTOR) return cudaErrorNotSupported;
     const long long total = (long long)P.B * (P.N - 1) * (P.ne + P.m);
-    k_expand_lie<MODEL_QUADROTOR><<<(unsigned)((total + 127) / 128), 128, 0, s>>>(P, mode);
+    static_assert(fraglayout::phys_z(0) == 1 && fraglayout::phys_z(5) == 12 && fraglayout::phys_z(11) == 15 && fraglayout::phys_z(12) == 0 && fraglayout::phys_z(15) == 6, "nibble table of k_expand_lie");
+    if (P.frag) k_expand_lie<MODEL_QUADROTOR, true><<<(unsigned)((total + 127) / 128), 128, 0, s>>>(P, mode);
+    else k_expand_lie<MODEL_QUADROTOR, false><<<(unsigned)((total + 127) / 128), 128, 0, s>>>(P, mode);
     return cudaGetLastError();
 }
 

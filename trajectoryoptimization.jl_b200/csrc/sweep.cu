@@ -106,7 +106,7 @@ __global__ void k_eval_constraints(const DevProblem P, int ci, double* __restric
     double zero_u[TO_MAXM] = {0};
     const double* x = traj_X(P, P.cur[b], b) + (size_t)(k1 - 1) * P.n;
     const double* u = (k1 == P.N) ? zero_u : traj_U(P, P.cur[b], b) + (size_t)(k1 - 1) * P.m;
-    double c[TO_MAXP];
+    double c[TO_MAXPV];
     con_evaluate(con, P.n, P.m, x, u, c);
     for (int i = 0; i < con.p; i++) vals[t * con.p + i] = c[i];
 }
@@ -154,7 +154,7 @@ __global__ void k_al_update(const DevProblem P) {
         for (int k1 = con.first + threadIdx.x; k1 <= con.last; k1 += blockDim.x) {
             const double* x = X + (size_t)(k1 - 1) * P.n;
             const double* u = (k1 == P.N) ? zero_u : U + (size_t)(k1 - 1) * P.m;
-            double c[TO_MAXP], lbar[TO_MAXP], lp[TO_MAXP];
+            double c[TO_MAXPV], lbar[TO_MAXPV], lp[TO_MAXPV];
             double* lam = lam_b + con.offset + (size_t)(k1 - con.first) * con.p;
             con_evaluate(con, P.n, P.m, x, u, c);
             for (int i = 0; i < con.p; i++) lbar[i] = lam[i] - mu * c[i];

@@ -34,12 +34,18 @@ def merit_device_tensor(prob, device):
     return torch.as_tensor(_DevPtr(ptr.value, 2), device=device)
 
 
-def all_reduce_merit(t2, group=None):
-    """in-place all-reduce of a 2-element tensor: SUM on [0], MAX on [1]."""
+def all_reduce_merit(t2, group=None, scratch=None):
+    """in-place reduction of a 2-element tensor over the ranks: SUM on [0], MAX on [1] -- ONE collective (an all-gather of the
+    2-vectors, reduced locally) instead of a SUM and a MAX all-reduce: the exchange is launch-latency bound (16 bytes per rank).
+    ``scratch``: a preallocated [world, 2] tensor on the same device (avoids an allocation per call)."""
+    import torch
     import torch.distributed as dist
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
-        dist.all_reduce(t2[0:1], op=dist.ReduceOp.SUM, group=group)
-        dist.all_reduce(t2[1:2], op=dist.ReduceOp.MAX, group=group)
+        world = dist.get_world_size(group)
+        buf = scratch if scratch is not None else torch.empty((world, 2), dtype=t2.dtype, device=t2.device)
+        dist.all_gather_into_tensor(buf, t2.reshape(1, 2), group=group) if t2.is_cuda else dist.all_gather(list(buf.unbind(0)), t2, group=group)
+        t2[0] = buf[:, 0].sum()
+        t2[1] = buf[:, 1].max()
     return t2
 
 

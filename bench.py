@@ -29,6 +29,7 @@ sys.path.insert(0, ROOT)
 WORKLOADS = {
     "quadrotor": dict(n=13, m=4, N=101, batch=4096, desc="Quadrotor point-to-point n=13 m=4 N=101, u in [0,10] + goal (AL-iLQR), Riccati on the Lie-group error state n_e=12 (what Altro does for this model)"),
     "quadrotor_fullstate": dict(n=13, m=4, N=101, batch=4096, desc="Quadrotor point-to-point n=13 m=4 N=101, u in [0,10] + goal (AL-iLQR), Riccati on the full 13-state (round-1 headline)"),
+    "quadrotor_calm": dict(n=13, m=4, N=101, batch=4096, desc="the quadrotor workload with a 25x smaller perturbation of the hover controls (the open-loop rollout does not tumble): no regularisation restarts in the backward pass -- isolates the single-sweep speed of the Riccati kernel"),
     "cartpole": dict(n=4, m=1, N=101, batch=1024, desc="Cartpole swing-up n=4 m=1 N=101, unconstrained LQR cost"),
     "acrobot": dict(n=4, m=1, N=201, batch=8192, desc="Acrobot n=4 m=1 N=201, dense second-order cost + |u|<=15 + goal (AL)"),
     "quadrotor_lie": dict(n=13, m=4, N=101, batch=4096, desc="Quadrotor n=13 m=4 N=101 on the Lie-group error state (n_e=12), LQR cost, u in [0,10] + goal; materialised expansion (lie.cu)"),
@@ -40,6 +41,8 @@ def build_problem(workload, B, N, cls=None, device=0):
     P = TO.problems
     if workload == "quadrotor":
         return P.quadrotor(B=B, N=N, cls=cls, device=device, error_state=True)
+    if workload == "quadrotor_calm":
+        return P.quadrotor(B=B, N=N, cls=cls, device=device, error_state=True, u_noise=0.002)
     if workload == "quadrotor_fullstate":
         return P.quadrotor(B=B, N=N, cls=cls, device=device)
     if workload == "cartpole":
@@ -161,7 +164,7 @@ def run_reference(args, rank, world):
 
 def make_config(args, w, per_gpu, N, world):
     """the `config` object of the JSON line -- identical for the GPU arm and the CPU (--impl reference) arm"""
-    n_r, nm_r = (w["n"] - 1, w["n"] + w["m"] - 1) if args.workload in ("quadrotor", "quadrotor_lie") else (w["n"], w["n"] + w["m"])
+    n_r, nm_r = (w["n"] - 1, w["n"] + w["m"] - 1) if args.workload in ("quadrotor", "quadrotor_lie", "quadrotor_calm") else (w["n"], w["n"] + w["m"])
     return {"workload": w["desc"], "batch_per_gpu": per_gpu, "N": N, "global_batch": per_gpu * world, "parallelism": f"batch-sharded x{world}",
             "step": "1 iLQR iteration = dynamics expansion + Riccati backward pass + forward pass/line search of every instance, K consecutive iterations of one solve",
             "merit_collective_every": (args.merit_every if world > 1 else None),
@@ -312,9 +315,9 @@ def main():
         traffic = json.load(open(os.path.join(ROOT, "profiles", "riccati_traffic.json"))).get(f"{args.workload}_B{B}_N{N}")
     except Exception:
         pass
-    frag = args.workload in ("quadrotor", "quadrotor_lie") and not os.environ.get("TO_NO_FRAG")
+    frag = args.workload in ("quadrotor", "quadrotor_lie", "quadrotor_calm") and not os.environ.get("TO_NO_FRAG")
     rk = "k_riccati_frag (riccati_frag.cu: register-resident tensor-core Riccati pass on the error state, timed alone)" if frag \
-        else "k_expansion_compact + k_riccati_dense_mma (lie.cu: error-state expansion + shared-memory tensor-core Riccati pass)" if args.workload in ("quadrotor", "quadrotor_lie") \
+        else "k_expansion_compact + k_riccati_dense_mma (lie.cu: error-state expansion + shared-memory tensor-core Riccati pass)" if args.workload in ("quadrotor", "quadrotor_lie", "quadrotor_calm") \
         else "k_riccati (Riccati backward pass)"
     roofline = {"kernel": rk, "bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
                 "frac": achieved / peak_gbs, "traffic": traffic, "peak_source": peak_src,
@@ -322,7 +325,7 @@ def main():
                 "phase_ms": phase, "fp64_tflops_riccati": None}
     # FP64 view of the same kernel: 2 * (T + Qzz + Qz + S-update + solves) FMA per knot, counted analytically
     nm = n + m
-    if args.workload in ("quadrotor", "quadrotor_lie"):
+    if args.workload in ("quadrotor", "quadrotor_lie", "quadrotor_calm"):
         n, nm = n - 1, nm - 1        # the recursion runs on the error state
     fma_knot = n * n * nm + n * nm * (nm + 1) // 2 + n * nm + m * n * (n + 1) // 2 + m * m * (n + 1) + m * m * m // 3
     roofline["fp64_tflops_riccati"] = (2.0 * fma_knot * (N - 1) * B / (r_ms * 1e-3)) / 1e12 if r_ms > 0 else None

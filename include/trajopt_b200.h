@@ -212,6 +212,10 @@ int to_ilqr_step(to_handle* h, int32_t iters);                                /*
 int to_al_update(to_handle* h);                                               /* dual + penalty update */
 int to_get_gains(to_handle* h, double* K /*[B][N-1][n_e][m]: m x n_e col-major (n_e = n unless error_state)*/, double* d /*[B][N-1][m]*/);
 /* ---- Lie-group error state ------------------------------------------------------------------- */
+int to_backward_algebra(const to_handle* h, int32_t* variant);             /* which arithmetic the next to_backward will use: 0 = pivot-by-pivot LDL' solve
+                                                                             (riccati.cu, riccati_small.cu, lie.cu), 1 = 2 x 2 block inverse + W'K update
+                                                                             (riccati_frag.cu).  Same mathematics (Altro backwardpass!); the oracle mirrors
+                                                                             either so that parity tests compare like with like */
 int to_error_state_dim(const to_handle* h, int32_t* ne);                      /* RD.errstate_dim(model): n, or n - 1 with spec.error_state */
 /* RD.state_diff(model, xbar, x) of every knot against the current trajectory: Xbar [B][N][n] (host) -> dx [B][N][n_e] */
 int to_state_diff(to_handle* h, const double* Xbar, double* dx);

@@ -523,6 +523,11 @@ struct Options {
     double penalty_scaling = 10.0;
     double penalty_max = 1e8;
     double dual_max = 1e8;
+    // 0: Cholesky solve + the long form of the cost-to-go update (below).  1 (m = 4 only): the ALGEBRA of the register-resident GPU
+    // kernel (csrc/riccati_frag.cu) in plain loops -- (Quu + rho I)^-1 by 2 x 2 block elimination, K = -Minv Qux, W = (I + rho Minv) Qux,
+    // S <- Qxx + W'K unsymmetrised, s <- Qx + K'w_d, dV2 = -(dV1 + rho d'd)/2.  Mathematically identical; the two differ by rounding only,
+    // which the Riccati recursion of an ill-conditioned trajectory amplifies (tests/test_oracle_variants.py measures by how much).
+    int backward_variant = 0;
 };
 
 struct Problem {
@@ -912,6 +917,55 @@ inline int backward_pass(Problem& P, int b) {
                 for (int r = 0; r < n; r++) t += AB[j * n + r] * s[r];
                 Qz[j] = grad[j] + t;
             }
+            if (P.opts.backward_variant == 1 && m == 4) {
+                auto Mq = [&](int a, int c) { return Qzz[(n + (a > c ? a : c)) * nm + n + (a > c ? c : a)]; };   // upper-triangle entry of Quu
+                const double a = Mq(0, 0) + rho, bq = Mq(0, 1), c = Mq(1, 1) + rho;
+                const double M20 = Mq(0, 2), M30 = Mq(0, 3), M21 = Mq(1, 2), M31 = Mq(1, 3);
+                const double R00 = Mq(2, 2) + rho, R01 = Mq(2, 3), R11 = Mq(3, 3) + rho;
+                const double detP = std::fma(a, c, -bq * bq);
+                const double iP = 1.0 / detP;
+                const double yt00 = std::fma(M20, c, -M21 * bq), yt01 = std::fma(M21, a, -M20 * bq);
+                const double yt10 = std::fma(M30, c, -M31 * bq), yt11 = std::fma(M31, a, -M30 * bq);
+                const double z00 = std::fma(yt00, M20, yt01 * M21), z01 = std::fma(yt00, M30, yt01 * M31), z11 = std::fma(yt10, M30, yt11 * M31);
+                const double s00 = std::fma(-iP, z00, R00), s01 = std::fma(-iP, z01, R01), s11 = std::fma(-iP, z11, R11);
+                const double detS = std::fma(s00, s11, -s01 * s01);
+                const double iS = 1.0 / detS;
+                if (!((a > 0) && (detP > 0) && (s00 > 0) && (detS > 0) && (detP < 1e300) && (detS < 1e300))) { ok = false; break; }
+                const double v00 = s11 * iS, v01 = -s01 * iS, v11 = s00 * iS;
+                const double y00 = yt00 * iP, y01 = yt01 * iP, y10 = yt10 * iP, y11 = yt11 * iP;
+                const double n00 = -std::fma(v00, y00, v01 * y10), n01 = -std::fma(v00, y01, v01 * y11);
+                const double n10 = -std::fma(v01, y00, v11 * y10), n11 = -std::fma(v01, y01, v11 * y11);
+                const double p00 = std::fma(c, iP, -std::fma(y00, n00, y10 * n10));
+                const double p01 = std::fma(-bq, iP, -std::fma(y00, n01, y10 * n11));
+                const double p11 = std::fma(a, iP, -std::fma(y01, n01, y11 * n11));
+                const double Mi[4][4] = {{p00, p01, n00, n10}, {p01, p11, n01, n11}, {n00, n01, v00, v01}, {n10, n11, v01, v11}};
+                double* Kk = &Kall[(size_t)k * m * n]; double* dk = &dall[(size_t)k * m];
+                std::vector<double> Wk((size_t)m * n);
+                double wd[4];
+                for (int cc = 0; cc <= n; cc++)
+                    for (int i = 0; i < 4; i++) {
+                        double kk = 0, ww = 0;
+                        for (int r = 0; r < 4; r++) {
+                            const double q = cc < n ? Qzz[(n + r) * nm + cc] : Qz[n + r];      // Qxu[cc][r] (the kernel reads the x rows of the u columns) | Qu[r]
+                            kk = std::fma(q, -Mi[r][i], kk);
+                            ww = std::fma(q, (r == i ? 1.0 : 0.0) + rho * Mi[r][i], ww);
+                        }
+                        if (cc < n) { Kk[cc * m + i] = kk; Wk[cc * m + i] = ww; } else { dk[i] = kk; wd[i] = ww; }
+                    }
+                for (int j = 0; j < n; j++) {
+                    for (int i = 0; i < n; i++) {
+                        double t = Qzz[j * nm + i];
+                        for (int r = 0; r < m; r++) t = std::fma(Wk[i * m + r], Kk[j * m + r], t);
+                        Sn[j * n + i] = t;
+                    }
+                    double t = Qz[j];
+                    for (int r = 0; r < m; r++) t = std::fma(wd[r], Kk[j * m + r], t);
+                    sn[j] = t;
+                }
+                for (int j = 0; j < n; j++) { s[j] = sn[j]; for (int i = 0; i < n; i++) S[j * n + i] = Sn[j * n + i]; }
+                for (int i = 0; i < m; i++) { dV1 = std::fma(dk[i], Qz[n + i], dV1); dV2 = std::fma(dk[i], dk[i], dV2); }   // dV2 holds sum d'd until the end
+                continue;
+            }
             // Cholesky of Quu + rho I (lower L, col-major m x m)
             for (int j = 0; j < m; j++) {
                 for (int i = j; i < m; i++) {
@@ -969,6 +1023,7 @@ inline int backward_pass(Problem& P, int b) {
             for (int j = 0; j < n; j++) { s[j] = sn[j]; for (int i = 0; i < n; i++) S[j * n + i] = 0.5 * (Sn[j * n + i] + Sn[i * n + j]); }
             for (int i = 0; i < m; i++) { dV1 += dk[i] * Qz[n + i]; dV2 += 0.5 * dk[i] * Quud[i]; }
         }
+        if (ok && P.opts.backward_variant == 1 && m == 4) dV2 = -0.5 * std::fma(rho, dV2, dV1);   // 1/2 d'Quu d = -(d'Qu + rho d'd)/2
         if (ok) { P.dV[2 * b] = dV1; P.dV[2 * b + 1] = dV2; break; }
         reg_increase(P.opts, P.rho[b], P.drho[b]);
         restarts++;

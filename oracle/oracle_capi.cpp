@@ -203,6 +203,13 @@ int orc_set_integrator(orc_handle* h, int order) {
     h->P.model.integrator = order; h->P.J_valid = false;
     return TO_OK;
 }
+// algebra of the backward pass: 0 = Cholesky solve (default), 1 = the block-inverse form of csrc/riccati_frag.cu (oracle.hpp Options)
+int orc_set_backward_variant(orc_handle* h, int v) {
+    if (v != 0 && v != 1) return TO_EINVAL;
+    h->P.opts.backward_variant = v;
+    return TO_OK;
+}
+int orc_get_backward_variant(orc_handle* h) { return h->P.opts.backward_variant; }
 int orc_set_threads(int nthreads) { omp_set_num_threads(nthreads > 0 ? nthreads : omp_get_num_procs()); return omp_get_max_threads(); }
 
 int orc_set_initial_state(orc_handle* h, const double* x0) { std::memcpy(h->P.x0.data(), x0, sizeof(double) * h->P.x0.size()); h->P.J_valid = false; return TO_OK; }

@@ -15,4 +15,4 @@ api = importlib.import_module(TO.Problem.__module__)
 api.Problem = oracle_binding.OracleProblem
 TO.Problem = oracle_binding.OracleProblem
 import pytest
-sys.exit(pytest.main(['--noconftest', '-W', 'ignore', os.path.join(ROOT, 'tests', 'test_gpu_parity.py'), os.path.join(ROOT, 'tests', 'test_golden.py'), '-m', 'gpu', '-q', '-p', 'no:cacheprovider']))
+sys.exit(pytest.main(['--noconftest', '-W', 'ignore', os.path.join(ROOT, 'tests', 'test_gpu_parity.py'), os.path.join(ROOT, 'tests', 'test_gpu_fullsize.py'), os.path.join(ROOT, 'tests', 'test_golden.py'), '-m', 'gpu', '-q', '-p', 'no:cacheprovider']))

@@ -46,6 +46,9 @@ class OracleProblem(TO.Problem):
             raise {K.TO_EDIM: TO.DimensionMismatch, K.TO_EINVAL: TO.ArgumentError}.get(rc, TO.TrajOptError)(msg)
 
     def _raw_call(self, name, *args):
+        if name == "to_backward_algebra":
+            args[0]._obj.value = self._lib.orc_get_backward_variant(self._h)
+            return
         fn = getattr(self._lib, "orc_" + name[3:])
         fn.restype = C.c_int
         conv = [C.c_double(a) if isinstance(a, float) else a for a in args]
@@ -56,6 +59,16 @@ class OracleProblem(TO.Problem):
     def _default_options(self, o):
         self._lib.orc_default_options(C.byref(o))
 
+    def set_backward_variant(self, v):
+        """arithmetic form of the backward pass (oracle.hpp Options::backward_variant): 0 = Cholesky solve, 1 = the block-inverse
+        algebra of csrc/riccati_frag.cu"""
+        assert self._lib.orc_set_backward_variant(self._h, int(v)) == 0
+        return self
+
+    def set_integrator(self, order):
+        assert self._lib.orc_set_integrator(self._h, int(order)) == 0
+        return self
+
     def close(self):
         if getattr(self, "_h", None):
             self._lib.orc_destroy(self._h)
@@ -64,6 +77,13 @@ class OracleProblem(TO.Problem):
 
 def _dp(a):
     return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def match_algebra(g, o):
+    """make the oracle problem `o` use the arithmetic form of the backward pass that the CUDA problem `g` will use, so that the
+    comparison is like with like (tests/test_oracle_variants.py measures what the OTHER form differs by)"""
+    o.set_backward_variant(TO.backward_algebra(g))
+    return o
 
 
 def oracle_projection(cone, x):

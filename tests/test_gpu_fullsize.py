@@ -5,81 +5,81 @@ of the batch, every knot, gains / expected decrease / step sizes / regularisatio
 oracle on the same seeded inputs.  More instances than resident warps (4096 > 148 x 16 or 148 x 28) exercises the atomic work
 queues of the persistent Riccati kernels, which the small batches cannot.
 
-Tolerances are the measured error budget of profiles/parity_budget.py: one backward pass agrees to
-K_RTOL (relative to the largest gain of the batch); the closed-loop rollout that follows multiplies a gain perturbation by the
-sensitivity of the trajectory to the gains, which is what ITER_RTOL covers after several iterations."""
+Tolerances (parity_util.py): one kernel application on identical inputs agrees with the oracle in the same arithmetic
+form to KERNEL tolerance; after closed-loop iterations every instance has to stay within FACTOR x the divergence of the oracle's two
+arithmetic forms on that instance (its intrinsic fp64 uncertainty) -- Cartpole / Acrobot: that IS the tight tolerance (the twins
+agree to 1e-11); the tumbling Quadrotor instances: whatever the problem's conditioning leaves."""
 import numpy as np
 import pytest
 
 import trajopt_b200 as TO
-from oracle_binding import OracleProblem
+from parity_util import check, decisions_agree, triple
 
 pytestmark = pytest.mark.gpu
 P = TO.problems
 
-K_RTOL = 1e-9       # gains / expected decrease of one backward pass
-F_RTOL = 1e-9       # trajectory and merit after the first forward pass
-ITER_RTOL = 1e-6    # merit / iterates after 3 iterations + AL update + 2 iterations
-
-
-def close(a, b, rtol, what):
-    a, b = np.asarray(a), np.asarray(b)
-    scale = max(1.0, float(np.max(np.abs(b))))
-    err = float(np.max(np.abs(a - b)))
-    assert np.all(np.isfinite(a)), f"{what}: non-finite GPU result"
-    assert err <= rtol * scale, f"{what}: max abs err {err:.3e} > {rtol:.0e} * {scale:.3e}"
-
+ROLLOUT_TOL = 1e-12  # rollout!, [A B]: no recursion, no amplification
+K_TOL = 2e-9         # gains / expected decrease of one backward pass, like with like (measured: 3.5e-11 full state, see profiles/r02_notes.md)
+F_TOL = 1e-9         # one forward pass: only where the twins say the instance is that well conditioned
+ITER_TOL = 1e-8      # after the iterations: ditto
 
 FULL = {
     # BASELINE.json configs[1]: Cartpole swing-up batch 1024, unconstrained (warp kernel is the automatic choice below 2048 instances)
     "cartpole_B1024": (lambda cls: P.cartpole(B=1024, N=101, cls=cls), {}),
-    # configs[2]: Quadrotor point-to-point batch 4096, goal + control bounds -- full-state recursion (k_riccati, DMMA n = 13)
-    "quadrotor_B4096": (lambda cls: P.quadrotor(B=4096, N=101, cls=cls), {}),
-    # ... and on the Lie-group error state, what Altro does for this model (k_riccati_frag, register-resident n_e = 12)
+    # configs[2]: Quadrotor point-to-point batch 4096, goal + control bounds -- on the Lie-group error state (what Altro does for this
+    # model; k_riccati_frag, register-resident n_e = 12) ...
     "quadrotor_errstate_B4096": (lambda cls: P.quadrotor(B=4096, N=101, cls=cls, error_state=True), {}),
+    # ... and the full-state recursion (k_riccati, DMMA n = 13; round-1 headline)
+    "quadrotor_fullstate_B4096": (lambda cls: P.quadrotor(B=4096, N=101, cls=cls), {}),
     # configs[3]: Acrobot batch 8192 N=201, AL + dense second-order cost expansion -- both Riccati kernels
     "acrobot_B8192_warp": (lambda cls: P.acrobot(B=8192, N=201, cls=cls), {"backward_kernel": 1}),
     "acrobot_B8192_diag_thread": (lambda cls: P.acrobot(B=8192, N=201, cls=cls, dense_cost=False), {"backward_kernel": 2}),
     # configs[4]: the MPC sweep's longest horizon
-    "quadrotor_N401_B1024": (lambda cls: P.quadrotor(B=1024, N=401, cls=cls, dt=0.05), {}),
     "quadrotor_errstate_N401_B1024": (lambda cls: P.quadrotor(B=1024, N=401, cls=cls, dt=0.05, error_state=True), {}),
+    "quadrotor_fullstate_N401_B1024": (lambda cls: P.quadrotor(B=1024, N=401, cls=cls, dt=0.05), {}),
 }
 
 
 @pytest.mark.parametrize("name", sorted(FULL))
 def test_full_size_elementwise(name):
     build, opts = FULL[name]
-    g, o = build(TO.Problem), build(OracleProblem)
-    if opts:
-        TO.set_options(g, **opts)
-    for p in (g, o):
+    g, o, t = triple(build, opts)
+    probs = (g, o, t)
+    for p in probs:
         TO.rollout(p); TO.expand(p)
-    close(TO.states(g), TO.states(o), 1e-10, "rollout X")
-    sg, so = TO.backward(g), TO.backward(o)
-    assert np.array_equal(sg, so), "regularisation restarts differ"
-    Kg, dg = TO.gains(g); Ko, do = TO.gains(o)
-    close(Kg, Ko, K_RTOL, "K"); close(dg, do, K_RTOL, "d")
-    close(TO.solver_state(g)["dV"], TO.solver_state(o)["dV"], K_RTOL, "dV")
-    Jg, ag = TO.forward(g); Jo, ao = TO.forward(o)
-    assert np.array_equal(ag, ao), "accepted step sizes differ"
-    close(Jg, Jo, F_RTOL, "merit after the forward pass")
-    close(TO.states(g), TO.states(o), F_RTOL, "X after the forward pass")
-    close(TO.controls(g), TO.controls(o), F_RTOL, "U after the forward pass")
-    for p in (g, o):
+    check("rollout X", TO.states(g), TO.states(o), TO.states(t), ROLLOUT_TOL)
+    AB = (lambda p: TO.error_dynamics(p)) if g.error_state else (lambda p: TO.dynamics_jacobians(p))
+    check("[A B]", AB(g), AB(o), AB(t), ROLLOUT_TOL)
+    sg, so, st_ = TO.backward(g), TO.backward(o), TO.backward(t)
+    decisions_agree("regularisation restarts", sg, so, st_)
+    same = (so == st_)                                    # instances whose two oracle forms took the same restarts
+    (Kg, dg), (Ko, do), (Kt, dt) = TO.gains(g), TO.gains(o), TO.gains(t)
+    # like with like: tight, no twin allowance (an instance that restarts differently in the twin is still compared)
+    check("K", Kg, Ko, Ko, K_TOL); check("d", dg, do, do, K_TOL)
+    check("dV", TO.solver_state(g)["dV"], TO.solver_state(o)["dV"], TO.solver_state(o)["dV"], K_TOL)
+    (Jg, ag), (Jo, ao), (Jt, at) = TO.forward(g), TO.forward(o), TO.forward(t)
+    decisions_agree("accepted step sizes", ag, ao, at, same)
+    ok = same & (ao == at)
+    check("merit after the forward pass", Jg, Jo, Jt, F_TOL, ok)
+    check("X after the forward pass", TO.states(g), TO.states(o), TO.states(t), F_TOL, ok)
+    check("U after the forward pass", TO.controls(g), TO.controls(o), TO.controls(t), F_TOL, ok)
+    for p in probs:
         TO.ilqr_step(p, 2)
         if len(p.constraints):
             TO.al_update(p)
             TO.ilqr_step(p, 2)
-    stg, sto = TO.solver_state(g), TO.solver_state(o)
+    stg, sto, stt = TO.solver_state(g), TO.solver_state(o), TO.solver_state(t)
     # an instance that has converged takes its discrete decisions on the last bits of J (test_gpu_parity.py)
     live = np.abs(sto["dV"][:, 0]) > 1e-9 * np.maximum(1.0, np.abs(TO.merit(o)))
     assert live.mean() > 0.5
-    for key in ("alpha", "ls_iters", "bp_status"):
-        assert np.array_equal(stg[key][live], sto[key][live]), key
-    close(stg["rho"][live], sto["rho"][live], 1e-12, "rho")
-    close(TO.merit(g)[live], TO.merit(o)[live], ITER_RTOL, "merit after the iterations")
-    close(TO.states(g)[live], TO.states(o)[live], ITER_RTOL, "X after the iterations")
-    close(TO.controls(g)[live], TO.controls(o)[live], ITER_RTOL, "U after the iterations")
+    # a different discrete decision anywhere along the way (one more restart, one more halving of the step) sends the twins to different
+    # iterates: compare the instances whose twins ended with the same last decisions, the others are counted
+    dec = live & (sto["alpha"] == stt["alpha"]) & (sto["bp_status"] == stt["bp_status"])
+    e_x, d_x = check("X after the iterations", TO.states(g), TO.states(o), TO.states(t), ITER_TOL, dec)
+    check("U after the iterations", TO.controls(g), TO.controls(o), TO.controls(t), ITER_TOL, dec)
+    check("merit after the iterations", TO.merit(g), TO.merit(o), TO.merit(t), ITER_TOL, dec)
     for i in range(len(g.constraints)):
-        close(TO.multipliers(g, i)[live], TO.multipliers(o, i)[live], ITER_RTOL, f"multipliers {i}")
-    g.close(); o.close()
+        check(f"multipliers {i}", TO.multipliers(g, i), TO.multipliers(o, i), TO.multipliers(t, i), ITER_TOL, dec)
+    print(f"{name}: decidable instances {dec.mean():.3f}, worst X error {e_x:.2e} (twin divergence up to {d_x:.2e})")
+    for p in probs:
+        p.close()

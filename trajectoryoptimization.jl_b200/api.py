@@ -1459,6 +1459,13 @@ def set_penalty(prob, con, mu):
     prob._call("to_set_penalty", _con_index(prob, con), float(mu))
 
 
+def backward_algebra(prob):
+    """0 / 1: which of the two mathematically identical arithmetic forms the next backward pass uses (``to_backward_algebra``)"""
+    v = C.c_int32()
+    prob._call("to_backward_algebra", C.byref(v))
+    return int(v.value)
+
+
 def solver_state(prob):
     B = prob.B
     rho, dV, alpha = np.empty(B), np.empty((B, 2)), np.empty(B)

@@ -958,6 +958,11 @@ int to_get_gains(to_handle* h, double* K, double* d) {
     return TO_OK;
 }
 // ---- Lie-group error state (lie.cu) ---------------------------------------------------------------------------
+int to_backward_algebra(const to_handle* h, int32_t* variant) {
+    if (!h || !variant) return TO_EINVAL;
+    *variant = (h->P.frag && h->P.opt.pad != 3 && h->P.opt.pad != 5) ? 1 : 0;
+    return TO_OK;
+}
 int to_error_state_dim(const to_handle* h, int32_t* ne) {
     if (!h || !ne) return TO_EINVAL;
     *ne = h->P.ne;

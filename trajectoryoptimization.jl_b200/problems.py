@@ -60,7 +60,7 @@ def cartpole(B=1024, N=101, seed=1, cls=None, u_bound=None, goal=False, dt_scale
     return prob
 
 
-def quadrotor(B=4096, N=101, seed=1, cls=None, constrained=True, dt=None, dense_cost=False, **kw):
+def quadrotor(B=4096, N=101, seed=1, cls=None, constrained=True, dt=None, dense_cost=False, u_noise=0.05, **kw):
     """Quadrotor point-to-point, test/internal_api.jl:20-34: Q=.1 I, R=.01 I, Qf=100 I, x0=[1,2,1;1,0,0,0;0;0],
     xf=[0,0,2;1,0,0,0;0;0], u in [0,10] at 1..N-1, Goal(xf) at N, tf=5; U0 = hover + N(0,0.05^2);
     batch: r0_b = r0 + U(-1,1)^3.  ``dt`` fixes the step (MPC sweep: dt = .05 for every N)."""
@@ -85,7 +85,7 @@ def quadrotor(B=4096, N=101, seed=1, cls=None, constrained=True, dt=None, dense_
     x0b = np.broadcast_to(x0, (B, n)).copy()
     if B > 1:
         x0b[:, :3] += r.uniform(-1, 1, (B, 3))
-    U0 = model.hover_control()[None, None, :] + 0.05 * r.standard_normal((B, N - 1, m))
+    U0 = model.hover_control()[None, None, :] + u_noise * r.standard_normal((B, N - 1, m))
     tf = 5.0 if dt is None else dt * (N - 1)
     prob = cls(model, obj, x0b, tf, xf=xf, constraints=cons, **kw)
     TO.initial_controls(prob, U0)

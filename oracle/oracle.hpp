@@ -525,9 +525,14 @@ struct Options {
     double dual_max = 1e8;
     // 0: Cholesky solve + the long form of the cost-to-go update (below).  1 (m = 4 only): the ALGEBRA of the register-resident GPU
     // kernel (csrc/riccati_frag.cu) in plain loops -- (Quu + rho I)^-1 by 2 x 2 block elimination, K = -Minv Qux, W = (I + rho Minv) Qux,
-    // S <- Qxx + W'K unsymmetrised, s <- Qx + K'w_d, dV2 = -(dV1 + rho d'd)/2.  Mathematically identical; the two differ by rounding only,
+    // S <- sym(Qxx + W'K), s <- Qx + K'w_d, dV2 = -(dV1 + rho d'd)/2.  Mathematically identical; the two differ by rounding only,
     // which the Riccati recursion of an ill-conditioned trajectory amplifies (tests/test_oracle_variants.py measures by how much).
     int backward_variant = 0;
+    // test instrument: after a successful backward pass multiply every gain K, d by (1 + gain_noise * u), u in (-1, 1) deterministic in
+    // (instance, entry, pass).  A problem run with gain_noise = the kernel tolerance is the yardstick for what a backward pass that is accurate
+    // to that tolerance may do to the iterates downstream (tests/parity_util.py): the closed loop amplifies it by orders of magnitude.
+    double gain_noise = 0.0;
+    unsigned noise_epoch = 0;
 };
 
 struct Problem {
@@ -962,7 +967,8 @@ inline int backward_pass(Problem& P, int b) {
                     for (int r = 0; r < m; r++) t = std::fma(wd[r], Kk[j * m + r], t);
                     sn[j] = t;
                 }
-                for (int j = 0; j < n; j++) { s[j] = sn[j]; for (int i = 0; i < n; i++) S[j * n + i] = Sn[j * n + i]; }
+                // (the antisymmetric part of S is an unstable mode of the recursion: every implementation has to remove it)
+                for (int j = 0; j < n; j++) { s[j] = sn[j]; for (int i = 0; i < n; i++) S[j * n + i] = 0.5 * (Sn[j * n + i] + Sn[i * n + j]); }
                 for (int i = 0; i < m; i++) { dV1 = std::fma(dk[i], Qz[n + i], dV1); dV2 = std::fma(dk[i], dk[i], dV2); }   // dV2 holds sum d'd until the end
                 continue;
             }
@@ -1028,6 +1034,16 @@ inline int backward_pass(Problem& P, int b) {
         reg_increase(P.opts, P.rho[b], P.drho[b]);
         restarts++;
         if (P.rho[b] > P.opts.bp_reg_max) { P.bp_status[b] = -1; return -1; }
+    }
+    if (P.opts.gain_noise > 0.0) {
+        auto unit = [&](unsigned long long i) {     // splitmix64 -> (-1, 1)
+            unsigned long long z = i + 0x9E3779B97F4A7C15ULL * (1ULL + P.opts.noise_epoch) + ((unsigned long long)b << 32);
+            z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL; z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL; z ^= z >> 31;
+            return (double)(z >> 11) * (2.0 / 9007199254740992.0) - 1.0;
+        };
+        const size_t nk = (size_t)(N - 1) * m * n, nd = (size_t)(N - 1) * m;
+        for (size_t i = 0; i < nk; i++) Kall[i] *= 1.0 + P.opts.gain_noise * unit(i);
+        for (size_t i = 0; i < nd; i++) dall[i] *= 1.0 + P.opts.gain_noise * unit(nk + i);
     }
     reg_decrease(P.opts, P.rho[b], P.drho[b]);
     P.bp_status[b] = restarts;
@@ -1101,6 +1117,7 @@ inline void ensure_merit(Problem& P) {
 inline void ilqr_step(Problem& P, int iters) {
     ensure_merit(P);
     for (int it = 0; it < iters; it++) {
+        P.opts.noise_epoch++;
 #pragma omp parallel for schedule(dynamic, 4)
         for (int b = 0; b < P.B; b++) {
             expand_dynamics(P, b);

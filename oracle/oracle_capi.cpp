@@ -209,6 +209,8 @@ int orc_set_backward_variant(orc_handle* h, int v) {
     h->P.opts.backward_variant = v;
     return TO_OK;
 }
+// test instrument (oracle.hpp Options::gain_noise): relative perturbation of the gains after every backward pass
+int orc_set_gain_noise(orc_handle* h, double rel) { h->P.opts.gain_noise = rel; return TO_OK; }
 int orc_get_backward_variant(orc_handle* h) { return h->P.opts.backward_variant; }
 int orc_set_threads(int nthreads) { omp_set_num_threads(nthreads > 0 ? nthreads : omp_get_num_procs()); return omp_get_max_threads(); }
 
@@ -392,6 +394,7 @@ int orc_hess_projection(int cone, int p, int count, const double* x, const doubl
 
 int orc_backward(orc_handle* h, int32_t* status) {
     Problem& P = h->P;
+    P.opts.noise_epoch++;
 #pragma omp parallel for schedule(dynamic, 4)
     for (int b = 0; b < P.B; b++) backward_pass(P, b);
     if (status) for (int b = 0; b < P.B; b++) status[b] = P.bp_status[b];

@@ -95,7 +95,17 @@ def terminal_state(HN, gN, junk=0.37):
     return frag_from_matrix(Sh)
 
 
-def knot(Sacc, AB, H, g, rho):
+def tile_transpose(X):
+    """the 4-shuffle transposition of an 8 x 8 tile in D-fragment form (csrc/riccati_frag.cu tile_transpose)"""
+    Y = np.zeros((32, 2))
+    for L, fr, fc in lanes():
+        src = 8 * fc + (fr >> 1)
+        a, b = X[src], X[src + 4]
+        Y[L, 0] = a[fr & 1]; Y[L, 1] = b[fr & 1]
+    return Y
+
+
+def knot(Sacc, AB, H, g, rho, symmetrise_diag=True):
     """One backward step in fragment form.  Sacc: fragments of Shat_{k+1}; AB 12 x 16, H 16 x 16, g 16 (logical z order).
     Returns (Sacc', K 4 x 12, d 4, dV1 term d'Qu, sum d^2, ok)."""
     abf = ab_fragments(AB)
@@ -110,11 +120,11 @@ def knot(Sacc, AB, H, g, rho):
                 dmma(Tacc[mi, nj], abf[ks, mi], Sacc[nj, ni, :, reg])
     # phase 2: Qhat[i][c] = Hhat + sum_r ABp[r][i] T'[c][r]
     Qacc = Hacc.copy()
-    for mi in range(2):
-        for nc in range(2):
-            for ks in range(3):
-                ni, reg = KS_TILE[ks]
-                dmma(Qacc[mi, nc], abf[ks, mi], Tacc[nc, ni, :, reg])
+    Qacc[0, 1] = np.nan                                # tile (0,1) is never computed nor used
+    for mi, nc in ((0, 0), (1, 0), (1, 1)):
+        for ks in range(3):
+            ni, reg = KS_TILE[ks]
+            dmma(Qacc[mi, nc], abf[ks, mi], Tacc[nc, ni, :, reg])
     # Qz in column form: lane (fr, 0) holds (AB's)[8mi+fr] in Tacc[mi][0][.][0]
     qz_col = np.zeros((2, 32))
     for mi in range(2):
@@ -157,17 +167,23 @@ def knot(Sacc, AB, H, g, rho):
                 K[fc, PHYS_X.index(p)] = kf[mi, L]
             if p == 0:
                 d[fc] = kf[mi, L]; Qu[fc] = qz_col[0, 8 * fc]
-    # phase 4: row 0 of the accumulators <- Qz (row form, needs the column -> row transposition), then S' = Q + W'K
-    for nj in range(2):
-        for L, fr, fc in lanes():
-            if fr == 0:
-                for r in range(2):
-                    c = 8 * nj + 2 * fc + r
-                    Qacc[0, nj, L, r] = qz_col[c >> 3, 4 * (c & 7)]     # from lane (c & 7, 0)
-    Snew = Qacc.copy()
+    # phase 4: column 0 <- Qz (column form, in place), row 0 of tile (0,0) <- Qz (two shuffles), S' = Q + W'K on three tiles,
+    # tile (0,1) = transpose of tile (1,0) (its row 0 is then s' for p = 8..15), diagonal tiles averaged with their transposes
     for mi in range(2):
-        for nj in range(2):
-            dmma(Snew[mi, nj], wf[mi], kf[nj])
+        for L, fr, fc in lanes():
+            if fc == 0:
+                Qacc[mi, 0, L, 0] = qz_col[mi, L]
+    for L, fr, fc in lanes():
+        if fr == 0:
+            for r in range(2):
+                Qacc[0, 0, L, r] = qz_col[0, 4 * (2 * fc + r)]           # from lane (2fc + r, 0)
+    Snew = Qacc.copy()
+    for mi, nj in ((0, 0), (1, 0), (1, 1)):
+        dmma(Snew[mi, nj], wf[mi], kf[nj])
+    Snew[0, 1] = tile_transpose(Snew[1, 0])
+    if symmetrise_diag:
+        for t in (0, 1):
+            Snew[t, t] = 0.5 * (Snew[t, t] + tile_transpose(Snew[t, t]))
     return Snew, K, d, float(d @ Qu), float(d @ d), ok
 
 
@@ -180,5 +196,6 @@ def dense_reference(S, s, AB, H, g, rho):
     K = -np.linalg.solve(Mr, Qux); d = -np.linalg.solve(Mr, Qu)
     W = Qux - rho * K
     Sn = Q[:12, :12] + W.T @ K
+    Sn = 0.5 * (Sn + Sn.T)
     sn = qz[:12] + W.T @ d
     return Sn, sn, K, d, float(d @ Qu), float(0.5 * d @ Quu @ d)

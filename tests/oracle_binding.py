@@ -65,6 +65,12 @@ class OracleProblem(TO.Problem):
         assert self._lib.orc_set_backward_variant(self._h, int(v)) == 0
         return self
 
+    def set_gain_noise(self, rel):
+        """test instrument (oracle.hpp Options::gain_noise): every backward pass returns gains perturbed by the relative amount `rel`"""
+        self._lib.orc_set_gain_noise.argtypes = [C.c_void_p, C.c_double]
+        assert self._lib.orc_set_gain_noise(self._h, float(rel)) == 0
+        return self
+
     def set_integrator(self, order):
         assert self._lib.orc_set_integrator(self._h, int(order)) == 0
         return self

@@ -1,24 +1,24 @@
 """Conditioning-aware GPU-vs-oracle comparison (test infrastructure).
 
-Why: the Riccati recursion and the closed-loop rollouts of the BASELINE Quadrotor problem amplify rounding differences by several
-orders of magnitude per stage (cheap controls R = 0.01 against Qf = 100: the cost-to-go update is a Schur complement with heavy
-cancellation; the open-loop initial guess tumbles).  Two CPU evaluations of the SAME mathematics in fp64 -- the oracle's two
-arithmetic forms of the backward pass, oracle.hpp Options::backward_variant -- already differ by 1e-7 in the gains and 1e-3 in
-the trajectory after one forward pass on that problem, while on Cartpole / Acrobot everything agrees to 1e-11 after six iterations
-(profiles/r02_notes.md).  So every comparison is made twice:
+Why: the closed loop of the BASELINE Quadrotor problem amplifies rounding differences by orders of magnitude per stage (cheap controls
+R = 0.01 against Qf = 100, a 5 s horizon whose open-loop initial guess tumbles): a relative difference of 1e-11 in the gains of one
+backward pass is 1e-7 in the trajectory after the forward pass and O(1e-2) three iterations later, for ANY two fp64 implementations
+(profiles/r02_notes.md has the measurements; Cartpole / Acrobot agree to 1e-11 after six iterations).  So:
 
-  * like with like: the oracle runs the arithmetic form the CUDA kernel uses (oracle_binding.match_algebra) -- this is the parity
-    statement, at kernel tolerance;
-  * against the TWIN (the oracle in the other form): the per-instance divergence D_b of the two oracle runs is the intrinsic fp64
-    uncertainty of instance b at that stage; after closed-loop iterations the CUDA result has to stay inside FACTOR x D_b (or the
-    tight tolerance, whichever is larger).  Discrete decisions (step size, restarts) are compared where the twins agree on them.
-"""
+  * ONE kernel application on identical inputs is compared with the oracle at kernel tolerance, the oracle running the arithmetic
+    form of the backward pass that the CUDA kernel uses (oracle_binding.match_algebra; the two forms themselves agree to 1e-11);
+  * everything DOWNSTREAM of a backward pass is compared against a yardstick: the TWIN, the same oracle whose backward passes return
+    gains perturbed by the relative amount GAIN_TOL (= the kernel tolerance of the gains; oracle.hpp Options::gain_noise).  The
+    divergence D_b of twin and oracle on instance b is what a backward pass that is accurate to GAIN_TOL may do to that instance; the CUDA
+    result has to stay within FACTOR x D_b (or the tight tolerance, whichever is larger).  Discrete decisions (step sizes, restarts)
+    are compared on the instances where the perturbation does not flip them in the twin."""
 import numpy as np
 
 import trajopt_b200 as TO
 from oracle_binding import OracleProblem, match_algebra
 
-FACTOR = 20.0
+GAIN_TOL = 2e-9     # kernel tolerance of K, d (measured: 4e-11 full-state kernel, 1.4e-9 register-resident kernel on random attitudes)
+FACTOR = 5.0
 
 
 def inst_err(a, b):
@@ -32,12 +32,12 @@ def inst_err(a, b):
 
 
 def triple(build, opts=None):
-    """(cuda problem, oracle in the same arithmetic form, oracle twin in the other form)"""
+    """(cuda problem, oracle in the same arithmetic form, twin = that oracle with GAIN_TOL noise on the gains of every backward pass)"""
     g = build(TO.Problem)
     if opts:
         TO.set_options(g, **opts)
     o = match_algebra(g, build(OracleProblem))
-    t = build(OracleProblem).set_backward_variant(1 - TO.backward_algebra(g))
+    t = match_algebra(g, build(OracleProblem)).set_gain_noise(GAIN_TOL)
     return g, o, t
 
 
@@ -53,11 +53,13 @@ def check(what, a_gpu, a_orc, a_twin, tight, sel=None):
     return float(e.max()) if e.size else 0.0, float(d.max()) if d.size else 0.0
 
 
-def decisions_agree(what, v_gpu, v_orc, v_twin, sel=None):
-    """discrete per-instance results are compared where the two oracle forms agree on them"""
+def decisions_agree(what, v_gpu, v_orc, v_twin, sel=None, allow=0.0):
+    """discrete per-instance results are compared where the perturbed twin takes the oracle's decision; `allow`: tolerated fraction of
+    mismatches among those (a decision that sits within the GAIN_TOL band of its threshold for the cuda run but not for the twin's noise draw)"""
     v_gpu, v_orc, v_twin = np.asarray(v_gpu), np.asarray(v_orc), np.asarray(v_twin)
     m = (v_orc == v_twin)
     if sel is not None:
         m &= sel
-    assert np.array_equal(v_gpu[m], v_orc[m]), f"{what}: {int(np.sum(v_gpu[m] != v_orc[m]))} mismatches among {int(m.sum())} decidable instances"
-    return float(m.mean())
+    bad = int(np.sum(v_gpu[m] != v_orc[m]))
+    assert bad <= allow * max(1, int(m.sum())), f"{what}: {bad} mismatches among {int(m.sum())} decidable instances"
+    return m & (v_gpu == v_orc)

@@ -23,7 +23,9 @@ def test_fragment_recursion_matches_dense_recursion():
         AB = 0.4 * rng.standard_normal((12, 16))
         H = np.diag(rng.uniform(0.1, 1, 16)); blk = rng.standard_normal((3, 3)); H[3:6, 3:6] += blk @ blk.T
         g = rng.standard_normal(16)
-        Sacc, K, d, t1, t2, ok = FE.knot(Sacc, AB, H, g, rho)
+        Sacc, K, d, t1, t2, ok = FE.knot(Sacc, AB, H, g, rho, symmetrise_diag=(k % 4 == 0))
+        Ssym = FE.matrix_from_frag(Sacc)
+        assert np.array_equal(Ssym[:8, 8:], Ssym[8:, :8].T)                # the off-diagonal tiles are exact mirrors
         S, s, Kr, dr, r1, r2 = FE.dense_reference(S, s, AB, H, g, rho)
         Sh = FE.matrix_from_frag(Sacc)
         Sf = np.array([[Sh[FE.PHYS_X[e], FE.PHYS_X[f]] for f in range(12)] for e in range(12)])
@@ -31,6 +33,8 @@ def test_fragment_recursion_matches_dense_recursion():
         scale = np.abs(S).max()
         assert ok
         assert np.abs(Sf - S).max() < 1e-12 * scale and np.abs(sf - s).max() < 1e-12 * scale
+        sc = np.array([Sh[FE.PHYS_X[e], 0] for e in range(12)])            # column 0 carries s as well (s = Qx + W'd)
+        assert np.abs(sc - s).max() < 1e-12 * scale
         assert np.abs(K - Kr).max() < 1e-12 * max(1, np.abs(Kr).max()) and np.abs(d - dr).max() < 1e-12 * max(1, np.abs(dr).max())
         assert abs(t1 - r1) < 1e-12 * max(1, abs(r1)) and abs(-0.5 * (t1 + rho * t2) - r2) < 1e-12 * max(1, abs(r2))
 

@@ -5,21 +5,21 @@ of the batch, every knot, gains / expected decrease / step sizes / regularisatio
 oracle on the same seeded inputs.  More instances than resident warps (4096 > 148 x 16 or 148 x 28) exercises the atomic work
 queues of the persistent Riccati kernels, which the small batches cannot.
 
-Tolerances (parity_util.py): one kernel application on identical inputs agrees with the oracle in the same arithmetic
-form to KERNEL tolerance; after closed-loop iterations every instance has to stay within FACTOR x the divergence of the oracle's two
-arithmetic forms on that instance (its intrinsic fp64 uncertainty) -- Cartpole / Acrobot: that IS the tight tolerance (the twins
-agree to 1e-11); the tumbling Quadrotor instances: whatever the problem's conditioning leaves."""
+Tolerances (parity_util.py, DESIGN.md 4a): one kernel application on identical inputs agrees with the oracle to kernel tolerance;
+downstream of a backward pass every instance has to stay within FACTOR x what a relative perturbation of the gains by that kernel
+tolerance does to it in the oracle itself (the twin) -- Cartpole / Acrobot: that is the tight tolerance; the tumbling Quadrotor
+instances: whatever the closed loop's amplification leaves."""
 import numpy as np
 import pytest
 
 import trajopt_b200 as TO
-from parity_util import check, decisions_agree, triple
+from parity_util import GAIN_TOL, check, decisions_agree, triple
 
 pytestmark = pytest.mark.gpu
 P = TO.problems
 
 ROLLOUT_TOL = 1e-12  # rollout!, [A B]: no recursion, no amplification
-K_TOL = 2e-9         # gains / expected decrease of one backward pass, like with like (measured: 3.5e-11 full state, see profiles/r02_notes.md)
+K_TOL = GAIN_TOL     # gains / expected decrease of one backward pass, like with like (measured: 4e-11 full state, 1e-9 register-resident kernel)
 F_TOL = 1e-9         # one forward pass: only where the twins say the instance is that well conditioned
 ITER_TOL = 1e-8      # after the iterations: ditto
 
@@ -51,15 +51,13 @@ def test_full_size_elementwise(name):
     AB = (lambda p: TO.error_dynamics(p)) if g.error_state else (lambda p: TO.dynamics_jacobians(p))
     check("[A B]", AB(g), AB(o), AB(t), ROLLOUT_TOL)
     sg, so, st_ = TO.backward(g), TO.backward(o), TO.backward(t)
-    decisions_agree("regularisation restarts", sg, so, st_)
-    same = (so == st_)                                    # instances whose two oracle forms took the same restarts
-    (Kg, dg), (Ko, do), (Kt, dt) = TO.gains(g), TO.gains(o), TO.gains(t)
-    # like with like: tight, no twin allowance (an instance that restarts differently in the twin is still compared)
+    assert np.array_equal(sg, so), "regularisation restarts differ"
+    (Kg, dg), (Ko, do) = TO.gains(g), TO.gains(o)
+    # one kernel application on identical inputs: kernel tolerance, no allowance
     check("K", Kg, Ko, Ko, K_TOL); check("d", dg, do, do, K_TOL)
     check("dV", TO.solver_state(g)["dV"], TO.solver_state(o)["dV"], TO.solver_state(o)["dV"], K_TOL)
     (Jg, ag), (Jo, ao), (Jt, at) = TO.forward(g), TO.forward(o), TO.forward(t)
-    decisions_agree("accepted step sizes", ag, ao, at, same)
-    ok = same & (ao == at)
+    ok = decisions_agree("accepted step sizes", ag, ao, at, allow=2e-3)
     check("merit after the forward pass", Jg, Jo, Jt, F_TOL, ok)
     check("X after the forward pass", TO.states(g), TO.states(o), TO.states(t), F_TOL, ok)
     check("U after the forward pass", TO.controls(g), TO.controls(o), TO.controls(t), F_TOL, ok)
@@ -74,7 +72,8 @@ def test_full_size_elementwise(name):
     assert live.mean() > 0.5
     # a different discrete decision anywhere along the way (one more restart, one more halving of the step) sends the twins to different
     # iterates: compare the instances whose twins ended with the same last decisions, the others are counted
-    dec = live & (sto["alpha"] == stt["alpha"]) & (sto["bp_status"] == stt["bp_status"])
+    dec = live & ok & (sto["alpha"] == stt["alpha"]) & (sto["bp_status"] == stt["bp_status"]) & (stg["alpha"] == sto["alpha"]) & (stg["bp_status"] == sto["bp_status"])
+    assert dec.sum() > 0.5 * live.sum(), "too few instances with a common decision history"
     e_x, d_x = check("X after the iterations", TO.states(g), TO.states(o), TO.states(t), ITER_TOL, dec)
     check("U after the iterations", TO.controls(g), TO.controls(o), TO.controls(t), ITER_TOL, dec)
     check("merit after the iterations", TO.merit(g), TO.merit(o), TO.merit(t), ITER_TOL, dec)

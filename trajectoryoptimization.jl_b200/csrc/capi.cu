@@ -45,10 +45,13 @@ struct to_handle {
     double* d_viol = nullptr;     // [B]
     double* d_merit2 = nullptr;   // {sum J, max viol}
     int* d_work = nullptr;
+    int* d_fragq = nullptr;       // work queue of the register-resident Riccati kernel (riccati_frag.cu)
     int* d_err = nullptr;
     Scratch scratch;
     double t0 = 0;
     bool J_valid = false, expanded = false, backward_done = false;
+    bool rec_valid = false;       // record path: the cost + AL expansion written by k_expand_lie is current (nothing it depends on -- trajectory,
+                                  // multipliers, penalties, cost tables -- has changed since)
     int64_t launches = 0;
     // phase timing
     bool timing = false;
@@ -457,6 +460,7 @@ int to_create(const to_spec* s, to_handle** out) {
     ALLOC(P.bp_status, B); ALLOC(P.ls_iters, B); ALLOC(P.accepted, B); ALLOC(P.acc1, B);
     ALLOC(h->d_stageX, P.strideX); ALLOC(h->d_stageU, P.strideU); ALLOC(h->d_viol, B); ALLOC(h->d_merit2, 2);
     ALLOC(h->d_work, 1); ALLOC(h->d_err, 1);
+    if (P.frag) ALLOC(h->d_fragq, frag_queue_ints(B));
 #undef ALLOC
     if (rc) return bail(rc);
     P.dt = d_dt; P.cost_index = d_ci; P.costs = h->d_costs; P.cons = h->d_cons; P.mu = h->d_mu; P.viol = h->d_viol;
@@ -530,7 +534,7 @@ int to_set_options(to_handle* h, const to_options* o) {
         CU(h, cudaMemsetAsync(h->P.drho, 0, sizeof(double) * h->P.B, h->stream));
         CU(h, cudaStreamSynchronize(h->stream));     // `r` goes out of scope
     }
-    h->J_valid = false;
+    h->J_valid = false; h->rec_valid = false;
     return upload_tables(h);
 }
 
@@ -591,7 +595,7 @@ int to_set_initial_state(to_handle* h, const double* x0) {
     JOIN(h);
     if (!h || !x0) return TO_EINVAL;
     CU(h, cudaMemcpyAsync(h->P.x0, x0, sizeof(double) * (size_t)h->P.B * h->P.n, cudaMemcpyHostToDevice, h->stream));
-    h->J_valid = false;
+    h->J_valid = false; h->rec_valid = false;
     return TO_OK;
 }
 int to_set_controls(to_handle* h, const double* U) {
@@ -599,7 +603,7 @@ int to_set_controls(to_handle* h, const double* U) {
     if (!h || !U) return TO_EINVAL;
     CU(h, cudaMemcpyAsync(h->d_stageU, U, sizeof(double) * h->P.strideU, cudaMemcpyHostToDevice, h->stream));
     CU(h, launch_scatter_traj(h->P, nullptr, h->d_stageU, h->stream)); h->launches++;
-    h->J_valid = false; h->expanded = false; h->backward_done = false;
+    h->J_valid = false; h->rec_valid = false; h->expanded = false; h->backward_done = false;
     return TO_OK;
 }
 int to_set_states(to_handle* h, const double* X) {
@@ -607,7 +611,7 @@ int to_set_states(to_handle* h, const double* X) {
     if (!h || !X) return TO_EINVAL;
     CU(h, cudaMemcpyAsync(h->d_stageX, X, sizeof(double) * h->P.strideX, cudaMemcpyHostToDevice, h->stream));
     CU(h, launch_scatter_traj(h->P, h->d_stageX, nullptr, h->stream)); h->launches++;
-    h->J_valid = false; h->expanded = false; h->backward_done = false;
+    h->J_valid = false; h->rec_valid = false; h->expanded = false; h->backward_done = false;
     return TO_OK;
 }
 int to_get_states(to_handle* h, double* X) {
@@ -651,7 +655,7 @@ int to_set_goal_state(to_handle* h, const double* xf, int objective, int constra
     if (constraint)
         for (auto& c : h->h_cons)
             if (c.kind == CON_GOAL) for (int i = 0; i < c.p; i++) c.a[i] = xf[c.inds[i]];
-    h->J_valid = false;
+    h->J_valid = false; h->rec_valid = false;
     return upload_tables(h);
 }
 
@@ -668,7 +672,7 @@ int to_update_trajectory(to_handle* h, const double* Xref, const double* Uref, i
         for (int a = 0; a < n; a++) { double t = 0; for (int j = 0; j < n; j++) t += c.Q[j * n + a] * xf[j]; c.q[a] = -t; }
         for (int a = 0; a < m; a++) { double t = 0; for (int j = 0; j < m; j++) t += c.R[j * m + a] * uf[j]; c.r[a] = -t; }
     }
-    h->J_valid = false; h->expanded = false; h->backward_done = false;
+    h->J_valid = false; h->rec_valid = false; h->expanded = false; h->backward_done = false;
     return upload_tables(h);
 }
 int to_shift_trajectory(to_handle* h, int32_t steps) {
@@ -678,14 +682,14 @@ int to_shift_trajectory(to_handle* h, int32_t steps) {
     if (steps > h->P.N - 1) steps = h->P.N - 1;
     CU(h, launch_shift_traj(h->P, steps, h->stream)); h->launches++;
     for (int k = 0; k < steps; k++) h->t0 += h->h_dt[k];
-    h->J_valid = false; h->expanded = false; h->backward_done = false;
+    h->J_valid = false; h->rec_valid = false; h->expanded = false; h->backward_done = false;
     return TO_OK;
 }
 int to_rollout(to_handle* h) {
     JOIN(h);
     if (!h) return TO_EINVAL;
     CU(h, launch_rollout(h->P, h->stream)); h->launches++;
-    h->J_valid = false; h->expanded = false; h->backward_done = false;
+    h->J_valid = false; h->rec_valid = false; h->expanded = false; h->backward_done = false;
     return TO_OK;
 }
 int to_expand(to_handle* h) {
@@ -694,6 +698,7 @@ int to_expand(to_handle* h) {
     { PhaseScope ps(h, TO_PHASE_EXPAND); CU(h, launch_expand(h->P, h->stream)); if (h->P.lie) { CU(h, launch_expand_lie(h->P, h->stream)); h->launches++; } }
     h->launches++; h->phase_launches[TO_PHASE_EXPAND]++;
     h->expanded = true; h->backward_done = false;
+    h->rec_valid = h->P.frag != 0;        // k_expand_lie wrote the records' cost + AL expansion too
     return TO_OK;
 }
 int to_get_dynamics_jacobians(to_handle* h, double* AB) {
@@ -847,10 +852,13 @@ static int materialise_expansion(to_handle* h, double* EG, double* EH) {
 static int do_backward(to_handle* h) {
     // to_options.backward_kernel: 0 automatic, 3 generic DFMA kernel on the full expansion, 5 shared-memory tensor kernel on the compact expansion
     if (h->P.frag && h->P.opt.pad != 3 && h->P.opt.pad != 5) {
-        { PhaseScope pe(h, TO_PHASE_COSTEXP); CU(h, launch_expansion_rec(h->P, h->stream)); }
-        h->launches++; h->phase_launches[TO_PHASE_COSTEXP]++;
+        if (!h->rec_valid) {      // normally written by the dynamics expansion kernel; stale after to_al_update / to_set_multipliers / ... without a new to_expand
+            { PhaseScope pe(h, TO_PHASE_COSTEXP); CU(h, launch_expansion_rec(h->P, h->stream)); }
+            h->launches++; h->phase_launches[TO_PHASE_COSTEXP]++;
+            h->rec_valid = true;
+        }
         PhaseScope ps(h, TO_PHASE_BACKWARD);
-        CU(h, launch_backward_frag(h->P, h->d_work, h->stream));
+        CU(h, launch_backward_frag(h->P, h->d_fragq, h->stream));
     } else if (h->P.dense_riccati) {
         PhaseScope ps(h, TO_PHASE_BACKWARD);
         if (h->P.frag) { CU(h, launch_export_abe(h->P, h->stream)); h->launches++; }     // the shared-memory kernels read P.ABe
@@ -873,7 +881,7 @@ static int do_forward(to_handle* h) {
     { PhaseScope ps(h, TO_PHASE_LADDER); CU(h, launch_ladder(h->P, h->stream)); }     // remaining trials + commit of failures
     h->launches++; h->phase_launches[TO_PHASE_LADDER]++;
 
-    h->expanded = false; h->backward_done = false;   // the trajectory moved
+    h->expanded = false; h->backward_done = false; h->rec_valid = false;   // the trajectory moved
     return TO_OK;
 }
 int to_backward(to_handle* h, int32_t* status) {
@@ -922,6 +930,7 @@ int to_ilqr_step(to_handle* h, int32_t iters) {
         h->launches++; h->phase_launches[TO_PHASE_EXPAND]++;
         JOIN(h);
         h->expanded = true;
+        h->rec_valid = h->P.frag != 0;
         rc = do_backward(h); if (rc) return rc;
         { PhaseScope ps(h, TO_PHASE_FORWARD); CU(h, launch_forward(h->P, h->stream)); }
         h->launches++; h->phase_launches[TO_PHASE_FORWARD]++;
@@ -935,7 +944,7 @@ int to_ilqr_step(to_handle* h, int32_t iters) {
             PhaseScope ps(h, TO_PHASE_LADDER); CU(h, launch_ladder(h->P, h->stream));
         }
         h->launches++; h->phase_launches[TO_PHASE_LADDER]++;
-        h->expanded = false; h->backward_done = false;   // the trajectory moved
+        h->expanded = false; h->backward_done = false; h->rec_valid = false;   // the trajectory moved
     }
     return TO_OK;
 }
@@ -946,7 +955,7 @@ int to_al_update(to_handle* h) {
     for (auto& mu : h->h_mu) mu = std::fmin(mu * h->P.opt.penalty_scaling, h->P.opt.penalty_max);
     if (!h->h_mu.empty()) CU(h, cudaMemcpyAsync(h->d_mu, h->h_mu.data(), sizeof(double) * h->h_mu.size(), cudaMemcpyHostToDevice, h->stream));
     CU(h, cudaStreamSynchronize(h->stream));
-    h->J_valid = false;
+    h->J_valid = false; h->rec_valid = false;
     return TO_OK;
 }
 int to_get_gains(to_handle* h, double* K, double* d) {
@@ -1013,7 +1022,7 @@ static int multipliers_copy(to_handle* h, int32_t con, double* host, bool to_hos
         CU(h, cudaMemcpy2DAsync(host, len * sizeof(double), h->P.lambda + c.offset, (size_t)h->P.lambda_len * sizeof(double), len * sizeof(double), h->P.B, cudaMemcpyDeviceToHost, h->stream));
     } else {
         CU(h, cudaMemcpy2DAsync(h->P.lambda + c.offset, (size_t)h->P.lambda_len * sizeof(double), host, len * sizeof(double), len * sizeof(double), h->P.B, cudaMemcpyHostToDevice, h->stream));
-        h->J_valid = false;
+        h->J_valid = false; h->rec_valid = false;
     }
     CU(h, cudaStreamSynchronize(h->stream));
     return TO_OK;
@@ -1032,7 +1041,7 @@ int to_set_penalty(to_handle* h, int32_t con, double mu) {
     h->h_mu[con] = mu;
     CU(h, cudaMemcpyAsync(h->d_mu, h->h_mu.data(), sizeof(double) * h->h_mu.size(), cudaMemcpyHostToDevice, h->stream));
     CU(h, cudaStreamSynchronize(h->stream));
-    h->J_valid = false;
+    h->J_valid = false; h->rec_valid = false;
     return TO_OK;
 }
 int to_get_solver_state(to_handle* h, double* rho, double* dV, double* alpha, int32_t* ls_iters, int32_t* bp_status) {

@@ -36,7 +36,8 @@ cudaError_t launch_expand_lie(const DevProblem& P, cudaStream_t s, int mode = 0)
 // register-resident Riccati pass of the error-state Quadrotor + its record producers   (riccati_frag.cu)
 cudaError_t launch_expansion_rec(const DevProblem& P, cudaStream_t s);                 // compact expansion -> REC[192..240) of every knot
 cudaError_t launch_export_abe(const DevProblem& P, cudaStream_t s);                    // REC fragments -> ABe (col-major 12 x 16)
-cudaError_t launch_backward_frag(const DevProblem& P, int* work_counter, cudaStream_t s);
+size_t frag_queue_ints(int B);                                                         // ints of the kernel's work queue (allocated by the handle)
+cudaError_t launch_backward_frag(const DevProblem& P, int* queue, cudaStream_t s);
 // forward pass: closed-loop rollout + merit + line search                     (forward.cu)
 cudaError_t launch_forward(const DevProblem& P, cudaStream_t s);
 cudaError_t launch_ladder(const DevProblem& P, cudaStream_t s);

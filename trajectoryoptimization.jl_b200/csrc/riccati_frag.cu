@@ -15,11 +15,13 @@
 //   * one warp per instance; z is held in the PHYSICAL order of frag_layout.cuh, chosen so that the D fragments of every
 //     mma.sync.m8n8k4.f64 (SASS DMMA) are exactly the A / B fragments of the next one:
 //        T' = [A B]' S^      12 DMMA   B operand = the S accumulators of the previous knot (s rides in row 0 of S^)
-//        Q^ = H^ + [A B]' T  12 DMMA   B operand = the T' accumulators; column 0 of T' is [A B]'s = Qz - lz for free
+//        Q^ = H^ + [A B]' T   9 DMMA   B operand = the T' accumulators; column 0 of T' is [A B]'s = Qz - lz for free; tiles (0,0),(1,0),(1,1)
 //        [K|W]' = Q^[:,u] [-Minv | I + rho Minv]   2 DMMA   A operand = register 0 of the Q^ tiles (u_a sits on p = 2a);
 //                                                  row 0 <- Qu gives d and w_d = Qu - rho d in the same product
-//        S^ <- Q^ + W'K      4 DMMA    A / B operands = the two result registers of the previous product (row 0 <- Qz gives s)
-//     30 DMMA per knot, S / T / Q never leave the register file; per knot the warp touches shared memory for the record
+//        S^ <- Q^ + W'K      3 DMMA    A / B operands = the two result registers of the previous product (row 0 / column 0 <- Qz give s);
+//                                      S^(0,1) = S^(1,0)' by 4 shuffles; the diagonal tiles are symmetrised every 4th knot (the antisymmetric
+//                                      part of S is an unstable mode of the recursion)
+//     26 DMMA per knot, S / T / Q never leave the register file; per knot the warp touches shared memory for the record
 //     (3 LDS.128 + 6 LDS.64), the 4 x 4 Quu (one STS, one LDS burst) and the 10 entries of its inverse.
 //   * (Quu + rho I)^-1 by 2 x 2 block elimination (two Newton reciprocals, 20-deep chain instead of the 47 of a scalar LDL'),
 //     evaluated by the lower half-warp only (an FP64 instruction of a half-empty warp takes one pipe pass);
@@ -69,6 +71,19 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
 __device__ __forceinline__ double2 lds128(const double* p) { return *reinterpret_cast<const double2*>(p); }
 __device__ __forceinline__ void dmma(double& d0, double& d1, double a, double b) {
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+__device__ __forceinline__ int ld_volatile_s32(const int* p) {
+    int v;
+    asm volatile("ld.volatile.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+// 8 x 8 tile held as D fragments (x0, x1) = X[fr][2fc], X[fr][2fc+1]  ->  its transpose in the same layout: Y[fr][2fc + r] = X[2fc + r][fr]
+// sits in lane (2fc + r, fr >> 1), register fr & 1.   src = 8 fc + (fr >> 1) = lane (2fc, fr >> 1).
+__device__ __forceinline__ void tile_transpose(double x0, double x1, int src, int odd_row, double& y0, double& y1) {
+    const double a0 = __shfl_sync(0xffffffffu, x0, src), a1 = __shfl_sync(0xffffffffu, x1, src);
+    const double b0 = __shfl_sync(0xffffffffu, x0, src + 4), b1 = __shfl_sync(0xffffffffu, x1, src + 4);
+    y0 = odd_row ? a1 : a0;
+    y1 = odd_row ? b1 : b0;
 }
 // 1/x for a positive finite x: hardware seed + two Newton steps (<= 1 ulp), no IEEE-division slow path on the pivot chain
 __device__ __forceinline__ double rcp_pos(double x) {
@@ -175,7 +190,7 @@ __device__ __forceinline__ int minv_slot(int i, int j) {   // slot of Minv[i][j]
 }
 
 template <int STAGES, int WARPS, int MINB>
-__global__ void __launch_bounds__(32 * WARPS, MINB) k_riccati_frag(const DevProblem P, int* __restrict__ work_counter) {
+__global__ void __launch_bounds__(32 * WARPS, MINB) k_riccati_frag(const DevProblem P, int* __restrict__ Qd) {
     using SM = FragSmem<STAGES, WARPS>;
     extern __shared__ __align__(128) unsigned char frag_smem_raw[];
     SM& sm = *reinterpret_cast<SM*>(frag_smem_raw);
@@ -195,6 +210,7 @@ __global__ void __launch_bounds__(32 * WARPS, MINB) k_riccati_frag(const DevProb
     const int eoff1 = fraglayout::e_of_p(8 + fr) * 4 + fc;                      // K[a = fc][e(p = 8 + fr)]
     const int mslot = minv_slot(fc, fr >> 1);                                     // this lane's entry Minv[fc][fr >> 1] of the B fragment
     const double bdelta = ((fr & 1) && fc == (fr >> 1)) ? 1.0 : 0.0;
+    const int tsrc = 8 * fc + (fr >> 1);          // lane (2 fc, fr >> 1): holder of the transposed entries of this lane's register 0 (register 1: + 4)
 
     if (lane == 0) {
 #pragma unroll
@@ -204,17 +220,46 @@ __global__ void __launch_bounds__(32 * WARPS, MINB) k_riccati_frag(const DevProb
     __syncwarp();
     uint32_t phase_bits = 0;
 
+    // ---- work queue (zero / 0xFF / 0x7F-initialised by the launcher) -------------------------------------------------------------------
+    //   Qd[0] head   next work index: indices < B are the first sweeps (instance = index), index B + q is slot q of the item list
+    //   Qd[1] tail   item slots handed out          Qd[2] nfinal  instances finalised          Qd[3] error flag (spin limit)
+    //   cnt[B]   candidates of the instance's current round still running     items[QCAP]  instance * 16 + candidate, -1 = not yet written
+    //   best[B]  lowest successful candidate of the round (0x7f7f7f7f = none)
+    // Regularisation ladder (Altro regularization_update!(:increase) after a failed sweep, restart from the terminal knot): the sequence
+    // rho_1, rho_2, ... an instance will try is a function of (rho_0, drho_0) alone, so after a failed first sweep the candidates are
+    // evaluated SPECULATIVELY IN PARALLEL by whichever warps are idle, in rounds {1}, {2,3}, {4..7}, {8..15}; the result is the lowest
+    // successful candidate = exactly what the sequential loop returns (it stops at its first success), in <= 5 sweep times instead of <= 14.
+    const int QCAP = 16 * P.B + 8192;
+    int* const q_head = Qd; int* const q_tail = Qd + 1; int* const q_nfinal = Qd + 2; int* const q_err = Qd + 3;
+    int* const q_cnt = Qd + 4; int* const q_items = q_cnt + P.B; int* const q_best = q_items + QCAP;
+
     for (;;) {
-        int b = 0;
-        if (lane == 0) b = atomicAdd(work_counter, 1);
-        b = __shfl_sync(0xffffffffu, b, 0);
-        if (b >= P.B) break;
+        int idx = 0;
+        if (lane == 0) idx = atomicAdd(q_head, 1);
+        idx = __shfl_sync(0xffffffffu, idx, 0);
+        int b, cand;
+        if (idx < P.B) { b = idx; cand = 0; }
+        else {
+            const int qi = idx - P.B;
+            int item = -2;
+            if (lane == 0) {
+                unsigned spins = 0;
+                for (;;) {
+                    item = (qi < QCAP) ? ld_volatile_s32(q_items + qi) : -1;
+                    if (item >= 0) break;
+                    if (ld_volatile_s32(q_nfinal) >= P.B) { item = -2; break; }      // every instance is finalised: nothing more will be queued
+                    __nanosleep(256);
+                    if (++spins > (1u << 22)) { atomicExch(q_err, 1); item = -2; break; }   // ~1 s: never hang the device
+                }
+            }
+            item = __shfl_sync(0xffffffffu, item, 0);
+            if (item < 0) break;
+            b = item >> 4; cand = item & 15;
+        }
         const double* recg = P.REC + (size_t)b * N * TO_REC_LEN;
         double* Kg = P.K + (size_t)b * (N - 1) * 48;
         double* dg = P.d + (size_t)b * (N - 1) * 4;
-        double rho = P.rho[b], drho = P.drho[b];
-        int restarts = 0;
-        bool failed = false;
+        const double rho0 = P.rho[b], drho0 = P.drho[b];
 
         auto issue = [&](int st, int k) {
             if (lane == 0) {
@@ -222,8 +267,16 @@ __global__ void __launch_bounds__(32 * WARPS, MINB) k_riccati_frag(const DevProb
                 bulk_g2s(ring + st * TO_REC_LEN, recg + (size_t)k * TO_REC_LEN, TO_REC_LEN * 8, &bar[st]);
             }
         };
-
-        for (;;) {   // regularisation restart loop
+        // (rho_j, drho_j): j applications of regularization_update!(:increase); returns the first i <= j whose rho exceeds bp_reg_max (the
+        // sequential loop gives up there) or 0
+        auto ladder = [&](int j, double& rho, double& drho) -> int {
+            rho = rho0; drho = drho0;
+            for (int i = 1; i <= j; i++) { reg_increase(P.opt, rho, drho); if (rho > P.opt.bp_reg_max) return i; }
+            return 0;
+        };
+        double acc1 = 0.0, acc2 = 0.0;   // lanes (0, fc): sum_k d_a Qu_a, sum_k d_a^2 of the last sweep
+        // one sweep N-1 .. 1 with the given rho; store: write the gains; poll: give up when a lower candidate of the round has succeeded
+        auto sweep = [&](double rho, bool store, bool poll) -> bool {
 #pragma unroll
             for (int s = 0; s < STAGES; s++) { const int k = N - 2 - s; if (k >= 0) issue(s, k); }
             // ---- terminal knot: S^ = H^_N with s = g_N in row 0 ---------------------------------------------------------------------
@@ -239,11 +292,12 @@ __global__ void __launch_bounds__(32 * WARPS, MINB) k_riccati_frag(const DevProb
                     S[0][1][0] = rN[TO_REC_G + 8 + 2 * fc]; S[0][1][1] = rN[TO_REC_G + 9 + 2 * fc];
                 }
             }
-            double acc1 = 0.0, acc2 = 0.0;   // lanes (0, fc): sum_k d_a Qu_a, sum_k d_a^2
-            bool ok = true;
+            acc1 = 0.0; acc2 = 0.0;
+            bool ok = true, aborted = false;
             int stage = 0;
             int k;
             for (k = N - 2; k >= 0; k--) {
+                const int best_seen = poll ? ld_volatile_s32(q_best + b) : 0x7fffffff;     // consumed at the bottom of the knot
                 mbar_wait(&bar[stage], (phase_bits >> stage) & 1u);
                 phase_bits ^= (1u << stage);
                 const double* r = ring + stage * TO_REC_LEN;
@@ -277,14 +331,13 @@ __global__ void __launch_bounds__(32 * WARPS, MINB) k_riccati_frag(const DevProb
 #pragma unroll
                 for (int ks = 0; ks < 3; ks++) {
                     const int ni = (ks == 0) ? 0 : 1, rg = (ks == 1) ? 0 : 1;
-#pragma unroll
-                    for (int mi = 0; mi < 2; mi++)
-#pragma unroll
-                        for (int nc = 0; nc < 2; nc++) dmma(Q[mi][nc][0], Q[mi][nc][1], abf[ks][mi], T[nc][ni][rg]);
+                    // the tiles on and below the diagonal: (0,1) is never used, the update leaves S^(0,1) = S^(1,0)'
+                    dmma(Q[0][0][0], Q[0][0][1], abf[ks][0], T[0][ni][rg]);
+                    dmma(Q[1][0][0], Q[1][0][1], abf[ks][1], T[0][ni][rg]);
+                    dmma(Q[1][1][0], Q[1][1][1], abf[ks][1], T[1][ni][rg]);
                 }
-                // Qz in row form for lanes (0, fc): entries 2fc, 2fc+1, 8+2fc, 9+2fc live in lanes (2fc, 0) / (2fc+1, 0)
+                // Qz in row form for lanes (0, fc): entries 2fc, 2fc+1 live in lanes (2fc, 0) / (2fc+1, 0)
                 const double qx00 = __shfl_sync(0xffffffffu, qzc0, 8 * fc), qx01 = __shfl_sync(0xffffffffu, qzc0, 8 * fc + 4);
-                const double qx10 = __shfl_sync(0xffffffffu, qzc1, 8 * fc), qx11 = __shfl_sync(0xffffffffu, qzc1, 8 * fc + 4);
                 // ---- gains -------------------------------------------------------------------------------------------------------------
                 if (fr_even) quu[(fr >> 1) * 4 + fc] = Q[0][0][0];      // Quu[a][b] = Q^[2a][2b] sits in lane (2a, b)
                 __syncwarp();
@@ -329,55 +382,124 @@ __global__ void __launch_bounds__(32 * WARPS, MINB) k_riccati_frag(const DevProb
                 dmma(k0, w0, af0, bfrag);             // lane (fr, fc): K[fc][p = fr], W[fc][p = fr]; row 0: d[fc], w_d[fc]
                 dmma(k1, w1, Q[1][0][0], bfrag);      //                K[fc][p = 8 + fr], W[fc][p = 8 + fr]
                 acc1 = fma(k0, af0, acc1); acc2 = fma(k0, k0, acc2);
-                if (eoff0 >= 0) Kg[(size_t)k * 48 + eoff0] = k0;
-                Kg[(size_t)k * 48 + eoff1] = k1;
-                if (row0) {
-                    dg[(size_t)k * 4 + fc] = k0;
-                    Q[0][0][0] = qx00; Q[0][0][1] = qx01; Q[0][1][0] = qx10; Q[0][1][1] = qx11;     // row 0 <- Qz: the product below leaves s there
+                if (store) {
+                    if (eoff0 >= 0) Kg[(size_t)k * 48 + eoff0] = k0;
+                    Kg[(size_t)k * 48 + eoff1] = k1;
+                    if (row0) dg[(size_t)k * 4 + fc] = k0;
                 }
-                // ---- S^ <- Q^ + W'K -----------------------------------------------------------------------------------------------------
+                // row 0 <- Qz (the product below leaves s = Qx + K'w_d there), column 0 <- Qz (... leaves s = Qx + W'd there: K^[a][0] = d[a])
+                if (fc == 0) { Q[0][0][0] = qzc0; Q[1][0][0] = qzc1; }
+                if (row0) { Q[0][0][0] = qx00; Q[0][0][1] = qx01; }
+                // ---- S^ <- Q^ + W'K on the three tiles; S^(0,1) <- S^(1,0)' ---------------------------------------------------------------
                 dmma(Q[0][0][0], Q[0][0][1], w0, k0);
-                dmma(Q[0][1][0], Q[0][1][1], w0, k1);
                 dmma(Q[1][0][0], Q[1][0][1], w1, k0);
                 dmma(Q[1][1][0], Q[1][1][1], w1, k1);
-#pragma unroll
-                for (int mi = 0; mi < 2; mi++)
-#pragma unroll
-                    for (int nj = 0; nj < 2; nj++) { S[mi][nj][0] = Q[mi][nj][0]; S[mi][nj][1] = Q[mi][nj][1]; }
+                S[0][0][0] = Q[0][0][0]; S[0][0][1] = Q[0][0][1]; S[1][0][0] = Q[1][0][0]; S[1][0][1] = Q[1][0][1];
+                S[1][1][0] = Q[1][1][0]; S[1][1][1] = Q[1][1][1];
+                tile_transpose(S[1][0][0], S[1][0][1], tsrc, fr & 1, S[0][1][0], S[0][1][1]);
+                // The antisymmetric part of S is an unstable mode of the recursion (it grows by ~1.25 per knot: 1e-16 -> 1e-6 over 100 knots,
+                // measured; profiles/r02_notes.md).  The off-diagonal tiles are exact mirrors by construction; the diagonal tiles are averaged
+                // with their transposes every 4th knot (growth 2.4 between two averagings).
+                if ((k & 3) == 0) {
+                    double y0, y1;
+                    tile_transpose(S[0][0][0], S[0][0][1], tsrc, fr & 1, y0, y1);
+                    S[0][0][0] = 0.5 * (S[0][0][0] + y0); S[0][0][1] = 0.5 * (S[0][0][1] + y1);
+                    tile_transpose(S[1][1][0], S[1][1][1], tsrc, fr & 1, y0, y1);
+                    S[1][1][0] = 0.5 * (S[1][1][0] + y0); S[1][1][1] = 0.5 * (S[1][1][1] + y1);
+                }
                 // the record and the Minv slots have been consumed by every lane: refill the ring slot
                 __syncwarp();
+                if (best_seen < cand) { ok = false; aborted = true; }      // a lower candidate of this round already succeeded: this sweep is moot
+                if (aborted) { k--; break; }                                 // (this knot's slot was consumed: same drain as a failure one knot later)
                 if (k - STAGES >= 0) issue(stage, k - STAGES);
                 stage = (stage + 1 == STAGES) ? 0 : stage + 1;
             }   // knots
-
-            if (ok) {
-                acc1 += __shfl_xor_sync(0xffffffffu, acc1, 1); acc1 += __shfl_xor_sync(0xffffffffu, acc1, 2);
-                acc2 += __shfl_xor_sync(0xffffffffu, acc2, 1); acc2 += __shfl_xor_sync(0xffffffffu, acc2, 2);
-                // 1/2 d'Quu d = -1/2 (d'Qu + rho d'd)   since (Quu + rho I) d = -Qu
-                if (lane == 0) { P.dV[2 * b] = acc1; P.dV[2 * b + 1] = -0.5 * fma(rho, acc2, acc1); }
-                break;
-            }
-            // ---- non-PD Quu + rho I at knot k: drain the copies in flight, increase rho (Altro regularization_update!(:increase)), restart ----
-            {
-                // slot `stage` (knot k) was consumed; the slots after it hold knots k-1 .. k-STAGES+1
-                const int outstanding = (k < STAGES - 1) ? k : STAGES - 1;
+            if (!ok) {
+                // drain the copies in flight: slot `stage` (knot k of the failure) was consumed, the slots after it hold knots k-1 .. k-STAGES+1
+                const int kf = aborted ? k + 1 : k;
+                const int outstanding = (kf < STAGES - 1) ? kf : STAGES - 1;
                 for (int i = 1; i <= outstanding; i++) {
                     const int st = (stage + i) % STAGES;
                     mbar_wait(&bar[st], (phase_bits >> st) & 1u);
                     phase_bits ^= (1u << st);
                 }
+                __syncwarp();
+            }
+            return ok;
+        };
+        // expected decrease of the sweep this warp just completed (the accumulators live in its registers)
+        auto write_dV = [&](double rho) {
+            acc1 += __shfl_xor_sync(0xffffffffu, acc1, 1); acc1 += __shfl_xor_sync(0xffffffffu, acc1, 2);
+            acc2 += __shfl_xor_sync(0xffffffffu, acc2, 1); acc2 += __shfl_xor_sync(0xffffffffu, acc2, 2);
+            // 1/2 d'Quu d = -1/2 (d'Qu + rho d'd)   since (Quu + rho I) d = -Qu
+            if (lane == 0) { P.dV[2 * b] = acc1; P.dV[2 * b + 1] = -0.5 * fma(rho, acc2, acc1); }
+        };
+        auto finalise = [&](double rho, double drho, int status) {
+            if (status >= 0) reg_decrease(P.opt, rho, drho);
+            if (lane == 0) {
+                P.rho[b] = rho; P.drho[b] = drho; P.bp_status[b] = status;
+                __threadfence();
+                atomicAdd(q_nfinal, 1);
+            }
+        };
+        // queue the candidates first .. first + n - 1 of instance b
+        auto start_round = [&](int first, int n) {
+            if (lane == 0) {
+                atomicExch(q_cnt + b, n);
+                atomicExch(q_best + b, 0x7f7f7f7f);
+                __threadfence();
+                const int slot = atomicAdd(q_tail, n);
+                for (int i = 0; i < n; i++)
+                    if (slot + i < QCAP) atomicExch(q_items + slot + i, b * 16 + first + i); else atomicExch(q_err, 2);
             }
             __syncwarp();
-            reg_increase(P.opt, rho, drho);
-            restarts++;
-            if (rho > P.opt.bp_reg_max) { failed = true; break; }
+        };
+
+        double rho, drho;
+        const int over = ladder(cand, rho, drho);
+        const bool first_of_round = (cand & (cand - 1)) == 0;            // 0, 1, 2, 4, 8: stores its gains speculatively
+        bool ok = false;
+        if (cand == 0 || !over) ok = sweep(rho, first_of_round, !first_of_round);
+        // the storing candidate is the lowest of its round: if it succeeds it IS the winner, its gains and dV are final
+        if (ok && first_of_round) write_dV(rho);
+        if (cand == 0) {
+            if (ok) finalise(rho, drho, 0);
+            else start_round(1, 1);
+            continue;
         }
-        if (!failed) reg_decrease(P.opt, rho, drho);
+        // a candidate of round [lo, 2 lo): record, and let the last one to finish decide
+        int lo = 1; while (2 * lo <= cand) lo *= 2;
+        int last = 0;
         if (lane == 0) {
-            P.rho[b] = rho; P.drho[b] = drho;
-            P.bp_status[b] = failed ? -1 : restarts;
+            if (ok) atomicMin(q_best + b, cand);
+            __threadfence();
+            last = (atomicSub(q_cnt + b, 1) == 1) ? 1 : 0;
         }
-        __syncwarp();
+        last = __shfl_sync(0xffffffffu, last, 0);
+        if (!last) continue;
+        int best = 0;
+        if (lane == 0) best = atomicAdd(q_best + b, 0);
+        best = __shfl_sync(0xffffffffu, best, 0);
+        if (best < 16) {
+            ladder(best, rho, drho);
+            // gains and dV of the round's storing candidate (lo) are in place; any other winner runs once more, storing
+            if (best != lo) { sweep(rho, true, false); write_dV(rho); }
+            finalise(rho, drho, best);
+            continue;
+        }
+        // nobody succeeded: the sequential loop gives up at the first rho beyond bp_reg_max, else the next round
+        const int hi = 2 * lo - 1;
+        const int ov = ladder(hi, rho, drho);
+        if (ov) { ladder(ov, rho, drho); finalise(rho, drho, -1); continue; }
+        if (hi < 15) { start_round(2 * lo, 2 * lo); continue; }
+        // ladder longer than 15 steps (a huge bp_reg_max): finish sequentially in this warp
+        int status = -1;
+        for (int j = 16; ; j++) {
+            reg_increase(P.opt, rho, drho);
+            if (rho > P.opt.bp_reg_max) break;
+            if (sweep(rho, true, false)) { status = j; write_dV(rho); break; }
+        }
+        finalise(rho, drho, status);
     }
 }
 
@@ -392,7 +514,9 @@ cudaError_t launch_export_abe(const DevProblem& P, cudaStream_t s) {
     return cudaGetLastError();
 }
 
-cudaError_t launch_backward_frag(const DevProblem& P, int* work_counter, cudaStream_t s) {
+size_t frag_queue_ints(int B) { return 4 + (size_t)B + (16 * (size_t)B + 8192) + (size_t)B; }
+
+cudaError_t launch_backward_frag(const DevProblem& P, int* queue, cudaStream_t s) {
     constexpr int STAGES = TO_FRAG_STAGES, WARPS = TO_FRAG_WARPS, MINB = TO_FRAG_MINB;
     using SM = FragSmem<STAGES, WARPS>;
     auto kern = k_riccati_frag<STAGES, WARPS, MINB>;
@@ -410,11 +534,15 @@ cudaError_t launch_backward_frag(const DevProblem& P, int* work_counter, cudaStr
         if (e != cudaSuccess) return e;
         ctas_per_sm[dev] = c < 1 ? 1 : c;
     }
-    e = cudaMemsetAsync(work_counter, 0, sizeof(int), s);
+    // queue layout (k_riccati_frag): head, tail, nfinal, error | cnt[B] = 0 | items[16 B + 8192] = -1 | best[B] = 0x7f7f7f7f
+    const size_t qcap = 16 * (size_t)P.B + 8192;
+    e = cudaMemsetAsync(queue, 0, sizeof(int) * (4 + (size_t)P.B), s);
+    if (e == cudaSuccess) e = cudaMemsetAsync(queue + 4 + P.B, 0xFF, sizeof(int) * qcap, s);
+    if (e == cudaSuccess) e = cudaMemsetAsync(queue + 4 + P.B + qcap, 0x7F, sizeof(int) * (size_t)P.B, s);
     if (e != cudaSuccess) return e;
-    int grid = num_sms[dev] * ctas_per_sm[dev];       // persistent: warps pull instances from the queue
-    const int need = (P.B + WARPS - 1) / WARPS;
+    int grid = num_sms[dev] * ctas_per_sm[dev];       // persistent: warps pull work from the queue (all CTAs are co-resident: the
+    const int need = (P.B + WARPS - 1) / WARPS;       // waiting warps of the speculative ladder cannot starve the running ones)
     if (grid > need) grid = need;
-    kern<<<grid, 32 * WARPS, smem, s>>>(P, work_counter);
+    kern<<<grid, 32 * WARPS, smem, s>>>(P, queue);
     return cudaGetLastError();
 }

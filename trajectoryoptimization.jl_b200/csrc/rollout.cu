@@ -79,7 +79,78 @@ __global__ void __launch_bounds__(128) k_expand(const DevProblem P, int mode) {
 // E(x_k) = blkdiag(I3, G(q_k), I6 | I4) through the RK4 step as the tangent of a Dual<1> -- the directional derivative [A G_k | B] e_j --
 // and projects the result with G(q_{k+1})' (q_{k+1} from the stored trajectory, as Altro's errstate_jacobian! does).  It writes column j
 // of [A_e B_e]_k (12 contiguous doubles, col-major 12 x 16): 1.5 KB per knot instead of the 2 KB of the padded full-state [A B].
-// FRAG: the column goes into the fragment block of the knot's record (frag_layout.cuh) instead of P.ABe.
+// (g, h) = (lz_i, lzz_ii) of entry i of the full-state z = [x; u] at knot k (0-based): DiagonalCost (RD.gradient!/hessian!, src/cost_functions.jl:137-233)
+// + the AL terms of the Goal / Bound rows acting on z_i (src/constraints.jl:55-68, :738-765; projection on the dual cone src/cones.jl:96-145).
+// The compact problem class only (P.compact): every cost diagonal, every constraint Goal or Bound.
+__device__ __forceinline__ void compact_entry_expansion(const DevProblem& P, int k, int i, double zi, const double* __restrict__ lam_b, double& g, double& h) {
+    const int n = P.n;
+    const bool last = (k == P.N - 1);
+    const DevCost& c = P.costs[P.cost_index[k]];
+    if (i < n) { g = fma(c.Qd[i], zi, c.q[i]); h = c.Qd[i]; }
+    else if (last) { g = 0.0; h = 0.0; return; }
+    else { g = fma(c.Rd[i - n], zi, c.r[i - n]); h = c.Rd[i - n]; }
+    for (int ci = 0; ci < P.ncon; ci++) {
+        const DevCon& con = P.cons[ci];
+        if (k + 1 < con.first || k + 1 > con.last) continue;
+        const double mu = P.mu[ci];
+        const double* lam = lam_b + con.offset + (size_t)(k + 1 - con.first) * con.p;
+        if (con.kind == CON_GOAL) {
+            const int row = (i < n) ? con.row_max[i] : -1;
+            if (row >= 0) { const double lb = lam[row] - mu * (zi - con.a[row]); g -= lb; h += mu; }
+        } else {
+            int row = con.row_max[i];
+            if (row >= 0) { const double lb = lam[row] - mu * (zi - con.a[i]); if (lb <= 0.0) { g -= lb; h += mu; } }
+            row = con.row_min[i];
+            if (row >= 0) { const double lb = lam[row] - mu * (con.b[i] - zi); if (lb <= 0.0) { g += lb; h += mu; } }
+        }
+    }
+}
+
+// Expansion part of the record of knot k (frag_layout.cuh [192, 240)) written by the 16 column threads of that knot: thread j owns the
+// error-state coordinate j.  Outside the attitude the error-state expansion of a diagonal full-state one is the same entry; the three
+// attitude threads project the quaternion block: G'g, G' diag(h) G - (q'g_q) I3 (Altro error_expansion!; lie.cu k_expansion_compact is the
+// one-thread-per-knot version of the same numbers).
+__device__ __forceinline__ void compact_record_expansion(const DevProblem& P, int b, int k, int j, const double* __restrict__ X, const double* __restrict__ U,
+                                                         double* __restrict__ rec) {
+    constexpr int qs = 3;
+    const int n = P.n;
+    const double* lam_b = P.lambda + (size_t)b * P.lambda_len;
+    const int p = (int)((0x6420FDB9E7CA8531ULL >> (4 * j)) & 15);
+    if (j >= qs && j < qs + 3) {
+        const int c = j - qs;
+        double g[4], h[4], q[4];
+#pragma unroll
+        for (int r = 0; r < 4; r++) { q[r] = X[qs + r]; compact_entry_expansion(P, k, qs + r, q[r], lam_b, g[r], h[r]); }
+        // rows of G' = (L(q) H)': (-x,w,z,-y), (-y,-z,w,x), (-z,y,-x,w)   (kept in registers: no run-time indexed arrays)
+        const double G0[4] = {-q[1], q[0], q[3], -q[2]}, G1[4] = {-q[2], -q[3], q[0], q[1]}, G2[4] = {-q[3], q[2], -q[1], q[0]};
+        double gc[4];
+#pragma unroll
+        for (int r = 0; r < 4; r++) gc[r] = (c == 0) ? G0[r] : (c == 1) ? G1[r] : G2[r];
+        double qb = 0.0, ge = 0.0, hb0 = 0.0, hb1 = 0.0, hb2 = 0.0;
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+            qb += q[r] * g[r]; ge += gc[r] * g[r];
+            const double t = gc[r] * h[r];
+            hb0 += t * G0[r]; hb1 += t * G1[r]; hb2 += t * G2[r];
+        }
+        const double hd = ((c == 0) ? hb0 : (c == 1) ? hb1 : hb2) - qb;
+        rec[TO_REC_G + p] = ge; rec[TO_REC_HD + p] = hd;
+        rec[TO_REC_HB + 4 * c + 0] = (c == 0) ? hd : hb0;
+        rec[TO_REC_HB + 4 * c + 1] = (c == 1) ? hd : hb1;
+        rec[TO_REC_HB + 4 * c + 2] = (c == 2) ? hd : hb2;
+        rec[TO_REC_HB + 4 * c + 3] = 0.0;
+    } else {
+        const int i = (j < qs) ? j : (j < n - 1 ? j + 1 : j + 1);       // full-state index of the coordinate (controls: n + a = j + 1)
+        const double zi = (i < n) ? X[i] : ((k == P.N - 1) ? 0.0 : U[i - n]);
+        double g, h;
+        compact_entry_expansion(P, k, i, zi, lam_b, g, h);
+        rec[TO_REC_G + p] = g; rec[TO_REC_HD + p] = h;
+        if (j == 7) { rec[TO_REC_HB + 12] = 0.0; rec[TO_REC_HB + 13] = 0.0; rec[TO_REC_HB + 14] = 0.0; rec[TO_REC_HB + 15] = h; }   // p = 14 is row 3 of Hb
+    }
+}
+
+// FRAG: the column goes into the fragment block of the knot's record (frag_layout.cuh) instead of P.ABe, and the thread writes its share of
+// the record's cost + AL expansion (the terminal knot's by the threads of knot N-2).
 template <int MODEL, bool FRAG>
 __global__ void __launch_bounds__(128) k_expand_lie(const DevProblem P, int mode) {
     constexpr int n = ModelDims<MODEL>::n, m = ModelDims<MODEL>::m, ne = n - 1, nme = ne + m, qs = 3;
@@ -94,6 +165,11 @@ __global__ void __launch_bounds__(128) k_expand_lie(const DevProblem P, int mode
     if (mode != 0 && (P.acc1[b] != 0) != (mode == 1)) return;
     const double* X = traj_X(P, P.cur[b], b) + (size_t)k * n;
     const double* U = traj_U(P, P.cur[b], b) + (size_t)k * m;
+    if constexpr (FRAG) {      // the record's cost + AL expansion first: its temporaries are dead before the RK4 step needs the registers
+        double* rec_k = P.REC + ((size_t)b * P.N + k) * TO_REC_LEN;
+        compact_record_expansion(P, b, k, j, X, U, rec_k);
+        if (k == P.N - 2) compact_record_expansion(P, b, k + 1, j, X + n, U, rec_k + TO_REC_LEN);
+    }
     D x[n], u[m], xn[n];
 #pragma unroll
     for (int i = 0; i < n; i++) { x[i].v = X[i]; x[i].d[0] = 0.0; }

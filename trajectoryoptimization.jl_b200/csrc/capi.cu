@@ -45,6 +45,7 @@ struct to_handle {
     double* d_viol = nullptr;     // [B]
     double* d_merit2 = nullptr;   // {sum J, max viol}
     int* d_work = nullptr;
+    ExpTab* d_exptab = nullptr;   // (frag) AL rows per z entry, rebuilt with the constraint tables / penalties
     int* d_fragq = nullptr;       // work queue of the register-resident Riccati kernel (riccati_frag.cu)
     int* d_err = nullptr;
     Scratch scratch;
@@ -96,6 +97,39 @@ int ensure_scratch(to_handle* h, size_t bytes) {
     return TO_OK;
 }
 
+// ExpTab (common.cuh): the Goal / Bound rows acting on each z entry, for the record expansion of the dynamics expansion kernel
+int upload_exptab(to_handle* h) {
+    if (!h->d_exptab) return TO_OK;
+    ExpTab t;
+    std::memset(&t, 0, sizeof(t));
+    const int nm = h->P.n + h->P.m, n = h->P.n;
+    for (int i = 0; i < nm; i++) {
+        int nterm = 0;
+        for (int k = 0; k < TO_EXP_MAXT; k++) { t.nms[k][i] = -1.0; t.pkx[k][i] = 4095u; }      // empty knot range
+        for (size_t ci = 0; ci < h->h_cons.size(); ci++) {
+            const DevCon& con = h->h_cons[ci];
+            if (!con.diagonal) continue;
+            const double mu = h->h_mu[ci];
+            for (int side = 0; side < 2; side++) {
+                int row = -1; double sign = 1.0, bound = 0.0; bool eq = false;
+                if (con.kind == CON_GOAL) { if (side == 0 && i < n) { row = con.row_max[i]; if (row >= 0) bound = con.a[row]; eq = true; } }
+                else if (side == 0) { row = con.row_max[i]; bound = con.a[i]; }
+                else { row = con.row_min[i]; bound = con.b[i]; sign = -1.0; }
+                if (row < 0) continue;
+                if (nterm < TO_EXP_MAXT && con.last >= con.first && con.first < 4095 && con.p < 128) {
+                    t.nms[nterm][i] = -mu * sign; t.bound[nterm][i] = bound;
+                    t.pkx[nterm][i] = (unsigned)con.first | ((unsigned)(con.last - con.first) << 12) | ((unsigned)con.p << 24) | (eq ? 0x80000000u : 0u);
+                    t.pky[nterm][i] = (unsigned)(con.offset + row - con.first * con.p);
+                }
+                nterm++;
+            }
+        }
+    }
+    CU(h, cudaMemcpyAsync(h->d_exptab, &t, sizeof(t), cudaMemcpyHostToDevice, h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));   // `t` goes out of scope
+    return TO_OK;
+}
+
 int upload_tables(to_handle* h) {
     CU(h, cudaMemcpyAsync(h->d_costs, h->h_costs.data(), sizeof(DevCost) * h->h_costs.size(), cudaMemcpyHostToDevice, h->stream));
     if (!h->h_cons.empty()) {
@@ -103,7 +137,7 @@ int upload_tables(to_handle* h) {
         CU(h, cudaMemcpyAsync(h->d_mu, h->h_mu.data(), sizeof(double) * h->h_mu.size(), cudaMemcpyHostToDevice, h->stream));
     }
     CU(h, cudaStreamSynchronize(h->stream));   // the host vectors may change right after
-    return TO_OK;
+    return upload_exptab(h);
 }
 
 // phase timing helpers
@@ -460,9 +494,10 @@ int to_create(const to_spec* s, to_handle** out) {
     ALLOC(P.bp_status, B); ALLOC(P.ls_iters, B); ALLOC(P.accepted, B); ALLOC(P.acc1, B);
     ALLOC(h->d_stageX, P.strideX); ALLOC(h->d_stageU, P.strideU); ALLOC(h->d_viol, B); ALLOC(h->d_merit2, 2);
     ALLOC(h->d_work, 1); ALLOC(h->d_err, 1);
-    if (P.frag) ALLOC(h->d_fragq, frag_queue_ints(B));
+    if (P.frag) { ALLOC(h->d_fragq, frag_queue_ints(B)); ALLOC(h->d_exptab, 1); }
 #undef ALLOC
     if (rc) return bail(rc);
+    P.exptab = h->d_exptab;
     P.dt = d_dt; P.cost_index = d_ci; P.costs = h->d_costs; P.cons = h->d_cons; P.mu = h->d_mu; P.viol = h->d_viol;
     cudaStream_t st = h->stream;
     bool okc = true;
@@ -692,13 +727,16 @@ int to_rollout(to_handle* h) {
     h->J_valid = false; h->rec_valid = false; h->expanded = false; h->backward_done = false;
     return TO_OK;
 }
+// the dynamics expansion kernel also writes the records' cost + AL expansion when the Goal / Bound rows fit its shared-memory table
+// (rollout.cu ExpTab: <= 3 rows per z entry, knot indices < 4095, < 128 rows per knot); otherwise k_expansion_rec does it
+static bool rec_fused(const DevProblem& P) { return P.frag && P.max_terms_per_z <= 3 && P.N < 4095 && P.max_p_knot < 128; }
 int to_expand(to_handle* h) {
     JOIN(h);
     if (!h) return TO_EINVAL;
     { PhaseScope ps(h, TO_PHASE_EXPAND); CU(h, launch_expand(h->P, h->stream)); if (h->P.lie) { CU(h, launch_expand_lie(h->P, h->stream)); h->launches++; } }
     h->launches++; h->phase_launches[TO_PHASE_EXPAND]++;
     h->expanded = true; h->backward_done = false;
-    h->rec_valid = h->P.frag != 0;        // k_expand_lie wrote the records' cost + AL expansion too
+    h->rec_valid = rec_fused(h->P);       // k_expand_lie wrote the records' cost + AL expansion too
     return TO_OK;
 }
 int to_get_dynamics_jacobians(to_handle* h, double* AB) {
@@ -930,7 +968,7 @@ int to_ilqr_step(to_handle* h, int32_t iters) {
         h->launches++; h->phase_launches[TO_PHASE_EXPAND]++;
         JOIN(h);
         h->expanded = true;
-        h->rec_valid = h->P.frag != 0;
+        h->rec_valid = rec_fused(h->P);
         rc = do_backward(h); if (rc) return rc;
         { PhaseScope ps(h, TO_PHASE_FORWARD); CU(h, launch_forward(h->P, h->stream)); }
         h->launches++; h->phase_launches[TO_PHASE_FORWARD]++;
@@ -956,7 +994,7 @@ int to_al_update(to_handle* h) {
     if (!h->h_mu.empty()) CU(h, cudaMemcpyAsync(h->d_mu, h->h_mu.data(), sizeof(double) * h->h_mu.size(), cudaMemcpyHostToDevice, h->stream));
     CU(h, cudaStreamSynchronize(h->stream));
     h->J_valid = false; h->rec_valid = false;
-    return TO_OK;
+    return upload_exptab(h);        // the penalties are part of the table
 }
 int to_get_gains(to_handle* h, double* K, double* d) {
     JOIN(h);
@@ -1042,7 +1080,7 @@ int to_set_penalty(to_handle* h, int32_t con, double mu) {
     CU(h, cudaMemcpyAsync(h->d_mu, h->h_mu.data(), sizeof(double) * h->h_mu.size(), cudaMemcpyHostToDevice, h->stream));
     CU(h, cudaStreamSynchronize(h->stream));
     h->J_valid = false; h->rec_valid = false;
-    return TO_OK;
+    return upload_exptab(h);
 }
 int to_get_solver_state(to_handle* h, double* rho, double* dV, double* alpha, int32_t* ls_iters, int32_t* bp_status) {
     JOIN(h);

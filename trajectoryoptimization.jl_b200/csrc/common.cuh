@@ -69,6 +69,17 @@ struct DevCon {
     double pconst[TO_EXPR_CONST];
 };
 
+// Table of the Goal / Bound rows acting on each full-state entry z_i (compact problems), built on the host whenever the constraint
+// tables or the penalties change, read by the dynamics expansion kernel for the records' cost + AL expansion (rollout.cu).
+// One AL term on z_i:  c = sign (z_i - bound);  Goal: equality (always active), Bound: inequality.
+#define TO_EXP_MAXT 3
+struct ExpTab {
+    double nms[TO_EXP_MAXT][TO_MAXNM];      // -mu * sign
+    double bound[TO_EXP_MAXT][TO_MAXNM];
+    unsigned pkx[TO_EXP_MAXT][TO_MAXNM];    // first knot (12 bits) | last - first (12) | rows p of the constraint (7) | equality (1)
+    unsigned pky[TO_EXP_MAXT][TO_MAXNM];    // lambda index of the row at knot 0
+};
+
 struct DevOptions {
     double bp_reg_increase_factor, bp_reg_max, bp_reg_min, bp_reg_initial, bp_reg_fp;
     double ls_lower, ls_upper;
@@ -98,6 +109,7 @@ struct DevProblem {
                               // filled on request (export, the shared-memory kernels forced by to_options.backward_kernel)
     double* EC;               // [B][N][TO_EC_LEN]: g_e(16) | diag(16) | block (0,1),(0,2),(1,2) | pad
     double* REC;              // [B][N][TO_REC_LEN] (frag)
+    const ExpTab* exptab;     // (frag) see ExpTab
     double* ABe;              // [B][N-1][ne+m][ne]   ne x (ne+m) col-major
     double* EG;               // [B][N][ne+m]
     double* EH;               // [B][N][ne+m][ne+m]

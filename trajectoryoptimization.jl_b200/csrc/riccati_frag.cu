@@ -243,13 +243,14 @@ __global__ void __launch_bounds__(32 * WARPS, MINB) k_riccati_frag(const DevProb
             const int qi = idx - P.B;
             int item = -2;
             if (lane == 0) {
-                unsigned spins = 0;
+                unsigned spins = 0, ns = 128;
                 for (;;) {
                     item = (qi < QCAP) ? ld_volatile_s32(q_items + qi) : -1;
                     if (item >= 0) break;
                     if (ld_volatile_s32(q_nfinal) >= P.B) { item = -2; break; }      // every instance is finalised: nothing more will be queued
-                    __nanosleep(256);
-                    if (++spins > (1u << 22)) { atomicExch(q_err, 1); item = -2; break; }   // ~1 s: never hang the device
+                    __nanosleep(ns);                                                  // back off: an idle warp must not take issue slots from the running ones
+                    if (ns < 4096) ns *= 2;
+                    if (++spins > (1u << 18)) { atomicExch(q_err, 1); item = -2; break; }   // ~1 s: never hang the device
                 }
             }
             item = __shfl_sync(0xffffffffu, item, 0);

@@ -81,27 +81,23 @@ __global__ void __launch_bounds__(128) k_expand(const DevProblem P, int mode) {
 // of [A_e B_e]_k (12 contiguous doubles, col-major 12 x 16): 1.5 KB per knot instead of the 2 KB of the padded full-state [A B].
 // (g, h) = (lz_i, lzz_ii) of entry i of the full-state z = [x; u] at knot k (0-based): DiagonalCost (RD.gradient!/hessian!, src/cost_functions.jl:137-233)
 // + the AL terms of the Goal / Bound rows acting on z_i (src/constraints.jl:55-68, :738-765; projection on the dual cone src/cones.jl:96-145).
-// The compact problem class only (P.compact): every cost diagonal, every constraint Goal or Bound.
-__device__ __forceinline__ void compact_entry_expansion(const DevProblem& P, int k, int i, double zi, const double* __restrict__ lam_b, double& g, double& h) {
+// The compact problem class only (P.compact): every cost diagonal, every constraint Goal or Bound, at most TO_EXP_MAXT rows per entry
+// (the host-built table P.exptab; walking the constraint descriptors per thread instead made this kernel 2x slower than its RK4 work).
+__device__ __forceinline__ void compact_entry_expansion(const DevProblem& P, const ExpTab& tab, int k, int i, double zi, const double* __restrict__ lam_b, double& g, double& h) {
     const int n = P.n;
     const bool last = (k == P.N - 1);
     const DevCost& c = P.costs[P.cost_index[k]];
     if (i < n) { g = fma(c.Qd[i], zi, c.q[i]); h = c.Qd[i]; }
     else if (last) { g = 0.0; h = 0.0; return; }
     else { g = fma(c.Rd[i - n], zi, c.r[i - n]); h = c.Rd[i - n]; }
-    for (int ci = 0; ci < P.ncon; ci++) {
-        const DevCon& con = P.cons[ci];
-        if (k + 1 < con.first || k + 1 > con.last) continue;
-        const double mu = P.mu[ci];
-        const double* lam = lam_b + con.offset + (size_t)(k + 1 - con.first) * con.p;
-        if (con.kind == CON_GOAL) {
-            const int row = (i < n) ? con.row_max[i] : -1;
-            if (row >= 0) { const double lb = lam[row] - mu * (zi - con.a[row]); g -= lb; h += mu; }
-        } else {
-            int row = con.row_max[i];
-            if (row >= 0) { const double lb = lam[row] - mu * (zi - con.a[i]); if (lb <= 0.0) { g -= lb; h += mu; } }
-            row = con.row_min[i];
-            if (row >= 0) { const double lb = lam[row] - mu * (con.b[i] - zi); if (lb <= 0.0) { g += lb; h += mu; } }
+#pragma unroll
+    for (int t = 0; t < TO_EXP_MAXT; t++) {
+        const unsigned px = __ldg(&tab.pkx[t][i]);
+        if ((unsigned)(k + 1) - (px & 0xfffu) <= ((px >> 12) & 0xfffu)) {
+            const double nms = __ldg(&tab.nms[t][i]);
+            const double lam = lam_b[(int)(__ldg(&tab.pky[t][i]) + (unsigned)(k + 1) * ((px >> 24) & 0x7fu))];
+            const double lb = fma(nms, zi - __ldg(&tab.bound[t][i]), lam);          // lambda - mu c
+            if ((px >> 31) || lb <= 0.0) { g += (nms < 0.0) ? -lb : lb; h += fabs(nms); }   // g -= sign lb ; h += mu
         }
     }
 }
@@ -110,7 +106,7 @@ __device__ __forceinline__ void compact_entry_expansion(const DevProblem& P, int
 // error-state coordinate j.  Outside the attitude the error-state expansion of a diagonal full-state one is the same entry; the three
 // attitude threads project the quaternion block: G'g, G' diag(h) G - (q'g_q) I3 (Altro error_expansion!; lie.cu k_expansion_compact is the
 // one-thread-per-knot version of the same numbers).
-__device__ __forceinline__ void compact_record_expansion(const DevProblem& P, int b, int k, int j, const double* __restrict__ X, const double* __restrict__ U,
+__device__ __forceinline__ void compact_record_expansion(const DevProblem& P, const ExpTab& tab, int b, int k, int j, const double* __restrict__ X, const double* __restrict__ U,
                                                          double* __restrict__ rec) {
     constexpr int qs = 3;
     const int n = P.n;
@@ -120,7 +116,7 @@ __device__ __forceinline__ void compact_record_expansion(const DevProblem& P, in
         const int c = j - qs;
         double g[4], h[4], q[4];
 #pragma unroll
-        for (int r = 0; r < 4; r++) { q[r] = X[qs + r]; compact_entry_expansion(P, k, qs + r, q[r], lam_b, g[r], h[r]); }
+        for (int r = 0; r < 4; r++) { q[r] = X[qs + r]; compact_entry_expansion(P, tab, k, qs + r, q[r], lam_b, g[r], h[r]); }
         // rows of G' = (L(q) H)': (-x,w,z,-y), (-y,-z,w,x), (-z,y,-x,w)   (kept in registers: no run-time indexed arrays)
         const double G0[4] = {-q[1], q[0], q[3], -q[2]}, G1[4] = {-q[2], -q[3], q[0], q[1]}, G2[4] = {-q[3], q[2], -q[1], q[0]};
         double gc[4];
@@ -143,42 +139,78 @@ __device__ __forceinline__ void compact_record_expansion(const DevProblem& P, in
         const int i = (j < qs) ? j : (j < n - 1 ? j + 1 : j + 1);       // full-state index of the coordinate (controls: n + a = j + 1)
         const double zi = (i < n) ? X[i] : ((k == P.N - 1) ? 0.0 : U[i - n]);
         double g, h;
-        compact_entry_expansion(P, k, i, zi, lam_b, g, h);
+        compact_entry_expansion(P, tab, k, i, zi, lam_b, g, h);
         rec[TO_REC_G + p] = g; rec[TO_REC_HD + p] = h;
         if (j == 7) { rec[TO_REC_HB + 12] = 0.0; rec[TO_REC_HB + 13] = 0.0; rec[TO_REC_HB + 14] = 0.0; rec[TO_REC_HB + 15] = h; }   // p = 14 is row 3 of Hb
     }
 }
 
+// Seed pruning.  The position r and the (world-frame) linear velocity v of a RigidBody enter the dynamics only through rdot = v: f does not
+// depend on r, and on v only in rdot.  Their columns of the discrete Jacobian are therefore known in closed form -- d x+/d r = e_r and
+// d x+/d v = h e_r + e_v (the RK4 weights sum to one) -- and need no dual-number sweep: 10 seeds (attitude, angular velocity, controls) are
+// pushed through the RK4 step instead of 16, one thread each; the six trivial columns are written by the first six of them.
+__device__ __forceinline__ int lie_seed(int s) { return (int)((0xFEDCBA9543ULL >> (4 * s)) & 15); }       // 3,4,5,9,10,11,12,13,14,15
+__device__ __forceinline__ int lie_trivial(int s) { return (int)((0x876210ULL >> (4 * s)) & 15); }        // 0,1,2,6,7,8
+
 // FRAG: the column goes into the fragment block of the knot's record (frag_layout.cuh) instead of P.ABe, and the thread writes its share of
 // the record's cost + AL expansion (the terminal knot's by the threads of knot N-2).
+#ifndef TO_EXPAND_LIE_MINB
+#define TO_EXPAND_LIE_MINB 3      // CTAs per SM the register allocation aims at (A/B: profiles/scripts/build_variant.sh)
+#endif
 template <int MODEL, bool FRAG>
-__global__ void __launch_bounds__(128) k_expand_lie(const DevProblem P, int mode) {
-    constexpr int n = ModelDims<MODEL>::n, m = ModelDims<MODEL>::m, ne = n - 1, nme = ne + m, qs = 3;
+__global__ void __launch_bounds__(128, TO_EXPAND_LIE_MINB) k_expand_lie(const DevProblem P, int mode) {
+    constexpr int n = ModelDims<MODEL>::n, m = ModelDims<MODEL>::m, ne = n - 1, nme = ne + m, qs = 3, NS = 10;
     using D = Dual<1>;
+    const bool fused = FRAG && P.max_terms_per_z <= TO_EXP_MAXT && P.N < 4095 && P.max_p_knot < 128;     // == capi.cu rec_fused
+    const ExpTab& tab = *P.exptab;
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long total = (long long)P.B * (P.N - 1) * nme;
+    const long long total = (long long)P.B * (P.N - 1) * NS;
     if (t >= total) return;
-    const int j = (int)(t % nme);
-    const long long bk = t / nme;
+    const int sd = (int)(t % NS);
+    const int j = lie_seed(sd);
+    const long long bk = t / NS;
     const int k = (int)(bk % (P.N - 1));
     const int b = (int)(bk / (P.N - 1));
     if (mode != 0 && (P.acc1[b] != 0) != (mode == 1)) return;
     const double* X = traj_X(P, P.cur[b], b) + (size_t)k * n;
     const double* U = traj_U(P, P.cur[b], b) + (size_t)k * m;
-    if constexpr (FRAG) {      // the record's cost + AL expansion first: its temporaries are dead before the RK4 step needs the registers
+    const double h = P.dt[k];
+    // where column jj of [A_e B_e] goes: the fragment slots of the record, or 12 contiguous doubles of P.ABe
+    auto store_column = [&](int jj, const double (&col)[ne]) {
+        if constexpr (FRAG) {
+            // element (row e, column jj) of the record: (ks(e)*32 + 4*(c & 7) + fc(e))*2 + (c >> 3), c = physical index of column jj
+            const int c = (int)((0x6420FDB9E7CA8531ULL >> (4 * jj)) & 15);       // fraglayout::phys_z(jj) as a nibble table
+            double* rec = P.REC + ((size_t)b * P.N + k) * TO_REC_LEN + 8 * (c & 7) + (c >> 3);
+#pragma unroll
+            for (int e = 0; e < ne; e++) rec[fraglayout::ab_index(e, 12)] = col[e];   // column 12 (u_0, c = 0) has a zero column offset
+        } else {
+            double* out = P.ABe + ((size_t)bk * nme + jj) * ne;
+#pragma unroll
+            for (int e = 0; e < ne; e++) out[e] = col[e];
+        }
+    };
+    if (fused) {               // the record's cost + AL expansion first: its temporaries are dead before the RK4 step needs the registers
         double* rec_k = P.REC + ((size_t)b * P.N + k) * TO_REC_LEN;
-        compact_record_expansion(P, b, k, j, X, U, rec_k);
-        if (k == P.N - 2) compact_record_expansion(P, b, k + 1, j, X + n, U, rec_k + TO_REC_LEN);
+        compact_record_expansion(P, tab, b, k, j, X, U, rec_k);
+        if (sd < 6) compact_record_expansion(P, tab, b, k, lie_trivial(sd), X, U, rec_k);
+        if (k == P.N - 2) {
+            compact_record_expansion(P, tab, b, k + 1, j, X + n, U, rec_k + TO_REC_LEN);
+            if (sd < 6) compact_record_expansion(P, tab, b, k + 1, lie_trivial(sd), X + n, U, rec_k + TO_REC_LEN);
+        }
+    }
+    if (sd < 6) {              // closed-form column of a position / velocity coordinate
+        const int jt = lie_trivial(sd);
+        double col[ne];
+#pragma unroll
+        for (int e = 0; e < ne; e++) col[e] = (e == jt) ? 1.0 : ((jt >= 6 && e == jt - 6) ? h : 0.0);
+        store_column(jt, col);
     }
     D x[n], u[m], xn[n];
 #pragma unroll
     for (int i = 0; i < n; i++) { x[i].v = X[i]; x[i].d[0] = 0.0; }
 #pragma unroll
     for (int i = 0; i < m; i++) { u[i].v = U[i]; u[i].d[0] = (ne + i == j) ? 1.0 : 0.0; }
-    if (j < qs) {
-#pragma unroll
-        for (int i = 0; i < qs; i++) x[i].d[0] = (i == j) ? 1.0 : 0.0;
-    } else if (j < qs + 3) {
+    if (j < qs + 3) {
         const double w = X[qs], qx = X[qs + 1], qy = X[qs + 2], qz = X[qs + 3];
         const int c = j - qs;        // column c of L(q) H: (-x,w,z,-y), (-y,-z,w,x), (-z,y,-x,w)
         x[qs].d[0] = (c == 0) ? -qx : (c == 1) ? -qy : -qz;
@@ -189,7 +221,7 @@ __global__ void __launch_bounds__(128) k_expand_lie(const DevProblem P, int mode
 #pragma unroll
         for (int i = qs + 4; i < n; i++) x[i].d[0] = (i == j + 1) ? 1.0 : 0.0;
     }
-    rk4_step<MODEL, D>(P.params, x, u, P.dt[k], xn);
+    rk4_step<MODEL, D>(P.params, x, u, h, xn);
     const double* q1 = X + n + qs;                                     // attitude of knot k + 1
     const double w1 = q1[0], x1 = q1[1], y1 = q1[2], z1 = q1[3];
     double col[ne];
@@ -201,22 +233,12 @@ __global__ void __launch_bounds__(128) k_expand_lie(const DevProblem P, int mode
     col[qs + 2] = -z1 * t0 + y1 * t1 - x1 * t2 + w1 * t3;
 #pragma unroll
     for (int i = qs + 4; i < n; i++) col[i - 1] = xn[i].d[0];
-    if constexpr (FRAG) {
-        // element (row e, column j) of the record: (ks(e)*32 + 4*(c & 7) + fc(e))*2 + (c >> 3), c = physical index of column j
-        const int c = (int)((0x6420FDB9E7CA8531ULL >> (4 * j)) & 15);       // fraglayout::phys_z(j) as a nibble table
-        double* rec = P.REC + ((size_t)b * P.N + k) * TO_REC_LEN + 8 * (c & 7) + (c >> 3);
-#pragma unroll
-        for (int e = 0; e < ne; e++) rec[fraglayout::ab_index(e, 12)] = col[e];   // column 12 (u_0, c = 0) has a zero column offset
-    } else {
-        double* out = P.ABe + ((size_t)bk * nme + j) * ne;
-#pragma unroll
-        for (int e = 0; e < ne; e++) out[e] = col[e];
-    }
+    store_column(j, col);
 }
 
 cudaError_t launch_expand_lie(const DevProblem& P, cudaStream_t s, int mode) {
     if (P.model != MODEL_QUADROTOR) return cudaErrorNotSupported;
-    const long long total = (long long)P.B * (P.N - 1) * (P.ne + P.m);
+    const long long total = (long long)P.B * (P.N - 1) * 10;      // 10 dual-number seeds per knot (k_expand_lie: seed pruning)
     static_assert(fraglayout::phys_z(0) == 1 && fraglayout::phys_z(5) == 12 && fraglayout::phys_z(11) == 15 && fraglayout::phys_z(12) == 0 && fraglayout::phys_z(15) == 6, "nibble table of k_expand_lie");
     if (P.frag) k_expand_lie<MODEL_QUADROTOR, true><<<(unsigned)((total + 127) / 128), 128, 0, s>>>(P, mode);
     else k_expand_lie<MODEL_QUADROTOR, false><<<(unsigned)((total + 127) / 128), 128, 0, s>>>(P, mode);

@@ -59,6 +59,72 @@ end
 sense_code(::TO.Equality) = Int32(0)
 sense_code(::TO.Inequality) = Int32(1)
 sense_code(::TO.SecondOrderCone) = Int32(2)
+sense_code(::TO.IdentityCone) = Int32(3)
+sense_code(::TO.PositiveOrthant) = Int32(4)
+
+# ---- ConstraintList entry -> to_constraint_spec (include/trajopt_b200.h to_con_kind), every constraint type of src/constraints.jl ----
+# `root` keeps the arrays whose pointers go into the spec alive until to_create has copied them.
+const NULLI = Ptr{Int32}(C_NULL); const NULLD = Ptr{Float64}(C_NULL)
+function constraint_spec(con::TO.GoalConstraint, f, l, n, m, root)                    # src/constraints.jl:22-87
+    ii = root(Vector{Int32}(con.inds)); a = root(Vector{Float64}(con.xf))
+    ToConstraintSpec(0, f, l, 0, 0, 0, length(ii), pointer(ii), pointer(a), NULLD, NULLD, NULLD, 0.0)
+end
+function constraint_spec(con::TO.BoundConstraint, f, l, n, m, root)                   # :644-783
+    a = root(Vector{Float64}(con.z_max)); b = root(Vector{Float64}(con.z_min))
+    ToConstraintSpec(1, f, l, 1, 0, 0, 0, NULLI, pointer(a), pointer(b), NULLD, NULLD, 0.0)
+end
+function bound_base_spec(bnd, f, l, n, m, root, control::Bool)                        # StateBound / ControlBound :547-631 = Bound with the other block open
+    zmax = fill(Inf, n + m); zmin = fill(-Inf, n + m); off = control ? n : 0
+    zmax[off .+ bnd.i_max] .= bnd.x_max; zmin[off .+ bnd.i_min] .= bnd.x_min
+    a = root(zmax); b = root(zmin)
+    ToConstraintSpec(1, f, l, 1, 0, 0, 0, NULLI, pointer(a), pointer(b), NULLD, NULLD, 0.0)
+end
+constraint_spec(con::TO.StateBound, f, l, n, m, root) = bound_base_spec(con.bnd, f, l, n, m, root, false)
+constraint_spec(con::TO.ControlBound, f, l, n, m, root) = bound_base_spec(con.bnd, f, l, n, m, root, true)
+function constraint_spec(con::TO.LinearConstraint, f, l, n, m, root)                  # :103-150 -- A acts on z[inds]; the device takes the x or the u block
+    inds = collect(con.inds); P = length(con.b)
+    A = Matrix{Float64}(con.A)
+    if all(i -> i <= n, inds)
+        Af = zeros(P, n); Af[:, inds] .= A; flag = 0
+    elseif all(i -> i > n, inds)
+        Af = zeros(P, m); Af[:, inds .- n] .= A; flag = 1
+    else
+        throw(ArgumentError("LinearConstraint across states and controls: split it into a state and a control constraint for the device"))
+    end
+    a = root(Af); b = root(Vector{Float64}(con.b))                                     # column-major p x w, as the ABI wants
+    ToConstraintSpec(2, f, l, sense_code(con.sense), P, flag, 0, NULLI, pointer(a), pointer(b), NULLD, NULLD, 0.0)
+end
+function constraint_spec(con::TO.CircleConstraint, f, l, n, m, root)                  # :168-233
+    a = root(Vector{Float64}(con.x)); b = root(Vector{Float64}(con.y)); r = root(Vector{Float64}(con.radius))
+    ii = root(Int32[con.xi, con.yi])
+    ToConstraintSpec(3, f, l, 1, length(a), 0, 2, pointer(ii), pointer(a), pointer(b), NULLD, pointer(r), 0.0)
+end
+function constraint_spec(con::TO.SphereConstraint, f, l, n, m, root)                  # :249-326
+    a = root(Vector{Float64}(con.x)); b = root(Vector{Float64}(con.y)); c = root(Vector{Float64}(con.z)); r = root(Vector{Float64}(con.radius))
+    ii = root(Int32[con.xi, con.yi, con.zi])
+    ToConstraintSpec(4, f, l, 1, length(a), 0, 3, pointer(ii), pointer(a), pointer(b), pointer(c), pointer(r), 0.0)
+end
+function constraint_spec(con::TO.NormConstraint, f, l, n, m, root)                    # :438-521 (the static evaluate: z[inds[j]], SURVEY 2.4)
+    ii = root(Vector{Int32}(con.inds))
+    ToConstraintSpec(5, f, l, sense_code(con.sense), 0, 0, length(ii), pointer(ii), NULLD, NULLD, NULLD, NULLD, Float64(con.val))
+end
+function constraint_spec(con::TO.CollisionConstraint, f, l, n, m, root)               # :341-389
+    ii = root(Int32[con.x1; con.x2])
+    ToConstraintSpec(6, f, l, 1, 0, 0, length(ii), pointer(ii), NULLD, NULLD, NULLD, NULLD, con.radius)
+end
+function constraint_spec(con::TO.QuatVecEq, f, l, n, m, root)                         # :938-965
+    a = root(Vector{Float64}(Rotations.params(con.qf))); ii = root(Vector{Int32}(con.qind))
+    ToConstraintSpec(7, f, l, 0, 3, 0, 4, pointer(ii), pointer(a), NULLD, NULLD, NULLD, 0.0)
+end
+function constraint_spec(con::TO.IndexedConstraint, f, l, n, m, root)                 # :820-936: the inner constraint with its indices moved into the new z
+    ix, iu = collect(con.ix), collect(con.iu) .- con.n                                # positions of the old x / u inside the new x / u
+    constraint_spec(TO.change_dimension(con.con, n, m, ix, iu), f, l, n, m, root)
+end
+function constraint_spec(con::TO.StageConstraint, f, l, n, m, root)                   # RD.@autodiff user constraint: record RD.evaluate
+    tape = root(record((x, u) -> RD.evaluate(con, x, u), n, m))
+    P = RD.output_dim(con)
+    ToConstraintSpec(8, f, l, sense_code(TO.sense(con)), P, length(tape.consts), length(tape.prog), pointer(tape.prog), pointer(tape.consts), NULLD, NULLD, NULLD, 0.0)
+end
 
 """
     BatchedProblem(prob::TO.Problem, model_id, B; device=0, params=Float64[])
@@ -100,18 +166,7 @@ function BatchedProblem(prob::TO.Problem, mid::Integer, B::Integer; device::Inte
     cons = ToConstraintSpec[]
     for (inds, con) in zip(TO.get_constraints(prob))
         f, l = Int32(first(inds)), Int32(last(inds))
-        if con isa TO.GoalConstraint
-            ii = root(Vector{Int32}(con.inds)); a = root(Vector{Float64}(con.xf))
-            push!(cons, ToConstraintSpec(0, f, l, 0, 0, 0, length(ii), pointer(ii), pointer(a), C_NULL, C_NULL, C_NULL, 0.0))
-        elseif con isa TO.BoundConstraint
-            a = root(Vector{Float64}(con.z_max)); b = root(Vector{Float64}(con.z_min))
-            push!(cons, ToConstraintSpec(1, f, l, 1, 0, 0, 0, C_NULL, pointer(a), pointer(b), C_NULL, C_NULL, 0.0))
-        elseif con isa TO.QuatVecEq                              # src/constraints.jl:938-965
-            a = root(Vector{Float64}(Rotations.params(con.qf))); ii = root(Vector{Int32}(con.qind))
-            push!(cons, ToConstraintSpec(7, f, l, 0, 3, 0, 4, pointer(ii), pointer(a), C_NULL, C_NULL, C_NULL, 0.0))
-        else
-            error("constraint $(typeof(con)) : add its descriptor here (kinds 2-6 of to_con_kind)")
-        end
+        push!(cons, constraint_spec(con, f, l, n, m, root))
     end
     dt = root(Vector{Float64}([RD.timestep(z) for z in TO.get_trajectory(prob)][1:N-1]))
     root(costs); root(index); root(cons); root(params)
@@ -214,6 +269,49 @@ end
 function TO.constraint_jacobians!(p::BatchedProblem, con_index::Integer, jac::Array{Float64,4})    # src/abstract_constraint.jl:236-248
     check(p.h, ccall((:to_constraint_jacobians, libb200), Cint, (Ptr{Cvoid}, Int32, Ptr{Float64}), p.h, con_index - 1, jac)); jac
 end
+
+# ---- the same sweeps with the REFERENCE'S OWN SIGNATURES (src/abstract_constraint.jl:200-280), dispatching on a batched trajectory ----
+# Altro calls   evaluate_constraints!(sig, con, vals, Z, inds) / constraint_jacobians!(sig, dif, con, jac, vals, Z, inds)
+# with Z = get_trajectory(prob).  `get_trajectory(::BatchedProblem)` returns a BatchedTrajectory, so those calls land here unchanged; the
+# output containers are 3- / 4-dimensional arrays (p, length(inds), B) / (p, n+m, length(inds), B) instead of vectors of vectors.
+struct BatchedTrajectory
+    p::BatchedProblem
+end
+TO.get_trajectory(p::BatchedProblem) = BatchedTrajectory(p)
+function con_index(p::BatchedProblem, con, inds)
+    for (i, (ii, c)) in enumerate(zip(TO.get_constraints(p.prob)))
+        c === con && first(ii) == first(inds) && last(ii) == last(inds) && return i
+    end
+    throw(ArgumentError("constraint / knot range is not part of the batched problem's ConstraintList"))
+end
+TO.evaluate_constraints!(::RD.FunctionSignature, con::TO.StageConstraint, vals::Array{Float64,3}, Z::BatchedTrajectory, inds) =
+    TO.evaluate_constraints!(Z.p, con_index(Z.p, con, inds), vals)
+TO.constraint_jacobians!(::RD.FunctionSignature, ::RD.DiffMethod, con::TO.StageConstraint, jac::Array{Float64,4}, vals, Z::BatchedTrajectory, inds) =
+    TO.constraint_jacobians!(Z.p, con_index(Z.p, con, inds), jac)
+# second-order term: H[:, :, j, b] = d/dz (grad c' lambda) at knot inds[j] of instance b  (to_constraint_hessians; lambda = (p, length(inds), B) or nothing = the current multipliers)
+function TO.∇constraint_jacobians!(::RD.FunctionSignature, ::RD.DiffMethod, con::TO.StageConstraint, H::Array{Float64,4}, λ, vals, Z::BatchedTrajectory, inds)
+    lp = λ === nothing ? Ptr{Float64}(C_NULL) : pointer(λ)
+    GC.@preserve λ check(Z.p.h, ccall((:to_constraint_hessians, libb200), Cint, (Ptr{Cvoid}, Int32, Ptr{Float64}, Ptr{Float64}), Z.p.h, con_index(Z.p, con, inds) - 1, lp, H))
+    H
+end
+# cost expansion of every knot of every instance: RD.gradient!(cost, grad, z) / RD.hessian!(cost, hess, z)  (src/cost_functions.jl:137-233)
+function RD.gradient!(p::BatchedProblem, grad::Array{Float64,3})            # (n+m, N, B)
+    check(p.h, ccall((:to_cost_gradient, libb200), Cint, (Ptr{Cvoid}, Ptr{Float64}), p.h, grad)); grad
+end
+function RD.hessian!(p::BatchedProblem, hess::Array{Float64,4})             # (n+m, n+m, N, B), written symmetric
+    check(p.h, ccall((:to_cost_hessian, libb200), Cint, (Ptr{Cvoid}, Ptr{Float64}), p.h, hess)); hess
+end
+function TO.cost!(p::BatchedProblem, J::Matrix{Float64})                    # cost!(obj, Z) src/objective.jl:104-106: (N, B) knot costs
+    check(p.h, ccall((:to_cost_knots, libb200), Cint, (Ptr{Cvoid}, Ptr{Float64}), p.h, J)); J
+end
+# cones (src/cones.jl:71-276) on `count` vectors of length p at once: x, px (p, count); J, H (p, p, count)
+TO.projection!(p::BatchedProblem, cone::TO.ConstraintSense, px::Matrix{Float64}, x::Matrix{Float64}) =
+    (check(p.h, ccall((:to_projection, libb200), Cint, (Ptr{Cvoid}, Int32, Int32, Int32, Ptr{Float64}, Ptr{Float64}), p.h, sense_code(cone), size(x, 1), size(x, 2), x, px)); px)
+TO.∇projection!(p::BatchedProblem, cone::TO.ConstraintSense, J::Array{Float64,3}, x::Matrix{Float64}) =
+    (check(p.h, ccall((:to_grad_projection, libb200), Cint, (Ptr{Cvoid}, Int32, Int32, Int32, Ptr{Float64}, Ptr{Float64}), p.h, sense_code(cone), size(x, 1), size(x, 2), x, J)); J)
+TO.∇²projection!(p::BatchedProblem, cone::TO.ConstraintSense, H::Array{Float64,3}, x::Matrix{Float64}, b::Matrix{Float64}) =
+    (check(p.h, ccall((:to_hess_projection, libb200), Cint, (Ptr{Cvoid}, Int32, Int32, Int32, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}), p.h, sense_code(cone), size(x, 1), size(x, 2), x, b, H)); H)
+
 TO.set_goal_state!(p::BatchedProblem, xf::Vector{Float64}; objective=true, constraint=true) =      # src/problem.jl:294-310
     check(p.h, ccall((:to_set_goal_state, libb200), Cint, (Ptr{Cvoid}, Ptr{Float64}, Cint, Cint), p.h, xf, objective, constraint))
 

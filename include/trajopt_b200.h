@@ -196,6 +196,9 @@ int to_cost_gradient(to_handle* h, double* grad /*[B][N][n+m]*/);             /*
 int to_cost_hessian(to_handle* h, double* hess /*[B][N][n+m][n+m]*/);         /* RD.hessian!        src/cost_functions.jl:212-233 (written symmetric) */
 int to_eval_constraints(to_handle* h, int32_t con, double* vals /*[B][last-first+1][p]*/);      /* evaluate_constraints! src/abstract_constraint.jl:200-225 */
 int to_constraint_jacobians(to_handle* h, int32_t con, double* jac /*[B][last-first+1][n+m][p]*/); /* constraint_jacobians! src/abstract_constraint.jl:236-248 */
+int to_constraint_hessians(to_handle* h, int32_t con, const double* lambda /*[B][last-first+1][p], NULL = the current multipliers*/,
+                           double* H /*[B][last-first+1][n+m][n+m]*/);   /* grad-constraint_jacobians! src/abstract_constraint.jl:267-280: d/dz (cz' lambda) of every knot
+                                                                            (`∇jacobian!`: zero for Goal / Bound, src/constraints.jl:70-73, :767-770; second-order AD otherwise) */
 int to_max_violation(to_handle* h, double* v /*[B]*/);
 int to_merit(to_handle* h, double* J /*[B]*/);                                /* cost + AL penalty of the current trajectory */
 int to_al_expansion(to_handle* h, double* grad /*[B][N][n+m]*/, double* hess /*[B][N][n+m][n+m]*/); /* cost expansion incl. AL terms */

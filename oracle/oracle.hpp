@@ -506,6 +506,62 @@ inline void con_jacobian(const Constraint& con, const double* x, const double* u
     }
 }
 
+// RD.grad-jacobian!(con, H, lambda, c, z)  (reference: `∇jacobian!`, src/constraints.jl:70-73, :767-770 define it as zero for Goal / Bound; every
+// other type gets RobotDynamics' ForwardDiff default): H[(n+m) x (n+m)] = d/dz (cz' lambda) = sum_i lambda_i Hess c_i(z), overwritten.
+// Consumed through grad-constraint_jacobians! (src/abstract_constraint.jl:267-280) by solvers that keep the second-order constraint term.
+inline void con_hess_vec(const Constraint& con, const double* x, const double* u, const double* lam, double* H) {
+    const int w = con.n + con.m;
+    std::fill(H, H + w * w, 0.0);
+    auto add = [&](int i, int j, double v) { H[j * w + i] += v; };
+    switch (con.kind) {
+        case CON_GOAL: case CON_BOUND: case CON_LINEAR: break;                                   // linear in z
+        case CON_CIRCLE:
+            for (int i = 0; i < con.p; i++) { add(con.xi, con.xi, -2 * lam[i]); add(con.yi, con.yi, -2 * lam[i]); }
+            break;
+        case CON_SPHERE:
+            for (int i = 0; i < con.p; i++) { add(con.xi, con.xi, -2 * lam[i]); add(con.yi, con.yi, -2 * lam[i]); add(con.zi, con.zi, -2 * lam[i]); }
+            break;
+        case CON_NORM:
+            if (con.sense != CONE_SECOND_ORDER) for (int j : con.inds) add(j, j, 2 * lam[0]);   // c = |z_inds|^2 - val^2
+            break;
+        case CON_COLLISION: {                                                                    // c = r^2 - |x[x1] - x[x2]|^2
+            const size_t D = con.inds.size() / 2;
+            for (size_t i = 0; i < D; i++) {
+                const int a = con.inds[i], b = con.inds[D + i];
+                add(a, a, -2 * lam[0]); add(b, b, -2 * lam[0]); add(a, b, 2 * lam[0]); add(b, a, 2 * lam[0]);
+            }
+            break;
+        }
+        case CON_EXPR: {                                                                         // second-order forward mode: one pass per pair (j <= k)
+            Hyper reg[EXPR_MAXLEN];
+            const int L = (int)con.prog.size() / 3;
+            for (int j = 0; j < w; j++)
+                for (int k = j; k < w; k++) {
+                    expr_run(con.prog.data(), L, con.consts.data(), con.n, x, u, true, j, k, reg);
+                    double v = 0;
+                    for (int i = 0; i < con.p; i++) v += lam[i] * reg[L - con.p + i].d12;
+                    H[k * w + j] = v; H[j * w + k] = v;
+                }
+            break;
+        }
+        case CON_QUATVEC: {   // c_i = q_{i+1} / |q| - const:  d2 (q_a/|q|) / dq_j dq_k = -(d_aj q_k + d_ak q_j + d_jk q_a)/|q|^3 + 3 q_a q_j q_k / |q|^5
+            double q[4], n2 = 0;
+            for (int i = 0; i < 4; i++) { q[i] = x[con.inds[i]]; n2 += q[i] * q[i]; }
+            const double n1 = std::sqrt(n2), i3 = 1.0 / (n2 * n1), i5 = i3 / n2;
+            for (int j = 0; j < 4; j++)
+                for (int k = 0; k < 4; k++) {
+                    double v = 0;
+                    for (int i = 0; i < 3; i++) {
+                        const int a = i + 1;
+                        v += lam[i] * (-((a == j ? q[k] : 0.0) + (a == k ? q[j] : 0.0) + (j == k ? q[a] : 0.0)) * i3 + 3 * q[a] * q[j] * q[k] * i5);
+                    }
+                    add(con.inds[j], con.inds[k], v);
+                }
+            break;
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // Solver options -- Altro.jl `SolverOptions` defaults, restated (Altro is not under /root/reference).
 struct Options {

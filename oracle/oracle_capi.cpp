@@ -350,6 +350,22 @@ int orc_constraint_jacobians(orc_handle* h, int con, double* jac) {
     for (int b = 0; b < P.B; b++) constraint_jacobians(P, con, P.Xb(b), P.Ub(b), &jac[b * len]);
     return TO_OK;
 }
+// grad-constraint_jacobians! (src/abstract_constraint.jl:267-280): H[B][knots][(n+m)^2]; lambda [B][knots][p] or NULL = the current multipliers
+int orc_constraint_hessians(orc_handle* h, int con, const double* lambda, double* H) {
+    Problem& P = h->P;
+    if (con < 0 || con >= (int)P.cons.size()) return fail(h, TO_EINVAL, "constraint index out of range");
+    const Constraint& c = P.cons[con];
+    const int w = P.n + P.m;
+    const size_t len = (size_t)c.nknots();
+#pragma omp parallel for schedule(static)
+    for (int b = 0; b < P.B; b++)
+        for (int k = c.first; k <= c.last; k++) {
+            const double* u = (k == P.N) ? ZERO_U : &P.Ub(b)[(k - 1) * P.m];
+            const double* lam = lambda ? &lambda[((size_t)b * len + (k - c.first)) * c.p] : &P.lamb(b)[P.con_offset[con] + (size_t)(k - c.first) * c.p];
+            con_hess_vec(c, &P.Xb(b)[(k - 1) * P.n], u, lam, &H[((size_t)b * len + (k - c.first)) * w * w]);
+        }
+    return TO_OK;
+}
 int orc_constraint_info(orc_handle* h, int con, int32_t* p, int32_t* sense, int32_t* first, int32_t* last) {
     Problem& P = h->P;
     if (con < 0 || con >= (int)P.cons.size()) return fail(h, TO_EINVAL, "constraint index out of range");

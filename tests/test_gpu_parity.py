@@ -341,9 +341,13 @@ def test_autodiff_constraints_in_all_kernels():
     U = TO.controls(g)
     close(TO.evaluate_constraints(g, 2)[..., 0], np.linalg.norm(U, axis=-1) - 7.0, 1e-13, "ControlNorm value (docs KAT)")
     close(TO.constraint_jacobians(g, 2)[..., 0, n:], U / np.linalg.norm(U, axis=-1)[..., None], 1e-13, "ControlNorm Jacobian (docs KAT)")
+    rl = np.random.default_rng(2)
     for i in range(len(g.constraints)):
         close(TO.evaluate_constraints(g, i), TO.evaluate_constraints(o, i), KERNEL_RTOL, f"constraint {i} values")
         close(TO.constraint_jacobians(g, i), TO.constraint_jacobians(o, i), KERNEL_RTOL, f"constraint {i} jacobians")
+        lam = rl.standard_normal(TO.evaluate_constraints(o, i).shape)       # second-order term d/dz (grad c' lambda), src/abstract_constraint.jl:267-280
+        close(TO.constraint_hessians(g, i, lam), TO.constraint_hessians(o, i, lam), KERNEL_RTOL, f"constraint {i} second-order term")
+    close(TO.constraint_hessians(g, 2), TO.constraint_hessians(o, 2), KERNEL_RTOL, "second-order term with the current multipliers")
     close(TO.merit(g), TO.merit(o), KERNEL_RTOL, "merit"); close(TO.max_violation(g), TO.max_violation(o), KERNEL_RTOL, "violation")
     gg, gh = TO.al_expansion(g); og, oh = TO.al_expansion(o)
     close(gg, og, KERNEL_RTOL, "AL gradient"); close(gh, oh, KERNEL_RTOL, "AL hessian")
@@ -477,9 +481,12 @@ def test_general_constraints_in_solver_kernels(kind):
     g, o = _general_pair(kind)
     for p in (g, o):
         TO.rollout(p); TO.expand(p)
+    rl = np.random.default_rng(2)
     for i in range(len(g.constraints)):
         close(TO.evaluate_constraints(g, i), TO.evaluate_constraints(o, i), KERNEL_RTOL, f"constraint {i} values")
         close(TO.constraint_jacobians(g, i), TO.constraint_jacobians(o, i), KERNEL_RTOL, f"constraint {i} jacobians")
+        lam = rl.standard_normal(TO.evaluate_constraints(o, i).shape)
+        close(TO.constraint_hessians(g, i, lam), TO.constraint_hessians(o, i, lam), KERNEL_RTOL, f"constraint {i} second-order term")
     gg, gh = TO.al_expansion(g); og, oh = TO.al_expansion(o)
     close(gg, og, KERNEL_RTOL, "AL gradient"); close(gh, oh, KERNEL_RTOL, "AL hessian")
     assert np.array_equal(TO.backward(g), TO.backward(o))

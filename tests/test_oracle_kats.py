@@ -685,3 +685,48 @@ def test_objective_constructors_reference_test():
     TO.initial_controls(prob, r.standard_normal((1, N - 1, m))); TO.rollout(prob)
     Jk = TO.cost_knots(prob)
     assert np.isclose(TO.get_J(prob.obj).sum(), TO.cost(prob)[0]) and np.array_equal(TO.get_J(prob.obj), Jk[0])                               # :139-140
+
+
+def test_second_order_constraint_term_matches_finite_differences_of_the_jacobian():
+    """`∇constraint_jacobians!` (src/abstract_constraint.jl:267-280): H = d/dz (∇c' λ).  Zero for Goal / Bound / Linear (src/constraints.jl:70-73,
+    :767-770 set `H .= 0`); Circle / Sphere / Norm / Collision / QuatVecEq in closed form, user constraints by second-order forward mode -- all
+    checked against central differences of the constraint Jacobian the same library returns."""
+    from test_oracle_nlcost import control_norm
+    n, m, N, B = 13, 4, 6, 2
+    r = np.random.default_rng(8)
+    base = TO.problems.quadrotor(B=B, N=N, cls=OracleProblem, dt=0.05)
+    cons = base.constraints
+    extra = [TO.SphereConstraint(n, [0.5, 0.2], [1.0, 0.5], [1.5, 1.2], [0.3, 0.25]), TO.NormConstraint(n, m, 3.0, TO.Inequality(), [8, 9, 10]),
+             TO.NormConstraint(n, m, 12.0, TO.SecondOrderCone(), "control"), TO.CollisionConstraint(n, [1, 2, 3], [8, 9, 10], 0.4),
+             TO.QuatVecEq(n, m, np.array([0.6, 0.0, 0.8, 0.0])), TO.AutodiffConstraint(n, m, control_norm(7.0), TO.Inequality(), "control"),
+             TO.AutodiffConstraint(n, m, lambda x, u: [TO.sin(x[0]) * u[1] + x[3] * x[4] * x[5], TO.exp(0.1 * u[0]) - x[7] ** 3], TO.Equality())]
+    for c in extra:
+        TO.add_constraint(cons, c, (1, N - 1))
+    prob = OracleProblem(base.model, base.obj, base.x0, 0.05 * (N - 1), xf=base.xf, constraints=cons)
+    X = r.standard_normal((B, N, n)); X[..., 3:7] += [2.0, 0, 0, 0]
+    U = 1.0 + r.standard_normal((B, N - 1, m))
+    TO.initial_states(prob, X); TO.initial_controls(prob, U)
+    eps = 1e-6
+    for i, con in enumerate(prob.constraints.constraints):
+        first, last = prob.constraints.inds[i]
+        L = last - first + 1
+        lam = r.standard_normal((B, L, con.p))
+        H = TO.constraint_hessians(prob, i, lam)
+        assert np.allclose(H, np.swapaxes(H, -1, -2), atol=1e-12)
+        if isinstance(con, (TO.GoalConstraint, TO.BoundConstraint)) or (isinstance(con, TO.NormConstraint) and con.p > 1):
+            assert not H.any()
+            continue
+        Hfd = np.zeros_like(H)
+        for j in range(n + m):
+            for sgn in (1.0, -1.0):
+                Xp, Up = X.copy(), U.copy()
+                if j < n: Xp[..., j] += sgn * eps
+                else: Up[..., j - n] += sgn * eps
+                TO.initial_states(prob, Xp); TO.initial_controls(prob, Up)
+                J = TO.constraint_jacobians(prob, i)                     # [B, L, p, n+m]
+                Hfd[:, :, j, :] += sgn * np.einsum("blp,blpz->blz", lam, J) / (2 * eps)
+        TO.initial_states(prob, X); TO.initial_controls(prob, U)
+        if last == N:                                                    # the terminal knot has no controls
+            Hfd[:, -1, n:, :] = 0; Hfd[:, -1, :, n:] = 0; H = H.copy(); H[:, -1, n:, :] = 0; H[:, -1, :, n:] = 0
+        assert np.allclose(H, Hfd, rtol=1e-6, atol=1e-6), (type(con).__name__, np.abs(H - Hfd).max())
+    prob.close(); base.close()

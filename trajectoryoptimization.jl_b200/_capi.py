@@ -147,6 +147,7 @@ def load_library():
         "to_rollout": [H], "to_expand": [H], "to_get_dynamics_jacobians": [H, c_double_p],
         "to_cost": [H, c_double_p], "to_cost_knots": [H, c_double_p], "to_cost_gradient": [H, c_double_p], "to_cost_hessian": [H, c_double_p],
         "to_eval_constraints": [H, C.c_int32, c_double_p], "to_constraint_jacobians": [H, C.c_int32, c_double_p],
+        "to_constraint_hessians": [H, C.c_int32, c_double_p, c_double_p],
         "to_max_violation": [H, c_double_p], "to_merit": [H, c_double_p], "to_al_expansion": [H, c_double_p, c_double_p],
         "to_projection": [H, C.c_int32, C.c_int32, C.c_int32, c_double_p, c_double_p],
         "to_grad_projection": [H, C.c_int32, C.c_int32, C.c_int32, c_double_p, c_double_p],

@@ -1307,6 +1307,19 @@ def constraint_jacobians(prob, con):
     return np.swapaxes(jac, -1, -2)
 
 
+def constraint_hessians(prob, con, lam=None):
+    """``∇constraint_jacobians!(sig, diff, con, H, λ, c, Z, inds)`` (src/abstract_constraint.jl:267-280): the second-order constraint term
+    ``d/dz (∇c' λ)`` of every knot in the constraint's range -> ``[B, len(inds), n+m, n+m]``; ``lam`` ``[B, len, p]`` (default: the
+    problem's current multipliers)."""
+    i = _con_index(prob, con)
+    first, last = prob.constraints.inds[i]
+    nm = prob.n + prob.m
+    H = np.empty((prob.B, last - first + 1, nm, nm))
+    lp = None if lam is None else K._dp(_bcast(lam, (prob.B, last - first + 1, prob.constraints[i].p), "lambda"))
+    prob._call("to_constraint_hessians", i, lp, K._dp(H))
+    return H
+
+
 def max_violation(prob):
     v = np.empty(prob.B)
     prob._call("to_max_violation", K._dp(v))

@@ -51,8 +51,6 @@ struct to_handle {
     Scratch scratch;
     double t0 = 0;
     bool J_valid = false, expanded = false, backward_done = false;
-    bool rec_valid = false;       // record path: the cost + AL expansion written by k_expand_lie is current (nothing it depends on -- trajectory,
-                                  // multipliers, penalties, cost tables -- has changed since)
     int64_t launches = 0;
     // phase timing
     bool timing = false;
@@ -525,6 +523,9 @@ int to_create(const to_spec* s, to_handle** out) {
     if (!okc) { h->err = std::string("device initialisation failed: ") + cudaGetErrorString(cudaGetLastError()); return bail(TO_ECUDA); }
     rc = upload_tables(h);
     if (rc) return bail(rc);
+    if (P.lie && P.model == MODEL_QUADROTOR) {        // the position / velocity columns of [A_e B_e] are functions of the time steps alone (rollout.cu)
+        if (launch_trivial_columns(P, st) != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess) { h->err = "k_trivial_columns failed"; return bail(TO_ECUDA); }
+    }
     *out = h;
     return TO_OK;
 }
@@ -569,7 +570,7 @@ int to_set_options(to_handle* h, const to_options* o) {
         CU(h, cudaMemsetAsync(h->P.drho, 0, sizeof(double) * h->P.B, h->stream));
         CU(h, cudaStreamSynchronize(h->stream));     // `r` goes out of scope
     }
-    h->J_valid = false; h->rec_valid = false;
+    h->J_valid = false;
     return upload_tables(h);
 }
 
@@ -630,7 +631,7 @@ int to_set_initial_state(to_handle* h, const double* x0) {
     JOIN(h);
     if (!h || !x0) return TO_EINVAL;
     CU(h, cudaMemcpyAsync(h->P.x0, x0, sizeof(double) * (size_t)h->P.B * h->P.n, cudaMemcpyHostToDevice, h->stream));
-    h->J_valid = false; h->rec_valid = false;
+    h->J_valid = false;
     return TO_OK;
 }
 int to_set_controls(to_handle* h, const double* U) {
@@ -638,7 +639,7 @@ int to_set_controls(to_handle* h, const double* U) {
     if (!h || !U) return TO_EINVAL;
     CU(h, cudaMemcpyAsync(h->d_stageU, U, sizeof(double) * h->P.strideU, cudaMemcpyHostToDevice, h->stream));
     CU(h, launch_scatter_traj(h->P, nullptr, h->d_stageU, h->stream)); h->launches++;
-    h->J_valid = false; h->rec_valid = false; h->expanded = false; h->backward_done = false;
+    h->J_valid = false; h->expanded = false; h->backward_done = false;
     return TO_OK;
 }
 int to_set_states(to_handle* h, const double* X) {
@@ -646,7 +647,7 @@ int to_set_states(to_handle* h, const double* X) {
     if (!h || !X) return TO_EINVAL;
     CU(h, cudaMemcpyAsync(h->d_stageX, X, sizeof(double) * h->P.strideX, cudaMemcpyHostToDevice, h->stream));
     CU(h, launch_scatter_traj(h->P, h->d_stageX, nullptr, h->stream)); h->launches++;
-    h->J_valid = false; h->rec_valid = false; h->expanded = false; h->backward_done = false;
+    h->J_valid = false; h->expanded = false; h->backward_done = false;
     return TO_OK;
 }
 int to_get_states(to_handle* h, double* X) {
@@ -690,7 +691,7 @@ int to_set_goal_state(to_handle* h, const double* xf, int objective, int constra
     if (constraint)
         for (auto& c : h->h_cons)
             if (c.kind == CON_GOAL) for (int i = 0; i < c.p; i++) c.a[i] = xf[c.inds[i]];
-    h->J_valid = false; h->rec_valid = false;
+    h->J_valid = false;
     return upload_tables(h);
 }
 
@@ -707,7 +708,7 @@ int to_update_trajectory(to_handle* h, const double* Xref, const double* Uref, i
         for (int a = 0; a < n; a++) { double t = 0; for (int j = 0; j < n; j++) t += c.Q[j * n + a] * xf[j]; c.q[a] = -t; }
         for (int a = 0; a < m; a++) { double t = 0; for (int j = 0; j < m; j++) t += c.R[j * m + a] * uf[j]; c.r[a] = -t; }
     }
-    h->J_valid = false; h->rec_valid = false; h->expanded = false; h->backward_done = false;
+    h->J_valid = false; h->expanded = false; h->backward_done = false;
     return upload_tables(h);
 }
 int to_shift_trajectory(to_handle* h, int32_t steps) {
@@ -717,18 +718,18 @@ int to_shift_trajectory(to_handle* h, int32_t steps) {
     if (steps > h->P.N - 1) steps = h->P.N - 1;
     CU(h, launch_shift_traj(h->P, steps, h->stream)); h->launches++;
     for (int k = 0; k < steps; k++) h->t0 += h->h_dt[k];
-    h->J_valid = false; h->rec_valid = false; h->expanded = false; h->backward_done = false;
+    h->J_valid = false; h->expanded = false; h->backward_done = false;
     return TO_OK;
 }
 int to_rollout(to_handle* h) {
     JOIN(h);
     if (!h) return TO_EINVAL;
     CU(h, launch_rollout(h->P, h->stream)); h->launches++;
-    h->J_valid = false; h->rec_valid = false; h->expanded = false; h->backward_done = false;
+    h->J_valid = false; h->expanded = false; h->backward_done = false;
     return TO_OK;
 }
-// the dynamics expansion kernel also writes the records' cost + AL expansion when the Goal / Bound rows fit its shared-memory table
-// (rollout.cu ExpTab: <= 3 rows per z entry, knot indices < 4095, < 128 rows per knot); otherwise k_expansion_rec does it
+// the records' cost + AL expansion comes from the host-built term table (common.cuh ExpTab) when the Goal / Bound rows fit it:
+// <= 3 rows per z entry, knot indices < 4095, < 128 rows per knot; otherwise k_expansion_rec walks the descriptors
 static bool rec_fused(const DevProblem& P) { return P.frag && P.max_terms_per_z <= 3 && P.N < 4095 && P.max_p_knot < 128; }
 int to_expand(to_handle* h) {
     JOIN(h);
@@ -736,7 +737,6 @@ int to_expand(to_handle* h) {
     { PhaseScope ps(h, TO_PHASE_EXPAND); CU(h, launch_expand(h->P, h->stream)); if (h->P.lie) { CU(h, launch_expand_lie(h->P, h->stream)); h->launches++; } }
     h->launches++; h->phase_launches[TO_PHASE_EXPAND]++;
     h->expanded = true; h->backward_done = false;
-    h->rec_valid = rec_fused(h->P);       // k_expand_lie wrote the records' cost + AL expansion too
     return TO_OK;
 }
 int to_get_dynamics_jacobians(to_handle* h, double* AB) {
@@ -817,6 +817,21 @@ int to_constraint_jacobians(to_handle* h, int32_t con, double* jac) {
     CU(h, cudaStreamSynchronize(h->stream));
     return TO_OK;
 }
+int to_constraint_hessians(to_handle* h, int32_t con, const double* lambda, double* H) {
+    JOIN(h);
+    if (!h || !H) return TO_EINVAL;
+    if (con < 0 || con >= (int)h->h_cons.size()) return fail(h, TO_EINVAL, "constraint index out of range");
+    const DevCon& c = h->h_cons[con];
+    const int len = c.last - c.first + 1, w = h->P.n + h->P.m;
+    const size_t nh = (size_t)h->P.B * len * w * w, nl = (size_t)h->P.B * len * c.p;
+    int rc = ensure_scratch(h, (nh + nl) * sizeof(double)); if (rc) return rc;
+    double* dH = (double*)h->scratch.ptr; double* dl = dH + nh;
+    if (lambda) CU(h, cudaMemcpyAsync(dl, lambda, nl * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    CU(h, launch_constraint_hessians(h->P, con, len, lambda ? dl : nullptr, dH, h->stream)); h->launches++;
+    CU(h, cudaMemcpyAsync(H, dH, nh * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
+    return TO_OK;
+}
 static int ensure_merit(to_handle* h) {
     if (h->J_valid) return TO_OK;
     CU(h, launch_merit(h->P, h->P.J, h->d_viol, h->stream)); h->launches++;
@@ -890,11 +905,12 @@ static int materialise_expansion(to_handle* h, double* EG, double* EH) {
 static int do_backward(to_handle* h) {
     // to_options.backward_kernel: 0 automatic, 3 generic DFMA kernel on the full expansion, 5 shared-memory tensor kernel on the compact expansion
     if (h->P.frag && h->P.opt.pad != 3 && h->P.opt.pad != 5) {
-        if (!h->rec_valid) {      // normally written by the dynamics expansion kernel; stale after to_al_update / to_set_multipliers / ... without a new to_expand
-            { PhaseScope pe(h, TO_PHASE_COSTEXP); CU(h, launch_expansion_rec(h->P, h->stream)); }
-            h->launches++; h->phase_launches[TO_PHASE_COSTEXP]++;
-            h->rec_valid = true;
+        {   // cost + AL expansion of every record: always from the current trajectory, multipliers and penalties
+            PhaseScope pe(h, TO_PHASE_COSTEXP);
+            if (rec_fused(h->P)) CU(h, launch_expansion_rec16(h->P, h->stream));      // 16 lanes per knot, host-built term table
+            else CU(h, launch_expansion_rec(h->P, h->stream));                          // more than 3 rows on one z entry: descriptor walk
         }
+        h->launches++; h->phase_launches[TO_PHASE_COSTEXP]++;
         PhaseScope ps(h, TO_PHASE_BACKWARD);
         CU(h, launch_backward_frag(h->P, h->d_fragq, h->stream));
     } else if (h->P.dense_riccati) {
@@ -919,7 +935,7 @@ static int do_forward(to_handle* h) {
     { PhaseScope ps(h, TO_PHASE_LADDER); CU(h, launch_ladder(h->P, h->stream)); }     // remaining trials + commit of failures
     h->launches++; h->phase_launches[TO_PHASE_LADDER]++;
 
-    h->expanded = false; h->backward_done = false; h->rec_valid = false;   // the trajectory moved
+    h->expanded = false; h->backward_done = false;   // the trajectory moved
     return TO_OK;
 }
 int to_backward(to_handle* h, int32_t* status) {
@@ -968,7 +984,6 @@ int to_ilqr_step(to_handle* h, int32_t iters) {
         h->launches++; h->phase_launches[TO_PHASE_EXPAND]++;
         JOIN(h);
         h->expanded = true;
-        h->rec_valid = rec_fused(h->P);
         rc = do_backward(h); if (rc) return rc;
         { PhaseScope ps(h, TO_PHASE_FORWARD); CU(h, launch_forward(h->P, h->stream)); }
         h->launches++; h->phase_launches[TO_PHASE_FORWARD]++;
@@ -982,7 +997,7 @@ int to_ilqr_step(to_handle* h, int32_t iters) {
             PhaseScope ps(h, TO_PHASE_LADDER); CU(h, launch_ladder(h->P, h->stream));
         }
         h->launches++; h->phase_launches[TO_PHASE_LADDER]++;
-        h->expanded = false; h->backward_done = false; h->rec_valid = false;   // the trajectory moved
+        h->expanded = false; h->backward_done = false;   // the trajectory moved
     }
     return TO_OK;
 }
@@ -993,7 +1008,7 @@ int to_al_update(to_handle* h) {
     for (auto& mu : h->h_mu) mu = std::fmin(mu * h->P.opt.penalty_scaling, h->P.opt.penalty_max);
     if (!h->h_mu.empty()) CU(h, cudaMemcpyAsync(h->d_mu, h->h_mu.data(), sizeof(double) * h->h_mu.size(), cudaMemcpyHostToDevice, h->stream));
     CU(h, cudaStreamSynchronize(h->stream));
-    h->J_valid = false; h->rec_valid = false;
+    h->J_valid = false;
     return upload_exptab(h);        // the penalties are part of the table
 }
 int to_get_gains(to_handle* h, double* K, double* d) {
@@ -1060,7 +1075,7 @@ static int multipliers_copy(to_handle* h, int32_t con, double* host, bool to_hos
         CU(h, cudaMemcpy2DAsync(host, len * sizeof(double), h->P.lambda + c.offset, (size_t)h->P.lambda_len * sizeof(double), len * sizeof(double), h->P.B, cudaMemcpyDeviceToHost, h->stream));
     } else {
         CU(h, cudaMemcpy2DAsync(h->P.lambda + c.offset, (size_t)h->P.lambda_len * sizeof(double), host, len * sizeof(double), len * sizeof(double), h->P.B, cudaMemcpyHostToDevice, h->stream));
-        h->J_valid = false; h->rec_valid = false;
+        h->J_valid = false;
     }
     CU(h, cudaStreamSynchronize(h->stream));
     return TO_OK;
@@ -1079,7 +1094,7 @@ int to_set_penalty(to_handle* h, int32_t con, double mu) {
     h->h_mu[con] = mu;
     CU(h, cudaMemcpyAsync(h->d_mu, h->h_mu.data(), sizeof(double) * h->h_mu.size(), cudaMemcpyHostToDevice, h->stream));
     CU(h, cudaStreamSynchronize(h->stream));
-    h->J_valid = false; h->rec_valid = false;
+    h->J_valid = false;
     return upload_exptab(h);
 }
 int to_get_solver_state(to_handle* h, double* rho, double* dV, double* alpha, int32_t* ls_iters, int32_t* bp_status) {

@@ -315,6 +315,59 @@ __device__ inline void con_jacobian(const DevCon& con, int n, int m, const doubl
     }
 }
 
+// H[(n+m)^2] col-major = d/dz (cz' lambda) = sum_i lambda_i Hess c_i(z), overwritten: the second-order constraint term the reference hands to
+// solvers through grad-constraint_jacobians! (src/abstract_constraint.jl:267-280; `∇jacobian!` is zero for Goal / Bound, src/constraints.jl:70-73,
+// :767-770, ForwardDiff for the rest).
+__device__ inline void con_hess_vec(const DevCon& con, int n, int m, const double* x, const double* u, const double* lam, double* H) {
+    const int w = n + m;
+    for (int i = 0; i < w * w; i++) H[i] = 0.0;
+    switch (con.kind) {
+        case CON_CIRCLE: case CON_SPHERE: {
+            const int nd = con.kind == CON_CIRCLE ? 2 : 3;
+            for (int i = 0; i < con.p; i++) for (int d = 0; d < nd; d++) H[con.inds[d] * w + con.inds[d]] += -2 * lam[i];
+            break;
+        }
+        case CON_NORM:
+            if (con.sense != CONE_SECOND_ORDER) for (int i = 0; i < con.ninds; i++) H[con.inds[i] * w + con.inds[i]] += 2 * lam[0];
+            break;
+        case CON_COLLISION: {
+            const int D = con.ninds / 2;
+            for (int i = 0; i < D; i++) {
+                const int a = con.inds[i], b = con.inds[D + i];
+                H[a * w + a] += -2 * lam[0]; H[b * w + b] += -2 * lam[0]; H[b * w + a] += 2 * lam[0]; H[a * w + b] += 2 * lam[0];
+            }
+            break;
+        }
+        case CON_EXPR: {
+            Hyper reg[TO_EXPR_LEN];
+            for (int j = 0; j < w; j++)
+                for (int k = j; k < w; k++) {
+                    expr_run(con.prog, con.prog_len, con.pconst, n, x, u, true, j, k, reg);
+                    double v = 0;
+                    for (int i = 0; i < con.p; i++) v += lam[i] * reg[con.prog_len - con.p + i].d12;
+                    H[k * w + j] = v; H[j * w + k] = v;
+                }
+            break;
+        }
+        case CON_QUATVEC: {
+            double q[4], n2 = 0;
+            for (int i = 0; i < 4; i++) { q[i] = x[con.inds[i]]; n2 = fma(q[i], q[i], n2); }
+            const double n1 = sqrt(n2), i3 = 1.0 / (n2 * n1), i5 = i3 / n2;
+            for (int j = 0; j < 4; j++)
+                for (int k = 0; k < 4; k++) {
+                    double v = 0;
+                    for (int i = 0; i < 3; i++) {
+                        const int a = i + 1;
+                        v += lam[i] * (-((a == j ? q[k] : 0.0) + (a == k ? q[j] : 0.0) + (j == k ? q[a] : 0.0)) * i3 + 3 * q[a] * q[j] * q[k] * i5);
+                    }
+                    H[con.inds[k] * w + con.inds[j]] += v;
+                }
+            break;
+        }
+        default: break;   // Goal, Bound, Linear: linear in z
+    }
+}
+
 // returns 0, or 1 for the reference's "Invalid second-order cone projection" error branch
 __device__ inline int cone_projection(int cone, const double* x, int p, double* px) {
     switch (cone) {

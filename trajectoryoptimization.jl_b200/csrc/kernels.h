@@ -13,6 +13,7 @@ cudaError_t launch_cost_hessian(const DevProblem& P, double* hess, cudaStream_t 
 cudaError_t launch_al_expansion(const DevProblem& P, double* grad, double* hess, cudaStream_t s);
 cudaError_t launch_eval_constraints(const DevProblem& P, int con, double* vals, cudaStream_t s);
 cudaError_t launch_constraint_jacobians(const DevProblem& P, int con, double* jac, cudaStream_t s);
+cudaError_t launch_constraint_hessians(const DevProblem& P, int con, int len, const double* lam, double* H, cudaStream_t s);
 cudaError_t launch_projection(int cone, int p, int count, const double* x, double* px, int* err, cudaStream_t s);
 cudaError_t launch_grad_projection(int cone, int p, int count, const double* x, double* J, int* err, cudaStream_t s);
 cudaError_t launch_hess_projection(int cone, int p, int count, const double* x, const double* b, double* H, int* err, cudaStream_t s);
@@ -35,6 +36,8 @@ cudaError_t launch_expansion_compact(const DevProblem& P, cudaStream_t s);      
 cudaError_t launch_expand_lie(const DevProblem& P, cudaStream_t s, int mode = 0);     // [A_e B_e] straight from the dual-number RK4 step (rollout.cu)
 // register-resident Riccati pass of the error-state Quadrotor + its record producers   (riccati_frag.cu)
 cudaError_t launch_expansion_rec(const DevProblem& P, cudaStream_t s);                 // compact expansion -> REC[192..240) of every knot
+cudaError_t launch_expansion_rec16(const DevProblem& P, cudaStream_t s);               // ... 16 lanes per knot, from the host-built term table (rollout.cu)
+cudaError_t launch_trivial_columns(const DevProblem& P, cudaStream_t s);               // closed-form position / velocity columns of [A_e B_e], once per problem
 cudaError_t launch_export_abe(const DevProblem& P, cudaStream_t s);                    // REC fragments -> ABe (col-major 12 x 16)
 size_t frag_queue_ints(int B);                                                         // ints of the kernel's work queue (allocated by the handle)
 cudaError_t launch_backward_frag(const DevProblem& P, int* queue, cudaStream_t s);

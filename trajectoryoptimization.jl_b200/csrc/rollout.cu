@@ -102,67 +102,22 @@ __device__ __forceinline__ void compact_entry_expansion(const DevProblem& P, con
     }
 }
 
-// Expansion part of the record of knot k (frag_layout.cuh [192, 240)) written by the 16 column threads of that knot: thread j owns the
-// error-state coordinate j.  Outside the attitude the error-state expansion of a diagonal full-state one is the same entry; the three
-// attitude threads project the quaternion block: G'g, G' diag(h) G - (q'g_q) I3 (Altro error_expansion!; lie.cu k_expansion_compact is the
-// one-thread-per-knot version of the same numbers).
-__device__ __forceinline__ void compact_record_expansion(const DevProblem& P, const ExpTab& tab, int b, int k, int j, const double* __restrict__ X, const double* __restrict__ U,
-                                                         double* __restrict__ rec) {
-    constexpr int qs = 3;
-    const int n = P.n;
-    const double* lam_b = P.lambda + (size_t)b * P.lambda_len;
-    const int p = (int)((0x6420FDB9E7CA8531ULL >> (4 * j)) & 15);
-    if (j >= qs && j < qs + 3) {
-        const int c = j - qs;
-        double g[4], h[4], q[4];
-#pragma unroll
-        for (int r = 0; r < 4; r++) { q[r] = X[qs + r]; compact_entry_expansion(P, tab, k, qs + r, q[r], lam_b, g[r], h[r]); }
-        // rows of G' = (L(q) H)': (-x,w,z,-y), (-y,-z,w,x), (-z,y,-x,w)   (kept in registers: no run-time indexed arrays)
-        const double G0[4] = {-q[1], q[0], q[3], -q[2]}, G1[4] = {-q[2], -q[3], q[0], q[1]}, G2[4] = {-q[3], q[2], -q[1], q[0]};
-        double gc[4];
-#pragma unroll
-        for (int r = 0; r < 4; r++) gc[r] = (c == 0) ? G0[r] : (c == 1) ? G1[r] : G2[r];
-        double qb = 0.0, ge = 0.0, hb0 = 0.0, hb1 = 0.0, hb2 = 0.0;
-#pragma unroll
-        for (int r = 0; r < 4; r++) {
-            qb += q[r] * g[r]; ge += gc[r] * g[r];
-            const double t = gc[r] * h[r];
-            hb0 += t * G0[r]; hb1 += t * G1[r]; hb2 += t * G2[r];
-        }
-        const double hd = ((c == 0) ? hb0 : (c == 1) ? hb1 : hb2) - qb;
-        rec[TO_REC_G + p] = ge; rec[TO_REC_HD + p] = hd;
-        rec[TO_REC_HB + 4 * c + 0] = (c == 0) ? hd : hb0;
-        rec[TO_REC_HB + 4 * c + 1] = (c == 1) ? hd : hb1;
-        rec[TO_REC_HB + 4 * c + 2] = (c == 2) ? hd : hb2;
-        rec[TO_REC_HB + 4 * c + 3] = 0.0;
-    } else {
-        const int i = (j < qs) ? j : (j < n - 1 ? j + 1 : j + 1);       // full-state index of the coordinate (controls: n + a = j + 1)
-        const double zi = (i < n) ? X[i] : ((k == P.N - 1) ? 0.0 : U[i - n]);
-        double g, h;
-        compact_entry_expansion(P, tab, k, i, zi, lam_b, g, h);
-        rec[TO_REC_G + p] = g; rec[TO_REC_HD + p] = h;
-        if (j == 7) { rec[TO_REC_HB + 12] = 0.0; rec[TO_REC_HB + 13] = 0.0; rec[TO_REC_HB + 14] = 0.0; rec[TO_REC_HB + 15] = h; }   // p = 14 is row 3 of Hb
-    }
-}
-
 // Seed pruning.  The position r and the (world-frame) linear velocity v of a RigidBody enter the dynamics only through rdot = v: f does not
 // depend on r, and on v only in rdot.  Their columns of the discrete Jacobian are therefore known in closed form -- d x+/d r = e_r and
 // d x+/d v = h e_r + e_v (the RK4 weights sum to one) -- and need no dual-number sweep: 10 seeds (attitude, angular velocity, controls) are
-// pushed through the RK4 step instead of 16, one thread each; the six trivial columns are written by the first six of them.
+// pushed through the RK4 step instead of 16, one thread each; the six trivial columns depend on the time steps only and are written once,
+// when the problem is created (k_trivial_columns).
 __device__ __forceinline__ int lie_seed(int s) { return (int)((0xFEDCBA9543ULL >> (4 * s)) & 15); }       // 3,4,5,9,10,11,12,13,14,15
 __device__ __forceinline__ int lie_trivial(int s) { return (int)((0x876210ULL >> (4 * s)) & 15); }        // 0,1,2,6,7,8
 
-// FRAG: the column goes into the fragment block of the knot's record (frag_layout.cuh) instead of P.ABe, and the thread writes its share of
-// the record's cost + AL expansion (the terminal knot's by the threads of knot N-2).
+// FRAG: the column goes into the fragment block of the knot's record (frag_layout.cuh) instead of P.ABe.
 #ifndef TO_EXPAND_LIE_MINB
-#define TO_EXPAND_LIE_MINB 3      // CTAs per SM the register allocation aims at (A/B: profiles/scripts/build_variant.sh)
+#define TO_EXPAND_LIE_MINB 4      // CTAs per SM the register allocation aims at: 128 registers, 16 warps per SM (r02g: 0.29 vs 0.37 ms at 168 registers / 12 warps)
 #endif
 template <int MODEL, bool FRAG>
 __global__ void __launch_bounds__(128, TO_EXPAND_LIE_MINB) k_expand_lie(const DevProblem P, int mode) {
     constexpr int n = ModelDims<MODEL>::n, m = ModelDims<MODEL>::m, ne = n - 1, nme = ne + m, qs = 3, NS = 10;
     using D = Dual<1>;
-    const bool fused = FRAG && P.max_terms_per_z <= TO_EXP_MAXT && P.N < 4095 && P.max_p_knot < 128;     // == capi.cu rec_fused
-    const ExpTab& tab = *P.exptab;
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long total = (long long)P.B * (P.N - 1) * NS;
     if (t >= total) return;
@@ -189,22 +144,6 @@ __global__ void __launch_bounds__(128, TO_EXPAND_LIE_MINB) k_expand_lie(const De
             for (int e = 0; e < ne; e++) out[e] = col[e];
         }
     };
-    if (fused) {               // the record's cost + AL expansion first: its temporaries are dead before the RK4 step needs the registers
-        double* rec_k = P.REC + ((size_t)b * P.N + k) * TO_REC_LEN;
-        compact_record_expansion(P, tab, b, k, j, X, U, rec_k);
-        if (sd < 6) compact_record_expansion(P, tab, b, k, lie_trivial(sd), X, U, rec_k);
-        if (k == P.N - 2) {
-            compact_record_expansion(P, tab, b, k + 1, j, X + n, U, rec_k + TO_REC_LEN);
-            if (sd < 6) compact_record_expansion(P, tab, b, k + 1, lie_trivial(sd), X + n, U, rec_k + TO_REC_LEN);
-        }
-    }
-    if (sd < 6) {              // closed-form column of a position / velocity coordinate
-        const int jt = lie_trivial(sd);
-        double col[ne];
-#pragma unroll
-        for (int e = 0; e < ne; e++) col[e] = (e == jt) ? 1.0 : ((jt >= 6 && e == jt - 6) ? h : 0.0);
-        store_column(jt, col);
-    }
     D x[n], u[m], xn[n];
 #pragma unroll
     for (int i = 0; i < n; i++) { x[i].v = X[i]; x[i].d[0] = 0.0; }
@@ -234,6 +173,99 @@ __global__ void __launch_bounds__(128, TO_EXPAND_LIE_MINB) k_expand_lie(const De
 #pragma unroll
     for (int i = qs + 4; i < n; i++) col[i - 1] = xn[i].d[0];
     store_column(j, col);
+}
+
+// the closed-form columns of [A_e B_e] (positions, velocities): thread = (instance, knot, one of the six)
+template <bool FRAG>
+__global__ void __launch_bounds__(128) k_trivial_columns(const DevProblem P) {
+    constexpr int ne = 12, nme = 16;
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (long long)P.B * (P.N - 1) * 6) return;
+    const int sd = (int)(t % 6);
+    const long long bk = t / 6;
+    const int k = (int)(bk % (P.N - 1)), b = (int)(bk / (P.N - 1));
+    const int jt = lie_trivial(sd);
+    const double h = P.dt[k];
+    for (int e = 0; e < ne; e++) {
+        const double v = (e == jt) ? 1.0 : ((jt >= 6 && e == jt - 6) ? h : 0.0);
+        if (FRAG) P.REC[((size_t)b * P.N + k) * TO_REC_LEN + fraglayout::ab_index(e, jt)] = v;
+        else P.ABe[((size_t)bk * nme + jt) * ne + e] = v;
+    }
+}
+cudaError_t launch_trivial_columns(const DevProblem& P, cudaStream_t s) {
+    const long long total = (long long)P.B * (P.N - 1) * 6;
+    if (P.frag) k_trivial_columns<true><<<(unsigned)((total + 127) / 128), 128, 0, s>>>(P);
+    else k_trivial_columns<false><<<(unsigned)((total + 127) / 128), 128, 0, s>>>(P);
+    return cudaGetLastError();
+}
+
+// Cost + AL expansion part of every record (frag_layout.cuh [192, 240)), the terminal knot included: 16 lanes per knot, lane i = entry i of
+// the full-state z = [x; u] (lane 0 also takes the 17th entry u_3).  Outside the attitude the error-state expansion of a diagonal full-state
+// one is the same entry; the quaternion block is projected by lanes 3..5 from the (g, h, q) of lanes 3..6, fetched by 16-lane shuffles:
+// G'g, G' diag(h) G - (q'g_q) I3 (Altro error_expansion!; lie.cu k_expansion_compact is the one-thread-per-knot version of the same numbers).
+// A light kernel (every load independent, ~40 registers) that runs at full occupancy; fused into the FP64-bound k_expand_lie it doubled that
+// kernel's time (profiles/r02_notes.md).
+__global__ void __launch_bounds__(256) k_expansion_rec16(const DevProblem P) {
+    constexpr int qs = 3;
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = t < (long long)P.B * P.N * 16;
+    const int i = (int)(t & 15);
+    const long long bk = live ? (t >> 4) : 0;
+    const int k = (int)(bk % P.N), b = (int)(bk / P.N);
+    const int n = P.n;
+    const bool last = (k == P.N - 1);
+    const double* X = traj_X(P, P.cur[b], b) + (size_t)k * n;
+    const double* U = traj_U(P, P.cur[b], b) + (size_t)(last ? 0 : k) * P.m;      // (not read at the terminal knot)
+    const double* lam_b = P.lambda + (size_t)b * P.lambda_len;
+    const ExpTab& tab = *P.exptab;
+    double* rec = P.REC + (size_t)bk * TO_REC_LEN;
+    const double zi = (i < n) ? X[i] : (last ? 0.0 : U[i - n]);
+    double g, h;
+    compact_entry_expansion(P, tab, k, i, zi, lam_b, g, h);
+    // the quaternion block: (g, h, q) of lanes 3..6 to every lane of the 16-lane group (lanes 3..5 use them)
+    double gq[4], hq[4], q[4];
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+        gq[r] = __shfl_sync(0xffffffffu, g, qs + r, 16); hq[r] = __shfl_sync(0xffffffffu, h, qs + r, 16); q[r] = __shfl_sync(0xffffffffu, zi, qs + r, 16);
+    }
+    if (!live) return;
+    if (i >= qs && i < qs + 3) {
+        const int c = i - qs;
+        // rows of G' = (L(q) H)': (-x,w,z,-y), (-y,-z,w,x), (-z,y,-x,w)   (kept in registers: no run-time indexed arrays)
+        const double G0[4] = {-q[1], q[0], q[3], -q[2]}, G1[4] = {-q[2], -q[3], q[0], q[1]}, G2[4] = {-q[3], q[2], -q[1], q[0]};
+        double gc[4];
+#pragma unroll
+        for (int r = 0; r < 4; r++) gc[r] = (c == 0) ? G0[r] : (c == 1) ? G1[r] : G2[r];
+        double qb = 0.0, ge = 0.0, hb0 = 0.0, hb1 = 0.0, hb2 = 0.0;
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+            qb += q[r] * gq[r]; ge += gc[r] * gq[r];
+            const double tt = gc[r] * hq[r];
+            hb0 += tt * G0[r]; hb1 += tt * G1[r]; hb2 += tt * G2[r];
+        }
+        const double hd = ((c == 0) ? hb0 : (c == 1) ? hb1 : hb2) - qb;
+        const int p = fraglayout::phys_x(3) + 2 * c;                       // attitude error e = 3 + c sits on p = 8, 10, 12
+        rec[TO_REC_G + p] = ge; rec[TO_REC_HD + p] = hd;
+        rec[TO_REC_HB + 4 * c + 0] = (c == 0) ? hd : hb0;
+        rec[TO_REC_HB + 4 * c + 1] = (c == 1) ? hd : hb1;
+        rec[TO_REC_HB + 4 * c + 2] = (c == 2) ? hd : hb2;
+        rec[TO_REC_HB + 4 * c + 3] = 0.0;
+    } else if (i != qs + 3) {                                              // lane 6 (q_z) has no coordinate of its own
+        const int e = (i < qs) ? i : i - 1;                               // error-state coordinate of full-state entry i (controls: 12 + a = i - 1)
+        const int p = (int)((0x6420FDB9E7CA8531ULL >> (4 * e)) & 15);
+        rec[TO_REC_G + p] = g; rec[TO_REC_HD + p] = h;
+        if (e == 7) { rec[TO_REC_HB + 12] = 0.0; rec[TO_REC_HB + 13] = 0.0; rec[TO_REC_HB + 14] = 0.0; rec[TO_REC_HB + 15] = h; }   // p = 14 is row 3 of Hb
+    }
+    if (i == 0) {                                                          // the 17th entry: u_3 -> coordinate 15
+        const double z3 = last ? 0.0 : U[3];
+        compact_entry_expansion(P, tab, k, n + 3, z3, lam_b, g, h);
+        rec[TO_REC_G + 6] = g; rec[TO_REC_HD + 6] = h;                     // phys_z(15) = 6
+    }
+}
+cudaError_t launch_expansion_rec16(const DevProblem& P, cudaStream_t s) {
+    const long long total = (long long)P.B * P.N * 16;
+    k_expansion_rec16<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(P);
+    return cudaGetLastError();
 }
 
 cudaError_t launch_expand_lie(const DevProblem& P, cudaStream_t s, int mode) {

@@ -111,6 +111,21 @@ __global__ void k_eval_constraints(const DevProblem P, int ci, double* __restric
     for (int i = 0; i < con.p; i++) vals[t * con.p + i] = c[i];
 }
 
+// lam_in: [B][len][p] or nullptr = the handle's multipliers
+__global__ void k_constraint_hessians(const DevProblem P, int ci, const double* __restrict__ lam_in, double* __restrict__ H) {
+    const DevCon& con = P.cons[ci];
+    const int len = con.last - con.first + 1, w = P.n + P.m;
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (long long)P.B * len) return;
+    const int ki = (int)(t % len), b = (int)(t / len);
+    const int k1 = con.first + ki;
+    double zero_u[TO_MAXM] = {0};
+    const double* x = traj_X(P, P.cur[b], b) + (size_t)(k1 - 1) * P.n;
+    const double* u = (k1 == P.N) ? zero_u : traj_U(P, P.cur[b], b) + (size_t)(k1 - 1) * P.m;
+    const double* lam = lam_in ? lam_in + t * con.p : P.lambda + (size_t)b * P.lambda_len + con.offset + (size_t)ki * con.p;
+    con_hess_vec(con, P.n, P.m, x, u, lam, H + t * w * w);
+}
+
 __global__ void k_constraint_jacobians(const DevProblem P, int ci, double* __restrict__ jac) {
     const DevCon& con = P.cons[ci];
     const int len = con.last - con.first + 1;
@@ -235,6 +250,11 @@ cudaError_t launch_al_expansion(const DevProblem& P, double* grad, double* hess,
 cudaError_t launch_eval_constraints(const DevProblem& P, int con, double* vals, cudaStream_t s) {
     // the knot-range length is read on the device; size the grid for the worst case N
     k_eval_constraints<<<nblk((long long)P.B * P.N, 128), 128, 0, s>>>(P, con, vals);
+    return cudaGetLastError();
+}
+cudaError_t launch_constraint_hessians(const DevProblem& P, int con, int len, const double* lam, double* H, cudaStream_t s) {
+    const long long total = (long long)P.B * len;
+    k_constraint_hessians<<<(unsigned)((total + 127) / 128), 128, 0, s>>>(P, con, lam, H);
     return cudaGetLastError();
 }
 cudaError_t launch_constraint_jacobians(const DevProblem& P, int con, double* jac, cudaStream_t s) {

@@ -156,3 +156,49 @@ def test_live_problem_follows_mutations_of_objective_and_constraint_list():
     TO.set_options(prob, penalty_scaling=3.0); TO.set_options(prob, iterations_linesearch=7)
     assert prob._options.penalty_scaling == 3.0 and prob._options.iterations_linesearch == 7      # earlier settings are kept
     prob.close(); ref.close()
+
+
+def test_abi_struct_layout_matches_the_binding_tables():
+    """INTEGRATION.md's offset table (what a Julia / ctypes binding has to reproduce field for field) against offsetof / sizeof printed by a C
+    program compiled from include/trajopt_b200.h, and against the ctypes structures of the Python binding."""
+    import re
+    import subprocess
+    import tempfile
+    import ctypes
+    import trajopt_b200 as TO
+    hdr = open(os.path.join(ROOT, "include", "trajopt_b200.h")).read()
+    structs = {}
+    for body, name in re.findall(r"typedef struct \{(.*?)\}\s*(to_cost_spec|to_constraint_spec|to_spec|to_options);", hdr, flags=re.S):
+        body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+        fields = []
+        for decl in body.split(";"):
+            decl = decl.strip()
+            if not decl:
+                continue
+            names = decl.split(",")
+            first = names[0].split()[-1]
+            fields.append(first.lstrip("*"))
+            fields += [n.strip().lstrip("*") for n in names[1:]]
+        structs[name] = fields
+    src = "#include <stdio.h>\n#include <stddef.h>\n#include \"trajopt_b200.h\"\nint main() {\n"
+    for name, fields in structs.items():
+        for f in fields:
+            src += f'  printf("{name} {f} %zu\\n", offsetof({name}, {f}));\n'
+        src += f'  printf("{name} sizeof %zu\\n", sizeof({name}));\n'
+    src += "  return 0;\n}\n"
+    with tempfile.TemporaryDirectory() as d:
+        open(os.path.join(d, "l.c"), "w").write(src)
+        subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), os.path.join(d, "l.c"), "-o", os.path.join(d, "l")])
+        out = subprocess.check_output([os.path.join(d, "l")], text=True)
+    c_layout = {tuple(l.split()[:2]): int(l.split()[2]) for l in out.splitlines()}
+    # the table in INTEGRATION.md: rows `| to_spec | field | offset | ...`
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    table = {(m.group(1), m.group(2)): int(m.group(3)) for m in re.finditer(r"^\| `(to_\w+)` \| `(\w+)` \| (\d+) \|", doc, flags=re.M)}
+    assert table, "INTEGRATION.md has no struct layout table"
+    assert table == c_layout, {k: (table.get(k), c_layout.get(k)) for k in set(table) | set(c_layout) if table.get(k) != c_layout.get(k)}
+    # the ctypes mirror
+    for name in structs:
+        cls = getattr(TO.capi, name)
+        assert ctypes.sizeof(cls) == c_layout[(name, "sizeof")], name
+        for f in structs[name]:
+            assert getattr(cls, f).offset == c_layout[(name, f)], (name, f)

@@ -179,7 +179,7 @@ EXPORTED_SYMBOLS = [
     "to_num_constraints", "to_constraint_info", "to_bounds", "to_set_initial_state", "to_set_controls", "to_set_states",
     "to_set_goal_state", "to_set_initial_time", "to_get_states", "to_get_controls", "to_get_times", "to_rollout", "to_expand",
     "to_get_dynamics_jacobians", "to_cost", "to_cost_knots", "to_cost_gradient", "to_cost_hessian", "to_eval_constraints",
-    "to_constraint_jacobians", "to_max_violation", "to_merit", "to_al_expansion", "to_projection", "to_grad_projection",
+    "to_constraint_jacobians", "to_constraint_hessians", "to_max_violation", "to_merit", "to_al_expansion", "to_projection", "to_grad_projection",
     "to_hess_projection", "to_backward", "to_forward", "to_ilqr_step", "to_al_update", "to_get_gains", "to_get_multipliers",
     "to_set_multipliers", "to_get_penalty", "to_set_penalty", "to_get_solver_state", "to_reduce_merit", "to_reduce_merit_async", "to_merit_device_ptr", "to_update_trajectory", "to_shift_trajectory",
     "to_set_phase_timing", "to_get_phase_times", "to_launch_count", "to_algorithmic_bytes",

@@ -523,6 +523,7 @@ int to_create(const to_spec* s, to_handle** out) {
     if (!okc) { h->err = std::string("device initialisation failed: ") + cudaGetErrorString(cudaGetLastError()); return bail(TO_ECUDA); }
     rc = upload_tables(h);
     if (rc) return bail(rc);
+    if (launch_trivial_columns_full(P, st) != cudaSuccess) { h->err = "k_trivial_columns_full failed"; return bail(TO_ECUDA); }   // closed-form columns of [A B] (rollout.cu SeedList)
     if (P.lie && P.model == MODEL_QUADROTOR) {        // the position / velocity columns of [A_e B_e] are functions of the time steps alone (rollout.cu)
         if (launch_trivial_columns(P, st) != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess) { h->err = "k_trivial_columns failed"; return bail(TO_ECUDA); }
     }
@@ -902,15 +903,15 @@ static int materialise_expansion(to_handle* h, double* EG, double* EH) {
     CU(h, launch_error_expansion(P, gf, hf, EG, EH, h->stream)); h->launches++;
     return TO_OK;
 }
-static int do_backward(to_handle* h) {
+static int do_backward(to_handle* h, bool costexp_done = false) {
     // to_options.backward_kernel: 0 automatic, 3 generic DFMA kernel on the full expansion, 5 shared-memory tensor kernel on the compact expansion
     if (h->P.frag && h->P.opt.pad != 3 && h->P.opt.pad != 5) {
-        {   // cost + AL expansion of every record: always from the current trajectory, multipliers and penalties
+        if (!costexp_done) {   // cost + AL expansion of every record: always from the current trajectory, multipliers and penalties
             PhaseScope pe(h, TO_PHASE_COSTEXP);
             if (rec_fused(h->P)) CU(h, launch_expansion_rec16(h->P, h->stream));      // 16 lanes per knot, host-built term table
             else CU(h, launch_expansion_rec(h->P, h->stream));                          // more than 3 rows on one z entry: descriptor walk
+            h->launches++; h->phase_launches[TO_PHASE_COSTEXP]++;
         }
-        h->launches++; h->phase_launches[TO_PHASE_COSTEXP]++;
         PhaseScope ps(h, TO_PHASE_BACKWARD);
         CU(h, launch_backward_frag(h->P, h->d_fragq, h->stream));
     } else if (h->P.dense_riccati) {
@@ -976,15 +977,23 @@ int to_ilqr_step(to_handle* h, int32_t iters) {
     for (int it = 0; it < iters; it++) {
         // (error state: only [A_e B_e] is needed by the solver kernels -- k_expand_lie; the full [A B] is produced by to_expand on request)
         auto expand = [&](cudaStream_t st, int mode) { return h->P.lie ? launch_expand_lie(h->P, st, mode) : launch_expand(h->P, st, mode); };
+        bool costexp_done = false;
         if (h->side_pending) {
             CU(h, expand(h->stream2, 2)); h->launches++;
+            // the records' cost + AL expansion (latency-bound, light) rides on the side stream behind the late line-search trials, next to the
+            // FP64-bound dynamics expansion on the main stream; every trajectory is final there (F pass 1 precedes the fork, pass 2 this kernel)
+            if (h->P.frag && h->P.opt.pad != 3 && h->P.opt.pad != 5 && rec_fused(h->P)) {
+                { PhaseScope pe(h, TO_PHASE_COSTEXP, h->stream2); CU(h, launch_expansion_rec16(h->P, h->stream2)); }
+                h->launches++; h->phase_launches[TO_PHASE_COSTEXP]++;
+                costexp_done = true;
+            }
             CU(h, cudaEventRecord(h->ev_join, h->stream2));
         }
         { PhaseScope ps(h, TO_PHASE_EXPAND); CU(h, expand(h->stream, h->side_pending ? 1 : 0)); }
         h->launches++; h->phase_launches[TO_PHASE_EXPAND]++;
         JOIN(h);
         h->expanded = true;
-        rc = do_backward(h); if (rc) return rc;
+        rc = do_backward(h, costexp_done); if (rc) return rc;
         { PhaseScope ps(h, TO_PHASE_FORWARD); CU(h, launch_forward(h->P, h->stream)); }
         h->launches++; h->phase_launches[TO_PHASE_FORWARD]++;
         if (h->overlap) {

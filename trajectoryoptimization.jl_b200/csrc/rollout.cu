@@ -34,16 +34,34 @@ __global__ void __launch_bounds__(64) k_rollout(const DevProblem P) {
     }
 }
 
+// Seed pruning (full state).  The position r and the world-frame linear velocity v of the Quadrotor (a RobotDynamics RigidBody) enter the
+// dynamics only through rdot = v, so their columns of [A B] are known in closed form -- d x+/d r = e_r, d x+/d v = h e_r + e_v (the RK4
+// weights sum to one) -- and are written once when the problem is created (k_trivial_columns_full); 11 seeds (quaternion, angular velocity,
+// controls) are pushed through the dual-number RK4 step instead of 17.  Other models: every seed.
+template <int MODEL> struct SeedList {
+    static constexpr int count = ModelDims<MODEL>::n + ModelDims<MODEL>::m;
+    __host__ __device__ static constexpr int seed(int s) { return s; }
+    __host__ __device__ static constexpr int ntrivial() { return 0; }
+    __host__ __device__ static constexpr int trivial(int) { return 0; }
+};
+template <> struct SeedList<MODEL_QUADROTOR> {
+    static constexpr int count = 11;
+    __host__ __device__ static constexpr int seed(int s) { return s < 4 ? 3 + s : 6 + s; }       // 3..6 (q), 10..12 (omega), 13..16 (u)
+    __host__ __device__ static constexpr int ntrivial() { return 6; }
+    __host__ __device__ static constexpr int trivial(int s) { return s < 3 ? s : 4 + s; }        // 0..2 (r), 7..9 (v)
+};
+
 template <int MODEL, int NP>
 __global__ void __launch_bounds__(128) k_expand(const DevProblem P, int mode) {
     constexpr int n = ModelDims<MODEL>::n, m = ModelDims<MODEL>::m, nm = n + m;
-    constexpr int TPK = (nm + NP - 1) / NP;        // threads per knot: each carries NP seed directions
+    constexpr int NSEED = SeedList<MODEL>::count;
+    constexpr int TPK = (NSEED + NP - 1) / NP;     // threads per knot: each carries NP seed directions
     using D = Dual<NP>;
     const int ld = P.ldab;
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long total = (long long)P.B * (P.N - 1) * TPK;
     if (t >= total) return;
-    const int j0 = (int)(t % TPK) * NP;            // first seed of this thread
+    const int s0 = (int)(t % TPK) * NP;            // first seed slot of this thread
     const long long bk = t / TPK;
     const int k = (int)(bk % (P.N - 1));
     const int b = (int)(bk / (P.N - 1));
@@ -51,34 +69,57 @@ __global__ void __launch_bounds__(128) k_expand(const DevProblem P, int mode) {
     double* AB = P.AB + ((size_t)b * (P.N - 1) + k) * n * ld;     // pad columns nm..ld-1 stay zero from to_create
     const double* X = traj_X(P, P.cur[b], b) + (size_t)k * n;
     const double* U = traj_U(P, P.cur[b], b) + (size_t)k * m;
+    int js[NP];                                    // the z index each seed slot differentiates with respect to (nm = none)
+#pragma unroll
+    for (int q = 0; q < NP; q++) js[q] = (s0 + q < NSEED) ? SeedList<MODEL>::seed(s0 + q) : nm;
     D x[n], u[m], xn[n];
 #pragma unroll
     for (int i = 0; i < n; i++) {
         x[i].v = X[i];
 #pragma unroll
-        for (int s = 0; s < NP; s++) x[i].d[s] = (i == j0 + s) ? 1.0 : 0.0;
+        for (int q = 0; q < NP; q++) x[i].d[q] = (i == js[q]) ? 1.0 : 0.0;
     }
 #pragma unroll
     for (int i = 0; i < m; i++) {
         u[i].v = U[i];
 #pragma unroll
-        for (int s = 0; s < NP; s++) u[i].d[s] = (n + i == j0 + s) ? 1.0 : 0.0;
+        for (int q = 0; q < NP; q++) u[i].d[q] = (n + i == js[q]) ? 1.0 : 0.0;
     }
     rk4_step<MODEL, D>(P.params, x, u, P.dt[k], xn);
 #pragma unroll
     for (int i = 0; i < n; i++) {
-        if (NP == 2 && j0 + 1 < nm) *reinterpret_cast<double2*>(&AB[i * ld + j0]) = make_double2(xn[i].d[0], xn[i].d[1]);
+        if (NP == 2 && js[1] == js[0] + 1 && !(js[0] & 1)) *reinterpret_cast<double2*>(&AB[i * ld + js[0]]) = make_double2(xn[i].d[0], xn[i].d[1]);
         else {
 #pragma unroll
-            for (int s = 0; s < NP; s++) if (j0 + s < nm) AB[i * ld + j0 + s] = xn[i].d[s];
+            for (int q = 0; q < NP; q++) if (js[q] < nm) AB[i * ld + js[q]] = xn[i].d[q];
         }
     }
 }
 
-// Error-state expansion of a Lie-group model (Quadrotor; SURVEY 8 f2, lie.cu): thread (instance, knot, j) pushes the j-th column of
-// E(x_k) = blkdiag(I3, G(q_k), I6 | I4) through the RK4 step as the tangent of a Dual<1> -- the directional derivative [A G_k | B] e_j --
-// and projects the result with G(q_{k+1})' (q_{k+1} from the stored trajectory, as Altro's errstate_jacobian! does).  It writes column j
-// of [A_e B_e]_k (12 contiguous doubles, col-major 12 x 16): 1.5 KB per knot instead of the 2 KB of the padded full-state [A B].
+// the closed-form columns of [A B] (SeedList<MODEL>::trivial): thread = (instance, knot, one of them); run once per problem
+template <int MODEL>
+__global__ void __launch_bounds__(128) k_trivial_columns_full(const DevProblem P) {
+    constexpr int n = ModelDims<MODEL>::n, NT = SeedList<MODEL>::ntrivial();
+    if constexpr (NT > 0) {
+        const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+        if (t >= (long long)P.B * (P.N - 1) * NT) return;
+        const int jt = SeedList<MODEL>::trivial((int)(t % NT));
+        const long long bk = t / NT;
+        const int k = (int)(bk % (P.N - 1));
+        double* AB = P.AB + (size_t)bk * n * P.ldab;
+        const double h = P.dt[k];
+        // x = [r(0..2); q(3..6); v(7..9); omega(10..12)]: d r+/d r = I, d r+/d v = h I, d v+/d v = I
+        for (int i = 0; i < n; i++) AB[i * P.ldab + jt] = (i == jt) ? 1.0 : ((jt >= 7 && i == jt - 7) ? h : 0.0);
+    }
+}
+cudaError_t launch_trivial_columns_full(const DevProblem& P, cudaStream_t s) {
+    if (P.model == MODEL_QUADROTOR) {
+        const long long total = (long long)P.B * (P.N - 1) * SeedList<MODEL_QUADROTOR>::ntrivial();
+        k_trivial_columns_full<MODEL_QUADROTOR><<<(unsigned)((total + 127) / 128), 128, 0, s>>>(P);
+    }
+    return cudaGetLastError();
+}
+
 // (g, h) = (lz_i, lzz_ii) of entry i of the full-state z = [x; u] at knot k (0-based): DiagonalCost (RD.gradient!/hessian!, src/cost_functions.jl:137-233)
 // + the AL terms of the Goal / Bound rows acting on z_i (src/constraints.jl:55-68, :738-765; projection on the dual cone src/cones.jl:96-145).
 // The compact problem class only (P.compact): every cost diagonal, every constraint Goal or Bound, at most TO_EXP_MAXT rows per entry
@@ -285,8 +326,7 @@ cudaError_t launch_rollout(const DevProblem& P, cudaStream_t s) {
 
 template <int MODEL, int NP>
 static cudaError_t launch_expand_t(const DevProblem& P, cudaStream_t s, int mode) {
-    constexpr int nm = ModelDims<MODEL>::n + ModelDims<MODEL>::m;
-    constexpr int TPK = (nm + NP - 1) / NP;
+    constexpr int TPK = (SeedList<MODEL>::count + NP - 1) / NP;
     const long long total = (long long)P.B * (P.N - 1) * TPK;
     const int threads = 128;
     k_expand<MODEL, NP><<<(unsigned)((total + threads - 1) / threads), threads, 0, s>>>(P, mode);

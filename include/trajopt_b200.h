@@ -40,7 +40,9 @@ enum to_model_id {
     TO_MODEL_DOUBLE_INTEGRATOR = 0, /* examples/quickstart.jl:11-23 ; n = 2*dim, m = dim, params[0] = mass */
     TO_MODEL_CARTPOLE = 1,          /* docs/src/model.md:14-51 ; params = mc, mp, l, g */
     TO_MODEL_QUADROTOR = 2,         /* examples/Quadrotor.ipynb cells 4,8 ; params = mass, J1..3, g1..3, motor_dist, kf, km */
-    TO_MODEL_ACROBOT = 3            /* RobotZoo.Acrobot ; params = l1,l2,m1,m2,J1,J2,friction,g */
+    TO_MODEL_ACROBOT = 3,           /* RobotZoo.Acrobot ; params = l1,l2,m1,m2,J1,J2,friction,g */
+    TO_MODEL_EXPR = 4               /* user dynamics recorded as programs, one per knot allowed (hybrid / variable-dimension models, src/dynamics.jl:15-31,
+                                       test/hybrid_dynamics_model.jl): to_spec.dyn, dyn_index, nx, nu */
 };
 
 /* QuadraticCostFunction (src/cost_functions.jl:326-347 DiagonalCost, :417-454 QuadraticCost) */
@@ -75,6 +77,16 @@ typedef struct {
     const int32_t* prog;    /* EXPR: prog_len x {op, a, b} */
     const double* consts;   /* EXPR */
 } to_cost_spec;
+
+/* One dynamics model of a hybrid problem: `RD.@autodiff struct M <: ContinuousDynamics` + `RD.dynamics(::M, x, u)` recorded as a program
+ * (to_expr_op; inputs x[0..n_in), u[0..m_in); the LAST n_out instructions are the outputs), discretised with RK4 like every model of the path,
+ * or -- `discrete` = 1 -- a jump map x+ = g(x, u) applied as is (n_out may differ from n_in: the state dimension changes there). */
+typedef struct {
+    int32_t n_in, m_in, n_out, discrete;
+    int32_t prog_len, nconst;
+    const int32_t* prog;
+    const double* consts;
+} to_dynamics_spec;
 
 /* ConstraintSense (src/cones.jl:17-61) */
 enum to_cone { TO_CONE_ZERO = 0 /* Equality */, TO_CONE_NEGATIVE_ORTHANT = 1 /* Inequality */, TO_CONE_SECOND_ORDER = 2,
@@ -132,6 +144,16 @@ typedef struct {
                                 Jacobian G(x) = blkdiag(I3, L(q) H, I6) (Rotations.jl grad-differential), dynamics A_e = G_{k+1}' A G_k, B_e = G_{k+1}' B,
                                 cost expansion G'lxx G + grad^2-differential, dx = state_diff(xbar, x) with the Cayley map.  The reference's hooks for
                                 it: src/abstract_constraint.jl:282-303 (error_expansion! of constraint Jacobians), src/lie_costs.jl.  0: full state. */
+    /* TO_MODEL_EXPR only (else 0 / NULL): `Problem(models::Vector{<:DiscreteDynamics}, ...)`, src/problem.jl:36-73 with RD.dims(models), src/dynamics.jl:15-31.
+       n, m are the LARGEST state / control dimensions; knot k has nx[k] <= n states and nu[k] <= m controls, stored in the first entries of the
+       n- / m-sized slots (the rest stays zero: costs and constraints are described on the padded [x(n); u(m)] layout, with unit weights on the
+       unused controls so that Quu stays positive definite).  Model dyn[dyn_index[k]] maps knot k to k+1: n_in = nx[k], m_in = nu[k], n_out = nx[k+1]
+       (checked: the reference's DimensionMismatch "Model mismatch at time step k"). */
+    int32_t ndyn;
+    const to_dynamics_spec* dyn;
+    const int32_t* dyn_index;   /* N-1 entries, 0-based */
+    const int32_t* nx;          /* N entries */
+    const int32_t* nu;          /* N entries (nu[N-1] = nu[N-2], as RD.dims does) */
 } to_spec;
 
 /* Solver options on the path (Altro.jl SolverOptions, restated in oracle/oracle.hpp `Options`) */

@@ -19,10 +19,11 @@
 //                       PARITY UNPINNED.
 #pragma once
 #include <cmath>
+#include <vector>
 
 namespace oracle {
 
-enum ModelId { MODEL_DOUBLE_INTEGRATOR = 0, MODEL_CARTPOLE = 1, MODEL_QUADROTOR = 2, MODEL_ACROBOT = 3 };
+enum ModelId { MODEL_DOUBLE_INTEGRATOR = 0, MODEL_CARTPOLE = 1, MODEL_QUADROTOR = 2, MODEL_ACROBOT = 3, MODEL_EXPR = 4 };
 
 // ---------------------------------------------------------------------------------------------
 // Forward-mode dual number with P partials (ForwardDiff.Dual restated).
@@ -52,6 +53,11 @@ template <int P> inline Dual<P> cos(const Dual<P>& a) { Dual<P> r; r.v = std::co
 // the constant 0 is returned, so the derivative is 0 for x <= 0 and 1 for x > 0.
 template <int P> inline Dual<P> relu(const Dual<P>& a) { return a.v > 0 ? a : Dual<P>(0.0); }
 inline double relu(double a) { return a > 0 ? a : 0.0; }
+// first-order chain rule for the unary functions a recorded dynamics program may use (MODEL_EXPR)
+template <int P> inline Dual<P> chain(const Dual<P>& a, double f, double df) { Dual<P> r; r.v = f; for (int i = 0; i < P; i++) r.d[i] = df * a.d[i]; return r; }
+inline double chain(double, double f, double) { return f; }
+template <class S> inline double value_of(const S& a) { return a.v; }
+template <> inline double value_of<double>(const double& a) { return a; }
 using std::sin;
 using std::cos;
 
@@ -60,8 +66,18 @@ struct ModelParams {
     int id = MODEL_CARTPOLE;
     int n = 4, m = 1;
     double p[16] = {0};
+    const struct DynProg* prog = nullptr;   // MODEL_EXPR: the recorded program of the knot being stepped (Problem::model_at)
     int integrator = 4;   // 4 = RK4 (the reference's default, src/problem.jl:119-123), 3 = RK3 (oracle only: the default of the
                           // TrajectoryOptimization v0.3 / Altro 0.3 versions that produced the recorded outputs of examples/*.ipynb)
+};
+
+// One model of a hybrid problem (include/trajopt_b200.h to_dynamics_spec; the reference: `Problem(models::Vector{<:DiscreteDynamics}, ...)`,
+// src/problem.jl:36-73, RD.dims(models) src/dynamics.jl:15-31, example test/hybrid_dynamics_model.jl:15-54): the user's `RD.dynamics(model, x, u)`
+// as a straight-line program; `discrete` = a jump map applied as is (its output dimension may differ from its state dimension).
+struct DynProg {
+    int n_in = 0, m_in = 0, n_out = 0, discrete = 0;
+    std::vector<int> prog;        // prog_len x {op, a, b}  (to_expr_op)
+    std::vector<double> consts;
 };
 
 inline ModelParams default_model(int id, int dim = 1) {
@@ -78,6 +94,7 @@ inline ModelParams default_model(int id, int dim = 1) {
             mp.p[8] = 1.0;                                   // kf
             mp.p[9] = 0.0245;                                // km
             break;
+        case MODEL_EXPR: mp.n = 4; mp.m = 2; break;   // padded dimensions of a recorded hybrid problem
         case MODEL_ACROBOT:
             mp.n = 4; mp.m = 1;
             mp.p[0] = 1.0; mp.p[1] = 1.0;                    // l1,l2
@@ -174,6 +191,41 @@ inline void acrobot_dynamics(const double* p, const S* x, const S* u, S* xd) {
     xd[3] = (m11 * r2 - m12 * r1) / det;
 }
 
+// evaluate a recorded program with the scalar type S; outputs = the last n_out instructions, the remaining (padded) slots are zero
+template <class S>
+inline void expr_dynamics(const DynProg& dp, int n, const S* x, const S* u, S* xd) {
+    const int len = (int)dp.prog.size() / 3;
+    std::vector<S> reg(len);
+    for (int i = 0; i < len; i++) {
+        const int op = dp.prog[3 * i], a = dp.prog[3 * i + 1], b = dp.prog[3 * i + 2];
+        S r = S(0.0);
+        switch (op) {
+            case 0: r = S(dp.consts[a]); break;
+            case 1: r = x[a]; break;
+            case 2: r = u[a]; break;
+            case 3: r = reg[a] + reg[b]; break;
+            case 4: r = reg[a] - reg[b]; break;
+            case 5: r = reg[a] * reg[b]; break;
+            case 6: r = reg[a] / reg[b]; break;
+            case 7: r = -reg[a]; break;
+            case 8: r = sin(reg[a]); break;
+            case 9: r = cos(reg[a]); break;
+            case 10: { const double e = std::exp(value_of(reg[a])); r = chain(reg[a], e, e); break; }
+            case 11: { const double v = value_of(reg[a]); r = chain(reg[a], std::log(v), 1.0 / v); break; }
+            case 12: { const double q = std::sqrt(value_of(reg[a])); r = chain(reg[a], q, 0.5 / q); break; }
+            case 13: { const double v = value_of(reg[a]), c = dp.consts[b]; r = chain(reg[a], std::pow(v, c), c * std::pow(v, c - 1.0)); break; }
+            case 14: { const double t = std::tanh(value_of(reg[a])); r = chain(reg[a], t, 1.0 - t * t); break; }
+            case 15: r = reg[a] + dp.consts[b]; break;
+            case 16: r = reg[a] * dp.consts[b]; break;
+            case 17: r = reg[a] * (1.0 / dp.consts[b]); break;
+            case 18: r = S(dp.consts[b]) / reg[a]; break;
+            case 19: r = dp.consts[b] - reg[a]; break;
+        }
+        reg[i] = r;
+    }
+    for (int i = 0; i < n; i++) xd[i] = (i < dp.n_out) ? reg[len - dp.n_out + i] : S(0.0);
+}
+
 template <class S>
 inline void dynamics(const ModelParams& mp, const S* x, const S* u, S* xd) {
     switch (mp.id) {
@@ -181,6 +233,7 @@ inline void dynamics(const ModelParams& mp, const S* x, const S* u, S* xd) {
         case MODEL_CARTPOLE: cartpole_dynamics<S>(mp.p, x, u, xd); break;
         case MODEL_QUADROTOR: quadrotor_dynamics<S>(mp.p, x, u, xd); break;
         case MODEL_ACROBOT: acrobot_dynamics<S>(mp.p, x, u, xd); break;
+        case MODEL_EXPR: expr_dynamics<S>(*mp.prog, mp.n, x, u, xd); break;
     }
 }
 
@@ -206,6 +259,7 @@ inline void rk3_step(const ModelParams& mp, const S* x, const S* u, double h, S*
 
 template <class S>
 inline void rk4_step(const ModelParams& mp, const S* x, const S* u, double h, S* xn) {
+    if (mp.id == MODEL_EXPR && mp.prog->discrete) { dynamics<S>(mp, x, u, xn); return; }   // a jump map is already discrete
     if (mp.integrator == 3) { rk3_step<S>(mp, x, u, h, xn); return; }
     const int n = mp.n;
     S k1[MAXN], k2[MAXN], k3[MAXN], k4[MAXN], xt[MAXN];

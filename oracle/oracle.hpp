@@ -593,6 +593,9 @@ struct Options {
 
 struct Problem {
     ModelParams model;
+    std::vector<DynProg> dyn;      // MODEL_EXPR: the models of a hybrid problem and which one steps knot k -> k+1
+    std::vector<int> dyn_index;    // N-1
+    ModelParams model_at(int k) const { ModelParams mp = model; if (model.id == MODEL_EXPR) mp.prog = &dyn[dyn_index[k]]; return mp; }
     int n = 0, m = 0, N = 0, B = 0;
     // Lie-group error state (to_spec.error_state): the Riccati recursion, the gains and the feedback act on ne = n - 1 dimensions,
     // the quaternion x[qs..qs+3] contributing its 3-dimensional differential (Altro.jl + RobotDynamics LieState, restated below)
@@ -745,7 +748,7 @@ inline void rollout(Problem& P, int b) {
     const int n = P.n, m = P.m, N = P.N;
     double* X = P.Xb(b); const double* U = P.Ub(b);
     for (int i = 0; i < n; i++) X[i] = P.x0[(size_t)b * n + i];
-    for (int k = 1; k < N; k++) rk4_step<double>(P.model, &X[(k - 1) * n], &U[(k - 1) * m], P.dt[k - 1], &X[k * n]);
+    for (int k = 1; k < N; k++) rk4_step<double>(P.model_at(k - 1), &X[(k - 1) * n], &U[(k - 1) * m], P.dt[k - 1], &X[k * n]);
 }
 
 // cost! / get_J  src/objective.jl:104-110 : per-knot J_k
@@ -851,7 +854,7 @@ inline void dynamics_jacobian(const ModelParams& mp, const double* x, const doub
 inline void expand_dynamics(Problem& P, int b) {
     const int n = P.n, m = P.m;
     for (int k = 0; k < P.N - 1; k++) {
-        dynamics_jacobian(P.model, &P.Xb(b)[k * n], &P.Ub(b)[k * m], P.dt[k], &P.ABb(b)[(size_t)k * n * (n + m)]);
+        dynamics_jacobian(P.model_at(k), &P.Xb(b)[k * n], &P.Ub(b)[k * m], P.dt[k], &P.ABb(b)[(size_t)k * n * (n + m)]);
         if (P.lie) error_dynamics(P, &P.Xb(b)[k * n], &P.Xb(b)[(k + 1) * n], &P.ABb(b)[(size_t)k * n * (n + m)], &P.ABeb(b)[(size_t)k * P.ne * (P.ne + m)]);
     }
 }
@@ -1123,7 +1126,7 @@ inline bool forward_rollout(const Problem& P, int b, double alpha, double* Xc, d
             Uc[k * m + a] = t;
             if (!(std::fabs(t) <= P.opts.max_control_value)) return false;
         }
-        rk4_step<double>(P.model, &Xc[k * n], &Uc[k * m], P.dt[k], &Xc[(k + 1) * n]);
+        rk4_step<double>(P.model_at(k), &Xc[k * n], &Uc[k * m], P.dt[k], &Xc[(k + 1) * n]);
         for (int i = 0; i < n; i++) if (!(std::fabs(Xc[(k + 1) * n + i]) <= P.opts.max_state_value)) return false;
     }
     return true;

@@ -32,7 +32,7 @@ const char* orc_last_error(const orc_handle* h) { return h ? h->err.c_str() : g_
 int orc_create(const to_spec* s, orc_handle** out) {
     if (!s || !out) return fail(nullptr, TO_EINVAL, "null argument");
     *out = nullptr;
-    if (s->model < 0 || s->model > MODEL_ACROBOT) return fail(nullptr, TO_EINVAL, "unknown model id");
+    if (s->model < 0 || s->model > MODEL_EXPR) return fail(nullptr, TO_EINVAL, "unknown model id");
     if (s->N < 2 || s->B < 1) return fail(nullptr, TO_EINVAL, "need N >= 2 and B >= 1");
     ModelParams mp = default_model(s->model, s->model == MODEL_DOUBLE_INTEGRATOR ? s->m : 1);
     if (mp.n != s->n) return fail(nullptr, TO_EDIM, "Objective state dimensions don't match model.");      // src/problem.jl:67
@@ -41,6 +41,28 @@ int orc_create(const to_spec* s, orc_handle** out) {
     auto* h = new orc_handle();
     Problem& P = h->P;
     P.model = mp; P.N = s->N; P.B = s->B; P.t0 = s->t0;
+    if (s->model == MODEL_EXPR) {   // Problem(models::Vector, ...): RD.dims(models), src/dynamics.jl:15-31
+        if (!s->dyn || s->ndyn < 1 || !s->dyn_index || !s->nx || !s->nu) { delete h; return fail(nullptr, TO_EINVAL, "recorded-program models: null dyn / dyn_index / nx / nu"); }
+        for (int i = 0; i < s->ndyn; i++) {
+            const to_dynamics_spec& d = s->dyn[i];
+            DynProg dp; dp.n_in = d.n_in; dp.m_in = d.m_in; dp.n_out = d.n_out; dp.discrete = d.discrete != 0;
+            if (!d.prog || d.prog_len < d.n_out || d.n_in > mp.n || d.m_in > mp.m || d.n_out > mp.n) { delete h; return fail(nullptr, TO_EINVAL, "recorded-program model: bad program size or dimensions"); }
+            dp.prog.assign(d.prog, d.prog + 3 * d.prog_len); dp.consts.assign(d.consts, d.consts + d.nconst);
+            P.dyn.push_back(dp);
+        }
+        for (int k = 0; k < s->N - 1; k++) {
+            const int di = s->dyn_index[k];
+            if (di < 0 || di >= s->ndyn) { delete h; return fail(nullptr, TO_EINVAL, "dyn_index out of range"); }
+            const DynProg& d = P.dyn[di];
+            if (d.n_in != s->nx[k] || d.m_in != s->nu[k]) { delete h; return fail(nullptr, TO_EDIM, "Model " + std::to_string(k + 1) + " does not have the dimensions of knot " + std::to_string(k + 1) + "."); }
+            if (d.n_out != s->nx[k + 1]) {    // src/dynamics.jl:23-28
+                delete h;
+                return fail(nullptr, TO_EDIM, "Model mismatch at time step " + std::to_string(k + 1) + ". Model " + std::to_string(k + 1) + " has an output dimension of " +
+                            std::to_string(d.n_out) + " but model " + std::to_string(k + 2) + " has a state dimension of " + std::to_string(s->nx[k + 1]) + ".");
+            }
+            P.dyn_index.push_back(di);
+        }
+    }
     P.dt.assign(s->dt, s->dt + (s->N - 1));
     const int n = mp.n, m = mp.m;
     for (int i = 0; i < s->ncost; i++) {

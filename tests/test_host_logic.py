@@ -168,7 +168,7 @@ def test_abi_struct_layout_matches_the_binding_tables():
     import trajopt_b200 as TO
     hdr = open(os.path.join(ROOT, "include", "trajopt_b200.h")).read()
     structs = {}
-    for body, name in re.findall(r"typedef struct \{(.*?)\}\s*(to_cost_spec|to_constraint_spec|to_spec|to_options);", hdr, flags=re.S):
+    for body, name in re.findall(r"typedef struct \{(.*?)\}\s*(to_cost_spec|to_dynamics_spec|to_constraint_spec|to_spec|to_options);", hdr, flags=re.S):
         body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
         fields = []
         for decl in body.split(";"):

@@ -20,7 +20,7 @@ LIB_PATH = os.environ.get("LIBTRAJOPT_B200") or os.path.join(_HERE, "libtrajopt_
 # error codes (include/trajopt_b200.h)
 TO_OK, TO_EINVAL, TO_EDIM, TO_ECUDA, TO_ENOMEM, TO_ESTATE, TO_ECONE = 0, -1, -2, -3, -4, -5, -6
 
-MODEL_DOUBLE_INTEGRATOR, MODEL_CARTPOLE, MODEL_QUADROTOR, MODEL_ACROBOT = 0, 1, 2, 3
+MODEL_DOUBLE_INTEGRATOR, MODEL_CARTPOLE, MODEL_QUADROTOR, MODEL_ACROBOT, MODEL_EXPR = 0, 1, 2, 3, 4
 COST_DIAGONAL, COST_QUADRATIC, COST_DIAGONAL_QUAT, COST_EXPR = 0, 1, 2, 3
 (OP_CONST, OP_X, OP_U, OP_ADD, OP_SUB, OP_MUL, OP_DIV, OP_NEG, OP_SIN, OP_COS, OP_EXP, OP_LOG, OP_SQRT, OP_POWC, OP_TANH,
  OP_ADDC, OP_MULC, OP_DIVC, OP_RDIVC, OP_RSUBC) = range(20)
@@ -45,11 +45,17 @@ class to_constraint_spec(C.Structure):
                 ("c", c_double_p), ("rad", c_double_p), ("val", C.c_double)]
 
 
+class to_dynamics_spec(C.Structure):
+    _fields_ = [("n_in", C.c_int32), ("m_in", C.c_int32), ("n_out", C.c_int32), ("discrete", C.c_int32), ("prog_len", C.c_int32), ("nconst", C.c_int32),
+                ("prog", c_int32_p), ("consts", c_double_p)]
+
+
 class to_spec(C.Structure):
     _fields_ = [("model", C.c_int32), ("n", C.c_int32), ("m", C.c_int32), ("N", C.c_int32), ("B", C.c_int32),
                 ("device", C.c_int32), ("nparams", C.c_int32), ("params", c_double_p), ("dt", c_double_p), ("t0", C.c_double),
                 ("ncost", C.c_int32), ("costs", C.POINTER(to_cost_spec)), ("cost_index", c_int32_p),
-                ("ncon", C.c_int32), ("cons", C.POINTER(to_constraint_spec)), ("error_state", C.c_int32)]
+                ("ncon", C.c_int32), ("cons", C.POINTER(to_constraint_spec)), ("error_state", C.c_int32),
+                ("ndyn", C.c_int32), ("dyn", C.POINTER(to_dynamics_spec)), ("dyn_index", c_int32_p), ("nx", c_int32_p), ("nu", c_int32_p)]
 
 
 class to_options(C.Structure):
@@ -76,7 +82,8 @@ def _f64(a):
 class Spec:
     """Owns the numpy buffers behind a ``to_spec`` so the pointers stay valid."""
 
-    def __init__(self, model, n, m, N, B, dt, costs, cost_index, cons, params=None, t0=0.0, device=0, error_state=False):
+    def __init__(self, model, n, m, N, B, dt, costs, cost_index, cons, params=None, t0=0.0, device=0, error_state=False,
+                 dyn=None, dyn_index=None, nx=None, nu=None):
         self.keep = []
         self.model, self.n, self.m, self.N, self.B = int(model), int(n), int(m), int(N), int(B)
         dt = _f64(dt)
@@ -113,8 +120,22 @@ class Spec:
                                        float(k.get("val", 0.0)))
         p = _f64(params)
         self.keep += [cs, ks, p]
+        ds, di, nxv, nuv = None, None, None, None
+        if dyn:     # hybrid problem: recorded programs, one model per knot (to_dynamics_spec)
+            ds = (to_dynamics_spec * len(dyn))()
+            for i, d in enumerate(dyn):
+                prog = np.ascontiguousarray(np.asarray(d["prog"], dtype=np.int32).reshape(-1, 3))
+                consts = _f64(d["consts"])
+                self.keep += [prog, consts]
+                ds[i] = to_dynamics_spec(int(d["n_in"]), int(d["m_in"]), int(d["n_out"]), int(bool(d.get("discrete", False))), len(prog), len(consts),
+                                         _ip(prog), _dp(consts) if len(consts) else None)
+            di = np.ascontiguousarray(np.asarray(dyn_index, dtype=np.int32))
+            nxv = np.ascontiguousarray(np.asarray(nx, dtype=np.int32)); nuv = np.ascontiguousarray(np.asarray(nu, dtype=np.int32))
+            self.keep += [ds, di, nxv, nuv]
         self.c = to_spec(self.model, self.n, self.m, self.N, self.B, int(device), 0 if p is None else len(p), _dp(p), _dp(dt), float(t0),
-                         len(costs), cs, _ip(ci), len(cons), ks, int(bool(error_state)))
+                         len(costs), cs, _ip(ci), len(cons), ks, int(bool(error_state)),
+                         0 if not dyn else len(dyn), ds, _ip(di), _ip(nxv), _ip(nuv))
+        self.dyn, self.dyn_index, self.nx, self.nu = dyn, dyn_index, nx, nu
         self.error_state = bool(error_state)
         self.costs, self.cost_index, self.cons, self.dt = costs, list(cost_index), cons, dt
         self.t0, self.device = float(t0), int(device)

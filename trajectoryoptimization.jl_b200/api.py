@@ -176,6 +176,58 @@ class Acrobot(_Model):
 # Cost functions (reference src/cost_functions.jl)
 
 
+class AutodiffDynamics(_Model):
+    """A user-defined dynamics model: the counterpart of ``RD.@autodiff struct M <: RD.ContinuousDynamics end`` + ``RD.state_dim`` /
+    ``RD.control_dim`` / ``RD.output_dim`` + ``RD.dynamics(::M, x, u)`` (test/hybrid_dynamics_model.jl:14-39), discretised with RK4 like every
+    model of the path (``RD.DiscretizedDynamics{RD.RK4}``).  ``fun(x, u)`` is called once with recording vectors (see ``Expr``) and returns
+    the ``output_dim`` entries of ``xdot``.  ``discrete=True``: ``fun`` is a jump map ``x+ = g(x, u)`` applied as is -- its output dimension
+    may differ from its state dimension, which is how the state dimension changes along a hybrid trajectory.  Used through
+    ``Problem([model_1, ..., model_{N-1}], obj, x0, tf)`` (src/problem.jl:36-73)."""
+    model_id = K.MODEL_EXPR
+
+    def __init__(self, n, m, fun, output_dim=None, discrete=False):
+        self.n, self.m, self.fun, self.discrete = int(n), int(m), fun, bool(discrete)
+        self.n_out = self.n if output_dim is None else int(output_dim)
+        if self.n_out != self.n and not self.discrete:
+            raise ArgumentError("a continuous model integrates its own state: output_dim != state_dim needs discrete=True (a jump map)")
+        tape = _Tape()
+        x = np.array([tape.emit(K.OP_X, i, 0) for i in range(self.n)], dtype=object)
+        u = np.array([tape.emit(K.OP_U, j, 0) for j in range(self.m)], dtype=object)
+        out = list(np.atleast_1d(np.asarray(fun(x, u), dtype=object)).ravel())
+        if len(out) != self.n_out:
+            raise DimensionMismatch(f"the dynamics function returned {len(out)} values, output_dim is {self.n_out}")
+        outs = [tape.lift(o) for o in out]
+        one = tape.const_index(1.0)
+        for o in outs:   # the outputs are the LAST n_out instructions, in order: re-emit each one (x * 1 is exact)
+            tape.emit(K.OP_MULC, o.idx, one)
+        self.prog, self.consts = np.asarray(tape.prog, dtype=np.int32), np.asarray(tape.consts, dtype=float)
+
+    def output_dim(self):   # RD.output_dim(model)
+        return self.n_out
+
+    def copy(self):
+        return self
+
+    def _spec(self):
+        return dict(n_in=self.n, m_in=self.m, n_out=self.n_out, discrete=self.discrete, prog=self.prog, consts=self.consts)
+
+
+def model_dims(models):
+    """``RD.dims(models::Vector{<:DiscreteDynamics})`` (src/dynamics.jl:15-31): ``(nx, nu)``, the state / control dimension at each of the ``N``
+    knot points of ``N - 1`` models; the last state dimension is the last model's output dimension, the last control dimension the last
+    model's.  Raises ``DimensionMismatch`` when consecutive models do not fit."""
+    models = list(models)
+    out = lambda mdl: mdl.output_dim() if hasattr(mdl, "output_dim") else mdl.dims()[0]
+    nx = [mdl.dims()[0] for mdl in models] + [out(models[-1])]
+    nu = [mdl.dims()[1] for mdl in models] + [models[-1].dims()[1]]
+    for k, mdl in enumerate(models, start=1):
+        ny = out(mdl)
+        if nx[k] != ny:
+            raise DimensionMismatch(f"Model mismatch at time step {k}. Model {k} has an output dimension of {ny} but model {k + 1} has a state "
+                                    f"dimension of {nx[k]}.")
+    return nx, nu
+
+
 def _isposdef(A):
     A = np.asarray(A, dtype=float)
     if not np.allclose(A, A.T):
@@ -540,11 +592,7 @@ class Objective:
             self.cost = list(cost) + [args[0]]
         else:
             self.cost = list(cost)
-        n, m = self.cost[0].state_dim, self.cost[0].control_dim
-        for c in self.cost:
-            if (c.state_dim, c.control_dim) != (n, m):
-                raise DimensionMismatch("all cost functions of an Objective must have the same dimensions")
-        self.J = np.zeros(len(self.cost))
+        self.J = np.zeros(len(self.cost))     # (costs of different dimensions are allowed: hybrid problems, RD.dims(obj) src/objective.jl:49)
 
     def __len__(self):
         return len(self.cost)
@@ -557,6 +605,9 @@ class Objective:
 
     def dims(self):
         return self.cost[0].state_dim, self.cost[0].control_dim
+
+    def dims_all(self):   # RD.dims(obj)  src/objective.jl:49: per-knot dimensions
+        return [c.state_dim for c in self.cost], [c.control_dim for c in self.cost]
 
     def copy(self):   # Base.copy(obj)  src/objective.jl:112: copies of the cost functions (knots that share a cost object keep sharing the copy)
         memo = {}
@@ -903,12 +954,26 @@ class ControlBound(BoundConstraint):   # src/constraints.jl:619-640
 
 
 class ConstraintList:
-    """``ConstraintList(n, m, N)`` (src/constraint_list.jl:35-52)."""
+    """``ConstraintList(n, m, N)``, ``ConstraintList(nx, nu)`` (per-knot dimensions) or ``ConstraintList(models)`` (src/constraint_list.jl:25-66)."""
 
-    def __init__(self, n, m, N):
-        self.n, self.m, self.N = n, m, N
+    def __init__(self, *args):
+        if len(args) == 3:
+            n, m, N = (int(a) for a in args)
+            self.nx, self.nu = [n] * N, [m] * N
+        elif len(args) == 2:
+            self.nx, self.nu = [int(a) for a in args[0]], [int(a) for a in args[1]]
+            if len(self.nx) != len(self.nu):
+                raise DimensionMismatch("nx and nu must have one entry per knot point")
+        elif len(args) == 1:
+            self.nx, self.nu = model_dims(args[0])
+        else:
+            raise ArgumentError("ConstraintList(n, m, N) | ConstraintList(nx, nu) | ConstraintList(models)")
+        self.N = len(self.nx)
+        self.n, self.m = self.nx[0], self.nu[0]
         self.constraints, self.inds = [], []
-        self.p = np.zeros(N, dtype=int)
+        self.p = np.zeros(self.N, dtype=int)
+
+    uniform = property(lambda s: len(set(s.nx)) == 1 and len(set(s.nu)) == 1)
 
     def __len__(self):
         return len(self.constraints)
@@ -923,7 +988,7 @@ class ConstraintList:
         return zip(self.inds, self.constraints)
 
     def copy(self):   # Base.copy(cons)  src/constraint_list.jl:54-60: a new list over the same constraint objects
-        new = ConstraintList(self.n, self.m, self.N)
+        new = ConstraintList(self.nx, self.nu)
         new.constraints, new.inds, new.p = list(self.constraints), list(self.inds), self.p.copy()
         return new
 
@@ -931,14 +996,14 @@ class ConstraintList:
 def add_constraint(cons, con, inds, idx=-1):
     """``add_constraint!(cons, con, inds)`` (src/constraint_list.jl:103-134); ``inds`` = knot ``k`` or ``(first, last)``."""
     first, last = (inds, inds) if np.ndim(inds) == 0 else (inds[0], inds[-1])
-    n_ok = getattr(con, "n", cons.n) == cons.n
-    m_ok = getattr(con, "m", cons.m) == cons.m
-    if not (n_ok and m_ok):
-        raise DimensionMismatch("New constraint not consistent with n and m")   # src/constraint_list.jl:108-110
     if not (1 <= first <= last <= cons.N):
         raise ArgumentError("Invalid inds, inds[end] must be less than number of knotpoints")   # @assert :107
-    if isinstance(con, StateBound): con._bind(cons.m)
-    if isinstance(con, ControlBound): con._bind(cons.n)
+    for k in range(first, last + 1):     # check_dims at every knot of the range  src/constraint_list.jl:107-111
+        nk, mk = cons.nx[k - 1], cons.nu[k - 1]
+        if not (getattr(con, "n", nk) == nk and getattr(con, "m", mk) == mk):
+            raise DimensionMismatch(f"New constraint not consistent with n={nk} and m={mk} at time step {k}.")
+    if isinstance(con, StateBound): con._bind(cons.nu[first - 1])
+    if isinstance(con, ControlBound): con._bind(cons.nx[first - 1])
     pos = len(cons.constraints) if idx == -1 else idx
     cons.constraints.insert(pos, con)
     cons.inds.insert(pos, (int(first), int(last)))
@@ -973,19 +1038,53 @@ class Problem:
         if len(args) != 2:
             raise ArgumentError("Problem(model, obj, x0, tf; xf, constraints, ...) takes x0 and tf positionally")
         x0, tf = args
-        n, m = model.dims()
         N = len(obj)
         x0 = np.asarray(x0, dtype=float)
+        self.hybrid = isinstance(model, (list, tuple))
+        if self.hybrid:
+            # Problem(models::Vector{<:DiscreteDynamics}, obj, x0, tf)  src/problem.jl:36-73: per-knot dimensions from RD.dims(models); the
+            # device works on the padded dimensions (n, m) = (4, 2) with the knot's own entries first (include/trajopt_b200.h to_spec.nx)
+            models = list(model)
+            nxv, nuv = model_dims(models)                       # DimensionMismatch "Model mismatch at time step k"
+            if len(models) != N - 1:
+                raise DimensionMismatch("need one model per time step (N - 1 models)")     # @assert length(models) == N-1
+            if any(not isinstance(mdl, AutodiffDynamics) for mdl in models):
+                raise ArgumentError("a model vector holds AutodiffDynamics models")
+            if max(nxv) > 4 or max(nuv) > 2:
+                raise ArgumentError("hybrid problems: at most 4 states and 2 controls per knot (the padded kernel instance)")
+            n, m = 4, 2
+            if error_state:
+                raise ArgumentError("error_state=True needs a Lie-group model (RD.errstate_dim(model) != state_dim)")
+            if x0.shape[-1] != nxv[0]:
+                raise DimensionMismatch("x0 does not match the first model's state dimension")   # @assert length(x0) == nx[1]
+            cons = constraints if constraints is not None else ConstraintList(nxv, nuv)
+            if cons.nx != nxv:
+                raise DimensionMismatch("Constraint state dimensions don't match model")      # src/problem.jl:62
+            if cons.nu != nuv:
+                raise DimensionMismatch("Constraint control dimensions don't match model")    # src/problem.jl:63
+            onx, onu = obj.dims_all()
+            if onx != nxv:
+                raise DimensionMismatch("Objective state dimensions don't match model.")      # src/problem.jl:65
+            if onu != nuv:
+                raise DimensionMismatch("Objective control dimensions don't match model.")    # src/problem.jl:66
+            x0 = np.concatenate([x0, np.zeros(x0.shape[:-1] + (n - nxv[0],))], axis=-1)
+            self.nx, self.nu = nxv, nuv
+            nf = nxv[-1]
+        else:
+            n, m = model.dims()
+            if x0.shape[-1] != n:
+                raise DimensionMismatch("x0 does not match the model's state dimension")   # @assert src/problem.jl:48
+            onx, onu = obj.dims_all()
+            if any(a != n for a in onx):
+                raise DimensionMismatch("Objective state dimensions don't match model.")      # src/problem.jl:67
+            if any(a != m for a in onu):
+                raise DimensionMismatch("Objective control dimensions don't match model.")    # src/problem.jl:68
+            cons = constraints if constraints is not None else ConstraintList(n, m, N)
+            if any(a != n for a in cons.nx) or any(a != m for a in cons.nu):
+                raise DimensionMismatch("Constraint state dimensions don't match model")   # src/problem.jl:64-65
+            self.nx, self.nu = [n] * N, [m] * N
+            nf = n
         B = int(batch) if batch is not None else (x0.shape[0] if x0.ndim == 2 else 1)
-        if x0.shape[-1] != n:
-            raise DimensionMismatch("x0 does not match the model's state dimension")   # @assert src/problem.jl:48
-        if obj.dims()[0] != n:
-            raise DimensionMismatch("Objective state dimensions don't match model.")      # src/problem.jl:67
-        if obj.dims()[1] != m:
-            raise DimensionMismatch("Objective control dimensions don't match model.")    # src/problem.jl:68
-        cons = constraints if constraints is not None else ConstraintList(n, m, N)
-        if (cons.n, cons.m) != (n, m):
-            raise DimensionMismatch("Constraint state dimensions don't match model")   # src/problem.jl:64-65
         if cons.N != N:
             raise DimensionMismatch("ConstraintList horizon does not match the objective")
         if dt is None:
@@ -1003,12 +1102,9 @@ class Problem:
         self.error_state = bool(error_state)
         self.ne = model.errstate_dim() if error_state else n
         self.x0 = np.broadcast_to(x0, (B, n)).copy()
-        self.xf = np.full(n, np.nan) if xf is None else np.asarray(xf, dtype=float).copy()
-        uniq, index = obj._tables()
-        self._cost_objs = uniq
-        con_specs = [c._spec(f, l) for (f, l), c in zip(cons.inds, cons.constraints)]
-        self.spec = K.Spec(model.model_id, n, m, N, B, dtv, [c._spec() for c in uniq], index, con_specs,
-                           params=model.params, t0=t0, device=device, error_state=self.error_state)
+        self.xf = np.full(nf, np.nan) if xf is None else np.asarray(xf, dtype=float).copy()
+        self._device = device
+        self.spec = self._make_spec(dtv, t0)
         self._open()
         self._sig = self._signature()
         self._call("to_set_initial_state", K._dp(self.x0))
@@ -1016,6 +1112,47 @@ class Problem:
             initial_controls(self, U0)
         if X0 is not None:
             initial_states(self, X0)
+
+    def _make_spec(self, dtv, t0):
+        """the ABI description of the current host-side problem (cost table, constraint list, models)"""
+        cons = self.constraints
+        if not self.hybrid:
+            uniq, index = self.obj._tables()
+            self._cost_objs = uniq
+            con_specs = [c._spec(f, l) for (f, l), c in zip(cons.inds, cons.constraints)]
+            return K.Spec(self.model.model_id, self.n, self.m, self.N, self.B, dtv, [c._spec() for c in uniq], index, con_specs,
+                          params=self.model.params, t0=t0, device=self._device, error_state=self.error_state)
+        # hybrid: every cost / constraint is re-expressed on the padded [x(4); u(2)] layout (change_dimension, src/cost_functions.jl:391-401,
+        # src/constraints.jl:934-936); the unused controls get a unit weight so that Quu stays positive definite -- they stay exactly zero
+        n, m = self.n, self.m
+        padded, uniq, index, seen = {}, [], [], {}
+        self._cost_objs = []
+        for k, c in enumerate(self.obj.cost):
+            key = (id(c), self.nx[k], self.nu[k])
+            if key not in padded:
+                if not isinstance(c, DiagonalCost) or isinstance(c, DiagonalQuatCost):
+                    raise ArgumentError("hybrid problems take DiagonalCost / LQRCost stage costs")
+                pc = c
+                if (self.nx[k], self.nu[k]) != (n, m):
+                    nk, mk = self.nx[k], self.nu[k]
+                    Qd, Rd, q, r = np.zeros(n), np.ones(m), np.zeros(n), np.zeros(m)
+                    Qd[:nk], Rd[:mk], q[:nk], r[:mk] = np.diag(c.Q), np.diag(c.R), c.q, c.r
+                    pc = DiagonalCost(Qd, Rd, q=q, r=r, c=c.c, terminal=c.terminal, checks=False)
+                padded[key] = pc
+                seen[key] = len(uniq); uniq.append(pc); self._cost_objs.append(c)
+            index.append(seen[key])
+        con_specs = []
+        for (f, l), c in zip(cons.inds, cons.constraints):
+            nk, mk = self.nx[f - 1], self.nu[f - 1]
+            pc = c if (nk, mk) == (n, m) else IndexedConstraint(n, m, c, (1, nk), (1, mk))
+            con_specs.append(pc._spec(f, l))
+        mods, dyn_index, mseen = [], [], {}
+        for mdl in self.model:
+            if id(mdl) not in mseen:
+                mseen[id(mdl)] = len(mods); mods.append(mdl._spec())
+            dyn_index.append(mseen[id(mdl)])
+        return K.Spec(K.MODEL_EXPR, n, m, self.N, self.B, dtv, [c._spec() for c in uniq], index, con_specs, t0=t0, device=self._device,
+                      dyn=mods, dyn_index=dyn_index, nx=self.nx, nu=self.nu)
 
     def _open(self):
         """create the device-side problem (to_create); fails loudly without the CUDA library / a GPU."""
@@ -1043,14 +1180,8 @@ class Problem:
         t = np.empty(self.N)
         self._raw_call("to_get_times", K._dp(t))
         opts = getattr(self, "_options", None)
-        uniq, index = self.obj._tables()
-        self._cost_objs = uniq
-        cons = self.constraints
-        con_specs = [c._spec(f, l) for (f, l), c in zip(cons.inds, cons.constraints)]
-        old = self.spec
         self.close()
-        self.spec = K.Spec(self.model.model_id, self.n, self.m, self.N, self.B, np.diff(t), [c._spec() for c in uniq], index, con_specs,
-                           params=self.model.params, t0=float(t[0]), device=old.device, error_state=self.error_state)
+        self.spec = self._make_spec(np.diff(t), float(t[0]))
         self._open()
         self._sig = self._signature()
         self._raw_call("to_set_initial_state", K._dp(self.x0))
@@ -1083,17 +1214,27 @@ class Problem:
             pass
 
 
-def dims(prob):   # RD.dims(prob, k)  src/problem.jl:147
+def dims(prob, k=None):   # RD.dims(prob) / RD.dims(prob, k)  src/problem.jl:146-147 ; RD.dims(models)  src/dynamics.jl:15 ; RD.dims(obj)
+    if isinstance(prob, (list, tuple)):
+        return model_dims(prob)
+    if isinstance(prob, Objective):
+        return prob.dims_all()
+    if k is not None:
+        return prob.nx[k - 1], prob.nu[k - 1], prob.N
+    if getattr(prob, "hybrid", False):
+        return list(prob.nx), list(prob.nu), prob.N
     return prob.n, prob.m, prob.N
 
 
 def state_dim(obj, k=1):   # RD.state_dim(prob | obj, k), state_dim(cost | con)  src/problem.jl:149, src/objective.jl:60
     if isinstance(obj, Objective): return obj[k - 1].state_dim
+    if isinstance(obj, Problem): return obj.nx[k - 1]
     return obj.state_dim if isinstance(obj, CostFunction) else obj.n
 
 
 def control_dim(obj, k=1):   # RD.control_dim(prob | obj, k)  src/problem.jl:150, src/objective.jl:61
     if isinstance(obj, Objective): return obj[k - 1].control_dim
+    if isinstance(obj, Problem): return obj.nu[k - 1]
     return obj.control_dim if isinstance(obj, CostFunction) else obj.m
 
 

@@ -37,6 +37,8 @@ struct to_handle {
     std::vector<DevCon> h_cons;
     std::vector<double> h_mu, h_dt;
     std::vector<int> h_cost_index;
+    std::vector<DevDyn> h_dyn;    // TO_MODEL_EXPR
+    std::vector<int> h_dyn_index;
     DevCost* d_costs = nullptr;
     DevCon* d_cons = nullptr;
     double* d_mu = nullptr;
@@ -172,6 +174,7 @@ void model_defaults(int model, int m, int& n_out, int& m_out, double* p) {
             p[7] = 0.1750; p[8] = 1.0; p[9] = 0.0245; break;
         case TO_MODEL_ACROBOT:
             n_out = 4; m_out = 1; p[0] = 1; p[1] = 1; p[2] = 1; p[3] = 1; p[4] = 1.0 / 12; p[5] = 1.0 / 12; p[6] = 1.0; p[7] = 9.81; break;
+        case TO_MODEL_EXPR: n_out = 4; m_out = 2; break;       // recorded programs on the padded dimensions the kernels are instantiated for
         default: n_out = -1; m_out = -1;
     }
 }
@@ -381,6 +384,45 @@ int to_create(const to_spec* s, to_handle** out) {
     model_defaults(s->model, s->m, mn, mm, params);
     if (mn < 0) return fail(nullptr, TO_EINVAL, "unknown model id");
     if (s->model == TO_MODEL_DOUBLE_INTEGRATOR && s->m != 1 && s->m != 2) return fail(nullptr, TO_EDIM, "DoubleIntegrator: supported dimensions are 1 and 2");
+    std::vector<DevDyn> dyn_tab; std::vector<int> dyn_idx;
+    if (s->model == TO_MODEL_EXPR) {
+        // Problem(models::Vector, ...) with RD.dims(models) (src/dynamics.jl:15-31): per-knot dimensions, padded to the (n, m) = (4, 2) the kernels exist for
+        if (s->n != 4 || s->m != 2) return fail(nullptr, TO_EDIM, "recorded-program models: the padded dimensions must be n = 4, m = 2 (largest per-knot dimensions <= that)");
+        if (s->N < 2 || !s->dyn || s->ndyn < 1 || !s->dyn_index || !s->nx || !s->nu) return fail(nullptr, TO_EINVAL, "recorded-program models: null dyn / dyn_index / nx / nu");
+        for (int i = 0; i < s->ndyn; i++) {
+            const to_dynamics_spec& d = s->dyn[i];
+            if (!d.prog || d.prog_len < 1 || d.prog_len > TO_EXPR_LEN || d.nconst < 0 || d.nconst > TO_EXPR_CONST || (d.nconst > 0 && !d.consts) ||
+                d.n_in < 1 || d.n_in > 4 || d.m_in < 0 || d.m_in > 2 || d.n_out < 1 || d.n_out > 4 || d.n_out > d.prog_len)
+                return fail(nullptr, TO_EINVAL, "recorded-program model: bad program size or dimensions");
+            DevDyn dd; std::memset(&dd, 0, sizeof(dd));
+            dd.n_in = d.n_in; dd.m_in = d.m_in; dd.n_out = d.n_out; dd.discrete = d.discrete != 0; dd.prog_len = d.prog_len;
+            for (int j = 0; j < d.prog_len; j++) {
+                const int op = d.prog[3 * j], a = d.prog[3 * j + 1], b = d.prog[3 * j + 2];
+                const bool bin = op >= TO_OP_ADD && op <= TO_OP_DIV;
+                bool ok = op >= 0 && op <= TO_OP_RSUBC;
+                if (op == TO_OP_CONST) ok = ok && a >= 0 && a < d.nconst;
+                else if (op == TO_OP_X) ok = ok && a >= 0 && a < d.n_in;
+                else if (op == TO_OP_U) ok = ok && a >= 0 && a < d.m_in;
+                else { ok = ok && a >= 0 && a < j; if (bin) ok = ok && b >= 0 && b < j; if (op == TO_OP_POWC || op >= TO_OP_ADDC) ok = ok && b >= 0 && b < d.nconst; }
+                if (!ok) return fail(nullptr, TO_EINVAL, "recorded-program model: invalid instruction");
+                dd.prog[3 * j] = op; dd.prog[3 * j + 1] = a; dd.prog[3 * j + 2] = b;
+            }
+            for (int j = 0; j < d.nconst; j++) dd.pconst[j] = d.consts[j];
+            dyn_tab.push_back(dd);
+        }
+        for (int k = 0; k < s->N - 1; k++) {
+            const int di = s->dyn_index[k];
+            if (di < 0 || di >= s->ndyn) return fail(nullptr, TO_EINVAL, "dyn_index out of range");
+            const DevDyn& d = dyn_tab[di];
+            if (d.n_in != s->nx[k] || d.m_in != s->nu[k])
+                return fail(nullptr, TO_EDIM, "Model " + std::to_string(k + 1) + " has state / control dimensions (" + std::to_string(d.n_in) + ", " + std::to_string(d.m_in) +
+                            ") but knot " + std::to_string(k + 1) + " has (" + std::to_string(s->nx[k]) + ", " + std::to_string(s->nu[k]) + ").");
+            if (d.n_out != s->nx[k + 1])     // src/dynamics.jl:23-28
+                return fail(nullptr, TO_EDIM, "Model mismatch at time step " + std::to_string(k + 1) + ". Model " + std::to_string(k + 1) + " has an output dimension of " +
+                            std::to_string(d.n_out) + " but model " + std::to_string(k + 2) + " has a state dimension of " + std::to_string(s->nx[k + 1]) + ".");
+            dyn_idx.push_back(di);
+        }
+    }
     if (mn != s->n) return fail(nullptr, TO_EDIM, "Objective state dimensions don't match model.");     // src/problem.jl:67
     if (mm != s->m) return fail(nullptr, TO_EDIM, "Objective control dimensions don't match model.");   // src/problem.jl:68
     if (s->N < 2 || s->B < 1) return fail(nullptr, TO_EINVAL, "need N >= 2 knot points and B >= 1 instances");
@@ -472,12 +514,15 @@ int to_create(const to_spec* s, to_handle** out) {
     }
     h->h_mu.assign(s->ncon, P.opt.penalty_initial);
     h->h_dt.assign(s->dt, s->dt + (N - 1));
+    h->h_dyn = dyn_tab; h->h_dyn_index = dyn_idx;
 
     int rc = TO_OK;
     double* d_dt = nullptr; int* d_ci = nullptr;
     P.strideX = (size_t)B * N * n; P.strideU = (size_t)B * (N - 1) * m;
 #define ALLOC(ptr, count) if (!rc) rc = dalloc(h, &(ptr), (size_t)(count))
     ALLOC(d_dt, N - 1); ALLOC(d_ci, N);
+    DevDyn* d_dyn = nullptr; int* d_dyni = nullptr;
+    if (!h->h_dyn.empty()) { ALLOC(d_dyn, h->h_dyn.size()); ALLOC(d_dyni, N - 1); }
     ALLOC(h->d_costs, s->ncost); ALLOC(h->d_cons, std::max(1, s->ncon)); ALLOC(h->d_mu, std::max(1, s->ncon));
     ALLOC(P.x0, (size_t)B * n); ALLOC(P.X, TO_NBUF * P.strideX); ALLOC(P.U, TO_NBUF * P.strideU); ALLOC(P.cur, B);
     ALLOC(P.AB, (size_t)B * (N - 1) * n * P.ldab); ALLOC(P.K, (size_t)B * (N - 1) * P.ne * m); ALLOC(P.d, (size_t)B * (N - 1) * m);
@@ -496,11 +541,16 @@ int to_create(const to_spec* s, to_handle** out) {
 #undef ALLOC
     if (rc) return bail(rc);
     P.exptab = h->d_exptab;
+    P.dyn = d_dyn; P.dyn_index = d_dyni;
     P.dt = d_dt; P.cost_index = d_ci; P.costs = h->d_costs; P.cons = h->d_cons; P.mu = h->d_mu; P.viol = h->d_viol;
     cudaStream_t st = h->stream;
     bool okc = true;
     okc &= cudaMemcpyAsync(d_dt, h->h_dt.data(), sizeof(double) * (N - 1), cudaMemcpyHostToDevice, st) == cudaSuccess;
     okc &= cudaMemcpyAsync(d_ci, h->h_cost_index.data(), sizeof(int) * N, cudaMemcpyHostToDevice, st) == cudaSuccess;
+    if (d_dyn) {
+        okc &= cudaMemcpyAsync(d_dyn, h->h_dyn.data(), sizeof(DevDyn) * h->h_dyn.size(), cudaMemcpyHostToDevice, st) == cudaSuccess;
+        okc &= cudaMemcpyAsync(d_dyni, h->h_dyn_index.data(), sizeof(int) * (N - 1), cudaMemcpyHostToDevice, st) == cudaSuccess;
+    }
     okc &= cudaMemsetAsync(P.x0, 0, sizeof(double) * B * n, st) == cudaSuccess;
     okc &= cudaMemsetAsync(P.X, 0xFF, sizeof(double) * TO_NBUF * P.strideX, st) == cudaSuccess;   // NaN: X0 = NaN until rollout!, src/problem.jl:83
     okc &= cudaMemsetAsync(P.U, 0, sizeof(double) * TO_NBUF * P.strideU, st) == cudaSuccess;      // U0 = 0, src/problem.jl:84

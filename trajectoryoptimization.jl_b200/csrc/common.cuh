@@ -25,7 +25,7 @@
 #define TO_NBUF 9            // trajectory buffers per instance: the live one + 8 line-search candidates
 
 // reference enums (mirrors include/trajopt_b200.h)
-enum { MODEL_DOUBLE_INTEGRATOR = 0, MODEL_CARTPOLE = 1, MODEL_QUADROTOR = 2, MODEL_ACROBOT = 3 };
+enum { MODEL_DOUBLE_INTEGRATOR = 0, MODEL_CARTPOLE = 1, MODEL_QUADROTOR = 2, MODEL_ACROBOT = 3, MODEL_EXPR = 4 };
 enum { CONE_ZERO = 0, CONE_NEGATIVE_ORTHANT = 1, CONE_SECOND_ORDER = 2, CONE_IDENTITY = 3, CONE_POSITIVE_ORTHANT = 4 };
 enum { CON_GOAL = 0, CON_BOUND = 1, CON_LINEAR = 2, CON_CIRCLE = 3, CON_SPHERE = 4, CON_NORM = 5, CON_COLLISION = 6, CON_QUATVEC = 7, CON_EXPR = 8 };
 
@@ -80,6 +80,14 @@ struct ExpTab {
     unsigned pky[TO_EXP_MAXT][TO_MAXNM];    // lambda index of the row at knot 0
 };
 
+// one dynamics model of a hybrid problem (to_dynamics_spec): a recorded program, RK4-discretised or a discrete jump map
+struct DevDyn {
+    int n_in, m_in, n_out, discrete;
+    int prog_len, pad[3];
+    int prog[3 * TO_EXPR_LEN];
+    double pconst[TO_EXPR_CONST];
+};
+
 struct DevOptions {
     double bp_reg_increase_factor, bp_reg_max, bp_reg_min, bp_reg_initial, bp_reg_fp;
     double ls_lower, ls_upper;
@@ -110,6 +118,8 @@ struct DevProblem {
     double* EC;               // [B][N][TO_EC_LEN]: g_e(16) | diag(16) | block (0,1),(0,2),(1,2) | pad
     double* REC;              // [B][N][TO_REC_LEN] (frag)
     const ExpTab* exptab;     // (frag) see ExpTab
+    const DevDyn* dyn;        // MODEL_EXPR: the models; knot k uses dyn[dyn_index[k]]
+    const int* dyn_index;     // [N-1]
     double* ABe;              // [B][N-1][ne+m][ne]   ne x (ne+m) col-major
     double* EG;               // [B][N][ne+m]
     double* EH;               // [B][N][ne+m][ne+m]

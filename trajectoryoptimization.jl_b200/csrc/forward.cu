@@ -304,7 +304,7 @@ __device__ __forceinline__ double rollout_fast(const DevProblem& P, const FwdTab
             }
         }
         if (!last) {
-            rk4_step<MODEL, double>(P.params, x, u, tab.dt[k], xn);
+            rk4_step<MODEL, double>(model_params<MODEL>(P, k), x, u, tab.dt[k], xn);
 #pragma unroll
             for (int i = 0; i < n; i++) { x[i] = xn[i]; if (!(fabs(xn[i]) <= P.opt.max_state_value)) ok = false; }
             // a blown-up trial keeps integrating (the group stays in lock step); its result is rejected through `ok`
@@ -361,7 +361,7 @@ __device__ __forceinline__ double rollout_generic(const DevProblem& P, int b, do
         J += cost_value(P.costs[P.cost_index[k]], n, m, x, u, !last);
         J += al_knot_penalty(P, k + 1, x, u, lam_b, viol);
         if (!last) {
-            rk4_step<MODEL, double>(P.params, x, u, P.dt[k], xn);
+            rk4_step<MODEL, double>(model_params<MODEL>(P, k), x, u, P.dt[k], xn);
 #pragma unroll
             for (int i = 0; i < n; i++) { x[i] = xn[i]; if (!(fabs(xn[i]) <= P.opt.max_state_value)) ok = false; }
             if (!ok) break;

@@ -61,6 +61,27 @@ __device__ __forceinline__ double dsin(double a) { return sin(a); }
 __device__ __forceinline__ double dcos(double a) { return cos(a); }
 __device__ __forceinline__ double drelu(double a) { return a > 0 ? a : 0.0; }
 template <class S> __device__ __forceinline__ S lift(double a) { return S(a); }
+// the remaining operations of the recorded-program interpreter (include/trajopt_b200.h to_expr_op), value + P partials
+DUAL_BIN dexp(const Dual<P>& a) { Dual<P> r; r.v = exp(a.v);
+#pragma unroll
+    for (int i = 0; i < P; i++) r.d[i] = r.v * a.d[i]; return r; }
+DUAL_BIN dlog(const Dual<P>& a) { Dual<P> r; r.v = log(a.v); const double iv = 1.0 / a.v;
+#pragma unroll
+    for (int i = 0; i < P; i++) r.d[i] = iv * a.d[i]; return r; }
+DUAL_BIN dsqrt(const Dual<P>& a) { Dual<P> r; r.v = sqrt(a.v); const double f = 0.5 / r.v;
+#pragma unroll
+    for (int i = 0; i < P; i++) r.d[i] = f * a.d[i]; return r; }
+DUAL_BIN dtanh(const Dual<P>& a) { Dual<P> r; r.v = tanh(a.v); const double f = 1.0 - r.v * r.v;
+#pragma unroll
+    for (int i = 0; i < P; i++) r.d[i] = f * a.d[i]; return r; }
+DUAL_BIN dpowc(const Dual<P>& a, double e) { Dual<P> r; r.v = pow(a.v, e); const double f = e * pow(a.v, e - 1.0);
+#pragma unroll
+    for (int i = 0; i < P; i++) r.d[i] = f * a.d[i]; return r; }
+__device__ __forceinline__ double dexp(double a) { return exp(a); }
+__device__ __forceinline__ double dlog(double a) { return log(a); }
+__device__ __forceinline__ double dsqrt(double a) { return sqrt(a); }
+__device__ __forceinline__ double dtanh(double a) { return tanh(a); }
+__device__ __forceinline__ double dpowc(double a, double e) { return pow(a, e); }
 
 // ---------------------------------------------------------------------------------------------------
 template <int MODEL> struct ModelDims;
@@ -71,10 +92,49 @@ template <> struct ModelDims<MODEL_ACROBOT> { static constexpr int n = 4, m = 1;
 constexpr int MODEL_DOUBLE_INTEGRATOR_2D = 16;
 template <> struct ModelDims<MODEL_DOUBLE_INTEGRATOR> { static constexpr int n = 2, m = 1; };
 template <> struct ModelDims<MODEL_DOUBLE_INTEGRATOR_2D> { static constexpr int n = 4, m = 2; };
+// user dynamics recorded as programs (TO_MODEL_EXPR), hybrid / variable-dimension models: instantiated for the padded dimensions (4, 2)
+// of the reference's example (test/hybrid_dynamics_model.jl:15-54)
+constexpr int MODEL_EXPR_42 = 20;
+template <> struct ModelDims<MODEL_EXPR_42> { static constexpr int n = 4, m = 2; };
 
 template <int MODEL, class S>
 __device__ __forceinline__ void dynamics(const double* __restrict__ p, const S* x, const S* u, S* xd) {
-    if constexpr (MODEL == MODEL_DOUBLE_INTEGRATOR || MODEL == MODEL_DOUBLE_INTEGRATOR_2D) {
+    if constexpr (MODEL == MODEL_EXPR_42) {
+        // `p` is the knot's DevDyn (model_params): interpret the recorded program with the scalar type S (double or dual numbers); the
+        // outputs are the last n_out instructions, the unused state slots of the next knot stay zero
+        constexpr int n = ModelDims<MODEL>::n;
+        const DevDyn& dy = *reinterpret_cast<const DevDyn*>(p);
+        S reg[TO_EXPR_LEN];
+        for (int i = 0; i < dy.prog_len; i++) {
+            const int op = dy.prog[3 * i], a = dy.prog[3 * i + 1], b = dy.prog[3 * i + 2];
+            S r = lift<S>(0.0);
+            switch (op) {
+                case 0: r = lift<S>(dy.pconst[a]); break;
+                case 1: r = x[a]; break;
+                case 2: r = u[a]; break;
+                case 3: r = reg[a] + reg[b]; break;
+                case 4: r = reg[a] - reg[b]; break;
+                case 5: r = reg[a] * reg[b]; break;
+                case 6: r = reg[a] / reg[b]; break;
+                case 7: r = -reg[a]; break;
+                case 8: r = dsin(reg[a]); break;
+                case 9: r = dcos(reg[a]); break;
+                case 10: r = dexp(reg[a]); break;
+                case 11: r = dlog(reg[a]); break;
+                case 12: r = dsqrt(reg[a]); break;
+                case 13: r = dpowc(reg[a], dy.pconst[b]); break;
+                case 14: r = dtanh(reg[a]); break;
+                case 15: r = reg[a] + dy.pconst[b]; break;
+                case 16: r = reg[a] * dy.pconst[b]; break;
+                case 17: r = reg[a] * (1.0 / dy.pconst[b]); break;
+                case 18: r = lift<S>(dy.pconst[b]) / reg[a]; break;
+                case 19: r = dy.pconst[b] - reg[a]; break;
+            }
+            reg[i] = r;
+        }
+#pragma unroll
+        for (int i = 0; i < n; i++) xd[i] = (i < dy.n_out) ? reg[dy.prog_len - dy.n_out + i] : lift<S>(0.0);
+    } else if constexpr (MODEL == MODEL_DOUBLE_INTEGRATOR || MODEL == MODEL_DOUBLE_INTEGRATOR_2D) {
         constexpr int dim = ModelDims<MODEL>::m;
         const double inv_mass = p[1];   // 1/mass, precomputed on the host
 #pragma unroll
@@ -145,6 +205,9 @@ __device__ __forceinline__ void dynamics(const double* __restrict__ p, const S* 
 template <int MODEL, class S>
 __device__ __forceinline__ void rk4_step(const double* __restrict__ p, const S* x, const S* u, double h, S* xn) {
     constexpr int n = ModelDims<MODEL>::n;
+    if constexpr (MODEL == MODEL_EXPR_42) {     // a discrete jump map is applied as is
+        if (reinterpret_cast<const DevDyn*>(p)->discrete) { dynamics<MODEL, S>(p, x, u, xn); return; }
+    }
     S k[n], acc[n], xt[n];
     dynamics<MODEL, S>(p, x, u, k);
 #pragma unroll
@@ -170,4 +233,12 @@ __device__ __forceinline__ void rk4_step(const double* __restrict__ p, const S* 
         case MODEL_CARTPOLE: { constexpr int MODEL = MODEL_CARTPOLE; CALL; } break;                \
         case MODEL_QUADROTOR: { constexpr int MODEL = MODEL_QUADROTOR; CALL; } break;              \
         case MODEL_ACROBOT: { constexpr int MODEL = MODEL_ACROBOT; CALL; } break;                  \
+        case MODEL_EXPR: { constexpr int MODEL = MODEL_EXPR_42; CALL; } break;                     \
     }
+
+// what rk4_step / dynamics take as `p`: the model's parameter vector, or -- recorded programs -- the DevDyn of knot k
+template <int MODEL>
+__device__ __forceinline__ const double* model_params(const DevProblem& P, int k) {
+    if constexpr (MODEL == MODEL_EXPR_42) return reinterpret_cast<const double*>(&P.dyn[P.dyn_index[k]]);
+    else return P.params;
+}

@@ -28,7 +28,7 @@ __global__ void __launch_bounds__(64) k_rollout(const DevProblem P) {
     for (int k = 0; k < P.N - 1; k++) {
 #pragma unroll
         for (int i = 0; i < m; i++) u[i] = U[k * m + i];
-        rk4_step<MODEL, double>(P.params, x, u, P.dt[k], xn);
+        rk4_step<MODEL, double>(model_params<MODEL>(P, k), x, u, P.dt[k], xn);
 #pragma unroll
         for (int i = 0; i < n; i++) { x[i] = xn[i]; X[(k + 1) * n + i] = xn[i]; }
     }
@@ -85,7 +85,7 @@ __global__ void __launch_bounds__(128) k_expand(const DevProblem P, int mode) {
 #pragma unroll
         for (int q = 0; q < NP; q++) u[i].d[q] = (n + i == js[q]) ? 1.0 : 0.0;
     }
-    rk4_step<MODEL, D>(P.params, x, u, P.dt[k], xn);
+    rk4_step<MODEL, D>(model_params<MODEL>(P, k), x, u, P.dt[k], xn);
 #pragma unroll
     for (int i = 0; i < n; i++) {
         if (NP == 2 && js[1] == js[0] + 1 && !(js[0] & 1)) *reinterpret_cast<double2*>(&AB[i * ld + js[0]]) = make_double2(xn[i].d[0], xn[i].d[1]);
@@ -201,7 +201,7 @@ __global__ void __launch_bounds__(128, TO_EXPAND_LIE_MINB) k_expand_lie(const De
 #pragma unroll
         for (int i = qs + 4; i < n; i++) x[i].d[0] = (i == j + 1) ? 1.0 : 0.0;
     }
-    rk4_step<MODEL, D>(P.params, x, u, h, xn);
+    rk4_step<MODEL, D>(model_params<MODEL>(P, k), x, u, h, xn);
     const double* q1 = X + n + qs;                                     // attitude of knot k + 1
     const double w1 = q1[0], x1 = q1[1], y1 = q1[2], z1 = q1[3];
     double col[ne];
@@ -248,64 +248,90 @@ cudaError_t launch_trivial_columns(const DevProblem& P, cudaStream_t s) {
 // kernel's time (profiles/r02_notes.md).
 __global__ void __launch_bounds__(256) k_expansion_rec16(const DevProblem P) {
     constexpr int qs = 3;
-    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const bool live = t < (long long)P.B * P.N * 16;
-    const int i = (int)(t & 15);
-    const long long bk = live ? (t >> 4) : 0;
-    const int k = (int)(bk % P.N), b = (int)(bk / P.N);
-    const int n = P.n;
-    const bool last = (k == P.N - 1);
-    const double* X = traj_X(P, P.cur[b], b) + (size_t)k * n;
-    const double* U = traj_U(P, P.cur[b], b) + (size_t)(last ? 0 : k) * P.m;      // (not read at the terminal knot)
-    const double* lam_b = P.lambda + (size_t)b * P.lambda_len;
+    const int i = threadIdx.x & 15;                                                   // full-state entry of this lane
+    const int n = P.n, N = P.N;
+    const int ngroups = (int)((gridDim.x * blockDim.x) >> 4);
     const ExpTab& tab = *P.exptab;
-    double* rec = P.REC + (size_t)bk * TO_REC_LEN;
-    const double zi = (i < n) ? X[i] : (last ? 0.0 : U[i - n]);
-    double g, h;
-    compact_entry_expansion(P, tab, k, i, zi, lam_b, g, h);
-    // the quaternion block: (g, h, q) of lanes 3..6 to every lane of the 16-lane group (lanes 3..5 use them)
-    double gq[4], hq[4], q[4];
+    // the AL rows acting on z_i: loop-invariant, kept in registers (the first version re-read them per knot: 530 instructions per thread)
+    unsigned px[TO_EXP_MAXT], py[TO_EXP_MAXT]; double nms[TO_EXP_MAXT], bnd[TO_EXP_MAXT];
 #pragma unroll
-    for (int r = 0; r < 4; r++) {
-        gq[r] = __shfl_sync(0xffffffffu, g, qs + r, 16); hq[r] = __shfl_sync(0xffffffffu, h, qs + r, 16); q[r] = __shfl_sync(0xffffffffu, zi, qs + r, 16);
-    }
-    if (!live) return;
-    if (i >= qs && i < qs + 3) {
-        const int c = i - qs;
-        // rows of G' = (L(q) H)': (-x,w,z,-y), (-y,-z,w,x), (-z,y,-x,w)   (kept in registers: no run-time indexed arrays)
-        const double G0[4] = {-q[1], q[0], q[3], -q[2]}, G1[4] = {-q[2], -q[3], q[0], q[1]}, G2[4] = {-q[3], q[2], -q[1], q[0]};
-        double gc[4];
+    for (int t = 0; t < TO_EXP_MAXT; t++) { px[t] = tab.pkx[t][i]; py[t] = tab.pky[t][i]; nms[t] = tab.nms[t][i]; bnd[t] = tab.bound[t][i]; }
+    const int e = (i < qs) ? i : i - 1;                                               // error-state coordinate of entry i (controls: 12 + a = i - 1)
+    const int pme = (int)((0x6420FDB9E7CA8531ULL >> (4 * (e & 15))) & 15);            // its physical slot
+    auto entry = [&](const DevCost& c, int k, int ii, double zi, const double* lam_b, const unsigned (&qx)[TO_EXP_MAXT], const unsigned (&qy)[TO_EXP_MAXT],
+                     const double (&qn)[TO_EXP_MAXT], const double (&qb)[TO_EXP_MAXT], double& g, double& h) {
+        const bool last = (k == N - 1);
+        if (ii < n) { g = fma(c.Qd[ii], zi, c.q[ii]); h = c.Qd[ii]; }
+        else if (last) { g = 0.0; h = 0.0; return; }
+        else { g = fma(c.Rd[ii - n], zi, c.r[ii - n]); h = c.Rd[ii - n]; }
 #pragma unroll
-        for (int r = 0; r < 4; r++) gc[r] = (c == 0) ? G0[r] : (c == 1) ? G1[r] : G2[r];
-        double qb = 0.0, ge = 0.0, hb0 = 0.0, hb1 = 0.0, hb2 = 0.0;
+        for (int t = 0; t < TO_EXP_MAXT; t++) {
+            if ((unsigned)(k + 1) - (qx[t] & 0xfffu) <= ((qx[t] >> 12) & 0xfffu)) {
+                const double lam = lam_b[(int)(qy[t] + (unsigned)(k + 1) * ((qx[t] >> 24) & 0x7fu))];
+                const double lb = fma(qn[t], zi - qb[t], lam);                         // lambda - mu c
+                if ((qx[t] >> 31) || lb <= 0.0) { g += (qn[t] < 0.0) ? -lb : lb; h += fabs(qn[t]); }   // g -= sign lb ; h += mu
+            }
+        }
+    };
+    const int total = P.B * N;
+    for (int bk = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 4); bk < total; bk += ngroups) {      // (whole 16-lane groups iterate together)
+        const int b = bk / N, k = bk - b * N;
+        const bool last = (k == N - 1);
+        const double* X = traj_X(P, P.cur[b], b) + (size_t)k * n;
+        const double* U = traj_U(P, P.cur[b], b) + (size_t)(last ? 0 : k) * P.m;      // (not read at the terminal knot)
+        const double* lam_b = P.lambda + (size_t)b * P.lambda_len;
+        const DevCost& c = P.costs[P.cost_index[k]];
+        double* rec = P.REC + (size_t)bk * TO_REC_LEN;
+        const double zi = (i < n) ? X[i] : (last ? 0.0 : U[i - n]);
+        double g, h;
+        entry(c, k, i, zi, lam_b, px, py, nms, bnd, g, h);
+        // the quaternion block: (g, h, q) of lanes 3..6 to every lane of the 16-lane group (lanes 3..5 use them)
+        double gq[4], hq[4], q[4];
 #pragma unroll
         for (int r = 0; r < 4; r++) {
-            qb += q[r] * gq[r]; ge += gc[r] * gq[r];
-            const double tt = gc[r] * hq[r];
-            hb0 += tt * G0[r]; hb1 += tt * G1[r]; hb2 += tt * G2[r];
+            gq[r] = __shfl_sync(0xffffffffu, g, qs + r, 16); hq[r] = __shfl_sync(0xffffffffu, h, qs + r, 16); q[r] = __shfl_sync(0xffffffffu, zi, qs + r, 16);
         }
-        const double hd = ((c == 0) ? hb0 : (c == 1) ? hb1 : hb2) - qb;
-        const int p = fraglayout::phys_x(3) + 2 * c;                       // attitude error e = 3 + c sits on p = 8, 10, 12
-        rec[TO_REC_G + p] = ge; rec[TO_REC_HD + p] = hd;
-        rec[TO_REC_HB + 4 * c + 0] = (c == 0) ? hd : hb0;
-        rec[TO_REC_HB + 4 * c + 1] = (c == 1) ? hd : hb1;
-        rec[TO_REC_HB + 4 * c + 2] = (c == 2) ? hd : hb2;
-        rec[TO_REC_HB + 4 * c + 3] = 0.0;
-    } else if (i != qs + 3) {                                              // lane 6 (q_z) has no coordinate of its own
-        const int e = (i < qs) ? i : i - 1;                               // error-state coordinate of full-state entry i (controls: 12 + a = i - 1)
-        const int p = (int)((0x6420FDB9E7CA8531ULL >> (4 * e)) & 15);
-        rec[TO_REC_G + p] = g; rec[TO_REC_HD + p] = h;
-        if (e == 7) { rec[TO_REC_HB + 12] = 0.0; rec[TO_REC_HB + 13] = 0.0; rec[TO_REC_HB + 14] = 0.0; rec[TO_REC_HB + 15] = h; }   // p = 14 is row 3 of Hb
-    }
-    if (i == 0) {                                                          // the 17th entry: u_3 -> coordinate 15
-        const double z3 = last ? 0.0 : U[3];
-        compact_entry_expansion(P, tab, k, n + 3, z3, lam_b, g, h);
-        rec[TO_REC_G + 6] = g; rec[TO_REC_HD + 6] = h;                     // phys_z(15) = 6
+        if (i >= qs && i < qs + 3) {
+            const int cc = i - qs;
+            // rows of G' = (L(q) H)': (-x,w,z,-y), (-y,-z,w,x), (-z,y,-x,w)   (kept in registers: no run-time indexed arrays)
+            const double G0[4] = {-q[1], q[0], q[3], -q[2]}, G1[4] = {-q[2], -q[3], q[0], q[1]}, G2[4] = {-q[3], q[2], -q[1], q[0]};
+            double gc[4];
+#pragma unroll
+            for (int r = 0; r < 4; r++) gc[r] = (cc == 0) ? G0[r] : (cc == 1) ? G1[r] : G2[r];
+            double qb = 0.0, ge = 0.0, hb0 = 0.0, hb1 = 0.0, hb2 = 0.0;
+#pragma unroll
+            for (int r = 0; r < 4; r++) {
+                qb += q[r] * gq[r]; ge += gc[r] * gq[r];
+                const double tt = gc[r] * hq[r];
+                hb0 += tt * G0[r]; hb1 += tt * G1[r]; hb2 += tt * G2[r];
+            }
+            const double hd = ((cc == 0) ? hb0 : (cc == 1) ? hb1 : hb2) - qb;
+            const int p = 8 + 2 * cc;                                                 // attitude error e = 3 + c sits on p = 8, 10, 12 (frag_layout.cuh)
+            rec[TO_REC_G + p] = ge; rec[TO_REC_HD + p] = hd;
+            rec[TO_REC_HB + 4 * cc + 0] = (cc == 0) ? hd : hb0;
+            rec[TO_REC_HB + 4 * cc + 1] = (cc == 1) ? hd : hb1;
+            rec[TO_REC_HB + 4 * cc + 2] = (cc == 2) ? hd : hb2;
+            rec[TO_REC_HB + 4 * cc + 3] = 0.0;
+        } else if (i != qs + 3) {                                                      // lane 6 (q_z) has no coordinate of its own
+            rec[TO_REC_G + pme] = g; rec[TO_REC_HD + pme] = h;
+            if (e == 7) { rec[TO_REC_HB + 12] = 0.0; rec[TO_REC_HB + 13] = 0.0; rec[TO_REC_HB + 14] = 0.0; rec[TO_REC_HB + 15] = h; }   // p = 14 is row 3 of Hb
+        }
+        if (i == 0) {                                                                  // the 17th entry: u_3 -> coordinate 15 (physical slot 6)
+            unsigned rx[TO_EXP_MAXT], ry[TO_EXP_MAXT]; double rn[TO_EXP_MAXT], rb[TO_EXP_MAXT];
+#pragma unroll
+            for (int t = 0; t < TO_EXP_MAXT; t++) { rx[t] = __ldg(&tab.pkx[t][n + 3]); ry[t] = __ldg(&tab.pky[t][n + 3]); rn[t] = __ldg(&tab.nms[t][n + 3]); rb[t] = __ldg(&tab.bound[t][n + 3]); }
+            entry(c, k, n + 3, last ? 0.0 : U[3], lam_b, rx, ry, rn, rb, g, h);
+            rec[TO_REC_G + 6] = g; rec[TO_REC_HD + 6] = h;
+        }
     }
 }
 cudaError_t launch_expansion_rec16(const DevProblem& P, cudaStream_t s) {
+    // persistent 16-lane groups (grid-stride over the knots): the per-lane term table stays in registers
     const long long total = (long long)P.B * P.N * 16;
-    k_expansion_rec16<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(P);
+    int dev = 0, sms = 148; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    long long blocks = (total + 255) / 256;
+    if (blocks > (long long)sms * 8) blocks = (long long)sms * 8;
+    k_expansion_rec16<<<(unsigned)blocks, 256, 0, s>>>(P);
     return cudaGetLastError();
 }
 

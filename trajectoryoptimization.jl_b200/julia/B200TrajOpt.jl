@@ -28,12 +28,17 @@ struct ToConstraintSpec
     inds::Ptr{Int32}; a::Ptr{Float64}; b::Ptr{Float64}; c::Ptr{Float64}; rad::Ptr{Float64}
     val::Float64
 end
+struct ToDynamicsSpec         # one recorded model of a hybrid problem (to_dynamics_spec; models given as programs: Python host API only for now)
+    n_in::Int32; m_in::Int32; n_out::Int32; discrete::Int32; prog_len::Int32; nconst::Int32
+    prog::Ptr{Int32}; consts::Ptr{Float64}
+end
 struct ToSpec
     model::Int32; n::Int32; m::Int32; N::Int32; B::Int32; device::Int32; nparams::Int32
     params::Ptr{Float64}; dt::Ptr{Float64}; t0::Float64
     ncost::Int32; costs::Ptr{ToCostSpec}; cost_index::Ptr{Int32}
     ncon::Int32; cons::Ptr{ToConstraintSpec}
     error_state::Int32       # 1: solver kernels on the Lie-group error state (RD.errstate_dim(model) != n), as Altro does
+    ndyn::Int32; dyn::Ptr{ToDynamicsSpec}; dyn_index::Ptr{Int32}; nx::Ptr{Int32}; nu::Ptr{Int32}    # TO_MODEL_EXPR only, else 0 / C_NULL
 end
 
 const TO_EDIM = -2
@@ -172,7 +177,7 @@ function BatchedProblem(prob::TO.Problem, mid::Integer, B::Integer; device::Inte
     root(costs); root(index); root(cons); root(params)
     spec = Ref(ToSpec(mid, n, m, N, B, device, length(params), isempty(params) ? C_NULL : pointer(params), pointer(dt),
                       TO.get_initial_time(prob), length(costs), pointer(costs), pointer(index), length(cons),
-                      isempty(cons) ? C_NULL : pointer(cons), error_state ? 1 : 0))
+                      isempty(cons) ? C_NULL : pointer(cons), error_state ? 1 : 0, 0, C_NULL, C_NULL, C_NULL, C_NULL))
     h = Ref{Ptr{Cvoid}}(C_NULL)
     rc = GC.@preserve keep ccall((:to_create, libb200), Cint, (Ref{ToSpec}, Ref{Ptr{Cvoid}}), spec, h)
     check(C_NULL, rc)

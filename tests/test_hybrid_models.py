@@ -146,7 +146,7 @@ def test_gpu_hybrid_problem_matches_the_oracle():
     # the library's own dimension check (what a C caller sees)
     model1, jumpmap, model2, models = hybrid_models()
     bad = TO.Problem.__new__(TO.Problem)
-    import trajopt_b200._capi as K
+    K = TO.capi
     spec = gp.spec
     nx_bad = list(spec.nx); nx_bad[6] = 4
     s2 = K.Spec(K.MODEL_EXPR, 4, 2, 11, 1, np.full(10, 0.2), spec.costs, spec.cost_index, spec.cons, dyn=spec.dyn, dyn_index=spec.dyn_index, nx=nx_bad, nu=spec.nu)

@@ -48,6 +48,7 @@ struct to_handle {
     double* d_merit2 = nullptr;   // {sum J, max viol}
     int* d_work = nullptr;
     ExpTab* d_exptab = nullptr;   // (frag) AL rows per z entry, rebuilt with the constraint tables / penalties
+    double* d_fragpool = nullptr; // gains of its speculative regularisation candidates
     int* d_fragq = nullptr;       // work queue of the register-resident Riccati kernel (riccati_frag.cu)
     int* d_err = nullptr;
     Scratch scratch;
@@ -537,7 +538,7 @@ int to_create(const to_spec* s, to_handle** out) {
     ALLOC(P.bp_status, B); ALLOC(P.ls_iters, B); ALLOC(P.accepted, B); ALLOC(P.acc1, B);
     ALLOC(h->d_stageX, P.strideX); ALLOC(h->d_stageU, P.strideU); ALLOC(h->d_viol, B); ALLOC(h->d_merit2, 2);
     ALLOC(h->d_work, 1); ALLOC(h->d_err, 1);
-    if (P.frag) { ALLOC(h->d_fragq, frag_queue_ints(B)); ALLOC(h->d_exptab, 1); }
+    if (P.frag) { ALLOC(h->d_fragq, frag_queue_ints(B)); ALLOC(h->d_fragpool, frag_pool_doubles(B, N)); ALLOC(h->d_exptab, 1); }
 #undef ALLOC
     if (rc) return bail(rc);
     P.exptab = h->d_exptab;
@@ -963,7 +964,7 @@ static int do_backward(to_handle* h, bool costexp_done = false) {
             h->launches++; h->phase_launches[TO_PHASE_COSTEXP]++;
         }
         PhaseScope ps(h, TO_PHASE_BACKWARD);
-        CU(h, launch_backward_frag(h->P, h->d_fragq, h->stream));
+        CU(h, launch_backward_frag(h->P, h->d_fragq, h->d_fragpool, h->stream));
     } else if (h->P.dense_riccati) {
         PhaseScope ps(h, TO_PHASE_BACKWARD);
         if (h->P.frag) { CU(h, launch_export_abe(h->P, h->stream)); h->launches++; }     // the shared-memory kernels read P.ABe

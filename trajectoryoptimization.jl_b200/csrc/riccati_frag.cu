@@ -39,6 +39,12 @@
 #ifndef TO_FRAG_WARPS
 #define TO_FRAG_WARPS 4
 #endif
+// Speculation rounds of the regularisation ladder: candidate c belongs to the round [first, next) with first = the largest boundary <= c.
+// 0: {1} {2,3} {4..7} {8..15}    1: {1} {2..15}    2: {1..3} {4..15}    3: {1} {2..7} {8..15}    4: {1..7} {8..15}    5: {1..15}
+// Measured on the BASELINE inputs (r02l): 0: 0.594 ms, 1: 0.562, 2: 0.539, 3: 0.574
+#ifndef TO_FRAG_ROUNDS
+#define TO_FRAG_ROUNDS 2
+#endif
 #ifndef TO_FRAG_MINB
 #define TO_FRAG_MINB 7
 #endif
@@ -190,7 +196,7 @@ __device__ __forceinline__ int minv_slot(int i, int j) {   // slot of Minv[i][j]
 }
 
 template <int STAGES, int WARPS, int MINB>
-__global__ void __launch_bounds__(32 * WARPS, MINB) k_riccati_frag(const DevProblem P, int* __restrict__ Qd) {
+__global__ void __launch_bounds__(32 * WARPS, MINB) k_riccati_frag(const DevProblem P, int* __restrict__ Qd, double* __restrict__ pool, int nslots) {
     using SM = FragSmem<STAGES, WARPS>;
     extern __shared__ __align__(128) unsigned char frag_smem_raw[];
     SM& sm = *reinterpret_cast<SM*>(frag_smem_raw);
@@ -224,14 +230,18 @@ __global__ void __launch_bounds__(32 * WARPS, MINB) k_riccati_frag(const DevProb
     //   Qd[0] head   next work index: indices < B are the first sweeps (instance = index), index B + q is slot q of the item list
     //   Qd[1] tail   item slots handed out          Qd[2] nfinal  instances finalised          Qd[3] error flag (spin limit)
     //   cnt[B]   candidates of the instance's current round still running     items[QCAP]  instance * 16 + candidate, -1 = not yet written
-    //   best[B]  lowest successful candidate of the round (0x7f7f7f7f = none)
+    //   best[B]  lowest successful candidate of the round: candidate << 16 | gain-pool slot (0x7f7f7f7f = none)
+    //   Qd[4] pool slots handed out.  A candidate that is not the lowest of its round writes its gains to a slot of `pool` (if one is left);
+    //   when it wins the round they are copied into place instead of being recomputed by one more sweep.
     // Regularisation ladder (Altro regularization_update!(:increase) after a failed sweep, restart from the terminal knot): the sequence
     // rho_1, rho_2, ... an instance will try is a function of (rho_0, drho_0) alone, so after a failed first sweep the candidates are
-    // evaluated SPECULATIVELY IN PARALLEL by whichever warps are idle, in rounds {1}, {2,3}, {4..7}, {8..15}; the result is the lowest
-    // successful candidate = exactly what the sequential loop returns (it stops at its first success), in <= 5 sweep times instead of <= 14.
+    // evaluated SPECULATIVELY IN PARALLEL by whichever warps are idle, in rounds (TO_FRAG_ROUNDS above); the result is the lowest
+    // successful candidate = exactly what the sequential loop returns (it stops at its first success), in <= 3 sweep times instead of <= 14.
     const int QCAP = 16 * P.B + 8192;
     int* const q_head = Qd; int* const q_tail = Qd + 1; int* const q_nfinal = Qd + 2; int* const q_err = Qd + 3;
-    int* const q_cnt = Qd + 4; int* const q_items = q_cnt + P.B; int* const q_best = q_items + QCAP;
+    int* const q_nslot = Qd + 4;
+    int* const q_cnt = Qd + 8; int* const q_items = q_cnt + P.B; int* const q_best = q_items + QCAP;
+    const size_t slot_stride = (size_t)(P.N - 1) * 52 + 2;       // K (48 per knot), d (4 per knot), dV (2)
 
     for (;;) {
         int idx = 0;
@@ -258,8 +268,9 @@ __global__ void __launch_bounds__(32 * WARPS, MINB) k_riccati_frag(const DevProb
             b = item >> 4; cand = item & 15;
         }
         const double* recg = P.REC + (size_t)b * N * TO_REC_LEN;
-        double* Kg = P.K + (size_t)b * (N - 1) * 48;
-        double* dg = P.d + (size_t)b * (N - 1) * 4;
+        double* const Kg = P.K + (size_t)b * (N - 1) * 48;
+        double* const dg = P.d + (size_t)b * (N - 1) * 4;
+        double* Kdst = Kg; double* ddst = dg;             // where a storing sweep puts its gains (the instance's, or a pool slot)
         const double rho0 = P.rho[b], drho0 = P.drho[b];
 
         auto issue = [&](int st, int k) {
@@ -384,9 +395,9 @@ __global__ void __launch_bounds__(32 * WARPS, MINB) k_riccati_frag(const DevProb
                 dmma(k1, w1, Q[1][0][0], bfrag);      //                K[fc][p = 8 + fr], W[fc][p = 8 + fr]
                 acc1 = fma(k0, af0, acc1); acc2 = fma(k0, k0, acc2);
                 if (store) {
-                    if (eoff0 >= 0) Kg[(size_t)k * 48 + eoff0] = k0;
-                    Kg[(size_t)k * 48 + eoff1] = k1;
-                    if (row0) dg[(size_t)k * 4 + fc] = k0;
+                    if (eoff0 >= 0) Kdst[(size_t)k * 48 + eoff0] = k0;
+                    Kdst[(size_t)k * 48 + eoff1] = k1;
+                    if (row0) ddst[(size_t)k * 4 + fc] = k0;
                 }
                 // row 0 <- Qz (the product below leaves s = Qx + K'w_d there), column 0 <- Qz (... leaves s = Qx + W'd there: K^[a][0] = d[a])
                 if (fc == 0) { Q[0][0][0] = qzc0; Q[1][0][0] = qzc1; }
@@ -410,7 +421,7 @@ __global__ void __launch_bounds__(32 * WARPS, MINB) k_riccati_frag(const DevProb
                 }
                 // the record and the Minv slots have been consumed by every lane: refill the ring slot
                 __syncwarp();
-                if (best_seen < cand) { ok = false; aborted = true; }      // a lower candidate of this round already succeeded: this sweep is moot
+                if ((best_seen >> 16) < cand) { ok = false; aborted = true; }      // a lower candidate of this round already succeeded: this sweep is moot
                 if (aborted) { k--; break; }                                 // (this knot's slot was consumed: same drain as a failure one knot later)
                 if (k - STAGES >= 0) issue(stage, k - STAGES);
                 stage = (stage + 1 == STAGES) ? 0 : stage + 1;
@@ -429,11 +440,11 @@ __global__ void __launch_bounds__(32 * WARPS, MINB) k_riccati_frag(const DevProb
             return ok;
         };
         // expected decrease of the sweep this warp just completed (the accumulators live in its registers)
-        auto write_dV = [&](double rho) {
+        auto write_dV = [&](double rho, double* dst) {
             acc1 += __shfl_xor_sync(0xffffffffu, acc1, 1); acc1 += __shfl_xor_sync(0xffffffffu, acc1, 2);
             acc2 += __shfl_xor_sync(0xffffffffu, acc2, 1); acc2 += __shfl_xor_sync(0xffffffffu, acc2, 2);
             // 1/2 d'Quu d = -1/2 (d'Qu + rho d'd)   since (Quu + rho I) d = -Qu
-            if (lane == 0) { P.dV[2 * b] = acc1; P.dV[2 * b + 1] = -0.5 * fma(rho, acc2, acc1); }
+            if (lane == 0) { dst[0] = acc1; dst[1] = -0.5 * fma(rho, acc2, acc1); }
         };
         auto finalise = [&](double rho, double drho, int status) {
             if (status >= 0) reg_decrease(P.opt, rho, drho);
@@ -458,47 +469,101 @@ __global__ void __launch_bounds__(32 * WARPS, MINB) k_riccati_frag(const DevProb
 
         double rho, drho;
         const int over = ladder(cand, rho, drho);
-        const bool first_of_round = (cand & (cand - 1)) == 0;            // 0, 1, 2, 4, 8: stores its gains speculatively
+        auto round_first = [](int c) {
+#if TO_FRAG_ROUNDS == 1
+            return c >= 2 ? 2 : 1;
+#elif TO_FRAG_ROUNDS == 2
+            return c >= 4 ? 4 : 1;
+#elif TO_FRAG_ROUNDS == 3
+            return c >= 8 ? 8 : (c >= 2 ? 2 : 1);
+#elif TO_FRAG_ROUNDS == 4
+            return c >= 8 ? 8 : 1;
+#elif TO_FRAG_ROUNDS == 5
+            return 1;
+#else
+            int lo = 1; while (2 * lo <= c) lo *= 2; return lo;
+#endif
+        };
+        auto round_next = [](int first) {                                  // first candidate of the following round (16 = none)
+#if TO_FRAG_ROUNDS == 1
+            return first == 1 ? 2 : 16;
+#elif TO_FRAG_ROUNDS == 2
+            return first == 1 ? 4 : 16;
+#elif TO_FRAG_ROUNDS == 3
+            return first == 1 ? 2 : (first == 2 ? 8 : 16);
+#elif TO_FRAG_ROUNDS == 4
+            return first == 1 ? 8 : 16;
+#elif TO_FRAG_ROUNDS == 5
+            return 16;
+#else
+            return 2 * first;
+#endif
+        };
+        const bool first_of_round = cand == 0 || cand == round_first(cand);   // the lowest candidate of a round stores its gains speculatively
         bool ok = false;
-        if (cand == 0 || !over) ok = sweep(rho, first_of_round, !first_of_round);
-        // the storing candidate is the lowest of its round: if it succeeds it IS the winner, its gains and dV are final
-        if (ok && first_of_round) write_dV(rho);
+        int myslot = 0xFFFF;
+        double* dVdst = P.dV + 2 * (size_t)b;
+        bool store = first_of_round;
+        if (!first_of_round && !over) {        // a speculative candidate: gains into a pool slot, copied into place if it wins its round
+            int sl = 0;
+            if (lane == 0) sl = atomicAdd(q_nslot, 1);
+            sl = __shfl_sync(0xffffffffu, sl, 0);
+            if (sl < nslots && sl < 0xFFFF) {
+                myslot = sl; store = true;
+                Kdst = pool + (size_t)sl * slot_stride; ddst = Kdst + (size_t)(N - 1) * 48; dVdst = Kdst + (size_t)(N - 1) * 52;
+            }
+        }
+        if (cand == 0 || !over) ok = sweep(rho, store, !first_of_round);
+        // the lowest candidate of a round stores in place: if it succeeds it IS the winner, its gains and dV are final
+        if (ok && store) write_dV(rho, dVdst);
+        if (myslot != 0xFFFF) { __threadfence(); __syncwarp(); }      // every lane's pool stores precede lane 0's atomicMin below
+        Kdst = Kg; ddst = dg;
         if (cand == 0) {
             if (ok) finalise(rho, drho, 0);
-            else start_round(1, 1);
+            else start_round(1, round_next(1) - 1);
             continue;
         }
         // a candidate of round [lo, 2 lo): record, and let the last one to finish decide
-        int lo = 1; while (2 * lo <= cand) lo *= 2;
+        const int lo = round_first(cand);
         int last = 0;
         if (lane == 0) {
-            if (ok) atomicMin(q_best + b, cand);
+            if (ok) atomicMin(q_best + b, (cand << 16) | myslot);
             __threadfence();
             last = (atomicSub(q_cnt + b, 1) == 1) ? 1 : 0;
         }
         last = __shfl_sync(0xffffffffu, last, 0);
         if (!last) continue;
         int best = 0;
-        if (lane == 0) best = atomicAdd(q_best + b, 0);
+        if (lane == 0) { best = atomicAdd(q_best + b, 0); __threadfence(); }
         best = __shfl_sync(0xffffffffu, best, 0);
+        const int bslot = best & 0xFFFF;
+        best >>= 16;
         if (best < 16) {
             ladder(best, rho, drho);
-            // gains and dV of the round's storing candidate (lo) are in place; any other winner runs once more, storing
-            if (best != lo) { sweep(rho, true, false); write_dV(rho); }
+            // gains and dV of the round's lowest candidate (lo) are in place; another winner's are in its pool slot (written before its
+            // atomicMin / fence, read here after ours, past L1) -- or, without a slot, recomputed by one more sweep
+            if (best != lo) {
+                if (bslot != 0xFFFF) {
+                    const double* src = pool + (size_t)bslot * slot_stride;
+                    for (int i = lane; i < (N - 1) * 48; i += 32) Kg[i] = __ldcg(src + i);
+                    for (int i = lane; i < (N - 1) * 4; i += 32) dg[i] = __ldcg(src + (size_t)(N - 1) * 48 + i);
+                    if (lane < 2) P.dV[2 * (size_t)b + lane] = __ldcg(src + (size_t)(N - 1) * 52 + lane);
+                } else { sweep(rho, true, false); write_dV(rho, P.dV + 2 * (size_t)b); }
+            }
             finalise(rho, drho, best);
             continue;
         }
         // nobody succeeded: the sequential loop gives up at the first rho beyond bp_reg_max, else the next round
-        const int hi = 2 * lo - 1;
+        const int hi = round_next(lo) - 1;
         const int ov = ladder(hi, rho, drho);
         if (ov) { ladder(ov, rho, drho); finalise(rho, drho, -1); continue; }
-        if (hi < 15) { start_round(2 * lo, 2 * lo); continue; }
+        if (hi < 15) { start_round(hi + 1, round_next(hi + 1) - (hi + 1)); continue; }
         // ladder longer than 15 steps (a huge bp_reg_max): finish sequentially in this warp
         int status = -1;
         for (int j = 16; ; j++) {
             reg_increase(P.opt, rho, drho);
             if (rho > P.opt.bp_reg_max) break;
-            if (sweep(rho, true, false)) { status = j; write_dV(rho); break; }
+            if (sweep(rho, true, false)) { status = j; write_dV(rho, P.dV + 2 * (size_t)b); break; }
         }
         finalise(rho, drho, status);
     }
@@ -515,9 +580,11 @@ cudaError_t launch_export_abe(const DevProblem& P, cudaStream_t s) {
     return cudaGetLastError();
 }
 
-size_t frag_queue_ints(int B) { return 4 + (size_t)B + (16 * (size_t)B + 8192) + (size_t)B; }
+size_t frag_queue_ints(int B) { return 8 + (size_t)B + (16 * (size_t)B + 8192) + (size_t)B; }
+int frag_pool_slots(int B) { return B < 4096 ? B : 4096; }
+size_t frag_pool_doubles(int B, int N) { return (size_t)frag_pool_slots(B) * ((size_t)(N - 1) * 52 + 2); }
 
-cudaError_t launch_backward_frag(const DevProblem& P, int* queue, cudaStream_t s) {
+cudaError_t launch_backward_frag(const DevProblem& P, int* queue, double* pool, cudaStream_t s) {
     constexpr int STAGES = TO_FRAG_STAGES, WARPS = TO_FRAG_WARPS, MINB = TO_FRAG_MINB;
     using SM = FragSmem<STAGES, WARPS>;
     auto kern = k_riccati_frag<STAGES, WARPS, MINB>;
@@ -535,15 +602,15 @@ cudaError_t launch_backward_frag(const DevProblem& P, int* queue, cudaStream_t s
         if (e != cudaSuccess) return e;
         ctas_per_sm[dev] = c < 1 ? 1 : c;
     }
-    // queue layout (k_riccati_frag): head, tail, nfinal, error | cnt[B] = 0 | items[16 B + 8192] = -1 | best[B] = 0x7f7f7f7f
+    // queue layout (k_riccati_frag): head, tail, nfinal, error, pool slots, 3 x pad | cnt[B] = 0 | items[16 B + 8192] = -1 | best[B] = 0x7f7f7f7f
     const size_t qcap = 16 * (size_t)P.B + 8192;
-    e = cudaMemsetAsync(queue, 0, sizeof(int) * (4 + (size_t)P.B), s);
-    if (e == cudaSuccess) e = cudaMemsetAsync(queue + 4 + P.B, 0xFF, sizeof(int) * qcap, s);
-    if (e == cudaSuccess) e = cudaMemsetAsync(queue + 4 + P.B + qcap, 0x7F, sizeof(int) * (size_t)P.B, s);
+    e = cudaMemsetAsync(queue, 0, sizeof(int) * (8 + (size_t)P.B), s);
+    if (e == cudaSuccess) e = cudaMemsetAsync(queue + 8 + P.B, 0xFF, sizeof(int) * qcap, s);
+    if (e == cudaSuccess) e = cudaMemsetAsync(queue + 8 + P.B + qcap, 0x7F, sizeof(int) * (size_t)P.B, s);
     if (e != cudaSuccess) return e;
     int grid = num_sms[dev] * ctas_per_sm[dev];       // persistent: warps pull work from the queue (all CTAs are co-resident: the
     const int need = (P.B + WARPS - 1) / WARPS;       // waiting warps of the speculative ladder cannot starve the running ones)
     if (grid > need) grid = need;
-    kern<<<grid, 32 * WARPS, smem, s>>>(P, queue);
+    kern<<<grid, 32 * WARPS, smem, s>>>(P, queue, pool, pool ? frag_pool_slots(P.B) : 0);
     return cudaGetLastError();
 }

@@ -246,7 +246,13 @@ cudaError_t launch_trivial_columns(const DevProblem& P, cudaStream_t s) {
 // G'g, G' diag(h) G - (q'g_q) I3 (Altro error_expansion!; lie.cu k_expansion_compact is the one-thread-per-knot version of the same numbers).
 // A light kernel (every load independent, ~40 registers) that runs at full occupancy; fused into the FP64-bound k_expand_lie it doubled that
 // kernel's time (profiles/r02_notes.md).
-__global__ void __launch_bounds__(256) k_expansion_rec16(const DevProblem P) {
+#ifndef TO_CEXP_ITERS
+#define TO_CEXP_ITERS 4          // knots per 16-lane group (the grid shrinks accordingly)
+#endif
+#ifndef TO_CEXP_MINB
+#define TO_CEXP_MINB 3
+#endif
+__global__ void __launch_bounds__(256, TO_CEXP_MINB) k_expansion_rec16(const DevProblem P) {
     constexpr int qs = 3;
     const int i = threadIdx.x & 15;                                                   // full-state entry of this lane
     const int n = P.n, N = P.N;
@@ -326,11 +332,11 @@ __global__ void __launch_bounds__(256) k_expansion_rec16(const DevProblem P) {
     }
 }
 cudaError_t launch_expansion_rec16(const DevProblem& P, cudaStream_t s) {
-    // persistent 16-lane groups (grid-stride over the knots): the per-lane term table stays in registers
+    // 16-lane groups, a few knots each (grid-stride): the per-lane term table stays in registers
     const long long total = (long long)P.B * P.N * 16;
     int dev = 0, sms = 148; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    long long blocks = (total + 255) / 256;
-    if (blocks > (long long)sms * 8) blocks = (long long)sms * 8;
+    long long blocks = ((total + 255) / 256 + TO_CEXP_ITERS - 1) / TO_CEXP_ITERS;
+    if (blocks < sms) blocks = sms;
     k_expansion_rec16<<<(unsigned)blocks, 256, 0, s>>>(P);
     return cudaGetLastError();
 }

@@ -194,6 +194,7 @@ def main():
     ap.add_argument("--merit-every", type=int, default=5, help="N > 1: iterations between two {sum merit, max violation} collectives (a solver's convergence report)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-depth", type=int, default=2, help="problem handles in flight in the end-to-end measurement (1 = strictly serial, 2 = double-buffered)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
@@ -298,7 +299,7 @@ def main():
         K.check(lib, h, lib.to_ilqr_step(h, 1))
     lib.to_get_phase_times(h, pms, pl, 1)
     lib.to_set_phase_timing(h, 0)
-    phase = {name: (pms[i] / max(1, pl[i])) for name, i in (("expand", K.PHASE_EXPAND), ("cost_expansion", K.PHASE_COSTEXP), ("backward", K.PHASE_BACKWARD), ("forward", K.PHASE_FORWARD), ("ladder", K.PHASE_LADDER))}
+    phase = {name: (pms[i] / max(1, pl[i])) for name, i in (("expand", K.PHASE_EXPAND), ("cost_expansion", K.PHASE_COSTEXP), ("backward", K.PHASE_BACKWARD), ("forward", K.PHASE_FORWARD), ("ladder", K.PHASE_LADDER), ("late_expansion", K.PHASE_LATE))}
     E, R, F = C.c_int64(), C.c_int64(), C.c_int64()
     lib.to_algorithmic_bytes(h, C.byref(E), C.byref(R), C.byref(F))
     peaks = {}
@@ -333,21 +334,40 @@ def main():
     # ---- end to end through the C ABI with host buffers -------------------------------------------------------------
     e2e = None
     if not args.no_e2e:
-        def e2e_step():
-            K.check(lib, h, lib.to_set_initial_state(h, dptr(x0_host)))     # H2D (pinned)
-            K.check(lib, h, lib.to_set_controls(h, dptr(U0_host)))          # H2D (pinned)
-            K.check(lib, h, lib.to_rollout(h))
-            K.check(lib, h, lib.to_ilqr_step(h, 1))
-            K.check(lib, h, lib.to_get_controls(h, dptr(U_out)))            # D2H (syncs)
-            K.check(lib, h, lib.to_merit(h, dptr(J_out)))                   # D2H (syncs)
-        for _ in range(args.warmup):
-            e2e_step()
+        # Two problem handles (each its own stream) work on alternate steps: while one batch iterates, the other batch's inputs are uploaded
+        # and the previous results downloaded -- the double buffering any caller streaming independent batches through the C ABI would use
+        # (setters are asynchronous, getters synchronise their own handle only).  Every step still uploads ITS inputs and downloads ITS
+        # results inside the timed region; --e2e-depth 1 gives the strictly serial upload -> iterate -> download of one handle.
+        depth = max(1, min(2, args.e2e_depth))
+        probs = [prob] + [build_problem(args.workload, B, N, device=local) for _ in range(depth - 1)]
+        outs = [(U_out, J_out)] + [(torch.empty_like(U0_host).pin_memory(), torch.empty(B, dtype=torch.float64).pin_memory()) for _ in range(depth - 1)]
+
+        def issue(i):
+            hh = probs[i % depth]._h
+            K.check(lib, hh, lib.to_set_initial_state(hh, dptr(x0_host)))     # H2D (pinned, asynchronous)
+            K.check(lib, hh, lib.to_set_controls(hh, dptr(U0_host)))          # H2D (pinned, asynchronous)
+            K.check(lib, hh, lib.to_rollout(hh))
+            K.check(lib, hh, lib.to_ilqr_step(hh, 1))
+
+        def collect(i):
+            hh = probs[i % depth]._h
+            K.check(lib, hh, lib.to_get_controls(hh, dptr(outs[i % depth][0])))   # D2H (synchronises this handle)
+            K.check(lib, hh, lib.to_merit(hh, dptr(outs[i % depth][1])))          # D2H
+
+        def e2e_run(k):
+            for i in range(k):
+                issue(i)
+                if i >= depth - 1:
+                    collect(i - (depth - 1))
+            for i in range(max(0, k - (depth - 1)), k):
+                collect(i)
+
+        e2e_run(args.warmup)
         barrier()
         t0 = time.perf_counter()
         g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         g0.record(stream)
-        for _ in range(args.steps):
-            e2e_step()
+        e2e_run(args.steps)
         g1.record(stream)
         barrier()
         wall_ms = (time.perf_counter() - t0) * 1e3
@@ -359,7 +379,11 @@ def main():
         e2e = {"value": B * world * args.steps / (ems * 1e-3), "unit": "instance-iterations/s",
                "h2d_bytes_per_step": int(x0_host.numel() * 8 + U0_host.numel() * 8), "d2h_bytes_per_step": int(U_out.numel() * 8 + J_out.numel() * 8),
                "ms_per_step": ems / args.steps,
-               "what": "per step: upload x0 + warm-start U (pinned host), rollout, 1 iLQR iteration, download U + merit J"}
+               "handles_in_flight": depth,
+               "what": "per step: upload x0 + warm-start U (pinned host), rollout, 1 iLQR iteration, download U + merit J"
+                       + ("; consecutive steps alternate between two problem handles so that one batch's copies overlap the other batch's iteration" if depth > 1 else "")}
+        for pb in probs[1:]:
+            pb.close()
 
     cpu = None
     if rank == 0 and not args.no_cpu_baseline:

@@ -264,7 +264,8 @@ int to_reduce_merit(to_handle* h);
 int to_reduce_merit_async(to_handle* h, void* consumer_stream);
 int to_merit_device_ptr(to_handle* h, void** ptr);
 /* per-phase device timing (CUDA events on the handle's stream) for the roofline report */
-enum to_phase { TO_PHASE_EXPAND = 0, TO_PHASE_BACKWARD = 1, TO_PHASE_FORWARD = 2, TO_PHASE_LADDER = 3, TO_PHASE_ACCEPT = 4, TO_PHASE_COSTEXP = 5 /* cost + AL expansion kernel of the record / materialised-expansion paths, when it is a launch of its own */, TO_PHASE_COUNT = 8 };
+enum to_phase { TO_PHASE_EXPAND = 0, TO_PHASE_BACKWARD = 1, TO_PHASE_FORWARD = 2, TO_PHASE_LADDER = 3, TO_PHASE_ACCEPT = 4, TO_PHASE_COSTEXP = 5 /* cost + AL expansion kernel of the record / materialised-expansion paths, when it is a launch of its own */,
+               TO_PHASE_LATE = 6 /* overlapped iterations: dynamics + cost expansion of the instances the late line-search trials moved (side stream) */, TO_PHASE_COUNT = 8 };
 int to_set_phase_timing(to_handle* h, int enable);
 int to_get_phase_times(to_handle* h, double* ms /*[TO_PHASE_COUNT] accumulated*/, int64_t* launches /*[TO_PHASE_COUNT]*/, int reset);
 int64_t to_launch_count(const to_handle* h);                                  /* kernels launched by this handle so far */

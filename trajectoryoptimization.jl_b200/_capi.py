@@ -27,7 +27,7 @@ COST_DIAGONAL, COST_QUADRATIC, COST_DIAGONAL_QUAT, COST_EXPR = 0, 1, 2, 3
 EXPR_MAXLEN, EXPR_MAXCONST = 128, 64
 CONE_ZERO, CONE_NEGATIVE_ORTHANT, CONE_SECOND_ORDER, CONE_IDENTITY, CONE_POSITIVE_ORTHANT = 0, 1, 2, 3, 4
 CON_GOAL, CON_BOUND, CON_LINEAR, CON_CIRCLE, CON_SPHERE, CON_NORM, CON_COLLISION, CON_QUATVEC, CON_EXPR = 0, 1, 2, 3, 4, 5, 6, 7, 8
-PHASE_EXPAND, PHASE_BACKWARD, PHASE_FORWARD, PHASE_LADDER, PHASE_ACCEPT, PHASE_COSTEXP, PHASE_COUNT = 0, 1, 2, 3, 4, 5, 8
+PHASE_EXPAND, PHASE_BACKWARD, PHASE_FORWARD, PHASE_LADDER, PHASE_ACCEPT, PHASE_COSTEXP, PHASE_LATE, PHASE_COUNT = 0, 1, 2, 3, 4, 5, 6, 8
 
 c_double_p = C.POINTER(C.c_double)
 c_int32_p = C.POINTER(C.c_int32)

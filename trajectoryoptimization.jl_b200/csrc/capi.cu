@@ -27,7 +27,9 @@ struct to_handle {
     int device = 0;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
+    cudaStream_t stream3 = nullptr;     // cost expansion of the instances accepted early, next to their dynamics expansion
     cudaStream_t stream2 = nullptr;     // high-priority side stream: late line-search trials overlap the next expansion
+    cudaEvent_t ev_c1 = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_merit = nullptr, ev_cons = nullptr;
     bool overlap = true;                // TO_NO_OVERLAP=1: keep every kernel on the main stream (profiling under ncu, A/B timing)
     bool side_pending = false;          // stream2 still holds the late line-search trials of the last iteration (ev_join follows them)
@@ -451,6 +453,8 @@ int to_create(const to_spec* s, to_handle** out) {
         if (const char* ev = getenv("TO_SIDE_PRIORITY")) { if (atoi(ev) == 0) hi = lo; }   // A/B switches (profiles/r01_notes.md)
         if (const char* ev = getenv("TO_NO_OVERLAP")) h->overlap = atoi(ev) == 0;
         if (cudaStreamCreateWithPriority(&h->stream2, cudaStreamNonBlocking, hi) != cudaSuccess ||
+            cudaStreamCreateWithPriority(&h->stream3, cudaStreamNonBlocking, getenv("TO_C1_LOW") ? lo : hi) != cudaSuccess ||
+            cudaEventCreateWithFlags(&h->ev_c1, cudaEventDisableTiming) != cudaSuccess ||
             cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
             cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming) != cudaSuccess ||
             cudaEventCreateWithFlags(&h->ev_merit, cudaEventDisableTiming) != cudaSuccess ||
@@ -591,6 +595,8 @@ int to_destroy(to_handle* h) {
     for (auto& e : h->pending) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
     for (auto e : h->pool) cudaEventDestroy(e);
     if (h->stream2) { cudaStreamSynchronize(h->stream2); cudaStreamDestroy(h->stream2); }
+    if (h->stream3) { cudaStreamSynchronize(h->stream3); cudaStreamDestroy(h->stream3); }
+    if (h->ev_c1) cudaEventDestroy(h->ev_c1);
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
     if (h->ev_join) cudaEventDestroy(h->ev_join);
     if (h->ev_merit) cudaEventDestroy(h->ev_merit);
@@ -959,7 +965,7 @@ static int do_backward(to_handle* h, bool costexp_done = false) {
     if (h->P.frag && h->P.opt.pad != 3 && h->P.opt.pad != 5) {
         if (!costexp_done) {   // cost + AL expansion of every record: always from the current trajectory, multipliers and penalties
             PhaseScope pe(h, TO_PHASE_COSTEXP);
-            if (rec_fused(h->P)) CU(h, launch_expansion_rec16(h->P, h->stream));      // 16 lanes per knot, host-built term table
+            if (rec_fused(h->P)) CU(h, launch_expansion_rec16(h->P, h->stream, 0));      // 16 lanes per knot, host-built term table
             else CU(h, launch_expansion_rec(h->P, h->stream));                          // more than 3 rows on one z entry: descriptor walk
             h->launches++; h->phase_launches[TO_PHASE_COSTEXP]++;
         }
@@ -1030,11 +1036,19 @@ int to_ilqr_step(to_handle* h, int32_t iters) {
         auto expand = [&](cudaStream_t st, int mode) { return h->P.lie ? launch_expand_lie(h->P, st, mode) : launch_expand(h->P, st, mode); };
         bool costexp_done = false;
         if (h->side_pending) {
-            CU(h, expand(h->stream2, 2)); h->launches++;
-            // the records' cost + AL expansion (latency-bound, light) rides on the side stream behind the late line-search trials, next to the
-            // FP64-bound dynamics expansion on the main stream; every trajectory is final there (F pass 1 precedes the fork, pass 2 this kernel)
-            if (h->P.frag && h->P.opt.pad != 3 && h->P.opt.pad != 5 && rec_fused(h->P)) {
-                { PhaseScope pe(h, TO_PHASE_COSTEXP, h->stream2); CU(h, launch_expansion_rec16(h->P, h->stream2)); }
+            const bool rec = h->P.frag && h->P.opt.pad != 3 && h->P.opt.pad != 5 && rec_fused(h->P);
+            {
+                PhaseScope pl(h, TO_PHASE_LATE, h->stream2);
+                CU(h, expand(h->stream2, 2)); h->launches++;
+                if (rec) { CU(h, launch_expansion_rec16(h->P, h->stream2, 2)); h->launches++; }
+            }
+            h->phase_launches[TO_PHASE_LATE]++;
+            // the records' cost + AL expansion (latency-bound, light) runs next to the FP64-bound dynamics expansion: for the late instances on the
+            // side stream behind their line-search trials (above), for the instances accepted in pass 1 (final since the fork) on a third stream
+            if (rec) {
+                CU(h, cudaStreamWaitEvent(h->stream3, h->ev_fork, 0));
+                { PhaseScope pe(h, TO_PHASE_COSTEXP, h->stream3); CU(h, launch_expansion_rec16(h->P, h->stream3, 1)); }
+                CU(h, cudaEventRecord(h->ev_c1, h->stream3));
                 h->launches++; h->phase_launches[TO_PHASE_COSTEXP]++;
                 costexp_done = true;
             }
@@ -1043,6 +1057,7 @@ int to_ilqr_step(to_handle* h, int32_t iters) {
         { PhaseScope ps(h, TO_PHASE_EXPAND); CU(h, expand(h->stream, h->side_pending ? 1 : 0)); }
         h->launches++; h->phase_launches[TO_PHASE_EXPAND]++;
         JOIN(h);
+        if (costexp_done) CU(h, cudaStreamWaitEvent(h->stream, h->ev_c1, 0));
         h->expanded = true;
         rc = do_backward(h, costexp_done); if (rc) return rc;
         { PhaseScope ps(h, TO_PHASE_FORWARD); CU(h, launch_forward(h->P, h->stream)); }

@@ -186,6 +186,8 @@ int to_constraint_info(const to_handle* h, int32_t con, int32_t* p, int32_t* sen
 int to_bounds(const to_handle* h, int32_t con, double* lower /*[p]*/, double* upper /*[p]*/); /* lower_bound/upper_bound src/abstract_constraint.jl:97-123 */
 
 /* ---- setters / getters (host arrays, instance-major) ------------------------------------------------ */
+/* The setters enqueue their host-to-device copy on the handle's stream and return: the host buffer must stay valid (and unchanged) until the next
+ * synchronising call on the handle -- to_synchronize or any getter.  Getters copy back and synchronise the handle's stream before returning. */
 int to_set_initial_state(to_handle* h, const double* x0 /*[B][n]*/);          /* set_initial_state! src/problem.jl:270 */
 int to_set_controls(to_handle* h, const double* U /*[B][N-1][m]*/);           /* initial_controls!  src/problem.jl:261 */
 int to_set_states(to_handle* h, const double* X /*[B][N][n]*/);               /* initial_states!    src/problem.jl:253 */

@@ -27,9 +27,7 @@ struct to_handle {
     int device = 0;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
-    cudaStream_t stream3 = nullptr;     // cost expansion of the instances accepted early, next to their dynamics expansion
     cudaStream_t stream2 = nullptr;     // high-priority side stream: late line-search trials overlap the next expansion
-    cudaEvent_t ev_c1 = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_merit = nullptr, ev_cons = nullptr;
     bool overlap = true;                // TO_NO_OVERLAP=1: keep every kernel on the main stream (profiling under ncu, A/B timing)
     bool side_pending = false;          // stream2 still holds the late line-search trials of the last iteration (ev_join follows them)
@@ -453,8 +451,6 @@ int to_create(const to_spec* s, to_handle** out) {
         if (const char* ev = getenv("TO_SIDE_PRIORITY")) { if (atoi(ev) == 0) hi = lo; }   // A/B switches (profiles/r01_notes.md)
         if (const char* ev = getenv("TO_NO_OVERLAP")) h->overlap = atoi(ev) == 0;
         if (cudaStreamCreateWithPriority(&h->stream2, cudaStreamNonBlocking, hi) != cudaSuccess ||
-            cudaStreamCreateWithPriority(&h->stream3, cudaStreamNonBlocking, getenv("TO_C1_LOW") ? lo : hi) != cudaSuccess ||
-            cudaEventCreateWithFlags(&h->ev_c1, cudaEventDisableTiming) != cudaSuccess ||
             cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
             cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming) != cudaSuccess ||
             cudaEventCreateWithFlags(&h->ev_merit, cudaEventDisableTiming) != cudaSuccess ||
@@ -540,6 +536,9 @@ int to_create(const to_spec* s, to_handle** out) {
     ALLOC(P.lambda, (size_t)B * std::max(1, P.lambda_len));
     ALLOC(P.rho, B); ALLOC(P.drho, B); ALLOC(P.dV, 2 * (size_t)B); ALLOC(P.J, B); ALLOC(P.Jc, B); ALLOC(P.alpha, B);
     ALLOC(P.bp_status, B); ALLOC(P.ls_iters, B); ALLOC(P.accepted, B); ALLOC(P.acc1, B);
+    // (the later line-search passes can walk a compact list of the late instances instead of scanning all: faster alone -- 0.22 vs 0.26 ms --
+    //  but slower next to the expansion kernels, where dense warps queue for the FP64 pipe: 0.53 vs 0.39 ms, r02r / r02s.  Off by default.)
+    if (getenv("TO_LATE_LIST")) { ALLOC(P.late_list, B); ALLOC(P.late_count, 1); }
     ALLOC(h->d_stageX, P.strideX); ALLOC(h->d_stageU, P.strideU); ALLOC(h->d_viol, B); ALLOC(h->d_merit2, 2);
     ALLOC(h->d_work, 1); ALLOC(h->d_err, 1);
     if (P.frag) { ALLOC(h->d_fragq, frag_queue_ints(B)); ALLOC(h->d_fragpool, frag_pool_doubles(B, N)); ALLOC(h->d_exptab, 1); }
@@ -595,8 +594,6 @@ int to_destroy(to_handle* h) {
     for (auto& e : h->pending) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
     for (auto e : h->pool) cudaEventDestroy(e);
     if (h->stream2) { cudaStreamSynchronize(h->stream2); cudaStreamDestroy(h->stream2); }
-    if (h->stream3) { cudaStreamSynchronize(h->stream3); cudaStreamDestroy(h->stream3); }
-    if (h->ev_c1) cudaEventDestroy(h->ev_c1);
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
     if (h->ev_join) cudaEventDestroy(h->ev_join);
     if (h->ev_merit) cudaEventDestroy(h->ev_merit);
@@ -1035,29 +1032,43 @@ int to_ilqr_step(to_handle* h, int32_t iters) {
         // (error state: only [A_e B_e] is needed by the solver kernels -- k_expand_lie; the full [A B] is produced by to_expand on request)
         auto expand = [&](cudaStream_t st, int mode) { return h->P.lie ? launch_expand_lie(h->P, st, mode) : launch_expand(h->P, st, mode); };
         bool costexp_done = false;
-        if (h->side_pending) {
-            const bool rec = h->P.frag && h->P.opt.pad != 3 && h->P.opt.pad != 5 && rec_fused(h->P);
-            {
-                PhaseScope pl(h, TO_PHASE_LATE, h->stream2);
-                CU(h, expand(h->stream2, 2)); h->launches++;
-                if (rec) { CU(h, launch_expansion_rec16(h->P, h->stream2, 2)); h->launches++; }
-            }
-            h->phase_launches[TO_PHASE_LATE]++;
-            // the records' cost + AL expansion (latency-bound, light) runs next to the FP64-bound dynamics expansion: for the late instances on the
-            // side stream behind their line-search trials (above), for the instances accepted in pass 1 (final since the fork) on a third stream
+        const bool rec = h->P.frag && h->P.opt.pad != 3 && h->P.opt.pad != 5 && rec_fused(h->P);
+        static const int order = getenv("TO_ITER_ORDER") ? atoi(getenv("TO_ITER_ORDER")) : 0;
+        if (h->side_pending && order == 1) {
+            // TO_ITER_ORDER=1 (A/B, r02s): only the latency-bound cost expansion of the instances accepted in pass 1 runs beside the late trials;
+            // the dynamics expansion of EVERY instance and the cost expansion of the late ones follow the join.  Measured slower than the
+            // default order below (1.585 vs 1.465 ms per step): the late trials are slowed as much by the cost expansion as by the dynamics one.
             if (rec) {
-                CU(h, cudaStreamWaitEvent(h->stream3, h->ev_fork, 0));
-                { PhaseScope pe(h, TO_PHASE_COSTEXP, h->stream3); CU(h, launch_expansion_rec16(h->P, h->stream3, 1)); }
-                CU(h, cudaEventRecord(h->ev_c1, h->stream3));
+                { PhaseScope pe(h, TO_PHASE_COSTEXP); CU(h, launch_expansion_rec16(h->P, h->stream, 1)); }
                 h->launches++; h->phase_launches[TO_PHASE_COSTEXP]++;
+            }
+            JOIN(h);
+            { PhaseScope ps(h, TO_PHASE_EXPAND); CU(h, expand(h->stream, 0)); }
+            h->launches++; h->phase_launches[TO_PHASE_EXPAND]++;
+            if (rec) {
+                { PhaseScope pl(h, TO_PHASE_LATE); CU(h, launch_expansion_rec16(h->P, h->stream, 2)); }
+                h->launches++; h->phase_launches[TO_PHASE_LATE]++;
                 costexp_done = true;
             }
-            CU(h, cudaEventRecord(h->ev_join, h->stream2));
+        } else {
+            if (h->side_pending) {
+                {
+                    PhaseScope pl(h, TO_PHASE_LATE, h->stream2);
+                    CU(h, expand(h->stream2, 2)); h->launches++;
+                    if (rec) { CU(h, launch_expansion_rec16(h->P, h->stream2, 2)); h->launches++; }
+                }
+                h->phase_launches[TO_PHASE_LATE]++;
+                if (rec) {
+                    { PhaseScope pe(h, TO_PHASE_COSTEXP); CU(h, launch_expansion_rec16(h->P, h->stream, 1)); }
+                    h->launches++; h->phase_launches[TO_PHASE_COSTEXP]++;
+                    costexp_done = true;
+                }
+                CU(h, cudaEventRecord(h->ev_join, h->stream2));
+            }
+            { PhaseScope ps(h, TO_PHASE_EXPAND); CU(h, expand(h->stream, h->side_pending ? 1 : 0)); }
+            h->launches++; h->phase_launches[TO_PHASE_EXPAND]++;
         }
-        { PhaseScope ps(h, TO_PHASE_EXPAND); CU(h, expand(h->stream, h->side_pending ? 1 : 0)); }
-        h->launches++; h->phase_launches[TO_PHASE_EXPAND]++;
         JOIN(h);
-        if (costexp_done) CU(h, cudaStreamWaitEvent(h->stream, h->ev_c1, 0));
         h->expanded = true;
         rc = do_backward(h, costexp_done); if (rc) return rc;
         { PhaseScope ps(h, TO_PHASE_FORWARD); CU(h, launch_forward(h->P, h->stream)); }

@@ -10,6 +10,7 @@
 //   lambda [B][lambda_len]    multipliers, per constraint: [knot in range][p]
 #pragma once
 #include <cuda_runtime.h>
+#include <cstdlib>
 #include <stdint.h>
 
 #define TO_MAXN 16
@@ -149,6 +150,8 @@ struct DevProblem {
     int* ls_iters;            // [B]
     int* accepted;            // [B]
     int* acc1;                // [B] accepted by the first line-search pass (read by the overlapped expansion)
+    int* late_list;           // [B] the instances pass 1 did not accept, in arrival order (written by pass 1, walked by the later passes)
+    int* late_count;          // [1] ... and how many; late_list == nullptr: the later passes scan every instance
     size_t strideX, strideU;  // elements between the two trajectory buffers
 };
 
@@ -161,6 +164,20 @@ __host__ __device__ inline double* traj_Uw(const DevProblem& P, int buf, int b) 
 // launchers cache their one-time configuration per device ordinal.
 #define TO_MAXDEV 64
 inline int current_device_slot() { int d = 0; cudaGetDevice(&d); return (d >= 0 && d < TO_MAXDEV) ? d : 0; }
+
+// The kernels of one iteration overlap on two streams (capi.cu to_ilqr_step).  Kernels that prefer different L1 / shared-memory splits cannot
+// share an SM until it drains -- so went the hypothesis; asking every kernel on the iteration path for one carve-out (TO_CARVEOUT = percent of
+// shared memory) measured WORSE than the driver's per-kernel default (-1, the default here): 1.513 / 1.553 ms per step at 100 / 50 against
+// 1.445 (profiles/r02_notes.md 6).  Kept as an A/B knob.
+template <class Kern>
+inline void prefer_common_carveout(Kern kern, bool (&done)[TO_MAXDEV]) {
+    const int dev = current_device_slot();
+    if (done[dev]) return;
+    done[dev] = true;
+    static int pct = -2;
+    if (pct == -2) { const char* e = getenv("TO_CARVEOUT"); pct = e ? atoi(e) : -1; }
+    if (pct >= 0) cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+}
 
 // Altro.jl regularization_update! (restated; see oracle/oracle.hpp reg_increase / reg_decrease)
 __host__ __device__ inline void reg_increase(const DevOptions& o, double& rho, double& drho) {

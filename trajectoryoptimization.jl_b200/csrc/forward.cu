@@ -102,6 +102,13 @@ __device__ __forceinline__ void cp_async16(double* smem_dst, const double* gsrc)
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+// Depth of the operand ring of the closed-loop rollout: knot k + FWD_STAGES - 1 is in flight while knot k is consumed.  One knot ahead
+// (2 stages) is enough: a knot takes ~2 us.  Deeper rings were tried against the slow-down of the late trials next to the expansion
+// kernels (r02t): 3 stages no change, 4 / 6 stages cost registers (128 -> 152) and shared memory and make pass 1 37 % slower.
+#ifndef TO_FWD_STAGES
+#define TO_FWD_STAGES 2
+#endif
+constexpr int FWD_STAGES = TO_FWD_STAGES;
 template <int NPEND> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(NPEND) : "memory"); }
 
 // shared-memory stage of one knot's operands for the IPB instances of a CTA.
@@ -177,17 +184,22 @@ __device__ __forceinline__ double rollout_fast(const DevProblem& P, const FwdTab
     ok = true; viol = 0.0;
 #pragma unroll
     for (int i = 0; i < n; i++) x[i] = P.x0[(size_t)b * n + i];
-    prefetch_knot<n, m, IPB, G, NE>(stage, g, l, 0, Kg, dg, X, U, lam_b, tab, N);
-    cp_async_commit();
+    constexpr int D = FWD_STAGES - 1;           // prefetch distance in knots
+#pragma unroll
+    for (int j = 0; j < D; j++) {
+        if (j < N) prefetch_knot<n, m, IPB, G, NE>(stage + j * S::DOUBLES, g, l, j, Kg, dg, X, U, lam_b, tab, N);
+        cp_async_commit();
+    }
+    int sb = 0, sp = D;                         // stage of knot k, stage knot k + D goes to (= the one knot k - 1 has just left)
     for (int k = 0; k < N; k++) {
         const bool last = (k == N - 1);
-        const int sb = k & 1;
-        __syncwarp(gmask);                      // every lane of the group is done reading stage sb^1 (knot k-1)
-        if (!last) prefetch_knot<n, m, IPB, G, NE>(stage + (sb ^ 1) * S::DOUBLES, g, l, k + 1, Kg, dg, X, U, lam_b, tab, N);
+        __syncwarp(gmask);                      // every lane of the group is done reading the stage of knot k-1
+        if (k + D < N) prefetch_knot<n, m, IPB, G, NE>(stage + sp * S::DOUBLES, g, l, k + D, Kg, dg, X, U, lam_b, tab, N);
         cp_async_commit();
-        cp_async_wait<1>();                     // this lane's copies for knot k have landed ...
+        cp_async_wait<D>();                     // this lane's copies for knot k have landed ...
         __syncwarp(gmask);                      // ... and so have the other lanes'
         const double* st = stage + sb * S::DOUBLES;
+        sb = (sb + 1 == FWD_STAGES) ? 0 : sb + 1; sp = (sp + 1 == FWD_STAGES) ? 0 : sp + 1;
         if (!last) {
 #pragma unroll
             for (int a = 0; a < m; a++) u[a] = fma(alpha, st[S::sidx(S::OFF_D + a, g)], st[S::sidx(S::OFF_U + a, g)]);
@@ -391,7 +403,10 @@ __global__ void __launch_bounds__(FWD_THREADS) k_linesearch(const DevProblem P, 
     FwdTab* tab = reinterpret_cast<FwdTab*>(fwd_smem);
     double* stage = reinterpret_cast<double*>(fwd_smem + sizeof(FwdTab));
     const int g = (threadIdx.x % LANES) / G, l = threadIdx.x % G;
-    const int b = blockIdx.x * IPB + g;
+    // pass 1 walks every instance; the later passes walk the list pass 1 left of the instances it did not accept, so that only CTAs with work
+    // stay resident next to the kernels of the main stream (a CTA with one late instance of four used to hold its registers for the whole pass)
+    int b = blockIdx.x * IPB + g;
+    if (!first_pass && P.late_list) b = (b < *P.late_count) ? P.late_list[b] : P.B;
     const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (g * G));
     const bool valid = b < P.B && threadIdx.x < LANES;
     const int status = valid ? P.bp_status[b] : -1;
@@ -420,7 +435,10 @@ __global__ void __launch_bounds__(FWD_THREADS) k_linesearch(const DevProblem P, 
             accepted = true;
         }
     }
-    if (l == 0 && first_pass) P.acc1[b] = accepted ? 1 : 0;
+    if (l == 0 && first_pass) {
+        P.acc1[b] = accepted ? 1 : 0;
+        if (!accepted && P.late_list) P.late_list[atomicAdd(P.late_count, 1)] = b;
+    }
     if (l == 0 && !accepted) {
         if (first_pass) P.accepted[b] = 0;
         if (status < 0) { P.alpha[b] = 0.0; P.ls_iters[b] = 0; }
@@ -440,7 +458,7 @@ cudaError_t launch_pass_l(const DevProblem& P, int trial0, int first_pass, int f
     constexpr int n = ModelDims<MODEL>::n, m = ModelDims<MODEL>::m, NE = LIE ? n - 1 : n;
     constexpr int IPB = LANES / G;
     const int blocks = (P.B + IPB - 1) / IPB;
-    const size_t smem = FAST ? sizeof(FwdTab) + (size_t)2 * Stage<n, m, IPB, NE>::DOUBLES * sizeof(double) : 0;
+    const size_t smem = FAST ? sizeof(FwdTab) + (size_t)FWD_STAGES * Stage<n, m, IPB, NE>::DOUBLES * sizeof(double) : 0;
     auto kern = k_linesearch<MODEL, G, FAST, LANES, LIE>;
     static bool configured[TO_MAXDEV] = {false};
     const int dev = current_device_slot();
@@ -449,6 +467,7 @@ cudaError_t launch_pass_l(const DevProblem& P, int trial0, int first_pass, int f
         if (e != cudaSuccess) return e;
     }
     configured[dev] = true;
+    { static bool done[TO_MAXDEV] = {false}; prefer_common_carveout(kern, done); }
     kern<<<blocks, FWD_THREADS, smem, s>>>(P, trial0, first_pass, final_pass);
     return cudaGetLastError();
 }
@@ -481,6 +500,7 @@ bool fast_path(const DevProblem& P) {
 cudaError_t launch_forward(const DevProblem& P, cudaStream_t s) {
     cudaError_t e = cudaErrorNotSupported;
     const int final_pass = P.opt.ls_iters < 4;
+    if (P.late_list) { e = cudaMemsetAsync(P.late_count, 0, sizeof(int), s); if (e != cudaSuccess) return e; e = cudaErrorNotSupported; }
     if (fast_path(P)) { TO_DISPATCH_MODEL(P.model, P.m, (e = launch_pass<MODEL, 4, true>(P, 0, 1, final_pass, s))); }
     else { TO_DISPATCH_MODEL(P.model, P.m, (e = launch_pass<MODEL, 4, false>(P, 0, 1, final_pass, s))); }
     return e;

@@ -581,6 +581,7 @@ __global__ void TO_RICCATI_BOUNDS(MINB) k_riccati(const DevProblem P, int* __res
 #pragma unroll
                             for (int ni = mi; ni < NT; ni++, t++) { q[t][0] = fma(a[mi], bb[ni].x, q[t][0]); q[t][1] = fma(a[mi], bb[ni].y, q[t][1]); }
                     }
+                    __syncwarp();     // every lane has read T: the Qz strip below overwrites it (racecheck flags the write-after-read without it)
                     // ---- + [lzz | lz] (lane-resident, fetched by shuffle) ; the u / Qz strip (columns >= n) goes to shared memory ----
                     {
                         double hrow[MQ], grow[MQ];

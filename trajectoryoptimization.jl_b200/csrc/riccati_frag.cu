@@ -611,6 +611,7 @@ cudaError_t launch_backward_frag(const DevProblem& P, int* queue, double* pool, 
     int grid = num_sms[dev] * ctas_per_sm[dev];       // persistent: warps pull work from the queue (all CTAs are co-resident: the
     const int need = (P.B + WARPS - 1) / WARPS;       // waiting warps of the speculative ladder cannot starve the running ones)
     if (grid > need) grid = need;
+    { static bool done[TO_MAXDEV] = {false}; prefer_common_carveout(kern, done); }
     kern<<<grid, 32 * WARPS, smem, s>>>(P, queue, pool, pool ? frag_pool_slots(P.B) : 0);
     return cudaGetLastError();
 }

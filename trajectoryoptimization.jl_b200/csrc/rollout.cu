@@ -155,8 +155,13 @@ __device__ __forceinline__ int lie_trivial(int s) { return (int)((0x876210ULL >>
 #ifndef TO_EXPAND_LIE_MINB
 #define TO_EXPAND_LIE_MINB 4      // CTAs per SM the register allocation aims at: 128 registers, 16 warps per SM (r02g: 0.29 vs 0.37 ms at 168 registers / 12 warps)
 #endif
+// CTA size: the kernel fills the register file (128 registers x 512 threads), so every CTA of another kernel that becomes resident next to it (the
+// late line-search trials on the side stream, 4096 registers each) evicts a whole CTA of this one: 64-thread CTAs lose 1/8 of an SM, not 1/4.
+#ifndef TO_EXPAND_LIE_THREADS
+#define TO_EXPAND_LIE_THREADS 64
+#endif
 template <int MODEL, bool FRAG>
-__global__ void __launch_bounds__(128, TO_EXPAND_LIE_MINB) k_expand_lie(const DevProblem P, int mode) {
+__global__ void __launch_bounds__(TO_EXPAND_LIE_THREADS, TO_EXPAND_LIE_MINB * 128 / TO_EXPAND_LIE_THREADS) k_expand_lie(const DevProblem P, int mode) {
     constexpr int n = ModelDims<MODEL>::n, m = ModelDims<MODEL>::m, ne = n - 1, nme = ne + m, qs = 3, NS = 10;
     using D = Dual<1>;
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -252,7 +257,10 @@ cudaError_t launch_trivial_columns(const DevProblem& P, cudaStream_t s) {
 #ifndef TO_CEXP_MINB
 #define TO_CEXP_MINB 4          // 64 registers: 32 warps per SM (r02m: 0.179 ms against 0.205 at 3)
 #endif
-__global__ void __launch_bounds__(256, TO_CEXP_MINB) k_expansion_rec16(const DevProblem P, int mode) {
+#ifndef TO_CEXP_THREADS
+#define TO_CEXP_THREADS 128
+#endif
+__global__ void __launch_bounds__(TO_CEXP_THREADS, TO_CEXP_MINB * 256 / TO_CEXP_THREADS) k_expansion_rec16(const DevProblem P, int mode) {
     constexpr int qs = 3;
     const int i = threadIdx.x & 15;                                                   // full-state entry of this lane
     const int n = P.n, N = P.N;
@@ -337,9 +345,11 @@ cudaError_t launch_expansion_rec16(const DevProblem& P, cudaStream_t s, int mode
     // 16-lane groups, a few knots each (grid-stride): the per-lane term table stays in registers
     const long long total = (long long)P.B * P.N * 16;
     int dev = 0, sms = 148; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    long long blocks = ((total + 255) / 256 + TO_CEXP_ITERS - 1) / TO_CEXP_ITERS;
+    constexpr int T = TO_CEXP_THREADS;
+    long long blocks = ((total + T - 1) / T + TO_CEXP_ITERS - 1) / TO_CEXP_ITERS;
     if (blocks < sms) blocks = sms;
-    k_expansion_rec16<<<(unsigned)blocks, 256, 0, s>>>(P, mode);
+    { static bool done[TO_MAXDEV] = {false}; prefer_common_carveout(k_expansion_rec16, done); }
+    k_expansion_rec16<<<(unsigned)blocks, T, 0, s>>>(P, mode);
     return cudaGetLastError();
 }
 
@@ -347,8 +357,10 @@ cudaError_t launch_expand_lie(const DevProblem& P, cudaStream_t s, int mode) {
     if (P.model != MODEL_QUADROTOR) return cudaErrorNotSupported;
     const long long total = (long long)P.B * (P.N - 1) * 10;      // 10 dual-number seeds per knot (k_expand_lie: seed pruning)
     static_assert(fraglayout::phys_z(0) == 1 && fraglayout::phys_z(5) == 12 && fraglayout::phys_z(11) == 15 && fraglayout::phys_z(12) == 0 && fraglayout::phys_z(15) == 6, "nibble table of k_expand_lie");
-    if (P.frag) k_expand_lie<MODEL_QUADROTOR, true><<<(unsigned)((total + 127) / 128), 128, 0, s>>>(P, mode);
-    else k_expand_lie<MODEL_QUADROTOR, false><<<(unsigned)((total + 127) / 128), 128, 0, s>>>(P, mode);
+    { static bool d1[TO_MAXDEV] = {false}, d2[TO_MAXDEV] = {false}; prefer_common_carveout(k_expand_lie<MODEL_QUADROTOR, true>, d1); prefer_common_carveout(k_expand_lie<MODEL_QUADROTOR, false>, d2); }
+    constexpr int T = TO_EXPAND_LIE_THREADS;
+    if (P.frag) k_expand_lie<MODEL_QUADROTOR, true><<<(unsigned)((total + T - 1) / T), T, 0, s>>>(P, mode);
+    else k_expand_lie<MODEL_QUADROTOR, false><<<(unsigned)((total + T - 1) / T), T, 0, s>>>(P, mode);
     return cudaGetLastError();
 }
 
@@ -363,6 +375,7 @@ static cudaError_t launch_expand_t(const DevProblem& P, cudaStream_t s, int mode
     constexpr int TPK = (SeedList<MODEL>::count + NP - 1) / NP;
     const long long total = (long long)P.B * (P.N - 1) * TPK;
     const int threads = 128;
+    { static bool done[TO_MAXDEV] = {false}; prefer_common_carveout(k_expand<MODEL, NP>, done); }
     k_expand<MODEL, NP><<<(unsigned)((total + threads - 1) / threads), threads, 0, s>>>(P, mode);
     return cudaGetLastError();
 }

@@ -260,6 +260,11 @@ def main():
     reset()
     for _ in range(args.warmup):
         step()
+    if world > 1:   # the first collective sets up NCCL's channels (tens of ms): it belongs to the warm-up whatever --merit-every is
+        K.check(lib, h, lib.to_reduce_merit_async(h, C.c_void_p(side.cuda_stream)))
+        with torch.cuda.stream(side):
+            TO.multi_gpu.all_reduce_merit(merit2, scratch=gather)
+        step_no[0] = 0
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.start(); time.sleep(0.3)

@@ -5,7 +5,7 @@ cd "$GRAFT_REPO_ROOT" || exit 1
 mkdir -p gpurun_out
 port=29611
 for n in $1; do
-  for mode in weak strong strong32k; do
+  for mode in ${MODES:-weak strong strong32k}; do
     extra="--scaling weak"
     [ $mode == strong ] && extra="--scaling strong"
     [ $mode == strong32k ] && extra="--scaling strong --batch 32768"

@@ -233,6 +233,25 @@ def test_fragment_riccati_kernel_regularisation_and_queue():
     g.close(); o.close()
 
 
+@pytest.mark.parametrize("B,N", [(1, 2), (3, 5), (5, 3), (33, 2), (2, 64)])
+def test_error_state_edge_sizes(B, N):
+    """the record / fragment path at the smallest and at odd sizes: one knot pair, fewer instances than a CTA has warps, a ring deeper than
+    the horizon, the 16-lane groups of the cost expansion ending inside a warp"""
+    g, o, t = triple(lambda cls: P.quadrotor(B=B, N=N, dt=0.05, error_state=True, cls=cls))
+    for p in (g, o, t):
+        TO.rollout(p); TO.expand(p)
+    close(TO.error_dynamics(g), TO.error_dynamics(o), KERNEL_RTOL, "[A_e B_e]")
+    assert np.array_equal(TO.backward(g), TO.backward(o)); TO.backward(t)
+    close(TO.gains(g)[0], TO.gains(o)[0], GAIN_TOL, "K"); close(TO.gains(g)[1], TO.gains(o)[1], GAIN_TOL, "d")
+    close(TO.solver_state(g)["dV"], TO.solver_state(o)["dV"], GAIN_TOL, "dV")
+    for p in (g, o, t):
+        TO.ilqr_step(p, 2); TO.al_update(p); TO.ilqr_step(p, 1)
+    check("X after 3 iterations", TO.states(g), TO.states(o), TO.states(t), 1e-9)
+    check("merit", TO.merit(g), TO.merit(o), TO.merit(t), 1e-9)
+    for p in (g, o, t):
+        p.close()
+
+
 def test_error_state_full_size_properties():
     """BASELINE-size batch on the error state: merit monotone, backward pass never fails, attitude stays on the unit sphere,
     instance 0..7 equal to an 8-instance problem with the same inputs (instances never interact)."""

@@ -48,6 +48,7 @@ struct to_handle {
     double* d_merit2 = nullptr;   // {sum J, max viol}
     int* d_work = nullptr;
     ExpTab* d_exptab = nullptr;   // (frag) AL rows per z entry, rebuilt with the constraint tables / penalties
+    int* d_fragerr = nullptr;     // sticky error word of that kernel (queue overflow / spin limit), read by to_synchronize
     double* d_fragpool = nullptr; // gains of its speculative regularisation candidates
     int* d_fragq = nullptr;       // work queue of the register-resident Riccati kernel (riccati_frag.cu)
     int* d_err = nullptr;
@@ -541,7 +542,7 @@ int to_create(const to_spec* s, to_handle** out) {
     if (getenv("TO_LATE_LIST")) { ALLOC(P.late_list, B); ALLOC(P.late_count, 1); }
     ALLOC(h->d_stageX, P.strideX); ALLOC(h->d_stageU, P.strideU); ALLOC(h->d_viol, B); ALLOC(h->d_merit2, 2);
     ALLOC(h->d_work, 1); ALLOC(h->d_err, 1);
-    if (P.frag) { ALLOC(h->d_fragq, frag_queue_ints(B)); ALLOC(h->d_fragpool, frag_pool_doubles(B, N)); ALLOC(h->d_exptab, 1); }
+    if (P.frag) { ALLOC(h->d_fragq, frag_queue_ints(B)); ALLOC(h->d_fragpool, frag_pool_doubles(B, N)); ALLOC(h->d_fragerr, 1); ALLOC(h->d_exptab, 1); }
 #undef ALLOC
     if (rc) return bail(rc);
     P.exptab = h->d_exptab;
@@ -573,6 +574,7 @@ int to_create(const to_spec* s, to_handle** out) {
     okc &= cudaMemsetAsync(P.ls_iters, 0, sizeof(int) * B, st) == cudaSuccess;
     okc &= cudaMemsetAsync(P.accepted, 0, sizeof(int) * B, st) == cudaSuccess;
     okc &= cudaMemsetAsync(P.acc1, 0, sizeof(int) * B, st) == cudaSuccess;
+    if (h->d_fragerr) okc &= cudaMemsetAsync(h->d_fragerr, 0, sizeof(int), st) == cudaSuccess;
     okc &= cudaMemsetAsync(h->d_err, 0, sizeof(int), st) == cudaSuccess;
     if (!okc) { h->err = std::string("device initialisation failed: ") + cudaGetErrorString(cudaGetLastError()); return bail(TO_ECUDA); }
     rc = upload_tables(h);
@@ -641,6 +643,11 @@ int to_synchronize(to_handle* h) {
     JOIN(h);
     if (!h) return TO_EINVAL;
     CU(h, cudaStreamSynchronize(h->stream));
+    if (h->d_fragerr) {     // the Riccati kernel's work queue never hangs the device: it gives up and says so here
+        int e = 0;
+        CU(h, cudaMemcpy(&e, h->d_fragerr, sizeof(int), cudaMemcpyDeviceToHost));
+        if (e) return fail(h, TO_ESTATE, e & 2 ? "backward pass: work queue overflow (results invalid)" : "backward pass: a warp waited for queued work beyond the spin limit (results invalid)");
+    }
     return TO_OK;
 }
 int to_dims(const to_handle* h, int32_t* n, int32_t* m, int32_t* N, int32_t* B) {
@@ -967,7 +974,7 @@ static int do_backward(to_handle* h, bool costexp_done = false) {
             h->launches++; h->phase_launches[TO_PHASE_COSTEXP]++;
         }
         PhaseScope ps(h, TO_PHASE_BACKWARD);
-        CU(h, launch_backward_frag(h->P, h->d_fragq, h->d_fragpool, h->stream));
+        CU(h, launch_backward_frag(h->P, h->d_fragq, h->d_fragpool, h->d_fragerr, h->stream));
     } else if (h->P.dense_riccati) {
         PhaseScope ps(h, TO_PHASE_BACKWARD);
         if (h->P.frag) { CU(h, launch_export_abe(h->P, h->stream)); h->launches++; }     // the shared-memory kernels read P.ABe

@@ -42,7 +42,7 @@ cudaError_t launch_trivial_columns(const DevProblem& P, cudaStream_t s);        
 cudaError_t launch_export_abe(const DevProblem& P, cudaStream_t s);                    // REC fragments -> ABe (col-major 12 x 16)
 size_t frag_queue_ints(int B);
 size_t frag_pool_doubles(int B, int N);                                                 // doubles of the speculative candidates' gain pool                                                         // ints of the kernel's work queue (allocated by the handle)
-cudaError_t launch_backward_frag(const DevProblem& P, int* queue, double* pool, cudaStream_t s);
+cudaError_t launch_backward_frag(const DevProblem& P, int* queue, double* pool, int* sticky_err, cudaStream_t s);
 // forward pass: closed-loop rollout + merit + line search                     (forward.cu)
 cudaError_t launch_forward(const DevProblem& P, cudaStream_t s);
 cudaError_t launch_ladder(const DevProblem& P, cudaStream_t s);

@@ -196,7 +196,7 @@ __device__ __forceinline__ int minv_slot(int i, int j) {   // slot of Minv[i][j]
 }
 
 template <int STAGES, int WARPS, int MINB>
-__global__ void __launch_bounds__(32 * WARPS, MINB) k_riccati_frag(const DevProblem P, int* __restrict__ Qd, double* __restrict__ pool, int nslots) {
+__global__ void __launch_bounds__(32 * WARPS, MINB) k_riccati_frag(const DevProblem P, int* __restrict__ Qd, double* __restrict__ pool, int nslots, int* __restrict__ sticky_err) {
     using SM = FragSmem<STAGES, WARPS>;
     extern __shared__ __align__(128) unsigned char frag_smem_raw[];
     SM& sm = *reinterpret_cast<SM*>(frag_smem_raw);
@@ -260,7 +260,7 @@ __global__ void __launch_bounds__(32 * WARPS, MINB) k_riccati_frag(const DevProb
                     if (ld_volatile_s32(q_nfinal) >= P.B) { item = -2; break; }      // every instance is finalised: nothing more will be queued
                     __nanosleep(ns);                                                  // back off: an idle warp must not take issue slots from the running ones
                     if (ns < 4096) ns *= 2;
-                    if (++spins > (1u << 18)) { atomicExch(q_err, 1); item = -2; break; }   // ~1 s: never hang the device
+                    if (++spins > (1u << 18)) { atomicExch(q_err, 1); atomicOr(sticky_err, 1); item = -2; break; }   // ~1 s: never hang the device
                 }
             }
             item = __shfl_sync(0xffffffffu, item, 0);
@@ -462,7 +462,7 @@ __global__ void __launch_bounds__(32 * WARPS, MINB) k_riccati_frag(const DevProb
                 __threadfence();
                 const int slot = atomicAdd(q_tail, n);
                 for (int i = 0; i < n; i++)
-                    if (slot + i < QCAP) atomicExch(q_items + slot + i, b * 16 + first + i); else atomicExch(q_err, 2);
+                    if (slot + i < QCAP) atomicExch(q_items + slot + i, b * 16 + first + i); else { atomicExch(q_err, 2); atomicOr(sticky_err, 2); }
             }
             __syncwarp();
         };
@@ -581,10 +581,16 @@ cudaError_t launch_export_abe(const DevProblem& P, cudaStream_t s) {
 }
 
 size_t frag_queue_ints(int B) { return 8 + (size_t)B + (16 * (size_t)B + 8192) + (size_t)B; }
-int frag_pool_slots(int B) { return B < 4096 ? B : 4096; }
-size_t frag_pool_doubles(int B, int N) { return (size_t)frag_pool_slots(B) * ((size_t)(N - 1) * 52 + 2); }
+// gain pool of the speculative candidates: one slot per instance up to 4096, and at most 1 GiB (a candidate without a slot is recomputed if it wins)
+int frag_pool_slots(int B, int N) {
+    const size_t slot = ((size_t)(N - 1) * 52 + 2) * sizeof(double);
+    size_t n = B < 4096 ? B : 4096;
+    if (n * slot > ((size_t)1 << 30)) n = ((size_t)1 << 30) / slot;
+    return (int)(n < 1 ? 1 : n);
+}
+size_t frag_pool_doubles(int B, int N) { return (size_t)frag_pool_slots(B, N) * ((size_t)(N - 1) * 52 + 2); }
 
-cudaError_t launch_backward_frag(const DevProblem& P, int* queue, double* pool, cudaStream_t s) {
+cudaError_t launch_backward_frag(const DevProblem& P, int* queue, double* pool, int* sticky_err, cudaStream_t s) {
     constexpr int STAGES = TO_FRAG_STAGES, WARPS = TO_FRAG_WARPS, MINB = TO_FRAG_MINB;
     using SM = FragSmem<STAGES, WARPS>;
     auto kern = k_riccati_frag<STAGES, WARPS, MINB>;
@@ -612,6 +618,6 @@ cudaError_t launch_backward_frag(const DevProblem& P, int* queue, double* pool, 
     const int need = (P.B + WARPS - 1) / WARPS;       // waiting warps of the speculative ladder cannot starve the running ones)
     if (grid > need) grid = need;
     { static bool done[TO_MAXDEV] = {false}; prefer_common_carveout(kern, done); }
-    kern<<<grid, 32 * WARPS, smem, s>>>(P, queue, pool, pool ? frag_pool_slots(P.B) : 0);
+    kern<<<grid, 32 * WARPS, smem, s>>>(P, queue, pool, pool ? frag_pool_slots(P.B, P.N) : 0, sticky_err);
     return cudaGetLastError();
 }

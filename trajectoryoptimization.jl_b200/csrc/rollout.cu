@@ -15,22 +15,39 @@
 #include "kernels.h"
 #include "models.cuh"
 
+// One thread integrates one instance; the warp writes its 32 states of a knot through a shared-memory transpose, so that the stores are runs of
+// n contiguous doubles per instance (full 32-byte sectors) instead of 32 scattered 8-byte words per instruction.
 template <int MODEL>
-__global__ void __launch_bounds__(64) k_rollout(const DevProblem P) {
+__global__ void __launch_bounds__(32) k_rollout(const DevProblem P) {
     constexpr int n = ModelDims<MODEL>::n, m = ModelDims<MODEL>::m;
-    const int b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= P.B) return;
-    double* X = traj_Xw(P, P.cur[b], b);
-    const double* U = traj_U(P, P.cur[b], b);
+    __shared__ double stage[32 * n];
+    __shared__ double* base[32];
+    const int lane = threadIdx.x;
+    const int b = blockIdx.x * 32 + lane;
+    const bool valid = b < P.B;
+    const int bc = valid ? b : P.B - 1;                     // (idle lanes of the last warp shadow a real instance and store nothing)
+    base[lane] = valid ? traj_Xw(P, P.cur[bc], bc) : nullptr;
+    const double* U = traj_U(P, P.cur[bc], bc);
     double x[n], u[m], xn[n];
 #pragma unroll
-    for (int i = 0; i < n; i++) { x[i] = P.x0[(size_t)b * n + i]; X[i] = x[i]; }
-    for (int k = 0; k < P.N - 1; k++) {
+    for (int i = 0; i < n; i++) x[i] = P.x0[(size_t)bc * n + i];
+    for (int k = 0; k < P.N; k++) {
+#pragma unroll
+        for (int i = 0; i < n; i++) stage[lane * n + i] = x[i];
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < n; j++) {
+            const int e = j * 32 + lane, ii = e / n, c = e - ii * n;
+            double* Xi = base[ii];
+            if (Xi) Xi[(size_t)k * n + c] = stage[e];
+        }
+        __syncwarp();
+        if (k == P.N - 1) break;
 #pragma unroll
         for (int i = 0; i < m; i++) u[i] = U[k * m + i];
         rk4_step<MODEL, double>(model_params<MODEL>(P, k), x, u, P.dt[k], xn);
 #pragma unroll
-        for (int i = 0; i < n; i++) { x[i] = xn[i]; X[(k + 1) * n + i] = xn[i]; }
+        for (int i = 0; i < n; i++) x[i] = xn[i];
     }
 }
 
@@ -365,7 +382,7 @@ cudaError_t launch_expand_lie(const DevProblem& P, cudaStream_t s, int mode) {
 }
 
 cudaError_t launch_rollout(const DevProblem& P, cudaStream_t s) {
-    const int threads = 64, blocks = (P.B + threads - 1) / threads;
+    const int threads = 32, blocks = (P.B + threads - 1) / threads;
     TO_DISPATCH_MODEL(P.model, P.m, (k_rollout<MODEL><<<blocks, threads, 0, s>>>(P)));
     return cudaGetLastError();
 }

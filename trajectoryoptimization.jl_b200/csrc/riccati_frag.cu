@@ -48,6 +48,11 @@
 #ifndef TO_FRAG_MINB
 #define TO_FRAG_MINB 7
 #endif
+// L2 prefetch distance of the record stream, in knots beyond the shared-memory ring (0 = off).  The ring hides the copy latency while the SM is
+// full (28 warps); a LONE warp -- the retry sweeps at the tail of the regularisation ladder, small batches -- waits for every record.
+#ifndef TO_FRAG_PF
+#define TO_FRAG_PF 0
+#endif
 
 namespace {
 
@@ -73,6 +78,9 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
                  "l"(src), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
+}
+__device__ __forceinline__ void bulk_prefetch_l2(const void* src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ double2 lds128(const double* p) { return *reinterpret_cast<const double2*>(p); }
 __device__ __forceinline__ void dmma(double& d0, double& d1, double a, double b) {
@@ -277,6 +285,7 @@ __global__ void __launch_bounds__(32 * WARPS, MINB) k_riccati_frag(const DevProb
             if (lane == 0) {
                 mbar_expect_tx(&bar[st], TO_REC_LEN * 8);
                 bulk_g2s(ring + st * TO_REC_LEN, recg + (size_t)k * TO_REC_LEN, TO_REC_LEN * 8, &bar[st]);
+                if (TO_FRAG_PF > 0 && k - TO_FRAG_PF >= 0) bulk_prefetch_l2(recg + (size_t)(k - TO_FRAG_PF) * TO_REC_LEN, TO_REC_LEN * 8);
             }
         };
         // (rho_j, drho_j): j applications of regularization_update!(:increase); returns the first i <= j whose rho exceeds bp_reg_max (the
@@ -291,6 +300,8 @@ __global__ void __launch_bounds__(32 * WARPS, MINB) k_riccati_frag(const DevProb
         auto sweep = [&](double rho, bool store, bool poll) -> bool {
 #pragma unroll
             for (int s = 0; s < STAGES; s++) { const int k = N - 2 - s; if (k >= 0) issue(s, k); }
+            if (TO_FRAG_PF > 1 && lane == 0)       // the knots between the ring and the first per-knot prefetch
+                for (int k = N - 2 - STAGES; k > N - 2 - STAGES - (TO_FRAG_PF - 1) && k >= 0; k--) bulk_prefetch_l2(recg + (size_t)k * TO_REC_LEN, TO_REC_LEN * 8);
             // ---- terminal knot: S^ = H^_N with s = g_N in row 0 ---------------------------------------------------------------------
             double S[2][2][2];
             {

@@ -358,10 +358,166 @@ __global__ void __launch_bounds__(TO_CEXP_THREADS, TO_CEXP_MINB * 256 / TO_CEXP_
         }
     }
 }
+// ---- k_expansion_rec16b: the same numbers, blocked by 16 knots (the default; TO_CEXP_V1=1 selects the kernel above) -----------------
+// k_expansion_rec16 spends 270 instructions per lane and knot on 3 outputs (ncu r02z_costexp: 112 M warp instructions, issue slots 59 %
+// busy, half of the stalls on two-level dependent loads cur[b] -> X, cost_index[k] -> DevCost): every 16-lane step pays for the
+// attitude projection that 3 of its lanes need (24 shuffles + ~40 FP64), for the 17th entry u_3 that lane 0 takes in a divergent second
+// call, and for the unpacking of the term table.  Here a 16-lane group owns a BLOCK of 16 consecutive knots of one instance:
+//   phase A   16 steps, lane i < 13 = state entry x_i of one knot: diagonal cost + AL terms -> (g, h); loads (x_i and the multipliers of
+//             its <= 3 terms) are issued for 4 knots at a time before the arithmetic; the cost coefficients of the lane are cached in
+//             registers while the cost index does not change; lanes 3..6 (the quaternion) leave (g, h, q) in shared memory
+//   phase B   lane j projects the attitude block of knot j (G'g, G' diag(h) G - (q'g_q) I3): once per knot instead of once per step
+//   phase C   lane j takes the four control entries of knot j (their Bound rows are the AL terms that are active at every knot: in
+//             phase A three lanes of sixteen would execute them at every step)
+// ~55 instructions per lane and knot.  Same expressions in the same order as above: the records are bit-identical.
+#ifndef TO_CEXP2_MINB
+#define TO_CEXP2_MINB 6
+#endif
+__global__ void __launch_bounds__(128, TO_CEXP2_MINB) k_expansion_rec16b(const DevProblem P, int mode) {
+    constexpr int qs = 3, n = 13, m = 4;
+    __shared__ double att_s[8][16][13];                                              // [half-warp][knot of the block][(g, h, q) of q_w..q_z], padded: lane j reads row j
+    const int i = threadIdx.x & 15;
+    double (*att)[13] = att_s[threadIdx.x >> 4];
+    const int N = P.N, NB = (N + 15) >> 4;
+    const int ngroups = (int)((gridDim.x * blockDim.x) >> 4);
+    const ExpTab& tab = *P.exptab;
+    unsigned px[TO_EXP_MAXT], py[TO_EXP_MAXT]; double nms[TO_EXP_MAXT], bnd[TO_EXP_MAXT];
+#pragma unroll
+    for (int t = 0; t < TO_EXP_MAXT; t++) { px[t] = tab.pkx[t][i]; py[t] = tab.pky[t][i]; nms[t] = tab.nms[t][i]; bnd[t] = tab.bound[t][i]; }
+    const int e = (i < qs) ? i : i - 1;                                               // error-state coordinate of entry i (controls: 12 + a = i - 1)
+    const int pme = (int)((0x6420FDB9E7CA8531ULL >> (4 * (e & 15))) & 15);            // its physical slot
+    const bool quat = (i >= qs && i <= qs + 3);
+    const unsigned gm = 0xFFFFu << (threadIdx.x & 16);
+    const int total = P.B * NB;
+    for (int unit = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 4); unit < total; unit += ngroups) {
+        const int b = unit / NB, kb = (unit - b * NB) << 4;
+        if (mode != 0 && (P.acc1[b] != 0) != (mode == 1)) continue;                   // (uniform over the group)
+        const int buf = P.cur[b];
+        const double* __restrict__ Xb = traj_X(P, buf, b);
+        const double* __restrict__ Ub = traj_U(P, buf, b);
+        const double* __restrict__ lam_b = P.lambda + (size_t)b * P.lambda_len;
+        double* __restrict__ recb = P.REC + ((size_t)b * N + kb) * TO_REC_LEN;
+        const int nk = (N - kb < 16) ? N - kb : 16;
+        const int mycid = (i < nk) ? P.cost_index[kb + i] : 0;                        // lane j <-> knot kb + j (phases B, C; broadcast in phase A)
+        int ccid = -1; double ca = 0.0, cb = 0.0;                                     // this lane's coefficients (Qd_i, q_i) / (Rd_a, r_a) of cost ccid
+        // term t acts on the knots of the block whose bit is set in act[t]; lp[t] = its multiplier at the first knot of the block
+        unsigned act[TO_EXP_MAXT]; const double* lp[TO_EXP_MAXT]; int ls[TO_EXP_MAXT];
+#pragma unroll
+        for (int t = 0; t < TO_EXP_MAXT; t++) {
+            const int first = (int)(px[t] & 0xfffu), span = (int)((px[t] >> 12) & 0xfffu);
+            int lo = first - 1 - kb, hi = first + span - kb;                          // knots kb + lo .. kb + hi - 1 (0-based) carry the row
+            lo = lo < 0 ? 0 : lo; hi = hi > nk ? nk : hi;
+            act[t] = (hi > lo && i < n) ? ((0xFFFFu >> (16 - (hi - lo))) << lo) : 0u;
+            ls[t] = (int)((px[t] >> 24) & 0x7fu);
+            lp[t] = lam_b + (int)(py[t] + (unsigned)(kb + 1) * (unsigned)ls[t]);
+        }
+        // ---- phase A: the state entries (lanes 0..12) ---------------------------------------------------------------------------------
+        const double* __restrict__ zp = Xb + (size_t)kb * n + (i < n ? i : 0);
+        for (int k0 = 0; k0 < nk; k0 += 4) {
+            double zi[4], lam[4][TO_EXP_MAXT];
+            const unsigned a0 = act[0] >> k0, a1 = act[1] >> k0, a2 = act[2] >> k0;
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int kk = k0 + u;
+                zi[u] = 0.0; lam[u][0] = 0.0; lam[u][1] = 0.0; lam[u][2] = 0.0;
+                if (kk < nk && i < n) zi[u] = __ldg(zp + kk * n);
+                if ((a0 >> u) & 1u) lam[u][0] = __ldg(lp[0] + kk * ls[0]);
+                if ((a1 >> u) & 1u) lam[u][1] = __ldg(lp[1] + kk * ls[1]);
+                if ((a2 >> u) & 1u) lam[u][2] = __ldg(lp[2] + kk * ls[2]);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                if (k0 + u >= nk) break;                                               // (uniform over the group)
+                const int cid = __shfl_sync(gm, mycid, k0 + u, 16);
+                if (i < n) {
+                    if (cid != ccid) { const DevCost& c = P.costs[cid]; ca = c.Qd[i]; cb = c.q[i]; ccid = cid; }
+                    double g = fma(ca, zi[u], cb), h = ca;
+#pragma unroll
+                    for (int t = 0; t < TO_EXP_MAXT; t++) {
+                        if ((((t == 0) ? a0 : (t == 1) ? a1 : a2) >> u) & 1u) {
+                            const double lb = fma(nms[t], zi[u] - bnd[t], lam[u][t]);   // lambda - mu c
+                            if ((px[t] >> 31) || lb <= 0.0) { g += (nms[t] < 0.0) ? -lb : lb; h += fabs(nms[t]); }   // g -= sign lb ; h += mu
+                        }
+                    }
+                    double* __restrict__ rec = recb + (size_t)(k0 + u) * TO_REC_LEN;
+                    if (quat) { double* a = &att[k0 + u][3 * (i - qs)]; a[0] = g; a[1] = h; a[2] = zi[u]; }
+                    else {
+                        rec[TO_REC_G + pme] = g; rec[TO_REC_HD + pme] = h;
+                        if (e == 7) { rec[TO_REC_HB + 12] = 0.0; rec[TO_REC_HB + 13] = 0.0; rec[TO_REC_HB + 14] = 0.0; rec[TO_REC_HB + 15] = h; }   // p = 14 is row 3 of Hb
+                    }
+                }
+            }
+        }
+        __syncwarp(gm);
+        if (i < nk) {
+            double* __restrict__ rec = recb + (size_t)i * TO_REC_LEN;
+            // ---- phase B: attitude block of knot kb + i ---------------------------------------------------------------------------
+            double gq[4], hq[4], q[4];
+#pragma unroll
+            for (int r = 0; r < 4; r++) { gq[r] = att[i][3 * r]; hq[r] = att[i][3 * r + 1]; q[r] = att[i][3 * r + 2]; }
+            // rows of G' = (L(q) H)': (-x,w,z,-y), (-y,-z,w,x), (-z,y,-x,w)
+            const double G0[4] = {-q[1], q[0], q[3], -q[2]}, G1[4] = {-q[2], -q[3], q[0], q[1]}, G2[4] = {-q[3], q[2], -q[1], q[0]};
+#pragma unroll
+            for (int cc = 0; cc < 3; cc++) {
+                double gc[4];
+#pragma unroll
+                for (int r = 0; r < 4; r++) gc[r] = (cc == 0) ? G0[r] : (cc == 1) ? G1[r] : G2[r];
+                double qb = 0.0, ge = 0.0, hb0 = 0.0, hb1 = 0.0, hb2 = 0.0;
+#pragma unroll
+                for (int r = 0; r < 4; r++) {
+                    qb += q[r] * gq[r]; ge += gc[r] * gq[r];
+                    const double tt = gc[r] * hq[r];
+                    hb0 += tt * G0[r]; hb1 += tt * G1[r]; hb2 += tt * G2[r];
+                }
+                const double hd = ((cc == 0) ? hb0 : (cc == 1) ? hb1 : hb2) - qb;
+                const int p = 8 + 2 * cc;                                             // attitude error e = 3 + c sits on p = 8, 10, 12 (frag_layout.cuh)
+                rec[TO_REC_G + p] = ge; rec[TO_REC_HD + p] = hd;
+                rec[TO_REC_HB + 4 * cc + 0] = (cc == 0) ? hd : hb0;
+                rec[TO_REC_HB + 4 * cc + 1] = (cc == 1) ? hd : hb1;
+                rec[TO_REC_HB + 4 * cc + 2] = (cc == 2) ? hd : hb2;
+                rec[TO_REC_HB + 4 * cc + 3] = 0.0;
+            }
+            // ---- phase C: the control entries of knot kb + i (coordinate 12 + a, physical slot 2a) ----------------------------------
+            const int k = kb + i;
+            const DevCost& c = P.costs[mycid];
+#pragma unroll
+            for (int a = 0; a < m; a++) {
+                double g = 0.0, h = 0.0;
+                if (k != N - 1) {
+                    const double z = __ldg(Ub + (size_t)k * m + a);
+                    g = fma(c.Rd[a], z, c.r[a]); h = c.Rd[a];
+#pragma unroll
+                    for (int t = 0; t < TO_EXP_MAXT; t++) {
+                        const unsigned rx = __ldg(&tab.pkx[t][n + a]);
+                        if ((unsigned)(k + 1) - (rx & 0xfffu) <= ((rx >> 12) & 0xfffu)) {
+                            const double rn = __ldg(&tab.nms[t][n + a]);
+                            const double lam1 = __ldg(lam_b + (int)(__ldg(&tab.pky[t][n + a]) + (unsigned)(k + 1) * ((rx >> 24) & 0x7fu)));
+                            const double lb = fma(rn, z - __ldg(&tab.bound[t][n + a]), lam1);
+                            if ((rx >> 31) || lb <= 0.0) { g += (rn < 0.0) ? -lb : lb; h += fabs(rn); }
+                        }
+                    }
+                }
+                rec[TO_REC_G + 2 * a] = g; rec[TO_REC_HD + 2 * a] = h;
+            }
+        }
+        __syncwarp(gm);                                                               // the block's rows of att are free again
+    }
+}
 cudaError_t launch_expansion_rec16(const DevProblem& P, cudaStream_t s, int mode) {
+    int dev = 0, sms = 148; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    static const int v1 = getenv("TO_CEXP_V1") ? atoi(getenv("TO_CEXP_V1")) : 0;
+    if (!v1 && P.n == 13 && P.m == 4) {
+        // blocks of 16 knots, one 16-lane group each, TO_CEXP2_UNITS blocks per group (grid-stride)
+        static const int upg = getenv("TO_CEXP2_UNITS") ? atoi(getenv("TO_CEXP2_UNITS")) : 2;
+        const long long units = (long long)P.B * ((P.N + 15) / 16);
+        long long blocks = ((units + 7) / 8 + upg - 1) / (upg < 1 ? 1 : upg);
+        if (blocks < sms) blocks = sms;
+        { static bool done[TO_MAXDEV] = {false}; prefer_common_carveout(k_expansion_rec16b, done); }
+        k_expansion_rec16b<<<(unsigned)blocks, 128, 0, s>>>(P, mode);
+        return cudaGetLastError();
+    }
     // 16-lane groups, a few knots each (grid-stride): the per-lane term table stays in registers
     const long long total = (long long)P.B * P.N * 16;
-    int dev = 0, sms = 148; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     constexpr int T = TO_CEXP_THREADS;
     long long blocks = ((total + T - 1) / T + TO_CEXP_ITERS - 1) / TO_CEXP_ITERS;
     if (blocks < sms) blocks = sms;

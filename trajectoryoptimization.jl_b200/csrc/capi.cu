@@ -6,6 +6,7 @@
 #include <cstring>
 #include <string>
 #include <vector>
+#include <cuda.h>      // types of the green-context (SM partition) API only: the entry points are resolved at run time, libcuda is not linked
 
 #include "../../include/trajopt_b200.h"
 #include "frag_layout.cuh"
@@ -31,6 +32,12 @@ struct to_handle {
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_merit = nullptr, ev_cons = nullptr;
     bool overlap = true;                // TO_NO_OVERLAP=1: keep every kernel on the main stream (profiling under ncu, A/B timing)
     bool side_pending = false;          // stream2 still holds the late line-search trials of the last iteration (ev_join follows them)
+    // TO_PARTITION=k (SM partition, CUDA green contexts): stream2 is confined to k SMs of its own for the latency-bound late trials and
+    // stream_big carries the expansion kernels that run beside them on the other SMs (to_ilqr_step); the Riccati and line-search passes
+    // keep the whole device on `stream`.
+    bool partition = false;
+    cudaStream_t stream_big = nullptr;
+    cudaEvent_t ev_late = nullptr;
     std::string err;
     std::vector<void*> allocs;
     std::vector<DevCost> h_costs;
@@ -141,6 +148,57 @@ int upload_tables(to_handle* h) {
     CU(h, cudaStreamSynchronize(h->stream));   // the host vectors may change right after
     return upload_exptab(h);
 }
+
+
+// ---- SM partition (CUDA green contexts) ----------------------------------------------------------------------------------------------------
+// The late line-search trials are a dependent FP64 chain in ~150 one-warp CTAs; beside the FP64-bound expansion kernels every instruction of that
+// chain queues behind 16 expansion warps of its SM and the pass takes 0.42 ms instead of 0.26 (profiles/r02_notes.md, section 6).  A green
+// context gives the side stream SMs of its own.  Driver entry points through cudaGetDriverEntryPoint: the library still links cudart only.
+namespace {
+struct GreenApi {
+    CUresult (*DeviceGet)(CUdevice*, int) = nullptr;
+    CUresult (*GetRes)(CUdevice, CUdevResource*, CUdevResourceType) = nullptr;
+    CUresult (*Split)(CUdevResource*, unsigned int*, const CUdevResource*, CUdevResource*, unsigned int, unsigned int) = nullptr;
+    CUresult (*Desc)(CUdevResourceDesc*, CUdevResource*, unsigned int) = nullptr;
+    CUresult (*Create)(CUgreenCtx*, CUdevResourceDesc, CUdevice, unsigned int) = nullptr;
+    CUresult (*Stream)(CUstream*, CUgreenCtx, unsigned int, int) = nullptr;
+    bool ok = false;
+};
+template <class F> bool driver_entry(const char* name, F& fn) {
+    void* p = nullptr; cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint(name, &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess || !p) { cudaGetLastError(); return false; }
+    fn = (F)p; return true;
+}
+const GreenApi& green_api() {
+    static GreenApi g = [] {
+        GreenApi a;
+        a.ok = driver_entry("cuDeviceGet", a.DeviceGet) && driver_entry("cuDeviceGetDevResource", a.GetRes) && driver_entry("cuDevSmResourceSplitByCount", a.Split) &&
+               driver_entry("cuDevResourceGenerateDesc", a.Desc) && driver_entry("cuGreenCtxCreate", a.Create) && driver_entry("cuGreenCtxStreamCreate", a.Stream);
+        return a;
+    }();
+    return g;
+}
+// the two partitions of a device, created once per process and shared by its handles (never destroyed: they live as long as the primary context)
+struct GreenPair { CUgreenCtx small = nullptr, big = nullptr; int sms_small = 0, sms_big = 0; int want = -1; };
+bool green_pair(int device, int want, GreenPair& out) {
+    static GreenPair cache[TO_MAXDEV];
+    GreenPair& c = cache[(device >= 0 && device < TO_MAXDEV) ? device : 0];
+    if (c.want == want) { out = c; return c.small != nullptr; }
+    const GreenApi& a = green_api();
+    c = GreenPair(); c.want = want;
+    if (a.ok) {
+        CUdevice dev; CUdevResource all, small, rest; unsigned int nb = 1; CUdevResourceDesc d1, d2;
+        if (a.DeviceGet(&dev, device) == CUDA_SUCCESS && a.GetRes(dev, &all, CU_DEV_RESOURCE_TYPE_SM) == CUDA_SUCCESS &&
+            a.Split(&small, &nb, &all, &rest, 0, (unsigned)want) == CUDA_SUCCESS && nb == 1 && rest.sm.smCount > 0 &&
+            a.Desc(&d1, &small, 1) == CUDA_SUCCESS && a.Desc(&d2, &rest, 1) == CUDA_SUCCESS &&
+            a.Create(&c.small, d1, dev, CU_GREEN_CTX_DEFAULT_STREAM) == CUDA_SUCCESS && a.Create(&c.big, d2, dev, CU_GREEN_CTX_DEFAULT_STREAM) == CUDA_SUCCESS) {
+            c.sms_small = (int)small.sm.smCount; c.sms_big = (int)rest.sm.smCount;
+        } else { c.small = nullptr; c.big = nullptr; }
+    }
+    out = c;
+    return c.small != nullptr;
+}
+}  // namespace
 
 // phase timing helpers
 struct PhaseScope {
@@ -456,6 +514,22 @@ int to_create(const to_spec* s, to_handle** out) {
             cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming) != cudaSuccess ||
             cudaEventCreateWithFlags(&h->ev_merit, cudaEventDisableTiming) != cudaSuccess ||
             cudaEventCreateWithFlags(&h->ev_cons, cudaEventDisableTiming) != cudaSuccess) { h->err = "side stream creation failed"; return bail(TO_ECUDA); }
+        // SM partition for the overlapped part of an iteration (A/B switch, off unless TO_PARTITION = SMs of the side stream's partition)
+        const int part = getenv("TO_PARTITION") ? atoi(getenv("TO_PARTITION")) : 0;
+        GreenPair gp;
+        if (part > 0 && h->overlap && green_pair(s->device, part, gp)) {
+            CUstream ss = nullptr, sb = nullptr;
+            if (green_api().Stream(&ss, gp.small, CU_STREAM_NON_BLOCKING, hi) == CUDA_SUCCESS && green_api().Stream(&sb, gp.big, CU_STREAM_NON_BLOCKING, lo) == CUDA_SUCCESS &&
+                cudaEventCreateWithFlags(&h->ev_late, cudaEventDisableTiming) == cudaSuccess) {
+                cudaStreamDestroy(h->stream2);
+                h->stream2 = (cudaStream_t)ss; h->stream_big = (cudaStream_t)sb; h->partition = true;
+                if (getenv("TO_VERBOSE")) fprintf(stderr, "[trajopt_b200] SM partition: side stream %d SMs, expansion stream %d SMs\n", gp.sms_small, gp.sms_big);
+            } else {
+                if (ss) cudaStreamDestroy((cudaStream_t)ss);
+                if (sb) cudaStreamDestroy((cudaStream_t)sb);
+                cudaGetLastError();
+            }
+        } else if (part > 0 && getenv("TO_VERBOSE")) fprintf(stderr, "[trajopt_b200] SM partition unavailable, plain streams\n");
     }
     DevProblem& P = h->P;
     P.model = s->model; P.n = mn; P.m = mm; P.N = s->N; P.B = s->B;
@@ -595,6 +669,8 @@ int to_destroy(to_handle* h) {
     if (h->scratch.ptr) cudaFree(h->scratch.ptr);
     for (auto& e : h->pending) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
     for (auto e : h->pool) cudaEventDestroy(e);
+    if (h->stream_big) { cudaStreamSynchronize(h->stream_big); cudaStreamDestroy(h->stream_big); }
+    if (h->ev_late) cudaEventDestroy(h->ev_late);
     if (h->stream2) { cudaStreamSynchronize(h->stream2); cudaStreamDestroy(h->stream2); }
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
     if (h->ev_join) cudaEventDestroy(h->ev_join);
@@ -1058,6 +1134,29 @@ int to_ilqr_step(to_handle* h, int32_t iters) {
                 costexp_done = true;
             }
         } else {
+            if (h->side_pending && h->partition) {
+                // SM partition: the late trials keep their own SMs (stream2); the expansion of the instances accepted in pass 1, then (once the
+                // late trials are through) the expansion of the late instances run on the other partition; the main stream waits for both.
+                cudaStream_t sb = h->stream_big;
+                CU(h, cudaStreamWaitEvent(sb, h->ev_fork, 0));                   // after pass 1 of the line search (nothing has followed it on the main stream)
+                if (rec) {
+                    { PhaseScope pe(h, TO_PHASE_COSTEXP, sb); CU(h, launch_expansion_rec16(h->P, sb, 1)); }
+                    h->launches++; h->phase_launches[TO_PHASE_COSTEXP]++;
+                    costexp_done = true;
+                }
+                { PhaseScope ps(h, TO_PHASE_EXPAND, sb); CU(h, expand(sb, 1)); }
+                h->launches++; h->phase_launches[TO_PHASE_EXPAND]++;
+                CU(h, cudaEventRecord(h->ev_late, h->stream2));                  // everything the side stream holds: the late trials (+ a merit reduction)
+                CU(h, cudaStreamWaitEvent(sb, h->ev_late, 0));
+                {
+                    PhaseScope pl(h, TO_PHASE_LATE, sb);
+                    CU(h, expand(sb, 2)); h->launches++;
+                    if (rec) { CU(h, launch_expansion_rec16(h->P, sb, 2)); h->launches++; }
+                }
+                h->phase_launches[TO_PHASE_LATE]++;
+                CU(h, cudaEventRecord(h->ev_join, sb));
+                goto joined;
+            }
             if (h->side_pending) {
                 {
                     PhaseScope pl(h, TO_PHASE_LATE, h->stream2);
@@ -1075,6 +1174,7 @@ int to_ilqr_step(to_handle* h, int32_t iters) {
             { PhaseScope ps(h, TO_PHASE_EXPAND); CU(h, expand(h->stream, h->side_pending ? 1 : 0)); }
             h->launches++; h->phase_launches[TO_PHASE_EXPAND]++;
         }
+    joined:
         JOIN(h);
         h->expanded = true;
         rc = do_backward(h, costexp_done); if (rc) return rc;

@@ -168,6 +168,42 @@ __device__ __forceinline__ void compact_entry_expansion(const DevProblem& P, con
 __device__ __forceinline__ int lie_seed(int s) { return (int)((0xFEDCBA9543ULL >> (4 * s)) & 15); }       // 3,4,5,9,10,11,12,13,14,15
 __device__ __forceinline__ int lie_trivial(int s) { return (int)((0x876210ULL >> (4 * s)) & 15); }        // 0,1,2,6,7,8
 
+// column j of [A_e B_e]_k: the RK4 step of knot k pushed through Dual<1> with the seed of error-state coordinate j (attitude: a column of G(q_k)),
+// projected on the error state of knot k + 1 with G(q_{k+1})'
+template <int MODEL>
+__device__ __forceinline__ void expand_lie_column(const DevProblem& P, int k, int j, const double* __restrict__ X, const double* __restrict__ U, double (&col)[ModelDims<MODEL>::n - 1]) {
+    constexpr int n = ModelDims<MODEL>::n, m = ModelDims<MODEL>::m, ne = n - 1, qs = 3;
+    using D = Dual<1>;
+    const double h = P.dt[k];
+    D x[n], u[m], xn[n];
+#pragma unroll
+    for (int i = 0; i < n; i++) { x[i].v = X[i]; x[i].d[0] = 0.0; }
+#pragma unroll
+    for (int i = 0; i < m; i++) { u[i].v = U[i]; u[i].d[0] = (ne + i == j) ? 1.0 : 0.0; }
+    if (j < qs + 3) {
+        const double w = X[qs], qx = X[qs + 1], qy = X[qs + 2], qz = X[qs + 3];
+        const int c = j - qs;        // column c of L(q) H: (-x,w,z,-y), (-y,-z,w,x), (-z,y,-x,w)
+        x[qs].d[0] = (c == 0) ? -qx : (c == 1) ? -qy : -qz;
+        x[qs + 1].d[0] = (c == 0) ? w : (c == 1) ? -qz : qy;
+        x[qs + 2].d[0] = (c == 0) ? qz : (c == 1) ? w : -qx;
+        x[qs + 3].d[0] = (c == 0) ? -qy : (c == 1) ? qx : w;
+    } else if (j < ne) {
+#pragma unroll
+        for (int i = qs + 4; i < n; i++) x[i].d[0] = (i == j + 1) ? 1.0 : 0.0;
+    }
+    rk4_step<MODEL, D>(model_params<MODEL>(P, k), x, u, h, xn);
+    const double* q1 = X + n + qs;                                     // attitude of knot k + 1
+    const double w1 = q1[0], x1 = q1[1], y1 = q1[2], z1 = q1[3];
+#pragma unroll
+    for (int i = 0; i < qs; i++) col[i] = xn[i].d[0];
+    const double t0 = xn[qs].d[0], t1 = xn[qs + 1].d[0], t2 = xn[qs + 2].d[0], t3 = xn[qs + 3].d[0];
+    col[qs] = -x1 * t0 + w1 * t1 + z1 * t2 - y1 * t3;
+    col[qs + 1] = -y1 * t0 - z1 * t1 + w1 * t2 + x1 * t3;
+    col[qs + 2] = -z1 * t0 + y1 * t1 - x1 * t2 + w1 * t3;
+#pragma unroll
+    for (int i = qs + 4; i < n; i++) col[i - 1] = xn[i].d[0];
+}
+
 // FRAG: the column goes into the fragment block of the knot's record (frag_layout.cuh) instead of P.ABe.
 #ifndef TO_EXPAND_LIE_MINB
 #define TO_EXPAND_LIE_MINB 4      // CTAs per SM the register allocation aims at: 128 registers, 16 warps per SM (r02g: 0.29 vs 0.37 ms at 168 registers / 12 warps)
@@ -207,35 +243,59 @@ __global__ void __launch_bounds__(TO_EXPAND_LIE_THREADS, TO_EXPAND_LIE_MINB * 12
             for (int e = 0; e < ne; e++) out[e] = col[e];
         }
     };
-    D x[n], u[m], xn[n];
-#pragma unroll
-    for (int i = 0; i < n; i++) { x[i].v = X[i]; x[i].d[0] = 0.0; }
-#pragma unroll
-    for (int i = 0; i < m; i++) { u[i].v = U[i]; u[i].d[0] = (ne + i == j) ? 1.0 : 0.0; }
-    if (j < qs + 3) {
-        const double w = X[qs], qx = X[qs + 1], qy = X[qs + 2], qz = X[qs + 3];
-        const int c = j - qs;        // column c of L(q) H: (-x,w,z,-y), (-y,-z,w,x), (-z,y,-x,w)
-        x[qs].d[0] = (c == 0) ? -qx : (c == 1) ? -qy : -qz;
-        x[qs + 1].d[0] = (c == 0) ? w : (c == 1) ? -qz : qy;
-        x[qs + 2].d[0] = (c == 0) ? qz : (c == 1) ? w : -qx;
-        x[qs + 3].d[0] = (c == 0) ? -qy : (c == 1) ? qx : w;
-    } else if (j < ne) {
-#pragma unroll
-        for (int i = qs + 4; i < n; i++) x[i].d[0] = (i == j + 1) ? 1.0 : 0.0;
-    }
-    rk4_step<MODEL, D>(model_params<MODEL>(P, k), x, u, h, xn);
-    const double* q1 = X + n + qs;                                     // attitude of knot k + 1
-    const double w1 = q1[0], x1 = q1[1], y1 = q1[2], z1 = q1[3];
     double col[ne];
-#pragma unroll
-    for (int i = 0; i < qs; i++) col[i] = xn[i].d[0];
-    const double t0 = xn[qs].d[0], t1 = xn[qs + 1].d[0], t2 = xn[qs + 2].d[0], t3 = xn[qs + 3].d[0];
-    col[qs] = -x1 * t0 + w1 * t1 + z1 * t2 - y1 * t3;
-    col[qs + 1] = -y1 * t0 - z1 * t1 + w1 * t2 + x1 * t3;
-    col[qs + 2] = -z1 * t0 + y1 * t1 - x1 * t2 + w1 * t3;
-#pragma unroll
-    for (int i = qs + 4; i < n; i++) col[i - 1] = xn[i].d[0];
+    expand_lie_column<MODEL>(P, k, j, X, U, col);
     store_column(j, col);
+}
+
+// k_expand_lie with the knot's fragment block staged in shared memory.  k_expand_lie stores a column as 12 scattered 8-byte words: every one is
+// a partial-sector write for the L2 (ncu r02z_expand: 368 MB of DRAM READS for 70 MB of inputs -- sector fills -- and 50 M sector transactions).
+// Here the 10 seed threads of a knot sit in one CTA, drop their columns (and the six closed-form ones) into a 1536-byte image of the
+// record's [A_e B_e] block, and the CTA writes the images out as whole lines.
+template <int MODEL>
+__global__ void __launch_bounds__(TO_EXPAND_LIE_THREADS, TO_EXPAND_LIE_MINB * 128 / TO_EXPAND_LIE_THREADS) k_expand_lie_staged(const DevProblem P, int mode) {
+    constexpr int n = ModelDims<MODEL>::n, m = ModelDims<MODEL>::m, ne = n - 1, NS = 10, T = TO_EXPAND_LIE_THREADS, KPC = T / NS;
+    static_assert(ne == 12 && m == 4, "record layout of the error-state Quadrotor");
+    __shared__ __align__(16) double st[KPC][TO_REC_G];
+    __shared__ int live[KPC];
+    const int tid = threadIdx.x, kk = tid / NS, sd = tid - kk * NS;
+    const long long nknots = (long long)P.B * (P.N - 1);
+    const long long bk0 = (long long)blockIdx.x * KPC;
+    bool work = kk < KPC && bk0 + kk < nknots;
+    int b = 0, k = 0;
+    if (work) {
+        k = (int)((bk0 + kk) % (P.N - 1)); b = (int)((bk0 + kk) / (P.N - 1));
+        if (mode != 0 && (P.acc1[b] != 0) != (mode == 1)) work = false;            // overlapped iterations: the other launch covers this instance
+    }
+    if (kk < KPC && sd == 0) live[kk] = work ? 1 : 0;
+    for (int idx = tid; idx < KPC * 72; idx += T) {                                // the closed-form columns (positions, velocities; k_trivial_columns)
+        const int q = idx / 72, r = idx - q * 72, s6 = r / 12, e = r - s6 * 12;
+        if (bk0 + q < nknots) {
+            const int kq = (int)((bk0 + q) % (P.N - 1));
+            const int jt = lie_trivial(s6);
+            st[q][fraglayout::ab_index(e, jt)] = (e == jt) ? 1.0 : ((jt >= 6 && e == jt - 6) ? P.dt[kq] : 0.0);
+        }
+    }
+    if (work) {
+        const int j = lie_seed(sd);
+        const double* X = traj_X(P, P.cur[b], b) + (size_t)k * n;
+        const double* U = traj_U(P, P.cur[b], b) + (size_t)k * m;
+        double col[ne];
+        expand_lie_column<MODEL>(P, k, j, X, U, col);
+        const int c = (int)((0x6420FDB9E7CA8531ULL >> (4 * j)) & 15);               // fraglayout::phys_z(j)
+        double* dst = &st[kk][8 * (c & 7) + (c >> 3)];
+#pragma unroll
+        for (int e = 0; e < ne; e++) dst[fraglayout::ab_index(e, 12)] = col[e];
+    }
+    __syncthreads();
+    for (int idx = tid; idx < KPC * (TO_REC_G / 2); idx += T) {
+        const int q = idx / (TO_REC_G / 2), w = idx - q * (TO_REC_G / 2);
+        if (live[q]) {
+            const int kq = (int)((bk0 + q) % (P.N - 1)), bq = (int)((bk0 + q) / (P.N - 1));
+            double2* rec = reinterpret_cast<double2*>(P.REC + ((size_t)bq * P.N + kq) * TO_REC_LEN);
+            rec[w] = reinterpret_cast<const double2*>(st[q])[w];
+        }
+    }
 }
 
 // the closed-form columns of [A_e B_e] (positions, velocities): thread = (instance, knot, one of the six)
@@ -371,13 +431,19 @@ __global__ void __launch_bounds__(TO_CEXP_THREADS, TO_CEXP_MINB * 256 / TO_CEXP_
 //             phase A three lanes of sixteen would execute them at every step)
 // ~55 instructions per lane and knot.  Same expressions in the same order as above: the records are bit-identical.
 #ifndef TO_CEXP2_MINB
-#define TO_CEXP2_MINB 6
+#define TO_CEXP2_MINB 9
 #endif
-__global__ void __launch_bounds__(128, TO_CEXP2_MINB) k_expansion_rec16b(const DevProblem P, int mode) {
+#ifndef TO_CEXP2_THREADS
+#define TO_CEXP2_THREADS 64
+#endif
+__global__ void __launch_bounds__(TO_CEXP2_THREADS, TO_CEXP2_MINB) k_expansion_rec16b(const DevProblem P, int mode) {
     constexpr int qs = 3, n = 13, m = 4;
-    __shared__ double att_s[8][16][13];                                              // [half-warp][knot of the block][(g, h, q) of q_w..q_z], padded: lane j reads row j
+    constexpr int ROW = 49;                                                          // 48 doubles of expansion per knot, padded: lane j works on row j (stride 98 words: conflict-free)
+    // the block's 16 x 48 outputs are staged in shared memory and leave as whole 128-byte lines: written entry by entry they are 8-byte
+    // stores scattered over the records, and every one of them costs the L2 a 32-byte sector transaction (r02v: 0.16 ms for 160 MB)
+    __shared__ __align__(16) double stage_s[TO_CEXP2_THREADS / 16][16][ROW];
     const int i = threadIdx.x & 15;
-    double (*att)[13] = att_s[threadIdx.x >> 4];
+    double (*stage)[ROW] = stage_s[threadIdx.x >> 4];
     const int N = P.N, NB = (N + 15) >> 4;
     const int ngroups = (int)((gridDim.x * blockDim.x) >> 4);
     const ExpTab& tab = *P.exptab;
@@ -389,6 +455,7 @@ __global__ void __launch_bounds__(128, TO_CEXP2_MINB) k_expansion_rec16b(const D
     const bool quat = (i >= qs && i <= qs + 3);
     const unsigned gm = 0xFFFFu << (threadIdx.x & 16);
     const int total = P.B * NB;
+    constexpr int G_ = TO_REC_G - TO_REC_G, HD_ = TO_REC_HD - TO_REC_G, HB_ = TO_REC_HB - TO_REC_G;   // offsets inside the staged 48 doubles
     for (int unit = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 4); unit < total; unit += ngroups) {
         const int b = unit / NB, kb = (unit - b * NB) << 4;
         if (mode != 0 && (P.acc1[b] != 0) != (mode == 1)) continue;                   // (uniform over the group)
@@ -396,10 +463,10 @@ __global__ void __launch_bounds__(128, TO_CEXP2_MINB) k_expansion_rec16b(const D
         const double* __restrict__ Xb = traj_X(P, buf, b);
         const double* __restrict__ Ub = traj_U(P, buf, b);
         const double* __restrict__ lam_b = P.lambda + (size_t)b * P.lambda_len;
-        double* __restrict__ recb = P.REC + ((size_t)b * N + kb) * TO_REC_LEN;
+        double* __restrict__ recb = P.REC + ((size_t)b * N + kb) * TO_REC_LEN + TO_REC_G;
         const int nk = (N - kb < 16) ? N - kb : 16;
         const int mycid = (i < nk) ? P.cost_index[kb + i] : 0;                        // lane j <-> knot kb + j (phases B, C; broadcast in phase A)
-        int ccid = -1; double ca = 0.0, cb = 0.0;                                     // this lane's coefficients (Qd_i, q_i) / (Rd_a, r_a) of cost ccid
+        int ccid = -1; double ca = 0.0, cb = 0.0;                                     // this lane's coefficients (Qd_i, q_i) of cost ccid
         // term t acts on the knots of the block whose bit is set in act[t]; lp[t] = its multiplier at the first knot of the block
         unsigned act[TO_EXP_MAXT]; const double* lp[TO_EXP_MAXT]; int ls[TO_EXP_MAXT];
 #pragma unroll
@@ -439,22 +506,22 @@ __global__ void __launch_bounds__(128, TO_CEXP2_MINB) k_expansion_rec16b(const D
                             if ((px[t] >> 31) || lb <= 0.0) { g += (nms[t] < 0.0) ? -lb : lb; h += fabs(nms[t]); }   // g -= sign lb ; h += mu
                         }
                     }
-                    double* __restrict__ rec = recb + (size_t)(k0 + u) * TO_REC_LEN;
-                    if (quat) { double* a = &att[k0 + u][3 * (i - qs)]; a[0] = g; a[1] = h; a[2] = zi[u]; }
+                    double* row = stage[k0 + u];
+                    if (quat) { double* a = row + HB_ + 3 * (i - qs); a[0] = g; a[1] = h; a[2] = zi[u]; }   // (g, h, q) of q_w..q_z wait in Hb[0..11] for phase B
                     else {
-                        rec[TO_REC_G + pme] = g; rec[TO_REC_HD + pme] = h;
-                        if (e == 7) { rec[TO_REC_HB + 12] = 0.0; rec[TO_REC_HB + 13] = 0.0; rec[TO_REC_HB + 14] = 0.0; rec[TO_REC_HB + 15] = h; }   // p = 14 is row 3 of Hb
+                        row[G_ + pme] = g; row[HD_ + pme] = h;
+                        if (e == 7) { row[HB_ + 12] = 0.0; row[HB_ + 13] = 0.0; row[HB_ + 14] = 0.0; row[HB_ + 15] = h; }   // p = 14 is row 3 of Hb
                     }
                 }
             }
         }
         __syncwarp(gm);
         if (i < nk) {
-            double* __restrict__ rec = recb + (size_t)i * TO_REC_LEN;
+            double* row = stage[i];
             // ---- phase B: attitude block of knot kb + i ---------------------------------------------------------------------------
             double gq[4], hq[4], q[4];
 #pragma unroll
-            for (int r = 0; r < 4; r++) { gq[r] = att[i][3 * r]; hq[r] = att[i][3 * r + 1]; q[r] = att[i][3 * r + 2]; }
+            for (int r = 0; r < 4; r++) { gq[r] = row[HB_ + 3 * r]; hq[r] = row[HB_ + 3 * r + 1]; q[r] = row[HB_ + 3 * r + 2]; }
             // rows of G' = (L(q) H)': (-x,w,z,-y), (-y,-z,w,x), (-z,y,-x,w)
             const double G0[4] = {-q[1], q[0], q[3], -q[2]}, G1[4] = {-q[2], -q[3], q[0], q[1]}, G2[4] = {-q[3], q[2], -q[1], q[0]};
 #pragma unroll
@@ -471,36 +538,53 @@ __global__ void __launch_bounds__(128, TO_CEXP2_MINB) k_expansion_rec16b(const D
                 }
                 const double hd = ((cc == 0) ? hb0 : (cc == 1) ? hb1 : hb2) - qb;
                 const int p = 8 + 2 * cc;                                             // attitude error e = 3 + c sits on p = 8, 10, 12 (frag_layout.cuh)
-                rec[TO_REC_G + p] = ge; rec[TO_REC_HD + p] = hd;
-                rec[TO_REC_HB + 4 * cc + 0] = (cc == 0) ? hd : hb0;
-                rec[TO_REC_HB + 4 * cc + 1] = (cc == 1) ? hd : hb1;
-                rec[TO_REC_HB + 4 * cc + 2] = (cc == 2) ? hd : hb2;
-                rec[TO_REC_HB + 4 * cc + 3] = 0.0;
+                row[G_ + p] = ge; row[HD_ + p] = hd;
+                row[HB_ + 4 * cc + 0] = (cc == 0) ? hd : hb0;
+                row[HB_ + 4 * cc + 1] = (cc == 1) ? hd : hb1;
+                row[HB_ + 4 * cc + 2] = (cc == 2) ? hd : hb2;
+                row[HB_ + 4 * cc + 3] = 0.0;
             }
             // ---- phase C: the control entries of knot kb + i (coordinate 12 + a, physical slot 2a) ----------------------------------
             const int k = kb + i;
             const DevCost& c = P.costs[mycid];
+            double zu[m], lu[m][TO_EXP_MAXT];
+#pragma unroll
+            for (int a = 0; a < m; a++) {                                             // every load of the phase first
+                zu[a] = (k != N - 1) ? __ldg(Ub + (size_t)k * m + a) : 0.0;
+#pragma unroll
+                for (int t = 0; t < TO_EXP_MAXT; t++) {
+                    const unsigned rx = __ldg(&tab.pkx[t][n + a]);
+                    lu[a][t] = (k != N - 1 && (unsigned)(k + 1) - (rx & 0xfffu) <= ((rx >> 12) & 0xfffu))
+                                   ? __ldg(lam_b + (int)(__ldg(&tab.pky[t][n + a]) + (unsigned)(k + 1) * ((rx >> 24) & 0x7fu))) : 0.0;
+                }
+            }
 #pragma unroll
             for (int a = 0; a < m; a++) {
                 double g = 0.0, h = 0.0;
                 if (k != N - 1) {
-                    const double z = __ldg(Ub + (size_t)k * m + a);
-                    g = fma(c.Rd[a], z, c.r[a]); h = c.Rd[a];
+                    g = fma(c.Rd[a], zu[a], c.r[a]); h = c.Rd[a];
 #pragma unroll
                     for (int t = 0; t < TO_EXP_MAXT; t++) {
                         const unsigned rx = __ldg(&tab.pkx[t][n + a]);
                         if ((unsigned)(k + 1) - (rx & 0xfffu) <= ((rx >> 12) & 0xfffu)) {
                             const double rn = __ldg(&tab.nms[t][n + a]);
-                            const double lam1 = __ldg(lam_b + (int)(__ldg(&tab.pky[t][n + a]) + (unsigned)(k + 1) * ((rx >> 24) & 0x7fu)));
-                            const double lb = fma(rn, z - __ldg(&tab.bound[t][n + a]), lam1);
+                            const double lb = fma(rn, zu[a] - __ldg(&tab.bound[t][n + a]), lu[a][t]);
                             if ((rx >> 31) || lb <= 0.0) { g += (rn < 0.0) ? -lb : lb; h += fabs(rn); }
                         }
                     }
                 }
-                rec[TO_REC_G + 2 * a] = g; rec[TO_REC_HD + 2 * a] = h;
+                row[G_ + 2 * a] = g; row[HD_ + 2 * a] = h;
             }
         }
-        __syncwarp(gm);                                                               // the block's rows of att are free again
+        __syncwarp(gm);
+        // ---- write-out: 384 contiguous bytes per knot, 16 bytes per lane and store -------------------------------------------------------
+        for (int kk = 0; kk < nk; kk++) {
+            const double* row = stage[kk];
+            double* dst = recb + (size_t)kk * TO_REC_LEN;
+            *reinterpret_cast<double2*>(dst + 2 * i) = make_double2(row[2 * i], row[2 * i + 1]);
+            if (i < 8) *reinterpret_cast<double2*>(dst + 32 + 2 * i) = make_double2(row[32 + 2 * i], row[33 + 2 * i]);
+        }
+        __syncwarp(gm);                                                               // the stage is free again
     }
 }
 cudaError_t launch_expansion_rec16(const DevProblem& P, cudaStream_t s, int mode) {
@@ -508,12 +592,13 @@ cudaError_t launch_expansion_rec16(const DevProblem& P, cudaStream_t s, int mode
     static const int v1 = getenv("TO_CEXP_V1") ? atoi(getenv("TO_CEXP_V1")) : 0;
     if (!v1 && P.n == 13 && P.m == 4) {
         // blocks of 16 knots, one 16-lane group each, TO_CEXP2_UNITS blocks per group (grid-stride)
-        static const int upg = getenv("TO_CEXP2_UNITS") ? atoi(getenv("TO_CEXP2_UNITS")) : 2;
+        static const int upg = getenv("TO_CEXP2_UNITS") ? atoi(getenv("TO_CEXP2_UNITS")) : 1;   // r02u: 1.369 / 1.384 / 1.411 ms per step at 1 / 2 / 4
         const long long units = (long long)P.B * ((P.N + 15) / 16);
-        long long blocks = ((units + 7) / 8 + upg - 1) / (upg < 1 ? 1 : upg);
+        constexpr int GPB = TO_CEXP2_THREADS / 16;                                   // 16-lane groups per CTA
+        long long blocks = ((units + GPB - 1) / GPB + upg - 1) / (upg < 1 ? 1 : upg);
         if (blocks < sms) blocks = sms;
         { static bool done[TO_MAXDEV] = {false}; prefer_common_carveout(k_expansion_rec16b, done); }
-        k_expansion_rec16b<<<(unsigned)blocks, 128, 0, s>>>(P, mode);
+        k_expansion_rec16b<<<(unsigned)blocks, TO_CEXP2_THREADS, 0, s>>>(P, mode);
         return cudaGetLastError();
     }
     // 16-lane groups, a few knots each (grid-stride): the per-lane term table stays in registers
@@ -532,7 +617,13 @@ cudaError_t launch_expand_lie(const DevProblem& P, cudaStream_t s, int mode) {
     static_assert(fraglayout::phys_z(0) == 1 && fraglayout::phys_z(5) == 12 && fraglayout::phys_z(11) == 15 && fraglayout::phys_z(12) == 0 && fraglayout::phys_z(15) == 6, "nibble table of k_expand_lie");
     { static bool d1[TO_MAXDEV] = {false}, d2[TO_MAXDEV] = {false}; prefer_common_carveout(k_expand_lie<MODEL_QUADROTOR, true>, d1); prefer_common_carveout(k_expand_lie<MODEL_QUADROTOR, false>, d2); }
     constexpr int T = TO_EXPAND_LIE_THREADS;
-    if (P.frag) k_expand_lie<MODEL_QUADROTOR, true><<<(unsigned)((total + T - 1) / T), T, 0, s>>>(P, mode);
+    static const int staged = getenv("TO_EXPAND_STAGE") ? atoi(getenv("TO_EXPAND_STAGE")) : 0;
+    if (P.frag && staged) {
+        constexpr int KPC = T / 10;
+        const long long nknots = (long long)P.B * (P.N - 1);
+        { static bool d3[TO_MAXDEV] = {false}; prefer_common_carveout(k_expand_lie_staged<MODEL_QUADROTOR>, d3); }
+        k_expand_lie_staged<MODEL_QUADROTOR><<<(unsigned)((nknots + KPC - 1) / KPC), T, 0, s>>>(P, mode);
+    } else if (P.frag) k_expand_lie<MODEL_QUADROTOR, true><<<(unsigned)((total + T - 1) / T), T, 0, s>>>(P, mode);
     else k_expand_lie<MODEL_QUADROTOR, false><<<(unsigned)((total + T - 1) / T), T, 0, s>>>(P, mode);
     return cudaGetLastError();
 }

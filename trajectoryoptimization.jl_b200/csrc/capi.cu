@@ -611,9 +611,15 @@ int to_create(const to_spec* s, to_handle** out) {
     ALLOC(P.lambda, (size_t)B * std::max(1, P.lambda_len));
     ALLOC(P.rho, B); ALLOC(P.drho, B); ALLOC(P.dV, 2 * (size_t)B); ALLOC(P.J, B); ALLOC(P.Jc, B); ALLOC(P.alpha, B);
     ALLOC(P.bp_status, B); ALLOC(P.ls_iters, B); ALLOC(P.accepted, B); ALLOC(P.acc1, B);
-    // (the later line-search passes can walk a compact list of the late instances instead of scanning all: faster alone -- 0.22 vs 0.26 ms --
-    //  but slower next to the expansion kernels, where dense warps queue for the FP64 pipe: 0.53 vs 0.39 ms, r02r / r02s.  Off by default.)
-    if (getenv("TO_LATE_LIST")) { ALLOC(P.late_list, B); ALLOC(P.late_count, 1); }
+    // The later line-search passes can walk a compact list of the late instances (the ones pass 1 did not accept) instead of scanning all, in half-warp
+    // CTAs of two instances (forward.cu launch_pass): only CTAs with work stay resident next to the expansion kernels of the main stream.  On the record
+    // path (error-state Quadrotor: cost + dynamics expansion on the main stream) that balances the two overlapped chains -- 1.295 vs 1.336 ms per step,
+    // quadrotor_lie 1.324 vs 1.379 -- and it is the default there; on the other paths the late pass itself is the longer chain and the list makes it
+    // longer (full state 1.370 vs 1.313, Acrobot 3.90 vs 3.48: r02zz), so they keep scanning with full warps.  TO_LATE_LIST = 0 / 1 overrides.
+    {
+        const char* ev = getenv("TO_LATE_LIST");
+        if (ev ? atoi(ev) != 0 : P.frag != 0) { ALLOC(P.late_list, B); ALLOC(P.late_count, 1); }
+    }
     ALLOC(h->d_stageX, P.strideX); ALLOC(h->d_stageU, P.strideU); ALLOC(h->d_viol, B); ALLOC(h->d_merit2, 2);
     ALLOC(h->d_work, 1); ALLOC(h->d_err, 1);
     if (P.frag) { ALLOC(h->d_fragq, frag_queue_ints(B)); ALLOC(h->d_fragpool, frag_pool_doubles(B, N)); ALLOC(h->d_fragerr, 1); ALLOC(h->d_exptab, 1); }

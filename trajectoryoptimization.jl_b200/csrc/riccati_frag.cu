@@ -29,6 +29,7 @@
 //   * the record of knot k (1920 B: fragments of [A_e B_e] + compact expansion) arrives by ONE 1-D bulk TMA copy (cp.async.bulk +
 //     mbarrier, SASS UBLKCP) into a per-warp ring, issued one knot ahead.
 //   * 72 registers, 4-warp CTAs x 7 per SM = 28 resident warps per SM: B = 4096 instances are a single wave on 148 SMs.
+#include <cstdlib>
 #include "costcon.cuh"
 #include "frag_layout.cuh"
 #include "kernels.h"
@@ -45,8 +46,12 @@
 #ifndef TO_FRAG_ROUNDS
 #define TO_FRAG_ROUNDS 2
 #endif
+// CTAs per SM the register allocation aims at.  7 (72 registers, 28 warps per SM): the 4096 first sweeps of the BASELINE batch are ONE wave -- the fastest
+// build when no instance restarts (quadrotor_calm 0.333 ms = 0.40 of the HBM roofline).  6 (80 registers, 24 warps, 1.15 waves, fewer spills): a sweep
+// is faster, which pays on the BASELINE inputs where the tail is "late failure + one more lone sweep": 0.466 vs 0.484 ms (r02y, r02zz), calm 0.36.
+// Both are compiled; TO_FRAG_MINB (environment, 6 or 7) picks one at run time, the macro is the default.
 #ifndef TO_FRAG_MINB
-#define TO_FRAG_MINB 7
+#define TO_FRAG_MINB 6
 #endif
 // L2 prefetch distance of the record stream, in knots beyond the shared-memory ring (0 = off).  The ring hides the copy latency while the SM is
 // full (28 warps); a LONE warp -- the retry sweeps at the tail of the regularisation ladder, small batches -- waits for every record.
@@ -601,8 +606,9 @@ int frag_pool_slots(int B, int N) {
 }
 size_t frag_pool_doubles(int B, int N) { return (size_t)frag_pool_slots(B, N) * ((size_t)(N - 1) * 52 + 2); }
 
-cudaError_t launch_backward_frag(const DevProblem& P, int* queue, double* pool, int* sticky_err, cudaStream_t s) {
-    constexpr int STAGES = TO_FRAG_STAGES, WARPS = TO_FRAG_WARPS, MINB = TO_FRAG_MINB;
+template <int MINB>
+static cudaError_t launch_backward_frag_t(const DevProblem& P, int* queue, double* pool, int* sticky_err, cudaStream_t s) {
+    constexpr int STAGES = TO_FRAG_STAGES, WARPS = TO_FRAG_WARPS;
     using SM = FragSmem<STAGES, WARPS>;
     auto kern = k_riccati_frag<STAGES, WARPS, MINB>;
     const int smem = (int)sizeof(SM);
@@ -631,4 +637,8 @@ cudaError_t launch_backward_frag(const DevProblem& P, int* queue, double* pool, 
     { static bool done[TO_MAXDEV] = {false}; prefer_common_carveout(kern, done); }
     kern<<<grid, 32 * WARPS, smem, s>>>(P, queue, pool, pool ? frag_pool_slots(P.B, P.N) : 0, sticky_err);
     return cudaGetLastError();
+}
+cudaError_t launch_backward_frag(const DevProblem& P, int* queue, double* pool, int* sticky_err, cudaStream_t s) {
+    static const int minb = getenv("TO_FRAG_MINB") ? atoi(getenv("TO_FRAG_MINB")) : TO_FRAG_MINB;
+    return minb >= 7 ? launch_backward_frag_t<7>(P, queue, pool, sticky_err, s) : launch_backward_frag_t<6>(P, queue, pool, sticky_err, s);
 }

@@ -28,7 +28,8 @@
 //     positive-definiteness = positive leading minors a, det P, s00, det S (the pivots of LDL' are their ratios).
 //   * the record of knot k (1920 B: fragments of [A_e B_e] + compact expansion) arrives by ONE 1-D bulk TMA copy (cp.async.bulk +
 //     mbarrier, SASS UBLKCP) into a per-warp ring, issued one knot ahead.
-//   * 72 registers, 4-warp CTAs x 7 per SM = 28 resident warps per SM: B = 4096 instances are a single wave on 148 SMs.
+//   * 4-warp CTAs; two builds (TO_FRAG_MINB below): 72 registers x 7 CTAs per SM = 28 resident warps, B = 4096 instances are a single wave on 148 SMs;
+//     80 registers x 6 CTAs = 24 warps, 1.15 waves of faster sweeps (the default: it wins when instances restart).
 #include <cstdlib>
 #include "costcon.cuh"
 #include "frag_layout.cuh"

@@ -202,3 +202,17 @@ def test_abi_struct_layout_matches_the_binding_tables():
         assert ctypes.sizeof(cls) == c_layout[(name, "sizeof")], name
         for f in structs[name]:
             assert getattr(cls, f).offset == c_layout[(name, f)], (name, f)
+
+
+def test_every_environment_switch_of_the_library_is_documented():
+    """INTEGRATION.md lists every TO_* variable the CUDA sources read with getenv (a switch a maintainer cannot find is a trap)."""
+    import glob
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    names = set()
+    for f in glob.glob(os.path.join(root, "trajectoryoptimization.jl_b200", "csrc", "*.cu*")):
+        names |= set(re.findall(r'getenv\("(TO_[A-Z0-9_]+)"\)', open(f).read()))
+    assert len(names) >= 10
+    doc = open(os.path.join(root, "INTEGRATION.md")).read()
+    missing = sorted(n for n in names if n not in doc)
+    assert not missing, f"undocumented environment switches: {missing}"
